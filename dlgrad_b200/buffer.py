@@ -1,0 +1,428 @@
+"""Buffer: a pointer plus shape metadata, and the shape logic of every op.
+
+Mirrors the public surface of dlgrad/buffer.py (same method names, argument meaning and errors) so
+that ops written in "Buffer algebra" read the same, but the device routing is rebuilt for a
+discrete GPU.  The reference hard-codes `device=Device.CPU` at 20 of its 31 dispatch sites and
+relies on unified memory; here every op goes through `_route`, which sends it to
+Device.CUDA — migrating host operands once, in place — unless *all* operands are host buffers AND a
+CPU runtime has been registered (only the test-suite's oracle does that).
+
+Differences from the reference that are deliberate:
+  * host scalars (`Buffer.from_scalar`) stay Python floats and are passed to kernels by value;
+  * views keep their base allocation alive (`tensor.py:816-821` in the reference does not);
+  * `unsqueeze`/`squeeze` still edit metadata in place, as the autograd code relies on it, but the
+    binary-op path no longer leaves operands permanently unsqueezed.
+"""
+from __future__ import annotations
+
+from dlgrad_b200.device import Device, as_device
+from dlgrad_b200.dispatch import dispatcher
+from dlgrad_b200.dtype import CDataPtr, DType, Scalar
+from dlgrad_b200.helpers import (
+    BinaryOps,
+    BufferOps,
+    CustomOps,
+    UnaryOps,
+    broadcast_shapes,
+    cal_sum_max_out_shape,
+    calculate_stride,
+    check_broadcast,
+    ffi,
+    get_broadcast_shape,
+    prod_,
+)
+
+_F32 = DType.FLOAT32
+_CPU, _CUDA = Device.CPU, Device.CUDA
+_dispatch = dispatcher.dispatch
+
+
+class BufferMetadata:
+    """shape / numel / stride / ndim / dtype / device / nbytes (dlgrad/buffer.py:24-32).  Strides
+    are derived on demand: every Buffer is dense row-major."""
+    __slots__ = ("shape", "numel", "ndim", "dtype", "device", "nbytes")
+
+    def __init__(self, shape: tuple, dtype: DType, device: Device) -> None:
+        self.shape = shape
+        self.numel = prod_(shape)
+        self.ndim = len(shape)
+        self.dtype = dtype
+        self.device = device
+        self.nbytes = self.numel * 4
+
+    @property
+    def stride(self) -> tuple:
+        return calculate_stride(self.shape)
+
+    def set_shape(self, shape: tuple) -> None:
+        self.shape = tuple(shape)
+        self.numel = prod_(shape)
+        self.ndim = len(shape)
+        self.nbytes = self.numel * 4
+
+
+def _host_compute_enabled() -> bool:
+    return dispatcher.has(BinaryOps.ADD, _CPU)
+
+
+class Buffer:
+    __slots__ = ("ptr", "metadata", "scalar", "aligned", "_keep")
+
+    def __init__(self, data: CDataPtr, shape: tuple, device: str | Device | None = _CPU,
+                 dtype: str | DType | None = _F32, **kwargs) -> None:
+        self.ptr = data
+        self.metadata = BufferMetadata(tuple(shape), dtype if isinstance(dtype, DType) else _F32,
+                                       device if isinstance(device, Device) else as_device(device))
+        self.scalar = kwargs.get("scalar")       # python float for host 0-d scalars
+        self.aligned = kwargs.get("aligned", True)   # 16-byte aligned base (false for odd-offset slices)
+        self._keep = kwargs.get("keep")          # object that owns the memory `ptr` points into
+
+    # ------------------------------------------------------------------ construction
+    @staticmethod
+    def from_scalar(val: Scalar) -> "Buffer":
+        cell = ffi.new("float[]", 1)
+        cell[0] = val
+        return Buffer(cell, (), _CPU, _F32, scalar=float(val))
+
+    @staticmethod
+    def from_numpy(arr, device: Device = _CPU) -> "Buffer":
+        ptr = ffi.from_buffer("float *", arr, require_writable=False)
+        return Buffer(ptr, tuple(arr.shape), _CPU, _F32, keep=arr)
+
+    @staticmethod
+    def _creation_device(device) -> tuple[Device, Device]:
+        """(label, where to run).  Creation ops run on CUDA unless the caller asked for a host
+        tensor and a host runtime exists."""
+        device = as_device(device)
+        run = _CPU if (device is _CPU and _host_compute_enabled()) else _CUDA
+        return (_CUDA if run is _CUDA else device), run
+
+    @staticmethod
+    def uniform(shape: tuple, device: Device, dtype: DType | str, **kwargs) -> "Buffer":
+        if isinstance(dtype, str):
+            dtype = DType.from_str(dtype)
+        if dtype is not _F32:
+            raise NotImplementedError("dlgrad only supports float32")
+        if not isinstance(shape, tuple):
+            raise ValueError("Shape must be a tuple")
+        label, run = Buffer._creation_device(device)
+        return Buffer(_dispatch(op=BufferOps.UNIFORM, device=run, shape=shape, **kwargs), shape, label, dtype)
+
+    @staticmethod
+    def full(shape: tuple, fill_value: Scalar, device: Device, dtype: DType = _F32) -> "Buffer":
+        label, run = Buffer._creation_device(device)
+        return Buffer(_dispatch(op=BufferOps.FULL, device=run, shape=shape, fill_value=fill_value),
+                      shape, label, dtype)
+
+    @staticmethod
+    def arange(shape: tuple, device: Device, dtype: DType = _F32) -> "Buffer":
+        label, run = Buffer._creation_device(device)
+        return Buffer(_dispatch(op=BufferOps.ARANGE, device=run, shape=shape), shape, label, dtype)
+
+    # ------------------------------------------------------------------ device routing
+    def _to_cuda(self) -> None:
+        """One-time, in-place migration of a host buffer (parameters created without device=,
+        numpy inputs, masks): the Buffer object keeps its identity, its storage moves to HBM."""
+        if self.metadata.device is _CUDA or self.scalar is not None:
+            return
+        from dlgrad_b200.runtime.cuda import transfer
+        self.ptr = transfer.upload(self.ptr, self.metadata.nbytes)
+        self._keep = None
+        self.aligned = True
+        self.metadata.device = _CUDA
+
+    @staticmethod
+    def _route(*bufs: "Buffer") -> Device:
+        on_cuda = False
+        for b in bufs:
+            if b.metadata.device is _CUDA:
+                on_cuda = True
+                break
+        if not on_cuda and _host_compute_enabled():
+            return _CPU
+        for b in bufs:
+            if b.metadata.device is not _CUDA and b.scalar is None:
+                b._to_cuda()
+        return _CUDA
+
+    def _like(self, ptr: CDataPtr, shape: tuple, dev: Device) -> "Buffer":
+        return Buffer(ptr, shape, dev, self.metadata.dtype)
+
+    # ------------------------------------------------------------------ host access
+    def numpy(self) -> "np.ndarray":  # type: ignore  # noqa: F821
+        import numpy as np
+        md = self.metadata
+        if self.scalar is not None:
+            return np.array(self.scalar, dtype=np.float32).reshape(md.shape)
+        if md.device is _CUDA:
+            from dlgrad_b200.runtime.cuda import transfer
+            return transfer.download(self.ptr, md.numel).reshape(md.shape)
+        flat = np.frombuffer(ffi.buffer(self.ptr, md.numel * 4), dtype=np.float32)
+        return flat.reshape(md.shape)
+
+    def show(self) -> None:
+        # the reference prints from C (PRINT op, dlgrad/runtime/cpu.py:1003-1025); D2H then print
+        print(self.numpy())
+
+    # ------------------------------------------------------------------ views
+    def reshape(self, new_shape: tuple) -> "Buffer":
+        new_shape = tuple(new_shape)
+        if -1 in new_shape:
+            known = -prod_(new_shape)
+            new_shape = tuple(self.numel // known if d == -1 else d for d in new_shape)
+        if prod_(new_shape) != self.metadata.numel:
+            raise ValueError(f"Cannot reshape {self.shape} ({self.metadata.numel} elements) to "
+                             f"{new_shape} ({prod_(new_shape)} elements)")
+        return Buffer(self.ptr, new_shape, self.metadata.device, self.metadata.dtype,
+                      scalar=self.scalar, aligned=self.aligned, keep=self._keep)
+
+    def unsqueeze(self, dim: list[int] | int) -> None:
+        if dim == -1:
+            dim = 0
+        dims = [dim] if isinstance(dim, int) else list(dim)
+        if len(set(dims)) != len(dims):
+            raise AssertionError(f"duplicate dims not allowed in unsqueeze: {dims}")
+        shp = list(self.shape)
+        for d in dims:
+            assert d <= len(shp), f"Cannot unsqueeze {dims} from {self.shape}"
+        for d in sorted(dims, reverse=True):
+            shp.insert(d, 1)
+        self.metadata.set_shape(tuple(shp))
+
+    def squeeze(self, dim: list[int] | int) -> None:
+        for d in ([dim] if isinstance(dim, int) else list(dim)):
+            if self.shape[d] == 1:
+                shp = list(self.shape)
+                shp.pop(d)
+                self.metadata.set_shape(tuple(shp))
+
+    # ------------------------------------------------------------------ reductions
+    def _reduce(self, op: UnaryOps, dim: int, keepdim: bool) -> "Buffer":
+        out_shape = cal_sum_max_out_shape(ndim=self.ndim, dim=dim, inp_shape=self.shape, keepdim=keepdim)
+        dev = Buffer._route(self)
+        return self._like(_dispatch(op=op, device=dev, x=self, dim=dim), out_shape, dev)
+
+    def sum(self, dim: int = -1, keepdim: bool = False) -> "Buffer":
+        return self._reduce(UnaryOps.SUM, dim, keepdim)
+
+    def mean(self, dim: int = -1, keepdim: bool = False) -> "Buffer":
+        return self._reduce(UnaryOps.MEAN, dim, keepdim)
+
+    def max(self, dim: int = -1, out: "Buffer" = None, keepdim: bool = False) -> "Buffer":
+        return self._reduce(UnaryOps.MAX, dim, keepdim)
+
+    def argmax(self, dim: int) -> "Buffer":
+        assert self.ndim == 2, "currently dlgrad supports argmax for 2d only"
+        shape = (1, self.shape[1]) if dim == 0 else (self.shape[0], 1) if dim == 1 else (1, 1)
+        dev = Buffer._route(self)
+        return self._like(_dispatch(op=UnaryOps.ARGMAX, device=dev, x=self, dim=dim), shape, dev)
+
+    # ------------------------------------------------------------------ matmul / layout
+    def matmul(self, other: "Buffer") -> "Buffer":
+        p1, p2, out_shape = broadcast_shapes(self.shape, other.shape)
+        dev = Buffer._route(self, other)
+        x = self if self.shape == p1 else self.reshape(p1)
+        y = other if other.shape == p2 else other.reshape(p2)
+        return self._like(_dispatch(op=BinaryOps.MATMUL, device=dev, x=x, y=y), out_shape, dev)
+
+    def permute(self, order: tuple) -> "Buffer":
+        out_shape = tuple(self.shape[i] for i in order)
+        dev = Buffer._route(self)
+        return self._like(_dispatch(op=UnaryOps.PERMUTE, device=dev, x=self, order=tuple(order)), out_shape, dev)
+
+    def transpose(self, dim0: int, dim1: int) -> "Buffer":
+        order = list(range(self.ndim))
+        order[dim0], order[dim1] = order[dim1], order[dim0]
+        return self.permute(tuple(order))
+
+    # ------------------------------------------------------------------ unary math
+    def _unary(self, op: UnaryOps, **kw) -> "Buffer":
+        if self.scalar is not None:
+            self = self._materialized()
+        dev = Buffer._route(self)
+        return self._like(_dispatch(op=op, device=dev, x=self, **kw), self.shape, dev)
+
+    def _materialized(self) -> "Buffer":
+        """A host scalar as a real one-element buffer on the compute device."""
+        import numpy as np
+        b = Buffer.from_numpy(np.full((1,), self.scalar, dtype=np.float32))
+        b.metadata.set_shape(())
+        return b
+
+    def exp(self) -> "Buffer":
+        return self._unary(UnaryOps.EXP)
+
+    def log(self) -> "Buffer":
+        return self._unary(UnaryOps.LOG)
+
+    def sqrt(self) -> "Buffer":
+        return self._unary(UnaryOps.SQRT)
+
+    def rsqrt(self) -> "Buffer":
+        return self._unary(UnaryOps.RSQRT)
+
+    def clamp(self, min: int | None = None, max: int | None = None) -> "Buffer":
+        return self._unary(UnaryOps.CLAMP, min_val=min, max_val=max)
+
+    def __neg__(self) -> "Buffer":
+        return self._unary(UnaryOps.NEG)
+
+    def __pow__(self, val: Scalar) -> "Buffer":
+        return self._unary(UnaryOps.POW, val=val)
+
+    # compositions, written as the reference composes them (dlgrad/buffer.py:338-362)
+    def relu(self) -> "Buffer":
+        return self.where(inp=self, other=0.0)
+
+    def leaky_relu(self, neg_slope: Scalar = 0.01) -> "Buffer":
+        return self.where(inp=self, other=self * neg_slope)
+
+    def sigmoid(self) -> "Buffer":
+        e = self.exp()
+        return e / (e + 1.0)
+
+    def tanh(self) -> "Buffer":
+        ep, en = self.exp(), (-self).exp()
+        return (ep - en) / (ep + en)
+
+    # fused row ops (CUDA backend); a host runtime may register the 5-op composition
+    def softmax(self, dim: int) -> "Buffer":
+        dev = Buffer._route(self)
+        return self._like(_dispatch(op=UnaryOps.SOFTMAX, device=dev, x=self, dim=dim), self.shape, dev)
+
+    def log_softmax(self, dim: int) -> "Buffer":
+        dev = Buffer._route(self)
+        return self._like(_dispatch(op=UnaryOps.LOG_SOFTMAX, device=dev, x=self, dim=dim), self.shape, dev)
+
+    # ------------------------------------------------------------------ select / compare
+    @staticmethod
+    def _as_buffer(v: "Buffer | Scalar") -> "Buffer":
+        return v if isinstance(v, Buffer) else Buffer.from_scalar(v)
+
+    def where(self, inp: "Buffer | Scalar", other: "Buffer | Scalar") -> "Buffer":
+        inp, other = Buffer._as_buffer(inp), Buffer._as_buffer(other)
+        dev = Buffer._route(self, inp, other)
+        return self._like(_dispatch(op=UnaryOps.WHERE, device=dev, cond=self, x=inp, y=other), self.shape, dev)
+
+    @staticmethod
+    def masked_fill(x: "Buffer", mask: "Buffer", val: Scalar) -> "Buffer":
+        out_shape = get_broadcast_shape(x.shape, mask.shape)
+        dev = Buffer._route(x, mask)
+        return x._like(_dispatch(op=UnaryOps.MASKED_FILL, device=dev, x=x, mask=mask, val=val,
+                                 out_shape=out_shape), out_shape, dev)
+
+    def __le__(self, other: "Buffer") -> "Buffer":
+        out_shape = get_broadcast_shape(self.shape, other.shape)
+        dev = Buffer._route(self, other)
+        return self._like(_dispatch(op=BinaryOps.CMP, device=dev, x=self, y=other, out_shape=out_shape,
+                                    mode="<="), out_shape, dev)
+
+    def _compare(self, other: "Buffer | Scalar", op: BinaryOps) -> "Buffer":
+        other = Buffer._as_buffer(other)
+        dev = Buffer._route(self, other)
+        return self._like(_dispatch(op=op, device=dev, x=self, y=other), self.shape, dev)
+
+    def __gt__(self, other: "Buffer | Scalar") -> "Buffer":
+        return self._compare(other, BinaryOps.GT)
+
+    def __ge__(self, other: "Buffer | Scalar") -> "Buffer":
+        return self._compare(other, BinaryOps.GTE)
+
+    def __eq__(self, other: "Buffer") -> "Buffer":  # type: ignore[override]
+        return self._compare(other, BinaryOps.EQT)
+
+    __hash__ = object.__hash__
+
+    # ------------------------------------------------------------------ arithmetic
+    def _binary_op(self, other: "Buffer", op: BinaryOps) -> "Buffer":
+        if not check_broadcast(self.shape, other.shape):
+            raise ValueError(f"Cannot broadcast {other.shape} to {self.shape}")
+        # The reference labels the result with the larger operand's shape (dlgrad/buffer.py:406);
+        # for the one-sided broadcasts it supports that equals the broadcast shape used here.
+        out_shape = get_broadcast_shape(self.shape, other.shape)
+        dev = Buffer._route(self, other)
+        return self._like(_dispatch(op=op, device=dev, x=self, y=other), out_shape, dev)
+
+    def __add__(self, other: "Buffer | Scalar") -> "Buffer":
+        return self._binary_op(Buffer._as_buffer(other), BinaryOps.ADD)
+
+    def __mul__(self, other: "Buffer | Scalar") -> "Buffer":
+        return self._binary_op(Buffer._as_buffer(other), BinaryOps.MUL)
+
+    def __sub__(self, other: "Buffer | Scalar") -> "Buffer":
+        # small - big: the reference evaluates -(big - small) (dlgrad/buffer.py:408-426); in IEEE
+        # arithmetic that is bit-identical to small - big with `small` broadcast, which is what runs.
+        return self._binary_op(Buffer._as_buffer(other), BinaryOps.SUB)
+
+    def __truediv__(self, other: "Buffer | Scalar") -> "Buffer":
+        other = Buffer._as_buffer(other)
+        if self.numel >= other.numel:
+            return self._binary_op(other, BinaryOps.DIV)
+        # small / big is computed as big**-1 * small by the reference (dlgrad/buffer.py:479-486)
+        return (other ** -1)._binary_op(self, BinaryOps.MUL)
+
+    def __rsub__(self, other: Scalar) -> "Buffer":
+        return Buffer._as_buffer(other)._binary_op(self, BinaryOps.SUB)
+
+    __radd__ = __add__
+    __rmul__ = __mul__
+
+    def __matmul__(self, other: "Buffer") -> "Buffer":
+        return self.matmul(other)
+
+    # ------------------------------------------------------------------ loss / embedding
+    @staticmethod
+    def ce_forward(x: "Buffer", y: "Buffer") -> "Buffer":
+        dev = Buffer._route(x, y)
+        return x._like(_dispatch(op=CustomOps.CE_FORWARD, device=dev, x=x, y=y), (1, x.shape[0]), dev)
+
+    @staticmethod
+    def ce_backward(**kwargs) -> None:
+        kwargs.pop("device", None)
+        op = kwargs.pop("op", CustomOps.CE_BACKWARD)
+        dev = Buffer._route(kwargs["x"], kwargs["target"])
+        _dispatch(op=op, device=dev, **kwargs)
+
+    def embedding(self, idx: "Buffer", backward: bool = False, upstream_grad: "Buffer" = None) -> "Buffer":
+        if backward:
+            dev = Buffer._route(self, idx, upstream_grad)
+            return self._like(_dispatch(op=CustomOps.EMBEDDING, device=dev, x=self, idx=idx,
+                                        out_numel=self.numel, backward=True, upstream_grad=upstream_grad),
+                              self.shape, dev)
+        out_shape = idx.shape + (self.shape[-1],)
+        dev = Buffer._route(self, idx)
+        return self._like(_dispatch(op=CustomOps.EMBEDDING, device=dev, x=self, idx=idx,
+                                    out_numel=prod_(out_shape)), out_shape, dev)
+
+    # ------------------------------------------------------------------ properties
+    @property
+    def T(self) -> "Buffer":  # noqa: N802
+        return self.transpose(0, 1)
+
+    @property
+    def numel(self) -> int:
+        return self.metadata.numel
+
+    @property
+    def shape(self) -> tuple:
+        return self.metadata.shape
+
+    @property
+    def stride(self) -> tuple:
+        return self.metadata.stride
+
+    @property
+    def ndim(self) -> int:
+        return self.metadata.ndim
+
+    @property
+    def dtype(self) -> DType:
+        return self.metadata.dtype
+
+    @property
+    def device(self) -> Device:
+        return self.metadata.device
+
+    @property
+    def nbytes(self) -> int:
+        return self.metadata.nbytes

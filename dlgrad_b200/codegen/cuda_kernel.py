@@ -1,0 +1,916 @@
+"""CUDA C generators for the bandwidth-bound ops of the dlgrad hot path (sm_100a).
+
+Counterpart of dlgrad/codegen/cpu_kernel.py, built the other way round: the reference emits
+ndim-generic scalar loops and passes shapes at run time (cpu_kernel.py:12-66); here every kernel
+is *shape-specialised* — extents, broadcast strides, vector width, grid and unroll are literals in
+the source — so index arithmetic is constant-folded (mul-shift instead of div), 128-bit accesses
+are chosen statically, and the launch geometry is part of the plan.  One cubin per (op, shape),
+cached by source hash (runtime/cuda/compiler.py).
+
+Every kernel has the fixed plan signature
+    (p0, p1, p2, p3, out, f0, f1, f2, f3)
+(see include/dlgrad_cuda.h).  Generators return `Kernel(name, source, grid, block, smem, out_elems)`.
+All generators are @cache'd: a given (op, shape) is generated once per process.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from functools import cache
+
+from dlgrad_b200.runtime.cuda.compiler import KNAME
+
+SIG = ("(const float* __restrict__ p0, const float* __restrict__ p1, const float* __restrict__ p2, "
+       "const float* __restrict__ p3, float* __restrict__ out, float f0, float f1, float f2, float f3)")
+# in-place kernels alias `out`/p* — no __restrict__
+SIG_ALIAS = ("(float* p0, float* p1, float* p2, float* p3, float* out, "
+             "float f0, float f1, float f2, float f3)")
+
+NUM_SMS = 148
+
+
+@dataclass(frozen=True)
+class Kernel:
+    name: str
+    source: str
+    grid: tuple
+    block: tuple
+    smem: int = 0
+    out_elems: int = 0
+    zero_out: bool = False
+
+
+def _cdiv(a: int, b: int) -> int:
+    return -(-a // b)
+
+
+def _pow2_floor(x: int) -> int:
+    return 1 << (max(1, x).bit_length() - 1)
+
+
+def _pow2_ceil(x: int) -> int:
+    return 1 << (max(1, x) - 1).bit_length()
+
+
+# ------------------------------------------------------------------------------------------------
+# elementwise map with broadcasting
+# ------------------------------------------------------------------------------------------------
+def collapse_dims(shape: tuple, strides_list: list[tuple]) -> tuple[tuple, list[tuple]]:
+    """Drop size-1 dims and merge neighbours that are jointly contiguous for every operand."""
+    dims = [(s, tuple(st[i] for st in strides_list)) for i, s in enumerate(shape) if s != 1]
+    if not dims:
+        return (1,), [(0,) for _ in strides_list]
+    merged = [dims[0]]
+    for size, strd in dims[1:]:
+        psize, pstrd = merged[-1]
+        if all(ps == s * size for ps, s in zip(pstrd, strd)):
+            merged[-1] = (psize * size, strd)
+        else:
+            merged.append((size, strd))
+    out_shape = tuple(s for s, _ in merged)
+    out_strides = [tuple(m[1][j] for m in merged) for j in range(len(strides_list))]
+    return out_shape, out_strides
+
+
+@cache
+def ewise(expr: str, out_shape: tuple, in_strides: tuple, aligned: bool = True, tag: str = "ew") -> Kernel:
+    """out[idx] = expr(v0, v1, v2, v3, f0..f3) where v_j = p_j[<idx, in_strides[j]>].
+
+    `in_strides[j]` are element strides of pointer operand j aligned to `out_shape`
+    (0 = broadcast, as in get_broadcast_strides_2, dlgrad/helpers.py:276-308).
+    Covers cpu_kernel.arithmetic (:12-66), utils (:246-319), clamp (:321-349), where (:536-587),
+    masked_fill (:604-650), cmp_2d (:653-668), full (:758-770), arange (:743-755) and permute
+    when the innermost axis stays innermost (:180-215).
+    """
+    numel = 1
+    for s in out_shape:
+        numel *= s
+    n_in = len(in_strides)
+    contiguous = []
+    acc = 1
+    for s in reversed(out_shape):
+        contiguous.append(acc)
+        acc *= s
+    out_strides = tuple(reversed(contiguous))
+    shape, strides = collapse_dims(tuple(out_shape), [out_strides, *in_strides])
+    ostr, istr = strides[0], strides[1:]
+    inner = shape[-1]
+    vec = (aligned and inner % 4 == 0 and all(st[-1] in (0, 1) for st in istr)
+           and all(all(s % 4 == 0 for s in st[:-1]) for st in istr))
+    V = 4 if vec else 1
+    nvec = numel // V
+    big = max([numel] + [sum((d - 1) * abs(s) for d, s in zip(shape, st)) + 1 for st in istr]) >= 2**31
+    idx_t = "unsigned long long" if big else "unsigned"
+    BLOCK = 256
+    U = 4 if nvec >= BLOCK * 4 * NUM_SMS else (2 if nvec >= BLOCK * 2 * NUM_SMS else 1)
+    grid = max(1, _cdiv(nvec, BLOCK * U))
+
+    # index decomposition of the (vector) index into collapsed dims
+    vshape = list(shape)
+    vshape[-1] = inner // V
+    lines = []
+    nd = len(vshape)
+    if nd == 1:
+        lines.append(f"{idx_t} i0 = vi;")
+    else:
+        lines.append(f"{idx_t} t = vi;")
+        for d in range(nd - 1, 0, -1):
+            lines.append(f"{idx_t} i{d} = t % {vshape[d]}u; t /= {vshape[d]}u;")
+        lines.append(f"{idx_t} i0 = t;")
+    offs = []
+    for j, st in enumerate(istr):
+        terms = []
+        for d, s in enumerate(st):
+            if s == 0:
+                continue
+            mult = s * (V if d == nd - 1 else 1)
+            terms.append(f"i{d}*{mult}u" if mult != 1 else f"i{d}")
+        offs.append(" + ".join(terms) if terms else "0")
+    decomp = "\n            ".join(lines)
+
+    T = "float4" if vec else "float"
+    loads = []
+    for j, st in enumerate(istr):
+        if vec and st[-1] == 0:
+            loads.append(f"{{ float s = __ldg(p{j} + ({offs[j]})); a{j}[u] = make_float4(s, s, s, s); }}")
+        elif vec:
+            loads.append(f"a{j}[u] = __ldg(reinterpret_cast<const float4*>(p{j} + ({offs[j]})));")
+        else:
+            loads.append(f"a{j}[u] = __ldg(p{j} + ({offs[j]}));")
+    load_block = "\n                ".join(loads)
+    decl = "".join(f"    {T} a{j}[{U}];\n" for j in range(n_in))
+    vargs = lambda comp: ", ".join([f"a{j}[u]{comp}" for j in range(n_in)] + ["f0", "f1", "f2", "f3"])  # noqa: E731
+    params = ", ".join([f"float v{j}" for j in range(n_in)] + ["float f0", "float f1", "float f2", "float f3"])
+    need_idx = "ei" in expr   # arange-style kernels use the flat element index
+    if vec:
+        if need_idx:
+            compute = ("float4 r; " + " ".join(
+                f"r.{c} = op({vargs('.' + c)}, (float)(vi*4u+{k}u));" for k, c in enumerate("xyzw")))
+        else:
+            compute = "float4 r; " + " ".join(f"r.{c} = op({vargs('.' + c)}, 0.f);" for c in "xyzw")
+        store = "reinterpret_cast<float4*>(out)[vi] = r;"
+    else:
+        compute = f"float r = op({vargs('')}, {'(float)vi' if need_idx else '0.f'});"
+        store = "out[vi] = r;"
+    src = f"""
+__device__ __forceinline__ float op({params}, float ei) {{ return {expr}; }}
+extern "C" __global__ void __launch_bounds__({BLOCK}) {KNAME}{SIG} {{
+    constexpr {idx_t} NV = {nvec}u;
+    const {idx_t} base = ({idx_t})blockIdx.x * {BLOCK * U}u + threadIdx.x;
+{decl}    #pragma unroll
+    for (int u = 0; u < {U}; ++u) {{
+        const {idx_t} vi = base + u * {BLOCK}u;
+        if (vi < NV) {{
+            {decomp}
+            {load_block}
+        }}
+    }}
+    #pragma unroll
+    for (int u = 0; u < {U}; ++u) {{
+        const {idx_t} vi = base + u * {BLOCK}u;
+        if (vi < NV) {{
+            {compute}
+            {store}
+        }}
+    }}
+}}
+"""
+    if n_in == 0:
+        src = src.replace("            \n", "")
+    return Kernel(tag, src, (grid, 1, 1), (BLOCK, 1, 1), 0, numel)
+
+
+# expressions (v0.. = operands in pointer-slot order, f0.. = scalar slots)
+BINARY_EXPR = {
+    "add": "{a} + {b}", "sub": "{a} - {b}", "mul": "{a} * {b}", "div": "{a} / {b}",
+    "eq": "({a} == {b}) ? 1.f : 0.f", "gt": "({a} > {b}) ? 1.f : 0.f",
+    "gte": "({a} >= {b}) ? 1.f : 0.f", "lte": "({a} <= {b}) ? 1.f : 0.f",
+}
+
+
+def pow_expr(n: int, v: str = "v0") -> str:
+    """x ** int(p): the reference truncates the exponent (dlgrad/runtime/cpu.py:500,
+    cpu_kernel.py:288-291: powf(x, (int)val)); gcc -ffast-math expands small powers to products."""
+    if n == 0:
+        return "1.f"
+    if n == 1:
+        return v
+    if n == 2:
+        return f"{v} * {v}"
+    if n == 3:
+        return f"{v} * {v} * {v}"
+    if n == 4:
+        return f"({v} * {v}) * ({v} * {v})"
+    if n == -1:
+        return f"1.f / {v}"
+    if n == -2:
+        return f"1.f / ({v} * {v})"
+    return f"powf({v}, {float(n)}f)"
+
+
+UNARY_EXPR = {
+    "neg": "-v0", "exp": "expf(v0)", "log": "logf(v0)", "sqrt": "sqrtf(v0)",
+    "rsqrt": "1.f / sqrtf(v0)", "copy": "v0",
+}
+
+
+# ------------------------------------------------------------------------------------------------
+# reductions over one axis of a contiguous tensor viewed as (outer, R, inner)
+# ------------------------------------------------------------------------------------------------
+_RED = {
+    "sum": ("0.f", "a + b", "acc"),
+    "mean": ("0.f", "a + b", "acc / {R}.f"),
+    "max": ("-3.402823466e+38f", "(b > a) ? b : a", "acc"),
+}
+
+
+@cache
+def reduce_rows(op: str, outer: int, R: int, aligned: bool = True, scale_R: int | None = None) -> Kernel:
+    """Last-axis reduce: out[o] = red_r x[o*R + r].  Sub-warp / warp / block per row, 128-bit loads,
+    shuffle tree.  Restates reduce_source with the reduced axis innermost and reduce()
+    (dlgrad/codegen/cpu_kernel.py:69-177); max keeps the reference's `-FLT_MAX` seed and strict `>`."""
+    init, comb, fin = _RED[op]
+    fin = fin.format(R=scale_R if scale_R is not None else R)
+    V = 4 if (aligned and R % 4 == 0) else 1
+    nv = R // V
+    if nv >= 2048 and outer < NUM_SMS * 8:
+        T = 256                       # block per row
+    else:
+        T = min(32, _pow2_ceil(_cdiv(nv, 4)))
+    BLOCK = 256
+    rows_per_block = BLOCK // T
+    grid = _cdiv(outer, rows_per_block)
+    ld = ("float4 v = __ldg(reinterpret_cast<const float4*>(row) + c); "
+          "a0 = red(a0, v.x); a1 = red(a1, v.y); a2 = red(a2, v.z); a3 = red(a3, v.w);"
+          if V == 4 else "a0 = red(a0, __ldg(row + c));")
+    if T <= 32:
+        tail = f"""
+    #pragma unroll
+    for (int m = {T // 2}; m > 0; m >>= 1) acc = red(acc, __shfl_xor_sync(0xffffffffu, acc, m));
+    if (lane == 0 && r < {outer}u) out[r] = {fin};"""
+    else:
+        tail = f"""
+    __shared__ float part[{T // 32}];
+    #pragma unroll
+    for (int m = 16; m > 0; m >>= 1) acc = red(acc, __shfl_xor_sync(0xffffffffu, acc, m));
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {{
+        acc = threadIdx.x < {T // 32} ? part[threadIdx.x] : {init};
+        #pragma unroll
+        for (int m = {max(1, T // 64)}; m > 0; m >>= 1) acc = red(acc, __shfl_xor_sync(0xffffffffu, acc, m));
+        if (threadIdx.x == 0) out[r] = {fin};
+    }}"""
+    src = f"""
+__device__ __forceinline__ float red(float a, float b) {{ return {comb}; }}
+extern "C" __global__ void __launch_bounds__({BLOCK}) {KNAME}{SIG} {{
+    const unsigned r = blockIdx.x * {rows_per_block}u + threadIdx.x / {T}u;
+    const unsigned lane = threadIdx.x % {T}u;
+    float a0 = {init}, a1 = {init}, a2 = {init}, a3 = {init};
+    if (r < {outer}u) {{
+        const float* row = p0 + (size_t)r * {R}u;
+        #pragma unroll 4
+        for (unsigned c = lane; c < {nv}u; c += {T}u) {{ {ld} }}
+    }}
+    float acc = red(red(a0, a1), red(a2, a3));{tail}
+}}
+"""
+    return Kernel(f"red_{op}_rows", src, (grid, 1, 1), (BLOCK, 1, 1), 0, outer)
+
+
+@cache
+def reduce_cols(op: str, outer: int, R: int, inner: int, aligned: bool = True,
+                splits: int = 1, scale_R: int | None = None) -> Kernel:
+    """Strided reduce: out[s][o][i] = red_{r in split s} x[(o*R + r)*inner + i].  Threads run along
+    `inner` (coalesced), 8 warps of a block take interleaved rows and meet in shared memory; `splits`
+    slices R across blockIdx.z when outer*inner alone cannot fill 148 SMs (a second reduce_cols pass
+    over the `splits` axis finishes).  The reference walks this case with a strided inner loop
+    (cpu_kernel.py:69-148), its slowest pattern (152 ms for 4096^2 axis 0)."""
+    init, comb, fin = _RED[op]
+    fin = fin.format(R=scale_R if scale_R is not None else R) if splits == 1 else "acc"
+    V = 4 if (aligned and inner % 4 == 0) else 1
+    ncolv = inner // V
+    Y = 8
+    rows_per_split = _cdiv(R, splits)
+    T = "float4" if V == 4 else "float"
+    if V == 4:
+        initv = f"make_float4({init}, {init}, {init}, {init})"
+        acc_upd = "acc.x = red(acc.x, v.x); acc.y = red(acc.y, v.y); acc.z = red(acc.z, v.z); acc.w = red(acc.w, v.w);"
+        ldv = "__ldg(reinterpret_cast<const float4*>(base + (size_t)r * %du) + cv)" % inner
+        comb_sm = ("acc.x = red(acc.x, o.x); acc.y = red(acc.y, o.y); acc.z = red(acc.z, o.z); acc.w = red(acc.w, o.w);")
+        fin4 = "; ".join(f"res.{c} = " + fin.replace("acc", f"acc.{c}") for c in "xyzw")
+        store = f"float4 res; {fin4}; reinterpret_cast<float4*>(dst)[cv] = res;"
+    else:
+        initv = init
+        acc_upd = "acc = red(acc, v);"
+        ldv = "__ldg(base + (size_t)r * %du + cv)" % inner
+        comb_sm = "acc = red(acc, o);"
+        store = f"dst[cv] = {fin};"
+    src = f"""
+__device__ __forceinline__ float red(float a, float b) {{ return {comb}; }}
+extern "C" __global__ void __launch_bounds__({32 * Y}) {KNAME}{SIG} {{
+    __shared__ {T} part[{Y}][33];
+    const unsigned cv = blockIdx.x * 32u + threadIdx.x;
+    const unsigned o = blockIdx.y, s = blockIdx.z;
+    const unsigned r0 = s * {rows_per_split}u;
+    const unsigned r1 = min(r0 + {rows_per_split}u, {R}u);
+    const float* base = p0 + (size_t)o * {R * inner}u;
+    {T} acc = {initv};
+    if (cv < {ncolv}u) {{
+        #pragma unroll 4
+        for (unsigned r = r0 + threadIdx.y; r < r1; r += {Y}u) {{
+            {T} v = {ldv};
+            {acc_upd}
+        }}
+    }}
+    part[threadIdx.y][threadIdx.x] = acc;
+    __syncthreads();
+    if (threadIdx.y == 0 && cv < {ncolv}u) {{
+        #pragma unroll
+        for (int y = 1; y < {Y}; ++y) {{ {T} o = part[y][threadIdx.x]; {comb_sm} }}
+        float* dst = out + ((size_t)s * {outer}u + o) * {inner}u;
+        {store}
+    }}
+}}
+"""
+    grid = (_cdiv(ncolv, 32), outer, splits)
+    return Kernel(f"red_{op}_cols", src, grid, (32, Y, 1), 0, splits * outer * inner)
+
+
+@cache
+def reduce_all_partial(op: str, numel: int, aligned: bool = True) -> Kernel:
+    """Stage 1 of a full reduce (cpu_kernel.reduce, :151-177): G blocks grid-stride over the tensor
+    and each leaves one partial in out[blockIdx.x]; reduce_rows(op, 1, G) finishes."""
+    init, comb, _ = _RED[op]
+    V = 4 if (aligned and numel % 4 == 0) else 1
+    nv = numel // V
+    BLOCK = 256
+    G = max(1, min(NUM_SMS * 4, _cdiv(nv, BLOCK * 4)))
+    ld = ("float4 v = __ldg(reinterpret_cast<const float4*>(p0) + c); "
+          "a0 = red(a0, v.x); a1 = red(a1, v.y); a2 = red(a2, v.z); a3 = red(a3, v.w);"
+          if V == 4 else "a0 = red(a0, __ldg(p0 + c));")
+    src = f"""
+__device__ __forceinline__ float red(float a, float b) {{ return {comb}; }}
+extern "C" __global__ void __launch_bounds__({BLOCK}) {KNAME}{SIG} {{
+    __shared__ float part[{BLOCK // 32}];
+    float a0 = {init}, a1 = {init}, a2 = {init}, a3 = {init};
+    #pragma unroll 4
+    for (size_t c = (size_t)blockIdx.x * {BLOCK}u + threadIdx.x; c < {nv}ull; c += {G * BLOCK}ull) {{ {ld} }}
+    float acc = red(red(a0, a1), red(a2, a3));
+    #pragma unroll
+    for (int m = 16; m > 0; m >>= 1) acc = red(acc, __shfl_xor_sync(0xffffffffu, acc, m));
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {{
+        acc = threadIdx.x < {BLOCK // 32} ? part[threadIdx.x] : {init};
+        #pragma unroll
+        for (int m = {BLOCK // 64}; m > 0; m >>= 1) acc = red(acc, __shfl_xor_sync(0xffffffffu, acc, m));
+        if (threadIdx.x == 0) out[blockIdx.x] = acc;
+    }}
+}}
+"""
+    return Kernel(f"red_{op}_all", src, (G, 1, 1), (BLOCK, 1, 1), 0, G)
+
+
+@cache
+def argmax(rows: int, cols: int, dim: int) -> Kernel:
+    """Index of the first maximum as float (cpu_kernel.argmax, :460-517): strict `>` scan so ties
+    resolve to the lowest index; dim 0 / 1 of a 2-D tensor, dim -1 over everything.  One warp per
+    output; lanes scan strided slices and merge on (value desc, index asc)."""
+    if dim == 1:
+        n_out, R, stride_r, stride_o = rows, cols, 1, cols
+    elif dim == 0:
+        n_out, R, stride_r, stride_o = cols, rows, cols, 1
+    else:
+        n_out, R, stride_r, stride_o = 1, rows * cols, 1, 0
+    BLOCK = 256
+    src = f"""
+extern "C" __global__ void __launch_bounds__({BLOCK}) {KNAME}{SIG} {{
+    const unsigned o = blockIdx.x * {BLOCK // 32}u + (threadIdx.x >> 5);
+    const unsigned lane = threadIdx.x & 31u;
+    if (o >= {n_out}u) return;
+    const float* base = p0 + (size_t)o * {stride_o}u;
+    float best = -3.402823466e+38f; unsigned bi = 0xffffffffu;
+    for (unsigned r = lane; r < {R}u; r += 32u) {{
+        float v = __ldg(base + (size_t)r * {stride_r}u);
+        if (v > best || bi == 0xffffffffu) {{ if (v > best || bi == 0xffffffffu) {{ best = v; bi = r; }} }}
+    }}
+    #pragma unroll
+    for (int m = 16; m > 0; m >>= 1) {{
+        float ov = __shfl_xor_sync(0xffffffffu, best, m);
+        unsigned oi = __shfl_xor_sync(0xffffffffu, bi, m);
+        if (oi != 0xffffffffu && (bi == 0xffffffffu || ov > best || (ov == best && oi < bi))) {{ best = ov; bi = oi; }}
+    }}
+    if (lane == 0) out[o] = (float)bi;
+}}
+"""
+    return Kernel("argmax", src, (_cdiv(n_out, BLOCK // 32), 1, 1), (BLOCK, 1, 1), 0, n_out)
+
+
+# ------------------------------------------------------------------------------------------------
+# permute
+# ------------------------------------------------------------------------------------------------
+@cache
+def transpose_tiled(out_shape: tuple, in_strides: tuple, tdim: int) -> Kernel:
+    """Materialised permutation whose innermost *output* axis is strided in the input, while output
+    axis `tdim` is the input's unit-stride axis: classic 32x33 shared-memory tile so both the read
+    (along tdim) and the write (along the last axis) are coalesced.  cpu_kernel.permute (:180-215)
+    does the same gather with a scalar strided loop."""
+    nd = len(out_shape)
+    ostr = []
+    acc = 1
+    for s in reversed(out_shape):
+        ostr.append(acc)
+        acc *= s
+    ostr = tuple(reversed(ostr))
+    J, Tn = out_shape[-1], out_shape[tdim]
+    sj = in_strides[-1]
+    batch_dims = [d for d in range(nd - 1) if d != tdim]
+    nbatch = 1
+    for d in batch_dims:
+        nbatch *= out_shape[d]
+    lines = ["unsigned bz = blockIdx.z; size_t ib = 0, ob = 0;"]
+    for d in reversed(batch_dims):
+        lines.append(f"{{ unsigned q = bz % {out_shape[d]}u; bz /= {out_shape[d]}u; "
+                     f"ib += (size_t)q * {in_strides[d]}u; ob += (size_t)q * {ostr[d]}u; }}")
+    decomp = "\n    ".join(lines)
+    src = f"""
+extern "C" __global__ void __launch_bounds__(256) {KNAME}{SIG} {{
+    __shared__ float tile[32][33];
+    {decomp}
+    const unsigned j0 = blockIdx.x * 32u, t0 = blockIdx.y * 32u;
+    #pragma unroll
+    for (int k = 0; k < 32; k += 8) {{
+        const unsigned j = j0 + threadIdx.y + k, t = t0 + threadIdx.x;
+        if (j < {J}u && t < {Tn}u) tile[threadIdx.y + k][threadIdx.x] = __ldg(p0 + ib + (size_t)j * {sj}u + t);
+    }}
+    __syncthreads();
+    #pragma unroll
+    for (int k = 0; k < 32; k += 8) {{
+        const unsigned t = t0 + threadIdx.y + k, j = j0 + threadIdx.x;
+        if (j < {J}u && t < {Tn}u) out[ob + (size_t)t * {ostr[tdim]}u + j] = tile[threadIdx.x][threadIdx.y + k];
+    }}
+}}
+"""
+    numel = nbatch * J * Tn
+    return Kernel("transpose", src, (_cdiv(J, 32), _cdiv(Tn, 32), nbatch), (32, 8, 1), 0, numel)
+
+
+# ------------------------------------------------------------------------------------------------
+# gather / scatter family (integer-valued floats index rows; results must be bit-exact)
+# ------------------------------------------------------------------------------------------------
+@cache
+def embedding_fwd(n_idx: int, C: int, aligned: bool = True) -> Kernel:
+    """out[i, :] = W[(int)idx[i], :]   (cpu_kernel.embedding, :218-229: row memcpy)."""
+    V = 4 if (aligned and C % 4 == 0) else 1
+    cv = C // V
+    T = "float4" if V == 4 else "float"
+    total = n_idx * cv
+    src = f"""
+extern "C" __global__ void __launch_bounds__(256) {KNAME}{SIG} {{
+    const size_t g = (size_t)blockIdx.x * 256u + threadIdx.x;
+    if (g >= {total}ull) return;
+    const unsigned i = g / {cv}u, c = g % {cv}u;
+    const int row = (int)__ldg(p1 + i);
+    reinterpret_cast<{T}*>(out)[g] = __ldg(reinterpret_cast<const {T}*>(p0 + (size_t)row * {C}u) + c);
+}}
+"""
+    return Kernel("emb_fwd", src, (_cdiv(total, 256), 1, 1), (256, 1, 1), 0, n_idx * C)
+
+
+@cache
+def embedding_bwd(n_rows: int, n_idx: int, C: int) -> Kernel:
+    """dW[row, c] = sum over i with idx[i] == row of g[i, c], accumulated in increasing i — exactly
+    the reference's sequential scatter-add order (cpu_kernel.embedding_backward, :232-243), so the
+    fp32 result is bit-identical; atomics would not be.  One block per (row, 128-column slab): the
+    index list streams through shared memory, matching tokens are compacted in order by a ballot
+    scan, then every thread adds its column over the compacted list."""
+    CB = 128
+    CH = 1024
+    src = f"""
+extern "C" __global__ void __launch_bounds__({CB}) {KNAME}{SIG} {{
+    // p0 = upstream grad (n_idx, C), p1 = idx (n_idx)
+    __shared__ unsigned hits[{CH}];
+    __shared__ unsigned warp_cnt[{CB // 32}];
+    __shared__ unsigned n_hits;
+    const unsigned row = blockIdx.x;
+    const unsigned c = blockIdx.y * {CB}u + threadIdx.x;
+    const unsigned lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+    float acc = 0.f;
+    for (unsigned base = 0; base < {n_idx}u; base += {CH}u) {{
+        if (threadIdx.x == 0) n_hits = 0;
+        __syncthreads();
+        // ordered compaction of matching token positions in this chunk
+        for (unsigned s = 0; s < {CH}u; s += {CB}u) {{
+            const unsigned i = base + s + threadIdx.x;
+            const bool hit = (i < {n_idx}u) && ((int)__ldg(p1 + i) == (int)row);
+            const unsigned m = __ballot_sync(0xffffffffu, hit);
+            if (lane == 0) warp_cnt[w] = __popc(m);
+            __syncthreads();
+            unsigned off = n_hits;
+            for (unsigned k = 0; k < w; ++k) off += warp_cnt[k];
+            if (hit) hits[off + __popc(m & ((1u << lane) - 1u))] = i;
+            __syncthreads();
+            if (threadIdx.x == 0) {{ unsigned t = 0; for (unsigned k = 0; k < {CB // 32}u; ++k) t += warp_cnt[k]; n_hits += t; }}
+            __syncthreads();
+        }}
+        const unsigned nh = n_hits;
+        if (c < {C}u) for (unsigned k = 0; k < nh; ++k) acc += __ldg(p0 + (size_t)hits[k] * {C}u + c);
+        __syncthreads();
+    }}
+    if (c < {C}u) out[(size_t)row * {C}u + c] = acc;
+}}
+"""
+    return Kernel("emb_bwd", src, (n_rows, _cdiv(C, CB), 1), (CB, 1, 1), 0, n_rows * C)
+
+
+@cache
+def ce_forward(n: int, stride0: int) -> Kernel:
+    """out[i] = x[(int)t[i] + stride0*i]   (cpu_kernel.ce_forward, :431-441)."""
+    src = f"""
+extern "C" __global__ void __launch_bounds__(256) {KNAME}{SIG} {{
+    const unsigned i = blockIdx.x * 256u + threadIdx.x;
+    if (i < {n}u) out[i] = __ldg(p0 + (size_t)i * {stride0}u + (int)__ldg(p1 + i));
+}}
+"""
+    return Kernel("ce_fwd", src, (_cdiv(n, 256), 1, 1), (256, 1, 1), 0, n)
+
+
+@cache
+def ce_backward(n: int, stride0: int) -> Kernel:
+    """In place: x[(int)t[i] + stride0*i] -= 1   (cpu_kernel.ce_backward, :444-457)."""
+    src = f"""
+extern "C" __global__ void __launch_bounds__(256) {KNAME}{SIG_ALIAS} {{
+    const unsigned i = blockIdx.x * 256u + threadIdx.x;
+    if (i < {n}u) {{ float* q = p0 + (size_t)i * {stride0}u + (int)p1[i]; *q = *q - 1.f; }}
+}}
+"""
+    return Kernel("ce_bwd", src, (_cdiv(n, 256), 1, 1), (256, 1, 1), 0, 0)
+
+
+# ------------------------------------------------------------------------------------------------
+# matmul, SIMT fallback (exact fp32 FMA chain, sequential in k like the reference's i-k-j loop)
+# ------------------------------------------------------------------------------------------------
+@cache
+def matmul_simt(M: int, N: int, K: int, nb0: int, nb1: int, a_bs: tuple, b_bs: tuple,
+                ta: bool = False, tb: bool = False, aligned: bool = True) -> Kernel:
+    """C[z] = op(A[z]) @ op(B[z]) for z over (nb0, nb1) batch dims; batch strides of 0 broadcast an
+    operand, as the reference's stride-zeroing does (dlgrad/runtime/cpu.py:507-575; kernels
+    cpu_kernel.matmul_{2,3,4}d, :352-428).  `ta`/`tb` read A as (K, M) / B as (N, K) so backward
+    needs no materialised transpose.  Shared-memory tiled, register-blocked FFMA; every output
+    accumulates its K products in increasing k with fused multiply-adds, which is what gcc makes of
+    the reference loop — the fp32 result is the same chain.  Used for shapes the tensor-core path
+    cannot take (N or K not a multiple of 8, tiny problems)."""
+    nb = nb0 * nb1
+    # pick the largest tile that still gives every SM a block
+    for BM, BN, TM, TN in ((128, 128, 8, 8), (64, 64, 4, 4), (32, 32, 2, 2)):
+        if _cdiv(M, BM) * _cdiv(N, BN) * nb >= NUM_SMS or (BM == 32):
+            break
+    if M <= 32 and N <= 32:
+        BM, BN, TM, TN = 32, 32, 2, 2
+    BK = 16
+    TX, TY = BN // TN, BM // TM
+    NT = TX * TY
+    lda = M if ta else K
+    ldb = K if tb else N
+    va = aligned and lda % 4 == 0 and all(s % 4 == 0 for s in a_bs)
+    vb = aligned and ldb % 4 == 0 and all(s % 4 == 0 for s in b_bs)
+    vc = aligned and N % 4 == 0 and TN % 4 == 0
+
+    def loader(name, smem, rows_dim, R0, RT, ld, transposed_store, vec, Rmax):
+        """Tile of `smem`[BK][RT] from a matrix whose tile is (RT x BK).  `transposed_store` means the
+        matrix is stored with k contiguous (rows = RT index), else with the RT index contiguous."""
+        out = []
+        if transposed_store:        # stored [r][k], k contiguous
+            if vec:
+                n4 = RT * BK // 4
+                out.append(f"for (unsigned e = tid; e < {n4}u; e += {NT}u) {{")
+                out.append(f"  const unsigned r = e / {BK // 4}u, k4 = (e % {BK // 4}u) * 4u;")
+                out.append(f"  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);")
+                out.append(f"  if ({R0} + r < {Rmax}u && k0 + k4 < {K}u) v = __ldg(reinterpret_cast<const float4*>({name} + (size_t)({R0} + r) * {ld}u + k0 + k4));")
+                out.append(f"  {smem}[k4][r] = v.x; {smem}[k4 + 1][r] = v.y; {smem}[k4 + 2][r] = v.z; {smem}[k4 + 3][r] = v.w;")
+                out.append("}")
+            else:
+                out.append(f"for (unsigned e = tid; e < {RT * BK}u; e += {NT}u) {{")
+                out.append(f"  const unsigned r = e / {BK}u, k = e % {BK}u;")
+                out.append(f"  {smem}[k][r] = ({R0} + r < {Rmax}u && k0 + k < {K}u) ? __ldg({name} + (size_t)({R0} + r) * {ld}u + k0 + k) : 0.f;")
+                out.append("}")
+        else:                       # stored [k][r], r contiguous
+            if vec:
+                n4 = RT * BK // 4
+                out.append(f"for (unsigned e = tid; e < {n4}u; e += {NT}u) {{")
+                out.append(f"  const unsigned k = e / {RT // 4}u, r4 = (e % {RT // 4}u) * 4u;")
+                out.append(f"  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);")
+                out.append(f"  if (k0 + k < {K}u && {R0} + r4 < {Rmax}u) v = __ldg(reinterpret_cast<const float4*>({name} + (size_t)(k0 + k) * {ld}u + {R0} + r4));")
+                out.append(f"  *reinterpret_cast<float4*>(&{smem}[k][r4]) = v;")
+                out.append("}")
+            else:
+                out.append(f"for (unsigned e = tid; e < {RT * BK}u; e += {NT}u) {{")
+                out.append(f"  const unsigned k = e / {RT}u, r = e % {RT}u;")
+                out.append(f"  {smem}[k][r] = (k0 + k < {K}u && {R0} + r < {Rmax}u) ? __ldg({name} + (size_t)(k0 + k) * {ld}u + {R0} + r) : 0.f;")
+                out.append("}")
+        return "\n        ".join(out)
+
+    a_load = loader("A", "As", "m", "m0", BM, lda, not ta, va, M)
+    b_load = loader("B", "Bs", "n", "n0", BN, ldb, tb, vb, N)
+
+    # register micro-tile: rows/cols split in two halves of 4 when the micro-tile is 8 wide so the
+    # 128-bit shared loads of a quarter-warp hit distinct banks
+    def frag(idx_var, T_, half):
+        if T_ == 8:
+            return [f"{idx_var} * 4u + {i}u" if i < 4 else f"{half}u + {idx_var} * 4u + {i - 4}u" for i in range(8)]
+        return [f"{idx_var} * {T_}u + {i}u" for i in range(T_)]
+
+    rows = frag("ty", TM, BM // 2)
+    cols = frag("tx", TN, BN // 2)
+
+    def frag_load(dst, smem, T_, idx_var, half):
+        if T_ == 8:
+            return (f"*reinterpret_cast<float4*>(&{dst}[0]) = *reinterpret_cast<const float4*>(&{smem}[kk][{idx_var} * 4u]); "
+                    f"*reinterpret_cast<float4*>(&{dst}[4]) = *reinterpret_cast<const float4*>(&{smem}[kk][{half}u + {idx_var} * 4u]);")
+        if T_ == 4:
+            return f"*reinterpret_cast<float4*>(&{dst}[0]) = *reinterpret_cast<const float4*>(&{smem}[kk][{idx_var} * 4u]);"
+        return " ".join(f"{dst}[{i}] = {smem}[kk][{idx_var} * {T_}u + {i}u];" for i in range(T_))
+
+    stores = []
+    for i in range(TM):
+        r = f"(m0 + {rows[i]})"
+        if vc:
+            for j0 in range(0, TN, 4):
+                c = f"(n0 + {cols[j0]})"
+                stores.append(f"if ({r} < {M}u && {c} < {N}u) *reinterpret_cast<float4*>(C + (size_t){r} * {N}u + {c}) = "
+                              f"make_float4(acc[{i}][{j0}], acc[{i}][{j0 + 1}], acc[{i}][{j0 + 2}], acc[{i}][{j0 + 3}]);")
+        else:
+            for j in range(TN):
+                c = f"(n0 + {cols[j]})"
+                stores.append(f"if ({r} < {M}u && {c} < {N}u) C[(size_t){r} * {N}u + {c}] = acc[{i}][{j}];")
+    store_block = "\n    ".join(stores)
+
+    src = f"""
+extern "C" __global__ void __launch_bounds__({NT}) {KNAME}{SIG} {{
+    __shared__ __align__(16) float As[{BK}][{BM + 4}];
+    __shared__ __align__(16) float Bs[{BK}][{BN + 4}];
+    const unsigned tid = threadIdx.x;
+    const unsigned z = blockIdx.z, b0 = z / {nb1}u, b1 = z % {nb1}u;
+    const float* A = p0 + (size_t)b0 * {a_bs[0]}u + (size_t)b1 * {a_bs[1]}u;
+    const float* B = p1 + (size_t)b0 * {b_bs[0]}u + (size_t)b1 * {b_bs[1]}u;
+    float* C = out + (size_t)z * {M * N}u;
+    const unsigned m0 = blockIdx.y * {BM}u, n0 = blockIdx.x * {BN}u;
+    const unsigned ty = tid / {TX}u, tx = tid % {TX}u;
+    float acc[{TM}][{TN}];
+    #pragma unroll
+    for (int i = 0; i < {TM}; ++i)
+        #pragma unroll
+        for (int j = 0; j < {TN}; ++j) acc[i][j] = 0.f;
+    for (unsigned k0 = 0; k0 < {K}u; k0 += {BK}u) {{
+        {a_load}
+        {b_load}
+        __syncthreads();
+        #pragma unroll
+        for (int kk = 0; kk < {BK}; ++kk) {{
+            __align__(16) float a[{TM}]; __align__(16) float b[{TN}];
+            {frag_load("a", "As", TM, "ty", BM // 2)}
+            {frag_load("b", "Bs", TN, "tx", BN // 2)}
+            #pragma unroll
+            for (int i = 0; i < {TM}; ++i)
+                #pragma unroll
+                for (int j = 0; j < {TN}; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }}
+        __syncthreads();
+    }}
+    {store_block}
+}}
+"""
+    grid = (_cdiv(N, BN), _cdiv(M, BM), nb)
+    return Kernel("mm_simt", src, grid, (NT, 1, 1), 0, nb * M * N)
+
+
+# ------------------------------------------------------------------------------------------------
+# fused row ops: softmax / log-softmax forward and backward, cross-entropy gradient
+# ------------------------------------------------------------------------------------------------
+def _row_geometry(R: int, aligned: bool, outer: int):
+    V = 4 if (aligned and R % 4 == 0) else 1
+    nv = R // V
+    T = min(32, _pow2_ceil(_cdiv(nv, 8)))
+    if _cdiv(nv, T) > 16:
+        T = 256 if _cdiv(nv, 256) <= 16 else 1024
+    per = _cdiv(nv, T)
+    return V, nv, T, per
+
+
+def _row_reduce_code(T: int, var: str, comb: str, ident: str, tag: str) -> str:
+    """reduce `var` across the T threads that share a row (in place, all threads get the result)."""
+    if T <= 32:
+        return (f"#pragma unroll\n    for (int m = {T // 2}; m > 0; m >>= 1) "
+                f"{{ float o = __shfl_xor_sync(0xffffffffu, {var}, m); {var} = {comb.format(a=var, b='o')}; }}")
+    nw = T // 32
+    return f"""#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) {{ float o = __shfl_xor_sync(0xffffffffu, {var}, m); {var} = {comb.format(a=var, b='o')}; }}
+    __shared__ float sm_{tag}[{nw}];
+    if ((threadIdx.x & 31) == 0) sm_{tag}[threadIdx.x >> 5] = {var};
+    __syncthreads();
+    {var} = {ident};
+    #pragma unroll
+    for (int w = 0; w < {nw}; ++w) {{ float o = sm_{tag}[w]; {var} = {comb.format(a=var, b='o')}; }}"""
+
+
+@cache
+def softmax_rows(kind: str, outer: int, R: int, aligned: bool = True) -> Kernel:
+    """Fused softmax / log-softmax over the last axis: one HBM read and one write per element, the
+    row lives in registers between the max, the exp-sum and the normalisation.  Replaces the
+    reference's 5-kernel chain max / sub / exp / sum / div (dlgrad/tensor.py:634-669) and, for the
+    loss, the first six kernels of ops.CrossEntropy.forward (dlgrad/ops.py:343-349).  Masked lanes
+    holding -inf come out as exactly 0 (softmax) like the reference's."""
+    V, nv, T, per = _row_geometry(R, aligned, outer)
+    BLOCK = 256 if T <= 256 else T
+    rpb = BLOCK // T
+    VT = "float4" if V == 4 else "float"
+    comps = ["x", "y", "z", "w"] if V == 4 else [""]
+
+    def each(fmt):
+        return " ".join(fmt.format(c=("." + c) if c else "") for c in comps)
+    if kind == "softmax":
+        final = each("v[i]{c} = v[i]{c} / s;")
+    else:
+        final = each("v[i]{c} = (xs[i]{c}) - ls;")
+    keep_shift = kind != "softmax"
+    src = f"""
+extern "C" __global__ void __launch_bounds__({BLOCK}) {KNAME}{SIG} {{
+    const unsigned r = blockIdx.x * {rpb}u + threadIdx.x / {T}u;
+    const unsigned lane = threadIdx.x % {T}u;
+    const bool live = r < {outer}u;
+    const {VT}* row = reinterpret_cast<const {VT}*>(p0 + (size_t)(live ? r : 0) * {R}u);
+    {VT} v[{per}];
+    float mx = -3.402823466e+38f;
+    #pragma unroll
+    for (int i = 0; i < {per}; ++i) {{
+        const unsigned c = lane + i * {T}u;
+        if (c < {nv}u) {{ v[i] = __ldg(row + c); {each("mx = (v[i]{c} > mx) ? v[i]{c} : mx;")} }}
+    }}
+    {_row_reduce_code(T, "mx", "({b} > {a}) ? {b} : {a}", "-3.402823466e+38f", "mx")}
+    float s = 0.f;
+    {VT} xs[{per if keep_shift else 1}];
+    #pragma unroll
+    for (int i = 0; i < {per}; ++i) {{
+        const unsigned c = lane + i * {T}u;
+        if (c < {nv}u) {{
+            {each("v[i]{c} = v[i]{c} - mx;")}
+            {"xs[i] = v[i];" if keep_shift else ""}
+            {each("v[i]{c} = expf(v[i]{c}); s += v[i]{c};")}
+        }}
+    }}
+    {_row_reduce_code(T, "s", "{a} + {b}", "0.f", "s")}
+    {"const float ls = logf(s);" if keep_shift else ""}
+    if (!live) return;
+    {VT}* orow = reinterpret_cast<{VT}*>(out + (size_t)r * {R}u);
+    #pragma unroll
+    for (int i = 0; i < {per}; ++i) {{
+        const unsigned c = lane + i * {T}u;
+        if (c < {nv}u) {{ {final} orow[c] = v[i]; }}
+    }}
+}}
+"""
+    return Kernel(f"{kind}_rows", src, (_cdiv(outer, rpb), 1, 1), (BLOCK, 1, 1), 0, outer * R)
+
+
+@cache
+def softmax_bwd_rows(kind: str, outer: int, R: int, aligned: bool = True) -> Kernel:
+    """Backward of the fused row ops.  softmax: dx = y * (g - sum(g*y)); log-softmax:
+    dx = g - exp(y) * sum(g).  p0 = forward output y, p1 = upstream g.  Algebraically what the
+    reference's autograd chain (Div/Exp/Sum/Sub/Max backward, ~17 kernels)
+    evaluates; the Max branch there contributes only rounding noise because softmax is
+    shift-invariant."""
+    V, nv, T, per = _row_geometry(R, aligned, outer)
+    BLOCK = 256 if T <= 256 else T
+    rpb = BLOCK // T
+    VT = "float4" if V == 4 else "float"
+    comps = ["x", "y", "z", "w"] if V == 4 else [""]
+
+    def each(fmt):
+        return " ".join(fmt.format(c=("." + c) if c else "") for c in comps)
+    if kind == "softmax":
+        accum = each("d += g[i]{c} * y[i]{c};")
+        final = each("g[i]{c} = y[i]{c} * (g[i]{c} - d);")
+    else:
+        accum = each("d += g[i]{c};")
+        final = each("g[i]{c} = g[i]{c} - expf(y[i]{c}) * d;")
+    src = f"""
+extern "C" __global__ void __launch_bounds__({BLOCK}) {KNAME}{SIG} {{
+    const unsigned r = blockIdx.x * {rpb}u + threadIdx.x / {T}u;
+    const unsigned lane = threadIdx.x % {T}u;
+    const bool live = r < {outer}u;
+    const size_t ro = (size_t)(live ? r : 0) * {R}u;
+    const {VT}* yrow = reinterpret_cast<const {VT}*>(p0 + ro);
+    const {VT}* grow = reinterpret_cast<const {VT}*>(p1 + ro);
+    {VT} y[{per}], g[{per}];
+    float d = 0.f;
+    #pragma unroll
+    for (int i = 0; i < {per}; ++i) {{
+        const unsigned c = lane + i * {T}u;
+        if (c < {nv}u) {{ y[i] = __ldg(yrow + c); g[i] = __ldg(grow + c); {accum} }}
+    }}
+    {_row_reduce_code(T, "d", "{a} + {b}", "0.f", "d")}
+    if (!live) return;
+    {VT}* orow = reinterpret_cast<{VT}*>(out + ro);
+    #pragma unroll
+    for (int i = 0; i < {per}; ++i) {{
+        const unsigned c = lane + i * {T}u;
+        if (c < {nv}u) {{ {final} orow[c] = g[i]; }}
+    }}
+}}
+"""
+    return Kernel(f"{kind}_bwd_rows", src, (_cdiv(outer, rpb), 1, 1), (BLOCK, 1, 1), 0, outer * R)
+
+
+@cache
+def ce_grad(n: int, V: int, up_is_ptr: bool) -> Kernel:
+    """(exp(logsm) - onehot(target)) * upstream / N in one pass — the four kernels of
+    ops.CrossEntropy.backward (dlgrad/ops.py:359-370: exp, in-place -1 at the target, mul, div),
+    same operation order per element.  p0 = log-softmax (n, V), p1 = target (n,), p2/f0 = upstream,
+    f1 = N."""
+    total = n * V
+    up = "__ldg(p2)" if up_is_ptr else "f0"
+    src = f"""
+extern "C" __global__ void __launch_bounds__(256) {KNAME}{SIG} {{
+    const size_t e = (size_t)blockIdx.x * 256u + threadIdx.x;
+    if (e >= {total}ull) return;
+    const unsigned i = e / {V}u, j = e % {V}u;
+    float t = expf(__ldg(p0 + e));
+    if ((int)__ldg(p1 + i) == (int)j) t = t - 1.f;
+    out[e] = __fdiv_rn(__fmul_rn(t, {up}), f1);
+}}
+"""
+    return Kernel("ce_grad", src, (_cdiv(total, 256), 1, 1), (256, 1, 1), 0, total)
+
+
+# ------------------------------------------------------------------------------------------------
+# optimizer steps (in place)
+# ------------------------------------------------------------------------------------------------
+def _flit(x: float) -> str:
+    """exact float32 literal"""
+    import struct
+    bits = struct.unpack("<I", struct.pack("<f", x))[0]
+    return f"__uint_as_float(0x{bits:08x}u)"
+
+
+@cache
+def adam_step(numel: int, beta1: float, beta2: float, eps: float, aligned: bool = True) -> Kernel:
+    """One fused, in-place Adam update per parameter tensor: reads g, m, v, p and writes m, v, p
+    (28 B/param) instead of the reference's ~14 elementwise dispatches with a fresh allocation
+    each (dlgrad/nn/optim.py:59-70).  The float32 operation sequence per element is the
+    reference's, op for op (no FMA contraction): m*b1 + g*(1-b1); v*b2 + (g*g)*(1-b2);
+    m/(1-b1^t); v/(1-b2^t); p - (mh/(sqrt(vh)+eps))*lr.  f0 = 1-b1^t, f1 = 1-b2^t, f2 = lr.
+    p0 = param, p1 = grad, p2 = m, p3 = v."""
+    V = 4 if (aligned and numel % 4 == 0) else 1
+    nv = numel // V
+    VT = "float4" if V == 4 else "float"
+    comps = ["x", "y", "z", "w"] if V == 4 else [""]
+    b1, b2, e_ = _flit(beta1), _flit(beta2), _flit(eps)
+    omb1, omb2 = _flit(1.0 - beta1), _flit(1.0 - beta2)
+    body = []
+    for c in comps:
+        s = ("." + c) if c else ""
+        body.append(f"""
+        {{ const float gg = g{s};
+          const float mn = __fadd_rn(__fmul_rn(m{s}, {b1}), __fmul_rn(gg, {omb1}));
+          const float vn = __fadd_rn(__fmul_rn(v{s}, {b2}), __fmul_rn(__fmul_rn(gg, gg), {omb2}));
+          const float mh = __fdiv_rn(mn, f0), vh = __fdiv_rn(vn, f1);
+          p{s} = __fsub_rn(p{s}, __fmul_rn(__fdiv_rn(mh, __fadd_rn(__fsqrt_rn(vh), {e_})), f2));
+          m{s} = mn; v{s} = vn; }}""")
+    src = f"""
+extern "C" __global__ void __launch_bounds__(256) {KNAME}{SIG_ALIAS} {{
+    const unsigned i = blockIdx.x * 256u + threadIdx.x;
+    if (i >= {nv}u) return;
+    {VT} p = reinterpret_cast<{VT}*>(p0)[i];
+    const {VT} g = reinterpret_cast<const {VT}*>(p1)[i];
+    {VT} m = reinterpret_cast<{VT}*>(p2)[i];
+    {VT} v = reinterpret_cast<{VT}*>(p3)[i];
+    {''.join(body)}
+    reinterpret_cast<{VT}*>(p0)[i] = p;
+    reinterpret_cast<{VT}*>(p2)[i] = m;
+    reinterpret_cast<{VT}*>(p3)[i] = v;
+}}
+"""
+    return Kernel("adam", src, (_cdiv(nv, 256), 1, 1), (256, 1, 1), 0, 0)
+
+
+@cache
+def sgd_step(numel: int, aligned: bool = True) -> Kernel:
+    """In-place p = p - lr*g (dlgrad/nn/optim.py:44: `param - self.lr * grad`, MUL then SUB).
+    p0 = param, p1 = grad, f0 = lr."""
+    V = 4 if (aligned and numel % 4 == 0) else 1
+    nv = numel // V
+    VT = "float4" if V == 4 else "float"
+    comps = ["x", "y", "z", "w"] if V == 4 else [""]
+    body = " ".join(f"p.{c} = __fsub_rn(p.{c}, __fmul_rn(f0, g.{c}));" if c else "p = __fsub_rn(p, __fmul_rn(f0, g));"
+                    for c in comps)
+    src = f"""
+extern "C" __global__ void __launch_bounds__(256) {KNAME}{SIG_ALIAS} {{
+    const unsigned i = blockIdx.x * 256u + threadIdx.x;
+    if (i >= {nv}u) return;
+    {VT} p = reinterpret_cast<{VT}*>(p0)[i];
+    const {VT} g = reinterpret_cast<const {VT}*>(p1)[i];
+    {body}
+    reinterpret_cast<{VT}*>(p0)[i] = p;
+}}
+"""
+    return Kernel("sgd", src, (_cdiv(nv, 256), 1, 1), (256, 1, 1), 0, 0)

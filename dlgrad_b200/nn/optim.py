@@ -1,0 +1,89 @@
+"""Optimizers (dlgrad/nn/optim.py:4-70).  Same constructor arguments and update rules; on CUDA each
+parameter is updated by ONE fused in-place kernel (codegen/cuda_kernel.adam_step / sgd_step) instead
+of the reference's chain of ~14 (Adam) or 2 (SGD) elementwise dispatches per parameter, each of
+which allocates a fresh tensor.  The per-element float32 operation sequence is the reference's.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from dlgrad_b200.buffer import Buffer
+from dlgrad_b200.device import Device
+from dlgrad_b200.dispatch import dispatcher
+from dlgrad_b200.helpers import CustomOps
+from dlgrad_b200.tensor import Tensor
+
+_f32 = np.float32
+
+
+class Optimizer:
+    def __init__(self, params: list[Tensor], lr: float = 1e-1) -> None:
+        self.params = params
+        self.lr = lr
+
+    def _device_for(self, *bufs: Buffer) -> Device:
+        return Buffer._route(*bufs)
+
+    def step(self) -> None:
+        for p in self.params:
+            if p.grad is None:
+                continue
+            assert p.shape == p.grad.shape, (
+                f"The shape of the parameter {p.shape} and its grad {p.grad.shape} do not match")
+            dev = self._device_for(p.data, p.grad.data)
+            dispatcher.dispatch(op=CustomOps.SGD_STEP, device=dev, param=p.data, grad=p.grad.data,
+                                lr=float(_f32(self.lr)))
+
+    def zero_grad(self) -> None:
+        for p in self.params:
+            p.grad = None
+
+
+class SGD(Optimizer):
+    def __init__(self, params: list[Tensor], lr: float = 1e-3, momentum: float = 0.0) -> None:
+        super().__init__(params, lr)
+        self.momentum = momentum
+        if momentum != 0:
+            # the reference's momentum branch raises TypeError (float * Tensor without __rmul__,
+            # dlgrad/nn/optim.py:40); velocity = momentum*velocity + grad is what it spells
+            self.velocities = {id(p): Tensor.zeros_like(p) for p in params}
+
+    def step(self) -> None:
+        if self.momentum == 0:
+            return super().step()
+        for p in self.params:
+            if p.grad is None:
+                continue
+            v = (self.velocities[id(p)] * self.momentum + p.grad).detach()
+            self.velocities[id(p)] = v
+            dev = self._device_for(p.data, v.data)
+            dispatcher.dispatch(op=CustomOps.SGD_STEP, device=dev, param=p.data, grad=v.data,
+                                lr=float(_f32(self.lr)))
+
+
+class Adam(Optimizer):
+    def __init__(self, params: list[Tensor], lr: float = 1e-3, betas: tuple[float, float] = (0.9, 0.999),
+                 eps: float = 1e-8) -> None:
+        self.params = params
+        self.lr = lr
+        self.beta1, self.beta2 = betas
+        self.eps = eps
+        self.t = 0
+        self.m = {id(p): Tensor.zeros_like(p) for p in params}
+        self.v = {id(p): Tensor.zeros_like(p) for p in params}
+
+    def step(self) -> None:
+        self.t += 1
+        # python-double scalars rounded to float32 once, exactly where the reference wraps them in a
+        # 0-d Tensor (dlgrad/nn/optim.py:64-69)
+        bc1 = float(_f32(1.0 - self.beta1 ** self.t))
+        bc2 = float(_f32(1.0 - self.beta2 ** self.t))
+        lr = float(_f32(self.lr))
+        b1, b2, eps = self.beta1, self.beta2, self.eps     # rounded to float32 inside the kernel generator
+        for p in self.params:
+            if p.grad is None:
+                continue
+            m, v = self.m[id(p)], self.v[id(p)]
+            dev = self._device_for(p.data, p.grad.data, m.data, v.data)
+            dispatcher.dispatch(op=CustomOps.ADAM_STEP, device=dev, param=p.data, grad=p.grad.data,
+                                m=m.data, v=v.data, beta1=b1, beta2=b2, eps=eps, bc1=bc1, bc2=bc2, lr=lr)

@@ -1,0 +1,422 @@
+"""Differentiable ops: forward/backward in Buffer algebra (class names follow dlgrad/ops.py so code
+that names `ops.Add`, `ops.MatMul`, ... keeps working).
+
+The gradient formulas are the reference's; where the CUDA backend has a fused kernel the op calls
+it (softmax / log-softmax, cross-entropy gradient, transposed matmuls in MatMul.backward) instead of
+composing primitives.  Reference behaviours that look like bugs but define the oracle's numbers are
+kept and marked QUIRK:
+  * Mean.backward multiplies by Buffer.full(1/N), and `full` truncates to int -> zeros;
+  * CrossEntropy.forward returns the SUM of the per-row NLL while backward divides by N.
+"""
+from __future__ import annotations
+
+from dlgrad_b200.buffer import Buffer
+from dlgrad_b200.device import Device
+from dlgrad_b200.dispatch import dispatcher
+from dlgrad_b200.dtype import Scalar
+from dlgrad_b200.helpers import CustomOps, UnaryOps, broadcast_shapes, check_broadcast
+from dlgrad_b200.tensor import OP
+
+
+def _expand_dims(g: Buffer, dim: int, keepdim: bool) -> Buffer:
+    """View of a reduced gradient with the reduced axis restored as size 1 (the reference edits the
+    incoming Buffer's metadata in place, dlgrad/ops.py:69-71; a reshaped view leaves it alone)."""
+    if keepdim:
+        return g
+    shp = list(g.shape)
+    shp.insert(0 if dim == -1 else dim, 1)
+    return g.reshape(tuple(shp))
+
+
+def unbroadcast(grad: Buffer, original_shape: tuple) -> Buffer:
+    """Sum a gradient back to the shape of a broadcast operand (dlgrad/ops.py:287-295 and
+    OP.reduce_grad_for_broadcasting, dlgrad/tensor.py:35-54)."""
+    while grad.ndim > len(original_shape):
+        grad = grad.sum(0, keepdim=False)
+    for i, (gd, od) in enumerate(zip(grad.shape, original_shape)):
+        if od == 1 and gd > 1:
+            grad = grad.sum(i, keepdim=True)
+    return grad
+
+
+# ------------------------------------------------------------------ shape ops
+class Reshape(OP):
+    def forward(self, x: Buffer, shape: tuple) -> Buffer:
+        self.input_shape = x.shape
+        return x.reshape(shape)
+
+    def backward(self, upstream_grad: Buffer) -> tuple[Buffer]:
+        return (upstream_grad.reshape(self.input_shape),)
+
+
+class Permute(OP):
+    def forward(self, x: Buffer, order: tuple) -> Buffer:
+        self.order = tuple(order)
+        return x.permute(self.order)
+
+    def backward(self, upstream_grad: Buffer) -> tuple[Buffer]:
+        inverse = [0] * len(self.order)
+        for dst, src in enumerate(self.order):
+            inverse[src] = dst
+        return (upstream_grad.permute(tuple(inverse)),)
+
+
+class Transpose(OP):
+    def forward(self, x: Buffer, dim0: int, dim1: int) -> Buffer:
+        self.dims = (dim0, dim1)
+        return x.transpose(dim0, dim1)
+
+    def backward(self, upstream_grad: Buffer) -> tuple[Buffer]:
+        return (upstream_grad.transpose(self.dims[1], self.dims[0]),)
+
+
+class Squeeze(OP):
+    def forward(self, x: Buffer, dim: list[int] | int) -> Buffer:
+        self.dim = dim
+        x.squeeze(dim)
+        return x
+
+    def backward(self, grad_output: Buffer) -> tuple[Buffer]:
+        grad_output.unsqueeze(self.dim)
+        return (grad_output,)
+
+
+class Unsqueeze(OP):
+    def forward(self, x: Buffer, dim: list[int] | int) -> Buffer:
+        self.dim = dim
+        x.unsqueeze(dim)
+        return x
+
+    def backward(self, grad_output: Buffer) -> tuple[Buffer]:
+        grad_output.squeeze(self.dim)
+        return (grad_output,)
+
+
+# ------------------------------------------------------------------ reductions
+class Sum(OP):
+    def forward(self, x: Buffer, dim: int = -1, keepdim: bool = False) -> Buffer:
+        self.inp_shape, self.device, self.dtype = x.shape, x.device, x.dtype
+        self.dim, self.keepdim = dim, keepdim
+        return x.sum(dim=dim, keepdim=keepdim)
+
+    def backward(self, upstream_grad: Buffer) -> tuple[Buffer]:
+        ones = Buffer.full(shape=self.inp_shape, fill_value=1.0, device=self.device, dtype=self.dtype)
+        return (ones * _expand_dims(upstream_grad, self.dim, self.keepdim),)
+
+
+class Mean(OP):
+    def forward(self, x: Buffer, dim: int = -1, keepdim: bool = False) -> Buffer:
+        self.inp_shape, self.device, self.dtype = x.shape, x.device, x.dtype
+        self.dim, self.keepdim = dim, keepdim
+        self.N = x.numel if dim == -1 else x.shape[dim]
+        return x.mean(dim=dim, keepdim=keepdim)
+
+    def backward(self, upstream_grad: Buffer) -> tuple[Buffer]:
+        # QUIRK: full() truncates 1/N to int(0) (dlgrad/ops.py:86-91 + dlgrad/runtime/cpu.py:252),
+        # so the reference's mean gradient is all zeros.  Kept: it defines RMSNorm's input gradient.
+        scale = Buffer.full(self.inp_shape, fill_value=1.0 / self.N, device=self.device, dtype=self.dtype)
+        return (scale * _expand_dims(upstream_grad, self.dim, self.keepdim),)
+
+
+class Max(OP):
+    def forward(self, x: Buffer, dim: int = -1, keepdim: bool = False) -> Buffer:
+        self.x, self.dim, self.keepdim = x, dim, keepdim
+        self.out = x.max(dim=dim, keepdim=keepdim)
+        return self.out
+
+    def backward(self, upstream_grad: Buffer) -> tuple[Buffer]:
+        is_max = self.x == _expand_dims(self.out, self.dim, self.keepdim)
+        return (is_max * _expand_dims(upstream_grad, self.dim, self.keepdim),)
+
+
+# ------------------------------------------------------------------ unary
+class Pow(OP):
+    def forward(self, x: Buffer, y: float) -> Buffer:
+        self.x, self.y = x, y
+        return x ** y
+
+    def backward(self, upstream_grad: Buffer) -> tuple[Buffer]:
+        return (upstream_grad * ((self.x ** (self.y - 1.0)) * self.y),)
+
+
+class Exp(OP):
+    def forward(self, x: Buffer) -> Buffer:
+        self.out = x.exp()
+        return self.out
+
+    def backward(self, upstream_grad: Buffer) -> tuple[Buffer]:
+        return (upstream_grad * self.out,)
+
+
+class Log(OP):
+    def forward(self, x: Buffer) -> Buffer:
+        self.x = x
+        return x.log()
+
+    def backward(self, upstream_grad: Buffer) -> tuple[Buffer]:
+        return (upstream_grad / self.x,)
+
+
+class Sqrt(OP):
+    def forward(self, x: Buffer) -> Buffer:
+        self.out = x.sqrt()
+        return self.out
+
+    def backward(self, grad_output: Buffer) -> tuple[Buffer]:
+        return (grad_output / (self.out * 2.0),)
+
+
+class RSqrt(OP):
+    def forward(self, x: Buffer) -> Buffer:
+        self.out = x.rsqrt()
+        return self.out
+
+    def backward(self, grad_output: Buffer) -> tuple[Buffer]:
+        return (grad_output * ((self.out ** 3) * -0.5),)
+
+
+class Relu(OP):
+    def forward(self, x: Buffer) -> Buffer:
+        self.out = x.relu()
+        return self.out
+
+    def backward(self, upstream_grad: Buffer) -> tuple[Buffer]:
+        return (self.out.where(inp=1.0, other=0.0) * upstream_grad,)
+
+
+class LeakyRelu(OP):
+    def forward(self, x: Buffer, neg_slope: Scalar = 0.01) -> Buffer:
+        self.neg_slope = neg_slope
+        self.out = x.leaky_relu(neg_slope=neg_slope)
+        return self.out
+
+    def backward(self, upstream_grad: Buffer) -> tuple[Buffer]:
+        return (self.out.where(inp=1.0, other=self.neg_slope) * upstream_grad,)
+
+
+class Sigmoid(OP):
+    def forward(self, x: Buffer) -> Buffer:
+        self.out = x.sigmoid()
+        return self.out
+
+    def backward(self, upstream_grad: Buffer) -> tuple[Buffer]:
+        return ((self.out * -(self.out - 1.0)) * upstream_grad,)
+
+
+class Tanh(OP):
+    def forward(self, x: Buffer) -> Buffer:
+        self.out = x.tanh()
+        return self.out
+
+    def backward(self, upstream_grad: Buffer) -> tuple[Buffer]:
+        one = Buffer.full(self.out.shape, 1.0, self.out.device, self.out.dtype)
+        return ((one - self.out ** 2) * upstream_grad,)
+
+
+class Clamp(OP):
+    def forward(self, x: Buffer, min: int | None, max: int | None) -> Buffer:  # noqa: A002
+        self.min, self.max = min, max
+        return x.clamp(min, max)
+
+    def backward(self, grad_output: Buffer) -> tuple[Buffer]:
+        # the reference clamps the gradient itself (dlgrad/ops.py:201-202); kept
+        return (grad_output.clamp(self.min, self.max),)
+
+
+class Softmax(OP):
+    """Tensor.softmax as one node (fused kernel on CUDA).  The reference builds it from
+    max/sub/exp/sum/div nodes (dlgrad/tensor.py:634-649); value and gradient are the same function."""
+    def forward(self, x: Buffer, dim: int) -> Buffer:
+        self.dim = dim
+        self.out = x.softmax(dim)
+        return self.out
+
+    def backward(self, upstream_grad: Buffer) -> tuple[Buffer]:
+        dev = Buffer._route(self.out, upstream_grad)
+        g = dispatcher.dispatch(op=UnaryOps.SOFTMAX_BACKWARD, device=dev, y=self.out, grad=upstream_grad, dim=self.dim)
+        return (Buffer(g, self.out.shape, dev, self.out.dtype),)
+
+
+class LogSoftmax(OP):
+    def forward(self, x: Buffer, dim: int) -> Buffer:
+        self.dim = dim
+        self.out = x.log_softmax(dim)
+        return self.out
+
+    def backward(self, upstream_grad: Buffer) -> tuple[Buffer]:
+        dev = Buffer._route(self.out, upstream_grad)
+        g = dispatcher.dispatch(op=UnaryOps.LOG_SOFTMAX_BACKWARD, device=dev, y=self.out, grad=upstream_grad,
+                                dim=self.dim)
+        return (Buffer(g, self.out.shape, dev, self.out.dtype),)
+
+
+# ------------------------------------------------------------------ binary
+class Add(OP):
+    def forward(self, x: Buffer, y: Buffer) -> Buffer:
+        self.xs, self.ys = x.shape, y.shape
+        check_broadcast(x.shape, y.shape)
+        return x + y
+
+    def backward(self, upstream_grad: Buffer) -> tuple[Buffer | None, Buffer | None]:
+        gx = unbroadcast(upstream_grad, self.xs) if self.req_grad[0] else None
+        gy = unbroadcast(upstream_grad, self.ys) if self.req_grad[1] else None
+        return gx, gy
+
+
+class Sub(OP):
+    def forward(self, x: Buffer, y: Buffer) -> Buffer:
+        self.xs, self.ys = x.shape, y.shape
+        check_broadcast(x.shape, y.shape)
+        return x - y
+
+    def backward(self, upstream_grad: Buffer) -> tuple[Buffer | None, Buffer | None]:
+        gx = unbroadcast(upstream_grad, self.xs) if self.req_grad[0] else None
+        gy = unbroadcast(-upstream_grad, self.ys) if self.req_grad[1] else None
+        return gx, gy
+
+
+class Mul(OP):
+    def forward(self, x: Buffer, y: Buffer) -> Buffer:
+        self.x, self.y = x, y
+        check_broadcast(x.shape, y.shape)
+        return x * y
+
+    def backward(self, upstream_grad: Buffer) -> tuple[Buffer | None, Buffer | None]:
+        gx = unbroadcast(upstream_grad * self.y, self.x.shape) if self.req_grad[0] else None
+        gy = unbroadcast(upstream_grad * self.x, self.y.shape) if self.req_grad[1] else None
+        return gx, gy
+
+
+class Div(OP):
+    def forward(self, x: Buffer, y: Buffer) -> Buffer:
+        self.x, self.y = x, y
+        check_broadcast(x.shape, y.shape)
+        return x / y
+
+    def backward(self, upstream_grad: Buffer) -> tuple[Buffer | None, Buffer | None]:
+        gx = unbroadcast(upstream_grad / self.y, self.x.shape) if self.req_grad[0] else None
+        gy = (unbroadcast((-upstream_grad * self.x) / self.y ** 2, self.y.shape)
+              if self.req_grad[1] else None)
+        return gx, gy
+
+
+class MatMul(OP):
+    def forward(self, x: Buffer, y: Buffer) -> Buffer:
+        self.p1, self.p2, self.out_shape = broadcast_shapes(x.shape, y.shape)
+        self.x, self.y = x, y
+        return x @ y
+
+    def backward(self, upstream_grad: Buffer) -> tuple[Buffer | None, Buffer | None]:
+        g = upstream_grad if upstream_grad.shape == self.out_shape else upstream_grad.reshape(self.out_shape)
+        xr, yr = self.x.reshape(self.p1), self.y.reshape(self.p2)
+        dev = Buffer._route(g, xr, yr)
+        if dev is Device.CUDA:
+            # CUDA: dX = g @ Y^T and dY = X^T @ g read the stored operands transposed inside the
+            # kernel; the reference materialises both transposes first (dlgrad/ops.py:319-327).
+            from dlgrad_b200.helpers import BinaryOps
+            gx = gy = None
+            if self.req_grad[0]:
+                gx = Buffer(dispatcher.dispatch(op=BinaryOps.MATMUL, device=dev, x=g, y=yr, trans_y=True),
+                            self.out_shape[:-2] + (self.p1[-2], self.p1[-1]), dev, g.dtype)
+                gx = unbroadcast(gx, self.x.shape)
+            if self.req_grad[1]:
+                gy = Buffer(dispatcher.dispatch(op=BinaryOps.MATMUL, device=dev, x=xr, y=g, trans_x=True),
+                            self.out_shape[:-2] + (self.p2[-2], self.p2[-1]), dev, g.dtype)
+                gy = unbroadcast(gy, self.y.shape)
+            return gx, gy
+        nd = xr.ndim
+        gx = unbroadcast(g @ yr.transpose(nd - 2, nd - 1), self.x.shape)
+        gy = unbroadcast(xr.transpose(nd - 2, nd - 1) @ g, self.y.shape)
+        return gx, gy
+
+
+# ------------------------------------------------------------------ losses
+class CrossEntropy(OP):
+    def forward(self, logits: Buffer, target: Buffer, dim: int = 1) -> Buffer:
+        assert logits.shape[0] == target.shape[0]
+        self.target = target
+        self.log_softmax = logits.log_softmax(dim)          # kept for backward, (N, V)
+        picked = Buffer.ce_forward(self.log_softmax, self.target)
+        self.N = float(logits.shape[0])
+        # QUIRK: sum, not mean (dlgrad/ops.py:357) — the printed loss is N x the per-row loss
+        return -picked.sum()
+
+    def backward(self, upstream_grad: Buffer) -> tuple[Buffer]:
+        ls = self.log_softmax
+        dev = Buffer._route(ls, self.target, upstream_grad)
+        g = dispatcher.dispatch(op=CustomOps.CE_GRAD, device=dev, logsm=ls, target=self.target,
+                                upstream=upstream_grad, n=self.N)
+        return (Buffer(g, ls.shape, dev, ls.dtype),)
+
+
+class BCEWithLogitsLoss(OP):
+    def forward(self, probs: Buffer, target: Buffer) -> Buffer:
+        assert probs.shape == target.shape, f"shape mismatch {probs.shape} vs {target.shape}"
+        self.probs, self.target = probs, target
+        max_val = (-probs).clamp(min=0)
+        loss = ((1.0 - target) * probs) + max_val + ((-max_val).exp() + (-(probs + max_val)).exp()).log()
+        return loss.mean()
+
+    def backward(self, upstream_grad: Buffer) -> tuple[Buffer]:
+        n = float(self.probs.numel)
+        return (((self.probs.sigmoid() - self.target) * upstream_grad) / n,)
+
+
+class Embedding(OP):
+    def forward(self, weight: Buffer, idx: Buffer) -> Buffer:
+        self.weight, self.idx = weight, idx
+        return weight.embedding(idx)
+
+    def backward(self, upstream_grad: Buffer) -> tuple[Buffer]:
+        return (self.weight.embedding(self.idx, backward=True, upstream_grad=upstream_grad),)
+
+
+# ------------------------------------------------------------------ select
+class Where(OP):
+    def forward(self, cond: Buffer, inp: Buffer | Scalar, other: Buffer | Scalar) -> Buffer:
+        self.cond = cond
+        return cond.where(inp, other)
+
+    def backward(self, upstream_grad: Buffer) -> tuple:
+        return (None, self.cond.where(upstream_grad, 0.0), self.cond.where(0.0, upstream_grad))
+
+
+class MaskedFill(OP):
+    def forward(self, data: Buffer, mask: Buffer, value: Scalar) -> Buffer:
+        self.mask = mask
+        return Buffer.masked_fill(x=data, mask=mask, val=value)
+
+    def backward(self, upstream_grad: Buffer) -> tuple:
+        return (Buffer.masked_fill(x=upstream_grad, mask=self.mask, val=0.0), None, None)
+
+
+class Tril(OP):
+    def forward(self, x: Buffer, k: Buffer | int = 0) -> Buffer:
+        # 2-D only, like the reference (dlgrad/ops.py:110-126): mask = cols <= rows + k
+        h, w = x.shape[0], x.shape[1]
+        rows = Buffer.arange((h, 1), x.device)
+        cols = Buffer.arange((1, w), x.device)
+        self.mask = cols <= (rows + k)
+        return self.mask.where(x, 0.0)
+
+    def backward(self, upstream_grad: Buffer) -> tuple:
+        return (self.mask.where(upstream_grad, 0.0), None)
+
+
+class Dropout(OP):
+    def forward(self, x: Buffer, p: Scalar) -> Buffer:
+        self.p = p
+        if p == 1.0:
+            return Buffer.full(x.shape, 0.0, x.device, x.dtype)
+        if p == 0.0:
+            return x
+        self.mask = Buffer.uniform(x.shape, x.device, x.dtype, low=0.0, high=1.0) >= p
+        self.scale = 1.0 / (1.0 - p)
+        return self.mask.where(x, 0.0) * self.scale
+
+    def backward(self, upstream_grad: Buffer) -> tuple[Buffer]:
+        if self.p == 1.0:
+            return (Buffer.full(upstream_grad.shape, 0.0, upstream_grad.device, upstream_grad.dtype),)
+        if self.p == 0.0:
+            return (upstream_grad,)
+        return (self.mask.where(upstream_grad, 0.0) * self.scale,)

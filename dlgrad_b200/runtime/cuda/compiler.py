@@ -1,0 +1,168 @@
+"""nvcc driver + on-disk kernel cache for the generated CUDA C.
+
+Same idea as the reference's CPU path — hash the generated source, compile once, cache the object,
+load it on later runs (dlgrad/runtime/cpu.py:47-62: write .c, fork the compiler, sha256 key) — with
+sm_100a cubins instead of host shared objects:
+
+    source --sha256--> _kcache/<key>.cubin            (one kernel, compiled on first use)
+                  \\--> _kcache/pack_<n>.cubin + index  (many kernels, pre-built by build())
+
+The cache directory lives inside the package so pre-built cubins travel with the repo snapshot.
+"""
+from __future__ import annotations
+
+import hashlib
+import json
+import os
+import shutil
+import subprocess
+import tempfile
+from concurrent.futures import ThreadPoolExecutor
+
+from dlgrad_b200.helpers import CACHE_DIR
+from dlgrad_b200.runtime.cuda import shim
+
+NVCC = os.environ.get("DLGRAD_NVCC") or shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-cubin", "-O3", "-lineinfo", "-std=c++17",
+              "-Xptxas", "-warn-spills"]
+_FLAG_TAG = " ".join(NVCC_FLAGS)
+
+KNAME = "DLG_KERNEL_NAME"     # placeholder the code generator puts where the function name goes
+
+_index: dict[str, list[str]] | None = None      # key -> [cubin file name, function name]
+_modules: dict[str, object] = {}                # cubin path -> CUmodule handle
+_functions: dict[str, object] = {}              # key -> CUfunction handle
+_pending: dict[str, tuple[str, str]] = {}       # compile-only mode: key -> (fname, source)
+
+
+def _index_path() -> str:
+    return os.path.join(CACHE_DIR, "index.json")
+
+
+def _load_index() -> dict:
+    global _index
+    if _index is None:
+        try:
+            with open(_index_path()) as f:
+                _index = json.load(f)
+        except (OSError, ValueError):
+            _index = {}
+    return _index
+
+
+def source_key(src: str) -> str:
+    return hashlib.sha256((_FLAG_TAG + "\n" + src).encode()).hexdigest()[:32]
+
+
+def _run_nvcc(cu_path: str, out_path: str) -> None:
+    cmd = [NVCC, *NVCC_FLAGS, "-o", out_path, cu_path]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError(f"Compilation failed ({' '.join(cmd)}):\n{res.stderr}\n--- source: {cu_path}")
+    if "spill" in res.stderr and "0 bytes spill" not in res.stderr:
+        # not fatal, but never silent
+        print(f"[dlgrad_b200] nvcc reported spills for {cu_path}:\n{res.stderr}")
+
+
+def _compile_single(key: str, fname: str, src: str) -> str:
+    os.makedirs(CACHE_DIR, exist_ok=True)
+    out = os.path.join(CACHE_DIR, f"{key}.cubin")
+    tmpdir = tempfile.mkdtemp(prefix="dlgk_")
+    try:
+        cu = os.path.join(tmpdir, f"{fname}.cu")
+        with open(cu, "w") as f:
+            f.write(src.replace(KNAME, fname))
+        tmp_out = os.path.join(tmpdir, "k.cubin")
+        _run_nvcc(cu, tmp_out)
+        shutil.move(tmp_out, out)
+    finally:
+        if not os.environ.get("DLGRAD_KEEP_SRC"):
+            shutil.rmtree(tmpdir, ignore_errors=True)
+    return out
+
+
+def _module(path: str):
+    m = _modules.get(path)
+    if m is None:
+        out = shim.ffi.new("void **")
+        shim.check(shim.lib.dlg_module_load(path.encode(), out), f"dlg_module_load({path})")
+        m = _modules[path] = out[0]
+    return m
+
+
+def get_function(base: str, src: str):
+    """Return the CUfunction for generated source `src` (function name placeholder = KNAME)."""
+    key = source_key(src)
+    fn = _functions.get(key)
+    if fn is not None:
+        return fn
+    fname = f"{base}_{key[:12]}"
+    idx = _load_index()
+    path = None
+    if key in idx:
+        cand = os.path.join(CACHE_DIR, idx[key][0])
+        if os.path.exists(cand):
+            path, fname = cand, idx[key][1]
+    if path is None:
+        cand = os.path.join(CACHE_DIR, f"{key}.cubin")
+        if os.path.exists(cand):
+            path = cand
+    if path is None:
+        if shim.COMPILE_ONLY:
+            _pending[key] = (fname, src)
+            _functions[key] = shim.ffi.cast("void *", 1)
+            return _functions[key]
+        path = _compile_single(key, fname, src)
+    if shim.COMPILE_ONLY:
+        fn = shim.ffi.cast("void *", 1)
+    else:
+        out = shim.ffi.new("void **")
+        shim.check(shim.lib.dlg_module_get(_module(path), fname.encode(), out), f"dlg_module_get({fname})")
+        fn = out[0]
+    _functions[key] = fn
+    return fn
+
+
+def flush_pending(jobs: int | None = None, pack_size: int = 24) -> int:
+    """Compile everything recorded in compile-only mode into pack cubins (parallel nvcc)."""
+    global _index
+    if not _pending:
+        return 0
+    os.makedirs(CACHE_DIR, exist_ok=True)
+    idx = _load_index()
+    items = sorted(_pending.items())
+    packs = [items[i:i + pack_size] for i in range(0, len(items), pack_size)]
+    jobs = jobs or min(len(packs), os.cpu_count() or 4)
+
+    def build(pack):
+        h = hashlib.sha256("".join(k for k, _ in pack).encode()).hexdigest()[:16]
+        name = f"pack_{h}.cubin"
+        tmpdir = tempfile.mkdtemp(prefix="dlgp_")
+        try:
+            cu = os.path.join(tmpdir, "pack.cu")
+            with open(cu, "w") as f:
+                for key, (fname, src) in pack:
+                    # each kernel in its own namespace so file-local helpers/constants cannot collide
+                    body = src.replace(KNAME, fname)
+                    f.write(f"// ---- {fname}\nnamespace ns_{fname} {{\n{body}\n}}\n")
+            out = os.path.join(tmpdir, name)
+            _run_nvcc(cu, out)
+            shutil.move(out, os.path.join(CACHE_DIR, name))
+        finally:
+            shutil.rmtree(tmpdir, ignore_errors=True)
+        return name, pack
+
+    with ThreadPoolExecutor(max_workers=jobs) as ex:
+        for name, pack in ex.map(build, packs):
+            for key, (fname, _src) in pack:
+                idx[key] = [name, fname]
+    with open(_index_path() + ".tmp", "w") as f:
+        json.dump(idx, f, indent=0, sort_keys=True)
+    os.replace(_index_path() + ".tmp", _index_path())
+    n = len(_pending)
+    _pending.clear()
+    return n
+
+
+def pending_count() -> int:
+    return len(_pending)

@@ -1,0 +1,62 @@
+"""MATMUL on Device.CUDA: picks between the tcgen05/TMEM/TMA 3xTF32 kernel (codegen/cuda_tcgen05.py)
+and the exact-fp32 SIMT kernel (codegen/cuda_kernel.matmul_simt) per shape.
+
+Operands arrive rank-aligned (2-D, 3-D or 4-D, dlgrad/buffer.py:234-235); leading dims of size 1
+broadcast against the other operand exactly as the reference zeroes the batch stride
+(dlgrad/runtime/cpu.py:507-575).  `trans_x` / `trans_y` are an extension of the CUDA backend used by
+MatMul.backward so that g @ B^T and A^T @ g need no materialised transpose.
+"""
+from __future__ import annotations
+
+import os
+
+from dlgrad_b200.buffer import Buffer
+from dlgrad_b200.codegen import cuda_kernel as ck
+from dlgrad_b200.helpers import prod_
+from dlgrad_b200.runtime.cuda import ops as _ops
+
+_plans: dict = {}
+FORCE_SIMT = os.environ.get("DLGRAD_MATMUL", "").lower() == "simt"
+
+
+def _geometry(xs: tuple, ys: tuple, tx: bool, ty: bool):
+    nd = len(xs)
+    bx, by = xs[:-2], ys[:-2]
+    M, K = (xs[-1], xs[-2]) if tx else (xs[-2], xs[-1])
+    K2, N = (ys[-1], ys[-2]) if ty else (ys[-2], ys[-1])
+    if K != K2:
+        raise ValueError(f"Matrix inner dims must match: {xs} and {ys}")
+    batch = tuple(max(a, b) for a, b in zip(bx, by))
+    for a, b in zip(bx, by):
+        if a != b and 1 not in (a, b):
+            raise ValueError(f"Cannot broadcast batch dims: {xs} and {ys}")
+    batch = (1,) * (2 - len(batch)) + batch
+    mat_x, mat_y = xs[-1] * xs[-2], ys[-1] * ys[-2]
+
+    def bstrides(b, mat):
+        b = (1,) * (2 - len(b)) + tuple(b)
+        s1 = mat if b[1] > 1 else 0
+        s0 = mat * b[1] if b[0] > 1 else 0
+        return (s0 if batch[0] > 1 else 0, s1 if batch[1] > 1 else 0)
+    return M, N, K, batch, bstrides(bx, mat_x), bstrides(by, mat_y), nd
+
+
+def run_matmul(x: Buffer, y: Buffer, trans_x: bool = False, trans_y: bool = False):
+    key = (x.metadata.shape, y.metadata.shape, trans_x, trans_y, x.aligned and y.aligned)
+    plan = _plans.get(key)
+    if plan is None:
+        plan = _plans[key] = _build(x.metadata.shape, y.metadata.shape, trans_x, trans_y,
+                                    x.aligned and y.aligned)
+    return plan(_ops._dev_ptr(x), _ops._dev_ptr(y))
+
+
+def _build(xs, ys, tx, ty, aligned):
+    M, N, K, batch, a_bs, b_bs, _ = _geometry(xs, ys, tx, ty)
+    if not FORCE_SIMT:
+        from dlgrad_b200.runtime.cuda import matmul_tc
+        tc = matmul_tc.try_build(M, N, K, batch, a_bs, b_bs, tx, ty, aligned)
+        if tc is not None:
+            return tc
+    k = ck.matmul_simt(M, N, K, batch[0], batch[1], a_bs, b_bs, tx, ty, aligned)
+    p = _ops.Plan(k, prod_(batch) * M * N)
+    return lambda a, b: p.run(a, b)

@@ -1,0 +1,543 @@
+"""Device.CUDA runtime: the functions registered with the dispatcher for every (op, Device.CUDA).
+
+Keyword names and return convention are the reference's (dlgrad/runtime/cpu.py): each
+function takes Buffers (+ python scalars / tuples) and returns a raw `float *` cdata that owns
+freshly allocated, contiguous storage (here: device memory, released to the caching allocator by
+`ffi.gc(ptr, dlg_free)`).
+
+Per (op, shape) the first call generates + compiles a shape-specialised kernel and freezes a launch
+plan in the shim; later calls are one dict lookup and one FFI call (`dlg_plan_run` = allocate
+output + launch).  No `os.path.exists`, no `ffi.new` per call — the reference spends 20-50 µs of
+Python per dispatch there.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from dlgrad_b200.buffer import Buffer
+from dlgrad_b200.codegen import cuda_kernel as ck
+from dlgrad_b200.device import Device
+from dlgrad_b200.dispatch import dispatcher
+from dlgrad_b200.dtype import CDataPtr, Scalar
+from dlgrad_b200.helpers import (
+    BinaryOps,
+    BufferOps,
+    CustomOps,
+    UnaryOps,
+    calculate_stride,
+    get_broadcast_shape,
+    get_broadcast_strides_2,
+    prod_,
+)
+from dlgrad_b200.runtime.cuda import compiler, shim, transfer
+
+ffi, lib, NULL = shim.ffi, shim.lib, shim.NULL
+_own = shim.own
+CUDA = Device.CUDA
+_plans: dict = {}
+_rng = np.random.default_rng()
+
+
+def manual_seed(seed: int) -> None:
+    """Seed Tensor.uniform/rand on this backend (the reference reseeds from /dev/random on every
+    call, dlgrad/codegen/cpu_kernel.py:774-874, and cannot be made reproducible)."""
+    global _rng
+    _rng = np.random.default_rng(seed)
+
+
+class Plan:
+    __slots__ = ("c", "nbytes", "kernel")
+
+    def __init__(self, kernel: ck.Kernel, out_elems: int | None = None, cluster: int = 1) -> None:
+        shim.init()
+        fn = compiler.get_function(kernel.name, kernel.source)
+        n = kernel.out_elems if out_elems is None else out_elems
+        self.nbytes = n * 4
+        self.kernel = kernel
+        self.c = lib.dlg_plan_create(fn, *kernel.grid, *kernel.block, kernel.smem, self.nbytes,
+                                     int(kernel.zero_out), cluster)
+        if self.c == NULL:
+            raise RuntimeError("dlg_plan_create failed: " + shim.last_error())
+
+    def run(self, p0=NULL, p1=NULL, p2=NULL, p3=NULL, f0=0.0, f1=0.0, f2=0.0, f3=0.0) -> CDataPtr:
+        out = lib.dlg_plan_run(self.c, p0, p1, p2, p3, f0, f1, f2, f3)
+        if out == NULL:
+            raise RuntimeError("kernel launch failed: " + shim.last_error())
+        return _own(out, self.nbytes)
+
+    def run_into(self, out, p0=NULL, p1=NULL, p2=NULL, p3=NULL, f0=0.0, f1=0.0, f2=0.0, f3=0.0) -> None:
+        if lib.dlg_plan_run_into(self.c, out, p0, p1, p2, p3, f0, f1, f2, f3) != 0:
+            raise RuntimeError("kernel launch failed: " + shim.last_error())
+
+
+def _dev_ptr(b: Buffer):
+    """Device pointer of a Buffer operand (host buffers are migrated by Buffer._route before we get
+    here; this catches direct dispatcher users)."""
+    if b.metadata.device is not CUDA:
+        b._to_cuda()
+    return b.ptr
+
+
+# ------------------------------------------------------------------------------------------------
+# binary elementwise (ADD/SUB/MUL/DIV/EQT/GT/GTE/CMP)        reference: cpu.py:257-311,784-791,835-862,906
+# ------------------------------------------------------------------------------------------------
+def _binary(name: str, x: Buffer, y: Buffer, out_shape: tuple | None = None) -> CDataPtr:
+    xs, ys = x.scalar, y.scalar
+    key = ("bin", name, x.metadata.shape, y.metadata.shape, xs is None, ys is None,
+           x.aligned and y.aligned, out_shape)
+    ent = _plans.get(key)
+    if ent is None:
+        if xs is not None and ys is not None:
+            # scalar (op) scalar: give x real storage and fall through
+            return _binary(name, x._materialized(), y, out_shape)
+        oshape = out_shape or get_broadcast_shape(x.metadata.shape, y.metadata.shape)
+        strides, names = [], []
+        for b, sc, slot in ((x, xs, "f0"), (y, ys, "f1")):
+            if sc is None:
+                names.append(f"v{len(strides)}")
+                strides.append(get_broadcast_strides_2(oshape, b.metadata.shape, calculate_stride(b.metadata.shape)))
+            else:
+                names.append(slot)
+        k = ck.ewise(ck.BINARY_EXPR[name].format(a=names[0], b=names[1]), tuple(oshape), tuple(strides),
+                     x.aligned and y.aligned, name)
+        mode = 0 if (xs is None and ys is None) else (1 if ys is not None else 2)
+        ent = _plans[key] = (Plan(k), mode)
+    plan, mode = ent
+    if mode == 0:
+        return plan.run(_dev_ptr(x), _dev_ptr(y))
+    if mode == 1:
+        return plan.run(_dev_ptr(x), NULL, NULL, NULL, 0.0, ys)
+    return plan.run(_dev_ptr(y), NULL, NULL, NULL, xs, 0.0)
+
+
+@dispatcher.register(BinaryOps.ADD, CUDA)
+def add(x: Buffer, y: Buffer) -> CDataPtr:
+    return _binary("add", x, y)
+
+
+@dispatcher.register(BinaryOps.SUB, CUDA)
+def sub(x: Buffer, y: Buffer) -> CDataPtr:
+    return _binary("sub", x, y)
+
+
+@dispatcher.register(BinaryOps.MUL, CUDA)
+def mul(x: Buffer, y: Buffer) -> CDataPtr:
+    return _binary("mul", x, y)
+
+
+@dispatcher.register(BinaryOps.DIV, CUDA)
+def div(x: Buffer, y: Buffer) -> CDataPtr:
+    return _binary("div", x, y)
+
+
+@dispatcher.register(BinaryOps.EQT, CUDA)
+def eqt(x: Buffer, y: Buffer) -> CDataPtr:
+    return _binary("eq", x, y)
+
+
+@dispatcher.register(BinaryOps.GT, CUDA)
+def gt(x: Buffer, y: Buffer | Scalar) -> CDataPtr:
+    return _binary("gt", x, Buffer._as_buffer(y))
+
+
+@dispatcher.register(BinaryOps.GTE, CUDA)
+def gte(x: Buffer, y: Buffer | Scalar) -> CDataPtr:
+    return _binary("gte", x, Buffer._as_buffer(y))
+
+
+@dispatcher.register(BinaryOps.CMP, CUDA)
+def cmp(x: Buffer, y: Buffer, out_shape: tuple, mode: str = "<=") -> CDataPtr:
+    if mode != "<=":
+        raise NotImplementedError(f"cmp mode {mode!r}")
+    return _binary("lte", x, y, tuple(out_shape))
+
+
+# ------------------------------------------------------------------------------------------------
+# unary elementwise                                           reference: cpu.py:314-502
+# ------------------------------------------------------------------------------------------------
+def _unary(tag: str, expr: str, x: Buffer, f0: float = 0.0, f1: float = 0.0) -> CDataPtr:
+    key = ("un", tag, expr, x.metadata.numel, x.aligned)
+    plan = _plans.get(key)
+    if plan is None:
+        n = x.metadata.numel
+        plan = _plans[key] = Plan(ck.ewise(expr, (n,), ((1,),), x.aligned, tag))
+    return plan.run(_dev_ptr(x), NULL, NULL, NULL, f0, f1)
+
+
+@dispatcher.register(UnaryOps.NEG, CUDA)
+def neg(x: Buffer) -> CDataPtr:
+    return _unary("neg", ck.UNARY_EXPR["neg"], x)
+
+
+@dispatcher.register(UnaryOps.EXP, CUDA)
+def exp(x: Buffer) -> CDataPtr:
+    return _unary("exp", ck.UNARY_EXPR["exp"], x)
+
+
+@dispatcher.register(UnaryOps.LOG, CUDA)
+def log(x: Buffer) -> CDataPtr:
+    return _unary("log", ck.UNARY_EXPR["log"], x)
+
+
+@dispatcher.register(UnaryOps.SQRT, CUDA)
+def sqrt(x: Buffer) -> CDataPtr:
+    return _unary("sqrt", ck.UNARY_EXPR["sqrt"], x)
+
+
+@dispatcher.register(UnaryOps.RSQRT, CUDA)
+def rsqrt(x: Buffer) -> CDataPtr:
+    return _unary("rsqrt", ck.UNARY_EXPR["rsqrt"], x)
+
+
+@dispatcher.register(UnaryOps.POW, CUDA)
+def pow_(x: Buffer, val: Scalar) -> CDataPtr:
+    return _unary("pow", ck.pow_expr(int(val)), x)      # int(): the reference truncates, cpu.py:500
+
+
+@dispatcher.register(UnaryOps.RELU, CUDA)
+def relu(x: Buffer) -> CDataPtr:
+    return _unary("relu", "(v0 <= 0.f) ? 0.f : v0", x)   # cpu_kernel.relu, :520-533
+
+
+@dispatcher.register(UnaryOps.CLAMP, CUDA)
+def clamp(x: Buffer, min_val: Scalar | None, max_val: Scalar | None) -> CDataPtr:
+    # cpu_kernel.clamp (:321-349): `if (val < min) val = min; if (val > max) val = max;`
+    e = "v0"
+    if min_val is not None:
+        e = f"(({e}) < f0 ? f0 : ({e}))"
+    if max_val is not None:
+        e = f"(({e}) > f1 ? f1 : ({e}))"
+    return _unary("clamp", e, x, float(min_val or 0.0), float(max_val or 0.0))
+
+
+# ------------------------------------------------------------------------------------------------
+# select                                                      reference: cpu.py:794-831,865-903
+# ------------------------------------------------------------------------------------------------
+@dispatcher.register(UnaryOps.WHERE, CUDA)
+def where(cond: Buffer, x: Buffer, y: Buffer) -> CDataPtr:
+    xs, ys = x.scalar, y.scalar
+    key = ("where", cond.metadata.shape, x.metadata.shape, y.metadata.shape, xs is None, ys is None,
+           cond.aligned and x.aligned and y.aligned)
+    ent = _plans.get(key)
+    if ent is None:
+        oshape = cond.metadata.shape
+        strides = [calculate_stride(oshape)]
+        names = []
+        for b, sc, slot in ((x, xs, "f0"), (y, ys, "f1")):
+            if sc is None:
+                names.append(f"v{len(strides)}")
+                strides.append(get_broadcast_strides_2(oshape, b.metadata.shape, calculate_stride(b.metadata.shape)))
+            else:
+                names.append(slot)
+        k = ck.ewise(f"(v0 > 0.f) ? {names[0]} : {names[1]}", tuple(oshape), tuple(strides),
+                     cond.aligned and x.aligned and y.aligned, "where")
+        ent = _plans[key] = Plan(k)
+    ptrs = [_dev_ptr(cond)] + [_dev_ptr(b) for b in (x, y) if b.scalar is None]
+    while len(ptrs) < 3:
+        ptrs.append(NULL)
+    return ent.run(ptrs[0], ptrs[1], ptrs[2], NULL, xs or 0.0, ys or 0.0)
+
+
+@dispatcher.register(UnaryOps.MASKED_FILL, CUDA)
+def masked_fill(x: Buffer, mask: Buffer, val: Scalar, out_shape: tuple) -> CDataPtr:
+    key = ("mfill", x.metadata.shape, mask.metadata.shape, tuple(out_shape), x.aligned and mask.aligned)
+    plan = _plans.get(key)
+    if plan is None:
+        oshape = tuple(out_shape)
+        sx = get_broadcast_strides_2(oshape, x.metadata.shape, calculate_stride(x.metadata.shape))
+        sm = get_broadcast_strides_2(oshape, mask.metadata.shape, calculate_stride(mask.metadata.shape))
+        plan = _plans[key] = Plan(ck.ewise("(v1 > 0.f) ? f0 : v0", oshape, (sx, sm),
+                                           x.aligned and mask.aligned, "masked_fill"))
+    return plan.run(_dev_ptr(x), _dev_ptr(mask), NULL, NULL, float(val))
+
+
+# ------------------------------------------------------------------------------------------------
+# creation                                                    reference: cpu.py:194-254
+# ------------------------------------------------------------------------------------------------
+@dispatcher.register(BufferOps.FULL, CUDA)
+def full(shape: tuple, fill_value: Scalar) -> CDataPtr:
+    n = prod_(shape)
+    key = ("full", n)
+    plan = _plans.get(key)
+    if plan is None:
+        plan = _plans[key] = Plan(ck.ewise("f0", (n,), (), True, "full"))
+    # `int(fill_value)`: the reference's C kernel takes an int (cpu.py:252, cpu_kernel.py:758-770),
+    # so Tensor.full(.., 0.5) is all zeros there — and here.
+    return plan.run(NULL, NULL, NULL, NULL, float(int(fill_value)))
+
+
+@dispatcher.register(BufferOps.ARANGE, CUDA)
+def arange(shape: tuple) -> CDataPtr:
+    n = prod_(shape)
+    key = ("arange", n)
+    plan = _plans.get(key)
+    if plan is None:
+        plan = _plans[key] = Plan(ck.ewise("ei", (n,), (), True, "arange"))
+    return plan.run()
+
+
+@dispatcher.register(BufferOps.UNIFORM, CUDA)
+def uniform(shape: tuple, low: float = 0.0, high: float = 1.0) -> CDataPtr:
+    # initialisation only: generated on the host, one H2D (SURVEY §2a "init only")
+    shim.init()
+    vals = (low + (high - low) * _rng.random(prod_(shape), dtype=np.float32)).astype(np.float32)
+    return transfer.upload_numpy(vals)
+
+
+# ------------------------------------------------------------------------------------------------
+# reductions                                                  reference: cpu.py:605-761,911-959
+# ------------------------------------------------------------------------------------------------
+def _reduce(op: str, x: Buffer, dim: int) -> CDataPtr:
+    shape = x.metadata.shape
+    if dim is None:
+        dim = -1
+    if dim != -1 and dim < 0:
+        dim += len(shape)
+    key = ("red", op, shape, dim, x.aligned)
+    stages = _plans.get(key)
+    if stages is None:
+        stages = _plans[key] = _build_reduce(op, shape, dim, x.aligned)
+    ptr = _dev_ptr(x)
+    for plan in stages:
+        ptr = plan.run(ptr)
+    return ptr
+
+
+def _build_reduce(op: str, shape: tuple, dim: int, aligned: bool) -> list[Plan]:
+    numel = prod_(shape)
+    first = "sum" if op == "mean" else op
+    if dim == -1 or len(shape) == 0:
+        outer, R, inner = 1, numel, 1
+    else:
+        outer, R, inner = prod_(shape[:dim]), shape[dim], prod_(shape[dim + 1:])
+    if inner == 1:
+        if outer == 1 and R >= 65536:
+            k1 = ck.reduce_all_partial(first, R, aligned)
+            G = k1.out_elems
+            return [Plan(k1), Plan(ck.reduce_rows(op, 1, G, True, scale_R=R))]
+        return [Plan(ck.reduce_rows(op, outer, R, aligned))]
+    # strided: split R across blocks when (outer x inner) cannot occupy the chip
+    V = 4 if (aligned and inner % 4 == 0) else 1
+    blocks = -(-(inner // V) // 32) * outer
+    splits = 1
+    if blocks < 2 * ck.NUM_SMS and R >= 128:
+        splits = max(1, min(R // 64, -(-2 * ck.NUM_SMS // blocks)))
+    if splits == 1:
+        return [Plan(ck.reduce_cols(op, outer, R, inner, aligned))]
+    return [Plan(ck.reduce_cols(first, outer, R, inner, aligned, splits)),
+            Plan(ck.reduce_cols(op, 1, splits, outer * inner, True, 1, scale_R=R))]
+
+
+@dispatcher.register(UnaryOps.SUM, CUDA)
+def sum_(x: Buffer, dim: int) -> CDataPtr:
+    return _reduce("sum", x, dim)
+
+
+@dispatcher.register(UnaryOps.MEAN, CUDA)
+def mean(x: Buffer, dim: int) -> CDataPtr:
+    return _reduce("mean", x, dim)
+
+
+@dispatcher.register(UnaryOps.MAX, CUDA)
+def max_(x: Buffer, dim: int) -> CDataPtr:
+    return _reduce("max", x, dim)
+
+
+@dispatcher.register(UnaryOps.ARGMAX, CUDA)
+def argmax(x: Buffer, dim: int) -> CDataPtr:
+    rows, cols = x.metadata.shape
+    if dim is None:
+        dim = -1
+    key = ("argmax", rows, cols, dim)
+    plan = _plans.get(key)
+    if plan is None:
+        plan = _plans[key] = Plan(ck.argmax(rows, cols, dim))
+    return plan.run(_dev_ptr(x))
+
+
+# ------------------------------------------------------------------------------------------------
+# fused row ops
+# ------------------------------------------------------------------------------------------------
+def _rows_of(shape: tuple, dim: int) -> tuple[int, int] | None:
+    if dim < 0:
+        dim += len(shape)
+    if dim != len(shape) - 1:
+        return None
+    R = shape[-1]
+    if R > 65536:
+        return None
+    return prod_(shape[:-1]), R
+
+
+def _softmax_family(kind: str, x: Buffer, dim: int) -> CDataPtr:
+    rows = _rows_of(x.metadata.shape, dim)
+    if rows is None:
+        # not the last axis (or a very long row): the reference's composition
+        # (dlgrad/tensor.py:634-669) on the primitive kernels
+        mx = x.max(dim=dim, keepdim=True)
+        sh = x - mx
+        e = sh.exp()
+        s = e.sum(dim=dim, keepdim=True)
+        return (e / s).ptr if kind == "softmax" else (sh - s.log()).ptr
+    key = (kind, rows, x.aligned)
+    plan = _plans.get(key)
+    if plan is None:
+        plan = _plans[key] = Plan(ck.softmax_rows(kind, rows[0], rows[1], x.aligned))
+    return plan.run(_dev_ptr(x))
+
+
+def _softmax_bwd_family(kind: str, y: Buffer, grad: Buffer, dim: int) -> CDataPtr:
+    rows = _rows_of(y.metadata.shape, dim)
+    if rows is None:
+        if kind == "softmax":
+            return (y * (grad - (grad * y).sum(dim=dim, keepdim=True))).ptr
+        return (grad - y.exp() * grad.sum(dim=dim, keepdim=True)).ptr
+    key = (kind + "_bwd", rows, y.aligned and grad.aligned)
+    plan = _plans.get(key)
+    if plan is None:
+        plan = _plans[key] = Plan(ck.softmax_bwd_rows(kind, rows[0], rows[1], y.aligned and grad.aligned))
+    return plan.run(_dev_ptr(y), _dev_ptr(grad))
+
+
+@dispatcher.register(UnaryOps.SOFTMAX, CUDA)
+def softmax(x: Buffer, dim: int) -> CDataPtr:
+    return _softmax_family("softmax", x, dim)
+
+
+@dispatcher.register(UnaryOps.LOG_SOFTMAX, CUDA)
+def log_softmax(x: Buffer, dim: int) -> CDataPtr:
+    return _softmax_family("log_softmax", x, dim)
+
+
+@dispatcher.register(UnaryOps.SOFTMAX_BACKWARD, CUDA)
+def softmax_backward(y: Buffer, grad: Buffer, dim: int) -> CDataPtr:
+    return _softmax_bwd_family("softmax", y, grad, dim)
+
+
+@dispatcher.register(UnaryOps.LOG_SOFTMAX_BACKWARD, CUDA)
+def log_softmax_backward(y: Buffer, grad: Buffer, dim: int) -> CDataPtr:
+    return _softmax_bwd_family("log_softmax", y, grad, dim)
+
+
+# ------------------------------------------------------------------------------------------------
+# permute                                                     reference: cpu.py:334-368
+# ------------------------------------------------------------------------------------------------
+@dispatcher.register(UnaryOps.PERMUTE, CUDA)
+def permute(x: Buffer, order: tuple) -> CDataPtr:
+    shape = x.metadata.shape
+    key = ("perm", shape, tuple(order), x.aligned)
+    plan = _plans.get(key)
+    if plan is None:
+        in_str = calculate_stride(shape)
+        out_shape = tuple(shape[i] for i in order)
+        pstr = tuple(in_str[i] for i in order)
+        # collapse first: (B,T,h,d)->(0,2,1,3) keeps d innermost, (1,128,96)->(0,2,1) is 2-D, ...
+        cshape, cstr = ck.collapse_dims(out_shape, [calculate_stride(out_shape), pstr])
+        cin = cstr[1]
+        if cin[-1] == 1 or len(cshape) == 1 or prod_(shape) < 1024:
+            k = ck.ewise("v0", out_shape, (pstr,), x.aligned, "permute")
+        else:
+            tdim = cin.index(1) if 1 in cin else None
+            if tdim is None:
+                k = ck.ewise("v0", out_shape, (pstr,), x.aligned, "permute")
+            else:
+                k = ck.transpose_tiled(tuple(cshape), tuple(cin), tdim)
+        plan = _plans[key] = Plan(k, prod_(shape))
+    return plan.run(_dev_ptr(x))
+
+
+# ------------------------------------------------------------------------------------------------
+# matmul                                                      reference: cpu.py:505-602
+# ------------------------------------------------------------------------------------------------
+@dispatcher.register(BinaryOps.MATMUL, CUDA)
+def matmul(x: Buffer, y: Buffer, trans_x: bool = False, trans_y: bool = False) -> CDataPtr:
+    from dlgrad_b200.runtime.cuda import matmul as _mm
+    return _mm.run_matmul(x, y, trans_x, trans_y)
+
+
+# ------------------------------------------------------------------------------------------------
+# cross-entropy pieces and embedding                          reference: cpu.py:962-1061
+# ------------------------------------------------------------------------------------------------
+@dispatcher.register(CustomOps.CE_FORWARD, CUDA)
+def ce_forward(x: Buffer, y: Buffer) -> CDataPtr:
+    n, s0 = x.metadata.shape[0], x.metadata.shape[1]
+    key = ("ce_fwd", n, s0)
+    plan = _plans.get(key)
+    if plan is None:
+        plan = _plans[key] = Plan(ck.ce_forward(n, s0))
+    return plan.run(_dev_ptr(x), _dev_ptr(y))
+
+
+@dispatcher.register(CustomOps.CE_BACKWARD, CUDA)
+def ce_backward(x: Buffer, target: Buffer) -> None:
+    n, s0 = x.metadata.shape[0], x.metadata.shape[1]
+    key = ("ce_bwd", n, s0)
+    plan = _plans.get(key)
+    if plan is None:
+        plan = _plans[key] = Plan(ck.ce_backward(n, s0))
+    plan.run_into(NULL, _dev_ptr(x), _dev_ptr(target))
+
+
+@dispatcher.register(CustomOps.CE_GRAD, CUDA)
+def ce_grad(logsm: Buffer, target: Buffer, upstream: Buffer, n: float) -> CDataPtr:
+    rows, V = logsm.metadata.shape
+    up_ptr = upstream.scalar is None
+    key = ("ce_grad", rows, V, up_ptr)
+    plan = _plans.get(key)
+    if plan is None:
+        plan = _plans[key] = Plan(ck.ce_grad(rows, V, up_ptr))
+    if up_ptr:
+        return plan.run(_dev_ptr(logsm), _dev_ptr(target), _dev_ptr(upstream), NULL, 0.0, float(n))
+    return plan.run(_dev_ptr(logsm), _dev_ptr(target), NULL, NULL, upstream.scalar, float(n))
+
+
+@dispatcher.register(CustomOps.EMBEDDING, CUDA)
+def embedding(x: Buffer, idx: Buffer, out_numel: int, backward: bool = False,
+              upstream_grad: Buffer | None = None) -> CDataPtr:
+    C = x.metadata.shape[-1]
+    n_idx = idx.metadata.numel
+    if not backward:
+        key = ("emb", n_idx, C, x.aligned)
+        plan = _plans.get(key)
+        if plan is None:
+            plan = _plans[key] = Plan(ck.embedding_fwd(n_idx, C, x.aligned))
+        return plan.run(_dev_ptr(x), _dev_ptr(idx))
+    rows = x.metadata.shape[0]
+    key = ("emb_bwd", rows, n_idx, C)
+    plan = _plans.get(key)
+    if plan is None:
+        plan = _plans[key] = Plan(ck.embedding_bwd(rows, n_idx, C))
+    return plan.run(_dev_ptr(upstream_grad), _dev_ptr(idx))
+
+
+# ------------------------------------------------------------------------------------------------
+# optimizer steps (in place)                                  reference: dlgrad/nn/optim.py:26-70
+# ------------------------------------------------------------------------------------------------
+@dispatcher.register(CustomOps.ADAM_STEP, CUDA)
+def adam_step(param: Buffer, grad: Buffer, m: Buffer, v: Buffer, beta1: float, beta2: float,
+              eps: float, bc1: float, bc2: float, lr: float) -> None:
+    ok = param.aligned and grad.aligned and m.aligned and v.aligned
+    key = ("adam", param.metadata.numel, beta1, beta2, eps, ok)
+    plan = _plans.get(key)
+    if plan is None:
+        plan = _plans[key] = Plan(ck.adam_step(param.metadata.numel, beta1, beta2, eps, ok))
+    plan.run_into(NULL, _dev_ptr(param), _dev_ptr(grad), _dev_ptr(m), _dev_ptr(v), bc1, bc2, lr)
+
+
+@dispatcher.register(CustomOps.SGD_STEP, CUDA)
+def sgd_step(param: Buffer, grad: Buffer, lr: float) -> None:
+    ok = param.aligned and grad.aligned
+    key = ("sgd", param.metadata.numel, ok)
+    plan = _plans.get(key)
+    if plan is None:
+        plan = _plans[key] = Plan(ck.sgd_step(param.metadata.numel, ok))
+    plan.run_into(NULL, _dev_ptr(param), _dev_ptr(grad), NULL, NULL, lr)
+
+
+@dispatcher.register(CustomOps.PRINT, CUDA)
+def show(x: Buffer) -> None:
+    print(x.numpy())
+
+
+def launch_count() -> int:
+    return int(lib.dlg_launch_count())
