@@ -1,0 +1,372 @@
+#!/usr/bin/env python
+"""bench.py — the driver's measurement contract for dlgrad_b200.
+
+    python bench.py --gpus N --steps K --warmup W            # this package on N B200s (torchrun for N>1)
+    python bench.py --impl reference --gpus N --steps K ...   # the reference's CPU path, same metric
+
+Metric (BASELINE.json): GPT train steps/s on the scaled dlgrad GPT — n_layer 12, n_embd 768,
+n_head 12, block_size 1024 (configs[4]), V = 96 (the reference's char vocabulary), per-GPU batch 8,
+Adam lr 1e-4, synthetic tokens, random-init weights.  One "step" = forward + backward + optimizer over
+ONE per-GPU batch; with N ranks (data parallel, weak scaling) every iteration completes N of them, so
+`value` = N * K / max-over-ranks device time.  The op microbenches of configs[1] (4096^2 elementwise /
+reduce in GB/s, 4096^3 matmul in TFLOP/s) ride along in "ops" at N = 1.
+
+Timed regions (each: barrier + device sync on both sides, CUDA events on the launching stream):
+  value  K steps with the token batches already resident in HBM, loss read back once at the end;
+  e2e    K steps through the public API with HOST inputs: Tensor(np, device="cuda") H2D every step and
+         loss.numpy() D2H every step.
+Inputs and activations are far larger than L2 (one step touches > 20 GB), so no explicit L2 flush.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from tests import models  # noqa: E402  (framework-agnostic GPT / MLP definitions)
+
+C5 = dict(vocab_size=96, block_size=1024, n_layer=12, n_head=12, n_embd=768)
+C4 = dict(vocab_size=96, block_size=128, n_layer=6, n_head=4, n_embd=128)
+
+
+def load_peaks() -> dict:
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            p = json.load(f)
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_burst": p["bf16_tflops"], "bf16_sustained": p["bf16_tflops_sustained"],
+                "source": "measured"}
+    except (OSError, KeyError, ValueError):
+        # fallback stated in /opt/skills/guides/B200_PROFILING.md
+        return {"hbm_gbs": 6650.0, "bf16_burst": 1590.0, "bf16_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int) -> None:
+        self.rows, self.proc, self.index = [], None, index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *exc):
+        if self.proc:
+            self.proc.terminate()
+
+    def summary(self) -> dict:
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 7:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle (CPU restatement of the reference's kernels, same autograd
+# layer) on a bounded sample of the same workload
+# ---------------------------------------------------------------------------------------------------
+def cpu_block_sample(cfg_kw: dict, repeats: int = 1) -> tuple[float, str]:
+    """Seconds for ONE transformer block, forward + backward, on ONE sequence of the benchmark config,
+    on the CPU oracle (single thread, as the reference)."""
+    import dlgrad_b200 as dl
+    from dlgrad_b200 import Tensor
+    from oracle import backend
+    backend.install()
+    cfg = models.GPTConfig(device="cpu", **cfg_kw)
+    rng = np.random.default_rng(0)
+    blk = models._Block(dl, cfg, rng)
+    x = (rng.random((1, cfg.block_size, cfg.n_embd), dtype=np.float32) - 0.5).astype(np.float32)
+    best = float("inf")
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        xt = Tensor(x.copy(), requires_grad=True)
+        y = blk(xt)
+        y.sum().backward()
+        best = min(best, time.perf_counter() - t0)
+    return best, (f"1 of {cfg.n_layer} transformer blocks x 1 sequence (T={cfg.block_size}, C={cfg.n_embd}), "
+                  f"forward+backward on the CPU oracle, single thread")
+
+
+def cpu_equiv_steps_per_s(block_seconds: float, cfg_kw: dict, batch: int) -> float:
+    """Extrapolate the block sample to full steps: L blocks x B sequences, plus the embedding / head /
+    loss / optimizer share taken from the FLOP model."""
+    cfg = models.GPTConfig(**cfg_kw)
+    full = models.gpt_train_flops(cfg, 1)
+    T, C, L = cfg.block_size, cfg.n_embd, cfg.n_layer
+    blocks = 3.0 * L * (24.0 * T * C * C + 4.0 * T * T * C)
+    step_seconds = block_seconds * L * batch * (full / blocks)
+    return 1.0 / step_seconds
+
+
+def run_reference(args) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cfg_kw = C5 if args.config == "c5" else C4
+    times = []
+    sample = ""
+    for i in range(args.warmup + args.steps):
+        t, sample = cpu_block_sample(cfg_kw)
+        if i >= args.warmup:
+            times.append(t)
+        if sum(times) > 240:      # keep the whole run within a few minutes
+            break
+    per_gpu = cpu_equiv_steps_per_s(float(np.mean(times)), cfg_kw, args.batch)
+    value = per_gpu           # the CPU path does not scale with --gpus: one host, one thread
+    line = {
+        "impl": "reference", "metric": "gpt_train_steps_per_s", "value": value, "unit": "steps/s",
+        "n_gpus": args.gpus, "steps": len(times), "warmup": args.warmup, "ms_per_step": 1000.0 / value,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(cfg_kw, args.batch, args.gpus),
+        "cpu_baseline": {"value": value, "unit": "steps/s", "cores": 1, "kind": "port", "sample": sample
+                         + f"; {len(times)} samples, mean {np.mean(times):.2f} s, scaled by L x B x FLOP share"},
+        "e2e": {"value": value, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "host": {"cpu_count": os.cpu_count()},
+    }
+    print(json.dumps(line))
+
+
+def workload_config(cfg_kw: dict, batch: int, gpus: int) -> dict:
+    return {"workload": f"scaled dlgrad GPT train step (BASELINE.json configs[4]): n_layer={cfg_kw['n_layer']} "
+                        f"n_embd={cfg_kw['n_embd']} n_head={cfg_kw['n_head']} block_size={cfg_kw['block_size']} "
+                        f"vocab={cfg_kw['vocab_size']}, Adam lr 1e-4",
+            "per_gpu_batch": batch, "global_batch": batch * gpus, "seq_len": cfg_kw["block_size"],
+            "parallelism": f"dp{gpus}", "l2": "working set per step >> 126 MB L2; no explicit flush"}
+
+
+# ---------------------------------------------------------------------------------------------------
+# this package
+# ---------------------------------------------------------------------------------------------------
+def build_gpt(cfg_kw: dict, device: str):
+    import dlgrad_b200 as dl
+    from dlgrad_b200 import nn
+    cfg = models.GPTConfig(device=device, **cfg_kw)
+    gpt = models.GPT(dl, cfg, np.random.default_rng(0))       # identical weights on every rank
+    params = nn.utils.get_parameters(gpt)
+    opt = nn.optim.Adam(params, lr=1e-4)
+    return cfg, gpt, params, opt
+
+
+def train_step(gpt, opt, params, x, y, world):
+    from dlgrad_b200 import distributed
+    opt.zero_grad()
+    _, loss = gpt(x, y)
+    loss.backward()
+    if world > 1:
+        distributed.all_reduce_gradients(params)
+    opt.step()
+    return loss
+
+
+def op_microbench(peaks: dict) -> dict:
+    """configs[1]: broadcast add/mul and sum/max over axis on 4096x4096 fp32; matmul 4096^3 fwd.
+    Each op: 3 warm-ups, then 20 launches timed with events; between launches a 512 MB buffer is
+    rewritten so no input survives in the 126 MB L2."""
+    from dlgrad_b200 import Tensor
+    from dlgrad_b200.runtime.cuda import profile, shim
+    rng = np.random.default_rng(0)
+    n = 4096
+    a, b = Tensor(rng.random((n, n), dtype=np.float32), device="cuda"), Tensor(rng.random((n, n), dtype=np.float32), device="cuda")
+    row, col = Tensor(rng.random((1, n), dtype=np.float32), device="cuda"), Tensor(rng.random((n, 1), dtype=np.float32), device="cuda")
+    flush = Tensor(np.zeros((128, 1024, 1024), dtype=np.float32), device="cuda")
+    MB = 1e6
+    full, half = 3 * n * n * 4, 2 * n * n * 4
+    specs = [("add_same", lambda: a + b, full, "GB/s"), ("mul_same", lambda: a * b, full, "GB/s"),
+             ("add_row", lambda: a + row, half, "GB/s"), ("mul_col", lambda: a * col, half, "GB/s"),
+             ("sum_axis0", lambda: a.sum(dim=0), n * n * 4, "GB/s"), ("sum_axis1", lambda: a.sum(dim=1), n * n * 4, "GB/s"),
+             ("max_axis0", lambda: a.max(dim=0), n * n * 4, "GB/s"), ("max_axis1", lambda: a.max(dim=1), n * n * 4, "GB/s"),
+             ("exp", lambda: a.exp(), half, "GB/s"), ("transpose", lambda: a.T, half, "GB/s"),
+             ("matmul_4096", lambda: a @ b, 2.0 * n ** 3, "TFLOP/s")]
+    out = {}
+    for name, fn, work, unit in specs:
+        for _ in range(3):
+            fn()
+        ms = []
+        for _ in range(20 if unit == "GB/s" else 5):
+            _ = flush * 1.0
+            e0 = profile.Event().record()
+            r = fn()
+            e1 = profile.Event().record()
+            e1.sync()
+            ms.append(e1.ms_since(e0))
+            del r
+        t = float(np.median(ms)) * 1e-3
+        if unit == "GB/s":
+            ach = work / t / 1e9
+            out[name] = {"achieved": ach, "unit": unit, "ms": t * 1e3, "frac_of_hbm_peak": ach / peaks["hbm_gbs"],
+                         "algorithmic_MB": work / MB}
+        else:
+            ach = work / t / 1e12
+            out[name] = {"achieved": ach, "unit": unit, "ms": t * 1e3,
+                         "frac_of_3xtf32_peak": ach / (peaks["bf16_burst"] / 6.0)}
+    shim.synchronize()
+    return out
+
+
+def run_b200(args) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    os.environ.setdefault("DLGRAD_CUDA_DEVICE", str(local))
+    from dlgrad_b200 import Tensor, distributed
+    from dlgrad_b200.runtime.cuda import ops as cuda_ops
+    from dlgrad_b200.runtime.cuda import profile, shim, transfer
+    shim.init(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist      # rendezvous + timing barrier only (gloo: no GPU context of its own)
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        uid = [distributed.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        distributed.init(rank, world, uid[0])
+
+    def barrier():
+        shim.synchronize()
+        if dist is not None:
+            dist.barrier()
+
+    cfg_kw = C5 if args.config == "c5" else C4
+    cfg, gpt, params, opt = build_gpt(cfg_kw, "cuda")
+    opt.grad_scale = 1.0 / world
+    data_rng = np.random.default_rng(1000 + rank)            # rank-specific tokens
+    batches = [models.gpt_batch(cfg, args.batch, data_rng) for _ in range(4)]
+    dev_batches = [(Tensor(x, device="cuda"), Tensor(y, device="cuda")) for x, y in batches]
+
+    if args.prebuild:       # compile-only census of every kernel the bench launches
+        train_step(gpt, opt, params, *dev_batches[0], world)
+        op_microbench(load_peaks())
+        return
+
+    for i in range(args.warmup):
+        loss = train_step(gpt, opt, params, *dev_batches[i % 4], world)
+    _ = loss.numpy() if args.warmup else None
+
+    peaks = load_peaks()
+    # ---- region A: device-resident inputs ----------------------------------------------------------
+    barrier()
+    launches0 = cuda_ops.launch_count()
+    profile.matmul_timer = profile.KernelTimer()
+    with ClockSampler(local) as clocks:
+        e0 = profile.Event().record()
+        for i in range(args.steps):
+            loss = train_step(gpt, opt, params, *dev_batches[i % 4], world)
+        e1 = profile.Event().record()
+        e1.sync()
+        barrier()
+    mm = profile.matmul_timer.collect()
+    profile.matmul_timer = None
+    ms_a = e1.ms_since(e0)
+    launches = cuda_ops.launch_count() - launches0
+    last_loss = float(loss.numpy())
+    # ---- region B: end to end from host buffers ------------------------------------------------------
+    transfer.reset_counters()
+    barrier()
+    e0 = profile.Event().record()
+    for i in range(args.steps):
+        x, y = batches[i % 4]
+        loss = train_step(gpt, opt, params, Tensor(x, device="cuda"), Tensor(y, device="cuda"), world)
+        _ = loss.numpy()
+    e1 = profile.Event().record()
+    e1.sync()
+    barrier()
+    ms_b = e1.ms_since(e0)
+    io = transfer.counters()
+
+    if dist is not None:      # max over ranks
+        import torch
+        t = torch.tensor([ms_a, ms_b], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_a, ms_b = float(t[0]), float(t[1])
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    value = world * args.steps / (ms_a * 1e-3)
+    e2e = world * args.steps / (ms_b * 1e-3)
+    flops_step = models.gpt_train_flops(cfg, args.batch)
+    mm_tflops = (mm["work"] / (mm["ms"] * 1e-3) / 1e12) if mm["ms"] > 0 else 0.0
+    peak_3xtf32 = peaks["bf16_sustained"] / 6.0      # TF32 dense = bf16/2, three MMAs per product
+    line = {
+        "metric": "gpt_train_steps_per_s", "value": value, "unit": "steps/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_a / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32 (3xTF32 tensor-core matmul, fp32 elsewhere)", "data": "synthetic",
+        "config": workload_config(cfg_kw, args.batch, world),
+        "tokens_per_s": value * args.batch * cfg.block_size,
+        "model_tflops": value * flops_step / 1e12,
+        "last_loss": last_loss,
+        "gpu_launches": int(launches),
+        "clocks": clocks.summary(),
+        "e2e": {"value": e2e, "unit": "steps/s", "h2d_bytes_per_step": io["h2d_bytes"] // args.steps,
+                "d2h_bytes_per_step": io["d2h_bytes"] // args.steps},
+        "roofline": {"bound": "tensor", "kernel": "matmul (all launches of the timed steps, CUDA events per launch)",
+                     "achieved": mm_tflops, "peak": peak_3xtf32, "unit": "TFLOP/s",
+                     "frac": mm_tflops / peak_3xtf32 if peak_3xtf32 else None, "traffic": None,
+                     "peak_note": f"3xTF32 = sustained bf16 {peaks['bf16_sustained']} TF/s / 6 ({peaks['source']}: "
+                                  "MEASURED_PEAKS.json has no TF32 entry; TF32 dense = bf16/2, 3 MMAs per product)",
+                     "matmul_share_of_step": mm["ms"] / ms_a if ms_a else None, "matmul_launches": mm["launches"]},
+    }
+    if world == 1 and not args.no_cpu:
+        t, sample = cpu_block_sample(cfg_kw)
+        v = cpu_equiv_steps_per_s(t, cfg_kw, args.batch)
+        line["cpu_baseline"] = {"value": v, "unit": "steps/s", "cores": 1, "kind": "port",
+                                "sample": sample + f" ({t:.2f} s), scaled by L x B x FLOP share; host has {os.cpu_count()} cores, "
+                                "the reference is single-threaded"}
+    if world == 1 and not args.no_ops:
+        line["ops"] = op_microbench(peaks)
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="c5", choices=["c5", "c4"])
+    ap.add_argument("--batch", type=int, default=8)
+    ap.add_argument("--no-ops", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--prebuild", action="store_true", help="compile-only census (used by __graft_entry__.build)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

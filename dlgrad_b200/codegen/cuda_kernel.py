@@ -858,7 +858,8 @@ def adam_step(numel: int, beta1: float, beta2: float, eps: float, aligned: bool 
     (28 B/param) instead of the reference's ~14 elementwise dispatches with a fresh allocation
     each (dlgrad/nn/optim.py:59-70).  The float32 operation sequence per element is the
     reference's, op for op (no FMA contraction): m*b1 + g*(1-b1); v*b2 + (g*g)*(1-b2);
-    m/(1-b1^t); v/(1-b2^t); p - (mh/(sqrt(vh)+eps))*lr.  f0 = 1-b1^t, f1 = 1-b2^t, f2 = lr.
+    m/(1-b1^t); v/(1-b2^t); p - (mh/(sqrt(vh)+eps))*lr.  f0 = 1-b1^t, f1 = 1-b2^t, f2 = lr,
+    f3 = gradient scale (1.0 on one GPU — an exact no-op — or 1/world after a data-parallel sum).
     p0 = param, p1 = grad, p2 = m, p3 = v."""
     V = 4 if (aligned and numel % 4 == 0) else 1
     nv = numel // V
@@ -870,7 +871,7 @@ def adam_step(numel: int, beta1: float, beta2: float, eps: float, aligned: bool 
     for c in comps:
         s = ("." + c) if c else ""
         body.append(f"""
-        {{ const float gg = g{s};
+        {{ const float gg = __fmul_rn(g{s}, f3);
           const float mn = __fadd_rn(__fmul_rn(m{s}, {b1}), __fmul_rn(gg, {omb1}));
           const float vn = __fadd_rn(__fmul_rn(v{s}, {b2}), __fmul_rn(__fmul_rn(gg, gg), {omb2}));
           const float mh = __fdiv_rn(mn, f0), vh = __fdiv_rn(vn, f1);
@@ -896,12 +897,12 @@ extern "C" __global__ void __launch_bounds__(256) {KNAME}{SIG_ALIAS} {{
 @cache
 def sgd_step(numel: int, aligned: bool = True) -> Kernel:
     """In-place p = p - lr*g (dlgrad/nn/optim.py:44: `param - self.lr * grad`, MUL then SUB).
-    p0 = param, p1 = grad, f0 = lr."""
+    p0 = param, p1 = grad, f0 = lr, f3 = gradient scale (1.0 = exact no-op)."""
     V = 4 if (aligned and numel % 4 == 0) else 1
     nv = numel // V
     VT = "float4" if V == 4 else "float"
     comps = ["x", "y", "z", "w"] if V == 4 else [""]
-    body = " ".join(f"p.{c} = __fsub_rn(p.{c}, __fmul_rn(f0, g.{c}));" if c else "p = __fsub_rn(p, __fmul_rn(f0, g));"
+    body = " ".join(f"p.{c} = __fsub_rn(p.{c}, __fmul_rn(f0, __fmul_rn(g.{c}, f3)));" if c else "p = __fsub_rn(p, __fmul_rn(f0, __fmul_rn(g, f3)));"
                     for c in comps)
     src = f"""
 extern "C" __global__ void __launch_bounds__(256) {KNAME}{SIG_ALIAS} {{

@@ -20,6 +20,7 @@ class Optimizer:
     def __init__(self, params: list[Tensor], lr: float = 1e-1) -> None:
         self.params = params
         self.lr = lr
+        self.grad_scale = 1.0     # set to 1/world by data-parallel training (dlgrad_b200/distributed.py)
 
     def _device_for(self, *bufs: Buffer) -> Device:
         return Buffer._route(*bufs)
@@ -32,7 +33,7 @@ class Optimizer:
                 f"The shape of the parameter {p.shape} and its grad {p.grad.shape} do not match")
             dev = self._device_for(p.data, p.grad.data)
             dispatcher.dispatch(op=CustomOps.SGD_STEP, device=dev, param=p.data, grad=p.grad.data,
-                                lr=float(_f32(self.lr)))
+                                lr=float(_f32(self.lr)), grad_scale=self.grad_scale)
 
     def zero_grad(self) -> None:
         for p in self.params:
@@ -58,7 +59,7 @@ class SGD(Optimizer):
             self.velocities[id(p)] = v
             dev = self._device_for(p.data, v.data)
             dispatcher.dispatch(op=CustomOps.SGD_STEP, device=dev, param=p.data, grad=v.data,
-                                lr=float(_f32(self.lr)))
+                                lr=float(_f32(self.lr)), grad_scale=self.grad_scale)
 
 
 class Adam(Optimizer):
@@ -69,6 +70,7 @@ class Adam(Optimizer):
         self.beta1, self.beta2 = betas
         self.eps = eps
         self.t = 0
+        self.grad_scale = 1.0
         self.m = {id(p): Tensor.zeros_like(p) for p in params}
         self.v = {id(p): Tensor.zeros_like(p) for p in params}
 
@@ -86,4 +88,5 @@ class Adam(Optimizer):
             m, v = self.m[id(p)], self.v[id(p)]
             dev = self._device_for(p.data, p.grad.data, m.data, v.data)
             dispatcher.dispatch(op=CustomOps.ADAM_STEP, device=dev, param=p.data, grad=p.grad.data,
-                                m=m.data, v=v.data, beta1=b1, beta2=b2, eps=eps, bc1=bc1, bc2=bc2, lr=lr)
+                                m=m.data, v=v.data, beta1=b1, beta2=b2, eps=eps, bc1=bc1, bc2=bc2, lr=lr,
+                                grad_scale=self.grad_scale)

@@ -17,7 +17,6 @@ import os
 import shutil
 import subprocess
 import tempfile
-from concurrent.futures import ThreadPoolExecutor
 
 from dlgrad_b200.helpers import CACHE_DIR
 from dlgrad_b200.runtime.cuda import shim
@@ -124,7 +123,7 @@ def get_function(base: str, src: str):
 
 
 def flush_pending(jobs: int | None = None, pack_size: int = 24) -> int:
-    """Compile everything recorded in compile-only mode into pack cubins (parallel nvcc)."""
+    """Compile everything recorded in compile-only mode into pack cubins (nvcc processes in parallel)."""
     global _index
     if not _pending:
         return 0
@@ -132,30 +131,38 @@ def flush_pending(jobs: int | None = None, pack_size: int = 24) -> int:
     idx = _load_index()
     items = sorted(_pending.items())
     packs = [items[i:i + pack_size] for i in range(0, len(items), pack_size)]
-    jobs = jobs or min(len(packs), os.cpu_count() or 4)
-
-    def build(pack):
-        h = hashlib.sha256("".join(k for k, _ in pack).encode()).hexdigest()[:16]
-        name = f"pack_{h}.cubin"
-        tmpdir = tempfile.mkdtemp(prefix="dlgp_")
-        try:
-            cu = os.path.join(tmpdir, "pack.cu")
+    jobs = jobs or (os.cpu_count() or 4)
+    tmpdir = tempfile.mkdtemp(prefix="dlgp_")
+    try:
+        todo = []
+        for pack in packs:
+            h = hashlib.sha256("".join(k for k, _ in pack).encode()).hexdigest()[:16]
+            name = f"pack_{h}.cubin"
+            cu = os.path.join(tmpdir, f"pack_{h}.cu")
             with open(cu, "w") as f:
                 for key, (fname, src) in pack:
-                    # each kernel in its own namespace so file-local helpers/constants cannot collide
-                    body = src.replace(KNAME, fname)
-                    f.write(f"// ---- {fname}\nnamespace ns_{fname} {{\n{body}\n}}\n")
-            out = os.path.join(tmpdir, name)
-            _run_nvcc(cu, out)
+                    # each kernel in its own namespace so file-local helpers cannot collide
+                    f.write(f"// ---- {fname}\nnamespace ns_{fname} {{\n{src.replace(KNAME, fname)}\n}}\n")
+            todo.append((name, cu, os.path.join(tmpdir, name), pack))
+        running: list = []
+        queue = list(todo)
+        while queue or running:
+            while queue and len(running) < jobs:
+                name, cu, out, pack = queue.pop(0)
+                proc = subprocess.Popen([NVCC, *NVCC_FLAGS, "-o", out, cu], stdout=subprocess.PIPE,
+                                        stderr=subprocess.PIPE, text=True)
+                running.append((proc, name, cu, out, pack))
+            proc, name, cu, out, pack = running.pop(0)
+            _so, se = proc.communicate()
+            if proc.returncode != 0:
+                for other in running:
+                    other[0].kill()
+                raise RuntimeError(f"Compilation failed for {cu}:\n{se}")
             shutil.move(out, os.path.join(CACHE_DIR, name))
-        finally:
-            shutil.rmtree(tmpdir, ignore_errors=True)
-        return name, pack
-
-    with ThreadPoolExecutor(max_workers=jobs) as ex:
-        for name, pack in ex.map(build, packs):
             for key, (fname, _src) in pack:
                 idx[key] = [name, fname]
+    finally:
+        shutil.rmtree(tmpdir, ignore_errors=True)
     with open(_index_path() + ".tmp", "w") as f:
         json.dump(idx, f, indent=0, sort_keys=True)
     os.replace(_index_path() + ".tmp", _index_path())
@@ -166,3 +173,8 @@ def flush_pending(jobs: int | None = None, pack_size: int = 24) -> int:
 
 def pending_count() -> int:
     return len(_pending)
+
+
+if shim.COMPILE_ONLY:
+    import atexit
+    atexit.register(flush_pending)

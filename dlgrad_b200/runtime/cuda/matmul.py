@@ -14,6 +14,7 @@ from dlgrad_b200.buffer import Buffer
 from dlgrad_b200.codegen import cuda_kernel as ck
 from dlgrad_b200.helpers import prod_
 from dlgrad_b200.runtime.cuda import ops as _ops
+from dlgrad_b200.runtime.cuda import profile as _profile
 
 _plans: dict = {}
 FORCE_SIMT = os.environ.get("DLGRAD_MATMUL", "").lower() == "simt"
@@ -47,7 +48,13 @@ def run_matmul(x: Buffer, y: Buffer, trans_x: bool = False, trans_y: bool = Fals
     if plan is None:
         plan = _plans[key] = _build(x.metadata.shape, y.metadata.shape, trans_x, trans_y,
                                     x.aligned and y.aligned)
-    return plan(_ops._dev_ptr(x), _ops._dev_ptr(y))
+    timer = _profile.matmul_timer
+    if timer is None:
+        return plan(_ops._dev_ptr(x), _ops._dev_ptr(y))
+    t0 = timer.start()
+    out = plan(_ops._dev_ptr(x), _ops._dev_ptr(y))
+    timer.stop(t0, plan.flops, plan.tag)
+    return out
 
 
 def _build(xs, ys, tx, ty, aligned):
@@ -59,4 +66,14 @@ def _build(xs, ys, tx, ty, aligned):
             return tc
     k = ck.matmul_simt(M, N, K, batch[0], batch[1], a_bs, b_bs, tx, ty, aligned)
     p = _ops.Plan(k, prod_(batch) * M * N)
-    return lambda a, b: p.run(a, b)
+    return MatmulPlan(lambda a, b: p.run(a, b), 2.0 * prod_(batch) * M * N * K, ("simt", M, N, K, prod_(batch)))
+
+
+class MatmulPlan:
+    __slots__ = ("fn", "flops", "tag")
+
+    def __init__(self, fn, flops: float, tag: tuple) -> None:
+        self.fn, self.flops, self.tag = fn, flops, tag
+
+    def __call__(self, a, b):
+        return self.fn(a, b)

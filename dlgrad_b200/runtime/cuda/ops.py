@@ -515,23 +515,23 @@ def embedding(x: Buffer, idx: Buffer, out_numel: int, backward: bool = False,
 # ------------------------------------------------------------------------------------------------
 @dispatcher.register(CustomOps.ADAM_STEP, CUDA)
 def adam_step(param: Buffer, grad: Buffer, m: Buffer, v: Buffer, beta1: float, beta2: float,
-              eps: float, bc1: float, bc2: float, lr: float) -> None:
+              eps: float, bc1: float, bc2: float, lr: float, grad_scale: float = 1.0) -> None:
     ok = param.aligned and grad.aligned and m.aligned and v.aligned
     key = ("adam", param.metadata.numel, beta1, beta2, eps, ok)
     plan = _plans.get(key)
     if plan is None:
         plan = _plans[key] = Plan(ck.adam_step(param.metadata.numel, beta1, beta2, eps, ok))
-    plan.run_into(NULL, _dev_ptr(param), _dev_ptr(grad), _dev_ptr(m), _dev_ptr(v), bc1, bc2, lr)
+    plan.run_into(NULL, _dev_ptr(param), _dev_ptr(grad), _dev_ptr(m), _dev_ptr(v), bc1, bc2, lr, grad_scale)
 
 
 @dispatcher.register(CustomOps.SGD_STEP, CUDA)
-def sgd_step(param: Buffer, grad: Buffer, lr: float) -> None:
+def sgd_step(param: Buffer, grad: Buffer, lr: float, grad_scale: float = 1.0) -> None:
     ok = param.aligned and grad.aligned
     key = ("sgd", param.metadata.numel, ok)
     plan = _plans.get(key)
     if plan is None:
         plan = _plans[key] = Plan(ck.sgd_step(param.metadata.numel, ok))
-    plan.run_into(NULL, _dev_ptr(param), _dev_ptr(grad), NULL, NULL, lr)
+    plan.run_into(NULL, _dev_ptr(param), _dev_ptr(grad), NULL, NULL, lr, 0.0, 0.0, grad_scale)
 
 
 @dispatcher.register(CustomOps.PRINT, CUDA)

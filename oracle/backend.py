@@ -269,8 +269,10 @@ def _ce_grad(logsm: Buffer, target: Buffer, upstream: Buffer, n: float):
     return ((tmp * upstream) / float(n)).ptr
 
 
-def _adam_step(param: Buffer, grad: Buffer, m: Buffer, v: Buffer, beta1, beta2, eps, bc1, bc2, lr):
+def _adam_step(param: Buffer, grad: Buffer, m: Buffer, v: Buffer, beta1, beta2, eps, bc1, bc2, lr, grad_scale=1.0):
     """dlgrad/nn/optim.py:59-70, op for op on the primitive kernels; results written back in place."""
+    if grad_scale != 1.0:
+        grad = grad * grad_scale
     m_new = (m * beta1) + (grad * (1.0 - beta1))
     v_new = (v * beta2) + ((grad ** 2.0) * (1.0 - beta2))
     m_hat = m_new / bc1
@@ -280,8 +282,10 @@ def _adam_step(param: Buffer, grad: Buffer, m: Buffer, v: Buffer, beta1, beta2, 
         _np(dst)[:] = _np(src)
 
 
-def _sgd_step(param: Buffer, grad: Buffer, lr: float):
+def _sgd_step(param: Buffer, grad: Buffer, lr: float, grad_scale: float = 1.0):
     """dlgrad/nn/optim.py:44: param - lr * grad."""
+    if grad_scale != 1.0:
+        grad = grad * grad_scale
     p_new = param - (Buffer.from_scalar(lr) * grad)
     _np(param)[:] = _np(p_new)
 
