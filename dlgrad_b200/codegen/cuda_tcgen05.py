@@ -1,0 +1,315 @@
+"""Tensor-core matmul generator: tcgen05.mma (kind::tf32) + TMEM accumulator + TMA operand staging,
+3xTF32 error-compensated so the result keeps fp32 accuracy (north star: <= 1e-4 relative).
+
+Replaces cpu_kernel.matmul_{2,3,4}d (dlgrad/codegen/cpu_kernel.py:352-428) for shapes whose pitches are
+16-byte multiples; everything else goes to cuda_kernel.matmul_simt.
+
+Algorithm per CTA (one 128 x BN output tile, K walked in blocks of 32 fp32 = one 128-byte swizzle span):
+
+    warp 0      TMA producer   cp.async.bulk.tensor (SWIZZLE_128B) of the fp32 A and B tiles -> full[s]
+    warps 2-5   splitter       lo = x - (x & 0xffffe000) into a twin buffer with the SAME swizzled layout
+                               (a purely linear pass, no layout knowledge needed) -> split[s].  The staged
+                               fp32 tile itself serves as `hi`: tcgen05 kind::tf32 TRUNCATES its fp32
+                               inputs to 10 mantissa bits (measured on B200: 1+2^-11+2^-12 -> 1.0,
+                               scripts/tc_probe.py), so hi needs no store.
+    warp 1      MMA issuer     one elected lane: per 8-wide k step three tcgen05.mma into one TMEM
+                               accumulator — A_lo*B_hi, A_hi*B_lo, A_hi*B_hi (small terms first);
+                               tcgen05.commit -> empty[s]; last commit -> acc_full
+    warps 2-5   epilogue       tcgen05.ld (32 lanes x 32 columns per warp) TMEM -> registers -> C
+
+Operand layouts (element = fp32, T = 4 elements per 16 bytes), after CUTLASS' canonical UMMA layouts:
+    K-major  (stored [rows][K], K contiguous): tile = rows x 128 B, 8-row groups 1024 B apart (SBO);
+             one TMA box {32, rows}; a k step of 8 advances the descriptor start by 32 B.
+    MN-major (stored [K][cols], cols contiguous): tile = (cols/32) boxes of {32 cols, 32 k} = 4 KiB each;
+             LBO = 4096 B between 32-column groups, SBO = 1024 B between 8-k groups; a k step of 8
+             advances the start by 1024 B.
+A is K-major for `x @ y`, MN-major for `x^T @ y`; B is MN-major for `x @ y`, K-major for `x @ y^T`.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from functools import cache
+
+from dlgrad_b200.runtime.cuda.compiler import KNAME
+
+BM = 128
+BK = 32
+
+
+@dataclass(frozen=True)
+class TcKernel:
+    name: str
+    source: str
+    grid: tuple
+    threads: int
+    smem: int
+    out_elems: int
+    bn: int
+    stages: int
+
+
+def _cdiv(a, b):
+    return -(-a // b)
+
+
+def pick_bn(N: int) -> int:
+    bn = min(256, _cdiv(N, 32) * 32)
+    if bn > 128 and N % 256 != 0 and N % 128 == 0:
+        bn = 128
+    return bn
+
+
+def _idesc(m: int, n: int, a_mn: bool, b_mn: bool) -> int:
+    """tcgen05 instruction descriptor (upper 32 bits of the idesc operand): c=F32 [4,6), a/b format TF32=2
+    at [7,10)/[10,13), a/b major at 15/16 (1 = MN-major), N>>3 at [17,23), M>>4 at [24,29)."""
+    return (1 << 4) | (2 << 7) | (2 << 10) | (int(a_mn) << 15) | (int(b_mn) << 16) | ((n >> 3) << 17) | ((m >> 4) << 24)
+
+
+@cache
+def matmul_tc(M: int, N: int, K: int, batch: int, a_mn: bool, b_mn: bool, a_bcast: bool, b_bcast: bool,
+              passes: int = 3, bn: int | None = None, stages: int | None = None, hi_inplace: bool = False) -> TcKernel:
+    BN = bn or pick_bn(N)
+    a_tile = BM * BK * 4                 # 16 KiB
+    b_tile = BN * BK * 4
+    per_stage = (a_tile + b_tile) * (2 if passes == 3 else 1)
+    if stages is None:
+        stages = max(2, min(6, (200 * 1024) // per_stage))
+    kblocks = _cdiv(K, BK)
+    stages = min(stages, max(2, kblocks))
+    tmem_cols = 32
+    while tmem_cols < BN:
+        tmem_cols *= 2
+    smem = stages * per_stage + 1024 + 256      # + alignment slack + barriers
+    idesc = _idesc(BM, BN, a_mn, b_mn)
+    # descriptor constants (units of 16 B): K-major: LBO unused(1), SBO = 1024 B; MN-major: LBO = 4096 B, SBO = 1024 B
+    # MN-major fp32/tf32 operands exist only in the SWIZZLE_128B_BASE32B flavour (layout type 1: 32-byte
+    # chunks XOR-ed with the row index, period 4 rows -> k-groups of 4 rows, SBO = 512 B); the TMA
+    # counterpart is CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B.  K-major uses plain SWIZZLE_128B (type 2).
+    a_lbo, a_sbo, a_kstep, a_lt = (256, 32, 64, 1) if a_mn else (1, 64, 2, 2)
+    b_lbo, b_sbo, b_kstep, b_lt = (256, 32, 64, 1) if b_mn else (1, 64, 2, 2)
+    a_boxes = BM // 32 if a_mn else 1
+    b_boxes = BN // 32 if b_mn else 1
+    n_conv = 128
+    a_v4, b_v4 = a_tile // 16, b_tile // 16
+
+    def tma_issue(which, boxes, mn, tile_var, row0):
+        """TMA loads for one stage of operand `which` ('A'/'B'); coordinates are {inner, outer, batch}."""
+        tm = f"tm{which}"
+        z = "0" if (a_bcast if which == "A" else b_bcast) else "z"
+        if mn:      # stored [K][cols]: inner = cols (tile origin row0 + 32*j), outer = k
+            return "\n                ".join(
+                f"tma_load_3d({tile_var} + {j * 4096}u, &{tm}, full_bar, (int)({row0} + {j * 32}u), (int)k0, (int){z});"
+                for j in range(boxes))
+        return f"tma_load_3d({tile_var}, &{tm}, full_bar, (int)k0, (int){row0}, (int){z});"
+
+    split_code = ""
+    if passes == 3:
+        hi_store = "src[i] = hi;" if hi_inplace else ""
+        split_code = f"""
+        // ===== splitter warps: hi/lo decomposition of the staged fp32 tiles =====
+        for (unsigned kb = 0; kb < {kblocks}u; ++kb) {{
+            const unsigned s = kb % {stages}u, ph = (kb / {stages}u) & 1u;
+            mbar_wait(full + s * 8u, ph);
+            float4* src = reinterpret_cast<float4*>(smem_gen + s * {per_stage}u);
+            float4* dst = reinterpret_cast<float4*>(smem_gen + s * {per_stage}u + {a_tile + b_tile}u);
+            #pragma unroll 4
+            for (unsigned i = ctid; i < {a_v4 + b_v4}u; i += {n_conv}u) {{
+                const float4 x = src[i];
+                float4 hi, lo;
+                hi.x = __uint_as_float(__float_as_uint(x.x) & 0xffffe000u); lo.x = x.x - hi.x;
+                hi.y = __uint_as_float(__float_as_uint(x.y) & 0xffffe000u); lo.y = x.y - hi.y;
+                hi.z = __uint_as_float(__float_as_uint(x.z) & 0xffffe000u); lo.z = x.z - hi.z;
+                hi.w = __uint_as_float(__float_as_uint(x.w) & 0xffffe000u); lo.w = x.w - hi.w;
+                {hi_store}
+                dst[i] = lo;
+            }}
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> visible to UMMA
+            mbar_arrive(split + s * 8u);
+        }}"""
+
+    if passes == 3:
+        mma_wait = "mbar_wait(split + s * 8u, ph);"
+        mma_body = f"""
+                    const unsigned long long a_hi = adesc + (unsigned long long)(k * {a_kstep}u);
+                    const unsigned long long b_hi = bdesc + (unsigned long long)(k * {b_kstep}u);
+                    const unsigned long long a_lo = a_hi + {(a_tile + b_tile) // 16}ull;
+                    const unsigned long long b_lo = b_hi + {(a_tile + b_tile) // 16}ull;
+                    umma_tf32(tmem_base, a_lo, b_hi, {idesc}u, (kb | k) != 0u);
+                    umma_tf32(tmem_base, a_hi, b_lo, {idesc}u, 1u);
+                    umma_tf32(tmem_base, a_hi, b_hi, {idesc}u, 1u);"""
+    else:
+        mma_wait = "mbar_wait(full + s * 8u, ph);"
+        mma_body = f"""
+                    umma_tf32(tmem_base, adesc + (unsigned long long)(k * {a_kstep}u),
+                              bdesc + (unsigned long long)(k * {b_kstep}u), {idesc}u, (kb | k) != 0u);"""
+
+    vec_store = N % 4 == 0
+    if vec_store:
+        store = f"""
+                    #pragma unroll
+                    for (int j = 0; j < 32; j += 4) {{
+                        const unsigned col = n0 + c * 32u + j;
+                        if (col < {N}u)
+                            *reinterpret_cast<float4*>(crow + col) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                                                                   __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+                    }}"""
+    else:
+        store = f"""
+                    #pragma unroll
+                    for (int j = 0; j < 32; ++j) {{
+                        const unsigned col = n0 + c * 32u + j;
+                        if (col < {N}u) crow[col] = __uint_as_float(v[j]);
+                    }}"""
+    regs = ", ".join(f"%{i}" for i in range(32))
+    outs = ", ".join(f'"=r"(v[{i}])' for i in range(32))
+
+    src = f"""
+struct alignas(64) TMap {{ unsigned long long opaque[16]; }};
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) {{ return (unsigned)__cvta_generic_to_shared(p); }}
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count));
+}}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}}
+__device__ __forceinline__ void mbar_arrive(unsigned bar) {{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
+}}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {{
+    // try_wait suspends for a HW-defined window; the watchdog turns a protocol bug into a trap
+    // (CUDA error) instead of a hung GPU.
+    const long long t0 = clock64();
+    for (;;) {{
+        unsigned ok;
+        asm volatile("{{\\n\\t.reg .pred p;\\n\\t"
+                     "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\\n\\t"
+                     "selp.b32 %0, 1, 0, p;\\n\\t}}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        if (ok) return;
+        if (clock64() - t0 > 4000000000LL) __trap();
+    }}
+}}
+__device__ __forceinline__ void tma_load_3d(unsigned dst, const TMap* map, unsigned bar, int c0, int c1, int c2) {{
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {{%3, %4, %5}}], [%2];"
+        :: "r"(dst), "l"((unsigned long long)map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}}
+__device__ __forceinline__ void umma_tf32(unsigned tmem_d, unsigned long long adesc, unsigned long long bdesc,
+                                          unsigned idesc, unsigned accumulate) {{
+    asm volatile(
+        "{{\\n\\t.reg .pred p;\\n\\t"
+        "setp.ne.b32 p, %4, 0;\\n\\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\\n\\t}}"
+        :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}}
+__device__ __forceinline__ void umma_commit(unsigned bar) {{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar) : "memory");
+}}
+// shared-memory matrix descriptor: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48), layout type [61,64)
+__device__ __forceinline__ unsigned long long make_desc(unsigned addr, unsigned lbo16, unsigned sbo16, unsigned ltype) {{
+    return (unsigned long long)((addr & 0x3ffffu) >> 4) | ((unsigned long long)lbo16 << 16) |
+           ((unsigned long long)sbo16 << 32) | (1ull << 46) | ((unsigned long long)ltype << 61);
+}}
+
+extern "C" __global__ void __launch_bounds__(192, 1)
+{KNAME}(const __grid_constant__ TMap tmA, const __grid_constant__ TMap tmB, const __grid_constant__ TMap tmC, float* __restrict__ C)
+{{
+    extern __shared__ unsigned char smem_raw[];
+    // SWIZZLE_128B atoms need 1024-byte alignment
+    const unsigned smem = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    unsigned char* smem_gen = smem_raw + (smem - smem_u32(smem_raw));     // same place as a generic pointer
+    const unsigned bars = smem + {stages * per_stage}u;
+    const unsigned full = bars, empty = bars + {stages * 8}u, split = bars + {stages * 16}u, acc_full = bars + {stages * 24}u;
+    __shared__ unsigned tmem_slot;
+    const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    const unsigned n0 = blockIdx.x * {BN}u, m0 = blockIdx.y * {BM}u, z = blockIdx.z;
+
+    if (threadIdx.x == 0) {{
+        for (unsigned s = 0; s < {stages}u; ++s) {{
+            mbar_init(full + s * 8u, 1u);
+            mbar_init(empty + s * 8u, 1u);
+            mbar_init(split + s * 8u, {n_conv}u);
+        }}
+        mbar_init(acc_full, 1u);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }}
+    if (warp == 1) {{
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&tmem_slot)), "n"({tmem_cols}));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }}
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const unsigned tmem_base = tmem_slot;
+
+    if (warp == 0) {{
+        // ===== TMA producer =====
+        if (lane == 0) {{
+            for (unsigned kb = 0; kb < {kblocks}u; ++kb) {{
+                const unsigned s = kb % {stages}u, ph = (kb / {stages}u) & 1u;
+                mbar_wait(empty + s * 8u, ph ^ 1u);
+                const unsigned full_bar = full + s * 8u;
+                const unsigned a_s = smem + s * {per_stage}u, b_s = a_s + {a_tile}u;
+                const unsigned k0 = kb * {BK}u;
+                mbar_expect_tx(full_bar, {a_tile + b_tile}u);
+                {tma_issue("A", a_boxes, a_mn, "a_s", "m0")}
+                {tma_issue("B", b_boxes, b_mn, "b_s", "n0")}
+            }}
+        }}
+    }} else if (warp == 1) {{
+        // ===== MMA issuer (one elected lane) =====
+        if (lane == 0) {{
+            for (unsigned kb = 0; kb < {kblocks}u; ++kb) {{
+                const unsigned s = kb % {stages}u, ph = (kb / {stages}u) & 1u;
+                {mma_wait}
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const unsigned a_s = smem + s * {per_stage}u, b_s = a_s + {a_tile}u;
+                const unsigned long long adesc = make_desc(a_s, {a_lbo}u, {a_sbo}u, {a_lt}u);
+                const unsigned long long bdesc = make_desc(b_s, {b_lbo}u, {b_sbo}u, {b_lt}u);
+                #pragma unroll
+                for (unsigned k = 0; k < {BK // 8}u; ++k) {{{mma_body}
+                }}
+                umma_commit(empty + s * 8u);          // frees the smem slot when these MMAs retire
+            }}
+            umma_commit(acc_full);
+        }}
+    }} else {{
+        const unsigned ctid = threadIdx.x - 64u;{split_code}
+        // ===== epilogue: TMEM -> registers -> global =====
+        mbar_wait(acc_full, 0u);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const unsigned q = warp & 3u;                       // TMEM lane quarter this warp may read
+        const unsigned row = m0 + q * 32u + lane;
+        float* crow = C + ((size_t)z * {M}u + row) * {N}u;
+        #pragma unroll 1
+        for (unsigned c = 0; c < {BN // 32}u; ++c) {{
+            unsigned v[32];
+            const unsigned taddr = tmem_base + ((q * 32u) << 16) + c * 32u;
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {{{regs}}}, [%32];" : {outs} : "r"(taddr));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (row < {M}u) {{{store}
+            }}
+        }}
+    }}
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {{
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "n"({tmem_cols}));
+    }}
+}}
+"""
+    grid = (_cdiv(N, BN), _cdiv(M, BM), batch)
+    return TcKernel(f"mm_tc{passes}", src, grid, 192, smem, batch * M * N, BN, stages)
+
+
+def tmap_descs(M: int, N: int, K: int, batch: int, a_mn: bool, b_mn: bool, a_bcast: bool, b_bcast: bool, BN: int):
+    """(dims, strides_bytes, box) triples for A, B and C in the shim's dlg_tmap_desc layout."""
+    def operand(rows, mn, bcast, tile_rows):
+        nb = 1 if bcast else batch
+        if mn:     # stored [K][rows]
+            return dict(rank=3, dims=(rows, K, nb), strides=(rows * 4, rows * K * 4), box=(32, BK, 1), swizzle=4)
+        return dict(rank=3, dims=(K, rows, nb), strides=(K * 4, rows * K * 4), box=(BK, tile_rows, 1), swizzle=3)
+    a = operand(M, a_mn, a_bcast, BM)
+    b = operand(N, b_mn, b_bcast, BN)
+    c = dict(rank=3, dims=(N, M, batch), strides=(N * 4, M * N * 4), box=(32, 32, 1), swizzle=0)
+    return a, b, c

@@ -226,7 +226,8 @@ int encode_tmap(CUtensorMap *out, const dlg_tmap_desc &d, const void *base) {
     cuuint64_t strides[2] = {d.strides_bytes[0], d.strides_bytes[1]};
     cuuint32_t box[3] = {d.box[0], d.box[1], d.box[2]};
     cuuint32_t estr[3] = {1, 1, 1};
-    CUtensorMapSwizzle sw = d.swizzle == 3   ? CU_TENSOR_MAP_SWIZZLE_128B
+    CUtensorMapSwizzle sw = d.swizzle == 4   ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B
+                            : d.swizzle == 3 ? CU_TENSOR_MAP_SWIZZLE_128B
                             : d.swizzle == 2 ? CU_TENSOR_MAP_SWIZZLE_64B
                             : d.swizzle == 1 ? CU_TENSOR_MAP_SWIZZLE_32B
                                              : CU_TENSOR_MAP_SWIZZLE_NONE;

@@ -1,7 +1,83 @@
-"""Tensor-core (tcgen05 + TMEM + TMA, 3xTF32) matmul plans.  Filled in by codegen/cuda_tcgen05.py;
-until a shape is supported `try_build` returns None and the SIMT kernel runs."""
+"""Plans for the tcgen05 / TMEM / TMA 3xTF32 matmul (codegen/cuda_tcgen05.py).
+
+`try_build` returns a MatmulPlan when the shape qualifies for TMA (16-byte pitches, operands either
+fully batched or fully broadcast) and is big enough to be worth a 128-row tile; otherwise None and the
+exact-fp32 SIMT kernel runs.  DLGRAD_TC_PASSES=1 selects single-pass TF32 (debug only: ~1e-3 accuracy).
+"""
 from __future__ import annotations
 
+import os
 
-def try_build(M, N, K, batch, a_bs, b_bs, tx, ty, aligned):
-    return None
+from dlgrad_b200.codegen import cuda_tcgen05 as tc
+from dlgrad_b200.helpers import prod_
+from dlgrad_b200.runtime.cuda import compiler, shim
+
+ffi, lib, NULL = shim.ffi, shim.lib, shim.NULL
+PASSES = int(os.environ.get("DLGRAD_TC_PASSES", "3"))
+ENABLED = os.environ.get("DLGRAD_TC", "1") != "0"
+MIN_FLOPS = 1 << 22
+
+
+def _tmap(d: dict):
+    t = ffi.new("dlg_tmap_desc *")
+    t.rank = d["rank"]
+    for i, v in enumerate(d["dims"]):
+        t.dims[i] = v
+    for i, v in enumerate(d["strides"]):
+        t.strides_bytes[i] = v
+    for i, v in enumerate(d["box"]):
+        t.box[i] = v
+    t.swizzle = d["swizzle"]
+    return t
+
+
+def qualifies(M, N, K, batch, a_bs, b_bs, tx, ty, aligned, force: bool = False) -> tuple | None:
+    if not (ENABLED and aligned):
+        return None
+    nb = prod_(batch)
+    full = (M * K * batch[1], M * K) if batch[1] > 1 else (M * K, 0)
+
+    def mode(bs, mat):
+        # fully batched (contiguous over the flattened batch) or fully broadcast
+        if nb == 1 or bs == (0, 0):
+            return "bcast" if nb > 1 else "full"
+        want = (mat * batch[1] if batch[0] > 1 else 0, mat if batch[1] > 1 else 0)
+        return "full" if tuple(bs) == want else None
+    am, bm = mode(a_bs, M * K), mode(b_bs, K * N)
+    if am is None or bm is None:
+        return None
+    a_mn, b_mn = bool(tx), not bool(ty)
+    if (M if a_mn else K) % 4 or (N if b_mn else K) % 4:
+        return None                                   # TMA needs 16-byte global pitches
+    if not force and (K < 8 or N < 8 or M < 16 or 2.0 * M * N * K * nb < MIN_FLOPS):
+        return None
+    _ = full
+    return a_mn, b_mn, am == "bcast", bm == "bcast", nb
+
+
+def try_build(M, N, K, batch, a_bs, b_bs, tx, ty, aligned, passes: int | None = None, bn: int | None = None,
+              stages: int | None = None, hi_inplace: bool = False, force: bool = False):
+    q = qualifies(M, N, K, batch, a_bs, b_bs, tx, ty, aligned, force)
+    if q is None:
+        return None
+    a_mn, b_mn, a_bc, b_bc, nb = q
+    passes = passes or PASSES
+    k = tc.matmul_tc(M, N, K, nb, a_mn, b_mn, a_bc, b_bc, passes, bn, stages, hi_inplace)
+    shim.init()
+    fn = compiler.get_function(k.name, k.source)
+    da, db, dc = tc.tmap_descs(M, N, K, nb, a_mn, b_mn, a_bc, b_bc, k.bn)
+    ta, tb, tcd = _tmap(da), _tmap(db), _tmap(dc)
+    plan = lib.dlg_mm_plan_create(fn, k.grid[0], k.grid[1], k.grid[2], k.threads, k.smem, 1, k.out_elems * 4,
+                                  ta, tb, tcd)
+    if plan == NULL:
+        raise RuntimeError("dlg_mm_plan_create failed: " + shim.last_error())
+    nbytes = k.out_elems * 4
+
+    def run(a, b):
+        out = lib.dlg_mm_plan_run(plan, a, b)
+        if out == NULL:
+            raise RuntimeError("tensor-core matmul launch failed: " + shim.last_error())
+        return shim.own(out, nbytes)
+
+    from dlgrad_b200.runtime.cuda.matmul import MatmulPlan
+    return MatmulPlan(run, 2.0 * nb * M * N * K, (f"tc{passes}", M, N, K, nb))

@@ -96,7 +96,7 @@ typedef struct dlg_tmap_desc {
     uint64_t dims[3];               /* innermost first, elements                            */
     uint64_t strides_bytes[2];      /* strides of dims[1], dims[2]                          */
     uint32_t box[3];                /* box size per dim, elements                           */
-    uint32_t swizzle;               /* 0 none, 1 32B, 2 64B, 3 128B                         */
+    uint32_t swizzle;               /* 0 none, 1 32B, 2 64B, 3 128B, 4 128B with 32B atoms  */
 } dlg_tmap_desc;
 
 void *dlg_mm_plan_create(void *fn, unsigned gx, unsigned gy, unsigned gz, unsigned threads,

@@ -1,0 +1,107 @@
+"""GPU probe for the tcgen05 matmul: correctness vs float64 for every operand-major combination, the
+TF32 input-conversion semantics of tcgen05 (truncate or round), and timing.  Run under gpurun."""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from dlgrad_b200.runtime.cuda import matmul_tc, profile, shim, transfer  # noqa: E402
+
+shim.init()
+rng = np.random.default_rng(0)
+results = {}
+
+
+def run(M, N, K, nb=1, tx=False, ty=False, a_b=False, b_b=False, passes=3, bn=None, stages=None, hi_inplace=True,
+        a=None, b=None, time_it=0):
+    batch = (1, nb)
+    if a is None:
+        a = (rng.random(((1 if a_b else nb), K, M) if tx else ((1 if a_b else nb), M, K), dtype=np.float32) - 0.5).astype(np.float32)
+    if b is None:
+        b = (rng.random(((1 if b_b else nb), N, K) if ty else ((1 if b_b else nb), K, N), dtype=np.float32) - 0.5).astype(np.float32)
+    a_bs = (0, 0) if (a_b or nb == 1) else (0, M * K)
+    b_bs = (0, 0) if (b_b or nb == 1) else (0, K * N)
+    plan = matmul_tc.try_build(M, N, K, batch, a_bs, b_bs, tx, ty, True, passes=passes, bn=bn, stages=stages,
+                               hi_inplace=hi_inplace, force=True)
+    assert plan is not None, "shape did not qualify"
+    da, db = transfer.upload_numpy(a), transfer.upload_numpy(b)
+    out = plan(da, db)
+    shim.synchronize()
+    c = transfer.download(out, nb * M * N).reshape(nb, M, N)
+    A = a.astype(np.float64)
+    B = b.astype(np.float64)
+    A = A.transpose(0, 2, 1) if tx else A
+    B = B.transpose(0, 2, 1) if ty else B
+    ref = A @ B
+    err = float(np.abs(c - ref).max() / np.abs(ref).max())
+    ms = None
+    if time_it:
+        for _ in range(2):
+            plan(da, db)
+        e0 = profile.Event().record()
+        for _ in range(time_it):
+            plan(da, db)
+        e1 = profile.Event().record()
+        e1.sync()
+        ms = e1.ms_since(e0) / time_it
+    return err, ms, c
+
+
+def case(name, **kw):
+    t0 = time.time()
+    try:
+        err, ms, _ = run(**kw)
+        tf = (2.0 * kw["M"] * kw["N"] * kw["K"] * kw.get("nb", 1) / (ms * 1e-3) / 1e12) if ms else None
+        results[name] = {"rel_err": err, "ms": ms, "tflops": tf}
+        print(f"{name:38s} rel_err {err:.3e}" + (f"  {ms:.3f} ms  {tf:.1f} TFLOP/s" if ms else ""), flush=True)
+    except Exception as exc:  # keep going: every case is independent evidence
+        results[name] = {"error": repr(exc)[:300]}
+        print(f"{name:38s} FAILED {exc!r}"[:400], flush=True)
+    return time.time() - t0
+
+
+which = sys.argv[1] if len(sys.argv) > 1 else "all"
+if which in ("all", "sem"):
+    # conversion semantics: x = 1 + 2^-11 + 2^-12; truncation -> 1.0, round-to-nearest -> 1 + 2^-10
+    x = np.float32(1.0 + 2.0 ** -11 + 2.0 ** -12)
+    a = np.full((1, 128, 32), x, dtype=np.float32)
+    b = np.zeros((1, 32, 32), dtype=np.float32)
+    b[0, 0, :] = 1.0
+    try:
+        _, _, c = run(128, 32, 32, passes=1, a=a, b=b)
+        v = float(c[0, 0, 0])
+        results["tf32_input_conversion"] = {"value": v, "mode": "truncate" if v == 1.0 else ("round" if v == 1.0 + 2.0 ** -10 else "other")}
+        print("tf32 input conversion:", results["tf32_input_conversion"], flush=True)
+    except Exception as exc:
+        print("semantics probe failed", repr(exc)[:300], flush=True)
+if which in ("all", "p1"):
+    case("p1 NN 128x128x128", M=128, N=128, K=128, passes=1)
+    case("p1 NN 256x256x64 bn256", M=256, N=256, K=64, passes=1)
+    case("p1 NT 128x128x128", M=128, N=128, K=128, ty=True, passes=1)
+    case("p1 TN 128x128x128", M=128, N=128, K=128, tx=True, passes=1)
+if which in ("all", "p3"):
+    case("p3 NN 128x128x128", M=128, N=128, K=128)
+    case("p3 NN 128x128x128 raw-hi", M=128, N=128, K=128, hi_inplace=False)
+    case("p3 NT 128x128x128", M=128, N=128, K=128, ty=True)
+    case("p3 TN 128x128x128", M=128, N=128, K=128, tx=True)
+    case("p3 NN 200x96x72 ragged", M=200, N=96, K=72)
+    case("p3 NN batched 8x1024x96x768 bB", M=1024, N=96, K=768, nb=8, b_b=True)
+    case("p3 NN batched 96x1024x64x1024", M=1024, N=64, K=1024, nb=96)
+    case("p3 NT batched 96x1024x1024x64", M=1024, N=1024, K=64, nb=96, ty=True)
+    case("p3 TN batched 96x1024x64x1024", M=1024, N=64, K=1024, nb=96, tx=True)
+if which in ("all", "perf"):
+    case("perf p3 NN 4096^3 bn256", M=4096, N=4096, K=4096, time_it=5)
+    case("perf p3 NN 4096^3 bn128", M=4096, N=4096, K=4096, bn=128, time_it=5)
+    case("perf p3 NN 4096^3 raw-hi bn256", M=4096, N=4096, K=4096, hi_inplace=False, time_it=5)
+    case("perf p1 NN 4096^3 bn256", M=4096, N=4096, K=4096, passes=1, time_it=5)
+    case("perf p3 NT 4096^3", M=4096, N=4096, K=4096, ty=True, time_it=5)
+    case("perf p3 TN 4096^3", M=4096, N=4096, K=4096, tx=True, time_it=5)
+    case("perf p3 NN 8192x768x768 bB", M=8192, N=768, K=768, b_b=True, time_it=10)
+    case("perf p3 NN 8192x3072x768", M=8192, N=3072, K=768, time_it=10)
+    case("perf p3 TN 768x3072x8192", M=768, N=3072, K=8192, tx=True, time_it=10)
+os.makedirs("gpurun_out", exist_ok=True)
+with open(f"gpurun_out/tc_probe_{which}.json", "w") as f:
+    json.dump(results, f, indent=1)

@@ -193,7 +193,8 @@ def test_config2_matmul_1024_fwd_bwd_vs_oracle(oracle):
 
 def test_config2_matmul_4096_properties():
     """4096^3 is ~30 s on the CPU oracle, so full size is checked through size-independent properties:
-    A @ I == A exactly, sampled rows against a float64 dot product, and linearity in A."""
+    A @ I == A (to 3xTF32 resolution), sampled rows against a float64 dot product on U[0,1) inputs (the
+    worst case for accumulator bias), and exact linearity under power-of-two scaling."""
     from dlgrad_b200 import Tensor
     rng = np.random.default_rng(2)
     n = 4096
@@ -201,7 +202,9 @@ def test_config2_matmul_4096_properties():
     b = rng.random((n, n), dtype=np.float32)
     A, B = Tensor(a, device="cuda"), Tensor(b, device="cuda")
     eye = Tensor(np.eye(n, dtype=np.float32), device="cuda")
-    check((A @ eye).numpy(), a, exact=True, what="A @ I")
+    # 3xTF32: A is carried as hi + lo with lo truncated to 11 significant bits, so A @ I reproduces A
+    # to 2^-21 relative, not bit for bit
+    runner.rel_check(check, (A @ eye).numpy(), a, 1e-6, "A @ I")
     C = (A @ B).numpy()
     rows = rng.integers(0, n, size=8)
     ref = a[rows].astype(np.float64) @ b.astype(np.float64)
