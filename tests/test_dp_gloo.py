@@ -1,0 +1,99 @@
+"""Data-parallel host logic on CPU: world_size-2 `gloo` run (no GPU).
+
+What is checked
+  * the flat-bucket layout used by dlgrad_b200.distributed (offsets, alignment, coverage);
+  * the DP arithmetic the GPU path relies on: each rank back-propagates its OWN half of the batch on the
+    CPU oracle, gradients are summed across ranks (gloo all_reduce standing in for ncclAllReduce) and the
+    optimizer runs with grad_scale = 1/world — the updated weights must equal a single-process step on
+    the concatenated batch (the reference's CE gradient is a per-rank mean);
+  * rank-dependent data seeds and identical weight seeds, as bench.py sets them up.
+"""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+from tests import models
+
+
+def _free_port() -> int:
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank: int, world: int, port: int, out_dir: str) -> None:
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch
+    import torch.distributed as dist
+
+    import dlgrad_b200 as dl
+    from dlgrad_b200 import Tensor, nn
+    from dlgrad_b200.distributed import shard_offsets
+    from oracle import backend
+    backend.install()
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    cfg = models.GPTConfig(vocab_size=17, block_size=16, n_layer=1, n_head=2, n_embd=32, device="cpu")
+    gpt = models.GPT(dl, cfg, np.random.default_rng(0))          # identical weights on every rank
+    params = nn.utils.get_parameters(gpt)
+    opt = nn.optim.Adam(params, lr=1e-3)
+    opt.grad_scale = 1.0 / world
+    full_x, full_y = models.gpt_batch(cfg, 4 * world, np.random.default_rng(7))
+    x, y = full_x[rank * 4:(rank + 1) * 4], full_y[rank * 4:(rank + 1) * 4]   # this rank's shard of the batch
+    opt.zero_grad()
+    _, loss = gpt(Tensor(x.copy()), Tensor(y.copy()))
+    loss.backward()
+    live = [p for p in params if p.grad is not None]
+    sizes = [p.grad.numel for p in live]
+    offs = shard_offsets(sizes)
+    flat = np.zeros(offs[-1], dtype=np.float32)
+    for p, o, n in zip(live, offs, sizes):
+        flat[o:o + n] = p.grad.numpy().reshape(-1)
+    t = torch.from_numpy(flat)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)                      # the one exchange per step
+    for p, o, n in zip(live, offs, sizes):
+        p.grad = Tensor(flat[o:o + n].reshape(p.grad.shape).copy())
+    opt.step()
+    np.savez(os.path.join(out_dir, f"rank{rank}.npz"), loss=float(loss.numpy()),
+             wte=gpt.wte.weight.numpy(), q=gpt.blocks[0].attn.q_proj.weight.numpy(), head=gpt.lm_head.weight.numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_shard_offsets_layout():
+    from dlgrad_b200.distributed import shard_offsets
+    sizes = [96 * 768, 1, 7, 768, 3072 * 768]
+    offs = shard_offsets(sizes)
+    assert len(offs) == len(sizes) + 1 and offs[0] == 0
+    for o, n, nxt in zip(offs, sizes, offs[1:]):
+        assert o % 64 == 0 and nxt >= o + n          # 256-byte aligned, non-overlapping
+    assert offs[-1] % 64 == 0
+
+
+@pytest.mark.timeout(300)
+def test_two_rank_dp_step_equals_full_batch_step(tmp_path):
+    import torch.multiprocessing as mp
+    world, port = 2, _free_port()
+    mp.start_processes(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True, start_method="spawn")
+    r0, r1 = np.load(tmp_path / "rank0.npz"), np.load(tmp_path / "rank1.npz")
+    for k in ("wte", "q", "head"):
+        assert np.array_equal(r0[k], r1[k]), f"ranks diverged on {k}"
+    # single process, full batch of 8
+    import dlgrad_b200 as dl
+    from dlgrad_b200 import Tensor, nn
+    from oracle import backend
+    backend.install()
+    cfg = models.GPTConfig(vocab_size=17, block_size=16, n_layer=1, n_head=2, n_embd=32, device="cpu")
+    gpt = models.GPT(dl, cfg, np.random.default_rng(0))
+    opt = nn.optim.Adam(nn.utils.get_parameters(gpt), lr=1e-3)
+    full_x, full_y = models.gpt_batch(cfg, 8, np.random.default_rng(7))
+    opt.zero_grad()
+    _, loss = gpt(Tensor(full_x.copy()), Tensor(full_y.copy()))
+    loss.backward()
+    opt.step()
+    # the sum-reduced loss adds across ranks; updated weights agree to fp32 rounding of the split sums
+    assert abs((float(r0["loss"]) + float(r1["loss"])) - float(loss.numpy())) <= 1e-5 * abs(float(loss.numpy()))
+    for k, ref in (("wte", gpt.wte.weight.numpy()), ("q", gpt.blocks[0].attn.q_proj.weight.numpy()),
+                   ("head", gpt.lm_head.weight.numpy())):
+        np.testing.assert_allclose(r0[k], ref, rtol=1e-5, atol=1e-6, err_msg=k)
