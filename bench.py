@@ -189,43 +189,70 @@ def train_step(gpt, opt, params, x, y, world):
     return loss
 
 
-def op_microbench(peaks: dict) -> dict:
+def op_microbench(peaks: dict, only: tuple | None = None) -> dict:
     """configs[1]: broadcast add/mul and sum/max over axis on 4096x4096 fp32; matmul 4096^3 fwd.
-    Each op: 3 warm-ups, then 20 launches timed with events; between launches a 512 MB buffer is
-    rewritten so no input survives in the 126 MB L2."""
+
+    Timing: every op is launched ROUNDS x SETS times back to back (captured in one CUDA graph, replayed
+    between ONE pair of CUDA events), walking round-robin over SETS = 6 independent input sets (6 x 64 MiB per
+    operand = 384 MiB > 3 x L2), so no launch finds its input in the 126 MB L2 ("inputs larger than L2") and
+    neither per-launch event latency nor Python dispatch is billed to a 20 us kernel.  2 warm-up rounds.  A device-to-device copy of the same 64 MiB arrays is timed
+    the same way as the size-matched ceiling (MEASURED_PEAKS' copy figure is for 2 GiB buffers)."""
     from dlgrad_b200 import Tensor
     from dlgrad_b200.runtime.cuda import profile, shim
     rng = np.random.default_rng(0)
-    n = 4096
-    a, b = Tensor(rng.random((n, n), dtype=np.float32), device="cuda"), Tensor(rng.random((n, n), dtype=np.float32), device="cuda")
-    row, col = Tensor(rng.random((1, n), dtype=np.float32), device="cuda"), Tensor(rng.random((n, 1), dtype=np.float32), device="cuda")
-    flush = Tensor(np.zeros((128, 1024, 1024), dtype=np.float32), device="cuda")
-    MB = 1e6
-    full, half = 3 * n * n * 4, 2 * n * n * 4
-    specs = [("add_same", lambda: a + b, full, "GB/s"), ("mul_same", lambda: a * b, full, "GB/s"),
-             ("add_row", lambda: a + row, half, "GB/s"), ("mul_col", lambda: a * col, half, "GB/s"),
-             ("sum_axis0", lambda: a.sum(dim=0), n * n * 4, "GB/s"), ("sum_axis1", lambda: a.sum(dim=1), n * n * 4, "GB/s"),
-             ("max_axis0", lambda: a.max(dim=0), n * n * 4, "GB/s"), ("max_axis1", lambda: a.max(dim=1), n * n * 4, "GB/s"),
-             ("exp", lambda: a.exp(), half, "GB/s"), ("transpose", lambda: a.T, half, "GB/s"),
-             ("matmul_4096", lambda: a @ b, 2.0 * n ** 3, "TFLOP/s")]
+    n, SETS, ROUNDS = 4096, 6, 4
+    mk = lambda *shape: [Tensor(rng.random(shape, dtype=np.float32), device="cuda") for _ in range(SETS)]   # noqa: E731
+    a, b, row, col = mk(n, n), mk(n, n), mk(1, n), mk(n, 1)
+    full, half, one = 3 * n * n * 4, 2 * n * n * 4, n * n * 4
+    specs = [("add_same", lambda i: a[i] + b[i], full, "GB/s"), ("mul_same", lambda i: a[i] * b[i], full, "GB/s"),
+             ("add_row", lambda i: a[i] + row[i], half, "GB/s"), ("mul_col", lambda i: a[i] * col[i], half, "GB/s"),
+             ("sum_axis0", lambda i: a[i].sum(dim=0), one, "GB/s"), ("sum_axis1", lambda i: a[i].sum(dim=1), one, "GB/s"),
+             ("max_axis0", lambda i: a[i].max(dim=0), one, "GB/s"), ("max_axis1", lambda i: a[i].max(dim=1), one, "GB/s"),
+             ("sum_all", lambda i: a[i].sum(), one, "GB/s"),
+             ("exp", lambda i: a[i].exp(), half, "GB/s"), ("transpose", lambda i: a[i].T, half, "GB/s"),
+             ("softmax_rows", lambda i: a[i].softmax(dim=1), half, "GB/s"),
+             ("matmul_4096", lambda i: a[i] @ b[i], 2.0 * n ** 3, "TFLOP/s")]
     out = {}
-    for name, fn, work, unit in specs:
-        for _ in range(3):
-            fn()
-        ms = []
-        for _ in range(20 if unit == "GB/s" else 5):
-            _ = flush * 1.0
+    scratch = [shim.alloc(one) for _ in range(SETS)]
+
+    def timed(fn, rounds):
+        """Seconds per launch.  The ROUNDS x SETS launches are captured into ONE CUDA graph and the graph is
+        replayed between a pair of events, so host dispatch (~10 us per op in Python) is not billed to
+        kernels that run for 10-30 us; the replay with the best time of three is reported."""
+        for r in range(2):
+            for i in range(SETS):
+                fn(i)
+        shim.synchronize()
+        shim.check(shim.lib.dlg_graph_begin(), "dlg_graph_begin")
+        keep = []
+        for r in range(rounds):
+            for i in range(SETS):
+                keep.append(fn(i))          # outputs stay referenced: no block is recycled inside the graph
+        graph = shim.lib.dlg_graph_end()
+        if graph == shim.NULL:
+            raise RuntimeError("graph capture failed: " + shim.last_error())
+        best = float("inf")
+        for _ in range(4):
             e0 = profile.Event().record()
-            r = fn()
+            shim.check(shim.lib.dlg_graph_launch(graph), "dlg_graph_launch")
             e1 = profile.Event().record()
             e1.sync()
-            ms.append(e1.ms_since(e0))
-            del r
-        t = float(np.median(ms)) * 1e-3
+            best = min(best, e1.ms_since(e0))
+        shim.lib.dlg_graph_destroy(graph)
+        del keep
+        return best * 1e-3 / (rounds * SETS)
+
+    t = timed(lambda i: shim.check(shim.lib.dlg_d2d(scratch[i], a[i].data.ptr, one), "d2d"), ROUNDS)
+    out["d2d_copy_same_size"] = {"achieved": half / t / 1e9, "unit": "GB/s", "ms": t * 1e3,
+                                 "frac_of_hbm_peak": half / t / 1e9 / peaks["hbm_gbs"], "algorithmic_MB": half / 1e6}
+    for name, fn, work, unit in specs:
+        if only and name not in only:
+            continue
+        t = timed(fn, ROUNDS if unit == "GB/s" else 2)
         if unit == "GB/s":
             ach = work / t / 1e9
             out[name] = {"achieved": ach, "unit": unit, "ms": t * 1e3, "frac_of_hbm_peak": ach / peaks["hbm_gbs"],
-                         "algorithmic_MB": work / MB}
+                         "algorithmic_MB": work / 1e6}
         else:
             ach = work / t / 1e12
             out[name] = {"achieved": ach, "unit": unit, "ms": t * 1e3,
@@ -271,6 +298,27 @@ def run_b200(args) -> None:
     for i in range(args.warmup):
         loss = train_step(gpt, opt, params, *dev_batches[i % 4], world)
     _ = loss.numpy() if args.warmup else None
+
+    if args.profile:
+        # every launch bracketed by events (serialises nothing, but adds event overhead): shares, not a bench value
+        profile.kernel_timer = profile.KernelTimer()
+        profile.matmul_timer = profile.KernelTimer()
+        nsteps = 3
+        e0 = profile.Event().record()
+        for i in range(nsteps):
+            loss = train_step(gpt, opt, params, *dev_batches[i % 4], world)
+        e1 = profile.Event().record()
+        e1.sync()
+        kt, mt = profile.kernel_timer.collect(), profile.matmul_timer.collect()
+        profile.kernel_timer = profile.matmul_timer = None
+        tot = e1.ms_since(e0) / nsteps
+        print(f"step {tot:.2f} ms; generated-kernel launches {kt['launches'] / nsteps:.0f}/step {kt['ms'] / nsteps:.2f} ms; "
+              f"matmul launches {mt['launches'] / nsteps:.0f}/step {mt['ms'] / nsteps:.2f} ms")
+        for tag, v in sorted(kt["by_tag"].items(), key=lambda kv: -kv[1][1]):
+            print(f"  {tag[0]:24s} n/step={v[0] / nsteps:7.1f}  ms/step={v[1] / nsteps:8.3f}  avg_us={1e3 * v[1] / v[0]:8.1f}")
+        for tag, v in sorted(mt["by_tag"].items(), key=lambda kv: -kv[1][1]):
+            print(f"  mm {tag}  n/step={v[0] / nsteps:6.1f}  ms/step={v[1] / nsteps:7.3f}  TF/s={v[2] / (v[1] * 1e-3) / 1e12:7.1f}")
+        return
 
     peaks = load_peaks()
     # ---- region A: device-resident inputs ----------------------------------------------------------
@@ -335,7 +383,10 @@ def run_b200(args) -> None:
                      "frac": mm_tflops / peak_3xtf32 if peak_3xtf32 else None, "traffic": None,
                      "peak_note": f"3xTF32 = sustained bf16 {peaks['bf16_sustained']} TF/s / 6 ({peaks['source']}: "
                                   "MEASURED_PEAKS.json has no TF32 entry; TF32 dense = bf16/2, 3 MMAs per product)",
-                     "matmul_share_of_step": mm["ms"] / ms_a if ms_a else None, "matmul_launches": mm["launches"]},
+                     "matmul_share_of_step": mm["ms"] / ms_a if ms_a else None, "matmul_launches": mm["launches"],
+                     "by_shape": [{"kernel": t[0], "M": t[1], "N": t[2], "K": t[3], "batch": t[4], "launches": v[0],
+                                   "ms_per_step": v[1] / args.steps, "tflops": v[2] / (v[1] * 1e-3) / 1e12 if v[1] else None}
+                                  for t, v in sorted(mm["by_tag"].items(), key=lambda kv: -kv[1][1])[:12]]},
     }
     if world == 1 and not args.no_cpu:
         t, sample = cpu_block_sample(cfg_kw)
@@ -361,7 +412,16 @@ def main() -> None:
     ap.add_argument("--no-ops", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--prebuild", action="store_true", help="compile-only census (used by __graft_entry__.build)")
+    ap.add_argument("--ops-only", action="store_true", help="run only the configs[1] op microbenches")
+    ap.add_argument("--profile", action="store_true", help="per-kernel-family CUDA-event breakdown of 3 steps (not a bench value)")
     args = ap.parse_args()
+    if args.ops_only:
+        from dlgrad_b200.runtime.cuda import shim
+        shim.init(int(os.environ.get("LOCAL_RANK", "0")))
+        res = op_microbench(load_peaks())
+        for k, v in res.items():
+            print(k, json.dumps({a: (round(b, 4) if isinstance(b, float) else b) for a, b in v.items()}))
+        return
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -15,6 +15,8 @@ Differences from the reference that are deliberate:
 """
 from __future__ import annotations
 
+import weakref
+
 from dlgrad_b200.device import Device, as_device
 from dlgrad_b200.dispatch import dispatcher
 from dlgrad_b200.dtype import CDataPtr, DType, Scalar
@@ -65,17 +67,78 @@ def _host_compute_enabled() -> bool:
     return dispatcher.has(BinaryOps.ADD, _CPU)
 
 
+LAZY_MIN_NUMEL = 1 << 16      # pointwise producers below this size are not worth deferring
+_pending_buffers: "weakref.WeakSet[Buffer]" = None  # type: ignore[assignment]  (created below)
+
+
+def flush_pending(written: tuple = ()) -> None:
+    """Materialise deferred buffers before an IN-PLACE write (optimizer steps, the cross-entropy in-place
+    subtract, copy_from): a deferred producer reads its sources when it runs, so it must run before one of
+    them is overwritten.  With `written` (the Buffers about to be mutated) only chains that read one of
+    them are forced; without it every pending buffer is."""
+    if not _pending_buffers:
+        return
+    ids = {id(w) for w in written}
+    for b in list(_pending_buffers):
+        if b._pending is None:
+            _pending_buffers.discard(b)
+            continue
+        if ids and not _reads_any(b, ids):
+            continue
+        _ = b.ptr
+        _pending_buffers.discard(b)
+
+
+def _reads_any(b: "Buffer", ids: set) -> bool:
+    stack = [b]
+    while stack:
+        cur = stack.pop()
+        if id(cur) in ids:
+            return True
+        pend = cur._pending
+        if pend is not None:
+            stack.extend(x for x in pend[1:] if isinstance(x, Buffer))
+    return False
+
+
 class Buffer:
-    __slots__ = ("ptr", "metadata", "scalar", "aligned", "_keep")
+    __slots__ = ("_ptr", "_pending", "metadata", "scalar", "aligned", "_keep", "__weakref__")
 
     def __init__(self, data: CDataPtr, shape: tuple, device: str | Device | None = _CPU,
                  dtype: str | DType | None = _F32, **kwargs) -> None:
-        self.ptr = data
+        self._ptr = data
+        self._pending = None                     # deferred producer (CUDA only), see _deferred()
         self.metadata = BufferMetadata(tuple(shape), dtype if isinstance(dtype, DType) else _F32,
                                        device if isinstance(device, Device) else as_device(device))
         self.scalar = kwargs.get("scalar")       # python float for host 0-d scalars
         self.aligned = kwargs.get("aligned", True)   # 16-byte aligned base (false for odd-offset slices)
         self._keep = kwargs.get("keep")          # object that owns the memory `ptr` points into
+
+    # ------------------------------------------------------------------ deferred pointwise producers
+    # A CUDA Buffer may be created WITHOUT running its kernel: `_pending` records a cheap pointwise
+    # producer — ("scale", src, s) for `src * python_scalar`, ("mfill", src, mask, val) for masked_fill,
+    # ("softmax_bwd", y, g, dim, kind) for the row backward.  Reading `.ptr` materialises it (one fused
+    # kernel for the whole pending chain); consumers that can fold the chain into their own kernel
+    # (softmax forward, and the chain materialiser itself) never trigger the intermediate writes.  The
+    # values are identical either way; only the number of passes over HBM changes.
+    @property
+    def ptr(self) -> CDataPtr:
+        if self._pending is not None:
+            from dlgrad_b200.runtime.cuda import ops as _cuda_ops
+            _cuda_ops.materialize(self)
+        return self._ptr
+
+    @ptr.setter
+    def ptr(self, value: CDataPtr) -> None:
+        self._ptr = value
+        self._pending = None
+
+    @staticmethod
+    def _deferred(pending: tuple, shape: tuple, dtype: DType = _F32) -> "Buffer":
+        b = Buffer(None, shape, _CUDA, dtype)
+        b._pending = pending
+        _pending_buffers.add(b)
+        return b
 
     # ------------------------------------------------------------------ construction
     @staticmethod
@@ -308,6 +371,8 @@ class Buffer:
     def masked_fill(x: "Buffer", mask: "Buffer", val: Scalar) -> "Buffer":
         out_shape = get_broadcast_shape(x.shape, mask.shape)
         dev = Buffer._route(x, mask)
+        if dev is _CUDA and out_shape == x.shape and x.numel >= LAZY_MIN_NUMEL:
+            return Buffer._deferred(("mfill", x, mask, float(val)), out_shape, x.dtype)
         return x._like(_dispatch(op=UnaryOps.MASKED_FILL, device=dev, x=x, mask=mask, val=val,
                                  out_shape=out_shape), out_shape, dev)
 
@@ -341,6 +406,11 @@ class Buffer:
         # for the one-sided broadcasts it supports that equals the broadcast shape used here.
         out_shape = get_broadcast_shape(self.shape, other.shape)
         dev = Buffer._route(self, other)
+        if op is BinaryOps.MUL and dev is _CUDA:
+            if other.scalar is not None and self.scalar is None and self.numel >= LAZY_MIN_NUMEL:
+                return Buffer._deferred(("scale", self, float(other.scalar)), out_shape, self.dtype)
+            if self.scalar is not None and other.scalar is None and other.numel >= LAZY_MIN_NUMEL:
+                return Buffer._deferred(("scale", other, float(self.scalar)), out_shape, other.dtype)
         return self._like(_dispatch(op=op, device=dev, x=self, y=other), out_shape, dev)
 
     def __add__(self, other: "Buffer | Scalar") -> "Buffer":
@@ -426,3 +496,6 @@ class Buffer:
     @property
     def nbytes(self) -> int:
         return self.metadata.nbytes
+
+
+_pending_buffers = weakref.WeakSet()

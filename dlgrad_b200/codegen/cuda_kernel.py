@@ -102,7 +102,10 @@ def ewise(expr: str, out_shape: tuple, in_strides: tuple, aligned: bool = True, 
     idx_t = "unsigned long long" if big else "unsigned"
     BLOCK = 256
     U = 4 if nvec >= BLOCK * 4 * NUM_SMS else (2 if nvec >= BLOCK * 2 * NUM_SMS else 1)
-    grid = max(1, _cdiv(nvec, BLOCK * U))
+    ntiles = max(1, _cdiv(nvec, BLOCK * U))
+    # persistent grid: at most 8 resident CTAs on each of the 148 SMs, tiles walked grid-stride, so a
+    # large tensor is not cut into 3.46 waves with a ragged tail
+    grid = min(ntiles, NUM_SMS * 8)
 
     # index decomposition of the (vector) index into collapsed dims
     vshape = list(shape)
@@ -155,7 +158,8 @@ def ewise(expr: str, out_shape: tuple, in_strides: tuple, aligned: bool = True, 
 __device__ __forceinline__ float op({params}, float ei) {{ return {expr}; }}
 extern "C" __global__ void __launch_bounds__({BLOCK}) {KNAME}{SIG} {{
     constexpr {idx_t} NV = {nvec}u;
-    const {idx_t} base = ({idx_t})blockIdx.x * {BLOCK * U}u + threadIdx.x;
+    for (unsigned tile = blockIdx.x; tile < {ntiles}u; tile += {grid}u) {{
+    const {idx_t} base = ({idx_t})tile * {BLOCK * U}u + threadIdx.x;
 {decl}    #pragma unroll
     for (int u = 0; u < {U}; ++u) {{
         const {idx_t} vi = base + u * {BLOCK}u;
@@ -171,6 +175,7 @@ extern "C" __global__ void __launch_bounds__({BLOCK}) {KNAME}{SIG} {{
             {compute}
             {store}
         }}
+    }}
     }}
 }}
 """
@@ -225,8 +230,9 @@ _RED = {
 
 @cache
 def reduce_rows(op: str, outer: int, R: int, aligned: bool = True, scale_R: int | None = None) -> Kernel:
-    """Last-axis reduce: out[o] = red_r x[o*R + r].  Sub-warp / warp / block per row, 128-bit loads,
-    shuffle tree.  Restates reduce_source with the reduced axis innermost and reduce()
+    """Last-axis reduce: out[o] = red_r x[o*R + r].  Sub-warp / warp / block per row, 128-bit loads, 8
+    independent accumulators per thread, shuffle tree; rows are walked grid-stride by a grid of at most
+    148 x 8 CTAs.  Restates reduce_source with the reduced axis innermost and reduce()
     (dlgrad/codegen/cpu_kernel.py:69-177); max keeps the reference's `-FLT_MAX` seed and strict `>`."""
     init, comb, fin = _RED[op]
     fin = fin.format(R=scale_R if scale_R is not None else R)
@@ -237,41 +243,52 @@ def reduce_rows(op: str, outer: int, R: int, aligned: bool = True, scale_R: int 
     else:
         T = min(32, _pow2_ceil(_cdiv(nv, 4)))
     BLOCK = 256
-    rows_per_block = BLOCK // T
-    grid = _cdiv(outer, rows_per_block)
-    ld = ("float4 v = __ldg(reinterpret_cast<const float4*>(row) + c); "
-          "a0 = red(a0, v.x); a1 = red(a1, v.y); a2 = red(a2, v.z); a3 = red(a3, v.w);"
-          if V == 4 else "a0 = red(a0, __ldg(row + c));")
+    rpb = BLOCK // T
+    nblocks = _cdiv(outer, rpb)
+    grid = min(nblocks, NUM_SMS * 8)
+    if V == 4:
+        ld = ("const float4 v = __ldg(rowv + c), w = (c + {T}u < {nv}u) ? __ldg(rowv + c + {T}u) : make_float4({i}, {i}, {i}, {i}); "
+              "a0 = red(a0, v.x); a1 = red(a1, v.y); a2 = red(a2, v.z); a3 = red(a3, v.w); "
+              "a4 = red(a4, w.x); a5 = red(a5, w.y); a6 = red(a6, w.z); a7 = red(a7, w.w);").format(T=T, nv=nv, i=init)
+        step = 2 * T
+        rowdecl = "const float4* rowv = reinterpret_cast<const float4*>(p0 + (size_t)r * %du);" % R
+    else:
+        ld = "a0 = red(a0, __ldg(rowv + c));"
+        step = T
+        rowdecl = "const float* rowv = p0 + (size_t)r * %du;" % R
     if T <= 32:
         tail = f"""
-    #pragma unroll
-    for (int m = {T // 2}; m > 0; m >>= 1) acc = red(acc, __shfl_xor_sync(0xffffffffu, acc, m));
-    if (lane == 0 && r < {outer}u) out[r] = {fin};"""
+        #pragma unroll
+        for (int m = {T // 2}; m > 0; m >>= 1) acc = red(acc, __shfl_xor_sync(0xffffffffu, acc, m));
+        if (lane == 0 && r < {outer}u) out[r] = {fin};"""
     else:
         tail = f"""
-    __shared__ float part[{T // 32}];
-    #pragma unroll
-    for (int m = 16; m > 0; m >>= 1) acc = red(acc, __shfl_xor_sync(0xffffffffu, acc, m));
-    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
-    __syncthreads();
-    if (threadIdx.x < 32) {{
-        acc = threadIdx.x < {T // 32} ? part[threadIdx.x] : {init};
         #pragma unroll
-        for (int m = {max(1, T // 64)}; m > 0; m >>= 1) acc = red(acc, __shfl_xor_sync(0xffffffffu, acc, m));
-        if (threadIdx.x == 0) out[r] = {fin};
-    }}"""
+        for (int m = 16; m > 0; m >>= 1) acc = red(acc, __shfl_xor_sync(0xffffffffu, acc, m));
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+        __syncthreads();
+        if (threadIdx.x < 32) {{
+            acc = threadIdx.x < {T // 32} ? part[threadIdx.x] : {init};
+            #pragma unroll
+            for (int m = {max(1, T // 64)}; m > 0; m >>= 1) acc = red(acc, __shfl_xor_sync(0xffffffffu, acc, m));
+            if (threadIdx.x == 0) out[r] = {fin};
+        }}"""
     src = f"""
 __device__ __forceinline__ float red(float a, float b) {{ return {comb}; }}
 extern "C" __global__ void __launch_bounds__({BLOCK}) {KNAME}{SIG} {{
-    const unsigned r = blockIdx.x * {rows_per_block}u + threadIdx.x / {T}u;
+    {"__shared__ float part[%d];" % (T // 32) if T > 32 else ""}
     const unsigned lane = threadIdx.x % {T}u;
-    float a0 = {init}, a1 = {init}, a2 = {init}, a3 = {init};
-    if (r < {outer}u) {{
-        const float* row = p0 + (size_t)r * {R}u;
-        #pragma unroll 4
-        for (unsigned c = lane; c < {nv}u; c += {T}u) {{ {ld} }}
+    for (unsigned blk = blockIdx.x; blk < {nblocks}u; blk += {grid}u) {{
+        const unsigned r = blk * {rpb}u + threadIdx.x / {T}u;
+        float a0 = {init}, a1 = {init}, a2 = {init}, a3 = {init}, a4 = {init}, a5 = {init}, a6 = {init}, a7 = {init};
+        if (r < {outer}u) {{
+            {rowdecl}
+            #pragma unroll 4
+            for (unsigned c = lane; c < {nv}u; c += {step}u) {{ {ld} }}
+        }}
+        float acc = red(red(red(a0, a1), red(a2, a3)), red(red(a4, a5), red(a6, a7)));{tail}
     }}
-    float acc = red(red(a0, a1), red(a2, a3));{tail}
 }}
 """
     return Kernel(f"red_{op}_rows", src, (grid, 1, 1), (BLOCK, 1, 1), 0, outer)
@@ -279,61 +296,153 @@ extern "C" __global__ void __launch_bounds__({BLOCK}) {KNAME}{SIG} {{
 
 @cache
 def reduce_cols(op: str, outer: int, R: int, inner: int, aligned: bool = True,
-                splits: int = 1, scale_R: int | None = None) -> Kernel:
-    """Strided reduce: out[s][o][i] = red_{r in split s} x[(o*R + r)*inner + i].  Threads run along
-    `inner` (coalesced), 8 warps of a block take interleaved rows and meet in shared memory; `splits`
-    slices R across blockIdx.z when outer*inner alone cannot fill 148 SMs (a second reduce_cols pass
-    over the `splits` axis finishes).  The reference walks this case with a strided inner loop
-    (cpu_kernel.py:69-148), its slowest pattern (152 ms for 4096^2 axis 0)."""
+                splits: int = 1, scale_R: int | None = None, cluster: bool = False) -> Kernel:
+    """Strided reduce: out[o][i] = red_r x[(o*R + r)*inner + i].  Threads run along `inner` (coalesced
+    128-bit loads), the 8 warps of a CTA take interleaved rows and meet in shared memory.  When
+    outer*inner alone cannot fill 148 SMs, R is cut into `splits` slices along blockIdx.z:
+      cluster=True  (splits <= 8): the slices of one column tile form a THREAD-BLOCK CLUSTER; every CTA
+                    leaves its partial in its own shared memory, and after a cluster barrier rank 0 adds
+                    the partials in rank order through distributed shared memory (mapa +
+                    ld.shared::cluster) — one launch, no atomics, deterministic order;
+      cluster=False the partials go to out[s][o][i] and a second reduce_cols pass over `splits` finishes.
+    The reference walks this case with a strided inner loop (cpu_kernel.py:69-148), its slowest pattern
+    (152 ms for 4096^2 axis 0)."""
     init, comb, fin = _RED[op]
-    fin = fin.format(R=scale_R if scale_R is not None else R) if splits == 1 else "acc"
+    final_here = splits == 1 or cluster
+    fin = fin.format(R=scale_R if scale_R is not None else R) if final_here else "acc"
     V = 4 if (aligned and inner % 4 == 0) else 1
     ncolv = inner // V
     Y = 8
     rows_per_split = _cdiv(R, splits)
     T = "float4" if V == 4 else "float"
-    if V == 4:
-        initv = f"make_float4({init}, {init}, {init}, {init})"
-        acc_upd = "acc.x = red(acc.x, v.x); acc.y = red(acc.y, v.y); acc.z = red(acc.z, v.z); acc.w = red(acc.w, v.w);"
-        ldv = "__ldg(reinterpret_cast<const float4*>(base + (size_t)r * %du) + cv)" % inner
-        comb_sm = ("acc.x = red(acc.x, o.x); acc.y = red(acc.y, o.y); acc.z = red(acc.z, o.z); acc.w = red(acc.w, o.w);")
-        fin4 = "; ".join(f"res.{c} = " + fin.replace("acc", f"acc.{c}") for c in "xyzw")
-        store = f"float4 res; {fin4}; reinterpret_cast<float4*>(dst)[cv] = res;"
+    comps = ["x", "y", "z", "w"] if V == 4 else [""]
+
+    def each(fmt):
+        return " ".join(fmt.format(c=("." + c) if c else "") for c in comps)
+    initv = f"make_float4({init}, {init}, {init}, {init})" if V == 4 else init
+    ldv = (f"__ldg(reinterpret_cast<const float4*>(base + (size_t)r * {inner}u) + cv)" if V == 4
+           else f"__ldg(base + (size_t)r * {inner}u + cv)")
+    fin_store = each("res{c} = " + fin.replace("acc", "acc{c}") + ";")
+    if cluster and splits > 1:
+        ld_remote = ('asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(o.x), "=f"(o.y), "=f"(o.z), "=f"(o.w) : "r"(ra));'
+                     if V == 4 else 'asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(o) : "r"(ra));')
+        finish = f"""
+    __shared__ {T} mine[32];
+    unsigned crank;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+    if (threadIdx.y == 0) mine[threadIdx.x] = acc;
+    asm volatile("barrier.cluster.arrive.release.aligned;\\n\\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    if (crank == 0 && threadIdx.y == 0 && cv < {ncolv}u) {{
+        const unsigned la = (unsigned)__cvta_generic_to_shared(&mine[threadIdx.x]);
+        for (unsigned pr = 1; pr < {splits}u; ++pr) {{
+            unsigned ra; {T} o;
+            asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(la), "r"(pr));
+            {ld_remote}
+            {each("acc{c} = red(acc{c}, o{c});")}
+        }}
+        float* dst = out + (size_t)o_ * {inner}u;
+        {T} res; {fin_store}
+        reinterpret_cast<{T}*>(dst)[cv] = res;
+    }}
+    asm volatile("barrier.cluster.arrive.release.aligned;\\n\\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");"""
+        attr = f"__cluster_dims__(1, 1, {splits}) "
+        out_elems = outer * inner
     else:
-        initv = init
-        acc_upd = "acc = red(acc, v);"
-        ldv = "__ldg(base + (size_t)r * %du + cv)" % inner
-        comb_sm = "acc = red(acc, o);"
-        store = f"dst[cv] = {fin};"
+        finish = f"""
+    if (threadIdx.y == 0 && cv < {ncolv}u) {{
+        float* dst = out + ((size_t)s * {outer}u + o_) * {inner}u;
+        {T} res; {fin_store}
+        reinterpret_cast<{T}*>(dst)[cv] = res;
+    }}"""
+        attr = ""
+        out_elems = splits * outer * inner
     src = f"""
 __device__ __forceinline__ float red(float a, float b) {{ return {comb}; }}
-extern "C" __global__ void __launch_bounds__({32 * Y}) {KNAME}{SIG} {{
+extern "C" __global__ void {attr}__launch_bounds__({32 * Y}) {KNAME}{SIG} {{
     __shared__ {T} part[{Y}][33];
     const unsigned cv = blockIdx.x * 32u + threadIdx.x;
-    const unsigned o = blockIdx.y, s = blockIdx.z;
+    const unsigned o_ = blockIdx.y, s = blockIdx.z;
     const unsigned r0 = s * {rows_per_split}u;
     const unsigned r1 = min(r0 + {rows_per_split}u, {R}u);
-    const float* base = p0 + (size_t)o * {R * inner}u;
-    {T} acc = {initv};
+    const float* base = p0 + (size_t)o_ * {R * inner}u;
+    {T} acc = {initv}, acc2 = {initv};
     if (cv < {ncolv}u) {{
+        unsigned r = r0 + threadIdx.y;
         #pragma unroll 4
-        for (unsigned r = r0 + threadIdx.y; r < r1; r += {Y}u) {{
-            {T} v = {ldv};
-            {acc_upd}
+        for (; r + {Y}u < r1; r += {2 * Y}u) {{
+            const {T} v = {ldv};
+            const {T} w = {ldv.replace("(size_t)r", "(size_t)(r + %du)" % Y)};
+            {each("acc{c} = red(acc{c}, v{c});")} {each("acc2{c} = red(acc2{c}, w{c});")}
         }}
+        if (r < r1) {{ const {T} v = {ldv}; {each("acc{c} = red(acc{c}, v{c});")} }}
+        {each("acc{c} = red(acc{c}, acc2{c});")}
     }}
     part[threadIdx.y][threadIdx.x] = acc;
     __syncthreads();
-    if (threadIdx.y == 0 && cv < {ncolv}u) {{
+    if (threadIdx.y == 0) {{
         #pragma unroll
-        for (int y = 1; y < {Y}; ++y) {{ {T} o = part[y][threadIdx.x]; {comb_sm} }}
-        float* dst = out + ((size_t)s * {outer}u + o) * {inner}u;
-        {store}
-    }}
+        for (int y = 1; y < {Y}; ++y) {{ const {T} o = part[y][threadIdx.x]; {each("acc{c} = red(acc{c}, o{c});")} }}
+    }}{finish}
 }}
 """
     grid = (_cdiv(ncolv, 32), outer, splits)
-    return Kernel(f"red_{op}_cols", src, grid, (32, Y, 1), 0, splits * outer * inner)
+    return Kernel(f"red_{op}_cols", src, grid, (32, Y, 1), 0, out_elems)
+
+
+@cache
+def reduce_cols_slab(op: str, outer: int, R: int, inner: int, slabs: int, final: bool,
+                     scale_R: int | None = None) -> Kernel:
+    """Strided reduce for wide `inner` (128-bit aligned): out[s][o][i] = red_{r in slab s} x[(o*R+r)*inner+i].
+    A CTA owns a slab of CONSECUTIVE rows and a span of up to 4096 contiguous columns, so every row it
+    touches is read as one long contiguous run (DRAM-page friendly, unlike 512-byte column strips at a
+    16 KiB pitch); each thread keeps up to 4 float4 column accumulators and two rows in flight.  With
+    slabs > 1 a second pass over the `slabs` axis (same kernel, final=True) finishes."""
+    init, comb, fin = _RED[op]
+    fin = fin.format(R=scale_R if scale_R is not None else R) if final else "acc"
+    ncolv = inner // 4
+    BLOCK = 256
+    TC = min(4, _cdiv(ncolv, BLOCK))
+    span = BLOCK * TC                       # float4 columns per CTA
+    nspans = _cdiv(ncolv, span)
+    rows_per = _cdiv(R, slabs)
+    accs = "\n    ".join(f"float4 a{j} = make_float4({init}, {init}, {init}, {init}), b{j} = a{j};" for j in range(TC))
+
+    def upd(acc, v):
+        return " ".join(f"{acc}.{c} = red({acc}.{c}, {v}.{c});" for c in "xyzw")
+    body_a = "\n            ".join(
+        f"if (c{j} < {ncolv}u) {{ const float4 v = __ldg(row0 + c{j}); {upd(f'a{j}', 'v')} }}" for j in range(TC))
+    body_b = "\n            ".join(
+        f"if (c{j} < {ncolv}u) {{ const float4 v = __ldg(row1 + c{j}); {upd(f'b{j}', 'v')} }}" for j in range(TC))
+    cols = "\n    ".join(f"const unsigned c{j} = blockIdx.x * {span}u + threadIdx.x + {j * BLOCK}u;" for j in range(TC))
+    stores = "\n    ".join(
+        f"if (c{j} < {ncolv}u) {{ float4 acc; {' '.join(f'acc.{c} = red(a{j}.{c}, b{j}.{c});' for c in 'xyzw')} "
+        f"float4 res; {' '.join('res.%s = %s;' % (c, fin.replace('acc', 'acc.' + c)) for c in 'xyzw')} dst[c{j}] = res; }}"
+        for j in range(TC))
+    src = f"""
+__device__ __forceinline__ float red(float a, float b) {{ return {comb}; }}
+extern "C" __global__ void __launch_bounds__({BLOCK}) {KNAME}{SIG} {{
+    const unsigned o_ = blockIdx.y, s = blockIdx.z;
+    const unsigned r0 = s * {rows_per}u, r1 = min(r0 + {rows_per}u, {R}u);
+    const float4* base = reinterpret_cast<const float4*>(p0 + (size_t)o_ * {R * inner}u);
+    {cols}
+    {accs}
+    unsigned r = r0;
+    #pragma unroll 2
+    for (; r + 1u < r1; r += 2u) {{
+        const float4* row0 = base + (size_t)r * {ncolv}u;
+        const float4* row1 = row0 + {ncolv}u;
+        {body_a}
+        {body_b}
+    }}
+    if (r < r1) {{
+        const float4* row0 = base + (size_t)r * {ncolv}u;
+        {body_a}
+    }}
+    float4* dst = reinterpret_cast<float4*>(out + ((size_t)s * {outer}u + o_) * {inner}u);
+    {stores}
+}}
+"""
+    return Kernel(f"red_{op}_slab", src, (nspans, outer, slabs), (BLOCK, 1, 1), 0, slabs * outer * inner)
 
 
 @cache
@@ -713,18 +822,51 @@ def _row_reduce_code(T: int, var: str, comb: str, ident: str, tag: str) -> str:
     for (int w = 0; w < {nw}; ++w) {{ float o = sm_{tag}[w]; {var} = {comb.format(a=var, b='o')}; }}"""
 
 
+
+def _chain_code(chain: tuple, var: str, comps: list, V: int) -> tuple[str, str]:
+    """Code for a chain of fused pointwise ops applied to the row vector `var` (a float4 or float):
+        ("scale", fslot)                                   var *= f<fslot>
+        ("mfill", pslot, fslot, lead_shape, lead_strides)  var = mask > 0 ? f<fslot> : var, mask = p<pslot>
+    Returns (per-row setup code computing the mask row offsets, per-vector code)."""
+    setup, body = [], []
+
+    def each(fmt):
+        return " ".join(fmt.format(c=("." + c) if c else "") for c in comps)
+    for k, op in enumerate(chain):
+        if op[0] == "scale":
+            body.append(each(var + "{c} = " + var + "{c} * f%d;" % op[1]))
+        elif op[0] == "mfill":
+            _, ps, fs, lead_shape, lead_strides = op
+            lines = [f"size_t moff{k} = 0; {{ unsigned q_ = (live ? r : 0u);"]
+            for d in range(len(lead_shape) - 1, -1, -1):
+                if lead_shape[d] == 1:
+                    continue
+                lines.append(f" {{ const unsigned i_ = q_ % {lead_shape[d]}u; q_ /= {lead_shape[d]}u; moff{k} += (size_t)i_ * {lead_strides[d]}u; }}")
+            lines.append("}")
+            setup.append("".join(lines))
+            VT = "float4" if V == 4 else "float"
+            body.append(f"{{ const {VT} m_ = __ldg(reinterpret_cast<const {VT}*>(p{ps} + moff{k}) + c); "
+                        + each("%s{c} = (m_{c} > 0.f) ? f%d : %s{c};" % (var, fs, var)) + " }")
+        else:
+            raise ValueError(op)
+    return "\n    ".join(setup), " ".join(body)
+
+
 @cache
-def softmax_rows(kind: str, outer: int, R: int, aligned: bool = True) -> Kernel:
+def softmax_rows(kind: str, outer: int, R: int, aligned: bool = True, chain: tuple = ()) -> Kernel:
     """Fused softmax / log-softmax over the last axis: one HBM read and one write per element, the
     row lives in registers between the max, the exp-sum and the normalisation.  Replaces the
     reference's 5-kernel chain max / sub / exp / sum / div (dlgrad/tensor.py:634-669) and, for the
     loss, the first six kernels of ops.CrossEntropy.forward (dlgrad/ops.py:343-349).  Masked lanes
-    holding -inf come out as exactly 0 (softmax) like the reference's."""
+    holding -inf come out as exactly 0 (softmax) like the reference's.  `chain` folds pending pointwise
+    producers of x into the load — attention's `(q @ k^T) * scale` and `.masked_fill(mask, -inf)`
+    (examples/gpt.py:51-53) — so those two full-size tensors are never written."""
     V, nv, T, per = _row_geometry(R, aligned, outer)
     BLOCK = 256 if T <= 256 else T
     rpb = BLOCK // T
     VT = "float4" if V == 4 else "float"
     comps = ["x", "y", "z", "w"] if V == 4 else [""]
+    pre_setup, pre_body = _chain_code(chain, "v[i]", comps, V)
 
     def each(fmt):
         return " ".join(fmt.format(c=("." + c) if c else "") for c in comps)
@@ -739,12 +881,13 @@ extern "C" __global__ void __launch_bounds__({BLOCK}) {KNAME}{SIG} {{
     const unsigned lane = threadIdx.x % {T}u;
     const bool live = r < {outer}u;
     const {VT}* row = reinterpret_cast<const {VT}*>(p0 + (size_t)(live ? r : 0) * {R}u);
+    {pre_setup}
     {VT} v[{per}];
     float mx = -3.402823466e+38f;
     #pragma unroll
     for (int i = 0; i < {per}; ++i) {{
         const unsigned c = lane + i * {T}u;
-        if (c < {nv}u) {{ v[i] = __ldg(row + c); {each("mx = (v[i]{c} > mx) ? v[i]{c} : mx;")} }}
+        if (c < {nv}u) {{ v[i] = __ldg(row + c); {pre_body} {each("mx = (v[i]{c} > mx) ? v[i]{c} : mx;")} }}
     }}
     {_row_reduce_code(T, "mx", "({b} > {a}) ? {b} : {a}", "-3.402823466e+38f", "mx")}
     float s = 0.f;
@@ -773,17 +916,19 @@ extern "C" __global__ void __launch_bounds__({BLOCK}) {KNAME}{SIG} {{
 
 
 @cache
-def softmax_bwd_rows(kind: str, outer: int, R: int, aligned: bool = True) -> Kernel:
+def softmax_bwd_rows(kind: str, outer: int, R: int, aligned: bool = True, chain: tuple = ()) -> Kernel:
     """Backward of the fused row ops.  softmax: dx = y * (g - sum(g*y)); log-softmax:
     dx = g - exp(y) * sum(g).  p0 = forward output y, p1 = upstream g.  Algebraically what the
     reference's autograd chain (Div/Exp/Sum/Sub/Max backward, ~17 kernels)
     evaluates; the Max branch there contributes only rounding noise because softmax is
-    shift-invariant."""
+    shift-invariant.  `chain` folds pending pointwise CONSUMERS of dx into the store (the backward of
+    masked_fill and of the scalar scale in attention)."""
     V, nv, T, per = _row_geometry(R, aligned, outer)
     BLOCK = 256 if T <= 256 else T
     rpb = BLOCK // T
     VT = "float4" if V == 4 else "float"
     comps = ["x", "y", "z", "w"] if V == 4 else [""]
+    post_setup, post_body = _chain_code(chain, "g[i]", comps, V)
 
     def each(fmt):
         return " ".join(fmt.format(c=("." + c) if c else "") for c in comps)
@@ -810,11 +955,12 @@ extern "C" __global__ void __launch_bounds__({BLOCK}) {KNAME}{SIG} {{
     }}
     {_row_reduce_code(T, "d", "{a} + {b}", "0.f", "d")}
     if (!live) return;
+    {post_setup}
     {VT}* orow = reinterpret_cast<{VT}*>(out + ro);
     #pragma unroll
     for (int i = 0; i < {per}; ++i) {{
         const unsigned c = lane + i * {T}u;
-        if (c < {nv}u) {{ {final} orow[c] = g[i]; }}
+        if (c < {nv}u) {{ {final} {post_body} orow[c] = g[i]; }}
     }}
 }}
 """
@@ -915,3 +1061,50 @@ extern "C" __global__ void __launch_bounds__(256) {KNAME}{SIG_ALIAS} {{
 }}
 """
     return Kernel("sgd", src, (_cdiv(nv, 256), 1, 1), (256, 1, 1), 0, 0)
+
+
+# ------------------------------------------------------------------------------------------------
+# RMSNorm (fused forward)
+# ------------------------------------------------------------------------------------------------
+@cache
+def rmsnorm_rows(outer: int, C: int, affine: bool, aligned: bool = True) -> Kernel:
+    """y = (x * rsqrt(mean(x^2) + eps)) * w over the last axis in one pass; the per-row rsqrt is also
+    written (to p2) for the backward.  Replaces the six kernels nn.RMSNorm composes (pow, mean, add eps,
+    rsqrt, mul, mul — dlgrad/nn/__init__.py:28-41) with the same per-element operation order.
+    p0 = x (outer, C), p1 = weight (C,), p2 = rstd out (outer,), f0 = eps."""
+    V, nv, T, per = _row_geometry(C, aligned, outer)
+    BLOCK = 256 if T <= 256 else T
+    rpb = BLOCK // T
+    VT = "float4" if V == 4 else "float"
+    comps = ["x", "y", "z", "w"] if V == 4 else [""]
+
+    def each(fmt):
+        return " ".join(fmt.format(c=("." + c) if c else "") for c in comps)
+    wload = f"const {VT} wv = __ldg(reinterpret_cast<const {VT}*>(p1) + c);" if affine else ""
+    scale = each("v[i]{c} = __fmul_rn(__fmul_rn(v[i]{c}, t), wv{c});") if affine else each("v[i]{c} = __fmul_rn(v[i]{c}, t);")
+    src = f"""
+extern "C" __global__ void __launch_bounds__({BLOCK}) {KNAME}{SIG} {{
+    const unsigned r = blockIdx.x * {rpb}u + threadIdx.x / {T}u;
+    const unsigned lane = threadIdx.x % {T}u;
+    const bool live = r < {outer}u;
+    const {VT}* row = reinterpret_cast<const {VT}*>(p0 + (size_t)(live ? r : 0) * {C}u);
+    {VT} v[{per}];
+    float ss = 0.f;
+    #pragma unroll
+    for (int i = 0; i < {per}; ++i) {{
+        const unsigned c = lane + i * {T}u;
+        if (c < {nv}u) {{ v[i] = __ldg(row + c); {each("ss += v[i]{c} * v[i]{c};")} }}
+    }}
+    {_row_reduce_code(T, "ss", "{a} + {b}", "0.f", "ss")}
+    const float t = 1.f / sqrtf(__fadd_rn(ss / {C}.f, f0));
+    if (!live) return;
+    if (lane == 0) const_cast<float*>(p2)[r] = t;
+    {VT}* orow = reinterpret_cast<{VT}*>(out + (size_t)r * {C}u);
+    #pragma unroll
+    for (int i = 0; i < {per}; ++i) {{
+        const unsigned c = lane + i * {T}u;
+        if (c < {nv}u) {{ {wload} {scale} orow[c] = v[i]; }}
+    }}
+}}
+"""
+    return Kernel("rmsnorm_rows", src, (_cdiv(outer, rpb), 1, 1), (BLOCK, 1, 1), 0, outer * C)

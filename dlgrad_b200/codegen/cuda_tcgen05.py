@@ -311,5 +311,314 @@ def tmap_descs(M: int, N: int, K: int, batch: int, a_mn: bool, b_mn: bool, a_bca
         return dict(rank=3, dims=(K, rows, nb), strides=(K * 4, rows * K * 4), box=(BK, tile_rows, 1), swizzle=3)
     a = operand(M, a_mn, a_bcast, BM)
     b = operand(N, b_mn, b_bcast, BN)
-    c = dict(rank=3, dims=(N, M, batch), strides=(N * 4, M * N * 4), box=(32, 32, 1), swizzle=0)
+    c = dict(rank=3, dims=(N, M, batch), strides=(N * 4, M * N * 4), box=(32, 32, 1), swizzle=3)
     return a, b, c
+
+
+# =====================================================================================================
+# v2: persistent kernel — one CTA per SM walks output tiles; the TMA ring and the hi/lo splitter run
+# continuously across tiles, the accumulator is double-buffered in TMEM so the epilogue of tile i
+# (TMEM -> registers -> swizzled smem -> TMA store) overlaps the main loop of tile i+1.
+# =====================================================================================================
+_HELPERS = r"""
+struct alignas(64) TMap { unsigned long long opaque[16]; };
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+    // try_wait suspends for a HW-defined window; the watchdog turns a protocol bug into a trap
+    // (a CUDA error) instead of a hung GPU.
+    const long long t0 = clock64();
+    for (;;) {
+        unsigned ok;
+        asm volatile("{\n\t.reg .pred p;\n\t"
+                     "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                     "selp.b32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        if (ok) return;
+        if (clock64() - t0 > 4000000000LL) __trap();
+    }
+}
+__device__ __forceinline__ void tma_load_3d(unsigned dst, const TMap* map, unsigned bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        :: "r"(dst), "l"((unsigned long long)map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const TMap* map, unsigned src, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                 :: "l"((unsigned long long)map), "r"(src), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_3d(const TMap* map, unsigned src, int c0, int c1, int c2) {
+    asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];"
+                 :: "l"((unsigned long long)map), "r"(src), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void umma_tf32(unsigned tmem_d, unsigned long long adesc, unsigned long long bdesc,
+                                          unsigned idesc, unsigned accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(unsigned bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar) : "memory");
+}
+// shared-memory matrix descriptor: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48), layout type [61,64)
+__device__ __forceinline__ unsigned long long make_desc(unsigned addr, unsigned lbo16, unsigned sbo16, unsigned ltype) {
+    return (unsigned long long)((addr & 0x3ffffu) >> 4) | ((unsigned long long)lbo16 << 16) |
+           ((unsigned long long)sbo16 << 32) | (1ull << 46) | ((unsigned long long)ltype << 61);
+}
+"""
+
+NUM_SMS = 148
+
+
+def pick_bn_persistent(M: int, N: int, batch: int, kblocks: int) -> int:
+    """Column-tile width that minimises (tiles per CTA) x (tile cost) on 148 persistent CTAs.  Tile cost
+    model: MMA time ~ BN per k-block plus a fixed per-tile part (epilogue / pipeline refill) that weighs more
+    when K is short."""
+    ntm = _cdiv(M, BM) * batch
+    best, best_cost = None, None
+    fixed = 32 + (256 // max(1, kblocks))
+    for cand in (256, 192, 128, 96, 64, 32):
+        if cand > _cdiv(N, 32) * 32 and cand != 32:
+            continue
+        tiles = ntm * _cdiv(N, cand)
+        # wide tiles leave room for only 2 smem stages (hi + lo buffers): measured 207 (BN=256) vs 216
+        # (BN=128, 3 stages) TFLOP/s at 4096^3 -> a 6 % handicap on the 2-stage widths when K is long
+        depth_penalty = (1.12 if kblocks > 32 else 1.06) if (cand > 128 and kblocks > 8) else 1.0
+        cost = _cdiv(tiles, NUM_SMS) * (cand + fixed) * depth_penalty
+        if best_cost is None or cost < best_cost:
+            best, best_cost = cand, cost
+    return best
+
+
+@cache
+def matmul_tc_persistent(M: int, N: int, K: int, batch: int, a_mn: bool, b_mn: bool, a_bcast: bool, b_bcast: bool,
+                         passes: int = 3, bn: int | None = None, stages: int | None = None,
+                         kc_blocks: int | None = None) -> TcKernel:
+    kblocks = _cdiv(K, BK)
+    # K is accumulated in TMEM in chunks of <= 1024: the tensor core adds into the fp32 accumulator with
+    # truncation, a bias that grows with the accumulator's magnitude (8.5e-5 at K = 4096 on U[0,1) inputs,
+    # measured).  Chunk partials are combined in global memory by TMA reduce-add (round-to-nearest fp32).
+    kc = kc_blocks or (32 if kblocks > 64 else kblocks)
+    nchunks = _cdiv(kblocks, kc)
+    BN = bn or pick_bn_persistent(M, N, batch, kblocks)
+    a_tile, b_tile = BM * BK * 4, BN * BK * 4
+    ab = a_tile + b_tile
+    per_stage = ab * (2 if passes == 3 else 1)
+    EPI_BUFS = 2
+    epi_bytes = 4 * EPI_BUFS * 4096                      # 4 epilogue warps x 2 staging boxes of 32x32 fp32
+    budget = 227 * 1024 - 1024 - 512 - epi_bytes
+    if stages is None:
+        stages = max(2, min(6, budget // per_stage))
+    ntm, ntn = _cdiv(M, BM), _cdiv(N, BN)
+    ntiles = ntm * ntn * batch
+    tmem_cols = 32
+    while tmem_cols < 2 * BN:
+        tmem_cols *= 2
+    smem = stages * per_stage + epi_bytes + 1024 + 512
+    idesc = _idesc(BM, BN, a_mn, b_mn)
+    a_lbo, a_sbo, a_kstep, a_lt = (256, 32, 64, 1) if a_mn else (1, 64, 2, 2)
+    b_lbo, b_sbo, b_kstep, b_lt = (256, 32, 64, 1) if b_mn else (1, 64, 2, 2)
+    a_boxes = BM // 32 if a_mn else 1
+    b_boxes = BN // 32 if b_mn else 1
+    grid = min(ntiles, NUM_SMS)
+
+    def tma_issue(which, boxes, mn, tile_var, row0):
+        tm = f"tm{which}"
+        z = "0" if (a_bcast if which == "A" else b_bcast) else "z"
+        if mn:
+            return "\n                    ".join(
+                f"tma_load_3d({tile_var} + {j * 4096}u, &{tm}, full_bar, (int)({row0} + {j * 32}u), (int)k0, (int){z});"
+                for j in range(boxes))
+        return f"tma_load_3d({tile_var}, &{tm}, full_bar, (int)k0, (int){row0}, (int){z});"
+
+    decode = f"""const unsigned z = t / {ntm * ntn}u, rem = t % {ntm * ntn}u;
+            const unsigned m0 = (rem / {ntn}u) * {BM}u, n0 = (rem % {ntn}u) * {BN}u;"""
+    if passes == 3:
+        mma_wait = "mbar_wait(split + s * 8u, ph);"
+        mma_body = f"""
+                        const unsigned long long a_hi = adesc + (unsigned long long)(k * {a_kstep}u);
+                        const unsigned long long b_hi = bdesc + (unsigned long long)(k * {b_kstep}u);
+                        umma_tf32(tacc, a_hi + {ab // 16}ull, b_hi, {idesc}u, (kbl | k) != 0u);
+                        umma_tf32(tacc, a_hi, b_hi + {ab // 16}ull, {idesc}u, 1u);
+                        umma_tf32(tacc, a_hi, b_hi, {idesc}u, 1u);"""
+        split_code = f"""
+        // ===== splitter warps: lo = x - trunc_tf32(x) into the twin buffer (same swizzled layout) =====
+        const unsigned ctid = threadIdx.x - 64u;
+        unsigned it = 0;
+        for (unsigned t = blockIdx.x; t < {ntiles}u; t += {grid}u) {{
+            for (unsigned kb = 0; kb < {kblocks}u; ++kb, ++it) {{
+                const unsigned s = it % {stages}u, ph = (it / {stages}u) & 1u;
+                mbar_wait(full + s * 8u, ph);
+                const float4* src = reinterpret_cast<const float4*>(smem_gen + s * {per_stage}u);
+                float4* dst = reinterpret_cast<float4*>(smem_gen + s * {per_stage}u + {ab}u);
+                #pragma unroll 4
+                for (unsigned i = ctid; i < {ab // 16}u; i += 128u) {{
+                    const float4 x = src[i];
+                    float4 lo;
+                    lo.x = x.x - __uint_as_float(__float_as_uint(x.x) & 0xffffe000u);
+                    lo.y = x.y - __uint_as_float(__float_as_uint(x.y) & 0xffffe000u);
+                    lo.z = x.z - __uint_as_float(__float_as_uint(x.z) & 0xffffe000u);
+                    lo.w = x.w - __uint_as_float(__float_as_uint(x.w) & 0xffffe000u);
+                    dst[i] = lo;
+                }}
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbar_arrive(split + s * 8u);
+            }}
+        }}"""
+    else:
+        mma_wait = "mbar_wait(full + s * 8u, ph);"
+        mma_body = f"""
+                        umma_tf32(tacc, adesc + (unsigned long long)(k * {a_kstep}u),
+                                  bdesc + (unsigned long long)(k * {b_kstep}u), {idesc}u, (kbl | k) != 0u);"""
+        split_code = ""
+
+    regs = ", ".join(f"%{i}" for i in range(32))
+    outs = ", ".join(f'"=r"(v[{i}])' for i in range(32))
+    stage_writes = "\n                    ".join(
+        f"*reinterpret_cast<float4*>(sbuf_gen + lane * 128u + (({j}u ^ (lane & 7u)) << 4)) = "
+        f"make_float4(__uint_as_float(v[{4 * j}]), __uint_as_float(v[{4 * j + 1}]), __uint_as_float(v[{4 * j + 2}]), __uint_as_float(v[{4 * j + 3}]));"
+        for j in range(8))
+
+    src = _HELPERS + f"""
+extern "C" __global__ void __launch_bounds__(320, 1)
+{KNAME}(const __grid_constant__ TMap tmA, const __grid_constant__ TMap tmB, const __grid_constant__ TMap tmC, float* __restrict__ C)
+{{
+    extern __shared__ unsigned char smem_raw[];
+    const unsigned smem = (smem_u32(smem_raw) + 1023u) & ~1023u;        // swizzle atoms need 1024-byte alignment
+    unsigned char* smem_gen = smem_raw + (smem - smem_u32(smem_raw));
+    const unsigned epi = smem + {stages * per_stage}u;
+    const unsigned bars = epi + {epi_bytes}u;
+    const unsigned full = bars, empty = bars + {stages * 8}u, split = bars + {stages * 16}u;
+    const unsigned tfull = bars + {stages * 24}u, tempty = tfull + 16u;
+    __shared__ unsigned tmem_slot;
+    const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+
+    if (threadIdx.x == 0) {{
+        for (unsigned s = 0; s < {stages}u; ++s) {{
+            mbar_init(full + s * 8u, 1u);
+            mbar_init(empty + s * 8u, 1u);
+            mbar_init(split + s * 8u, 128u);
+        }}
+        for (unsigned b = 0; b < 2u; ++b) {{
+            mbar_init(tfull + b * 8u, 1u);
+            mbar_init(tempty + b * 8u, 4u);
+        }}
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }}
+    if (warp == 1) {{
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&tmem_slot)), "n"({tmem_cols}));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }}
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const unsigned tmem_base = tmem_slot;
+
+    if (warp == 0) {{
+        // ===== TMA producer =====
+        if (lane == 0) {{
+            unsigned it = 0;
+            for (unsigned t = blockIdx.x; t < {ntiles}u; t += {grid}u) {{
+                {decode}
+                for (unsigned kb = 0; kb < {kblocks}u; ++kb, ++it) {{
+                    const unsigned s = it % {stages}u, ph = (it / {stages}u) & 1u;
+                    mbar_wait(empty + s * 8u, ph ^ 1u);
+                    const unsigned full_bar = full + s * 8u;
+                    const unsigned a_s = smem + s * {per_stage}u, b_s = a_s + {a_tile}u;
+                    const unsigned k0 = kb * {BK}u;
+                    mbar_expect_tx(full_bar, {ab}u);
+                    {tma_issue("A", a_boxes, a_mn, "a_s", "m0")}
+                    {tma_issue("B", b_boxes, b_mn, "b_s", "n0")}
+                }}
+            }}
+        }}
+    }} else if (warp == 1) {{
+        // ===== MMA issuer (one lane) =====
+        if (lane == 0) {{
+            unsigned it = 0, u = 0;
+            for (unsigned t = blockIdx.x; t < {ntiles}u; t += {grid}u) {{
+                for (unsigned ch = 0; ch < {nchunks}u; ++ch, ++u) {{
+                    const unsigned b = u & 1u;
+                    mbar_wait(tempty + b * 8u, ((u >> 1) & 1u) ^ 1u);       // epilogue has drained this accumulator
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const unsigned tacc = tmem_base + b * {BN}u;
+                    const unsigned kend = min((ch + 1u) * {kc}u, {kblocks}u);
+                    for (unsigned kb = ch * {kc}u, kbl = 0; kb < kend; ++kb, ++kbl, ++it) {{
+                        const unsigned s = it % {stages}u, ph = (it / {stages}u) & 1u;
+                        {mma_wait}
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        const unsigned a_s = smem + s * {per_stage}u, b_s = a_s + {a_tile}u;
+                        const unsigned long long adesc = make_desc(a_s, {a_lbo}u, {a_sbo}u, {a_lt}u);
+                        const unsigned long long bdesc = make_desc(b_s, {b_lbo}u, {b_sbo}u, {b_lt}u);
+                        #pragma unroll
+                        for (unsigned k = 0; k < {BK // 8}u; ++k) {{{mma_body}
+                        }}
+                        umma_commit(empty + s * 8u);
+                    }}
+                    umma_commit(tfull + b * 8u);
+                }}
+            }}
+        }}
+    }} else if (warp < 6) {{{split_code}
+    }} else {{
+        // ===== epilogue warps: TMEM -> registers -> swizzled smem box -> TMA store =====
+        const unsigned q = warp & 3u;                          // TMEM lane quarter this warp may read
+        const unsigned my_epi = epi + (warp - 6u) * {EPI_BUFS * 4096}u;
+        unsigned char* my_epi_gen = smem_gen + {stages * per_stage}u + (warp - 6u) * {EPI_BUFS * 4096}u;
+        unsigned u = 0, nstore = 0;
+        for (unsigned t = blockIdx.x; t < {ntiles}u; t += {grid}u) {{
+            {decode}
+            for (unsigned ch = 0; ch < {nchunks}u; ++ch, ++u) {{
+                const unsigned b = u & 1u;
+                mbar_wait(tfull + b * 8u, (u >> 1) & 1u);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                // a later K-chunk is ADDED to what the earlier chunk stored: that store must have landed
+                if (ch != 0u && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+                #pragma unroll 1
+                for (unsigned c = 0; c < {BN // 32}u; ++c) {{
+                    unsigned v[32];
+                    const unsigned taddr = tmem_base + ((q * 32u) << 16) + b * {BN}u + c * 32u;
+                    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {{{regs}}}, [%32];" : {outs} : "r"(taddr));
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    if (n0 + c * 32u < {N}u && m0 + q * 32u < {M}u) {{
+                        const unsigned sb = nstore & {EPI_BUFS - 1}u;
+                        // the staging box we are about to overwrite must have been read by its earlier TMA store
+                        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read {EPI_BUFS - 1};" ::: "memory");
+                        __syncwarp();
+                        unsigned char* sbuf_gen = my_epi_gen + sb * 4096u;
+                        {stage_writes}
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                        __syncwarp();
+                        if (lane == 0) {{
+                            if (ch == 0u) tma_store_3d(&tmC, my_epi + sb * 4096u, (int)(n0 + c * 32u), (int)(m0 + q * 32u), (int)z);
+                            else tma_reduce_add_3d(&tmC, my_epi + sb * 4096u, (int)(n0 + c * 32u), (int)(m0 + q * 32u), (int)z);
+                            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                        }}
+                        ++nstore;
+                    }}
+                }}
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tempty + b * 8u);        // accumulator b may be overwritten
+            }}
+        }}
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }}
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {{
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "n"({tmem_cols}));
+    }}
+}}
+"""
+    return TcKernel(f"mm_tcp{passes}", src, (grid, 1, 1), 320, smem, batch * M * N, BN, stages)

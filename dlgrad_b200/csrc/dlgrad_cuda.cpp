@@ -575,7 +575,7 @@ void dlg_event_destroy(void *ev) {
 
 int dlg_graph_begin(void) {
     REQUIRE_READY(g_status)
-    CU(cuStreamBeginCapture(g_stream, CU_STREAM_CAPTURE_MODE_THREAD_LOCAL));
+    CU(cuStreamBeginCapture(g_stream, CU_STREAM_CAPTURE_MODE_RELAXED));
     return 0;
 }
 void *dlg_graph_end(void) {

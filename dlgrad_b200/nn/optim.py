@@ -7,7 +7,7 @@ from __future__ import annotations
 
 import numpy as np
 
-from dlgrad_b200.buffer import Buffer
+from dlgrad_b200.buffer import Buffer, flush_pending
 from dlgrad_b200.device import Device
 from dlgrad_b200.dispatch import dispatcher
 from dlgrad_b200.helpers import CustomOps
@@ -25,7 +25,13 @@ class Optimizer:
     def _device_for(self, *bufs: Buffer) -> Device:
         return Buffer._route(*bufs)
 
+    def _before_inplace(self, extra: list | None = None) -> None:
+        """The updates below write parameters (and optimizer state) in place: deferred pointwise producers
+        that still read one of those buffers must run first (dlgrad_b200/buffer.py)."""
+        flush_pending(tuple(p.data for p in self.params) + tuple(extra or ()))
+
     def step(self) -> None:
+        self._before_inplace()
         for p in self.params:
             if p.grad is None:
                 continue
@@ -52,6 +58,7 @@ class SGD(Optimizer):
     def step(self) -> None:
         if self.momentum == 0:
             return super().step()
+        self._before_inplace()
         for p in self.params:
             if p.grad is None:
                 continue
@@ -81,6 +88,7 @@ class Adam(Optimizer):
         bc1 = float(_f32(1.0 - self.beta1 ** self.t))
         bc2 = float(_f32(1.0 - self.beta2 ** self.t))
         lr = float(_f32(self.lr))
+        self._before_inplace([t.data for t in self.m.values()] + [t.data for t in self.v.values()])
         b1, b2, eps = self.beta1, self.beta2, self.eps     # rounded to float32 inside the kernel generator
         for p in self.params:
             if p.grad is None:

@@ -181,6 +181,9 @@ class Relu(OP):
         return self.out
 
     def backward(self, upstream_grad: Buffer) -> tuple[Buffer]:
+        if Buffer._route(self.out, upstream_grad) is Device.CUDA and self.out.shape == upstream_grad.shape:
+            # one select instead of the reference's where(1, 0) followed by a multiply (same values)
+            return (self.out.where(upstream_grad, 0.0),)
         return (self.out.where(inp=1.0, other=0.0) * upstream_grad,)
 
 
@@ -233,6 +236,10 @@ class Softmax(OP):
 
     def backward(self, upstream_grad: Buffer) -> tuple[Buffer]:
         dev = Buffer._route(self.out, upstream_grad)
+        if dev is Device.CUDA and self.dim == self.out.ndim - 1 and self.out.numel >= (1 << 16):
+            # deferred: the masked_fill / scale backward that usually follow are folded into this kernel
+            return (Buffer._deferred(("softmax_bwd", self.out, upstream_grad, self.dim, "softmax"), self.out.shape,
+                                     self.out.dtype),)
         g = dispatcher.dispatch(op=UnaryOps.SOFTMAX_BACKWARD, device=dev, y=self.out, grad=upstream_grad, dim=self.dim)
         return (Buffer(g, self.out.shape, dev, self.out.dtype),)
 
@@ -248,6 +255,34 @@ class LogSoftmax(OP):
         g = dispatcher.dispatch(op=UnaryOps.LOG_SOFTMAX_BACKWARD, device=dev, y=self.out, grad=upstream_grad,
                                 dim=self.dim)
         return (Buffer(g, self.out.shape, dev, self.out.dtype),)
+
+
+class RMSNorm(OP):
+    """nn.RMSNorm as one node on CUDA (dlgrad/nn/__init__.py:28-41 composes pow / mean / add / rsqrt /
+    mul / mul).  The backward is what the reference's autograd yields for that composition INCLUDING its
+    zero Mean.backward (QUIRK, dlgrad/ops.py:86-91): the rsqrt branch receives no gradient, so
+        dx = (g * w) * rstd                      dw = sum_rows g * (x * rstd)."""
+    def forward(self, x: Buffer, weight: Buffer | None = None, eps: float = 1e-6) -> Buffer:
+        from dlgrad_b200.helpers import CustomOps as _C
+        dev = Buffer._route(x) if weight is None else Buffer._route(x, weight)
+        self.x, self.w = x, weight
+        y, rstd = dispatcher.dispatch(op=_C.RMSNORM, device=dev, x=x, weight=weight, eps=eps)
+        self.rstd = Buffer(rstd, x.shape[:-1] + (1,), dev, x.dtype)
+        return Buffer(y, x.shape, dev, x.dtype)
+
+    def backward(self, upstream_grad: Buffer) -> tuple:
+        from dlgrad_b200.runtime.cuda import ops as _rt
+        g, x, w, t = upstream_grad, self.x, self.w, self.rstd
+        gx = gw = None
+        if self.req_grad[0]:
+            if w is not None:
+                gx = Buffer(_rt.ewise3("rms_dx", "(v0 * v1) * v2", x.shape, [g, w, t]), x.shape, Device.CUDA, x.dtype)
+            else:
+                gx = Buffer(_rt.ewise3("rms_dx", "v0 * v1", x.shape, [g, t]), x.shape, Device.CUDA, x.dtype)
+        if w is not None and len(self.req_grad) > 1 and self.req_grad[1]:
+            z = Buffer(_rt.ewise3("rms_dw", "v0 * (v1 * v2)", x.shape, [g, x, t]), x.shape, Device.CUDA, x.dtype)
+            gw = z.reshape((x.numel // x.shape[-1], x.shape[-1])).sum(0, keepdim=True).reshape(w.shape)
+        return (gx, gw)
 
 
 # ------------------------------------------------------------------ binary
@@ -328,6 +363,39 @@ class MatMul(OP):
         gx = unbroadcast(g @ yr.transpose(nd - 2, nd - 1), self.x.shape)
         gy = unbroadcast(xr.transpose(nd - 2, nd - 1) @ g, self.y.shape)
         return gx, gy
+
+
+class Linear(OP):
+    """`x @ weight.T (+ bias)` as one node on CUDA (Tensor.linear, dlgrad/tensor.py:520-535, builds it from
+    a materialised transpose, a batched matmul whose second operand is broadcast, and an add).  Here the
+    stored (out, in) weight is read K-major by the tensor-core kernel, so no transpose is written; in the
+    backward dX = g @ W, and dW = g^T @ x runs as ONE GEMM over the flattened (batch*tokens) axis instead
+    of per-batch products followed by a sum over the batch and a transpose back."""
+    def forward(self, x: Buffer, weight: Buffer, bias: Buffer | None = None) -> Buffer:
+        from dlgrad_b200.helpers import BinaryOps
+        self.x, self.w, self.b = x, weight, bias
+        out_f, in_f = weight.shape
+        rows = x.numel // in_f
+        y = dispatcher.dispatch(op=BinaryOps.MATMUL, device=Device.CUDA, x=x.reshape((rows, in_f)), y=weight, trans_y=True)
+        out = Buffer(y, x.shape[:-1] + (out_f,), Device.CUDA, x.dtype)
+        return out if bias is None else out + bias
+
+    def backward(self, upstream_grad: Buffer) -> tuple:
+        from dlgrad_b200.helpers import BinaryOps
+        out_f, in_f = self.w.shape
+        rows = self.x.numel // in_f
+        g2 = upstream_grad.reshape((rows, out_f))
+        gx = gw = gb = None
+        if self.req_grad[0]:
+            gx = Buffer(dispatcher.dispatch(op=BinaryOps.MATMUL, device=Device.CUDA, x=g2, y=self.w),
+                        self.x.shape, Device.CUDA, self.x.dtype)
+        if self.req_grad[1]:
+            gw = Buffer(dispatcher.dispatch(op=BinaryOps.MATMUL, device=Device.CUDA, x=g2,
+                                            y=self.x.reshape((rows, in_f)), trans_x=True),
+                        (out_f, in_f), Device.CUDA, self.w.dtype)
+        if self.b is not None and self.req_grad[2]:
+            gb = g2.sum(0, keepdim=True).reshape(self.b.shape)
+        return (gx, gw, gb) if self.b is not None else (gx, gw)
 
 
 # ------------------------------------------------------------------ losses

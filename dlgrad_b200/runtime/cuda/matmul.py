@@ -51,8 +51,9 @@ def run_matmul(x: Buffer, y: Buffer, trans_x: bool = False, trans_y: bool = Fals
     timer = _profile.matmul_timer
     if timer is None:
         return plan(_ops._dev_ptr(x), _ops._dev_ptr(y))
+    px, py = _ops._dev_ptr(x), _ops._dev_ptr(y)      # materialise deferred operands OUTSIDE the bracket
     t0 = timer.start()
-    out = plan(_ops._dev_ptr(x), _ops._dev_ptr(y))
+    out = plan(px, py)
     timer.stop(t0, plan.flops, plan.tag)
     return out
 
@@ -61,12 +62,49 @@ def _build(xs, ys, tx, ty, aligned):
     M, N, K, batch, a_bs, b_bs, _ = _geometry(xs, ys, tx, ty)
     if not FORCE_SIMT:
         from dlgrad_b200.runtime.cuda import matmul_tc
+        split = _split_k(M, N, K, batch, tx, ty)
+        if split > 1:
+            sk = _build_split_k(M, N, K, split, aligned)
+            if sk is not None:
+                return sk
         tc = matmul_tc.try_build(M, N, K, batch, a_bs, b_bs, tx, ty, aligned)
         if tc is not None:
             return tc
     k = ck.matmul_simt(M, N, K, batch[0], batch[1], a_bs, b_bs, tx, ty, aligned)
     p = _ops.Plan(k, prod_(batch) * M * N)
     return MatmulPlan(lambda a, b: p.run(a, b), 2.0 * prod_(batch) * M * N * K, ("simt", M, N, K, prod_(batch)))
+
+
+def _split_k(M: int, N: int, K: int, batch: tuple, tx: bool, ty: bool) -> int:
+    """Weight-gradient GEMMs (x^T @ g: small M x N output, K = batch*tokens) leave most of the 148 SMs idle
+    with one CTA per output tile.  For the TN form both operands are stored [K][cols], so K-slices ARE a
+    batch dimension: run S independent slices as a batched GEMM and add the S partial outputs in a fixed
+    order with the column-reduce kernel (deterministic, no atomics)."""
+    if not (tx and not ty) or prod_(batch) != 1 or K < 2048:
+        return 1
+    tiles = -(-M // 128) * -(-N // 128)
+    if tiles >= 100:
+        return 1
+    s = 1
+    while s * 2 * tiles <= 160 and K % (s * 2) == 0 and K // (s * 2) >= 512:
+        s *= 2
+    return s
+
+
+def _build_split_k(M: int, N: int, K: int, S: int, aligned: bool):
+    from dlgrad_b200.runtime.cuda import matmul_tc
+    ks = K // S
+    part = matmul_tc.try_build(M, N, ks, (1, S), (0, ks * M), (0, ks * N), True, False, aligned)
+    if part is None:
+        return None
+    reduce_plans = _ops._build_reduce("sum", (S, M * N), 0, True)
+
+    def run(a, b):
+        ptr = part(a, b)
+        for p in reduce_plans:
+            ptr = p.run(ptr)
+        return ptr
+    return MatmulPlan(run, 2.0 * M * N * K, ("tc3_splitk", M, N, K, S))
 
 
 class MatmulPlan:

@@ -16,6 +16,7 @@ ffi, lib, NULL = shim.ffi, shim.lib, shim.NULL
 PASSES = int(os.environ.get("DLGRAD_TC_PASSES", "3"))
 ENABLED = os.environ.get("DLGRAD_TC", "1") != "0"
 MIN_FLOPS = 1 << 22
+KERNEL = os.environ.get("DLGRAD_TC_KERNEL", "v2")     # v2 = persistent, v1 = one tile per CTA
 
 
 def _tmap(d: dict):
@@ -47,7 +48,7 @@ def qualifies(M, N, K, batch, a_bs, b_bs, tx, ty, aligned, force: bool = False) 
     if am is None or bm is None:
         return None
     a_mn, b_mn = bool(tx), not bool(ty)
-    if (M if a_mn else K) % 4 or (N if b_mn else K) % 4:
+    if (M if a_mn else K) % 4 or (N if b_mn else K) % 4 or N % 4:
         return None                                   # TMA needs 16-byte global pitches
     if not force and (K < 8 or N < 8 or M < 16 or 2.0 * M * N * K * nb < MIN_FLOPS):
         return None
@@ -56,13 +57,16 @@ def qualifies(M, N, K, batch, a_bs, b_bs, tx, ty, aligned, force: bool = False) 
 
 
 def try_build(M, N, K, batch, a_bs, b_bs, tx, ty, aligned, passes: int | None = None, bn: int | None = None,
-              stages: int | None = None, hi_inplace: bool = False, force: bool = False):
+              stages: int | None = None, hi_inplace: bool = False, force: bool = False, kernel: str | None = None):
     q = qualifies(M, N, K, batch, a_bs, b_bs, tx, ty, aligned, force)
     if q is None:
         return None
     a_mn, b_mn, a_bc, b_bc, nb = q
     passes = passes or PASSES
-    k = tc.matmul_tc(M, N, K, nb, a_mn, b_mn, a_bc, b_bc, passes, bn, stages, hi_inplace)
+    if (kernel or KERNEL) == "v1":
+        k = tc.matmul_tc(M, N, K, nb, a_mn, b_mn, a_bc, b_bc, passes, bn, stages, hi_inplace)
+    else:
+        k = tc.matmul_tc_persistent(M, N, K, nb, a_mn, b_mn, a_bc, b_bc, passes, bn, stages)
     shim.init()
     fn = compiler.get_function(k.name, k.source)
     da, db, dc = tc.tmap_descs(M, N, K, nb, a_mn, b_mn, a_bc, b_bc, k.bn)

@@ -12,9 +12,11 @@ Python per dispatch there.
 """
 from __future__ import annotations
 
+import builtins
+
 import numpy as np
 
-from dlgrad_b200.buffer import Buffer
+from dlgrad_b200.buffer import Buffer, flush_pending
 from dlgrad_b200.codegen import cuda_kernel as ck
 from dlgrad_b200.device import Device
 from dlgrad_b200.dispatch import dispatcher
@@ -30,12 +32,14 @@ from dlgrad_b200.helpers import (
     prod_,
 )
 from dlgrad_b200.runtime.cuda import compiler, shim, transfer
+from dlgrad_b200.runtime.cuda import profile as _profile
 
 ffi, lib, NULL = shim.ffi, shim.lib, shim.NULL
 _own = shim.own
 CUDA = Device.CUDA
 _plans: dict = {}
 _rng = np.random.default_rng()
+builtins_max, builtins_min = builtins.max, builtins.min
 
 
 def manual_seed(seed: int) -> None:
@@ -60,14 +64,131 @@ class Plan:
             raise RuntimeError("dlg_plan_create failed: " + shim.last_error())
 
     def run(self, p0=NULL, p1=NULL, p2=NULL, p3=NULL, f0=0.0, f1=0.0, f2=0.0, f3=0.0) -> CDataPtr:
-        out = lib.dlg_plan_run(self.c, p0, p1, p2, p3, f0, f1, f2, f3)
+        timer = _profile.kernel_timer
+        if timer is not None:
+            t0 = timer.start()
+            out = lib.dlg_plan_run(self.c, p0, p1, p2, p3, f0, f1, f2, f3)
+            timer.stop(t0, float(self.nbytes), (self.kernel.name,))
+        else:
+            out = lib.dlg_plan_run(self.c, p0, p1, p2, p3, f0, f1, f2, f3)
         if out == NULL:
             raise RuntimeError("kernel launch failed: " + shim.last_error())
         return _own(out, self.nbytes)
 
     def run_into(self, out, p0=NULL, p1=NULL, p2=NULL, p3=NULL, f0=0.0, f1=0.0, f2=0.0, f3=0.0) -> None:
+        timer = _profile.kernel_timer
+        t0 = timer.start() if timer is not None else None
         if lib.dlg_plan_run_into(self.c, out, p0, p1, p2, p3, f0, f1, f2, f3) != 0:
             raise RuntimeError("kernel launch failed: " + shim.last_error())
+        if timer is not None:
+            timer.stop(t0, 0.0, (self.kernel.name,))
+
+
+# ------------------------------------------------------------------------------------------------
+# deferred pointwise chains (Buffer._pending)
+# ------------------------------------------------------------------------------------------------
+def _peel_chain(buf: Buffer) -> tuple[list, Buffer]:
+    """Pending pointwise ops from `buf` down to its base, innermost first."""
+    chain, b = [], buf
+    while b._pending is not None and b._pending[0] in ("scale", "mfill"):
+        chain.append(b._pending)
+        b = b._pending[1]
+    chain.reverse()
+    return chain, b
+
+
+def _mask_lead(out_shape: tuple, mask: Buffer):
+    """(lead_shape, lead_strides, ok) of a mask broadcast against rows of `out_shape`."""
+    ms = get_broadcast_strides_2(out_shape, mask.metadata.shape, calculate_stride(mask.metadata.shape))
+    if ms[-1] != 1 and out_shape[-1] != 1:
+        return None
+    return tuple(out_shape[:-1]), tuple(ms[:-1])
+
+
+def _row_chain_args(chain: list, out_shape: tuple, aligned: bool):
+    """Translate pending ops into softmax-kernel chain descriptors + launch arguments.  Slots: p2/p3 carry
+    up to two masks (p0/p1 are the row kernel's own operands), f0/f2 carry scales, f1/f3 fill values."""
+    desc, ptrs, fl = [], [], [0.0, 0.0, 0.0, 0.0]
+    n_scale = n_mask = 0
+    for op in chain:
+        if op[0] == "scale":
+            if n_scale >= 2:
+                return None
+            slot = (0, 2)[n_scale]
+            fl[slot] = op[2]
+            desc.append(("scale", slot))
+            n_scale += 1
+        else:
+            if n_mask >= 2:
+                return None
+            lead = _mask_lead(out_shape, op[2])
+            if lead is None or not op[2].aligned or any(s % 4 for s in lead[1]):
+                return None
+            fslot, pslot = (1, 3)[n_mask], (2, 3)[n_mask]
+            fl[fslot] = op[3]
+            desc.append(("mfill", pslot, fslot, lead[0], lead[1]))
+            ptrs.append(op[2])
+            n_mask += 1
+    return tuple(desc), ptrs, fl
+
+
+def materialize(buf: Buffer) -> None:
+    """Run the deferred producer chain of `buf` as ONE kernel and give it real storage."""
+    pend = buf._pending
+    if pend is None:
+        return
+    chain, base = _peel_chain(buf)
+    shape = buf.metadata.shape
+    bp = base._pending
+    if bp is not None and bp[0] == "softmax_bwd":
+        _, y, g, dim, kind = bp
+        rows = _rows_of(shape, dim)
+        args = _row_chain_args(chain, shape, y.aligned and g.aligned) if rows is not None else None
+        if args is not None:
+            desc, masks, fl = args
+            ok = y.aligned and g.aligned
+            key = (kind + "_bwd_chain", rows, ok, desc)
+            plan = _plans.get(key)
+            if plan is None:
+                plan = _plans[key] = Plan(ck.softmax_bwd_rows(kind, rows[0], rows[1], ok, desc))
+            mp = [_dev_ptr(m) for m in masks] + [NULL, NULL]
+            buf.ptr = plan.run(_dev_ptr(y), _dev_ptr(g), mp[0], mp[1], fl[0], fl[1], fl[2], fl[3])
+            return
+        base.ptr = _softmax_bwd_family(kind, y, g, dim)          # could not fold: plain kernel, then the chain
+    if base._pending is not None:
+        materialize(base)
+    if not chain:
+        buf.ptr = base._ptr
+        return
+    # pointwise chain over a materialised base: one generated ewise kernel
+    expr, strides, ptrs, fl, nf = "v0", [calculate_stride(shape)], [base], [0.0, 0.0, 0.0, 0.0], 0
+    for op in chain:
+        if nf >= 4 or len(ptrs) >= 4:
+            break
+        if op[0] == "scale":
+            expr = f"(({expr}) * f{nf})"
+            fl[nf] = op[2]
+            nf += 1
+        else:
+            mask = op[2]
+            strides.append(get_broadcast_strides_2(shape, mask.metadata.shape, calculate_stride(mask.metadata.shape)))
+            expr = f"((v{len(ptrs)} > 0.f) ? f{nf} : ({expr}))"
+            ptrs.append(mask)
+            fl[nf] = op[3]
+            nf += 1
+    else:
+        ok = all(p.aligned for p in ptrs)
+        key = ("chain", expr, shape, tuple(strides), ok)
+        plan = _plans.get(key)
+        if plan is None:
+            plan = _plans[key] = Plan(ck.ewise(expr, shape, tuple(strides), ok, "chain"))
+        pp = [_dev_ptr(p) for p in ptrs] + [NULL] * 3
+        buf.ptr = plan.run(pp[0], pp[1], pp[2], pp[3], fl[0], fl[1], fl[2], fl[3])
+        return
+    # chain too long for one kernel: materialise the inner part first
+    inner = buf._pending[1]
+    materialize(inner)
+    materialize(buf)
 
 
 def _dev_ptr(b: Buffer):
@@ -316,14 +437,30 @@ def _build_reduce(op: str, shape: tuple, dim: int, aligned: bool) -> list[Plan]:
             G = k1.out_elems
             return [Plan(k1), Plan(ck.reduce_rows(op, 1, G, True, scale_R=R))]
         return [Plan(ck.reduce_rows(op, outer, R, aligned))]
-    # strided: split R across blocks when (outer x inner) cannot occupy the chip
+    if aligned and inner % 4 == 0 and inner >= 128:
+        # wide contiguous axis: row-slab kernel (consecutive rows, long contiguous runs per CTA)
+        ncolv = inner // 4
+        nspans = -(-ncolv // (256 * builtins_min(4, -(-ncolv // 256))))
+        ctas = nspans * outer
+        slabs = 1
+        if ctas < 2 * ck.NUM_SMS and R >= 16:
+            slabs = builtins_max(1, builtins_min(R // 8, -(-2 * ck.NUM_SMS // ctas)))
+        if slabs == 1:
+            return [Plan(ck.reduce_cols_slab(op, outer, R, inner, 1, True))]
+        # second pass over the (L2-resident) slab partials: 128-column strips, 8 warps interleaving rows
+        return [Plan(ck.reduce_cols_slab(first, outer, R, inner, slabs, False)),
+                Plan(ck.reduce_cols(op, 1, slabs, outer * inner, True, 1, scale_R=R))]
+    # narrow / unaligned: column strips; R split across a thread-block cluster when the grid is small
     V = 4 if (aligned and inner % 4 == 0) else 1
     blocks = -(-(inner // V) // 32) * outer
     splits = 1
     if blocks < 2 * ck.NUM_SMS and R >= 128:
-        splits = max(1, min(R // 64, -(-2 * ck.NUM_SMS // blocks)))
+        splits = builtins_max(1, builtins_min(R // 64, -(-2 * ck.NUM_SMS // blocks)))
     if splits == 1:
         return [Plan(ck.reduce_cols(op, outer, R, inner, aligned))]
+    if splits <= 8 or R // 8 >= 256:
+        # one launch: the R-slices of a column tile form a thread-block cluster and combine through DSMEM
+        return [Plan(ck.reduce_cols(op, outer, R, inner, aligned, builtins_min(splits, 8), None, True))]
     return [Plan(ck.reduce_cols(first, outer, R, inner, aligned, splits)),
             Plan(ck.reduce_cols(op, 1, splits, outer * inner, True, 1, scale_R=R))]
 
@@ -379,6 +516,18 @@ def _softmax_family(kind: str, x: Buffer, dim: int) -> CDataPtr:
         e = sh.exp()
         s = e.sum(dim=dim, keepdim=True)
         return (e / s).ptr if kind == "softmax" else (sh - s.log()).ptr
+    if x._pending is not None:
+        chain, base = _peel_chain(x)
+        if chain and base._pending is None:
+            args = _row_chain_args(chain, x.metadata.shape, base.aligned)
+            if args is not None:
+                desc, masks, fl = args
+                key = (kind + "_chain", rows, base.aligned, desc)
+                plan = _plans.get(key)
+                if plan is None:
+                    plan = _plans[key] = Plan(ck.softmax_rows(kind, rows[0], rows[1], base.aligned, desc))
+                mp = [_dev_ptr(m) for m in masks] + [NULL, NULL]
+                return plan.run(_dev_ptr(base), NULL, mp[0], mp[1], fl[0], fl[1], fl[2], fl[3])
     key = (kind, rows, x.aligned)
     plan = _plans.get(key)
     if plan is None:
@@ -471,6 +620,7 @@ def ce_forward(x: Buffer, y: Buffer) -> CDataPtr:
 @dispatcher.register(CustomOps.CE_BACKWARD, CUDA)
 def ce_backward(x: Buffer, target: Buffer) -> None:
     n, s0 = x.metadata.shape[0], x.metadata.shape[1]
+    flush_pending((x,))
     key = ("ce_bwd", n, s0)
     plan = _plans.get(key)
     if plan is None:
@@ -532,6 +682,34 @@ def sgd_step(param: Buffer, grad: Buffer, lr: float, grad_scale: float = 1.0) ->
     if plan is None:
         plan = _plans[key] = Plan(ck.sgd_step(param.metadata.numel, ok))
     plan.run_into(NULL, _dev_ptr(param), _dev_ptr(grad), NULL, NULL, lr, 0.0, 0.0, grad_scale)
+
+
+@dispatcher.register(CustomOps.RMSNORM, CUDA)
+def rmsnorm(x: Buffer, weight: Buffer | None, eps: float):
+    """Fused RMSNorm forward -> (y, rstd); nn.RMSNorm composes six kernels (dlgrad/nn/__init__.py:28-41)."""
+    shape = x.metadata.shape
+    C, rows = shape[-1], prod_(shape[:-1])
+    ok = x.aligned and (weight is None or weight.aligned)
+    key = ("rmsnorm", rows, C, weight is not None, ok)
+    plan = _plans.get(key)
+    if plan is None:
+        plan = _plans[key] = Plan(ck.rmsnorm_rows(rows, C, weight is not None, ok))
+    rstd = shim.alloc(rows * 4)
+    y = plan.run(_dev_ptr(x), _dev_ptr(weight) if weight is not None else NULL, rstd, NULL, float(eps))
+    return y, rstd
+
+
+def ewise3(tag: str, expr: str, out_shape: tuple, operands: list[Buffer]) -> CDataPtr:
+    """out = expr(v0, v1, v2) with every operand broadcast to out_shape (helper for fused backward formulas)."""
+    ok = all(b.aligned for b in operands)
+    key = ("ew3", tag, expr, out_shape, tuple(b.metadata.shape for b in operands), ok)
+    plan = _plans.get(key)
+    if plan is None:
+        strides = tuple(get_broadcast_strides_2(out_shape, b.metadata.shape, calculate_stride(b.metadata.shape))
+                        for b in operands)
+        plan = _plans[key] = Plan(ck.ewise(expr, tuple(out_shape), strides, ok, tag))
+    pp = [_dev_ptr(b) for b in operands] + [NULL] * 3
+    return plan.run(pp[0], pp[1], pp[2], pp[3])
 
 
 @dispatcher.register(CustomOps.PRINT, CUDA)

@@ -59,3 +59,4 @@ class KernelTimer:
 
 
 matmul_timer: KernelTimer | None = None     # set by bench.py around the timed region
+kernel_timer: KernelTimer | None = None     # every generated-kernel launch, by kernel family (bench.py --profile)

@@ -97,6 +97,8 @@ class Tensor:
         """Overwrite the storage with raw bytes (H2D when on CUDA); dlgrad/tensor.py:131-138."""
         if len(source_bytes) != self.nbytes:
             raise ValueError(f"Buffer size mismatch! Expected {self.nbytes} bytes, got {len(source_bytes)}")
+        from dlgrad_b200.buffer import flush_pending
+        flush_pending()
         if self.data.metadata.device is _CUDA:
             from dlgrad_b200.runtime.cuda import transfer
             transfer.write_bytes(self.data.ptr, bytes(source_bytes))
@@ -179,6 +181,9 @@ class Tensor:
 
     def linear(self, weight: "Tensor", bias: "Tensor | None") -> "Tensor":
         """`self @ weight.T + bias` (dlgrad/tensor.py:520-535)."""
+        if not self._on_host_runtime() and weight.ndim == 2 and self.ndim >= 2:
+            Buffer._route(self.data, weight.data)          # host-created layers migrate to HBM here, once
+            return ops.Linear.execute(self, weight, bias) if bias is not None else ops.Linear.execute(self, weight)
         out = self @ weight.T
         return out + bias if bias is not None else out
 
@@ -339,6 +344,10 @@ class Tensor:
                     continue
                 g_t = Tensor(g)
                 parent.grad = g_t if parent.grad is None else parent.grad + g_t
+            if node is not self:
+                # an interior node's gradient has been consumed: release it (a (B,h,T,T) attention gradient
+                # is 400 MB at the benchmark config; the reference keeps every one alive until the graph dies)
+                node.grad = None
         if order:
             self._ctx = None
 

@@ -1,7 +1,7 @@
 #!/bin/bash
 mkdir -p gpurun_out
-for part in sem p1 p3 perf; do
-  timeout 120 python scripts/tc_probe.py $part > gpurun_out/tc_probe_$part.log 2>&1; echo "exit $?" >> gpurun_out/tc_probe_$part.log
-  tail -30 gpurun_out/tc_probe_$part.log
+for part in p1 p3 perf; do
+  timeout 180 python scripts/tc_probe.py $part > gpurun_out/tc_probe_$part.log 2>&1; echo "exit $?" >> gpurun_out/tc_probe_$part.log
+  tail -40 gpurun_out/tc_probe_$part.log
 done
-nvidia-smi --query-gpu=name,temperature.gpu --format=csv
+timeout 300 python bench.py --ops-only > gpurun_out/ops.log 2>&1; echo "exit $?" >> gpurun_out/ops.log; cat gpurun_out/ops.log | tail -20

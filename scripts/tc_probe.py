@@ -15,8 +15,8 @@ rng = np.random.default_rng(0)
 results = {}
 
 
-def run(M, N, K, nb=1, tx=False, ty=False, a_b=False, b_b=False, passes=3, bn=None, stages=None, hi_inplace=True,
-        a=None, b=None, time_it=0):
+def run(M, N, K, nb=1, tx=False, ty=False, a_b=False, b_b=False, passes=3, bn=None, stages=None, hi_inplace=False,
+        a=None, b=None, time_it=0, kernel=None):
     batch = (1, nb)
     if a is None:
         a = (rng.random(((1 if a_b else nb), K, M) if tx else ((1 if a_b else nb), M, K), dtype=np.float32) - 0.5).astype(np.float32)
@@ -25,7 +25,7 @@ def run(M, N, K, nb=1, tx=False, ty=False, a_b=False, b_b=False, passes=3, bn=No
     a_bs = (0, 0) if (a_b or nb == 1) else (0, M * K)
     b_bs = (0, 0) if (b_b or nb == 1) else (0, K * N)
     plan = matmul_tc.try_build(M, N, K, batch, a_bs, b_bs, tx, ty, True, passes=passes, bn=bn, stages=stages,
-                               hi_inplace=hi_inplace, force=True)
+                               hi_inplace=hi_inplace, force=True, kernel=kernel)
     assert plan is not None, "shape did not qualify"
     da, db = transfer.upload_numpy(a), transfer.upload_numpy(b)
     out = plan(da, db)
@@ -84,24 +84,34 @@ if which in ("all", "p1"):
     case("p1 TN 128x128x128", M=128, N=128, K=128, tx=True, passes=1)
 if which in ("all", "p3"):
     case("p3 NN 128x128x128", M=128, N=128, K=128)
-    case("p3 NN 128x128x128 raw-hi", M=128, N=128, K=128, hi_inplace=False)
     case("p3 NT 128x128x128", M=128, N=128, K=128, ty=True)
     case("p3 TN 128x128x128", M=128, N=128, K=128, tx=True)
     case("p3 NN 200x96x72 ragged", M=200, N=96, K=72)
+    case("p3 NN 333x100x44 ragged", M=333, N=100, K=44)
+    case("p3 NN 1000x1000x1000", M=1000, N=1000, K=1000)
     case("p3 NN batched 8x1024x96x768 bB", M=1024, N=96, K=768, nb=8, b_b=True)
     case("p3 NN batched 96x1024x64x1024", M=1024, N=64, K=1024, nb=96)
     case("p3 NT batched 96x1024x1024x64", M=1024, N=1024, K=64, nb=96, ty=True)
     case("p3 TN batched 96x1024x64x1024", M=1024, N=64, K=1024, nb=96, tx=True)
+    case("p3 NN 4096^3 accuracy U[0,1)", M=4096, N=4096, K=4096,
+         a=np.random.default_rng(5).random((1, 4096, 4096), dtype=np.float32), b=np.random.default_rng(6).random((1, 4096, 4096), dtype=np.float32))
+    case("p3 TN 768x3072x8192 accuracy U[0,1)", M=768, N=3072, K=8192, tx=True,
+         a=np.random.default_rng(5).random((1, 8192, 768), dtype=np.float32), b=np.random.default_rng(6).random((1, 8192, 3072), dtype=np.float32))
+    case("p3 NN 512x512x16384 accuracy U[0,1)", M=512, N=512, K=16384,
+         a=np.random.default_rng(5).random((1, 512, 16384), dtype=np.float32), b=np.random.default_rng(6).random((1, 16384, 512), dtype=np.float32))
 if which in ("all", "perf"):
-    case("perf p3 NN 4096^3 bn256", M=4096, N=4096, K=4096, time_it=5)
-    case("perf p3 NN 4096^3 bn128", M=4096, N=4096, K=4096, bn=128, time_it=5)
-    case("perf p3 NN 4096^3 raw-hi bn256", M=4096, N=4096, K=4096, hi_inplace=False, time_it=5)
-    case("perf p1 NN 4096^3 bn256", M=4096, N=4096, K=4096, passes=1, time_it=5)
-    case("perf p3 NT 4096^3", M=4096, N=4096, K=4096, ty=True, time_it=5)
-    case("perf p3 TN 4096^3", M=4096, N=4096, K=4096, tx=True, time_it=5)
-    case("perf p3 NN 8192x768x768 bB", M=8192, N=768, K=768, b_b=True, time_it=10)
-    case("perf p3 NN 8192x3072x768", M=8192, N=3072, K=768, time_it=10)
-    case("perf p3 TN 768x3072x8192", M=768, N=3072, K=8192, tx=True, time_it=10)
+    shapes = {"4096^3": dict(M=4096, N=4096, K=4096), "8192x768x768": dict(M=8192, N=768, K=768),
+              "8192x3072x768": dict(M=8192, N=3072, K=768), "8192x768x3072": dict(M=8192, N=768, K=3072),
+              "TN 768x3072x8192": dict(M=768, N=3072, K=8192, tx=True), "TN 768x768x8192": dict(M=768, N=768, K=8192, tx=True),
+              "NT 8192x768x3072": dict(M=8192, N=768, K=3072, ty=True),
+              "b96 QK^T 1024x1024x64": dict(M=1024, N=1024, K=64, nb=96), "b96 AV 1024x64x1024": dict(M=1024, N=64, K=1024, nb=96),
+              "b96 dV TN 1024x64x1024": dict(M=1024, N=64, K=1024, nb=96, tx=True),
+              "b96 dAtt NT 1024x1024x64": dict(M=1024, N=1024, K=64, nb=96, ty=True)}
+    for name, kw in shapes.items():
+        case(f"perf auto {name}", time_it=10, **kw)
+        for bn in (64, 128, 192, 256):
+            if bn <= kw["N"]:
+                case(f"perf bn{bn} {name}", time_it=10, bn=bn, **kw)
 os.makedirs("gpurun_out", exist_ok=True)
 with open(f"gpurun_out/tc_probe_{which}.json", "w") as f:
     json.dump(results, f, indent=1)
