@@ -302,7 +302,8 @@ extern "C" __global__ void __launch_bounds__(192, 1)
     return TcKernel(f"mm_tc{passes}", src, grid, 192, smem, batch * M * N, BN, stages)
 
 
-def tmap_descs(M: int, N: int, K: int, batch: int, a_mn: bool, b_mn: bool, a_bcast: bool, b_bcast: bool, BN: int):
+def tmap_descs(M: int, N: int, K: int, batch: int, a_mn: bool, b_mn: bool, a_bcast: bool, b_bcast: bool, BN: int,
+               b_tile_rows: int | None = None):
     """(dims, strides_bytes, box) triples for A, B and C in the shim's dlg_tmap_desc layout."""
     def operand(rows, mn, bcast, tile_rows):
         nb = 1 if bcast else batch
@@ -310,7 +311,7 @@ def tmap_descs(M: int, N: int, K: int, batch: int, a_mn: bool, b_mn: bool, a_bca
             return dict(rank=3, dims=(rows, K, nb), strides=(rows * 4, rows * K * 4), box=(32, BK, 1), swizzle=4)
         return dict(rank=3, dims=(K, rows, nb), strides=(K * 4, rows * K * 4), box=(BK, tile_rows, 1), swizzle=3)
     a = operand(M, a_mn, a_bcast, BM)
-    b = operand(N, b_mn, b_bcast, BN)
+    b = operand(N, b_mn, b_bcast, b_tile_rows or BN)
     c = dict(rank=3, dims=(N, M, batch), strides=(N * 4, M * N * 4), box=(32, 32, 1), swizzle=3)
     return a, b, c
 
@@ -403,7 +404,7 @@ def pick_bn_persistent(M: int, N: int, batch: int, kblocks: int) -> int:
 @cache
 def matmul_tc_persistent(M: int, N: int, K: int, batch: int, a_mn: bool, b_mn: bool, a_bcast: bool, b_bcast: bool,
                          passes: int = 3, bn: int | None = None, stages: int | None = None,
-                         kc_blocks: int | None = None) -> TcKernel:
+                         kc_blocks: int | None = None, split_warps: int = 8) -> TcKernel:
     kblocks = _cdiv(K, BK)
     # K is accumulated in TMEM in chunks of <= 1024: the tensor core adds into the fp32 accumulator with
     # truncation, a bias that grows with the accumulator's magnitude (8.5e-5 at K = 4096 on U[0,1) inputs,
@@ -431,6 +432,9 @@ def matmul_tc_persistent(M: int, N: int, K: int, batch: int, a_mn: bool, b_mn: b
     a_boxes = BM // 32 if a_mn else 1
     b_boxes = BN // 32 if b_mn else 1
     grid = min(ntiles, NUM_SMS)
+    nsw = split_warps if passes == 3 else 4
+    nthreads = 64 + 32 * nsw + 128
+    epi_w0 = 2 + nsw                       # first epilogue warp (4 consecutive warps cover the 4 TMEM lane quarters)
 
     def tma_issue(which, boxes, mn, tile_var, row0):
         tm = f"tm{which}"
@@ -462,7 +466,7 @@ def matmul_tc_persistent(M: int, N: int, K: int, batch: int, a_mn: bool, b_mn: b
                 const float4* src = reinterpret_cast<const float4*>(smem_gen + s * {per_stage}u);
                 float4* dst = reinterpret_cast<float4*>(smem_gen + s * {per_stage}u + {ab}u);
                 #pragma unroll 4
-                for (unsigned i = ctid; i < {ab // 16}u; i += 128u) {{
+                for (unsigned i = ctid; i < {ab // 16}u; i += {32 * nsw}u) {{
                     const float4 x = src[i];
                     float4 lo;
                     lo.x = x.x - __uint_as_float(__float_as_uint(x.x) & 0xffffe000u);
@@ -490,7 +494,7 @@ def matmul_tc_persistent(M: int, N: int, K: int, batch: int, a_mn: bool, b_mn: b
         for j in range(8))
 
     src = _HELPERS + f"""
-extern "C" __global__ void __launch_bounds__(320, 1)
+extern "C" __global__ void __launch_bounds__({nthreads}, 1)
 {KNAME}(const __grid_constant__ TMap tmA, const __grid_constant__ TMap tmB, const __grid_constant__ TMap tmC, float* __restrict__ C)
 {{
     extern __shared__ unsigned char smem_raw[];
@@ -507,7 +511,7 @@ extern "C" __global__ void __launch_bounds__(320, 1)
         for (unsigned s = 0; s < {stages}u; ++s) {{
             mbar_init(full + s * 8u, 1u);
             mbar_init(empty + s * 8u, 1u);
-            mbar_init(split + s * 8u, 128u);
+            mbar_init(split + s * 8u, {32 * nsw}u);
         }}
         for (unsigned b = 0; b < 2u; ++b) {{
             mbar_init(tfull + b * 8u, 1u);
@@ -569,12 +573,12 @@ extern "C" __global__ void __launch_bounds__(320, 1)
                 }}
             }}
         }}
-    }} else if (warp < 6) {{{split_code}
+    }} else if (warp < {epi_w0}u) {{{split_code}
     }} else {{
         // ===== epilogue warps: TMEM -> registers -> swizzled smem box -> TMA store =====
         const unsigned q = warp & 3u;                          // TMEM lane quarter this warp may read
-        const unsigned my_epi = epi + (warp - 6u) * {EPI_BUFS * 4096}u;
-        unsigned char* my_epi_gen = smem_gen + {stages * per_stage}u + (warp - 6u) * {EPI_BUFS * 4096}u;
+        const unsigned my_epi = epi + (warp - {epi_w0}u) * {EPI_BUFS * 4096}u;
+        unsigned char* my_epi_gen = smem_gen + {stages * per_stage}u + (warp - {epi_w0}u) * {EPI_BUFS * 4096}u;
         unsigned u = 0, nstore = 0;
         for (unsigned t = blockIdx.x; t < {ntiles}u; t += {grid}u) {{
             {decode}
@@ -621,4 +625,265 @@ extern "C" __global__ void __launch_bounds__(320, 1)
     }}
 }}
 """
-    return TcKernel(f"mm_tcp{passes}", src, (grid, 1, 1), 320, smem, batch * M * N, BN, stages)
+    return TcKernel(f"mm_tcp{passes}", src, (grid, 1, 1), nthreads, smem, batch * M * N, BN, stages)
+
+
+# =====================================================================================================
+# v3: CTA-pair kernel (cta_group::2).  Two CTAs of a cluster (one TPC) compute a 256 x BN tile: each
+# stages ITS 128 rows of A and ITS half of the B columns, the leader issues M=256 MMAs that read both
+# shared memories, so every SM moves, splits and feeds only half of B — the shared-memory traffic that
+# bounds the 1-CTA kernel (TMA writes + hi/lo split + three operand reads per k-step) drops by a third.
+# =====================================================================================================
+_HELPERS_2CTA = r"""
+__device__ __forceinline__ unsigned cluster_rank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ unsigned map_to_cta(unsigned local_addr, unsigned rank) {
+    unsigned ra; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(local_addr), "r"(rank)); return ra;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(unsigned cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" :: "r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(unsigned bar, unsigned parity) {
+    // acquire at CLUSTER scope: the arrivals come from the partner CTA's threads
+    const long long t0 = clock64();
+    for (;;) {
+        unsigned ok;
+        asm volatile("{\n\t.reg .pred p;\n\t"
+                     "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+                     "selp.b32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        if (ok) return;
+        if (clock64() - t0 > 4000000000LL) __trap();
+    }
+}
+__device__ __forceinline__ void umma_tf32_2cta(unsigned tmem_d, unsigned long long adesc, unsigned long long bdesc,
+                                               unsigned idesc, unsigned accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit_2cta(unsigned bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 :: "r"(bar), "h"((unsigned short)3) : "memory");
+}
+"""
+
+
+@cache
+def matmul_tc_pair(M: int, N: int, K: int, batch: int, a_mn: bool, b_mn: bool, a_bcast: bool, b_bcast: bool,
+                   bn: int | None = None, stages: int | None = None, kc_blocks: int | None = None) -> TcKernel:
+    kblocks = _cdiv(K, BK)
+    kc = kc_blocks or (32 if kblocks > 64 else kblocks)
+    nchunks = _cdiv(kblocks, kc)
+    BN = bn or 256
+    BNH = BN // 2                                       # B columns staged by each CTA of the pair
+    a_tile, b_tile = BM * BK * 4, BNH * BK * 4
+    ab = a_tile + b_tile
+    per_stage = 2 * ab
+    EPI_BUFS = 2
+    epi_bytes = 4 * EPI_BUFS * 4096
+    budget = 227 * 1024 - 1024 - 512 - epi_bytes
+    if stages is None:
+        stages = max(2, min(6, budget // per_stage))
+    ntm, ntn = _cdiv(M, 2 * BM), _cdiv(N, BN)
+    ntiles = ntm * ntn * batch
+    npairs = min(ntiles, NUM_SMS // 2)
+    tmem_cols = 32
+    while tmem_cols < 2 * BN:
+        tmem_cols *= 2
+    smem = stages * per_stage + epi_bytes + 1024 + 512
+    idesc = _idesc(2 * BM, BN, a_mn, b_mn)
+    a_lbo, a_sbo, a_kstep, a_lt = (256, 32, 64, 1) if a_mn else (1, 64, 2, 2)
+    b_lbo, b_sbo, b_kstep, b_lt = (256, 32, 64, 1) if b_mn else (1, 64, 2, 2)
+    a_boxes = BM // 32 if a_mn else 1
+    b_boxes = BNH // 32 if b_mn else 1
+    nsw = 4
+    nthreads = 64 + 32 * nsw + 128
+    epi_w0 = 2 + nsw
+
+    def tma_issue(which, boxes, mn, tile_var, row0):
+        tm = f"tm{which}"
+        z = "0" if (a_bcast if which == "A" else b_bcast) else "z"
+        if mn:
+            return "\n                    ".join(
+                f"tma_load_3d({tile_var} + {j * 4096}u, &{tm}, full_bar, (int)({row0} + {j * 32}u), (int)k0, (int){z});"
+                for j in range(boxes))
+        return f"tma_load_3d({tile_var}, &{tm}, full_bar, (int)k0, (int){row0}, (int){z});"
+
+    decode = f"""const unsigned z = t / {ntm * ntn}u, rem = t % {ntm * ntn}u;
+            const unsigned m0 = (rem / {ntn}u) * {2 * BM}u + crank * {BM}u, n0 = (rem % {ntn}u) * {BN}u;"""
+    regs = ", ".join(f"%{i}" for i in range(32))
+    outs = ", ".join(f'"=r"(v[{i}])' for i in range(32))
+    stage_writes = "\n                        ".join(
+        f"*reinterpret_cast<float4*>(sbuf_gen + lane * 128u + (({j}u ^ (lane & 7u)) << 4)) = "
+        f"make_float4(__uint_as_float(v[{4 * j}]), __uint_as_float(v[{4 * j + 1}]), __uint_as_float(v[{4 * j + 2}]), __uint_as_float(v[{4 * j + 3}]));"
+        for j in range(8))
+
+    src = _HELPERS + _HELPERS_2CTA + f"""
+extern "C" __global__ void __launch_bounds__({nthreads}, 1)   // launched with cluster dimension 2 (shim: cluster_x)
+{KNAME}(const __grid_constant__ TMap tmA, const __grid_constant__ TMap tmB, const __grid_constant__ TMap tmC, float* __restrict__ C)
+{{
+    extern __shared__ unsigned char smem_raw[];
+    const unsigned smem = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    unsigned char* smem_gen = smem_raw + (smem - smem_u32(smem_raw));
+    const unsigned epi = smem + {stages * per_stage}u;
+    const unsigned bars = epi + {epi_bytes}u;
+    const unsigned full = bars, empty = bars + {stages * 8}u, split = bars + {stages * 16}u;
+    const unsigned tfull = bars + {stages * 24}u, tempty = tfull + 16u;
+    __shared__ unsigned tmem_slot;
+    const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    const unsigned crank = cluster_rank();               // 0 = leader (issues the MMAs)
+    const unsigned pair = blockIdx.x >> 1;
+
+    if (threadIdx.x == 0) {{
+        for (unsigned s = 0; s < {stages}u; ++s) {{
+            mbar_init(full + s * 8u, 1u);                // own TMA loads
+            mbar_init(empty + s * 8u, 1u);               // multicast commit from the leader
+            mbar_init(split + s * 8u, {2 * nsw}u);       // (leader's copy is used) one arrive per splitter warp of both CTAs
+        }}
+        for (unsigned b = 0; b < 2u; ++b) {{
+            mbar_init(tfull + b * 8u, 1u);               // multicast commit from the leader
+            mbar_init(tempty + b * 8u, 8u);              // (leader's copy) one arrive per epilogue warp of both CTAs
+        }}
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }}
+    if (warp == 1) {{
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&tmem_slot)), "n"({tmem_cols}));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+    }}
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    cluster_sync_all();                                  // both CTAs' barriers are initialised before any remote arrive
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const unsigned tmem_base = tmem_slot;
+
+    if (warp == 0) {{
+        // ===== TMA producer (each CTA stages its own A rows and its own half of the B columns) =====
+        if (lane == 0) {{
+            unsigned it = 0;
+            for (unsigned t = pair; t < {ntiles}u; t += {npairs}u) {{
+                {decode}
+                const unsigned nb0 = n0 + crank * {BNH}u;
+                for (unsigned kb = 0; kb < {kblocks}u; ++kb, ++it) {{
+                    const unsigned s = it % {stages}u, ph = (it / {stages}u) & 1u;
+                    mbar_wait(empty + s * 8u, ph ^ 1u);
+                    const unsigned full_bar = full + s * 8u;
+                    const unsigned a_s = smem + s * {per_stage}u, b_s = a_s + {a_tile}u;
+                    const unsigned k0 = kb * {BK}u;
+                    mbar_expect_tx(full_bar, {ab}u);
+                    {tma_issue("A", a_boxes, a_mn, "a_s", "m0")}
+                    {tma_issue("B", b_boxes, b_mn, "b_s", "nb0")}
+                }}
+            }}
+        }}
+    }} else if (warp == 1) {{
+        // ===== MMA issuer: leader CTA only, one lane; M = 256 across the pair =====
+        if (crank == 0 && lane == 0) {{
+            unsigned it = 0, u = 0;
+            for (unsigned t = pair; t < {ntiles}u; t += {npairs}u) {{
+                for (unsigned ch = 0; ch < {nchunks}u; ++ch, ++u) {{
+                    const unsigned b = u & 1u;
+                    mbar_wait_cluster(tempty + b * 8u, ((u >> 1) & 1u) ^ 1u);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const unsigned tacc = tmem_base + b * {BN}u;
+                    const unsigned kend = min((ch + 1u) * {kc}u, {kblocks}u);
+                    for (unsigned kb = ch * {kc}u, kbl = 0; kb < kend; ++kb, ++kbl, ++it) {{
+                        const unsigned s = it % {stages}u, ph = (it / {stages}u) & 1u;
+                        mbar_wait_cluster(split + s * 8u, ph);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        const unsigned a_s = smem + s * {per_stage}u, b_s = a_s + {a_tile}u;
+                        const unsigned long long adesc = make_desc(a_s, {a_lbo}u, {a_sbo}u, {a_lt}u);
+                        const unsigned long long bdesc = make_desc(b_s, {b_lbo}u, {b_sbo}u, {b_lt}u);
+                        #pragma unroll
+                        for (unsigned k = 0; k < {BK // 8}u; ++k) {{
+                            const unsigned long long a_hi = adesc + (unsigned long long)(k * {a_kstep}u);
+                            const unsigned long long b_hi = bdesc + (unsigned long long)(k * {b_kstep}u);
+                            umma_tf32_2cta(tacc, a_hi + {ab // 16}ull, b_hi, {idesc}u, (kbl | k) != 0u);
+                            umma_tf32_2cta(tacc, a_hi, b_hi + {ab // 16}ull, {idesc}u, 1u);
+                            umma_tf32_2cta(tacc, a_hi, b_hi, {idesc}u, 1u);
+                        }}
+                        umma_commit_2cta(empty + s * 8u);          // frees stage s in BOTH CTAs
+                    }}
+                    umma_commit_2cta(tfull + b * 8u);               // accumulator b is complete in BOTH CTAs
+                }}
+            }}
+        }}
+    }} else if (warp < {epi_w0}u) {{
+        // ===== splitter warps (both CTAs): lo = x - trunc_tf32(x); report to the LEADER's split barrier =====
+        const unsigned ctid = threadIdx.x - 64u;
+        unsigned it = 0;
+        for (unsigned t = pair; t < {ntiles}u; t += {npairs}u) {{
+            for (unsigned kb = 0; kb < {kblocks}u; ++kb, ++it) {{
+                const unsigned s = it % {stages}u, ph = (it / {stages}u) & 1u;
+                mbar_wait(full + s * 8u, ph);
+                const float4* src = reinterpret_cast<const float4*>(smem_gen + s * {per_stage}u);
+                float4* dst = reinterpret_cast<float4*>(smem_gen + s * {per_stage}u + {ab}u);
+                #pragma unroll 4
+                for (unsigned i = ctid; i < {ab // 16}u; i += {32 * nsw}u) {{
+                    const float4 x = src[i];
+                    float4 lo;
+                    lo.x = x.x - __uint_as_float(__float_as_uint(x.x) & 0xffffe000u);
+                    lo.y = x.y - __uint_as_float(__float_as_uint(x.y) & 0xffffe000u);
+                    lo.z = x.z - __uint_as_float(__float_as_uint(x.z) & 0xffffe000u);
+                    lo.w = x.w - __uint_as_float(__float_as_uint(x.w) & 0xffffe000u);
+                    dst[i] = lo;
+                }}
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(map_to_cta(split + s * 8u, 0u));
+            }}
+        }}
+    }} else {{
+        // ===== epilogue warps (both CTAs drain their own 128 accumulator rows) =====
+        const unsigned q = warp & 3u;
+        const unsigned my_epi = epi + (warp - {epi_w0}u) * {EPI_BUFS * 4096}u;
+        unsigned char* my_epi_gen = smem_gen + {stages * per_stage}u + (warp - {epi_w0}u) * {EPI_BUFS * 4096}u;
+        unsigned u = 0, nstore = 0;
+        for (unsigned t = pair; t < {ntiles}u; t += {npairs}u) {{
+            {decode}
+            for (unsigned ch = 0; ch < {nchunks}u; ++ch, ++u) {{
+                const unsigned b = u & 1u;
+                mbar_wait(tfull + b * 8u, (u >> 1) & 1u);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (ch != 0u && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+                #pragma unroll 1
+                for (unsigned c = 0; c < {BN // 32}u; ++c) {{
+                    unsigned v[32];
+                    const unsigned taddr = tmem_base + ((q * 32u) << 16) + b * {BN}u + c * 32u;
+                    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {{{regs}}}, [%32];" : {outs} : "r"(taddr));
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    if (n0 + c * 32u < {N}u && m0 + q * 32u < {M}u) {{
+                        const unsigned sb = nstore & {EPI_BUFS - 1}u;
+                        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read {EPI_BUFS - 1};" ::: "memory");
+                        __syncwarp();
+                        unsigned char* sbuf_gen = my_epi_gen + sb * 4096u;
+                        {stage_writes}
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                        __syncwarp();
+                        if (lane == 0) {{
+                            if (ch == 0u) tma_store_3d(&tmC, my_epi + sb * 4096u, (int)(n0 + c * 32u), (int)(m0 + q * 32u), (int)z);
+                            else tma_reduce_add_3d(&tmC, my_epi + sb * 4096u, (int)(n0 + c * 32u), (int)(m0 + q * 32u), (int)z);
+                            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                        }}
+                        ++nstore;
+                    }}
+                }}
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(map_to_cta(tempty + b * 8u, 0u));
+            }}
+        }}
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }}
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    cluster_sync_all();                                  // no CTA leaves while its partner may still touch it
+    if (warp == 1) {{
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "n"({tmem_cols}));
+    }}
+}}
+"""
+    return TcKernel("mm_tc2cta", src, (2 * npairs, 1, 1), nthreads, smem, batch * M * N, BN, stages)

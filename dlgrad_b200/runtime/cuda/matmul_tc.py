@@ -16,7 +16,8 @@ ffi, lib, NULL = shim.ffi, shim.lib, shim.NULL
 PASSES = int(os.environ.get("DLGRAD_TC_PASSES", "3"))
 ENABLED = os.environ.get("DLGRAD_TC", "1") != "0"
 MIN_FLOPS = 1 << 22
-KERNEL = os.environ.get("DLGRAD_TC_KERNEL", "v2")     # v2 = persistent, v1 = one tile per CTA
+SPLIT_WARPS = int(os.environ.get("DLGRAD_TC_SPLIT_WARPS", "4"))
+KERNEL = os.environ.get("DLGRAD_TC_KERNEL", "auto")   # auto | v3 = CTA pair | v2 = persistent 1-CTA | v1 = one tile per CTA
 
 
 def _tmap(d: dict):
@@ -57,21 +58,34 @@ def qualifies(M, N, K, batch, a_bs, b_bs, tx, ty, aligned, force: bool = False) 
 
 
 def try_build(M, N, K, batch, a_bs, b_bs, tx, ty, aligned, passes: int | None = None, bn: int | None = None,
-              stages: int | None = None, hi_inplace: bool = False, force: bool = False, kernel: str | None = None):
+              stages: int | None = None, hi_inplace: bool = False, force: bool = False, kernel: str | None = None,
+              split_warps: int | None = None):
     q = qualifies(M, N, K, batch, a_bs, b_bs, tx, ty, aligned, force)
     if q is None:
         return None
     a_mn, b_mn, a_bc, b_bc, nb = q
     passes = passes or PASSES
-    if (kernel or KERNEL) == "v1":
+    cluster = 1
+    b_rows = None
+    which = kernel or KERNEL
+    if which == "auto":
+        # CTA pairs (256 x 256 tiles on 74 pairs) win when there are enough pair tiles to balance: measured
+        # 228 vs 210 TFLOP/s at 4096^3 and 228 vs 205 at 8192x3072x768, but 161 vs 174 at 8192x768x768
+        pair_tiles = -(-M // 256) * -(-N // 256) * nb
+        which = "v3" if (passes == 3 and M >= 512 and N >= 1024 and pair_tiles >= 148 and K >= 256) else "v2"
+    if which == "v3" and passes == 3 and M > 128 and (bn or 256) % 64 == 0:
+        k = tc.matmul_tc_pair(M, N, K, nb, a_mn, b_mn, a_bc, b_bc, bn, stages)
+        cluster, b_rows = 2, k.bn // 2
+    elif which == "v1":
         k = tc.matmul_tc(M, N, K, nb, a_mn, b_mn, a_bc, b_bc, passes, bn, stages, hi_inplace)
     else:
-        k = tc.matmul_tc_persistent(M, N, K, nb, a_mn, b_mn, a_bc, b_bc, passes, bn, stages)
+        k = tc.matmul_tc_persistent(M, N, K, nb, a_mn, b_mn, a_bc, b_bc, passes, bn, stages, None,
+                                    split_warps or SPLIT_WARPS)
     shim.init()
     fn = compiler.get_function(k.name, k.source)
-    da, db, dc = tc.tmap_descs(M, N, K, nb, a_mn, b_mn, a_bc, b_bc, k.bn)
+    da, db, dc = tc.tmap_descs(M, N, K, nb, a_mn, b_mn, a_bc, b_bc, k.bn, b_rows)
     ta, tb, tcd = _tmap(da), _tmap(db), _tmap(dc)
-    plan = lib.dlg_mm_plan_create(fn, k.grid[0], k.grid[1], k.grid[2], k.threads, k.smem, 1, k.out_elems * 4,
+    plan = lib.dlg_mm_plan_create(fn, k.grid[0], k.grid[1], k.grid[2], k.threads, k.smem, cluster, k.out_elems * 4,
                                   ta, tb, tcd)
     if plan == NULL:
         raise RuntimeError("dlg_mm_plan_create failed: " + shim.last_error())

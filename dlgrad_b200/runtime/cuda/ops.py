@@ -437,32 +437,20 @@ def _build_reduce(op: str, shape: tuple, dim: int, aligned: bool) -> list[Plan]:
             G = k1.out_elems
             return [Plan(k1), Plan(ck.reduce_rows(op, 1, G, True, scale_R=R))]
         return [Plan(ck.reduce_rows(op, outer, R, aligned))]
-    if aligned and inner % 4 == 0 and inner >= 128:
-        # wide contiguous axis: row-slab kernel (consecutive rows, long contiguous runs per CTA)
-        ncolv = inner // 4
-        nspans = -(-ncolv // (256 * builtins_min(4, -(-ncolv // 256))))
-        ctas = nspans * outer
-        slabs = 1
-        if ctas < 2 * ck.NUM_SMS and R >= 16:
-            slabs = builtins_max(1, builtins_min(R // 8, -(-2 * ck.NUM_SMS // ctas)))
-        if slabs == 1:
-            return [Plan(ck.reduce_cols_slab(op, outer, R, inner, 1, True))]
-        # second pass over the (L2-resident) slab partials: 128-column strips, 8 warps interleaving rows
-        return [Plan(ck.reduce_cols_slab(first, outer, R, inner, slabs, False)),
-                Plan(ck.reduce_cols(op, 1, slabs, outer * inner, True, 1, scale_R=R))]
-    # narrow / unaligned: column strips; R split across a thread-block cluster when the grid is small
+    # strided axis: 128-column strips (each warp reads full 512-byte row segments), 8 warps interleave the
+    # rows of a strip.  When outer x strips cannot occupy the chip, R is cut into `splits` row ranges until
+    # ~148 x 8 CTAs exist, and a second, tiny pass adds the partials in split order.  Measured on 4096^2
+    # (scripts/reduce_probe.py): 32 splits + second pass 13.4 us (5.0 TB/s); a thread-block cluster of 8
+    # combining through DSMEM in one launch 22 us; row slabs 25 us.
     V = 4 if (aligned and inner % 4 == 0) else 1
     blocks = -(-(inner // V) // 32) * outer
     splits = 1
-    if blocks < 2 * ck.NUM_SMS and R >= 128:
-        splits = builtins_max(1, builtins_min(R // 64, -(-2 * ck.NUM_SMS // blocks)))
+    if blocks < 4 * ck.NUM_SMS and R >= 64:
+        splits = builtins_max(1, builtins_min(R // 16, -(-8 * ck.NUM_SMS // blocks), 64))
     if splits == 1:
         return [Plan(ck.reduce_cols(op, outer, R, inner, aligned))]
-    if splits <= 8 or R // 8 >= 256:
-        # one launch: the R-slices of a column tile form a thread-block cluster and combine through DSMEM
-        return [Plan(ck.reduce_cols(op, outer, R, inner, aligned, builtins_min(splits, 8), None, True))]
     return [Plan(ck.reduce_cols(first, outer, R, inner, aligned, splits)),
-            Plan(ck.reduce_cols(op, 1, splits, outer * inner, True, 1, scale_R=R))]
+            Plan(ck.reduce_cols(op, 1, splits, outer * inner, aligned and (outer * inner) % 4 == 0, 1, scale_R=R))]
 
 
 @dispatcher.register(UnaryOps.SUM, CUDA)

@@ -16,7 +16,7 @@ results = {}
 
 
 def run(M, N, K, nb=1, tx=False, ty=False, a_b=False, b_b=False, passes=3, bn=None, stages=None, hi_inplace=False,
-        a=None, b=None, time_it=0, kernel=None):
+        a=None, b=None, time_it=0, kernel=None, split_warps=None):
     batch = (1, nb)
     if a is None:
         a = (rng.random(((1 if a_b else nb), K, M) if tx else ((1 if a_b else nb), M, K), dtype=np.float32) - 0.5).astype(np.float32)
@@ -25,7 +25,7 @@ def run(M, N, K, nb=1, tx=False, ty=False, a_b=False, b_b=False, passes=3, bn=No
     a_bs = (0, 0) if (a_b or nb == 1) else (0, M * K)
     b_bs = (0, 0) if (b_b or nb == 1) else (0, K * N)
     plan = matmul_tc.try_build(M, N, K, batch, a_bs, b_bs, tx, ty, True, passes=passes, bn=bn, stages=stages,
-                               hi_inplace=hi_inplace, force=True, kernel=kernel)
+                               hi_inplace=hi_inplace, force=True, kernel=kernel, split_warps=split_warps)
     assert plan is not None, "shape did not qualify"
     da, db = transfer.upload_numpy(a), transfer.upload_numpy(b)
     out = plan(da, db)
@@ -99,19 +99,26 @@ if which in ("all", "p3"):
          a=np.random.default_rng(5).random((1, 8192, 768), dtype=np.float32), b=np.random.default_rng(6).random((1, 8192, 3072), dtype=np.float32))
     case("p3 NN 512x512x16384 accuracy U[0,1)", M=512, N=512, K=16384,
          a=np.random.default_rng(5).random((1, 512, 16384), dtype=np.float32), b=np.random.default_rng(6).random((1, 16384, 512), dtype=np.float32))
+if which in ("all", "v3"):
+    case("v3 NN 256x256x128", M=256, N=256, K=128, kernel="v3")
+    case("v3 NT 256x256x128", M=256, N=256, K=128, ty=True, kernel="v3")
+    case("v3 TN 256x256x128", M=256, N=256, K=128, tx=True, kernel="v3")
+    case("v3 NN 1000x1000x1000", M=1000, N=1000, K=1000, kernel="v3")
+    case("v3 NN 333x200x44 ragged", M=333, N=200, K=44, kernel="v3")
+    case("v3 NN batched 8x1024x96x768 bB bn128", M=1024, N=96, K=768, nb=8, b_b=True, kernel="v3", bn=128)
+    case("v3 NN 4096^3 accuracy U[0,1)", M=4096, N=4096, K=4096, kernel="v3",
+         a=np.random.default_rng(5).random((1, 4096, 4096), dtype=np.float32), b=np.random.default_rng(6).random((1, 4096, 4096), dtype=np.float32))
 if which in ("all", "perf"):
     shapes = {"4096^3": dict(M=4096, N=4096, K=4096), "8192x768x768": dict(M=8192, N=768, K=768),
+              "NT 8192x768x768": dict(M=8192, N=768, K=768, ty=True),
               "8192x3072x768": dict(M=8192, N=3072, K=768), "8192x768x3072": dict(M=8192, N=768, K=3072),
               "TN 768x3072x8192": dict(M=768, N=3072, K=8192, tx=True), "TN 768x768x8192": dict(M=768, N=768, K=8192, tx=True),
-              "NT 8192x768x3072": dict(M=8192, N=768, K=3072, ty=True),
-              "b96 QK^T 1024x1024x64": dict(M=1024, N=1024, K=64, nb=96), "b96 AV 1024x64x1024": dict(M=1024, N=64, K=1024, nb=96),
-              "b96 dV TN 1024x64x1024": dict(M=1024, N=64, K=1024, nb=96, tx=True),
-              "b96 dAtt NT 1024x1024x64": dict(M=1024, N=1024, K=64, nb=96, ty=True)}
+              "b96 QK^T 1024x1024x64": dict(M=1024, N=1024, K=64, nb=96)}
     for name, kw in shapes.items():
-        case(f"perf auto {name}", time_it=10, **kw)
-        for bn in (64, 128, 192, 256):
+        case(f"perf v2 auto {name}", time_it=10, **kw)
+        for bn in (128, 256):
             if bn <= kw["N"]:
-                case(f"perf bn{bn} {name}", time_it=10, bn=bn, **kw)
+                case(f"perf v3 bn{bn} {name}", time_it=10, bn=bn, kernel="v3", **kw)
 os.makedirs("gpurun_out", exist_ok=True)
 with open(f"gpurun_out/tc_probe_{which}.json", "w") as f:
     json.dump(results, f, indent=1)
