@@ -51,6 +51,16 @@ def load_peaks() -> dict:
         return {"hbm_gbs": 6650.0, "bf16_burst": 1590.0, "bf16_sustained": 1400.0, "source": "fallback"}
 
 
+def load_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant matmul shape, from the committed
+    `ncu --set full` capture (profiles/r01_ncu_mm_traffic.json); null when no capture is committed."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_ncu_mm_traffic.json")) as f:
+            return json.load(f)
+    except (OSError, ValueError):
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
 
@@ -162,7 +172,8 @@ def workload_config(cfg_kw: dict, batch: int, gpus: int) -> dict:
                         f"n_embd={cfg_kw['n_embd']} n_head={cfg_kw['n_head']} block_size={cfg_kw['block_size']} "
                         f"vocab={cfg_kw['vocab_size']}, Adam lr 1e-4",
             "per_gpu_batch": batch, "global_batch": batch * gpus, "seq_len": cfg_kw["block_size"],
-            "parallelism": f"dp{gpus}", "l2": "working set per step >> 126 MB L2; no explicit flush"}
+            "parallelism": f"dp{gpus}", "l2": "working set per step >> 126 MB L2; no explicit flush",
+            "arithmetic": "fp32 everywhere; matmul = 3xTF32 on tcgen05 tensor cores (hi/lo split, fp32 accumulate)"}
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -351,11 +362,14 @@ def run_b200(args) -> None:
     ms_b = e1.ms_since(e0)
     io = transfer.counters()
 
-    if dist is not None:      # max over ranks
+    if dist is not None:      # max over ranks; launches summed over ranks
         import torch
         t = torch.tensor([ms_a, ms_b], dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_a, ms_b = float(t[0]), float(t[1])
+        n = torch.tensor([launches], dtype=torch.int64)
+        dist.all_reduce(n, op=dist.ReduceOp.SUM)
+        launches = int(n[0])
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -369,7 +383,7 @@ def run_b200(args) -> None:
     line = {
         "metric": "gpt_train_steps_per_s", "value": value, "unit": "steps/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_a / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32 (3xTF32 tensor-core matmul, fp32 elsewhere)", "data": "synthetic",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(cfg_kw, args.batch, world),
         "tokens_per_s": value * args.batch * cfg.block_size,
         "model_tflops": value * flops_step / 1e12,
@@ -380,7 +394,7 @@ def run_b200(args) -> None:
                 "d2h_bytes_per_step": io["d2h_bytes"] // args.steps},
         "roofline": {"bound": "tensor", "kernel": "matmul (all launches of the timed steps, CUDA events per launch)",
                      "achieved": mm_tflops, "peak": peak_3xtf32, "unit": "TFLOP/s",
-                     "frac": mm_tflops / peak_3xtf32 if peak_3xtf32 else None, "traffic": None,
+                     "frac": mm_tflops / peak_3xtf32 if peak_3xtf32 else None, "traffic": load_traffic(),
                      "peak_note": f"3xTF32 = sustained bf16 {peaks['bf16_sustained']} TF/s / 6 ({peaks['source']}: "
                                   "MEASURED_PEAKS.json has no TF32 entry; TF32 dense = bf16/2, 3 MMAs per product)",
                      "matmul_share_of_step": mm["ms"] / ms_a if ms_a else None, "matmul_launches": mm["launches"],
