@@ -871,7 +871,8 @@ def softmax_rows(kind: str, outer: int, R: int, aligned: bool = True, chain: tup
     def each(fmt):
         return " ".join(fmt.format(c=("." + c) if c else "") for c in comps)
     if kind == "softmax":
-        final = each("v[i]{c} = v[i]{c} / s;")
+        # e * (1/s): one reciprocal per row instead of a division per element (<= 1 ulp from e / s)
+        final = each("v[i]{c} = v[i]{c} * inv_s;")
     else:
         final = each("v[i]{c} = (xs[i]{c}) - ls;")
     keep_shift = kind != "softmax"
@@ -902,7 +903,7 @@ extern "C" __global__ void __launch_bounds__({BLOCK}) {KNAME}{SIG} {{
         }}
     }}
     {_row_reduce_code(T, "s", "{a} + {b}", "0.f", "s")}
-    {"const float ls = logf(s);" if keep_shift else ""}
+    {"const float ls = logf(s);" if keep_shift else "const float inv_s = 1.f / s;"}
     if (!live) return;
     {VT}* orow = reinterpret_cast<{VT}*>(out + (size_t)r * {R}u);
     #pragma unroll
