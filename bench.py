@@ -125,7 +125,21 @@ def cpu_block_sample(cfg_kw: dict, repeats: int = 1) -> tuple[float, str]:
         y.sum().backward()
         best = min(best, time.perf_counter() - t0)
     return best, (f"1 of {cfg.n_layer} transformer blocks x 1 sequence (T={cfg.block_size}, C={cfg.n_embd}), "
-                  f"forward+backward on the CPU oracle, single thread")
+                  f"forward+backward on {cpu_kind_text()}, single thread")
+
+
+def cpu_kind() -> str:
+    """'reference' when every kernel of the CPU sample was the reference's own generated C (oracle/_ref,
+    compiled from /root/reference/dlgrad/codegen/cpu_kernel.py with the reference's flags), 'port' when the
+    restatement in oracle/kernels.c served any of them."""
+    from oracle import backend
+    o = backend.kernel_origin
+    return "reference" if (o["reference"] > 0 and o["port"] == 0) else "port"
+
+
+def cpu_kind_text() -> str:
+    return ("the reference's own generated C kernels (oracle/_ref) under this package's autograd layer"
+            if cpu_kind() == "reference" else "the CPU oracle (oracle/kernels.c restatement)")
 
 
 def cpu_equiv_steps_per_s(block_seconds: float, cfg_kw: dict, batch: int) -> float:
@@ -159,7 +173,7 @@ def run_reference(args) -> None:
         "n_gpus": args.gpus, "steps": len(times), "warmup": args.warmup, "ms_per_step": 1000.0 / value,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(cfg_kw, args.batch, args.gpus),
-        "cpu_baseline": {"value": value, "unit": "steps/s", "cores": 1, "kind": "port", "sample": sample
+        "cpu_baseline": {"value": value, "unit": "steps/s", "cores": 1, "kind": cpu_kind(), "sample": sample
                          + f"; {len(times)} samples, mean {np.mean(times):.2f} s, scaled by L x B x FLOP share"},
         "e2e": {"value": value, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "host": {"cpu_count": os.cpu_count()},
@@ -405,7 +419,7 @@ def run_b200(args) -> None:
     if world == 1 and not args.no_cpu:
         t, sample = cpu_block_sample(cfg_kw)
         v = cpu_equiv_steps_per_s(t, cfg_kw, args.batch)
-        line["cpu_baseline"] = {"value": v, "unit": "steps/s", "cores": 1, "kind": "port",
+        line["cpu_baseline"] = {"value": v, "unit": "steps/s", "cores": 1, "kind": cpu_kind(),
                                 "sample": sample + f" ({t:.2f} s), scaled by L x B x FLOP share; host has {os.cpu_count()} cores, "
                                 "the reference is single-threaded"}
     if world == 1 and not args.no_ops:

@@ -12,6 +12,7 @@ Each function mirrors the argument handling of its counterpart in dlgrad/runtime
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -43,6 +44,35 @@ def lib():
     if _lib is None:
         _lib = C.CDLL(build.build_oracle())
     return _lib
+
+
+# ---- the reference's OWN generated kernels (oracle/_ref/*.so, built by oracle/build.py from
+# /root/reference/dlgrad/codegen/cpu_kernel.py) are used in place of the restatement when they are present and
+# USE_REF is on; per op the call below mirrors the argument packing of dlgrad/runtime/cpu.py.  `kernel_origin`
+# records which implementation actually served each op (bench.py reports cpu_baseline.kind from it).
+USE_REF = os.environ.get("DLGRAD_ORACLE_REF", "1") != "0"
+_ref_libs: dict = {}
+kernel_origin = {"reference": 0, "port": 0}
+
+
+def _ref(stem: str):
+    if not USE_REF:
+        return None
+    lib_ = _ref_libs.get(stem, False)
+    if lib_ is False:
+        path = os.path.join(build.REF_DIR, f"{stem}.so")
+        lib_ = C.CDLL(path) if os.path.exists(path) else None
+        _ref_libs[stem] = lib_
+    return lib_
+
+
+def _ints(vals) -> "C.Array":
+    vals = [int(v) for v in vals]
+    return (C.c_int * max(1, len(vals)))(*vals)
+
+
+def _count(which: str) -> None:
+    kernel_origin[which] += 1
 
 
 def _np(b: Buffer) -> np.ndarray:
@@ -82,6 +112,16 @@ def _binary(name: str, x: Buffer, y: Buffer, out_shape=None):
     sx = get_broadcast_strides_2(oshape, xs, calculate_stride(xs))
     sy = get_broadcast_strides_2(oshape, ys, calculate_stride(ys))
     xa, ya = _np(x), _np(y)
+    nd = len(oshape)
+    r = _ref(f"{name}_{nd}d") if (name != "lte" and 1 <= nd <= 4) else (_ref("cmp") if (name == "lte" and nd == 2) else None)
+    if r is not None:
+        _count("reference")
+        if name == "lte":      # cmp_2d, cpu.py:835-862
+            r.cmp(_f(xa), _f(ya), _f(out), _ints(oshape), _ints(sx), _ints(sy), _ints(calculate_stride(oshape)))
+        else:                  # arithmetic(op, ndim), cpu.py:257-291
+            getattr(r, f"{name}_{nd}d")(_f(xa), _f(ya), _f(out), _ints(oshape), _ints(sx), _ints(sy))
+        return _ret(out)
+    _count("port")
     getattr(lib(), f"orc_{name}")(_f(xa), _f(ya), _f(out), _i4(oshape), _s4(sx), _s4(sy))
     return _ret(out)
 
@@ -102,6 +142,22 @@ def _reg_binary():
 def _unary(name: str, x: Buffer, *extra):
     xa = _np(x)
     out = np.empty(xa.size, dtype=np.float32)
+    if name == "clamp":
+        has_min, lo, has_max, hi = (e.value for e in extra)
+        r = _ref(f"clamp_{int(bool(has_min))}{int(bool(has_max))}")
+        if r is not None:      # clamp(has_min, has_max), cpu.py:431-462
+            _count("reference")
+            fn = getattr(r, f"clamp_{'min' if has_min else ''}_{'max' if has_max else ''}")
+            args = [C.c_float(lo)] * bool(has_min) + [C.c_float(hi)] * bool(has_max)
+            fn(_f(xa), _f(out), C.c_int(xa.size), *args)
+            return _ret(out)
+    else:
+        r = _ref("relu") if name == "relu" else _ref(f"c_{name}")
+        if r is not None:      # utils(func) / relu, cpu.py:314-502,764
+            _count("reference")
+            getattr(r, "relu" if name == "relu" else f"c_{name}")(_f(xa), _f(out), C.c_int(xa.size), *extra)
+            return _ret(out)
+    _count("port")
     getattr(lib(), f"orc_{name}")(_f(xa), _f(out), C.c_int(xa.size), *extra)
     return _ret(out)
 
@@ -123,6 +179,14 @@ def _where(cond: Buffer, x: Buffer, y: Buffer):
     out = np.empty(prod_(oshape), dtype=np.float32)
     st = [get_broadcast_strides_2(oshape, b.metadata.shape, calculate_stride(b.metadata.shape)) for b in (cond, x, y)]
     ca, xa, ya = _np(cond), _np(x), _np(y)
+    nd = len(oshape)
+    r = _ref(f"where_{nd}d") if 1 <= nd <= 4 else None
+    if r is not None:          # where(ndim), cpu.py:865-903
+        _count("reference")
+        getattr(r, f"where_{nd}d")(_f(ca), _f(xa), _f(ya), _f(out), _ints(oshape), _ints(st[0]), _ints(st[1]),
+                                  _ints(st[2]), _ints(calculate_stride(oshape)))
+        return _ret(out)
+    _count("port")
     lib().orc_where(_f(ca), _f(xa), _f(ya), _f(out), _i4(oshape), _s4(st[0]), _s4(st[1]), _s4(st[2]))
     return _ret(out)
 
@@ -133,6 +197,14 @@ def _masked_fill(x: Buffer, mask: Buffer, val: float, out_shape: tuple):
     sx = get_broadcast_strides_2(oshape, x.metadata.shape, calculate_stride(x.metadata.shape))
     sm = get_broadcast_strides_2(oshape, mask.metadata.shape, calculate_stride(mask.metadata.shape))
     xa, ma = _np(x), _np(mask)
+    nd = len(oshape)
+    r = _ref(f"masked_fill_{nd}d") if 2 <= nd <= 4 else None
+    if r is not None:          # masked_fill(ndim), cpu.py:794-831
+        _count("reference")
+        getattr(r, f"masked_fill_{nd}d")(_f(xa), _f(ma), _f(out), _ints(oshape), _ints(sx), _ints(sm),
+                                        _ints(calculate_stride(oshape)), C.c_float(val))
+        return _ret(out)
+    _count("port")
     lib().orc_masked_fill(_f(xa), _f(ma), _f(out), _i4(oshape), _s4(sx), _s4(sm), C.c_float(val))
     return _ret(out)
 
@@ -143,12 +215,27 @@ def _reduce(name: str, x: Buffer, dim):
     shape = x.metadata.shape
     if dim is None or dim == -1:
         out = np.empty(1, dtype=np.float32)
+        r = _ref(f"reduce_{name}")
+        if r is not None:      # reduce(op), cpu.py:612-630
+            _count("reference")
+            getattr(r, f"reduce_{name}")(_f(xa), _f(out), C.c_int(xa.size))
+            return _ret(out)
+        _count("port")
         getattr(lib(), f"orc_reduce_all_{name}")(_f(xa), _f(out), C.c_int(xa.size))
         return _ret(out)
     if dim < 0:
         dim += len(shape)
     outer, R, inner = prod_(shape[:dim]), shape[dim], prod_(shape[dim + 1:])
     out = np.empty(outer * inner, dtype=np.float32)
+    nd = len(shape)
+    r = _ref(f"reduce_{name}_{nd}d_axis{dim}") if 1 <= nd <= 4 else None
+    if r is not None:          # reduce_source(op, ndim, dim), cpu.py:632-658
+        _count("reference")
+        oshape = [s_ for i, s_ in enumerate(shape) if i != dim]
+        getattr(r, f"reduce_{name}_{nd}d_axis{dim}")(_f(xa), _f(out), _ints(shape), _ints(calculate_stride(shape)),
+                                                   _ints(calculate_stride(oshape)))
+        return _ret(out)
+    _count("port")
     getattr(lib(), f"orc_reduce_{name}")(_f(xa), _f(out), C.c_int(outer), C.c_int(R), C.c_int(inner))
     return _ret(out)
 
@@ -163,6 +250,14 @@ def _argmax(x: Buffer, dim):
             dim += len(shape)
         outer, R, inner = prod_(shape[:dim]), shape[dim], prod_(shape[dim + 1:])
     out = np.empty(outer * inner, dtype=np.float32)
+    r = _ref(f"argmax_2d_axis{dim}") if (dim is not None and len(shape) == 2) else None
+    if r is not None:          # argmax(ndim, dim), cpu.py:911-959
+        _count("reference")
+        oshape = [s_ for i, s_ in enumerate(shape) if i != dim]
+        getattr(r, f"argmax_2d_axis{dim}")(_f(xa), _f(out), _ints(shape), _ints(calculate_stride(shape)),
+                                         _ints(calculate_stride(oshape)))
+        return _ret(out)
+    _count("port")
     lib().orc_argmax(_f(xa), _f(out), C.c_int(outer), C.c_int(R), C.c_int(inner))
     return _ret(out)
 
@@ -175,6 +270,13 @@ def _permute(x: Buffer, order: tuple):
     pstr = tuple(in_str[i] for i in order)
     xa = _np(x)
     out = np.empty(xa.size, dtype=np.float32)
+    nd = len(shape)
+    r = _ref(f"permute_{nd}d") if 2 <= nd <= 4 else None
+    if r is not None:          # permute(ndim), cpu.py:334-368
+        _count("reference")
+        getattr(r, f"permute_{nd}d")(_f(xa), _f(out), _ints(oshape), _ints(pstr), _ints(calculate_stride(oshape)))
+        return _ret(out)
+    _count("port")
     lib().orc_permute(_f(xa), _f(out), _i4(oshape), _s4(pstr))
     return _ret(out)
 
@@ -195,6 +297,20 @@ def _matmul(x: Buffer, y: Buffer, trans_x: bool = False, trans_y: bool = False):
     yb1 = 0 if (by[1] == 1 and B1 > 1) else sy[1]
     xa, ya = _np(x), _np(y)
     out = np.zeros(B0 * B1 * M * N, dtype=np.float32)
+    nd = len(xs)
+    r = _ref(f"matmul_{nd}d") if nd in (2, 3, 4) else None
+    if r is not None:          # matmul_{2,3,4}d with the batch strides of a broadcast operand zeroed, cpu.py:505-602
+        _count("reference")
+        if nd == 2:
+            r.matmul_2d(_f(xa), _f(ya), _f(out), _ints(xs), _ints(calculate_stride(xs)), _ints(ys), _ints(calculate_stride(ys)))
+        elif nd == 3:
+            r.matmul_3d(_f(xa), _f(ya), _f(out), C.c_int(B1), C.c_int(M), C.c_int(K), C.c_int(N),
+                        _ints((xb1, K, 1)), _ints((yb1, N, 1)), _ints((M * N, N, 1)))
+        else:
+            r.matmul_4d(_f(xa), _f(ya), _f(out), _ints((B0, B1, M, K, N)), _ints((xb0, xb1, K, 1)),
+                        _ints((yb0, yb1, N, 1)), _ints((B1 * M * N, M * N, N, 1)))
+        return _ret(out)
+    _count("port")
     lib().orc_matmul(_f(xa), _f(ya), _f(out), *(C.c_int(v) for v in (B0, B1, M, K, N, xb0, xb1, yb0, yb1)))
     return _ret(out)
 
@@ -204,12 +320,24 @@ def _ce_forward(x: Buffer, y: Buffer):
     xa, ta = _np(x), _np(y)
     n = x.metadata.shape[0]
     out = np.empty(n, dtype=np.float32)
+    r = _ref("ce_forward")
+    if r is not None:
+        _count("reference")
+        r.ce_forward(_f(xa), _f(ta), _f(out), C.c_int(n), _ints(x.metadata.stride))
+        return _ret(out)
+    _count("port")
     lib().orc_ce_forward(_f(xa), _f(ta), _f(out), C.c_int(n), C.c_int(x.metadata.stride[0]))
     return _ret(out)
 
 
 def _ce_backward(x: Buffer, target: Buffer):
     xa, ta = _np(x), _np(target)
+    r = _ref("ce_backward")
+    if r is not None:
+        _count("reference")
+        r.ce_backward(_f(xa), _f(ta), _ints(x.metadata.shape), _ints(x.metadata.stride))
+        return
+    _count("port")
     lib().orc_ce_backward(_f(xa), _f(ta), C.c_int(x.metadata.shape[0]), C.c_int(x.metadata.stride[0]))
 
 
@@ -219,10 +347,22 @@ def _embedding(x: Buffer, idx: Buffer, out_numel: int, backward: bool = False, u
     if backward:
         out = np.zeros(out_numel, dtype=np.float32)
         ga = _np(upstream_grad)
+        r = _ref("embedding_backward")
+        if r is not None:
+            _count("reference")
+            r.embedding_backward(_f(out), _f(ga), _f(ia), C.c_int(ia.size), C.c_int(width))
+            return _ret(out)
+        _count("port")
         lib().orc_embedding_backward(_f(out), _f(ga), _f(ia), C.c_int(ia.size), C.c_int(width))
         return _ret(out)
     xa = _np(x)
     out = np.empty(out_numel, dtype=np.float32)
+    r = _ref("embedding")
+    if r is not None:
+        _count("reference")
+        r.embedding(_f(xa), _f(ia), _f(out), C.c_int(ia.size), C.c_int(width))
+        return _ret(out)
+    _count("port")
     lib().orc_embedding(_f(xa), _f(ia), _f(out), C.c_int(ia.size), C.c_int(width))
     return _ret(out)
 
@@ -230,12 +370,24 @@ def _embedding(x: Buffer, idx: Buffer, out_numel: int, backward: bool = False, u
 # ---- creation: cpu.py:194-254 ----------------------------------------------------------------------
 def _full(shape: tuple, fill_value: float):
     out = np.empty(prod_(shape), dtype=np.float32)
-    lib().orc_full(_f(out), C.c_int(out.size), C.c_int(int(fill_value)))      # int(): cpu.py:252
+    r = _ref("full")
+    if r is not None:
+        _count("reference")
+        r.full(_f(out), C.c_int(out.size), C.c_int(int(fill_value)))            # int(): cpu.py:252
+        return _ret(out)
+    _count("port")
+    lib().orc_full(_f(out), C.c_int(out.size), C.c_int(int(fill_value)))
     return _ret(out)
 
 
 def _arange(shape: tuple):
     out = np.empty(prod_(shape), dtype=np.float32)
+    r = _ref("arange")
+    if r is not None:
+        _count("reference")
+        r.arange(_f(out), C.c_int(out.size))
+        return _ret(out)
+    _count("port")
     lib().orc_arange(_f(out), C.c_int(out.size))
     return _ret(out)
 

@@ -71,7 +71,8 @@ _REF_KERNELS = (
     + [("matmul_2d", "matmul_2d", ()), ("matmul_3d", "matmul_3d", ()), ("matmul_4d", "matmul_4d", ()),
        ("ce_forward", "ce_forward", ()), ("ce_backward", "ce_backward", ()),
        ("embedding", "embedding", ()), ("embedding_backward", "embedding_backward", ()),
-       ("cmp", "cmp_2d", ("<=",)), ("full", "full", ()), ("arange", "arange", ())]
+       ("cmp", "cmp_2d", ("<=",)), ("full", "full", ()), ("arange", "arange", ()), ("relu", "relu", ())]
+    + [(f"clamp_{int(a)}{int(b)}", "clamp", (a, b)) for a in (False, True) for b in (False, True)]
 )
 
 

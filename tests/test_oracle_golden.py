@@ -16,6 +16,20 @@ from tests.conftest import check
 
 _CASES = cases.op_cases(np.random.default_rng(1234))
 
+
+@pytest.fixture(params=["restatement", "reference-kernels"])
+def oracle_kernels(request, oracle):
+    """Every test below runs twice: on the C restatement (oracle/kernels.c) and — where oracle/_ref exists
+    — on the reference's own generated kernels driven by the same argument packing."""
+    import os
+    from oracle import build
+    if request.param == "reference-kernels" and not (os.path.isdir(build.REF_DIR) and os.listdir(build.REF_DIR)):
+        pytest.skip("oracle/_ref not built")
+    prev = oracle.USE_REF
+    oracle.USE_REF = request.param == "reference-kernels"
+    yield oracle
+    oracle.USE_REF = prev
+
 # sums/means taken in a different vector order by gcc for the generic-rank loop nest; fp32 ulp-level
 SUM_TOL = 2e-6
 # softmax backward through the reference chain cancels (g*e/s - e*sum(g*e/s^2)): last-bit differences in the
@@ -24,7 +38,7 @@ SOFTMAX_GRAD_TOL = 5e-5
 
 
 @pytest.mark.parametrize("name", sorted(_CASES))
-def test_op_case_matches_reference(name, oracle, golden_ops):
+def test_op_case_matches_reference(name, oracle_kernels, golden_ops):
     fn, inputs, diff = _CASES[name]
     for i, a in enumerate(inputs):       # the generator is deterministic: inputs must be the stored ones
         assert np.array_equal(a, golden_ops[f"{name}/in{i}"])
@@ -46,7 +60,7 @@ def test_op_case_matches_reference(name, oracle, golden_ops):
                 runner.rel_check(check, v, g, tol, f"{name} {k}")
 
 
-def test_integer_and_index_ops_bit_exact(oracle, golden_ops):
+def test_integer_and_index_ops_bit_exact(oracle_kernels, golden_ops):
     from dlgrad_b200 import Tensor
     g = golden_ops
     a = g["argmax_d0/in0"]
@@ -66,7 +80,7 @@ def test_integer_and_index_ops_bit_exact(oracle, golden_ops):
     check(Tensor.full((3, 4), 2.9).numpy(), g["full_2p9/out"], exact=True, what="full(2.9) int truncation")
 
 
-def test_embedding_gather_and_ordered_scatter_add_bit_exact(oracle, golden_ops):
+def test_embedding_gather_and_ordered_scatter_add_bit_exact(oracle_kernels, golden_ops):
     from dlgrad_b200 import Tensor
     g = golden_ops
     wt = Tensor(g["embedding/W"].copy(), requires_grad=True)
@@ -76,7 +90,7 @@ def test_embedding_gather_and_ordered_scatter_add_bit_exact(oracle, golden_ops):
     check(wt.grad.numpy(), g["embedding/grad"], exact=True, what="embedding scatter-add")
 
 
-def test_losses_and_rmsnorm(oracle, golden_ops):
+def test_losses_and_rmsnorm(oracle_kernels, golden_ops):
     from dlgrad_b200 import Tensor, nn
     g = golden_ops
     lt = Tensor(g["ce/logits"].copy(), requires_grad=True)
@@ -98,7 +112,7 @@ def test_losses_and_rmsnorm(oracle, golden_ops):
     runner.rel_check(check, norm.weight.grad.numpy(), g["rmsnorm/grad_w"], SUM_TOL, "rmsnorm grad_w")
 
 
-def test_models_match_reference_loss_curves(oracle, golden_models):
+def test_models_match_reference_loss_curves(oracle_kernels, golden_models):
     """MLP (3 SGD steps), narrow GAN (one D + one G Adam step) and reduced char-GPT (3 Adam steps):
     the oracle-backed stack reproduces the reference's losses, gradients and updated weights."""
     import dlgrad_b200 as dl
