@@ -1109,3 +1109,53 @@ extern "C" __global__ void __launch_bounds__({BLOCK}) {KNAME}{SIG} {{
 }}
 """
     return Kernel("rmsnorm_rows", src, (_cdiv(outer, rpb), 1, 1), (BLOCK, 1, 1), 0, outer * C)
+
+
+@cache
+def adam_multi(sizes: tuple, beta1: float, beta2: float, eps: float) -> Kernel:
+    """The Adam update of EVERY parameter tensor in one launch (multi-tensor apply).  p0 is a device table of
+    4 addresses per tensor (param, grad, m, v); the block -> tensor map is a literal prefix array, found by
+    binary search.  Same per-element arithmetic as adam_step.  All tensors must be 16-byte aligned with
+    numel % 4 == 0 (the caller falls back to per-tensor launches otherwise).  100 launches -> 1 for the
+    benchmark GPT (85.9 M parameters in 100 tensors)."""
+    CH = 1024                                       # float4 per block
+    starts, acc = [0], 0
+    for n in sizes:
+        acc += _cdiv(n // 4, CH)
+        starts.append(acc)
+    b1, b2, e_ = _flit(beta1), _flit(beta2), _flit(eps)
+    omb1, omb2 = _flit(1.0 - beta1), _flit(1.0 - beta2)
+    body = []
+    for c in "xyzw":
+        body.append(f"""
+            {{ const float gg = __fmul_rn(g.{c}, f3);
+              const float mn = __fadd_rn(__fmul_rn(m.{c}, {b1}), __fmul_rn(gg, {omb1}));
+              const float vn = __fadd_rn(__fmul_rn(v.{c}, {b2}), __fmul_rn(__fmul_rn(gg, gg), {omb2}));
+              const float mh = __fdiv_rn(mn, f0), vh = __fdiv_rn(vn, f1);
+              p.{c} = __fsub_rn(p.{c}, __fmul_rn(__fdiv_rn(mh, __fadd_rn(__fsqrt_rn(vh), {e_})), f2));
+              m.{c} = mn; v.{c} = vn; }}""")
+    src = f"""
+__device__ const unsigned blk_start[{len(starts)}] = {{{", ".join(str(s) + "u" for s in starts)}}};
+__device__ const unsigned vec_count[{len(sizes)}] = {{{", ".join(str(n // 4) + "u" for n in sizes)}}};
+extern "C" __global__ void __launch_bounds__(256) {KNAME}{SIG_ALIAS} {{
+    const unsigned long long* tab = reinterpret_cast<const unsigned long long*>(p0);
+    unsigned lo = 0, hi = {len(sizes)}u;            // tensor t with blk_start[t] <= blockIdx.x < blk_start[t+1]
+    while (hi - lo > 1u) {{ const unsigned mid = (lo + hi) >> 1; if (blk_start[mid] <= blockIdx.x) lo = mid; else hi = mid; }}
+    const unsigned t = lo, nv = vec_count[t];
+    float4* P = reinterpret_cast<float4*>(tab[4u * t]);
+    const float4* G = reinterpret_cast<const float4*>(tab[4u * t + 1u]);
+    float4* M = reinterpret_cast<float4*>(tab[4u * t + 2u]);
+    float4* V = reinterpret_cast<float4*>(tab[4u * t + 3u]);
+    const unsigned base = (blockIdx.x - blk_start[t]) * {CH}u;
+    #pragma unroll
+    for (unsigned k = 0; k < {CH // 256}u; ++k) {{
+        const unsigned i = base + k * 256u + threadIdx.x;
+        if (i < nv) {{
+            float4 p = P[i]; const float4 g = G[i]; float4 m = M[i]; float4 v = V[i];
+            {''.join(body)}
+            P[i] = p; M[i] = m; V[i] = v;
+        }}
+    }}
+}}
+"""
+    return Kernel("adam_multi", src, (acc, 1, 1), (256, 1, 1), 0, 0)

@@ -71,6 +71,7 @@ class CustomOps(Enum):
     CE_LOSS = auto()          # log-softmax + gather + (-sum) in one pass, keeps log-softmax for backward
     CE_GRAD = auto()          # (exp(logsm) - onehot) * upstream / N
     ADAM_STEP = auto()
+    ADAM_MULTI = auto()       # every parameter tensor in one launch
     SGD_STEP = auto()
     RMSNORM = auto()
     RMSNORM_BACKWARD = auto()

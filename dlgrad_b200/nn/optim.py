@@ -90,6 +90,17 @@ class Adam(Optimizer):
         lr = float(_f32(self.lr))
         self._before_inplace([t.data for t in self.m.values()] + [t.data for t in self.v.values()])
         b1, b2, eps = self.beta1, self.beta2, self.eps     # rounded to float32 inside the kernel generator
+        live = [p for p in self.params if p.grad is not None]
+        if live:
+            dev = self._device_for(*[p.data for p in live], *[p.grad.data for p in live])
+            if dispatcher.has(CustomOps.ADAM_MULTI, dev):
+                done = dispatcher.dispatch(
+                    op=CustomOps.ADAM_MULTI, device=dev, params=[p.data for p in live],
+                    grads=[p.grad.data for p in live], ms=[self.m[id(p)].data for p in live],
+                    vs=[self.v[id(p)].data for p in live], beta1=b1, beta2=b2, eps=eps, bc1=bc1, bc2=bc2, lr=lr,
+                    grad_scale=self.grad_scale)
+                if done:
+                    return
         for p in self.params:
             if p.grad is None:
                 continue

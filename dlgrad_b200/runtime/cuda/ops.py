@@ -662,6 +662,45 @@ def adam_step(param: Buffer, grad: Buffer, m: Buffer, v: Buffer, beta1: float, b
     plan.run_into(NULL, _dev_ptr(param), _dev_ptr(grad), _dev_ptr(m), _dev_ptr(v), bc1, bc2, lr, grad_scale)
 
 
+_adam_tables: dict = {}
+
+
+@dispatcher.register(CustomOps.ADAM_MULTI, CUDA)
+def adam_multi(params: list, grads: list, ms: list, vs: list, beta1: float, beta2: float, eps: float,
+               bc1: float, bc2: float, lr: float, grad_scale: float = 1.0) -> bool:
+    """One launch for all parameter tensors (codegen adam_multi).  The address table (4 pointers per tensor)
+    is staged in pinned host memory and copied asynchronously ahead of the kernel on the compute stream; two
+    staging buffers alternate so a table is never rewritten while its copy may still be in flight.  Returns
+    False (nothing done) when a tensor does not qualify for the 128-bit path."""
+    bufs = list(params) + list(grads) + list(ms) + list(vs)
+    if not all(b.aligned and b.metadata.numel % 4 == 0 for b in bufs):
+        return False
+    sizes = tuple(p.metadata.numel for p in params)
+    key = ("adam_multi", sizes, beta1, beta2, eps)
+    ent = _adam_tables.get(key)
+    if ent is None:
+        n = len(sizes)
+        plan = Plan(ck.adam_multi(sizes, beta1, beta2, eps))
+        host = [lib.dlg_host_alloc(32 * n), lib.dlg_host_alloc(32 * n)]
+        if host[0] == NULL or host[1] == NULL:
+            raise MemoryError("pinned staging allocation failed: " + shim.last_error())
+        views = [ffi.cast("unsigned long long *", h) for h in host]
+        ent = _adam_tables[key] = {"plan": plan, "host": host, "views": views, "dev": shim.alloc(32 * n), "flip": 0}
+    ent["flip"] ^= 1
+    tab = ent["views"][ent["flip"]]
+    cast = ffi.cast
+    i = 0
+    for p, g, m, v in zip(params, grads, ms, vs):
+        tab[i] = int(cast("uintptr_t", _dev_ptr(p)))
+        tab[i + 1] = int(cast("uintptr_t", _dev_ptr(g)))
+        tab[i + 2] = int(cast("uintptr_t", _dev_ptr(m)))
+        tab[i + 3] = int(cast("uintptr_t", _dev_ptr(v)))
+        i += 4
+    shim.check(lib.dlg_h2d_async(ent["dev"], ent["host"][ent["flip"]], 32 * len(sizes)), "dlg_h2d_async")
+    ent["plan"].run_into(NULL, ent["dev"], NULL, NULL, NULL, bc1, bc2, lr, grad_scale)
+    return True
+
+
 @dispatcher.register(CustomOps.SGD_STEP, CUDA)
 def sgd_step(param: Buffer, grad: Buffer, lr: float, grad_scale: float = 1.0) -> None:
     ok = param.aligned and grad.aligned

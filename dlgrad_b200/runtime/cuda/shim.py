@@ -74,7 +74,10 @@ class _CompileOnlyLib:
     def dlg_d2h(self, d, s, n): return 0
     def dlg_d2d(self, d, s, n): return 0
     def dlg_memset32(self, d, w, n): return 0
-    def dlg_host_alloc(self, n): return self._addr(n)
+    def dlg_host_alloc(self, n):
+        buf = ffi.new("char[]", int(n) or 1)        # real host memory: callers write through it
+        self._host = getattr(self, "_host", []) + [buf]
+        return ffi.cast("void *", buf)
     def dlg_host_free(self, p): return None
     def dlg_h2d_async(self, d, s, n): return 0
     def dlg_d2h_async(self, d, s, n): return 0
