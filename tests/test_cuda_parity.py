@@ -410,3 +410,63 @@ def test_dropout_semantics():
         assert abs(kept.mean() - 0.75) < 0.01
         np.testing.assert_allclose(out[kept], x[kept] / 0.75, rtol=1e-6)
         np.testing.assert_array_equal(g != 0, kept)
+
+
+def test_deferred_pointwise_chains_are_transparent(oracle):
+    """Buffer._pending (buffer.py): `x * scalar`, masked_fill and the softmax backward are deferred on CUDA and
+    folded into their consumers.  Whatever the consumer, the values must be those of eager evaluation, and a
+    deferred producer must read its source BEFORE an in-place writer (optimizer step, copy_from) changes it."""
+    from dlgrad_b200 import Tensor, nn
+    from dlgrad_b200.buffer import Buffer
+    rng = np.random.default_rng(11)
+    a = (rng.random((300, 512), dtype=np.float32) - 0.5).astype(np.float32)       # >= LAZY_MIN_NUMEL
+    mask = (rng.random((300, 512)) > 0.7).astype(np.float32)
+    A, M = Tensor(a.copy(), device="cuda"), Tensor(mask.copy(), device="cuda")
+    # 1. a chain consumed by numpy(): scale -> mask -> scale -> scale (one generated kernel)
+    t = (((A * 2.0).masked_fill(M, -3.0)) * 0.5) * 4.0
+    if not __import__("tests.conftest", fromlist=["x"]).COMPILE_ONLY:
+        assert t.data._pending is not None, "expected a deferred chain"
+    ref = np.where(mask > 0, np.float32(-3.0), a * np.float32(2.0)) * np.float32(0.5) * np.float32(4.0)
+    check(t.numpy(), ref, exact=True, what="deferred chain -> numpy")
+    # 2. an intermediate of a chain used on its own
+    p = A * 3.0
+    q = p.masked_fill(M, 0.0)
+    check((p + q).numpy(), a * np.float32(3.0) + np.where(mask > 0, np.float32(0), a * np.float32(3.0)), exact=True,
+          what="intermediate reused")
+    # 3. softmax over a NON-last axis and over the last axis with a pending producer, vs the oracle
+    Ah, Mh = Tensor(a.copy()), Tensor(mask.copy())
+    for dim in (0, 1):
+        got = (A * 0.25).masked_fill(M, float("-inf")).softmax(dim=dim).numpy()
+        exp = (Ah * 0.25).masked_fill(Mh, float("-inf")).softmax(dim=dim).numpy()
+        ok = np.isfinite(exp)
+        runner.rel_check(check, got[ok], exp[ok], runner.TOL_ELEMENTWISE, f"chained softmax dim {dim}")
+    # 4. a deferred read of a parameter must see the value from BEFORE the optimizer's in-place update
+    w = rng.random((256, 256), dtype=np.float32)
+    P = Tensor(w.copy(), requires_grad=True, device="cuda")
+    opt = nn.optim.SGD([P], lr=0.5)
+    (P * 1.0).sum().backward()
+    snapshot = P * 2.0                       # deferred, reads P
+    opt.step()                               # P <- P - 0.5 * 1
+    check(snapshot.numpy(), w * np.float32(2.0), exact=True, what="deferred read ordered before the in-place step")
+    check(P.numpy(), w - np.float32(0.5), exact=True, what="SGD step")
+    snap2 = P * 2.0
+    P.copy_from((w * 0).tobytes())
+    check(snap2.numpy(), (w - np.float32(0.5)) * np.float32(2.0), exact=True, what="deferred read ordered before copy_from")
+    _ = Buffer
+
+
+def test_split_k_weight_gradient_gemm(oracle):
+    """x^T @ g with a small output and K = batch*tokens (the Linear weight gradient) runs as split-K: K-slices
+    as a batch + an ordered sum (runtime/cuda/matmul.py).  Checked against float64 and, at a smaller K, the oracle."""
+    from dlgrad_b200 import Tensor
+    rng = np.random.default_rng(12)
+    x = (rng.random((8192, 256), dtype=np.float32) - 0.5).astype(np.float32)
+    g = (rng.random((8192, 384), dtype=np.float32) - 0.5).astype(np.float32)
+    lin_in = Tensor(x.copy(), device="cuda", requires_grad=True)
+    W = Tensor(rng.random((384, 256), dtype=np.float32), device="cuda", requires_grad=True)
+    y = lin_in.linear(W, None)
+    (y * Tensor(g.copy(), device="cuda")).sum().backward()
+    ref = g.astype(np.float64).T @ x.astype(np.float64)
+    runner.rel_check(check, W.grad.numpy(), ref, runner.TOL_MATMUL, "dW = g^T @ x, K = 8192 (split-K)")
+    runner.rel_check(check, lin_in.grad.numpy(), g.astype(np.float64) @ W.numpy().astype(np.float64), runner.TOL_MATMUL,
+                     "dX = g @ W")
