@@ -405,6 +405,9 @@ def pick_bn_persistent(M: int, N: int, batch: int, kblocks: int) -> int:
 def matmul_tc_persistent(M: int, N: int, K: int, batch: int, a_mn: bool, b_mn: bool, a_bcast: bool, b_bcast: bool,
                          passes: int = 3, bn: int | None = None, stages: int | None = None,
                          kc_blocks: int | None = None, split_warps: int = 8) -> TcKernel:
+    import os
+    trace = os.environ.get("DLGRAD_TC_TRACE", "0") == "1"     # diagnostic: CTA 0 timestamps its first 32 k-blocks
+    TR = (lambda kind, cond="true": f"if (blockIdx.x == 0u && it < 32u && {cond}) trace[{kind}][it] = clock64();") if trace else (lambda *a: "")
     kblocks = _cdiv(K, BK)
     # K is accumulated in TMEM in chunks of <= 1024: the tensor core adds into the fp32 accumulator with
     # truncation, a bias that grows with the accumulator's magnitude (8.5e-5 at K = 4096 on U[0,1) inputs,
@@ -463,6 +466,7 @@ def matmul_tc_persistent(M: int, N: int, K: int, batch: int, a_mn: bool, b_mn: b
             for (unsigned kb = 0; kb < {kblocks}u; ++kb, ++it) {{
                 const unsigned s = it % {stages}u, ph = (it / {stages}u) & 1u;
                 mbar_wait(full + s * 8u, ph);
+                {TR(1, "ctid == 0u")}
                 const float4* src = reinterpret_cast<const float4*>(smem_gen + s * {per_stage}u);
                 float4* dst = reinterpret_cast<float4*>(smem_gen + s * {per_stage}u + {ab}u);
                 #pragma unroll 4
@@ -477,6 +481,7 @@ def matmul_tc_persistent(M: int, N: int, K: int, batch: int, a_mn: bool, b_mn: b
                 }}
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 mbar_arrive(split + s * 8u);
+                {TR(2, "ctid == 0u")}
             }}
         }}"""
     else:
@@ -505,6 +510,7 @@ extern "C" __global__ void __launch_bounds__({nthreads}, 1)
     const unsigned full = bars, empty = bars + {stages * 8}u, split = bars + {stages * 16}u;
     const unsigned tfull = bars + {stages * 24}u, tempty = tfull + 16u;
     __shared__ unsigned tmem_slot;
+    {"__shared__ long long trace[5][32];" if trace else ""}
     const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
 
     if (threadIdx.x == 0) {{
@@ -537,6 +543,7 @@ extern "C" __global__ void __launch_bounds__({nthreads}, 1)
                 for (unsigned kb = 0; kb < {kblocks}u; ++kb, ++it) {{
                     const unsigned s = it % {stages}u, ph = (it / {stages}u) & 1u;
                     mbar_wait(empty + s * 8u, ph ^ 1u);
+                    {TR(0)}
                     const unsigned full_bar = full + s * 8u;
                     const unsigned a_s = smem + s * {per_stage}u, b_s = a_s + {a_tile}u;
                     const unsigned k0 = kb * {BK}u;
@@ -560,6 +567,7 @@ extern "C" __global__ void __launch_bounds__({nthreads}, 1)
                     for (unsigned kb = ch * {kc}u, kbl = 0; kb < kend; ++kb, ++kbl, ++it) {{
                         const unsigned s = it % {stages}u, ph = (it / {stages}u) & 1u;
                         {mma_wait}
+                        {TR(3)}
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                         const unsigned a_s = smem + s * {per_stage}u, b_s = a_s + {a_tile}u;
                         const unsigned long long adesc = make_desc(a_s, {a_lbo}u, {a_sbo}u, {a_lt}u);
@@ -568,6 +576,7 @@ extern "C" __global__ void __launch_bounds__({nthreads}, 1)
                         for (unsigned k = 0; k < {BK // 8}u; ++k) {{{mma_body}
                         }}
                         umma_commit(empty + s * 8u);
+                        {TR(4)}
                     }}
                     umma_commit(tfull + b * 8u);
                 }}
@@ -620,12 +629,314 @@ extern "C" __global__ void __launch_bounds__({nthreads}, 1)
     }}
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    {"if (blockIdx.x == 0u && threadIdx.x < 160u) reinterpret_cast<long long*>(C)[threadIdx.x] = (&trace[0][0])[threadIdx.x];" if trace else ""}
     if (warp == 1) {{
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "n"({tmem_cols}));
     }}
 }}
 """
     return TcKernel(f"mm_tcp{passes}", src, (grid, 1, 1), nthreads, smem, batch * M * N, BN, stages)
+
+
+# =====================================================================================================
+# v4: persistent kernel with the A operand in TENSOR MEMORY (tcgen05.mma "TS" form).
+#
+# Pipeline traces of v2 (scripts/tc_trace.py, profiles/r01_tc_pipeline_trace_v2.txt) show its k-block
+# period equals the shared-memory traffic at 128 B/clk: the splitter reads and writes every staged byte
+# once and the three MMAs of a k-step read every operand byte three times -> 5 x (A + B) bytes per k-block
+# (BN=128: 160 KiB = 1280 clk against a 768 clk tensor-pipe floor).  Here the splitter threads own one A row
+# each (thread = TMEM lane), read it once from the swizzled TMA tile and write A_hi and A_lo straight into
+# TMEM with tcgen05.st; the MMAs take A from TMEM, so A costs 1 x and only B costs 5 x of its bytes
+# (BN=128: 96 KiB = 768 clk, level with the tensor pipe), and a stage shrinks from 2(A+B) to A+2B bytes
+# (4 stages instead of 3 at BN=128).
+# =====================================================================================================
+_HELPERS_TS = r"""
+__device__ __forceinline__ void umma_tf32_ts(unsigned tmem_d, unsigned tmem_a, unsigned long long bdesc,
+                                             unsigned idesc, unsigned accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+        :: "r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+"""
+
+
+# k-block period and exposed per-tile epilogue of the TS kernel, in units of the BN=128 k-block period
+# (fitted to scripts/tc_probe.py perf4 on B200: 4096^3, the GPT projection shapes and the attention GEMMs)
+_TS_PERIOD = {32: 0.75, 64: 0.82, 96: 0.92, 128: 1.0, 192: 1.364, 256: 2.03}
+_TS_EPILOGUE = {32: 0.3, 64: 0.5, 96: 0.9, 128: 1.2, 192: 2.5, 256: 3.5}
+
+
+def pick_bn_ts(M: int, N: int, batch: int, kblocks: int) -> int:
+    """Column-tile width minimising (tiles per persistent CTA) x (k-blocks x period + epilogues)."""
+    ntm = _cdiv(M, BM) * batch
+    chunks = _cdiv(kblocks, 32) if kblocks > 64 else 1
+    best, best_cost = 128, None
+    for cand in (192, 128, 256, 96, 64, 32):
+        if cand > _cdiv(N, 32) * 32 and cand != 32:
+            continue
+        tiles = ntm * _cdiv(N, cand)
+        cost = _cdiv(tiles, NUM_SMS) * (kblocks * _TS_PERIOD[cand] + chunks * _TS_EPILOGUE[cand])
+        if best_cost is None or cost < best_cost * 0.999:
+            best, best_cost = cand, cost
+    return best
+
+
+@cache
+def matmul_tc_ts(M: int, N: int, K: int, batch: int, a_mn: bool, b_mn: bool, a_bcast: bool, b_bcast: bool,
+                 bn: int | None = None, stages: int | None = None, kc_blocks: int | None = None) -> TcKernel:
+    import os
+    trace = os.environ.get("DLGRAD_TC_TRACE", "0") == "1"     # diagnostic: CTA 0 timestamps its first 32 k-blocks
+    TR = (lambda kind, cond="true": f"if (blockIdx.x == 0u && it < 32u && {cond}) trace[{kind}][it] = clock64();") if trace else (lambda *a: "")
+    kblocks = _cdiv(K, BK)
+    kc = kc_blocks or (32 if kblocks > 64 else kblocks)       # K chunks of <= 1024, see matmul_tc_persistent
+    nchunks = _cdiv(kblocks, kc)
+    BN = bn or pick_bn_ts(M, N, batch, kblocks)
+    a_tile, b_tile = BM * BK * 4, BN * BK * 4
+    per_stage = a_tile + 2 * b_tile                          # raw A | raw B (= B_hi) | B_lo
+    EPI_BUFS = 2
+    epi_bytes = 4 * EPI_BUFS * 4096
+    budget = 227 * 1024 - 1024 - 512 - epi_bytes
+    if stages is None:
+        stages = max(2, min(6, budget // per_stage))
+    # TMEM columns: accumulator(s) first, then 64 per stage (A_hi 32 | A_lo 32)
+    acc_bufs = 2 if 2 * BN + 64 * min(stages, 3) <= 512 else 1
+    stages = min(stages, (512 - acc_bufs * BN) // 64)
+    assert stages >= 2, (BN, stages)
+    a_tmem0 = acc_bufs * BN
+    tmem_cols = 32
+    while tmem_cols < a_tmem0 + 64 * stages:
+        tmem_cols *= 2
+    ntm, ntn = _cdiv(M, BM), _cdiv(N, BN)
+    ntiles = ntm * ntn * batch
+    smem = stages * per_stage + epi_bytes + 1024 + 512
+    idesc = _idesc(BM, BN, False, b_mn)                      # A comes from TMEM: rows = lanes, k = columns
+    b_lbo, b_sbo, b_kstep, b_lt = (256, 32, 64, 1) if b_mn else (1, 64, 2, 2)
+    a_boxes = BM // 32 if a_mn else 1
+    b_boxes = BN // 32 if b_mn else 1
+    grid = min(ntiles, NUM_SMS)
+    nthreads = 64 + 128 + 128
+    epi_w0 = 6
+
+    def tma_issue(which, boxes, mn, tile_var, row0):
+        tm = f"tm{which}"
+        z = "0" if (a_bcast if which == "A" else b_bcast) else "z"
+        if mn:
+            return "\n                    ".join(
+                f"tma_load_3d({tile_var} + {j * 4096}u, &{tm}, full_bar, (int)({row0} + {j * 32}u), (int)k0, (int){z});"
+                for j in range(boxes))
+        return f"tma_load_3d({tile_var}, &{tm}, full_bar, (int)k0, (int){row0}, (int){z});"
+
+    decode = f"""const unsigned z = t / {ntm * ntn}u, rem = t % {ntm * ntn}u;
+            const unsigned m0 = (rem / {ntn}u) * {BM}u, n0 = (rem % {ntn}u) * {BN}u;"""
+    if a_mn:
+        # stored [K][M]: box `sq` = 32 k-rows x 32 m-columns (128 B rows, 32-byte chunks XOR-ed with k & 3)
+        a_read = """
+                const unsigned char* abox = stage_gen + sq * 4096u;
+                #pragma unroll
+                for (unsigned k = 0; k < 32u; ++k)
+                    x[k] = *reinterpret_cast<const float*>(abox + k * 128u + ((((lane >> 3) ^ (k & 3u)) << 5) | ((lane & 7u) << 2)));"""
+    else:
+        # stored [M][K]: one 128-byte row per thread, 16-byte chunks XOR-ed with row & 7
+        a_read = """
+                const unsigned char* arow = stage_gen + (sq * 32u + lane) * 128u;
+                #pragma unroll
+                for (unsigned j = 0; j < 8u; ++j) {
+                    const float4 v4 = *reinterpret_cast<const float4*>(arow + ((j ^ (lane & 7u)) << 4));
+                    x[4 * j] = v4.x; x[4 * j + 1] = v4.y; x[4 * j + 2] = v4.z; x[4 * j + 3] = v4.w;
+                }"""
+    regs_in = ", ".join(f"%{i + 1}" for i in range(32))
+    hi_ops = ", ".join(f'"r"(hi[{i}])' for i in range(32))
+    lo_ops = ", ".join(f'"r"(lo[{i}])' for i in range(32))
+
+    regs = ", ".join(f"%{i}" for i in range(32))
+    outs = ", ".join(f'"=r"(v[{i}])' for i in range(32))
+    stage_writes = "\n                    ".join(
+        f"*reinterpret_cast<float4*>(sbuf_gen + lane * 128u + (({j}u ^ (lane & 7u)) << 4)) = "
+        f"make_float4(__uint_as_float(v[{4 * j}]), __uint_as_float(v[{4 * j + 1}]), __uint_as_float(v[{4 * j + 2}]), __uint_as_float(v[{4 * j + 3}]));"
+        for j in range(8))
+
+    src = _HELPERS + _HELPERS_TS + f"""
+extern "C" __global__ void __launch_bounds__({nthreads}, 1)
+{KNAME}(const __grid_constant__ TMap tmA, const __grid_constant__ TMap tmB, const __grid_constant__ TMap tmC, float* __restrict__ C)
+{{
+    extern __shared__ unsigned char smem_raw[];
+    const unsigned smem = (smem_u32(smem_raw) + 1023u) & ~1023u;        // swizzle atoms need 1024-byte alignment
+    unsigned char* smem_gen = smem_raw + (smem - smem_u32(smem_raw));
+    const unsigned epi = smem + {stages * per_stage}u;
+    const unsigned bars = epi + {epi_bytes}u;
+    const unsigned full = bars, empty = bars + {stages * 8}u, split = bars + {stages * 16}u;
+    const unsigned tfull = bars + {stages * 24}u, tempty = tfull + 16u;
+    __shared__ unsigned tmem_slot;
+    {"__shared__ long long trace[5][32];" if trace else ""}
+    const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+
+    if (threadIdx.x == 0) {{
+        for (unsigned s = 0; s < {stages}u; ++s) {{
+            mbar_init(full + s * 8u, 1u);
+            mbar_init(empty + s * 8u, 1u);
+            mbar_init(split + s * 8u, 128u);
+        }}
+        for (unsigned b = 0; b < 2u; ++b) {{
+            mbar_init(tfull + b * 8u, 1u);
+            mbar_init(tempty + b * 8u, 4u);
+        }}
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }}
+    if (warp == 1) {{
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&tmem_slot)), "n"({tmem_cols}));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }}
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const unsigned tmem_base = tmem_slot;
+
+    if (warp == 0) {{
+        // ===== TMA producer =====
+        if (lane == 0) {{
+            unsigned it = 0;
+            for (unsigned t = blockIdx.x; t < {ntiles}u; t += {grid}u) {{
+                {decode}
+                for (unsigned kb = 0; kb < {kblocks}u; ++kb, ++it) {{
+                    const unsigned s = it % {stages}u, ph = (it / {stages}u) & 1u;
+                    mbar_wait(empty + s * 8u, ph ^ 1u);
+                    {TR(0)}
+                    const unsigned full_bar = full + s * 8u;
+                    const unsigned a_s = smem + s * {per_stage}u, b_s = a_s + {a_tile}u;
+                    const unsigned k0 = kb * {BK}u;
+                    mbar_expect_tx(full_bar, {a_tile + b_tile}u);
+                    {tma_issue("A", a_boxes, a_mn, "a_s", "m0")}
+                    {tma_issue("B", b_boxes, b_mn, "b_s", "n0")}
+                }}
+            }}
+        }}
+    }} else if (warp == 1) {{
+        // ===== MMA issuer (one lane): A_lo*B_hi, A_hi*B_lo, A_hi*B_hi per 8-wide k step, A from TMEM =====
+        if (lane == 0) {{
+            unsigned it = 0, u = 0;
+            for (unsigned t = blockIdx.x; t < {ntiles}u; t += {grid}u) {{
+                for (unsigned ch = 0; ch < {nchunks}u; ++ch, ++u) {{
+                    const unsigned b = u % {acc_bufs}u;
+                    mbar_wait(tempty + b * 8u, ((u / {acc_bufs}u) & 1u) ^ 1u);       // epilogue has drained this accumulator
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const unsigned tacc = tmem_base + b * {BN}u;
+                    const unsigned kend = min((ch + 1u) * {kc}u, {kblocks}u);
+                    for (unsigned kb = ch * {kc}u, kbl = 0; kb < kend; ++kb, ++kbl, ++it) {{
+                        const unsigned s = it % {stages}u, ph = (it / {stages}u) & 1u;
+                        mbar_wait(split + s * 8u, ph);
+                        {TR(3)}
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        const unsigned b_s = smem + s * {per_stage}u + {a_tile}u;
+                        const unsigned long long bdesc = make_desc(b_s, {b_lbo}u, {b_sbo}u, {b_lt}u);
+                        const unsigned a_hi = tmem_base + {a_tmem0}u + s * 64u, a_lo = a_hi + 32u;
+                        #pragma unroll
+                        for (unsigned k = 0; k < {BK // 8}u; ++k) {{
+                            const unsigned long long b_hi = bdesc + (unsigned long long)(k * {b_kstep}u);
+                            umma_tf32_ts(tacc, a_lo + k * 8u, b_hi, {idesc}u, (kbl | k) != 0u);
+                            umma_tf32_ts(tacc, a_hi + k * 8u, b_hi + {b_tile // 16}ull, {idesc}u, 1u);
+                            umma_tf32_ts(tacc, a_hi + k * 8u, b_hi, {idesc}u, 1u);
+                        }}
+                        umma_commit(empty + s * 8u);
+                        {TR(4)}
+                    }}
+                    umma_commit(tfull + b * 8u);
+                }}
+            }}
+        }}
+    }} else if (warp < {epi_w0}u) {{
+        // ===== splitter warps: thread = A row = TMEM lane.  A_hi / A_lo -> TMEM, B_lo -> twin smem buffer =====
+        const unsigned ctid = threadIdx.x - 64u;
+        const unsigned sq = warp & 3u;                         // the TMEM lane quarter this warp may write
+        unsigned it = 0;
+        for (unsigned t = blockIdx.x; t < {ntiles}u; t += {grid}u) {{
+            for (unsigned kb = 0; kb < {kblocks}u; ++kb, ++it) {{
+                const unsigned s = it % {stages}u, ph = (it / {stages}u) & 1u;
+                mbar_wait(full + s * 8u, ph);
+                {TR(1, "ctid == 0u")}
+                const unsigned char* stage_gen = smem_gen + s * {per_stage}u;
+                float x[32];{a_read}
+                unsigned hi[32], lo[32];
+                #pragma unroll
+                for (unsigned k = 0; k < 32u; ++k) {{
+                    hi[k] = __float_as_uint(x[k]) & 0xffffe000u;
+                    lo[k] = __float_as_uint(x[k] - __uint_as_float(hi[k]));
+                }}
+                const unsigned ta = tmem_base + ((sq * 32u) << 16) + {a_tmem0}u + s * 64u;
+                asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {{{regs_in}}};" :: "r"(ta), {hi_ops} : "memory");
+                asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {{{regs_in}}};" :: "r"(ta + 32u), {lo_ops} : "memory");
+                const float4* bsrc = reinterpret_cast<const float4*>(stage_gen + {a_tile}u);
+                float4* bdst = reinterpret_cast<float4*>(smem_gen + s * {per_stage}u + {a_tile + b_tile}u);
+                #pragma unroll 4
+                for (unsigned i = ctid; i < {b_tile // 16}u; i += 128u) {{
+                    const float4 v4 = bsrc[i];
+                    float4 l4;
+                    l4.x = v4.x - __uint_as_float(__float_as_uint(v4.x) & 0xffffe000u);
+                    l4.y = v4.y - __uint_as_float(__float_as_uint(v4.y) & 0xffffe000u);
+                    l4.z = v4.z - __uint_as_float(__float_as_uint(v4.z) & 0xffffe000u);
+                    l4.w = v4.w - __uint_as_float(__float_as_uint(v4.w) & 0xffffe000u);
+                    bdst[i] = l4;
+                }}
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                mbar_arrive(split + s * 8u);
+                {TR(2, "ctid == 0u")}
+            }}
+        }}
+    }} else {{
+        // ===== epilogue warps: TMEM -> registers -> swizzled smem box -> TMA store =====
+        const unsigned q = warp & 3u;                          // TMEM lane quarter this warp may read
+        const unsigned my_epi = epi + (warp - {epi_w0}u) * {EPI_BUFS * 4096}u;
+        unsigned char* my_epi_gen = smem_gen + {stages * per_stage}u + (warp - {epi_w0}u) * {EPI_BUFS * 4096}u;
+        unsigned u = 0, nstore = 0;
+        for (unsigned t = blockIdx.x; t < {ntiles}u; t += {grid}u) {{
+            {decode}
+            for (unsigned ch = 0; ch < {nchunks}u; ++ch, ++u) {{
+                const unsigned b = u % {acc_bufs}u;
+                mbar_wait(tfull + b * 8u, (u / {acc_bufs}u) & 1u);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                // a later K-chunk is ADDED to what the earlier chunk stored: that store must have landed
+                if (ch != 0u && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+                #pragma unroll 1
+                for (unsigned c = 0; c < {BN // 32}u; ++c) {{
+                    unsigned v[32];
+                    const unsigned taddr = tmem_base + ((q * 32u) << 16) + b * {BN}u + c * 32u;
+                    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {{{regs}}}, [%32];" : {outs} : "r"(taddr));
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    if (n0 + c * 32u < {N}u && m0 + q * 32u < {M}u) {{
+                        const unsigned sb = nstore & {EPI_BUFS - 1}u;
+                        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read {EPI_BUFS - 1};" ::: "memory");
+                        __syncwarp();
+                        unsigned char* sbuf_gen = my_epi_gen + sb * 4096u;
+                        {stage_writes}
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                        __syncwarp();
+                        if (lane == 0) {{
+                            if (ch == 0u) tma_store_3d(&tmC, my_epi + sb * 4096u, (int)(n0 + c * 32u), (int)(m0 + q * 32u), (int)z);
+                            else tma_reduce_add_3d(&tmC, my_epi + sb * 4096u, (int)(n0 + c * 32u), (int)(m0 + q * 32u), (int)z);
+                            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                        }}
+                        ++nstore;
+                    }}
+                }}
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tempty + b * 8u);        // accumulator b may be overwritten
+            }}
+        }}
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }}
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    {"if (blockIdx.x == 0u && threadIdx.x < 160u) reinterpret_cast<long long*>(C)[threadIdx.x] = (&trace[0][0])[threadIdx.x];" if trace else ""}
+    if (warp == 1) {{
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "n"({tmem_cols}));
+    }}
+}}
+"""
+    return TcKernel("mm_tcts", src, (grid, 1, 1), nthreads, smem, batch * M * N, BN, stages)
 
 
 # =====================================================================================================
@@ -675,6 +986,9 @@ __device__ __forceinline__ void umma_commit_2cta(unsigned bar) {
 @cache
 def matmul_tc_pair(M: int, N: int, K: int, batch: int, a_mn: bool, b_mn: bool, a_bcast: bool, b_bcast: bool,
                    bn: int | None = None, stages: int | None = None, kc_blocks: int | None = None) -> TcKernel:
+    import os
+    trace = os.environ.get("DLGRAD_TC_TRACE", "0") == "1"     # diagnostic: pair 0's leader timestamps its first 32 k-blocks
+    TR = (lambda kind, cond="true": f"if (blockIdx.x == 0u && it < 32u && {cond}) trace[{kind}][it] = clock64();") if trace else (lambda *a: "")
     kblocks = _cdiv(K, BK)
     kc = kc_blocks or (32 if kblocks > 64 else kblocks)
     nchunks = _cdiv(kblocks, kc)
@@ -734,6 +1048,7 @@ extern "C" __global__ void __launch_bounds__({nthreads}, 1)   // launched with c
     const unsigned full = bars, empty = bars + {stages * 8}u, split = bars + {stages * 16}u;
     const unsigned tfull = bars + {stages * 24}u, tempty = tfull + 16u;
     __shared__ unsigned tmem_slot;
+    {"__shared__ long long trace[5][32];" if trace else ""}
     const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
     const unsigned crank = cluster_rank();               // 0 = leader (issues the MMAs)
     const unsigned pair = blockIdx.x >> 1;
@@ -770,6 +1085,7 @@ extern "C" __global__ void __launch_bounds__({nthreads}, 1)   // launched with c
                 for (unsigned kb = 0; kb < {kblocks}u; ++kb, ++it) {{
                     const unsigned s = it % {stages}u, ph = (it / {stages}u) & 1u;
                     mbar_wait(empty + s * 8u, ph ^ 1u);
+                    {TR(0)}
                     const unsigned full_bar = full + s * 8u;
                     const unsigned a_s = smem + s * {per_stage}u, b_s = a_s + {a_tile}u;
                     const unsigned k0 = kb * {BK}u;
@@ -793,6 +1109,7 @@ extern "C" __global__ void __launch_bounds__({nthreads}, 1)   // launched with c
                     for (unsigned kb = ch * {kc}u, kbl = 0; kb < kend; ++kb, ++kbl, ++it) {{
                         const unsigned s = it % {stages}u, ph = (it / {stages}u) & 1u;
                         mbar_wait_cluster(split + s * 8u, ph);
+                        {TR(3)}
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                         const unsigned a_s = smem + s * {per_stage}u, b_s = a_s + {a_tile}u;
                         const unsigned long long adesc = make_desc(a_s, {a_lbo}u, {a_sbo}u, {a_lt}u);
@@ -806,6 +1123,7 @@ extern "C" __global__ void __launch_bounds__({nthreads}, 1)   // launched with c
                             umma_tf32_2cta(tacc, a_hi, b_hi, {idesc}u, 1u);
                         }}
                         umma_commit_2cta(empty + s * 8u);          // frees stage s in BOTH CTAs
+                        {TR(4)}
                     }}
                     umma_commit_2cta(tfull + b * 8u);               // accumulator b is complete in BOTH CTAs
                 }}
@@ -819,6 +1137,7 @@ extern "C" __global__ void __launch_bounds__({nthreads}, 1)   // launched with c
             for (unsigned kb = 0; kb < {kblocks}u; ++kb, ++it) {{
                 const unsigned s = it % {stages}u, ph = (it / {stages}u) & 1u;
                 mbar_wait(full + s * 8u, ph);
+                {TR(1, "ctid == 0u")}
                 const float4* src = reinterpret_cast<const float4*>(smem_gen + s * {per_stage}u);
                 float4* dst = reinterpret_cast<float4*>(smem_gen + s * {per_stage}u + {ab}u);
                 #pragma unroll 4
@@ -834,6 +1153,7 @@ extern "C" __global__ void __launch_bounds__({nthreads}, 1)   // launched with c
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
                 if (lane == 0) mbar_arrive_cluster(map_to_cta(split + s * 8u, 0u));
+                {TR(2, "ctid == 0u")}
             }}
         }}
     }} else {{
@@ -881,6 +1201,7 @@ extern "C" __global__ void __launch_bounds__({nthreads}, 1)   // launched with c
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     cluster_sync_all();                                  // no CTA leaves while its partner may still touch it
+    {"if (blockIdx.x == 0u && threadIdx.x < 160u) reinterpret_cast<long long*>(C)[threadIdx.x] = (&trace[0][0])[threadIdx.x];" if trace else ""}
     if (warp == 1) {{
         asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "n"({tmem_cols}));
     }}

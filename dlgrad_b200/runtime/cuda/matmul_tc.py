@@ -17,7 +17,8 @@ PASSES = int(os.environ.get("DLGRAD_TC_PASSES", "3"))
 ENABLED = os.environ.get("DLGRAD_TC", "1") != "0"
 MIN_FLOPS = 1 << 22
 SPLIT_WARPS = int(os.environ.get("DLGRAD_TC_SPLIT_WARPS", "4"))
-KERNEL = os.environ.get("DLGRAD_TC_KERNEL", "auto")   # auto | v3 = CTA pair | v2 = persistent 1-CTA | v1 = one tile per CTA
+# auto = v4 | v4 = persistent, A operand in TMEM | v3 = CTA pair | v2 = persistent, both operands in smem | v1 = one tile per CTA
+KERNEL = os.environ.get("DLGRAD_TC_KERNEL", "auto")
 
 
 def _tmap(d: dict):
@@ -69,13 +70,14 @@ def try_build(M, N, K, batch, a_bs, b_bs, tx, ty, aligned, passes: int | None = 
     b_rows = None
     which = kernel or KERNEL
     if which == "auto":
-        # CTA pairs (256 x 256 tiles on 74 pairs) win when there are enough pair tiles to balance: measured
-        # 228 vs 210 TFLOP/s at 4096^3 and 228 vs 205 at 8192x3072x768, but 161 vs 174 at 8192x768x768
-        pair_tiles = -(-M // 256) * -(-N // 256) * nb
-        which = "v3" if (passes == 3 and M >= 512 and N >= 1024 and pair_tiles >= 148 and K >= 256) else "v2"
+        # A-in-TMEM beats both shared-memory-operand kernels on every shape of scripts/tc_probe.py perf/perf4
+        # (e.g. 8192x768x768: 210 vs 156 TFLOP/s, 4096^3: 244 vs 235, TN 768x3072x8192: 240 vs 200)
+        which = "v4" if passes == 3 else "v2"
     if which == "v3" and passes == 3 and M > 128 and (bn or 256) % 64 == 0:
         k = tc.matmul_tc_pair(M, N, K, nb, a_mn, b_mn, a_bc, b_bc, bn, stages)
         cluster, b_rows = 2, k.bn // 2
+    elif which == "v4" and passes == 3:
+        k = tc.matmul_tc_ts(M, N, K, nb, a_mn, b_mn, a_bc, b_bc, bn, stages)
     elif which == "v1":
         k = tc.matmul_tc(M, N, K, nb, a_mn, b_mn, a_bc, b_bc, passes, bn, stages, hi_inplace)
     else:

@@ -108,16 +108,47 @@ if which in ("all", "v3"):
     case("v3 NN batched 8x1024x96x768 bB bn128", M=1024, N=96, K=768, nb=8, b_b=True, kernel="v3", bn=128)
     case("v3 NN 4096^3 accuracy U[0,1)", M=4096, N=4096, K=4096, kernel="v3",
          a=np.random.default_rng(5).random((1, 4096, 4096), dtype=np.float32), b=np.random.default_rng(6).random((1, 4096, 4096), dtype=np.float32))
+if which in ("all", "v4"):
+    for bn in (128, 64, 192, 256):
+        case(f"v4 NN 256x256x128 bn{bn}", M=256, N=256, K=128, kernel="v4", bn=bn)
+        case(f"v4 NT 256x256x128 bn{bn}", M=256, N=256, K=128, ty=True, kernel="v4", bn=bn)
+        case(f"v4 TN 256x256x128 bn{bn}", M=256, N=256, K=128, tx=True, kernel="v4", bn=bn)
+        case(f"v4 TT 256x256x128 bn{bn}", M=256, N=256, K=128, tx=True, ty=True, kernel="v4", bn=bn)
+    case("v4 NN 1000x1000x1000", M=1000, N=1000, K=1000, kernel="v4")
+    case("v4 TN 1000x1000x1000", M=1000, N=1000, K=1000, tx=True, kernel="v4")
+    case("v4 NN 333x200x44 ragged", M=333, N=200, K=44, kernel="v4")
+    case("v4 TN 333x200x44 ragged", M=333, N=200, K=44, tx=True, kernel="v4")
+    case("v4 NN batched 8x1024x96x768 bB", M=1024, N=96, K=768, nb=8, b_b=True, kernel="v4")
+    case("v4 NN batched 96x1024x64x1024 bn64", M=1024, N=64, K=1024, nb=96, kernel="v4", bn=64)
+    case("v4 TN batched 96x1024x64x1024 bn64", M=1024, N=64, K=1024, nb=96, tx=True, kernel="v4", bn=64)
+    case("v4 NN 4096^3 accuracy U[0,1)", M=4096, N=4096, K=4096, kernel="v4",
+         a=np.random.default_rng(5).random((1, 4096, 4096), dtype=np.float32), b=np.random.default_rng(6).random((1, 4096, 4096), dtype=np.float32))
+    case("v4 TN 768x3072x8192 accuracy U[0,1)", M=768, N=3072, K=8192, tx=True, kernel="v4",
+         a=np.random.default_rng(5).random((1, 8192, 768), dtype=np.float32), b=np.random.default_rng(6).random((1, 8192, 3072), dtype=np.float32))
+if which in ("all", "perf4"):
+    shapes = {"4096^3": dict(M=4096, N=4096, K=4096), "8192x768x768": dict(M=8192, N=768, K=768),
+              "NT 8192x768x768": dict(M=8192, N=768, K=768, ty=True),
+              "8192x3072x768": dict(M=8192, N=3072, K=768), "8192x768x3072": dict(M=8192, N=768, K=3072),
+              "TN 768x3072x8192": dict(M=768, N=3072, K=8192, tx=True), "TN b4 768x768x2048": dict(M=768, N=768, K=2048, nb=4, tx=True),
+              "b96 QK^T 1024x1024x64": dict(M=1024, N=1024, K=64, nb=96), "b96 AV 1024x64x1024": dict(M=1024, N=64, K=1024, nb=96),
+              "b96 TN 64x1024x1024": dict(M=64, N=1024, K=1024, nb=96, tx=True)}
+    for name, kw in shapes.items():
+        for bn in (64, 128, 192, 256):
+            if bn <= kw["N"]:
+                case(f"perf v4 bn{bn} {name}", time_it=10, bn=bn, kernel="v4", **kw)
 if which in ("all", "perf"):
     shapes = {"4096^3": dict(M=4096, N=4096, K=4096), "8192x768x768": dict(M=8192, N=768, K=768),
               "NT 8192x768x768": dict(M=8192, N=768, K=768, ty=True),
               "8192x3072x768": dict(M=8192, N=3072, K=768), "8192x768x3072": dict(M=8192, N=768, K=3072),
-              "TN 768x3072x8192": dict(M=768, N=3072, K=8192, tx=True), "TN 768x768x8192": dict(M=768, N=768, K=8192, tx=True),
-              "b96 QK^T 1024x1024x64": dict(M=1024, N=1024, K=64, nb=96)}
+              "TN 768x3072x8192": dict(M=768, N=3072, K=8192, tx=True), "TN b4 768x768x2048": dict(M=768, N=768, K=2048, nb=4, tx=True),
+              "b96 QK^T 1024x1024x64": dict(M=1024, N=1024, K=64, nb=96), "b96 AV 1024x64x1024": dict(M=1024, N=64, K=1024, nb=96),
+              "b96 TN 64x1024x1024": dict(M=64, N=1024, K=1024, nb=96, tx=True)}
     for name, kw in shapes.items():
-        case(f"perf v2 auto {name}", time_it=10, **kw)
-        for bn in (128, 256):
+        for bn in (64, 128, 192, 256):
             if bn <= kw["N"]:
+                case(f"perf v2 bn{bn} {name}", time_it=10, bn=bn, kernel="v2", **kw)
+        if kw["M"] >= 512 and kw["N"] >= 256:
+            for bn in (128, 256):
                 case(f"perf v3 bn{bn} {name}", time_it=10, bn=bn, kernel="v3", **kw)
 os.makedirs("gpurun_out", exist_ok=True)
 with open(f"gpurun_out/tc_probe_{which}.json", "w") as f:
