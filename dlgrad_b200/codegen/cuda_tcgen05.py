@@ -334,18 +334,20 @@ __device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
 __device__ __forceinline__ void mbar_arrive(unsigned bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
 }
+__device__ __forceinline__ unsigned mbar_try(unsigned bar, unsigned parity) {
+    unsigned ok;
+    asm volatile("{\n\t.reg .pred p;\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                 "selp.b32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok;
+}
 __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
     // try_wait suspends for a HW-defined window; the watchdog turns a protocol bug into a trap
-    // (a CUDA error) instead of a hung GPU.
+    // (a CUDA error) instead of a hung GPU.  The clock is only read once the first try has failed.
+    if (mbar_try(bar, parity)) return;
     const long long t0 = clock64();
-    for (;;) {
-        unsigned ok;
-        asm volatile("{\n\t.reg .pred p;\n\t"
-                     "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-                     "selp.b32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-        if (ok) return;
+    while (!mbar_try(bar, parity))
         if (clock64() - t0 > 4000000000LL) __trap();
-    }
 }
 __device__ __forceinline__ void tma_load_3d(unsigned dst, const TMap* map, unsigned bar, int c0, int c1, int c2) {
     asm volatile(
@@ -651,6 +653,13 @@ extern "C" __global__ void __launch_bounds__({nthreads}, 1)
 # (4 stages instead of 3 at BN=128).
 # =====================================================================================================
 _HELPERS_TS = r"""
+// true in exactly one lane of a converged warp; ptxas recognises the elect.sync predicate and issues the
+// guarded tcgen05 instructions once, without the per-thread serialisation loop an `if (lane == 0)` gets
+__device__ __forceinline__ bool elect_one() {
+    unsigned pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0u;
+}
 __device__ __forceinline__ void umma_tf32_ts(unsigned tmem_d, unsigned tmem_a, unsigned long long bdesc,
                                              unsigned idesc, unsigned accumulate) {
     asm volatile(
@@ -688,6 +697,7 @@ def matmul_tc_ts(M: int, N: int, K: int, batch: int, a_mn: bool, b_mn: bool, a_b
                  bn: int | None = None, stages: int | None = None, kc_blocks: int | None = None) -> TcKernel:
     import os
     trace = os.environ.get("DLGRAD_TC_TRACE", "0") == "1"     # diagnostic: CTA 0 timestamps its first 32 k-blocks
+    exp = os.environ.get("DLGRAD_TC_EXPERIMENT", "")          # diagnostic variants (wrong results): mma1, mma2, nobsplit
     TR = (lambda kind, cond="true": f"if (blockIdx.x == 0u && it < 32u && {cond}) trace[{kind}][it] = clock64();") if trace else (lambda *a: "")
     kblocks = _cdiv(K, BK)
     kc = kc_blocks or (32 if kblocks > 64 else kblocks)       # K chunks of <= 1024, see matmul_tc_persistent
@@ -716,8 +726,8 @@ def matmul_tc_ts(M: int, N: int, K: int, batch: int, a_mn: bool, b_mn: bool, a_b
     a_boxes = BM // 32 if a_mn else 1
     b_boxes = BN // 32 if b_mn else 1
     grid = min(ntiles, NUM_SMS)
-    nthreads = 64 + 128 + 128
-    epi_w0 = 6
+    nthreads = 64 + 128 + 128 + 128       # producer, MMA | 4 A-splitter warps | 4 B-splitter warps | 4 epilogue warps
+    epi_w0 = 10
 
     def tma_issue(which, boxes, mn, tile_var, row0):
         tm = f"tm{which}"
@@ -776,7 +786,7 @@ extern "C" __global__ void __launch_bounds__({nthreads}, 1)
         for (unsigned s = 0; s < {stages}u; ++s) {{
             mbar_init(full + s * 8u, 1u);
             mbar_init(empty + s * 8u, 1u);
-            mbar_init(split + s * 8u, 128u);
+            mbar_init(split + s * 8u, 8u);                 // one arrive per splitter warp
         }}
         for (unsigned b = 0; b < 2u; ++b) {{
             mbar_init(tfull + b * 8u, 1u);
@@ -794,28 +804,34 @@ extern "C" __global__ void __launch_bounds__({nthreads}, 1)
     const unsigned tmem_base = tmem_slot;
 
     if (warp == 0) {{
-        // ===== TMA producer =====
-        if (lane == 0) {{
+        // ===== TMA producer: the warp walks the ring together, one elected lane issues =====
+        {{
             unsigned it = 0;
             for (unsigned t = blockIdx.x; t < {ntiles}u; t += {grid}u) {{
                 {decode}
                 for (unsigned kb = 0; kb < {kblocks}u; ++kb, ++it) {{
                     const unsigned s = it % {stages}u, ph = (it / {stages}u) & 1u;
                     mbar_wait(empty + s * 8u, ph ^ 1u);
-                    {TR(0)}
+                    {TR(0, "lane == 0u")}
                     const unsigned full_bar = full + s * 8u;
                     const unsigned a_s = smem + s * {per_stage}u, b_s = a_s + {a_tile}u;
                     const unsigned k0 = kb * {BK}u;
-                    mbar_expect_tx(full_bar, {a_tile + b_tile}u);
-                    {tma_issue("A", a_boxes, a_mn, "a_s", "m0")}
-                    {tma_issue("B", b_boxes, b_mn, "b_s", "n0")}
+                    if (elect_one()) {{
+                        mbar_expect_tx(full_bar, {a_tile + b_tile}u);
+                        {tma_issue("A", a_boxes, a_mn, "a_s", "m0")}
+                        {tma_issue("B", b_boxes, b_mn, "b_s", "n0")}
+                    }}
+                    __syncwarp();
                 }}
             }}
         }}
     }} else if (warp == 1) {{
-        // ===== MMA issuer (one lane): A_lo*B_hi, A_hi*B_lo, A_hi*B_hi per 8-wide k step, A from TMEM =====
-        if (lane == 0) {{
+        // ===== MMA issuer: the whole warp walks the loop, one elected lane issues.  A_lo*B_hi, A_hi*B_lo, A_hi*B_hi
+        //       per 8-wide k step, A from TMEM =====
+        {{
             unsigned it = 0, u = 0;
+            const unsigned long long bdesc0 = make_desc(smem + {a_tile}u, {b_lbo}u, {b_sbo}u, {b_lt}u);   // stage 0; a stage is {per_stage // 16} 16-byte units
+            const unsigned a_tmem = tmem_base + {a_tmem0}u;
             for (unsigned t = blockIdx.x; t < {ntiles}u; t += {grid}u) {{
                 for (unsigned ch = 0; ch < {nchunks}u; ++ch, ++u) {{
                     const unsigned b = u % {acc_bufs}u;
@@ -826,35 +842,37 @@ extern "C" __global__ void __launch_bounds__({nthreads}, 1)
                     for (unsigned kb = ch * {kc}u, kbl = 0; kb < kend; ++kb, ++kbl, ++it) {{
                         const unsigned s = it % {stages}u, ph = (it / {stages}u) & 1u;
                         mbar_wait(split + s * 8u, ph);
-                        {TR(3)}
+                        {TR(3, "lane == 0u")}
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                        const unsigned b_s = smem + s * {per_stage}u + {a_tile}u;
-                        const unsigned long long bdesc = make_desc(b_s, {b_lbo}u, {b_sbo}u, {b_lt}u);
-                        const unsigned a_hi = tmem_base + {a_tmem0}u + s * 64u, a_lo = a_hi + 32u;
-                        #pragma unroll
-                        for (unsigned k = 0; k < {BK // 8}u; ++k) {{
-                            const unsigned long long b_hi = bdesc + (unsigned long long)(k * {b_kstep}u);
-                            umma_tf32_ts(tacc, a_lo + k * 8u, b_hi, {idesc}u, (kbl | k) != 0u);
-                            umma_tf32_ts(tacc, a_hi + k * 8u, b_hi + {b_tile // 16}ull, {idesc}u, 1u);
-                            umma_tf32_ts(tacc, a_hi + k * 8u, b_hi, {idesc}u, 1u);
+                        const unsigned long long bdesc = bdesc0 + (unsigned long long)(s * {per_stage // 16}u);
+                        const unsigned a_hi = a_tmem + s * 64u, a_lo = a_hi + 32u;
+                        if (elect_one()) {{
+                            #pragma unroll
+                            for (unsigned k = 0; k < {BK // 8}u; ++k) {{
+                                const unsigned long long b_hi = bdesc + (unsigned long long)(k * {b_kstep}u);
+                                umma_tf32_ts(tacc, a_lo + k * 8u, b_hi, {idesc}u, (kbl | k) != 0u);
+                                {"" if exp in ("mma1",) else f"umma_tf32_ts(tacc, a_hi + k * 8u, b_hi + {b_tile // 16}ull, {idesc}u, 1u);"}
+                                {"" if exp in ("mma1", "mma2") else f"umma_tf32_ts(tacc, a_hi + k * 8u, b_hi, {idesc}u, 1u);"}
+                            }}
+                            umma_commit(empty + s * 8u);
                         }}
-                        umma_commit(empty + s * 8u);
-                        {TR(4)}
+                        __syncwarp();
+                        {TR(4, "lane == 0u")}
                     }}
-                    umma_commit(tfull + b * 8u);
+                    if (elect_one()) umma_commit(tfull + b * 8u);
+                    __syncwarp();
                 }}
             }}
         }}
-    }} else if (warp < {epi_w0}u) {{
-        // ===== splitter warps: thread = A row = TMEM lane.  A_hi / A_lo -> TMEM, B_lo -> twin smem buffer =====
-        const unsigned ctid = threadIdx.x - 64u;
+    }} else if (warp < 6u) {{
+        // ===== A-splitter warps: thread = A row = TMEM lane; A_hi and A_lo go straight to tensor memory =====
         const unsigned sq = warp & 3u;                         // the TMEM lane quarter this warp may write
         unsigned it = 0;
         for (unsigned t = blockIdx.x; t < {ntiles}u; t += {grid}u) {{
             for (unsigned kb = 0; kb < {kblocks}u; ++kb, ++it) {{
                 const unsigned s = it % {stages}u, ph = (it / {stages}u) & 1u;
                 mbar_wait(full + s * 8u, ph);
-                {TR(1, "ctid == 0u")}
+                {TR(1, "threadIdx.x == 64u")}
                 const unsigned char* stage_gen = smem_gen + s * {per_stage}u;
                 float x[32];{a_read}
                 unsigned hi[32], lo[32];
@@ -866,10 +884,25 @@ extern "C" __global__ void __launch_bounds__({nthreads}, 1)
                 const unsigned ta = tmem_base + ((sq * 32u) << 16) + {a_tmem0}u + s * 64u;
                 asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {{{regs_in}}};" :: "r"(ta), {hi_ops} : "memory");
                 asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {{{regs_in}}};" :: "r"(ta + 32u), {lo_ops} : "memory");
-                const float4* bsrc = reinterpret_cast<const float4*>(stage_gen + {a_tile}u);
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(split + s * 8u);
+                {TR(2, "threadIdx.x == 64u")}
+            }}
+        }}
+    }} else if (warp < {epi_w0}u) {{
+        // ===== B-splitter warps: B_lo = x - trunc_tf32(x) into the twin buffer (same swizzled layout, linear pass) =====
+        const unsigned ctid = threadIdx.x - 192u;
+        unsigned it = 0;
+        for (unsigned t = blockIdx.x; t < {ntiles}u; t += {grid}u) {{
+            for (unsigned kb = 0; kb < {kblocks}u; ++kb, ++it) {{
+                const unsigned s = it % {stages}u, ph = (it / {stages}u) & 1u;
+                mbar_wait(full + s * 8u, ph);
+                const float4* bsrc = reinterpret_cast<const float4*>(smem_gen + s * {per_stage}u + {a_tile}u);
                 float4* bdst = reinterpret_cast<float4*>(smem_gen + s * {per_stage}u + {a_tile + b_tile}u);
-                #pragma unroll 4
-                for (unsigned i = ctid; i < {b_tile // 16}u; i += 128u) {{
+                #pragma unroll 8
+                for (unsigned i = ctid; i < {0 if exp == "nobsplit" else b_tile // 16}u; i += 128u) {{
                     const float4 v4 = bsrc[i];
                     float4 l4;
                     l4.x = v4.x - __uint_as_float(__float_as_uint(v4.x) & 0xffffe000u);
@@ -878,11 +911,9 @@ extern "C" __global__ void __launch_bounds__({nthreads}, 1)
                     l4.w = v4.w - __uint_as_float(__float_as_uint(v4.w) & 0xffffe000u);
                     bdst[i] = l4;
                 }}
-                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                mbar_arrive(split + s * 8u);
-                {TR(2, "ctid == 0u")}
+                __syncwarp();
+                if (lane == 0) mbar_arrive(split + s * 8u);
             }}
         }}
     }} else {{
