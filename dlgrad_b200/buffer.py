@@ -117,7 +117,8 @@ class Buffer:
     # ------------------------------------------------------------------ deferred pointwise producers
     # A CUDA Buffer may be created WITHOUT running its kernel: `_pending` records a cheap pointwise
     # producer — ("scale", src, s) for `src * python_scalar`, ("mfill", src, mask, val) for masked_fill,
-    # ("softmax_bwd", y, g, dim, kind) for the row backward.  Reading `.ptr` materialises it (one fused
+    # ("softmax_bwd", y, g, dim, kind) for the row backward, ("tr", src) for a transpose of the two
+    # innermost dims.  Reading `.ptr` materialises it (one fused
     # kernel for the whole pending chain); consumers that can fold the chain into their own kernel
     # (softmax forward, and the chain materialiser itself) never trigger the intermediate writes.  The
     # values are identical either way; only the number of passes over HBM changes.
@@ -290,12 +291,31 @@ class Buffer:
 
     def permute(self, order: tuple) -> "Buffer":
         out_shape = tuple(self.shape[i] for i in order)
+        pend = self._pending
+        if pend is not None and pend[0] == "tr":
+            # permuting a deferred transpose: one kernel over the stored operand with the composed order
+            nd, src = self.ndim, pend[1]
+            swap = list(range(nd))
+            swap[nd - 2], swap[nd - 1] = nd - 1, nd - 2
+            order = tuple(swap[i] for i in order)
+            return src._like(_dispatch(op=UnaryOps.PERMUTE, device=_CUDA, x=src, order=order), out_shape, _CUDA)
         dev = Buffer._route(self)
         return self._like(_dispatch(op=UnaryOps.PERMUTE, device=dev, x=self, order=tuple(order)), out_shape, dev)
 
     def transpose(self, dim0: int, dim1: int) -> "Buffer":
-        order = list(range(self.ndim))
+        nd = self.ndim
+        order = list(range(nd))
         order[dim0], order[dim1] = order[dim1], order[dim0]
+        if (nd >= 2 and self.metadata.device is _CUDA and self.scalar is None
+                and {dim0 % nd, dim1 % nd} == {nd - 2, nd - 1} and self.numel >= LAZY_MIN_NUMEL):
+            # Transposing the two innermost dims of a CUDA buffer is deferred: matmul reads the stored
+            # operand through its transpose flag (no copy); any other consumer materialises it through
+            # `.ptr` with the permute kernel.  (x^T)^T is the stored operand itself.
+            pend = self._pending
+            if pend is not None and pend[0] == "tr":
+                src = pend[1]
+                return Buffer(src.ptr, src.shape, _CUDA, src.metadata.dtype, aligned=src.aligned, keep=src._keep)
+            return Buffer._deferred(("tr", self), tuple(self.shape[i] for i in order), self.metadata.dtype)
         return self.permute(tuple(order))
 
     # ------------------------------------------------------------------ unary math

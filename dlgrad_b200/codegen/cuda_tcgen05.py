@@ -694,7 +694,10 @@ def pick_bn_ts(M: int, N: int, batch: int, kblocks: int) -> int:
 
 @cache
 def matmul_tc_ts(M: int, N: int, K: int, batch: int, a_mn: bool, b_mn: bool, a_bcast: bool, b_bcast: bool,
-                 bn: int | None = None, stages: int | None = None, kc_blocks: int | None = None) -> TcKernel:
+                 bn: int | None = None, stages: int | None = None, kc_blocks: int | None = None,
+                 bias: bool = False) -> TcKernel:
+    """`bias`: the kernel takes a 5th parameter, a length-N row the epilogue adds to every output row (the
+    Linear bias; it rides on the first K-chunk's store)."""
     import os
     trace = os.environ.get("DLGRAD_TC_TRACE", "0") == "1"     # diagnostic: CTA 0 timestamps its first 32 k-blocks
     exp = os.environ.get("DLGRAD_TC_EXPERIMENT", "")          # diagnostic variants (wrong results): mma1, mma2, nobsplit
@@ -760,6 +763,20 @@ def matmul_tc_ts(M: int, N: int, K: int, batch: int, a_mn: bool, b_mn: bool, a_b
     hi_ops = ", ".join(f'"r"(hi[{i}])' for i in range(32))
     lo_ops = ", ".join(f'"r"(lo[{i}])' for i in range(32))
 
+    bias_code = "" if not bias else f"""
+                        if (ch == 0u) {{
+                            #pragma unroll
+                            for (unsigned j = 0; j < 8u; ++j) {{
+                                const unsigned col = n0 + c * 32u + j * 4u;
+                                if (col < {N}u) {{                      // N % 4 == 0: a float4 is all in or all out
+                                    const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + col));
+                                    v[4 * j] = __float_as_uint(__uint_as_float(v[4 * j]) + bv.x);
+                                    v[4 * j + 1] = __float_as_uint(__uint_as_float(v[4 * j + 1]) + bv.y);
+                                    v[4 * j + 2] = __float_as_uint(__uint_as_float(v[4 * j + 2]) + bv.z);
+                                    v[4 * j + 3] = __float_as_uint(__uint_as_float(v[4 * j + 3]) + bv.w);
+                                }}
+                            }}
+                        }}"""
     regs = ", ".join(f"%{i}" for i in range(32))
     outs = ", ".join(f'"=r"(v[{i}])' for i in range(32))
     stage_writes = "\n                    ".join(
@@ -769,7 +786,7 @@ def matmul_tc_ts(M: int, N: int, K: int, batch: int, a_mn: bool, b_mn: bool, a_b
 
     src = _HELPERS + _HELPERS_TS + f"""
 extern "C" __global__ void __launch_bounds__({nthreads}, 1)
-{KNAME}(const __grid_constant__ TMap tmA, const __grid_constant__ TMap tmB, const __grid_constant__ TMap tmC, float* __restrict__ C)
+{KNAME}(const __grid_constant__ TMap tmA, const __grid_constant__ TMap tmB, const __grid_constant__ TMap tmC, float* __restrict__ C{", const float* __restrict__ bias" if bias else ""})
 {{
     extern __shared__ unsigned char smem_raw[];
     const unsigned smem = (smem_u32(smem_raw) + 1023u) & ~1023u;        // swizzle atoms need 1024-byte alignment
@@ -936,7 +953,7 @@ extern "C" __global__ void __launch_bounds__({nthreads}, 1)
                     const unsigned taddr = tmem_base + ((q * 32u) << 16) + b * {BN}u + c * 32u;
                     asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {{{regs}}}, [%32];" : {outs} : "r"(taddr));
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                    if (n0 + c * 32u < {N}u && m0 + q * 32u < {M}u) {{
+                    if (n0 + c * 32u < {N}u && m0 + q * 32u < {M}u) {{{bias_code}
                         const unsigned sb = nstore & {EPI_BUFS - 1}u;
                         if (lane == 0) asm volatile("cp.async.bulk.wait_group.read {EPI_BUFS - 1};" ::: "memory");
                         __syncwarp();
@@ -967,7 +984,7 @@ extern "C" __global__ void __launch_bounds__({nthreads}, 1)
     }}
 }}
 """
-    return TcKernel("mm_tcts", src, (grid, 1, 1), nthreads, smem, batch * M * N, BN, stages)
+    return TcKernel("mm_tcts_b" if bias else "mm_tcts", src, (grid, 1, 1), nthreads, smem, batch * M * N, BN, stages)
 
 
 # =====================================================================================================

@@ -343,20 +343,35 @@ class MatMul(OP):
 
     def backward(self, upstream_grad: Buffer) -> tuple[Buffer | None, Buffer | None]:
         g = upstream_grad if upstream_grad.shape == self.out_shape else upstream_grad.reshape(self.out_shape)
-        xr, yr = self.x.reshape(self.p1), self.y.reshape(self.p2)
+        xr = self.x if self.x.shape == self.p1 else self.x.reshape(self.p1)
+        yr = self.y if self.y.shape == self.p2 else self.y.reshape(self.p2)
         dev = Buffer._route(g, xr, yr)
         if dev is Device.CUDA:
             # CUDA: dX = g @ Y^T and dY = X^T @ g read the stored operands transposed inside the
             # kernel; the reference materialises both transposes first (dlgrad/ops.py:319-327).
+            # When an operand is itself a deferred transpose s^T (q @ k.transpose(2, 3)), the gradient is
+            # produced for the STORED matrix s and handed on as a deferred transpose, which the Transpose
+            # node's backward cancels: ds = (dX)^T = Y @ g^T resp. (dY)^T = g^T @ X.
             from dlgrad_b200.helpers import BinaryOps
+
+            def mm(a, b, shape, **kw):
+                return Buffer(dispatcher.dispatch(op=BinaryOps.MATMUL, device=dev, x=a, y=b, **kw), shape, dev, g.dtype)
+
+            def lazy_t(b):
+                return Buffer._deferred(("tr", b), b.shape[:-2] + (b.shape[-1], b.shape[-2]), b.dtype)
+            batch = self.out_shape[:-2]
             gx = gy = None
             if self.req_grad[0]:
-                gx = Buffer(dispatcher.dispatch(op=BinaryOps.MATMUL, device=dev, x=g, y=yr, trans_y=True),
-                            self.out_shape[:-2] + (self.p1[-2], self.p1[-1]), dev, g.dtype)
+                if xr._pending is not None and xr._pending[0] == "tr":
+                    gx = lazy_t(mm(yr, g, batch + (self.p1[-1], self.p1[-2]), trans_y=True))
+                else:
+                    gx = mm(g, yr, batch + (self.p1[-2], self.p1[-1]), trans_y=True)
                 gx = unbroadcast(gx, self.x.shape)
             if self.req_grad[1]:
-                gy = Buffer(dispatcher.dispatch(op=BinaryOps.MATMUL, device=dev, x=xr, y=g, trans_x=True),
-                            self.out_shape[:-2] + (self.p2[-2], self.p2[-1]), dev, g.dtype)
+                if yr._pending is not None and yr._pending[0] == "tr":
+                    gy = lazy_t(mm(g, xr, batch + (self.p2[-1], self.p2[-2]), trans_x=True))
+                else:
+                    gy = mm(xr, g, batch + (self.p2[-2], self.p2[-1]), trans_x=True)
                 gy = unbroadcast(gy, self.y.shape)
             return gx, gy
         nd = xr.ndim
@@ -376,7 +391,13 @@ class Linear(OP):
         self.x, self.w, self.b = x, weight, bias
         out_f, in_f = weight.shape
         rows = x.numel // in_f
-        y = dispatcher.dispatch(op=BinaryOps.MATMUL, device=Device.CUDA, x=x.reshape((rows, in_f)), y=weight, trans_y=True)
+        x2 = x.reshape((rows, in_f))
+        if bias is not None and bias.numel == out_f:
+            # the bias row rides on the GEMM epilogue when the shape runs on the tensor-core kernel
+            y, applied = dispatcher.dispatch(op=BinaryOps.MATMUL, device=Device.CUDA, x=x2, y=weight, trans_y=True, bias=bias)
+            out = Buffer(y, x.shape[:-1] + (out_f,), Device.CUDA, x.dtype)
+            return out if applied else out + bias
+        y = dispatcher.dispatch(op=BinaryOps.MATMUL, device=Device.CUDA, x=x2, y=weight, trans_y=True)
         out = Buffer(y, x.shape[:-1] + (out_f,), Device.CUDA, x.dtype)
         return out if bias is None else out + bias
 

@@ -42,20 +42,54 @@ def _geometry(xs: tuple, ys: tuple, tx: bool, ty: bool):
     return M, N, K, batch, bstrides(bx, mat_x), bstrides(by, mat_y), nd
 
 
-def run_matmul(x: Buffer, y: Buffer, trans_x: bool = False, trans_y: bool = False):
-    key = (x.metadata.shape, y.metadata.shape, trans_x, trans_y, x.aligned and y.aligned)
-    plan = _plans.get(key)
-    if plan is None:
-        plan = _plans[key] = _build(x.metadata.shape, y.metadata.shape, trans_x, trans_y,
-                                    x.aligned and y.aligned)
+def _fold_transpose(b: Buffer, flag: bool):
+    pend = b._pending
+    if pend is not None and pend[0] == "tr":
+        src = pend[1]
+        ss = src.metadata.shape
+        if b.metadata.shape == ss[:-2] + (ss[-1], ss[-2]):      # not reshaped in place since (unsqueeze/squeeze)
+            return src, not flag
+    return b, flag
+
+
+def run_matmul(x: Buffer, y: Buffer, trans_x: bool = False, trans_y: bool = False, bias: Buffer | None = None):
+    """`bias` (a length-N row) is added by the GEMM epilogue when the shape runs on the TS tensor-core kernel;
+    returns (ptr, bias_applied) in that case so the caller adds it separately otherwise."""
+    # a deferred transpose of an operand (Buffer.transpose) is folded into the kernel's operand-major flag
+    x, trans_x = _fold_transpose(x, trans_x)
+    y, trans_y = _fold_transpose(y, trans_y)
+    aligned = x.aligned and y.aligned
+    fused = None
+    if bias is not None and bias.aligned and bias.scalar is None:
+        bkey = (x.metadata.shape, y.metadata.shape, trans_x, trans_y, aligned, "bias")
+        fused = _plans.get(bkey)
+        if fused is None and bkey not in _plans:
+            fused = _plans[bkey] = _build_bias(x.metadata.shape, y.metadata.shape, trans_x, trans_y, aligned)
+    if fused is not None:
+        plan, args = fused, (_ops._dev_ptr(x), _ops._dev_ptr(y), _ops._dev_ptr(bias))
+    else:
+        key = (x.metadata.shape, y.metadata.shape, trans_x, trans_y, aligned)
+        plan = _plans.get(key)
+        if plan is None:
+            plan = _plans[key] = _build(x.metadata.shape, y.metadata.shape, trans_x, trans_y, aligned)
+        args = (_ops._dev_ptr(x), _ops._dev_ptr(y))      # materialises deferred operands OUTSIDE the timer bracket
     timer = _profile.matmul_timer
     if timer is None:
-        return plan(_ops._dev_ptr(x), _ops._dev_ptr(y))
-    px, py = _ops._dev_ptr(x), _ops._dev_ptr(y)      # materialise deferred operands OUTSIDE the bracket
-    t0 = timer.start()
-    out = plan(px, py)
-    timer.stop(t0, plan.flops, plan.tag)
-    return out
+        out = plan(*args)
+    else:
+        t0 = timer.start()
+        out = plan(*args)
+        timer.stop(t0, plan.flops, plan.tag)
+    return out if bias is None else (out, fused is not None)
+
+
+def _build_bias(xs, ys, tx, ty, aligned):
+    """The bias-in-epilogue variant, or None when this shape does not run on the TS kernel as one launch."""
+    M, N, K, batch, a_bs, b_bs, _ = _geometry(xs, ys, tx, ty)
+    if FORCE_SIMT or _split_k(M, N, K, batch, tx, ty) > 1:
+        return None
+    from dlgrad_b200.runtime.cuda import matmul_tc
+    return matmul_tc.try_build(M, N, K, batch, a_bs, b_bs, tx, ty, aligned, bias=True)
 
 
 def _build(xs, ys, tx, ty, aligned):
@@ -113,5 +147,5 @@ class MatmulPlan:
     def __init__(self, fn, flops: float, tag: tuple) -> None:
         self.fn, self.flops, self.tag = fn, flops, tag
 
-    def __call__(self, a, b):
-        return self.fn(a, b)
+    def __call__(self, *operands):
+        return self.fn(*operands)

@@ -60,7 +60,8 @@ def qualifies(M, N, K, batch, a_bs, b_bs, tx, ty, aligned, force: bool = False) 
 
 def try_build(M, N, K, batch, a_bs, b_bs, tx, ty, aligned, passes: int | None = None, bn: int | None = None,
               stages: int | None = None, hi_inplace: bool = False, force: bool = False, kernel: str | None = None,
-              split_warps: int | None = None):
+              split_warps: int | None = None, bias: bool = False):
+    """`bias=True` builds the variant whose epilogue adds a length-N row (only the TS kernel has one; None otherwise)."""
     q = qualifies(M, N, K, batch, a_bs, b_bs, tx, ty, aligned, force)
     if q is None:
         return None
@@ -73,11 +74,13 @@ def try_build(M, N, K, batch, a_bs, b_bs, tx, ty, aligned, passes: int | None = 
         # A-in-TMEM beats both shared-memory-operand kernels on every shape of scripts/tc_probe.py perf/perf4
         # (e.g. 8192x768x768: 210 vs 156 TFLOP/s, 4096^3: 244 vs 235, TN 768x3072x8192: 240 vs 200)
         which = "v4" if passes == 3 else "v2"
+    if bias and not (which == "v4" and passes == 3):
+        return None
     if which == "v3" and passes == 3 and M > 128 and (bn or 256) % 64 == 0:
         k = tc.matmul_tc_pair(M, N, K, nb, a_mn, b_mn, a_bc, b_bc, bn, stages)
         cluster, b_rows = 2, k.bn // 2
     elif which == "v4" and passes == 3:
-        k = tc.matmul_tc_ts(M, N, K, nb, a_mn, b_mn, a_bc, b_bc, bn, stages)
+        k = tc.matmul_tc_ts(M, N, K, nb, a_mn, b_mn, a_bc, b_bc, bn, stages, None, bias)
     elif which == "v1":
         k = tc.matmul_tc(M, N, K, nb, a_mn, b_mn, a_bc, b_bc, passes, bn, stages, hi_inplace)
     else:
@@ -93,11 +96,18 @@ def try_build(M, N, K, batch, a_bs, b_bs, tx, ty, aligned, passes: int | None = 
         raise RuntimeError("dlg_mm_plan_create failed: " + shim.last_error())
     nbytes = k.out_elems * 4
 
-    def run(a, b):
-        out = lib.dlg_mm_plan_run(plan, a, b)
-        if out == NULL:
-            raise RuntimeError("tensor-core matmul launch failed: " + shim.last_error())
-        return shim.own(out, nbytes)
+    if bias:
+        def run(a, b, aux):
+            out = lib.dlg_mm_plan_run_aux(plan, a, b, aux)
+            if out == NULL:
+                raise RuntimeError("tensor-core matmul launch failed: " + shim.last_error())
+            return shim.own(out, nbytes)
+    else:
+        def run(a, b):
+            out = lib.dlg_mm_plan_run(plan, a, b)
+            if out == NULL:
+                raise RuntimeError("tensor-core matmul launch failed: " + shim.last_error())
+            return shim.own(out, nbytes)
 
     from dlgrad_b200.runtime.cuda.matmul import MatmulPlan
     return MatmulPlan(run, 2.0 * nb * M * N * K, (f"tc{passes}", M, N, K, nb))

@@ -137,6 +137,11 @@ def materialize(buf: Buffer) -> None:
     pend = buf._pending
     if pend is None:
         return
+    if pend[0] == "tr":
+        src = pend[1]
+        nd = len(src.metadata.shape)
+        buf.ptr = permute(src, tuple(range(nd - 2)) + (nd - 1, nd - 2))
+        return
     chain, base = _peel_chain(buf)
     shape = buf.metadata.shape
     bp = base._pending
@@ -587,9 +592,10 @@ def permute(x: Buffer, order: tuple) -> CDataPtr:
 # matmul                                                      reference: cpu.py:505-602
 # ------------------------------------------------------------------------------------------------
 @dispatcher.register(BinaryOps.MATMUL, CUDA)
-def matmul(x: Buffer, y: Buffer, trans_x: bool = False, trans_y: bool = False) -> CDataPtr:
+def matmul(x: Buffer, y: Buffer, trans_x: bool = False, trans_y: bool = False, bias: Buffer | None = None):
+    """With `bias` (CUDA extension used by ops.Linear) returns (ptr, bias_applied)."""
     from dlgrad_b200.runtime.cuda import matmul as _mm
-    return _mm.run_matmul(x, y, trans_x, trans_y)
+    return _mm.run_matmul(x, y, trans_x, trans_y, bias)
 
 
 # ------------------------------------------------------------------------------------------------

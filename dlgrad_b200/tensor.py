@@ -197,6 +197,8 @@ class Tensor:
     def transpose(self, dim0: int, dim1: int) -> "Tensor":
         nd = self.ndim
         d0, d1 = dim0 % nd, dim1 % nd
+        if {d0, d1} == {nd - 2, nd - 1} and not self._on_host_runtime():
+            return ops.Transpose.execute(self, dim0=d0, dim1=d1)      # deferred on CUDA, folded into matmul
         order = list(range(nd))
         order[d0], order[d1] = order[d1], order[d0]
         return self.permute(tuple(order))

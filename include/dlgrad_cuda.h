@@ -104,6 +104,9 @@ void *dlg_mm_plan_create(void *fn, unsigned gx, unsigned gy, unsigned gz, unsign
                          const dlg_tmap_desc *a, const dlg_tmap_desc *b, const dlg_tmap_desc *c);
 void *dlg_mm_plan_run(void *plan, const void *a, const void *b);            /* returns C     */
 int   dlg_mm_plan_run_into(void *plan, void *c, const void *a, const void *b);
+/* same, with an auxiliary operand handed to the kernel as its 5th parameter: the bias row that the
+ * epilogue of a Linear GEMM adds (replaces the separate broadcast ADD of dlgrad/tensor.py:534) */
+void *dlg_mm_plan_run_aux(void *plan, const void *a, const void *b, const void *aux);
 
 /* ---- timing / graphs -----------------------------------------------------------------*/
 void *dlg_event_create(void);

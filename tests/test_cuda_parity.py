@@ -455,6 +455,88 @@ def test_deferred_pointwise_chains_are_transparent(oracle):
     _ = Buffer
 
 
+def test_deferred_transpose_folds_into_matmul(oracle):
+    """Buffer.transpose of the two innermost dims is deferred on CUDA (buffer.py, pending kind "tr"): matmul reads the
+    stored operand through its transpose flag, MatMul.backward hands the gradient of the stored matrix back as
+    a deferred transpose that Transpose.backward cancels, and every other consumer sees the materialised values."""
+    from dlgrad_b200 import Tensor, nn
+    compile_only = __import__("tests.conftest", fromlist=["x"]).COMPILE_ONLY
+    rng = np.random.default_rng(21)
+    q = (rng.random((2, 4, 128, 64), dtype=np.float32) - 0.5).astype(np.float32)       # numel = LAZY_MIN_NUMEL
+    k = (rng.random((2, 4, 128, 64), dtype=np.float32) - 0.5).astype(np.float32)
+    # 1. plain consumers: numpy(), elementwise, a second transpose (cancels), permute of a deferred transpose
+    K = Tensor(k.copy(), device="cuda")
+    kt = K.transpose(2, 3)
+    if not compile_only:
+        assert kt.data._pending is not None and kt.data._pending[0] == "tr"
+    check(kt.numpy(), k.transpose(0, 1, 3, 2), exact=True, what="deferred transpose -> numpy")
+    check((K.transpose(2, 3) + 1.0).numpy(), k.transpose(0, 1, 3, 2) + np.float32(1), exact=True, what="deferred transpose -> add")
+    check(K.transpose(2, 3).transpose(3, 2).numpy(), k, exact=True, what="(x^T)^T")
+    check(K.transpose(2, 3).permute((0, 3, 1, 2)).numpy(), k.transpose(0, 1, 3, 2).transpose(0, 3, 1, 2), exact=True,
+          what="permute of a deferred transpose")
+    check((K.transpose(2, 3) * 0.5).transpose(2, 3).numpy(), k * np.float32(0.5), exact=True, what="scale between transposes")
+    # 2. q @ k^T, k^T as left operand, both operands deferred: forward and both gradients vs the oracle
+    for name, build in {
+        "q @ k^T": lambda Q, Kx: Q @ Kx.transpose(2, 3),
+        "k^T @ q": lambda Q, Kx: Kx.transpose(2, 3) @ Q,
+        "q^T @ (k^T)^T-free": lambda Q, Kx: Q.transpose(2, 3) @ Kx,
+        "(q^T) @ (k^T)^T": lambda Q, Kx: Q.transpose(2, 3) @ Kx.transpose(2, 3).transpose(2, 3),
+        "q^T @ k2^T": lambda Q, Kx: (Q.transpose(2, 3) @ Q) @ Kx.transpose(2, 3),
+    }.items():
+        res = {}
+        for dev in ("cuda", "cpu"):
+            Q = Tensor(q.copy(), device=dev, requires_grad=True)
+            Kx = Tensor(k.copy(), device=dev, requires_grad=True)
+            out = build(Q, Kx)
+            w = Tensor(np.linspace(0.5, 1.5, int(np.prod(out.shape)), dtype=np.float32).reshape(out.shape), device=dev)
+            (out * w).sum().backward()
+            res[dev] = (out.numpy(), Q.grad.numpy(), Kx.grad.numpy())
+        for got, exp, what in zip(res["cuda"], res["cpu"], ("fwd", "dq", "dk")):
+            runner.rel_check(check, got, exp, runner.TOL_MATMUL, f"{name} {what}")
+    # 3. 2-D: x @ w.T with a parameter, then an in-place optimizer step BEFORE the deferred transpose is consumed
+    w = rng.random((256, 384), dtype=np.float32)
+    x = rng.random((64, 384), dtype=np.float32)
+    W = Tensor(w.copy(), device="cuda", requires_grad=True)
+    X = Tensor(x.copy(), device="cuda")
+    wt = W.T                                  # deferred, reads W
+    (W * 1.0).sum().backward()
+    nn.optim.SGD([W], lr=0.25).step()         # W <- W - 0.25
+    runner.rel_check(check, (X @ wt).numpy(), x.astype(np.float64) @ w.astype(np.float64).T, runner.TOL_MATMUL,
+                     "deferred w.T read ordered before the in-place step")
+    runner.rel_check(check, (X @ W.T).numpy(), x.astype(np.float64) @ (w.astype(np.float64) - 0.25).T, runner.TOL_MATMUL,
+                     "w.T after the step")
+
+
+@pytest.mark.parametrize("rows,in_f,out_f", [(512, 256, 384), (1000, 128, 96), (256, 4096, 100), (700, 72, 44)])
+def test_linear_bias_rides_on_gemm_epilogue(oracle, rows, in_f, out_f):
+    """ops.Linear on CUDA hands the bias row to the tensor-core GEMM, whose epilogue adds it before the store
+    (codegen/cuda_tcgen05.matmul_tc_ts, `bias`); forward and all three gradients vs the oracle's
+    matmul + broadcast add (dlgrad/tensor.py:520-535).  Ragged N (96, 100, 44) covers partial column chunks,
+    K = 4096 the multi-chunk accumulation where the bias must be added exactly once."""
+    from dlgrad_b200 import Tensor
+    from dlgrad_b200.runtime.cuda import matmul as mm
+    rng = np.random.default_rng(rows + out_f)
+    x = (rng.random((rows, in_f), dtype=np.float32) - 0.5).astype(np.float32)
+    w = (rng.random((out_f, in_f), dtype=np.float32) - 0.5).astype(np.float32)
+    b = (rng.random((1, out_f), dtype=np.float32) * 4 - 2).astype(np.float32)
+    res = {}
+    for dev in ("cuda", "cpu"):
+        X = Tensor(x.copy(), device=dev, requires_grad=True)
+        W = Tensor(w.copy(), device=dev, requires_grad=True)
+        B = Tensor(b.copy(), device=dev, requires_grad=True)
+        out = X.linear(W, B)
+        coef = Tensor(np.linspace(0.5, 1.5, rows * out_f, dtype=np.float32).reshape(rows, out_f), device=dev)
+        (out * coef).sum().backward()
+        res[dev] = (out.numpy(), X.grad.numpy(), W.grad.numpy(), B.grad.numpy())
+    if not __import__("tests.conftest", fromlist=["x"]).COMPILE_ONLY:
+        fused = [k for k in mm._plans if k[-1] == "bias" and k[0] == (rows, in_f) and mm._plans[k] is not None]
+        assert fused, "expected the bias-in-epilogue plan for this shape"
+    ref = x.astype(np.float64) @ w.astype(np.float64).T + b.astype(np.float64)
+    runner.rel_check(check, res["cuda"][0], ref, runner.TOL_MATMUL, "linear+bias fwd vs float64")
+    for got, exp, what in zip(res["cuda"], res["cpu"], ("fwd", "dx", "dw", "db")):
+        runner.rel_check(check, got, exp, runner.TOL_MATMUL, f"linear+bias {what} vs oracle")
+
+
 def test_split_k_weight_gradient_gemm(oracle):
     """x^T @ g with a small output and K = batch*tokens (the Linear weight gradient) runs as split-K: K-slices
     as a batch + an ordered sum (runtime/cuda/matmul.py).  Checked against float64 and, at a smaller K, the oracle."""
