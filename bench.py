@@ -340,7 +340,7 @@ def run_b200(args) -> None:
         print(f"step {tot:.2f} ms; generated-kernel launches {kt['launches'] / nsteps:.0f}/step {kt['ms'] / nsteps:.2f} ms; "
               f"matmul launches {mt['launches'] / nsteps:.0f}/step {mt['ms'] / nsteps:.2f} ms")
         for tag, v in sorted(kt["by_tag"].items(), key=lambda kv: -kv[1][1]):
-            print(f"  {tag[0]:24s} n/step={v[0] / nsteps:7.1f}  ms/step={v[1] / nsteps:8.3f}  avg_us={1e3 * v[1] / v[0]:8.1f}")
+            print(f"  {tag[0]:24s} out_MB={tag[1] / 1e6:8.2f} n/step={v[0] / nsteps:7.1f}  ms/step={v[1] / nsteps:8.3f}  avg_us={1e3 * v[1] / v[0]:8.1f}")
         for tag, v in sorted(mt["by_tag"].items(), key=lambda kv: -kv[1][1]):
             print(f"  mm {tag}  n/step={v[0] / nsteps:6.1f}  ms/step={v[1] / nsteps:7.3f}  TF/s={v[2] / (v[1] * 1e-3) / 1e12:7.1f}")
         return

@@ -695,13 +695,19 @@ def pick_bn_ts(M: int, N: int, batch: int, kblocks: int) -> int:
 @cache
 def matmul_tc_ts(M: int, N: int, K: int, batch: int, a_mn: bool, b_mn: bool, a_bcast: bool, b_bcast: bool,
                  bn: int | None = None, stages: int | None = None, kc_blocks: int | None = None,
-                 bias: bool = False) -> TcKernel:
+                 bias: bool = False, mma_batch: int | None = None) -> TcKernel:
     """`bias`: the kernel takes a 5th parameter, a length-N row the epilogue adds to every output row (the
     Linear bias; it rides on the first K-chunk's store)."""
     import os
-    trace = os.environ.get("DLGRAD_TC_TRACE", "0") == "1"     # diagnostic: CTA 0 timestamps its first 32 k-blocks
+    tmode = os.environ.get("DLGRAD_TC_TRACE", "0")            # diagnostic: CTA 0 timestamps its first 32 k-blocks
+    trace = tmode in ("1", "2", "3")                          # 1 = one stamp per pipeline role, 2 = inside the MMA warp,
+                                                              # 3 = only kernel begin/end (clock64 + globaltimer -> SM clock)
     exp = os.environ.get("DLGRAD_TC_EXPERIMENT", "")          # diagnostic variants (wrong results): mma1, mma2, nobsplit
-    TR = (lambda kind, cond="true": f"if (blockIdx.x == 0u && it < 32u && {cond}) trace[{kind}][it] = clock64();") if trace else (lambda *a: "")
+
+    def stamp(kind, cond):
+        return f"if (blockIdx.x == 0u && it < 32u && {cond}) trace[{kind}][it] = clock64();"
+    TR = (lambda kind, cond="true": stamp(kind, cond)) if tmode == "1" else (lambda *a: "")
+    TM = (lambda kind, cond="lane == 0u": stamp(kind, cond)) if tmode == "2" else (lambda *a: "")
     kblocks = _cdiv(K, BK)
     kc = kc_blocks or (32 if kblocks > 64 else kblocks)       # K chunks of <= 1024, see matmul_tc_persistent
     nchunks = _cdiv(kblocks, kc)
@@ -718,6 +724,9 @@ def matmul_tc_ts(M: int, N: int, K: int, batch: int, a_mn: bool, b_mn: bool, a_b
     stages = min(stages, (512 - acc_bufs * BN) // 64)
     assert stages >= 2, (BN, stages)
     a_tmem0 = acc_bufs * BN
+    # k-blocks issued per commit group.  >1 was measured SLOWER on every shape (4096^3 bn128: 846 -> 982 clk per
+    # k-block with 2): releasing a stage one k-block later costs more than the issue bubble it hides.
+    G = max(1, min(mma_batch or int(os.environ.get("DLGRAD_TC_MMA_BATCH", "0")) or 1, stages - 1))
     tmem_cols = 32
     while tmem_cols < a_tmem0 + 64 * stages:
         tmem_cols *= 2
@@ -798,6 +807,7 @@ extern "C" __global__ void __launch_bounds__({nthreads}, 1)
     __shared__ unsigned tmem_slot;
     {"__shared__ long long trace[5][32];" if trace else ""}
     const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    {"if (blockIdx.x == 0u && threadIdx.x == 0u) { trace[0][0] = clock64(); unsigned long long g; asm volatile(\"mov.u64 %0, %%globaltimer;\" : \"=l\"(g)); trace[0][1] = (long long)g; }" if tmode == "3" else ""}
 
     if (threadIdx.x == 0) {{
         for (unsigned s = 0; s < {stages}u; ++s) {{
@@ -856,25 +866,40 @@ extern "C" __global__ void __launch_bounds__({nthreads}, 1)
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const unsigned tacc = tmem_base + b * {BN}u;
                     const unsigned kend = min((ch + 1u) * {kc}u, {kblocks}u);
-                    for (unsigned kb = ch * {kc}u, kbl = 0; kb < kend; ++kb, ++kbl, ++it) {{
-                        const unsigned s = it % {stages}u, ph = (it / {stages}u) & 1u;
-                        mbar_wait(split + s * 8u, ph);
-                        {TR(3, "lane == 0u")}
-                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                        const unsigned long long bdesc = bdesc0 + (unsigned long long)(s * {per_stage // 16}u);
-                        const unsigned a_hi = a_tmem + s * 64u, a_lo = a_hi + 32u;
+                    // {G} k-block(s) are issued before their commits.  The issuing thread stalls at a commit until the
+                    // queued MMAs have drained (measured: 12 MMAs issue in ~330 clk, then ~300 clk blocked), so the
+                    // wait / fence / descriptor set-up of the next k-block (~200 clk) runs with the tensor pipe empty.
+                    for (unsigned kb = ch * {kc}u, kbl = 0; kb < kend;) {{
+                        const unsigned n = min({G}u, kend - kb);
+                        #pragma unroll
+                        for (unsigned g = 0; g < {G}u; ++g) {{
+                            if (g < n) {{
+                                const unsigned s = (it + g) % {stages}u, ph = ((it + g) / {stages}u) & 1u;
+                                mbar_wait(split + s * 8u, ph);
+                                {TR(3, "lane == 0u && g == 0u")}
+                                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                                const unsigned long long bdesc = bdesc0 + (unsigned long long)(s * {per_stage // 16}u);
+                                const unsigned a_hi = a_tmem + s * 64u, a_lo = a_hi + 32u;
+                                if (elect_one()) {{
+                                    #pragma unroll
+                                    for (unsigned k = 0; k < {BK // 8}u; ++k) {{
+                                        const unsigned long long b_hi = bdesc + (unsigned long long)(k * {b_kstep}u);
+                                        umma_tf32_ts(tacc, a_lo + k * 8u, b_hi, {idesc}u, (kbl | g | k) != 0u);
+                                        {"" if exp in ("mma1",) else f"umma_tf32_ts(tacc, a_hi + k * 8u, b_hi + {b_tile // 16}ull, {idesc}u, 1u);"}
+                                        {"" if exp in ("mma1", "mma2") else f"umma_tf32_ts(tacc, a_hi + k * 8u, b_hi, {idesc}u, 1u);"}
+                                    }}
+                                }}
+                                __syncwarp();
+                            }}
+                        }}
                         if (elect_one()) {{
                             #pragma unroll
-                            for (unsigned k = 0; k < {BK // 8}u; ++k) {{
-                                const unsigned long long b_hi = bdesc + (unsigned long long)(k * {b_kstep}u);
-                                umma_tf32_ts(tacc, a_lo + k * 8u, b_hi, {idesc}u, (kbl | k) != 0u);
-                                {"" if exp in ("mma1",) else f"umma_tf32_ts(tacc, a_hi + k * 8u, b_hi + {b_tile // 16}ull, {idesc}u, 1u);"}
-                                {"" if exp in ("mma1", "mma2") else f"umma_tf32_ts(tacc, a_hi + k * 8u, b_hi, {idesc}u, 1u);"}
-                            }}
-                            umma_commit(empty + s * 8u);
+                            for (unsigned g = 0; g < {G}u; ++g)
+                                if (g < n) umma_commit(empty + ((it + g) % {stages}u) * 8u);
                         }}
                         __syncwarp();
                         {TR(4, "lane == 0u")}
+                        kb += n; kbl += n; it += n;
                     }}
                     if (elect_one()) umma_commit(tfull + b * 8u);
                     __syncwarp();
@@ -891,7 +916,7 @@ extern "C" __global__ void __launch_bounds__({nthreads}, 1)
                 mbar_wait(full + s * 8u, ph);
                 {TR(1, "threadIdx.x == 64u")}
                 const unsigned char* stage_gen = smem_gen + s * {per_stage}u;
-                float x[32];{a_read}
+                float x[32];{a_read if exp not in ("nosplit",) else "for (unsigned k = 0; k < 32u; ++k) x[k] = (float)k;"}
                 unsigned hi[32], lo[32];
                 #pragma unroll
                 for (unsigned k = 0; k < 32u; ++k) {{
@@ -919,7 +944,7 @@ extern "C" __global__ void __launch_bounds__({nthreads}, 1)
                 const float4* bsrc = reinterpret_cast<const float4*>(smem_gen + s * {per_stage}u + {a_tile}u);
                 float4* bdst = reinterpret_cast<float4*>(smem_gen + s * {per_stage}u + {a_tile + b_tile}u);
                 #pragma unroll 8
-                for (unsigned i = ctid; i < {0 if exp == "nobsplit" else b_tile // 16}u; i += 128u) {{
+                for (unsigned i = ctid; i < {0 if exp in ("nobsplit", "nosplit") else b_tile // 16}u; i += 128u) {{
                     const float4 v4 = bsrc[i];
                     float4 l4;
                     l4.x = v4.x - __uint_as_float(__float_as_uint(v4.x) & 0xffffe000u);
@@ -978,6 +1003,7 @@ extern "C" __global__ void __launch_bounds__({nthreads}, 1)
     }}
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    {"if (blockIdx.x == 0u && threadIdx.x == 0u) { trace[0][2] = clock64(); unsigned long long g; asm volatile(\"mov.u64 %0, %%globaltimer;\" : \"=l\"(g)); trace[0][3] = (long long)g; } __syncthreads();" if tmode == "3" else ""}
     {"if (blockIdx.x == 0u && threadIdx.x < 160u) reinterpret_cast<long long*>(C)[threadIdx.x] = (&trace[0][0])[threadIdx.x];" if trace else ""}
     if (warp == 1) {{
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "n"({tmem_cols}));

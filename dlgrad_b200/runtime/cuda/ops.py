@@ -68,7 +68,7 @@ class Plan:
         if timer is not None:
             t0 = timer.start()
             out = lib.dlg_plan_run(self.c, p0, p1, p2, p3, f0, f1, f2, f3)
-            timer.stop(t0, float(self.nbytes), (self.kernel.name,))
+            timer.stop(t0, float(self.nbytes), (self.kernel.name, self.nbytes))
         else:
             out = lib.dlg_plan_run(self.c, p0, p1, p2, p3, f0, f1, f2, f3)
         if out == NULL:
@@ -81,7 +81,7 @@ class Plan:
         if lib.dlg_plan_run_into(self.c, out, p0, p1, p2, p3, f0, f1, f2, f3) != 0:
             raise RuntimeError("kernel launch failed: " + shim.last_error())
         if timer is not None:
-            timer.stop(t0, 0.0, (self.kernel.name,))
+            timer.stop(t0, 0.0, (self.kernel.name, 0))
 
 
 # ------------------------------------------------------------------------------------------------

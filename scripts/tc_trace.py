@@ -10,7 +10,7 @@ Columns (cycles, relative to the producer's first TMA issue):
 import os
 import sys
 
-os.environ["DLGRAD_TC_TRACE"] = "1"
+os.environ.setdefault("DLGRAD_TC_TRACE", "1")
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np  # noqa: E402
 
@@ -26,7 +26,7 @@ a = rng.random((1, M, K), dtype=np.float32)
 b = rng.random((1, K, N), dtype=np.float32)
 plan = matmul_tc.try_build(M, N, K, (1, 1), (0, 0), (0, 0), False, False, True, bn=bn, stages=stages, force=True, kernel=kernel)
 da, db = transfer.upload_numpy(a), transfer.upload_numpy(b)
-for _ in range(3):
+for _ in range(int(os.environ.get("TC_TRACE_ITERS", "3"))):
     out = plan(da, db)
 shim.synchronize()
 if shim.COMPILE_ONLY:
@@ -34,6 +34,19 @@ if shim.COMPILE_ONLY:
 host = transfer.download(out, 320).view(np.int64).reshape(5, 32)
 t0 = host[0, 0]
 print(f"# {kernel} {M}x{N}x{K} bn{bn} stages={stages}")
+if os.environ["DLGRAD_TC_TRACE"] == "3":
+    cyc, ns = int(host[0, 2] - host[0, 0]), int(host[0, 3] - host[0, 1])
+    tiles = -(-M // 128) * -(-N // bn)
+    kbs = -(-tiles // 148) * -(-K // 32)
+    print(f"CTA0: {cyc} cycles in {ns} ns -> {cyc / ns * 1e3:.0f} MHz; {kbs} k-blocks -> {cyc / kbs:.0f} cycles / {ns / kbs:.0f} ns per k-block")
+    sys.exit(0)
+if os.environ["DLGRAD_TC_TRACE"] == "2":
+    print("  i     top   ready  issued  commit    sync | wait+fence issue12  commit syncwarp  loop(back to top)")
+    for i in range(32):
+        t = host[:, i] - t0
+        nxt = host[0, i + 1] - host[4, i] if i < 31 else 0
+        print(f"{i:3d} {t[0]:7d} {t[1]:7d} {t[2]:7d} {t[3]:7d} {t[4]:7d} | {t[1]-t[0]:6d} {t[2]-t[1]:10d} {t[3]-t[2]:8d} {t[4]-t[3]:7d} {nxt:6d}")
+    sys.exit(0)
 print("  i     tma    full   split     mma  commit | full-tma split-full mma-split  d(tma) d(commit)")
 for i in range(32):
     t = host[:, i] - t0
