@@ -677,8 +677,26 @@ _TS_PERIOD = {32: 0.75, 64: 0.82, 96: 0.92, 128: 1.0, 192: 1.364, 256: 2.03}
 _TS_EPILOGUE = {32: 0.3, 64: 0.5, 96: 0.9, 128: 1.2, 192: 2.5, 256: 3.5}
 
 
+def wants_streamk(M: int, N: int, K: int, batch: int, bn: int) -> bool:
+    """Stream-K pays when whole tiles leave a ragged last wave (2.59 waves of tiles cost 3 tile times) and K is
+    short.  Measured (scripts/tc_probe.py sk): 8192x768x768 219 -> 231 TFLOP/s, 8192x768x3072 239 -> 248;
+    but 4096^3 263 -> 247 and the batched attention GEMMs lose too — contiguous unit ranges spread the 148
+    CTAs over distant tiles and cost L2 reuse.  Inside the GPT step the gain was within run-to-run noise,
+    so the automatic choice is OFF unless DLGRAD_TC_STREAMK=1 (an explicit `streamk=True` always works)."""
+    import os
+    if os.environ.get("DLGRAD_TC_STREAMK", "0") != "1":
+        return False
+    tiles = _cdiv(M, BM) * _cdiv(N, bn) * batch
+    kblocks = _cdiv(K, BK)
+    if batch != 1 or tiles <= NUM_SMS or kblocks > 128 or kblocks < 8:
+        return False
+    waves = tiles / NUM_SMS
+    return _cdiv(tiles, NUM_SMS) / waves >= 1.12
+
+
 def pick_bn_ts(M: int, N: int, batch: int, kblocks: int) -> int:
-    """Column-tile width minimising (tiles per persistent CTA) x (k-blocks x period + epilogues)."""
+    """Column-tile width minimising (tiles per persistent CTA) x (k-blocks x period + epilogues); a shape that
+    will run stream-K recovers about half of its ragged last wave."""
     ntm = _cdiv(M, BM) * batch
     chunks = _cdiv(kblocks, 32) if kblocks > 64 else 1
     best, best_cost = 128, None
@@ -686,7 +704,10 @@ def pick_bn_ts(M: int, N: int, batch: int, kblocks: int) -> int:
         if cand > _cdiv(N, 32) * 32 and cand != 32:
             continue
         tiles = ntm * _cdiv(N, cand)
-        cost = _cdiv(tiles, NUM_SMS) * (kblocks * _TS_PERIOD[cand] + chunks * _TS_EPILOGUE[cand])
+        waves = float(_cdiv(tiles, NUM_SMS))
+        if wants_streamk(M, N, kblocks * BK, batch, cand):
+            waves = 0.5 * (waves + tiles / NUM_SMS)
+        cost = waves * (kblocks * _TS_PERIOD[cand] + chunks * _TS_EPILOGUE[cand])
         if best_cost is None or cost < best_cost * 0.999:
             best, best_cost = cand, cost
     return best
@@ -695,9 +716,17 @@ def pick_bn_ts(M: int, N: int, batch: int, kblocks: int) -> int:
 @cache
 def matmul_tc_ts(M: int, N: int, K: int, batch: int, a_mn: bool, b_mn: bool, a_bcast: bool, b_bcast: bool,
                  bn: int | None = None, stages: int | None = None, kc_blocks: int | None = None,
-                 bias: bool = False, mma_batch: int | None = None) -> TcKernel:
-    """`bias`: the kernel takes a 5th parameter, a length-N row the epilogue adds to every output row (the
-    Linear bias; it rides on the first K-chunk's store)."""
+                 bias: bool = False, mma_batch: int | None = None, streamk: bool = False) -> TcKernel:
+    """Kernel parameters after C: `bias` (a length-N row the epilogue adds to every output row when `bias` is
+    set — the Linear bias; it rides on the plain store) and `flags` (uint32[ntiles * 4], zero, used when
+    `streamk` is set).
+
+    streamk: instead of whole tiles round-robin, every CTA owns one CONTIGUOUS range of (tile, k-block) units
+    of equal length, so 2.59 waves of tiles cost 2.59 — not 3 — tile times.  A tile cut by a range boundary
+    is finished by two CTAs: the one holding its k-tail meets it FIRST in its range, stores the partial sum
+    and raises flags[tile][quarter]; the one holding its k-head meets it LAST, waits for the flag (long
+    since raised) and TMA-reduce-adds its partial.  Two addends in fixed roles -> the sum is deterministic.
+    Requires ntiles >= grid (every range at least one tile long, so no tile has three owners)."""
     import os
     tmode = os.environ.get("DLGRAD_TC_TRACE", "0")            # diagnostic: CTA 0 timestamps its first 32 k-blocks
     trace = tmode in ("1", "2", "3")                          # 1 = one stamp per pipeline role, 2 = inside the MMA warp,
@@ -738,6 +767,14 @@ def matmul_tc_ts(M: int, N: int, K: int, batch: int, a_mn: bool, b_mn: bool, a_b
     a_boxes = BM // 32 if a_mn else 1
     b_boxes = BN // 32 if b_mn else 1
     grid = min(ntiles, NUM_SMS)
+    units = ntiles * kblocks
+    if streamk:
+        assert ntiles >= grid and units < (1 << 30), (ntiles, grid)
+        seg_open = f"""for (unsigned u = u_begin, t, kb0, kb1; u < u_end; u += kb1 - kb0) {{
+            t = u / {kblocks}u; kb0 = u - t * {kblocks}u; kb1 = min({kblocks}u, kb0 + (u_end - u));"""
+    else:
+        seg_open = f"""for (unsigned t = blockIdx.x; t < {ntiles}u; t += {grid}u) {{
+            const unsigned kb0 = 0u, kb1 = {kblocks}u;"""
     nthreads = 64 + 128 + 128 + 128       # producer, MMA | 4 A-splitter warps | 4 B-splitter warps | 4 epilogue warps
     epi_w0 = 10
 
@@ -773,7 +810,7 @@ def matmul_tc_ts(M: int, N: int, K: int, batch: int, a_mn: bool, b_mn: bool, a_b
     lo_ops = ", ".join(f'"r"(lo[{i}])' for i in range(32))
 
     bias_code = "" if not bias else f"""
-                        if (ch == 0u) {{
+                        if (plain) {{
                             #pragma unroll
                             for (unsigned j = 0; j < 8u; ++j) {{
                                 const unsigned col = n0 + c * 32u + j * 4u;
@@ -786,6 +823,31 @@ def matmul_tc_ts(M: int, N: int, K: int, batch: int, a_mn: bool, b_mn: bool, a_b
                                 }}
                             }}
                         }}"""
+    if streamk:
+        sk_seg_begin = """const bool seg_head = kb0 == 0u && kb1 < %du;      // k-head of a tile shared with the next CTA
+            const bool seg_tail = kb0 != 0u;                      // k-tail of a tile shared with the previous CTA
+            unsigned* flag = flags + t * 4u + q;
+            if (seg_head) {
+                // the tail's partial was stored by the next CTA at the START of its range; then we add ours
+                if (lane == 0) {
+                    const long long t0 = clock64();
+                    unsigned f;
+                    do {
+                        asm volatile("ld.acquire.gpu.global.u32 %%0, [%%1];" : "=r"(f) : "l"(flag) : "memory");
+                        if (clock64() - t0 > 4000000000LL) __trap();
+                    } while (f == 0u);
+                    *flag = 0u;                                   // re-armed for the next launch
+                    asm volatile("fence.proxy.async;" ::: "memory");
+                }
+                __syncwarp();
+            }""" % kblocks
+        sk_seg_end = """if (seg_tail && lane == 0) {
+                asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");      // our stores have landed
+                asm volatile("fence.proxy.async;" ::: "memory");
+                asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(flag), "r"(1u) : "memory");
+            }"""
+    else:
+        sk_seg_begin, sk_seg_end = "const bool seg_head = false;", ""
     regs = ", ".join(f"%{i}" for i in range(32))
     outs = ", ".join(f'"=r"(v[{i}])' for i in range(32))
     stage_writes = "\n                    ".join(
@@ -795,7 +857,7 @@ def matmul_tc_ts(M: int, N: int, K: int, batch: int, a_mn: bool, b_mn: bool, a_b
 
     src = _HELPERS + _HELPERS_TS + f"""
 extern "C" __global__ void __launch_bounds__({nthreads}, 1)
-{KNAME}(const __grid_constant__ TMap tmA, const __grid_constant__ TMap tmB, const __grid_constant__ TMap tmC, float* __restrict__ C{", const float* __restrict__ bias" if bias else ""})
+{KNAME}(const __grid_constant__ TMap tmA, const __grid_constant__ TMap tmB, const __grid_constant__ TMap tmC, float* __restrict__ C, const float* __restrict__ bias, unsigned* __restrict__ flags)
 {{
     extern __shared__ unsigned char smem_raw[];
     const unsigned smem = (smem_u32(smem_raw) + 1023u) & ~1023u;        // swizzle atoms need 1024-byte alignment
@@ -807,6 +869,7 @@ extern "C" __global__ void __launch_bounds__({nthreads}, 1)
     __shared__ unsigned tmem_slot;
     {"__shared__ long long trace[5][32];" if trace else ""}
     const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    {f"const unsigned u_begin = (unsigned)(((unsigned long long)blockIdx.x * {units}ull) / {grid}ull), u_end = (unsigned)(((unsigned long long)(blockIdx.x + 1u) * {units}ull) / {grid}ull);" if streamk else ""}
     {"if (blockIdx.x == 0u && threadIdx.x == 0u) { trace[0][0] = clock64(); unsigned long long g; asm volatile(\"mov.u64 %0, %%globaltimer;\" : \"=l\"(g)); trace[0][1] = (long long)g; }" if tmode == "3" else ""}
 
     if (threadIdx.x == 0) {{
@@ -834,9 +897,9 @@ extern "C" __global__ void __launch_bounds__({nthreads}, 1)
         // ===== TMA producer: the warp walks the ring together, one elected lane issues =====
         {{
             unsigned it = 0;
-            for (unsigned t = blockIdx.x; t < {ntiles}u; t += {grid}u) {{
+            {seg_open}
                 {decode}
-                for (unsigned kb = 0; kb < {kblocks}u; ++kb, ++it) {{
+                for (unsigned kb = kb0; kb < kb1; ++kb, ++it) {{
                     const unsigned s = it % {stages}u, ph = (it / {stages}u) & 1u;
                     mbar_wait(empty + s * 8u, ph ^ 1u);
                     {TR(0, "lane == 0u")}
@@ -856,20 +919,20 @@ extern "C" __global__ void __launch_bounds__({nthreads}, 1)
         // ===== MMA issuer: the whole warp walks the loop, one elected lane issues.  A_lo*B_hi, A_hi*B_lo, A_hi*B_hi
         //       per 8-wide k step, A from TMEM =====
         {{
-            unsigned it = 0, u = 0;
+            unsigned it = 0, ua = 0;
             const unsigned long long bdesc0 = make_desc(smem + {a_tile}u, {b_lbo}u, {b_sbo}u, {b_lt}u);   // stage 0; a stage is {per_stage // 16} 16-byte units
             const unsigned a_tmem = tmem_base + {a_tmem0}u;
-            for (unsigned t = blockIdx.x; t < {ntiles}u; t += {grid}u) {{
-                for (unsigned ch = 0; ch < {nchunks}u; ++ch, ++u) {{
-                    const unsigned b = u % {acc_bufs}u;
-                    mbar_wait(tempty + b * 8u, ((u / {acc_bufs}u) & 1u) ^ 1u);       // epilogue has drained this accumulator
+            {seg_open}
+                for (unsigned cs = kb0; cs < kb1; cs += {kc}u, ++ua) {{
+                    const unsigned b = ua % {acc_bufs}u;
+                    mbar_wait(tempty + b * 8u, ((ua / {acc_bufs}u) & 1u) ^ 1u);      // epilogue has drained this accumulator
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const unsigned tacc = tmem_base + b * {BN}u;
-                    const unsigned kend = min((ch + 1u) * {kc}u, {kblocks}u);
+                    const unsigned kend = min(cs + {kc}u, kb1);
                     // {G} k-block(s) are issued before their commits.  The issuing thread stalls at a commit until the
                     // queued MMAs have drained (measured: 12 MMAs issue in ~330 clk, then ~300 clk blocked), so the
                     // wait / fence / descriptor set-up of the next k-block (~200 clk) runs with the tensor pipe empty.
-                    for (unsigned kb = ch * {kc}u, kbl = 0; kb < kend;) {{
+                    for (unsigned kb = cs, kbl = 0; kb < kend;) {{
                         const unsigned n = min({G}u, kend - kb);
                         #pragma unroll
                         for (unsigned g = 0; g < {G}u; ++g) {{
@@ -910,8 +973,8 @@ extern "C" __global__ void __launch_bounds__({nthreads}, 1)
         // ===== A-splitter warps: thread = A row = TMEM lane; A_hi and A_lo go straight to tensor memory =====
         const unsigned sq = warp & 3u;                         // the TMEM lane quarter this warp may write
         unsigned it = 0;
-        for (unsigned t = blockIdx.x; t < {ntiles}u; t += {grid}u) {{
-            for (unsigned kb = 0; kb < {kblocks}u; ++kb, ++it) {{
+        {seg_open}
+            for (unsigned kb = kb0; kb < kb1; ++kb, ++it) {{
                 const unsigned s = it % {stages}u, ph = (it / {stages}u) & 1u;
                 mbar_wait(full + s * 8u, ph);
                 {TR(1, "threadIdx.x == 64u")}
@@ -937,8 +1000,8 @@ extern "C" __global__ void __launch_bounds__({nthreads}, 1)
         // ===== B-splitter warps: B_lo = x - trunc_tf32(x) into the twin buffer (same swizzled layout, linear pass) =====
         const unsigned ctid = threadIdx.x - 192u;
         unsigned it = 0;
-        for (unsigned t = blockIdx.x; t < {ntiles}u; t += {grid}u) {{
-            for (unsigned kb = 0; kb < {kblocks}u; ++kb, ++it) {{
+        {seg_open}
+            for (unsigned kb = kb0; kb < kb1; ++kb, ++it) {{
                 const unsigned s = it % {stages}u, ph = (it / {stages}u) & 1u;
                 mbar_wait(full + s * 8u, ph);
                 const float4* bsrc = reinterpret_cast<const float4*>(smem_gen + s * {per_stage}u + {a_tile}u);
@@ -963,15 +1026,17 @@ extern "C" __global__ void __launch_bounds__({nthreads}, 1)
         const unsigned q = warp & 3u;                          // TMEM lane quarter this warp may read
         const unsigned my_epi = epi + (warp - {epi_w0}u) * {EPI_BUFS * 4096}u;
         unsigned char* my_epi_gen = smem_gen + {stages * per_stage}u + (warp - {epi_w0}u) * {EPI_BUFS * 4096}u;
-        unsigned u = 0, nstore = 0;
-        for (unsigned t = blockIdx.x; t < {ntiles}u; t += {grid}u) {{
+        unsigned ua = 0, nstore = 0;
+        {seg_open}
             {decode}
-            for (unsigned ch = 0; ch < {nchunks}u; ++ch, ++u) {{
-                const unsigned b = u % {acc_bufs}u;
-                mbar_wait(tfull + b * 8u, (u / {acc_bufs}u) & 1u);
+            {sk_seg_begin}
+            for (unsigned cs = kb0; cs < kb1; cs += {kc}u, ++ua) {{
+                const unsigned b = ua % {acc_bufs}u;
+                const bool plain = (cs == kb0) && !seg_head;       // this chunk STORES; every other one reduce-adds
+                mbar_wait(tfull + b * 8u, (ua / {acc_bufs}u) & 1u);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 // a later K-chunk is ADDED to what the earlier chunk stored: that store must have landed
-                if (ch != 0u && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+                if (cs != kb0 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
                 #pragma unroll 1
                 for (unsigned c = 0; c < {BN // 32}u; ++c) {{
                     unsigned v[32];
@@ -987,7 +1052,7 @@ extern "C" __global__ void __launch_bounds__({nthreads}, 1)
                         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                         __syncwarp();
                         if (lane == 0) {{
-                            if (ch == 0u) tma_store_3d(&tmC, my_epi + sb * 4096u, (int)(n0 + c * 32u), (int)(m0 + q * 32u), (int)z);
+                            if (plain) tma_store_3d(&tmC, my_epi + sb * 4096u, (int)(n0 + c * 32u), (int)(m0 + q * 32u), (int)z);
                             else tma_reduce_add_3d(&tmC, my_epi + sb * 4096u, (int)(n0 + c * 32u), (int)(m0 + q * 32u), (int)z);
                             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                         }}
@@ -998,6 +1063,7 @@ extern "C" __global__ void __launch_bounds__({nthreads}, 1)
                 __syncwarp();
                 if (lane == 0) mbar_arrive(tempty + b * 8u);        // accumulator b may be overwritten
             }}
+            {sk_seg_end}
         }}
         if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }}
@@ -1010,7 +1076,7 @@ extern "C" __global__ void __launch_bounds__({nthreads}, 1)
     }}
 }}
 """
-    return TcKernel("mm_tcts_b" if bias else "mm_tcts", src, (grid, 1, 1), nthreads, smem, batch * M * N, BN, stages)
+    return TcKernel("mm_tcts" + ("_b" if bias else "") + ("_sk" if streamk else ""), src, (grid, 1, 1), nthreads, smem, batch * M * N, BN, stages)
 
 
 # =====================================================================================================

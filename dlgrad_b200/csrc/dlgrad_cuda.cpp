@@ -523,26 +523,26 @@ void *dlg_mm_plan_create(void *fn, unsigned gx, unsigned gy, unsigned gz, unsign
     return p;
 }
 
-static int mm_launch(MMPlan *p, void *c, const void *a, const void *b, const void *aux) {
+static int mm_launch(MMPlan *p, void *c, const void *a, const void *b, const void *aux0, void *aux1) {
     alignas(64) CUtensorMap ta, tb, tc;
     if (int r = encode_tmap(&ta, p->a, a)) return r;
     if (int r = encode_tmap(&tb, p->b, b)) return r;
     if (int r = encode_tmap(&tc, p->c, c)) return r;
-    void *args[5] = {&ta, &tb, &tc, &c, &aux};      // kernels without an aux parameter ignore the 5th slot
+    void *args[6] = {&ta, &tb, &tc, &c, &aux0, &aux1};      // kernels with four parameters ignore the rest
     unsigned block[3] = {p->threads, 1, 1};
     g_status = 0;
     return launch_ex(p->fn, p->grid, block, p->smem, p->cluster_x, args);
 }
 
 int dlg_mm_plan_run_into(void *plan, void *c, const void *a, const void *b) {
-    return mm_launch((MMPlan *)plan, c, a, b, nullptr);
+    return mm_launch((MMPlan *)plan, c, a, b, nullptr, nullptr);
 }
 
-void *dlg_mm_plan_run_aux(void *plan, const void *a, const void *b, const void *aux) {
+void *dlg_mm_plan_run_aux(void *plan, const void *a, const void *b, const void *aux0, void *aux1) {
     MMPlan *p = (MMPlan *)plan;
     void *c = dlg_alloc(p->out_bytes);
     if (!c) return nullptr;
-    if (mm_launch(p, c, a, b, aux) != 0) {
+    if (mm_launch(p, c, a, b, aux0, aux1) != 0) {
         dlg_free(c);
         return nullptr;
     }
@@ -550,7 +550,7 @@ void *dlg_mm_plan_run_aux(void *plan, const void *a, const void *b, const void *
 }
 
 void *dlg_mm_plan_run(void *plan, const void *a, const void *b) {
-    return dlg_mm_plan_run_aux(plan, a, b, nullptr);
+    return dlg_mm_plan_run_aux(plan, a, b, nullptr, nullptr);
 }
 
 // ---- events / graphs -----------------------------------------------------------------

@@ -60,7 +60,7 @@ def qualifies(M, N, K, batch, a_bs, b_bs, tx, ty, aligned, force: bool = False) 
 
 def try_build(M, N, K, batch, a_bs, b_bs, tx, ty, aligned, passes: int | None = None, bn: int | None = None,
               stages: int | None = None, hi_inplace: bool = False, force: bool = False, kernel: str | None = None,
-              split_warps: int | None = None, bias: bool = False):
+              split_warps: int | None = None, bias: bool = False, streamk: bool | None = None):
     """`bias=True` builds the variant whose epilogue adds a length-N row (only the TS kernel has one; None otherwise)."""
     q = qualifies(M, N, K, batch, a_bs, b_bs, tx, ty, aligned, force)
     if q is None:
@@ -69,6 +69,7 @@ def try_build(M, N, K, batch, a_bs, b_bs, tx, ty, aligned, passes: int | None = 
     passes = passes or PASSES
     cluster = 1
     b_rows = None
+    flags = None
     which = kernel or KERNEL
     if which == "auto":
         # A-in-TMEM beats both shared-memory-operand kernels on every shape of scripts/tc_probe.py perf/perf4
@@ -81,6 +82,11 @@ def try_build(M, N, K, batch, a_bs, b_bs, tx, ty, aligned, passes: int | None = 
         cluster, b_rows = 2, k.bn // 2
     elif which == "v4" and passes == 3:
         k = tc.matmul_tc_ts(M, N, K, nb, a_mn, b_mn, a_bc, b_bc, bn, stages, None, bias)
+        sk = tc.wants_streamk(M, N, K, nb, k.bn) if streamk is None else streamk
+        if sk:
+            k = tc.matmul_tc_ts(M, N, K, nb, a_mn, b_mn, a_bc, b_bc, k.bn, stages, None, bias, None, True)
+            ntiles = -(-M // 128) * -(-N // k.bn) * nb
+            flags = shim.calloc(ntiles * 16)              # uint32[ntiles][4], re-armed by the kernel itself
     elif which == "v1":
         k = tc.matmul_tc(M, N, K, nb, a_mn, b_mn, a_bc, b_bc, passes, bn, stages, hi_inplace)
     else:
@@ -96,9 +102,11 @@ def try_build(M, N, K, batch, a_bs, b_bs, tx, ty, aligned, passes: int | None = 
         raise RuntimeError("dlg_mm_plan_create failed: " + shim.last_error())
     nbytes = k.out_elems * 4
 
-    if bias:
-        def run(a, b, aux):
-            out = lib.dlg_mm_plan_run_aux(plan, a, b, aux)
+    if bias or flags is not None:
+        fl = NULL if flags is None else flags
+
+        def run(a, b, aux=NULL):
+            out = lib.dlg_mm_plan_run_aux(plan, a, b, aux, fl)
             if out == NULL:
                 raise RuntimeError("tensor-core matmul launch failed: " + shim.last_error())
             return shim.own(out, nbytes)
@@ -108,6 +116,5 @@ def try_build(M, N, K, batch, a_bs, b_bs, tx, ty, aligned, passes: int | None = 
             if out == NULL:
                 raise RuntimeError("tensor-core matmul launch failed: " + shim.last_error())
             return shim.own(out, nbytes)
-
     from dlgrad_b200.runtime.cuda.matmul import MatmulPlan
     return MatmulPlan(run, 2.0 * nb * M * N * K, (f"tc{passes}", M, N, K, nb))

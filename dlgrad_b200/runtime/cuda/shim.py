@@ -100,7 +100,7 @@ class _CompileOnlyLib:
         self.launches += 1
         return self._addr(int(ffi.cast("uintptr_t", plan)) - 1)
     def dlg_mm_plan_run_into(self, plan, c, a, b): self.launches += 1; return 0
-    def dlg_mm_plan_run_aux(self, plan, a, b, aux): return self.dlg_mm_plan_run(plan, a, b)
+    def dlg_mm_plan_run_aux(self, plan, a, b, aux0, aux1): return self.dlg_mm_plan_run(plan, a, b)
     def dlg_event_create(self): return ffi.cast("void *", 1)
     def dlg_event_record(self, e): return 0
     def dlg_event_sync(self, e): return 0
@@ -179,6 +179,16 @@ def alloc(nbytes: int):
     if _state["device"] is None:
         init()
     p = lib.dlg_alloc(nbytes)
+    if p == NULL:
+        raise MemoryError(f"Failed to allocate {nbytes} bytes of device memory: {last_error()}")
+    return own(p, nbytes)
+
+
+def calloc(nbytes: int):
+    """Zero-filled device storage (dlg_calloc), owned like alloc()."""
+    if _state["device"] is None:
+        init()
+    p = lib.dlg_calloc(nbytes)
     if p == NULL:
         raise MemoryError(f"Failed to allocate {nbytes} bytes of device memory: {last_error()}")
     return own(p, nbytes)

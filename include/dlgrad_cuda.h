@@ -104,9 +104,10 @@ void *dlg_mm_plan_create(void *fn, unsigned gx, unsigned gy, unsigned gz, unsign
                          const dlg_tmap_desc *a, const dlg_tmap_desc *b, const dlg_tmap_desc *c);
 void *dlg_mm_plan_run(void *plan, const void *a, const void *b);            /* returns C     */
 int   dlg_mm_plan_run_into(void *plan, void *c, const void *a, const void *b);
-/* same, with an auxiliary operand handed to the kernel as its 5th parameter: the bias row that the
- * epilogue of a Linear GEMM adds (replaces the separate broadcast ADD of dlgrad/tensor.py:534) */
-void *dlg_mm_plan_run_aux(void *plan, const void *a, const void *b, const void *aux);
+/* same, with two auxiliary operands handed to the kernel as its 5th and 6th parameters: `aux0` = the bias
+ * row that the epilogue of a Linear GEMM adds (replaces the separate broadcast ADD of
+ * dlgrad/tensor.py:534), `aux1` = the zeroed flag workspace of a stream-K plan.  Either may be NULL. */
+void *dlg_mm_plan_run_aux(void *plan, const void *a, const void *b, const void *aux0, void *aux1);
 
 /* ---- timing / graphs -----------------------------------------------------------------*/
 void *dlg_event_create(void);

@@ -16,7 +16,7 @@ results = {}
 
 
 def run(M, N, K, nb=1, tx=False, ty=False, a_b=False, b_b=False, passes=3, bn=None, stages=None, hi_inplace=False,
-        a=None, b=None, time_it=0, kernel=None, split_warps=None):
+        a=None, b=None, time_it=0, kernel=None, split_warps=None, streamk=None):
     batch = (1, nb)
     if a is None:
         a = (rng.random(((1 if a_b else nb), K, M) if tx else ((1 if a_b else nb), M, K), dtype=np.float32) - 0.5).astype(np.float32)
@@ -25,7 +25,7 @@ def run(M, N, K, nb=1, tx=False, ty=False, a_b=False, b_b=False, passes=3, bn=No
     a_bs = (0, 0) if (a_b or nb == 1) else (0, M * K)
     b_bs = (0, 0) if (b_b or nb == 1) else (0, K * N)
     plan = matmul_tc.try_build(M, N, K, batch, a_bs, b_bs, tx, ty, True, passes=passes, bn=bn, stages=stages,
-                               hi_inplace=hi_inplace, force=True, kernel=kernel, split_warps=split_warps)
+                               hi_inplace=hi_inplace, force=True, kernel=kernel, split_warps=split_warps, streamk=streamk)
     assert plan is not None, "shape did not qualify"
     da, db = transfer.upload_numpy(a), transfer.upload_numpy(b)
     out = plan(da, db)
@@ -125,6 +125,27 @@ if which in ("all", "v4"):
          a=np.random.default_rng(5).random((1, 4096, 4096), dtype=np.float32), b=np.random.default_rng(6).random((1, 4096, 4096), dtype=np.float32))
     case("v4 TN 768x3072x8192 accuracy U[0,1)", M=768, N=3072, K=8192, tx=True, kernel="v4",
          a=np.random.default_rng(5).random((1, 8192, 768), dtype=np.float32), b=np.random.default_rng(6).random((1, 8192, 3072), dtype=np.float32))
+if which in ("all", "sk"):
+    # stream-K: ragged last wave, tiles cut between two CTAs; every operand-major combination, ragged edges, batch,
+    # K > 1024 (chunked accumulation inside each segment), then the launch repeated (flags must re-arm themselves)
+    case("sk NN 8192x768x768 bn128", M=8192, N=768, K=768, kernel="v4", bn=128, streamk=True)
+    case("sk NT 8192x768x768 bn192", M=8192, N=768, K=768, ty=True, kernel="v4", bn=192, streamk=True)
+    case("sk TN 8192x768x768 bn128", M=8192, N=768, K=768, tx=True, kernel="v4", bn=128, streamk=True)
+    case("sk NN 8192x768x3072 bn128", M=8192, N=768, K=3072, kernel="v4", bn=128, streamk=True)
+    case("sk NN 5000x1000x1000 ragged", M=5000, N=1000, K=1000, kernel="v4", bn=128, streamk=True)
+    case("sk NN b96 1024x64x1024 bn64", M=1024, N=64, K=1024, nb=96, kernel="v4", bn=64, streamk=True)
+    case("sk TN b96 1024x64x1024 bn64", M=1024, N=64, K=1024, nb=96, tx=True, kernel="v4", bn=64, streamk=True)
+    case("sk NN 4096^3 U[0,1) bn128", M=4096, N=4096, K=4096, kernel="v4", bn=128, streamk=True,
+         a=np.random.default_rng(5).random((1, 4096, 4096), dtype=np.float32), b=np.random.default_rng(6).random((1, 4096, 4096), dtype=np.float32))
+    case("sk NN 8192x768x768 x20 launches", M=8192, N=768, K=768, kernel="v4", bn=128, streamk=True, time_it=20)
+    shapes = {"4096^3": dict(M=4096, N=4096, K=4096), "8192x768x768": dict(M=8192, N=768, K=768),
+              "8192x3072x768": dict(M=8192, N=3072, K=768), "8192x768x3072": dict(M=8192, N=768, K=3072),
+              "b96 QK^T 1024x1024x64": dict(M=1024, N=1024, K=64, nb=96), "b96 AV 1024x64x1024": dict(M=1024, N=64, K=1024, nb=96)}
+    for name, kw in shapes.items():
+        for bn in (64, 128, 192):
+            if bn <= kw["N"]:
+                for sk in (False, True):
+                    case(f"perf sk={int(sk)} bn{bn} {name}", time_it=10, bn=bn, kernel="v4", streamk=sk, **kw)
 if which in ("all", "perf4"):
     shapes = {"4096^3": dict(M=4096, N=4096, K=4096), "8192x768x768": dict(M=8192, N=768, K=768),
               "NT 8192x768x768": dict(M=8192, N=768, K=768, ty=True),

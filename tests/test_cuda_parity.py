@@ -537,6 +537,33 @@ def test_linear_bias_rides_on_gemm_epilogue(oracle, rows, in_f, out_f):
         runner.rel_check(check, got, exp, runner.TOL_MATMUL, f"linear+bias {what} vs oracle")
 
 
+@pytest.mark.parametrize("shape", [(8192, 768, 768, False, False, 128), (8192, 768, 768, False, True, 192),
+                                   (5000, 1000, 1000, False, False, 128), (4096, 640, 2304, True, False, 128)])
+def test_stream_k_matmul(shape):
+    """Opt-in stream-K schedule of the tensor-core GEMM (codegen/cuda_tcgen05.matmul_tc_ts, streamk=True): tiles cut
+    between two CTAs are combined by a flagged TMA reduce-add.  Checked against float64, and launched repeatedly:
+    the flag workspace re-arms itself, and the result must be bit-identical from launch to launch (two addends in
+    fixed roles)."""
+    from dlgrad_b200.runtime.cuda import matmul_tc, shim, transfer
+    M, N, K, tx, ty, bn = shape
+    rng = np.random.default_rng(M + N)
+    a = (rng.random((K, M) if tx else (M, K), dtype=np.float32) - 0.5).astype(np.float32)
+    b = (rng.random((N, K) if ty else (K, N), dtype=np.float32) - 0.5).astype(np.float32)
+    plan = matmul_tc.try_build(M, N, K, (1, 1), (0, 0), (0, 0), tx, ty, True, bn=bn, kernel="v4", streamk=True)
+    assert plan is not None
+    da, db = transfer.upload_numpy(a), transfer.upload_numpy(b)
+    outs = []
+    for _ in range(3):
+        out = plan(da, db)
+        shim.synchronize()
+        outs.append(transfer.download(out, M * N).reshape(M, N))
+    A = a.astype(np.float64).T if tx else a.astype(np.float64)
+    B = b.astype(np.float64).T if ty else b.astype(np.float64)
+    runner.rel_check(check, outs[0], A @ B, runner.TOL_MATMUL, "stream-K vs float64")
+    check(outs[1], outs[0], exact=True, what="stream-K relaunch 1 bit-identical")
+    check(outs[2], outs[0], exact=True, what="stream-K relaunch 2 bit-identical")
+
+
 def test_split_k_weight_gradient_gemm(oracle):
     """x^T @ g with a small output and K = batch*tokens (the Linear weight gradient) runs as split-K: K-slices
     as a batch + an ordered sum (runtime/cuda/matmul.py).  Checked against float64 and, at a smaller K, the oracle."""
