@@ -13,13 +13,13 @@ a, b = T(4096, 4096), T(4096, 4096)
 att = T(8, 12, 1024, 1024)
 mask = Tensor(np.triu(np.ones((1024, 1024), dtype=np.float32), 1), device="cuda")
 for _ in range(2):
-    y = lin(x)                                            # persistent 1-CTA tcgen05 matmul, (8192, 768, 768) NT
-    c = a @ b                                             # CTA-pair tcgen05 matmul, 4096^3
+    y = lin(x)                                            # persistent tcgen05 matmul, A in TMEM, (8192, 768, 768) NT
+    c = a @ b                                             # same kernel family, 4096^3
     s = a + b                                             # ewise
     r0 = a.sum(dim=0)                                     # strip column reduce (two passes)
     r1 = a.sum(dim=1)                                     # row reduce
     p = (att * 0.125).masked_fill(mask, float("-inf")).softmax(dim=3)   # fused scale+mask+softmax
-    t = a.T                                               # tiled transpose
+    t = a.permute((1, 0))                                 # tiled transpose (a.T alone is deferred into its consumer)
     _ = float(r1.sum().numpy())
 shim.synchronize()
 print("ok")
