@@ -14,6 +14,7 @@ from __future__ import annotations
 import hashlib
 import json
 import os
+import re
 import shutil
 import subprocess
 import tempfile
@@ -89,8 +90,28 @@ def _module(path: str):
     return m
 
 
+_ENTRY = re.compile(r'(extern "C" __global__ void[^{;]*\{)')
+_PDL_PROLOGUE = ('\n    // programmatic dependent launch: let the next kernel start its prologue now; touch global memory'
+                 '\n    // only after every earlier kernel on the stream has completed and flushed'
+                 '\n    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");'
+                 '\n    asm volatile("griddepcontrol.wait;" ::: "memory");')
+PDL = os.environ.get("DLGRAD_PDL", "1") != "0"
+
+
+def with_pdl_prologue(src: str) -> str:
+    """Insert the griddepcontrol pair at the top of the kernel (csrc/dlgrad_cuda.cpp launch_ex sets the
+    matching launch attribute).  Both are no-ops for a kernel launched without the attribute."""
+    if not PDL:
+        return src
+    out, n = _ENTRY.subn(lambda m: m.group(1) + _PDL_PROLOGUE, src, count=1)
+    if n != 1:
+        raise RuntimeError("generated kernel without an extern \"C\" __global__ entry point")
+    return out
+
+
 def get_function(base: str, src: str):
     """Return the CUfunction for generated source `src` (function name placeholder = KNAME)."""
+    src = with_pdl_prologue(src)
     key = source_key(src)
     fn = _functions.get(key)
     if fn is not None:

@@ -6,6 +6,8 @@ import struct
 import numpy as np
 import pytest
 
+from tests.conftest import check
+
 from dlgrad_b200.nn import datasets
 
 
@@ -50,8 +52,9 @@ def test_mnist_on_device(tmp_path):
     tensors = datasets.mnist(device="cuda", root=str(tmp_path))
     assert [t.shape for t in tensors] == [(12, 784), (12, 1), (12, 784), (12, 1)]
     assert all(not t.requires_grad for t in tensors)
-    np.testing.assert_array_equal(tensors[0].numpy(), px.reshape(12, 784).astype(np.float32))
-    np.testing.assert_array_equal(tensors[3].numpy()[:, 0], lb.astype(np.float32))
+    check(tensors[0].numpy(), px.reshape(12, 784).astype(np.float32), exact=True, what="train images")
+    check(tensors[3].numpy()[:, 0], lb.astype(np.float32), exact=True, what="test labels")
     # usable by the hot path: a normalised batch through a matmul
     x = tensors[0] / 255.0
-    assert float((x @ x.T).numpy().max()) > 0
+    ref = px.reshape(12, 784).astype(np.float64) / 255.0
+    check((x @ x.T).numpy(), ref @ ref.T, rtol=1e-4, what="normalised batch through a matmul")
