@@ -716,7 +716,7 @@ def pick_bn_ts(M: int, N: int, batch: int, kblocks: int) -> int:
 @cache
 def matmul_tc_ts(M: int, N: int, K: int, batch: int, a_mn: bool, b_mn: bool, a_bcast: bool, b_bcast: bool,
                  bn: int | None = None, stages: int | None = None, kc_blocks: int | None = None,
-                 bias: bool = False, mma_batch: int | None = None, streamk: bool = False) -> TcKernel:
+                 bias: bool = False, issuers: int | None = None, streamk: bool = False) -> TcKernel:
     """Kernel parameters after C: `bias` (a length-N row the epilogue adds to every output row when `bias` is
     set — the Linear bias; it rides on the plain store) and `flags` (uint32[ntiles * 4], zero, used when
     `streamk` is set).
@@ -753,9 +753,10 @@ def matmul_tc_ts(M: int, N: int, K: int, batch: int, a_mn: bool, b_mn: bool, a_b
     stages = min(stages, (512 - acc_bufs * BN) // 64)
     assert stages >= 2, (BN, stages)
     a_tmem0 = acc_bufs * BN
-    # k-blocks issued per commit group.  >1 was measured SLOWER on every shape (4096^3 bn128: 846 -> 982 clk per
-    # k-block with 2): releasing a stage one k-block later costs more than the issue bubble it hides.
-    G = max(1, min(mma_batch or int(os.environ.get("DLGRAD_TC_MMA_BATCH", "0")) or 1, stages - 1))
+    # MMA-issuing warps.  Two help the narrow tiles, whose k-block is issue-bound (BN=64: 390 -> 335 ns per
+    # k-block); at BN >= 128 the k-block is bound by shared-memory traffic and a second issuer changes nothing
+    # (BN=128: 569 vs 546 ns, BN=192: 794 vs 818 ns).
+    NI = issuers or int(os.environ.get("DLGRAD_TC_ISSUERS", "0")) or (2 if BN <= 96 else 1)
     tmem_cols = 32
     while tmem_cols < a_tmem0 + 64 * stages:
         tmem_cols *= 2
@@ -775,7 +776,7 @@ def matmul_tc_ts(M: int, N: int, K: int, batch: int, a_mn: bool, b_mn: bool, a_b
     else:
         seg_open = f"""for (unsigned t = blockIdx.x; t < {ntiles}u; t += {grid}u) {{
             const unsigned kb0 = 0u, kb1 = {kblocks}u;"""
-    nthreads = 64 + 128 + 128 + 128       # producer, MMA | 4 A-splitter warps | 4 B-splitter warps | 4 epilogue warps
+    nthreads = 64 + 128 + 128 + 128 + (32 if NI == 2 else 0)   # producer, MMA | 4 A-split | 4 B-split | 4 epilogue | 2nd MMA issuer
     epi_w0 = 10
 
     def tma_issue(which, boxes, mn, tile_var, row0):
@@ -865,7 +866,7 @@ extern "C" __global__ void __launch_bounds__({nthreads}, 1)
     const unsigned epi = smem + {stages * per_stage}u;
     const unsigned bars = epi + {epi_bytes}u;
     const unsigned full = bars, empty = bars + {stages * 8}u, split = bars + {stages * 16}u;
-    const unsigned tfull = bars + {stages * 24}u, tempty = tfull + 16u;
+    const unsigned tfull = bars + {stages * 24}u, tempty = tfull + 16u, turn = tempty + 16u;
     __shared__ unsigned tmem_slot;
     {"__shared__ long long trace[5][32];" if trace else ""}
     const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
@@ -881,6 +882,7 @@ extern "C" __global__ void __launch_bounds__({nthreads}, 1)
         for (unsigned b = 0; b < 2u; ++b) {{
             mbar_init(tfull + b * 8u, 1u);
             mbar_init(tempty + b * 8u, 4u);
+            mbar_init(turn + b * 8u, 1u);
         }}
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }}
@@ -915,57 +917,51 @@ extern "C" __global__ void __launch_bounds__({nthreads}, 1)
                 }}
             }}
         }}
-    }} else if (warp == 1) {{
-        // ===== MMA issuer: the whole warp walks the loop, one elected lane issues.  A_lo*B_hi, A_hi*B_lo, A_hi*B_hi
-        //       per 8-wide k step, A from TMEM =====
+    }} else if (warp == 1{" || warp == 14" if NI == 2 else ""}) {{
+        // ===== MMA issuer(s): the whole warp walks the loop, one elected lane issues.  A_lo*B_hi, A_hi*B_lo, A_hi*B_hi
+        //       per 8-wide k step, A from TMEM.  The issuing thread blocks at tcgen05.commit until the MMAs it queued
+        //       have drained and then needs ~200 clk to re-arm (loop, try_wait, fence, descriptors); with two issuers
+        //       taking alternate k-blocks — `turn` barriers keep the issue order, hence the accumulation order,
+        //       fixed — one re-arms while the other's MMAs execute. =====
         {{
-            unsigned it = 0, ua = 0;
+            const unsigned me = (warp == 1u) ? 0u : 1u;
+            unsigned it = 0, ua = 0, mine = 0;
             const unsigned long long bdesc0 = make_desc(smem + {a_tile}u, {b_lbo}u, {b_sbo}u, {b_lt}u);   // stage 0; a stage is {per_stage // 16} 16-byte units
             const unsigned a_tmem = tmem_base + {a_tmem0}u;
             {seg_open}
                 for (unsigned cs = kb0; cs < kb1; cs += {kc}u, ++ua) {{
                     const unsigned b = ua % {acc_bufs}u;
-                    mbar_wait(tempty + b * 8u, ((ua / {acc_bufs}u) & 1u) ^ 1u);      // epilogue has drained this accumulator
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const unsigned tacc = tmem_base + b * {BN}u;
                     const unsigned kend = min(cs + {kc}u, kb1);
-                    // {G} k-block(s) are issued before their commits.  The issuing thread stalls at a commit until the
-                    // queued MMAs have drained (measured: 12 MMAs issue in ~330 clk, then ~300 clk blocked), so the
-                    // wait / fence / descriptor set-up of the next k-block (~200 clk) runs with the tensor pipe empty.
-                    for (unsigned kb = cs, kbl = 0; kb < kend;) {{
-                        const unsigned n = min({G}u, kend - kb);
-                        #pragma unroll
-                        for (unsigned g = 0; g < {G}u; ++g) {{
-                            if (g < n) {{
-                                const unsigned s = (it + g) % {stages}u, ph = ((it + g) / {stages}u) & 1u;
-                                mbar_wait(split + s * 8u, ph);
-                                {TR(3, "lane == 0u && g == 0u")}
-                                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                                const unsigned long long bdesc = bdesc0 + (unsigned long long)(s * {per_stage // 16}u);
-                                const unsigned a_hi = a_tmem + s * 64u, a_lo = a_hi + 32u;
-                                if (elect_one()) {{
-                                    #pragma unroll
-                                    for (unsigned k = 0; k < {BK // 8}u; ++k) {{
-                                        const unsigned long long b_hi = bdesc + (unsigned long long)(k * {b_kstep}u);
-                                        umma_tf32_ts(tacc, a_lo + k * 8u, b_hi, {idesc}u, (kbl | g | k) != 0u);
-                                        {"" if exp in ("mma1",) else f"umma_tf32_ts(tacc, a_hi + k * 8u, b_hi + {b_tile // 16}ull, {idesc}u, 1u);"}
-                                        {"" if exp in ("mma1", "mma2") else f"umma_tf32_ts(tacc, a_hi + k * 8u, b_hi, {idesc}u, 1u);"}
-                                    }}
-                                }}
-                                __syncwarp();
-                            }}
+                    for (unsigned kb = cs, kbl = 0; kb < kend; ++kb, ++kbl, ++it) {{
+                        if ({NI}u == 2u && (it & 1u) != me) continue;
+                        if (kbl == 0u) {{
+                            mbar_wait(tempty + b * 8u, ((ua / {acc_bufs}u) & 1u) ^ 1u);      // epilogue has drained this accumulator
+                            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                         }}
+                        const unsigned s = it % {stages}u, ph = (it / {stages}u) & 1u;
+                        mbar_wait(split + s * 8u, ph);
+                        {TR(3, "lane == 0u")}
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        const unsigned long long bdesc = bdesc0 + (unsigned long long)(s * {per_stage // 16}u);
+                        const unsigned a_hi = a_tmem + s * 64u, a_lo = a_hi + 32u;
+                        {"mbar_wait(turn + me * 8u, (mine & 1u) ^ (me ^ 1u));      // the k-block before mine has been issued" if NI == 2 else ""}
                         if (elect_one()) {{
                             #pragma unroll
-                            for (unsigned g = 0; g < {G}u; ++g)
-                                if (g < n) umma_commit(empty + ((it + g) % {stages}u) * 8u);
+                            for (unsigned k = 0; k < {BK // 8}u; ++k) {{
+                                const unsigned long long b_hi = bdesc + (unsigned long long)(k * {b_kstep}u);
+                                umma_tf32_ts(tacc, a_lo + k * 8u, b_hi, {idesc}u, (kbl | k) != 0u);
+                                {"" if exp in ("mma1",) else f"umma_tf32_ts(tacc, a_hi + k * 8u, b_hi + {b_tile // 16}ull, {idesc}u, 1u);"}
+                                {"" if exp in ("mma1", "mma2") else f"umma_tf32_ts(tacc, a_hi + k * 8u, b_hi, {idesc}u, 1u);"}
+                            }}
+                            {"mbar_arrive(turn + (me ^ 1u) * 8u);" if NI == 2 else ""}
+                            umma_commit(empty + s * 8u);
+                            if (kb + 1u == kend) umma_commit(tfull + b * 8u);      // in-order pipe: the other issuer's earlier MMAs are done too
                         }}
                         __syncwarp();
                         {TR(4, "lane == 0u")}
-                        kb += n; kbl += n; it += n;
+                        ++mine;
                     }}
-                    if (elect_one()) umma_commit(tfull + b * 8u);
-                    __syncwarp();
                 }}
             }}
         }}
@@ -1021,7 +1017,7 @@ extern "C" __global__ void __launch_bounds__({nthreads}, 1)
                 if (lane == 0) mbar_arrive(split + s * 8u);
             }}
         }}
-    }} else {{
+    }} else if (warp < 14u) {{
         // ===== epilogue warps: TMEM -> registers -> swizzled smem box -> TMA store =====
         const unsigned q = warp & 3u;                          // TMEM lane quarter this warp may read
         const unsigned my_epi = epi + (warp - {epi_w0}u) * {EPI_BUFS * 4096}u;
