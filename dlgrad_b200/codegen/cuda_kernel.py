@@ -870,6 +870,16 @@ def softmax_rows(kind: str, outer: int, R: int, aligned: bool = True, chain: tup
 
     def each(fmt):
         return " ".join(fmt.format(c=("." + c) if c else "") for c in comps)
+    load = "v[i] = __ldg(row + c); " + pre_body
+    if chain and chain[-1][0] == "mfill":
+        # The chain ends in a masked_fill: a vector whose lanes are ALL masked is the fill value whatever x
+        # holds, so x is not read there.  Under a causal mask that is the upper triangle of (B,h,T,T): a
+        # quarter of this kernel's HBM traffic.
+        k_last, (_, ps, fs, _, _) = len(chain) - 1, chain[-1]
+        allm = " && ".join(f"mk_{('.' + c) if c else ''} > 0.f" for c in comps)
+        fillv = f"make_float4(f{fs}, f{fs}, f{fs}, f{fs})" if V == 4 else f"f{fs}"
+        load = (f"const {VT} mk_ = __ldg(reinterpret_cast<const {VT}*>(p{ps} + moff{k_last}) + c); "
+                f"if ({allm}) {{ v[i] = {fillv}; }} else {{ {load} }}")
     if kind == "softmax":
         # e * (1/s): one reciprocal per row instead of a division per element (<= 1 ulp from e / s)
         final = each("v[i]{c} = v[i]{c} * inv_s;")
@@ -888,7 +898,7 @@ extern "C" __global__ void __launch_bounds__({BLOCK}) {KNAME}{SIG} {{
     #pragma unroll
     for (int i = 0; i < {per}; ++i) {{
         const unsigned c = lane + i * {T}u;
-        if (c < {nv}u) {{ v[i] = __ldg(row + c); {pre_body} {each("mx = (v[i]{c} > mx) ? v[i]{c} : mx;")} }}
+        if (c < {nv}u) {{ {load} {each("mx = (v[i]{c} > mx) ? v[i]{c} : mx;")} }}
     }}
     {_row_reduce_code(T, "mx", "({b} > {a}) ? {b} : {a}", "-3.402823466e+38f", "mx")}
     float s = 0.f;
@@ -933,9 +943,15 @@ def softmax_bwd_rows(kind: str, outer: int, R: int, aligned: bool = True, chain:
 
     def each(fmt):
         return " ".join(fmt.format(c=("." + c) if c else "") for c in comps)
+    gload = "g[i] = __ldg(grow + c);"
     if kind == "softmax":
         accum = each("d += g[i]{c} * y[i]{c};")
         final = each("g[i]{c} = y[i]{c} * (g[i]{c} - d);")
+        # where y is exactly 0 in all lanes of a vector (masked attention scores: exp(-inf)), g only ever
+        # meets a factor 0: it is not read.  Under a causal mask that is half of g.
+        allz = " && ".join(f"y[i]{('.' + c) if c else ''} == 0.f" for c in comps)
+        zero = "make_float4(0.f, 0.f, 0.f, 0.f)" if V == 4 else "0.f"
+        gload = f"if ({allz}) {{ g[i] = {zero}; }} else {{ g[i] = __ldg(grow + c); }}"
     else:
         accum = each("d += g[i]{c};")
         final = each("g[i]{c} = g[i]{c} - expf(y[i]{c}) * d;")
@@ -952,7 +968,7 @@ extern "C" __global__ void __launch_bounds__({BLOCK}) {KNAME}{SIG} {{
     #pragma unroll
     for (int i = 0; i < {per}; ++i) {{
         const unsigned c = lane + i * {T}u;
-        if (c < {nv}u) {{ y[i] = __ldg(yrow + c); g[i] = __ldg(grow + c); {accum} }}
+        if (c < {nv}u) {{ y[i] = __ldg(yrow + c); {gload} {accum} }}
     }}
     {_row_reduce_code(T, "d", "{a} + {b}", "0.f", "d")}
     if (!live) return;
