@@ -62,7 +62,7 @@ def load_traffic():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled every 100 ms while the timed regions (A and B, the same load) run."""
 
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -74,7 +74,7 @@ class ClockSampler:
     def __enter__(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except OSError:
@@ -350,13 +350,13 @@ def run_b200(args) -> None:
     barrier()
     launches0 = cuda_ops.launch_count()
     profile.matmul_timer = profile.KernelTimer()
-    with ClockSampler(local) as clocks:
-        e0 = profile.Event().record()
-        for i in range(args.steps):
-            loss = train_step(gpt, opt, params, *dev_batches[i % 4], world)
-        e1 = profile.Event().record()
-        e1.sync()
-        barrier()
+    clocks = ClockSampler(local).__enter__()          # keeps sampling through region B; closed after it
+    e0 = profile.Event().record()
+    for i in range(args.steps):
+        loss = train_step(gpt, opt, params, *dev_batches[i % 4], world)
+    e1 = profile.Event().record()
+    e1.sync()
+    barrier()
     mm = profile.matmul_timer.collect()
     profile.matmul_timer = None
     ms_a = e1.ms_since(e0)
@@ -375,6 +375,12 @@ def run_b200(args) -> None:
     barrier()
     ms_b = e1.ms_since(e0)
     io = transfer.counters()
+    if not clocks.rows:                               # a very short run: keep the load up until one sample exists
+        t_end = time.perf_counter() + 1.5
+        fill = Tensor(np.ones((2048, 2048), dtype=np.float32), device="cuda")
+        while not clocks.rows and time.perf_counter() < t_end:      # rank-local load only: no collective in here
+            _ = float((fill @ fill).sum().numpy())
+    clocks.__exit__(None, None, None)
 
     if dist is not None:      # max over ranks; launches summed over ranks
         import torch
