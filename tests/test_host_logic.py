@@ -1,0 +1,137 @@
+"""Host-side logic that needs no GPU: shape rules (dlgrad/helpers.py), the dispatcher contract
+(dlgrad/dispatch.py:19-34), Tensor argument checking (dlgrad/tensor.py:100-123) and the matmul planner's
+geometry / tile / split-K decisions."""
+import numpy as np
+import pytest
+
+from dlgrad_b200 import Tensor
+from dlgrad_b200.codegen import cuda_tcgen05 as tc
+from dlgrad_b200.device import Device
+from dlgrad_b200.dispatch import Dispatcher
+from dlgrad_b200.helpers import (BinaryOps, broadcast_shapes, cal_sum_max_out_shape, calculate_stride, check_broadcast,
+                                 get_broadcast_shape, get_broadcast_strides_2)
+
+
+def test_strides_and_broadcast_shapes():
+    assert calculate_stride((2, 3, 4)) == (12, 4, 1)
+    assert calculate_stride(()) == ()
+    assert get_broadcast_shape((2, 1, 4), (3, 1)) == (2, 3, 4)
+    assert get_broadcast_strides_2((2, 3, 4), (3, 1), (1, 1)) == (0, 1, 0)
+    with pytest.raises(ValueError):
+        get_broadcast_shape((2, 3), (4, 3))
+    with pytest.raises(AssertionError, match="Cannot broadcast"):
+        check_broadcast((2, 3), (4, 3))
+    assert check_broadcast((2, 3), (1, 3))
+
+
+def test_matmul_rank_alignment_and_errors():
+    p1, p2, out = broadcast_shapes((4, 5), (2, 3, 5, 6))
+    assert (p1, p2, out) == ((1, 1, 4, 5), (2, 3, 5, 6), (2, 3, 4, 6))
+    with pytest.raises(ValueError, match="inner dims"):
+        broadcast_shapes((4, 5), (6, 7))
+    with pytest.raises(ValueError, match="batch dims"):
+        broadcast_shapes((2, 4, 5), (3, 5, 6))
+
+
+def test_reduce_out_shape_quirk():
+    # dim == -1 means "all"; with keepdim the reference returns the INPUT shape there
+    assert cal_sum_max_out_shape(3, -1, (2, 3, 4)) == ()
+    assert cal_sum_max_out_shape(3, -1, (2, 3, 4), keepdim=True) == (2, 3, 4)
+    assert cal_sum_max_out_shape(3, 1, (2, 3, 4)) == (2, 4)
+    assert cal_sum_max_out_shape(3, 1, (2, 3, 4), keepdim=True) == (2, 1, 4)
+
+
+def test_dispatcher_contract():
+    d = Dispatcher()
+    d.register(BinaryOps.ADD, Device.CPU)(lambda x, y: ("first", x + y))     # (the reference's decorator returns None;
+    # this one hands the function back so that runtime ops can call each other by name)
+    assert d.dispatch(op=BinaryOps.ADD, device=Device.CPU, x=1, y=2) == ("first", 3)
+    d.register(BinaryOps.ADD, Device.CPU)(lambda x, y: ("second", x + y))
+    assert d.dispatch(op=BinaryOps.ADD, device=Device.CPU, x=1, y=2)[0] == "second"      # last registration wins
+    assert d.has(BinaryOps.ADD, Device.CPU) and not d.has(BinaryOps.MUL, Device.CPU)
+    with pytest.raises(Exception):
+        d.dispatch(op=BinaryOps.MUL, device=Device.CPU, x=1, y=2)
+
+
+def test_tensor_argument_checks():
+    with pytest.raises(ValueError, match="float32"):
+        Tensor(np.zeros((2, 2), dtype=np.float64))
+    with pytest.raises(ValueError, match="4D"):
+        Tensor(np.zeros((1, 1, 1, 1, 2), dtype=np.float32))
+    with pytest.raises(ValueError):
+        Tensor("nope")
+    t = Tensor(np.arange(6, dtype=np.float32).reshape(2, 3))
+    assert t.shape == (2, 3) and t.ndim == 2 and t.numel == 6 and t.nbytes == 24
+    with pytest.raises(ValueError, match="Buffer size mismatch"):
+        t.copy_from(b"\0" * 8)
+    with pytest.raises(ValueError, match="Cannot reshape"):
+        t.data.reshape((4, 2))
+    assert t.data.reshape((3, -1)).shape == (3, 2)
+    np.testing.assert_array_equal(Tensor(np.ascontiguousarray(np.arange(6, dtype=np.float32).reshape(2, 3).T)).numpy(),
+                                  np.arange(6, dtype=np.float32).reshape(2, 3).T)
+
+
+def test_host_scalar_and_views_need_no_runtime():
+    s = Tensor(2.5)
+    assert s.shape == () and float(s.numpy()) == 2.5
+    t = Tensor(np.arange(24, dtype=np.float32).reshape(2, 3, 4))
+    b = t.data
+    b.unsqueeze(0)
+    assert b.shape == (1, 2, 3, 4)
+    b.squeeze(0)
+    assert b.shape == (2, 3, 4)
+    with pytest.raises(AssertionError):
+        b.unsqueeze([1, 1])
+
+
+@pytest.mark.parametrize("M,N,K,nb", [(4096, 4096, 4096, 1), (8192, 768, 768, 1), (8192, 96, 768, 1), (1024, 64, 1024, 96),
+                                      (200, 96, 72, 1), (64, 1024, 1024, 96), (8192, 768, 96, 1), (2048, 128, 128, 1)])
+def test_tile_width_choice_is_legal(M, N, K, nb):
+    kblocks = -(-K // 32)
+    bn = tc.pick_bn_ts(M, N, nb, kblocks)
+    assert bn in (32, 64, 96, 128, 192, 256) and bn % 16 == 0
+    assert bn <= max(32, -(-N // 32) * 32)
+    k = tc.matmul_tc_ts(M, N, K, nb, False, True, False, False)
+    assert k.bn == bn and 2 <= k.stages <= 6 and k.smem <= 227 * 1024 and k.grid[0] <= 148
+    # TMEM budget: accumulator buffers + 64 columns per ring stage never exceed the 512 columns of an SM
+    acc = 2 * bn if 2 * bn + 64 * min(k.stages, 3) <= 512 else bn
+    assert acc + 64 * k.stages <= 512
+    assert k.out_elems == nb * M * N
+
+
+def test_matmul_geometry_and_split_k():
+    from dlgrad_b200.runtime.cuda import matmul as mm
+    M, N, K, batch, a_bs, b_bs, nd = mm._geometry((8, 12, 1024, 64), (8, 12, 64, 1024), False, False)
+    assert (M, N, K, batch) == (1024, 1024, 64, (8, 12)) and a_bs == (12 * 1024 * 64, 1024 * 64)
+    M, N, K, batch, a_bs, b_bs, nd = mm._geometry((8192, 768), (8192, 3072), True, False)       # x^T @ g
+    assert (M, N, K) == (768, 3072, 8192) and batch == (1, 1)
+    M, N, K, batch, a_bs, b_bs, nd = mm._geometry((4, 5, 6), (1, 6, 7), False, False)           # broadcast batch
+    assert batch == (1, 4) and b_bs == (0, 0)
+    with pytest.raises(ValueError):
+        mm._geometry((4, 5), (6, 7), False, False)
+    assert mm._split_k(768, 768, 8192, (1, 1), True, False) == 4          # Linear dW: 36 tiles -> 4 K-slices
+    assert mm._split_k(768, 3072, 8192, (1, 1), True, False) == 1         # 144 tiles already fill the GPU
+    assert mm._split_k(768, 768, 8192, (1, 1), False, False) == 1         # only the TN form has K as a batch axis
+    assert mm._split_k(768, 768, 512, (1, 1), True, False) == 1
+
+
+def test_stream_k_is_opt_in(monkeypatch):
+    monkeypatch.delenv("DLGRAD_TC_STREAMK", raising=False)
+    assert tc.wants_streamk(8192, 768, 768, 1, 128) is False
+    monkeypatch.setenv("DLGRAD_TC_STREAMK", "1")
+    assert tc.wants_streamk(8192, 768, 768, 1, 128) is True               # 2.59 waves of tiles
+    assert tc.wants_streamk(8192, 3072, 768, 1, 192) is False             # 6.92 waves: nothing to recover
+    assert tc.wants_streamk(1024, 64, 1024, 96, 64) is False              # batched: measured slower
+    k = tc.matmul_tc_ts(8192, 768, 768, 1, False, True, False, False, bn=128, streamk=True)
+    assert "flags + t * 4u + q" in k.source and k.name.endswith("_sk")
+
+
+def test_every_kernel_gets_the_dependent_launch_prologue():
+    from dlgrad_b200.codegen import cuda_kernel as ck
+    from dlgrad_b200.runtime.cuda import compiler
+    for k in (ck.ewise("v0 + v1", (64, 64), ((64, 1), (64, 1)), True, "add"), tc.matmul_tc_ts(256, 256, 128, 1, False, True, False, False)):
+        src = compiler.with_pdl_prologue(k.source)
+        body = src[src.index('extern "C" __global__'):]
+        first = body[body.index("{") + 1:]
+        assert first.lstrip().startswith("//") and "griddepcontrol.launch_dependents" in first[:400]
+        assert first.index("griddepcontrol.wait") < first.index("blockIdx") if "blockIdx" in first else True
