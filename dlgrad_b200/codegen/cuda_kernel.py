@@ -1005,6 +1005,32 @@ extern "C" __global__ void __launch_bounds__(256) {KNAME}{SIG} {{
     return Kernel("ce_grad", src, (_cdiv(total, 256), 1, 1), (256, 1, 1), 0, total)
 
 
+@cache
+def cat2(outer: int, la: int, lb: int, aligned: bool = True) -> Kernel:
+    """Concatenation of two tensors along one axis, seen as rows: out[o] = a[o] (la elements) ++ b[o] (lb
+    elements) for `outer` rows.  No reference kernel: examples/gpt.py appends to its KV cache with
+    np.concatenate on the host (:140-147), a D2H + H2D round trip per layer and token.  p0 = a, p1 = b."""
+    L = la + lb
+    total = outer * L
+    V = 4 if (aligned and la % 4 == 0 and lb % 4 == 0) else 1
+    T = "float4" if V == 4 else "float"
+    nv, lav, lv = total // V, la // V, L // V
+    grid = max(1, min(_cdiv(nv, 256), NUM_SMS * 8))
+    src = f"""
+extern "C" __global__ void __launch_bounds__(256) {KNAME}{SIG} {{
+    const {T}* a = reinterpret_cast<const {T}*>(p0);
+    const {T}* b = reinterpret_cast<const {T}*>(p1);
+    {T}* o = reinterpret_cast<{T}*>(out);
+    for (size_t i = (size_t)blockIdx.x * 256u + threadIdx.x; i < {nv}ull; i += (size_t)gridDim.x * 256u) {{
+        const size_t r = i / {lv}u;
+        const unsigned j = (unsigned)(i - r * {lv}u);
+        o[i] = (j < {lav}u) ? __ldg(a + r * {lav}u + j) : __ldg(b + r * {lv - lav}u + (j - {lav}u));
+    }}
+}}
+"""
+    return Kernel("cat2", src, (grid, 1, 1), (256, 1, 1), 0, total)
+
+
 # ------------------------------------------------------------------------------------------------
 # optimizer steps (in place)
 # ------------------------------------------------------------------------------------------------

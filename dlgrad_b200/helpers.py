@@ -75,6 +75,7 @@ class CustomOps(Enum):
     SGD_STEP = auto()
     RMSNORM = auto()
     RMSNORM_BACKWARD = auto()
+    CAT = auto()              # concatenate two tensors along an axis (device-side KV-cache append)
 
 
 def prod_(x: Iterable) -> int:

@@ -70,6 +70,39 @@ class Transpose(OP):
         return (upstream_grad.transpose(self.dims[1], self.dims[0]),)
 
 
+class Cat(OP):
+    """Concatenate two tensors along `dim`.  An addition of the CUDA backend for the inference path: the
+    reference appends to its KV cache with np.concatenate on the host (examples/gpt.py:140-147).  On CUDA it is
+    one kernel; on a host runtime it is the same numpy concatenation.  Backward hands each operand its slice of
+    the upstream gradient."""
+    def forward(self, x: Buffer, y: Buffer, dim: int) -> Buffer:
+        self.dim, self.xs, self.ys = dim, x.shape, y.shape
+        if x.shape[:dim] != y.shape[:dim] or x.shape[dim + 1:] != y.shape[dim + 1:]:
+            raise ValueError(f"Cannot concatenate {x.shape} and {y.shape} along dim {dim}")
+        out_shape = x.shape[:dim] + (x.shape[dim] + y.shape[dim],) + x.shape[dim + 1:]
+        dev = Buffer._route(x, y)
+        if dev is Device.CUDA:
+            from dlgrad_b200.helpers import CustomOps
+            return Buffer(dispatcher.dispatch(op=CustomOps.CAT, device=dev, x=x, y=y, dim=dim), out_shape, dev, x.dtype)
+        import numpy as np
+        return Buffer.from_numpy(np.ascontiguousarray(np.concatenate((x.numpy(), y.numpy()), axis=dim)))
+
+    def backward(self, upstream_grad: Buffer) -> tuple:
+        import numpy as np
+        g = upstream_grad.numpy()                       # inference-path op: the gradient split stays simple
+        n0 = self.xs[self.dim]
+        idx_a = tuple(slice(None) if d != self.dim else slice(0, n0) for d in range(len(self.xs)))
+        idx_b = tuple(slice(None) if d != self.dim else slice(n0, None) for d in range(len(self.xs)))
+        dev = upstream_grad.device
+
+        def up(a):
+            b = Buffer.from_numpy(np.ascontiguousarray(a))
+            if dev is Device.CUDA:
+                b._to_cuda()
+            return b
+        return (up(g[idx_a]) if self.req_grad[0] else None, up(g[idx_b]) if self.req_grad[1] else None)
+
+
 class Squeeze(OP):
     def forward(self, x: Buffer, dim: list[int] | int) -> Buffer:
         self.dim = dim

@@ -589,6 +589,22 @@ def permute(x: Buffer, order: tuple) -> CDataPtr:
 
 
 # ------------------------------------------------------------------------------------------------
+# concat (no reference kernel: examples/gpt.py:140-147 round-trips the KV cache through numpy)
+# ------------------------------------------------------------------------------------------------
+@dispatcher.register(CustomOps.CAT, CUDA)
+def cat(x: Buffer, y: Buffer, dim: int) -> CDataPtr:
+    xs, ys = x.metadata.shape, y.metadata.shape
+    outer = prod_(xs[:dim])
+    la, lb = prod_(xs[dim:]), prod_(ys[dim:])
+    ok = x.aligned and y.aligned
+    key = ("cat2", outer, la, lb, ok)
+    plan = _plans.get(key)
+    if plan is None:
+        plan = _plans[key] = Plan(ck.cat2(outer, la, lb, ok))
+    return plan.run(_dev_ptr(x), _dev_ptr(y))
+
+
+# ------------------------------------------------------------------------------------------------
 # matmul                                                      reference: cpu.py:505-602
 # ------------------------------------------------------------------------------------------------
 @dispatcher.register(BinaryOps.MATMUL, CUDA)

@@ -203,6 +203,19 @@ class Tensor:
         order[d0], order[d1] = order[d1], order[d0]
         return self.permute(tuple(order))
 
+    @staticmethod
+    def cat(tensors: "list[Tensor] | tuple", dim: int = 0) -> "Tensor":
+        """Concatenate along `dim` on the tensors' device (extension: the reference's scripts use
+        np.concatenate on host copies, examples/gpt.py:140-147)."""
+        tensors = list(tensors)
+        if not tensors:
+            raise ValueError("Tensor.cat needs at least one tensor")
+        out = tensors[0]
+        d = dim % out.ndim
+        for t in tensors[1:]:
+            out = ops.Cat.execute(out, t, dim=d)
+        return out
+
     def squeeze(self, dim: list[int] | int) -> "Tensor":
         return ops.Squeeze.execute(self, dim=dim)
 

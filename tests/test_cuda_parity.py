@@ -379,8 +379,11 @@ def test_inference_kv_cache_path_vs_oracle(oracle):
             q = a.q_proj(h).reshape((1, 1, a.n_head, a.head_dim)).transpose(1, 2)
             k = a.k_proj(h).reshape((1, 1, a.n_head, a.head_dim)).transpose(1, 2)
             v = a.v_proj(h).reshape((1, 1, a.n_head, a.head_dim)).transpose(1, 2)
-            k = Tensor(np.concatenate((pk.numpy(), k.numpy()), axis=2), device=dev)
-            v = Tensor(np.concatenate((pv.numpy(), v.numpy()), axis=2), device=dev)
+            if dev == "cuda":          # device-side append (Tensor.cat); the host run keeps the reference's numpy round trip
+                k, v = Tensor.cat([pk, k], dim=2), Tensor.cat([pv, v], dim=2)
+            else:
+                k = Tensor(np.concatenate((pk.numpy(), k.numpy()), axis=2), device=dev)
+                v = Tensor(np.concatenate((pv.numpy(), v.numpy()), axis=2), device=dev)
             att = ((q @ k.transpose(2, 3)) * a.scale).softmax(dim=3)
             y = (att @ v).transpose(1, 2).reshape((1, 1, cfg.n_embd))
             x = x + a.c_proj(y)
@@ -389,6 +392,35 @@ def test_inference_kv_cache_path_vs_oracle(oracle):
     runner.rel_check(check, outs["cuda"], outs["cpu"], 1e-4, "incremental-decode logits")
     if not __import__("tests.conftest", fromlist=["x"]).COMPILE_ONLY:
         assert int(outs["cuda"].argmax()) == int(outs["cpu"].argmax())
+
+
+@pytest.mark.parametrize("shape_a,shape_b,dim", [((1, 4, 6, 32), (1, 4, 1, 32), 2), ((8, 12, 1023, 64), (8, 12, 1, 64), 2),
+                                                 ((3, 5), (4, 5), 0), ((3, 5), (3, 2), 1), ((2, 3, 7), (2, 3, 1), -1)])
+def test_device_side_concat_matches_numpy(oracle, shape_a, shape_b, dim):
+    """Tensor.cat: the KV-cache append of the inference path stays on the device instead of
+    examples/gpt.py:140-147's np.concatenate round trip.  Data movement: bit-exact; gradients are the slices."""
+    from dlgrad_b200 import Tensor
+    rng = np.random.default_rng(len(shape_a) + shape_b[-1])
+    a = rng.random(shape_a, dtype=np.float32)
+    b = rng.random(shape_b, dtype=np.float32)
+    A = Tensor(a.copy(), device="cuda", requires_grad=True)
+    B = Tensor(b.copy(), device="cuda", requires_grad=True)
+    out = Tensor.cat([A, B], dim=dim)
+    ref = np.concatenate((a, b), axis=dim)
+    assert out.shape == ref.shape
+    check(out.numpy(), ref, exact=True, what="cat")
+    w = np.arange(ref.size, dtype=np.float32).reshape(ref.shape)
+    (out * Tensor(w.copy(), device="cuda")).sum().backward()
+    d = dim % len(shape_a)
+    ia = tuple(slice(None) if k != d else slice(0, shape_a[d]) for k in range(len(shape_a)))
+    ib = tuple(slice(None) if k != d else slice(shape_a[d], None) for k in range(len(shape_a)))
+    check(A.grad.numpy(), w[ia], exact=True, what="cat grad a")
+    check(B.grad.numpy(), w[ib], exact=True, what="cat grad b")
+    # three operands, and the oracle path (numpy) agrees
+    three = Tensor.cat([A, B, B], dim=dim).numpy()
+    check(three, np.concatenate((a, b, b), axis=dim), exact=True, what="cat of three")
+    host = Tensor.cat([Tensor(a.copy()), Tensor(b.copy())], dim=dim).numpy()
+    check(host, ref, exact=True, what="host cat")
 
 
 def test_dropout_semantics():
