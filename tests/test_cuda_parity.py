@@ -596,6 +596,26 @@ def test_stream_k_matmul(shape):
     check(outs[2], outs[0], exact=True, what="stream-K relaunch 2 bit-identical")
 
 
+@pytest.mark.parametrize("kernel", ["v1", "v2", "v3", "v4"])
+@pytest.mark.parametrize("tx,ty", [(False, False), (False, True), (True, False)])
+def test_every_tensor_core_kernel_generation(kernel, tx, ty):
+    """The four generations of the tcgen05 3xTF32 GEMM (codegen/cuda_tcgen05.py: one tile per CTA, persistent,
+    CTA pair, A operand in TMEM) stay selectable through DLGRAD_TC_KERNEL; each is checked against float64 on a
+    ragged shape in the NN / NT / TN operand layouts."""
+    from dlgrad_b200.runtime.cuda import matmul_tc, shim, transfer
+    M, N, K = 520, 392, 200
+    rng = np.random.default_rng(17)
+    a = (rng.random((K, M) if tx else (M, K), dtype=np.float32) - 0.5).astype(np.float32)
+    b = (rng.random((N, K) if ty else (K, N), dtype=np.float32) - 0.5).astype(np.float32)
+    plan = matmul_tc.try_build(M, N, K, (1, 1), (0, 0), (0, 0), tx, ty, True, kernel=kernel, force=True)
+    assert plan is not None
+    out = plan(transfer.upload_numpy(a), transfer.upload_numpy(b))
+    shim.synchronize()
+    A = a.astype(np.float64).T if tx else a.astype(np.float64)
+    B = b.astype(np.float64).T if ty else b.astype(np.float64)
+    runner.rel_check(check, transfer.download(out, M * N).reshape(M, N), A @ B, runner.TOL_MATMUL, f"{kernel} tx={tx} ty={ty}")
+
+
 def test_split_k_weight_gradient_gemm(oracle):
     """x^T @ g with a small output and K = batch*tokens (the Linear weight gradient) runs as split-K: K-slices
     as a batch + an ordered sum (runtime/cuda/matmul.py).  Checked against float64 and, at a smaller K, the oracle."""
