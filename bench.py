@@ -409,6 +409,8 @@ def run_b200(args) -> None:
         "model_tflops": value * flops_step / 1e12,
         "last_loss": last_loss,
         "gpu_launches": int(launches),
+        "hbm": {"peak_gb": int(shim.lib.dlg_mem_peak()) / 1e9, "reserved_gb": int(shim.lib.dlg_mem_reserved()) / 1e9,
+                "note": "caching allocator, per rank; B200 has 180 GB"},
         "clocks": clocks.summary(),
         "e2e": {"value": e2e, "unit": "steps/s", "h2d_bytes_per_step": io["h2d_bytes"] // args.steps,
                 "d2h_bytes_per_step": io["d2h_bytes"] // args.steps},
