@@ -234,7 +234,7 @@ def op_microbench(peaks: dict, only: tuple | None = None) -> dict:
              ("sum_axis0", lambda i: a[i].sum(dim=0), one, "GB/s"), ("sum_axis1", lambda i: a[i].sum(dim=1), one, "GB/s"),
              ("max_axis0", lambda i: a[i].max(dim=0), one, "GB/s"), ("max_axis1", lambda i: a[i].max(dim=1), one, "GB/s"),
              ("sum_all", lambda i: a[i].sum(), one, "GB/s"),
-             ("exp", lambda i: a[i].exp(), half, "GB/s"), ("transpose", lambda i: a[i].T, half, "GB/s"),
+             ("exp", lambda i: a[i].exp(), half, "GB/s"), ("transpose", lambda i: a[i].permute((1, 0)), half, "GB/s"),
              ("softmax_rows", lambda i: a[i].softmax(dim=1), half, "GB/s"),
              ("matmul_4096", lambda i: a[i] @ b[i], 2.0 * n ** 3, "TFLOP/s")]
     out = {}
