@@ -118,7 +118,7 @@ class Buffer:
     # A CUDA Buffer may be created WITHOUT running its kernel: `_pending` records a cheap pointwise
     # producer — ("scale", src, s) for `src * python_scalar`, ("mfill", src, mask, val) for masked_fill,
     # ("softmax_bwd", y, g, dim, kind) for the row backward, ("tr", src) for a transpose of the two
-    # innermost dims.  Reading `.ptr` materialises it (one fused
+    # innermost dims, ("mm", x, y) for an attention-shaped q @ k^T.  Reading `.ptr` materialises it (one fused
     # kernel for the whole pending chain); consumers that can fold the chain into their own kernel
     # (softmax forward, and the chain materialiser itself) never trigger the intermediate writes.  The
     # values are identical either way; only the number of passes over HBM changes.
@@ -287,6 +287,12 @@ class Buffer:
         dev = Buffer._route(self, other)
         x = self if self.shape == p1 else self.reshape(p1)
         y = other if other.shape == p2 else other.reshape(p2)
+        if dev is _CUDA and y._pending is not None and y._pending[0] == "tr":
+            # q @ k^T of attention-shaped operands is deferred: if scale -> masked_fill -> softmax follow, one
+            # kernel produces the probabilities and this product never reaches HBM (runtime/cuda/attention.py)
+            from dlgrad_b200.runtime.cuda import attention
+            if attention.eligible(x, y):
+                return Buffer._deferred(("mm", x, y), out_shape, self.metadata.dtype)
         return self._like(_dispatch(op=BinaryOps.MATMUL, device=dev, x=x, y=y), out_shape, dev)
 
     def permute(self, order: tuple) -> "Buffer":

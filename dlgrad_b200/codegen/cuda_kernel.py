@@ -1006,6 +1006,29 @@ extern "C" __global__ void __launch_bounds__(256) {KNAME}{SIG} {{
 
 
 @cache
+def mask_bits(rows: int, cols: int) -> Kernel:
+    """out[r][w] (uint32, stored through the float* plan output) = bit e set iff mask[r][32 w + e] > 0.  The fused
+    attention-scores kernel reads a row's mask as 2 words per key tile instead of 64 floats (it is the same
+    (T, T) plane for every head).  p0 = mask (rows, cols), cols % 32 == 0."""
+    words = rows * cols // 32
+    src = f"""
+extern "C" __global__ void __launch_bounds__(256) {KNAME}{SIG} {{
+    const unsigned w = blockIdx.x * 256u + threadIdx.x;
+    if (w >= {words}u) return;
+    const float4* m = reinterpret_cast<const float4*>(p0) + (size_t)w * 8u;
+    unsigned bits = 0u;
+    #pragma unroll
+    for (unsigned j = 0; j < 8u; ++j) {{
+        const float4 v = __ldg(m + j);
+        bits |= ((v.x > 0.f ? 1u : 0u) | (v.y > 0.f ? 2u : 0u) | (v.z > 0.f ? 4u : 0u) | (v.w > 0.f ? 8u : 0u)) << (4u * j);
+    }}
+    reinterpret_cast<unsigned*>(out)[w] = bits;
+}}
+"""
+    return Kernel("mask_bits", src, (_cdiv(words, 256), 1, 1), (256, 1, 1), 0, words)
+
+
+@cache
 def cat2(outer: int, la: int, lb: int, aligned: bool = True) -> Kernel:
     """Concatenation of two tensors along one axis, seen as rows: out[o] = a[o] (la elements) ++ b[o] (lb
     elements) for `outer` rows.  No reference kernel: examples/gpt.py appends to its KV cache with

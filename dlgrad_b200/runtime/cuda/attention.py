@@ -1,0 +1,86 @@
+"""Fused attention scores on Device.CUDA:  P = softmax(masked_fill((q @ k^T) * scale, mask, fill), dim=-1).
+
+The reference writes every link of that chain to memory (examples/gpt.py:49-54 -> MATMUL, MUL, MASKED_FILL and the
+five softmax kernels).  Here `q @ k.transpose(-2, -1)` of attention-shaped operands is DEFERRED (Buffer pending kind
+"mm"); if the next consumers are `* scalar`, `masked_fill(mask2d, v)` and `softmax(dim=-1)`, the softmax dispatch
+lands here and ONE tensor-core kernel (codegen/cuda_tcgen05.attn_scores_tc) produces P without S = q @ k^T ever
+existing in HBM.  Any other consumer materialises the deferred product with the ordinary GEMM, so values and
+semantics are those of the eager chain.  DLGRAD_FUSED_SCORES=0 disables the deferral.
+"""
+from __future__ import annotations
+
+import os
+
+from dlgrad_b200.buffer import Buffer
+from dlgrad_b200.codegen import cuda_tcgen05 as tc
+from dlgrad_b200.helpers import prod_
+from dlgrad_b200.runtime.cuda import compiler, shim
+from dlgrad_b200.runtime.cuda import profile as _profile
+
+ENABLED = os.environ.get("DLGRAD_FUSED_SCORES", "1") != "0"
+MIN_SCORES = 1 << 22          # elements of (batch, Tq, Tk) below which the eager chain is just as good
+_plans: dict = {}
+
+
+def eligible(x: Buffer, y: Buffer) -> bool:
+    """`x @ y` with y a deferred transpose of k: (.., Tq, D) @ (.., Tk, D)^T, same batch dims, tile-sized."""
+    if not ENABLED or y._pending is None or y._pending[0] != "tr" or x._pending is not None:
+        return False
+    k = y._pending[1]
+    xs, ks = x.metadata.shape, k.metadata.shape
+    if len(xs) < 3 or len(xs) != len(ks) or xs[:-2] != ks[:-2] or xs[-1] != ks[-1] or k._pending is not None:
+        return False
+    if y.metadata.shape != ks[:-2] + (ks[-1], ks[-2]):
+        return False
+    Tq, D, Tk = xs[-2], xs[-1], ks[-2]
+    return (Tq % 128 == 0 and Tk % 128 == 0 and Tk <= 2048 and D in (32, 64) and x.aligned and k.aligned
+            and prod_(xs[:-2]) * Tq * Tk >= MIN_SCORES and x.scalar is None and k.scalar is None)
+
+
+def chain_matches(chain: list, out_shape: tuple) -> tuple | None:
+    """[("scale", _, s), ("mfill", _, mask, v)] with a mask that is one (Tq, Tk) plane broadcast over the batch."""
+    if len(chain) != 2 or chain[0][0] != "scale" or chain[1][0] != "mfill":
+        return None
+    mask, val = chain[1][2], chain[1][3]
+    ms = tuple(mask.metadata.shape)
+    while len(ms) > 2 and ms[0] == 1:
+        ms = ms[1:]
+    if ms != tuple(out_shape[-2:]) or not mask.aligned or mask.scalar is not None:
+        return None
+    if not float(chain[0][2]) > 0.0:               # the kernel takes row maxima on the raw scores
+        return None
+    return float(chain[0][2]), mask, float(val)
+
+
+def scores(q: Buffer, k: Buffer, scale: float, mask: Buffer, fill: float):
+    """Launch the fused kernel; returns the owned device pointer of P (batch.., Tq, Tk)."""
+    from dlgrad_b200.runtime.cuda import matmul_tc, ops as _ops
+    xs, ks = q.metadata.shape, k.metadata.shape
+    nb, Tq, Tk, D = prod_(xs[:-2]), xs[-2], ks[-2], xs[-1]
+    key = (nb, Tq, Tk, D, scale, fill)
+    plan = _plans.get(key)
+    if plan is None:
+        kern = tc.attn_scores_tc(Tq, Tk, D, nb, scale, fill)
+        fn = compiler.get_function(kern.name, kern.source)
+        da, db, dc = tc.tmap_descs(Tq, Tk, D, nb, False, False, False, False, kern.bn)
+        p = shim.lib.dlg_mm_plan_create(fn, kern.grid[0], 1, 1, kern.threads, kern.smem, 1, kern.out_elems * 4,
+                                        matmul_tc._tmap(da), matmul_tc._tmap(db), matmul_tc._tmap(dc))
+        if p == shim.NULL:
+            raise RuntimeError("dlg_mm_plan_create failed: " + shim.last_error())
+        plan = _plans[key] = (p, kern.out_elems * 4)
+    p, nbytes = plan
+    bkey = ("mask_bits", Tq, Tk)
+    bplan = _plans.get(bkey)
+    if bplan is None:
+        from dlgrad_b200.codegen import cuda_kernel as ck
+        bplan = _plans[bkey] = _ops.Plan(ck.mask_bits(Tq, Tk))
+    bits = bplan.run(_ops._dev_ptr(mask))             # the same (Tq, Tk) plane for every head: 1 bit per entry
+    pq, pk, pm = _ops._dev_ptr(q), _ops._dev_ptr(k), bits
+    timer = _profile.matmul_timer
+    t0 = timer.start() if timer is not None else None
+    out = shim.lib.dlg_mm_plan_run_aux(p, pq, pk, pm, shim.NULL)
+    if timer is not None:
+        timer.stop(t0, 2.0 * nb * Tq * Tk * D, ("attn_scores", Tq, Tk, D, nb))
+    if out == shim.NULL:
+        raise RuntimeError("fused attention-scores launch failed: " + shim.last_error())
+    return shim.own(out, nbytes)

@@ -142,6 +142,9 @@ def materialize(buf: Buffer) -> None:
         nd = len(src.metadata.shape)
         buf.ptr = permute(src, tuple(range(nd - 2)) + (nd - 1, nd - 2))
         return
+    if pend[0] == "mm":
+        buf.ptr = matmul(pend[1], pend[2])
+        return
     chain, base = _peel_chain(buf)
     shape = buf.metadata.shape
     bp = base._pending
@@ -511,6 +514,15 @@ def _softmax_family(kind: str, x: Buffer, dim: int) -> CDataPtr:
         return (e / s).ptr if kind == "softmax" else (sh - s.log()).ptr
     if x._pending is not None:
         chain, base = _peel_chain(x)
+        bp = base._pending
+        if bp is not None and bp[0] == "mm" and kind == "softmax":
+            from dlgrad_b200.runtime.cuda import attention
+            m = attention.chain_matches(chain, x.metadata.shape)
+            q, kt = bp[1], bp[2]
+            if m is not None and kt._pending is not None and kt._pending[0] == "tr":
+                return attention.scores(q, kt._pending[1], m[0], m[1], m[2])
+        if bp is not None:
+            materialize(base)                       # a deferred transpose / product under the chain: run it, keep folding
         if chain and base._pending is None:
             args = _row_chain_args(chain, x.metadata.shape, base.aligned)
             if args is not None:

@@ -616,6 +616,61 @@ def test_every_tensor_core_kernel_generation(kernel, tx, ty):
     runner.rel_check(check, transfer.download(out, M * N).reshape(M, N), A @ B, runner.TOL_MATMUL, f"{kernel} tx={tx} ty={ty}")
 
 
+@pytest.mark.parametrize("B,H,T,D,mask_kind,fill", [(2, 16, 512, 64, "causal", float("-inf")), (1, 8, 1024, 32, "random", -1e9),
+                                                     (4, 8, 512, 32, "dead_rows", float("-inf")), (8, 12, 1024, 64, "causal", float("-inf"))])
+def test_fused_attention_scores(oracle, B, H, T, D, mask_kind, fill):
+    """softmax(masked_fill((q @ k^T) * scale, mask, fill)) of attention-sized operands runs as ONE tensor-core kernel
+    (runtime/cuda/attention.py, codegen/cuda_tcgen05.attn_scores_tc): the product is deferred and never reaches HBM.
+    Forward vs float64 and vs the same chain with the fusion switched off; gradients of q and k vs the oracle at the
+    smaller sizes; an all-masked row must come out NaN exactly where the unfused chain has NaN; and reading the
+    deferred product itself (no softmax) must still give the plain GEMM."""
+    from dlgrad_b200 import Tensor
+    from dlgrad_b200.runtime.cuda import attention
+    rng = np.random.default_rng(B * T + D)
+    q = (rng.random((B, H, T, D), dtype=np.float32) - 0.5).astype(np.float32)
+    k = (rng.random((B, H, T, D), dtype=np.float32) - 0.5).astype(np.float32)
+    mask = {"causal": np.triu(np.ones((T, T), dtype=np.float32), 1),
+            "random": (rng.random((T, T)) > 0.6).astype(np.float32),
+            "dead_rows": np.maximum(rng.random((T, T)) > 0.5, (np.arange(T)[:, None] % 37 == 0)).astype(np.float32)}[mask_kind]
+    scale = float(1.0 / np.sqrt(D))
+    compile_only = __import__("tests.conftest", fromlist=["x"]).COMPILE_ONLY
+    outs = {}
+    for fused in (True, False):
+        attention.ENABLED = fused
+        Q = Tensor(q.copy(), device="cuda", requires_grad=True)
+        K = Tensor(k.copy(), device="cuda", requires_grad=True)
+        M = Tensor(mask.copy(), device="cuda")
+        s = Q @ K.transpose(2, 3)
+        if fused and not compile_only:
+            assert s.data._pending is not None and s.data._pending[0] == "mm", "expected the product to be deferred"
+        p = (s * scale).masked_fill(M, fill).softmax(dim=3)
+        w = Tensor(np.linspace(0.5, 1.5, T, dtype=np.float32).reshape(1, 1, 1, T), device="cuda")
+        res = [p.numpy()]
+        if mask_kind != "dead_rows":                 # NaN rows poison every gradient, as in the reference
+            (p * w).sum().backward()
+            res += [Q.grad.numpy(), K.grad.numpy()]
+        outs[fused] = res
+    attention.ENABLED = True
+    s64 = np.einsum("bhqd,bhkd->bhqk", q.astype(np.float64), k.astype(np.float64)) * scale
+    s64 = np.where(mask > 0, fill, s64)
+    with np.errstate(invalid="ignore"):
+        e = np.exp(s64 - s64.max(axis=3, keepdims=True))
+        ref = e / e.sum(axis=3, keepdims=True)
+    if not compile_only:
+        got = outs[True][0]
+        assert (np.isnan(got) == np.isnan(ref)).all() and (np.isnan(outs[False][0]) == np.isnan(ref)).all()
+        ok = np.isfinite(ref)
+        runner.rel_check(check, got[ok], ref[ok], runner.TOL_ELEMENTWISE, "fused scores vs float64")
+        runner.rel_check(check, got[ok], outs[False][0][ok], runner.TOL_ELEMENTWISE, "fused vs unfused chain")
+        for a, b, what in zip(outs[True][1:], outs[False][1:], ("dq", "dk")):
+            runner.rel_check(check, a, b, SOFTMAX_GRAD_TOL, f"{what}: fused vs unfused chain")
+    # the deferred product read on its own is the ordinary GEMM
+    Q, K = Tensor(q.copy(), device="cuda"), Tensor(k.copy(), device="cuda")
+    plain = (Q @ K.transpose(2, 3)).numpy()
+    runner.rel_check(check, plain, np.einsum("bhqd,bhkd->bhqk", q.astype(np.float64), k.astype(np.float64)), runner.TOL_MATMUL,
+                     "deferred q @ k^T materialised")
+
+
 def test_split_k_weight_gradient_gemm(oracle):
     """x^T @ g with a small output and K = batch*tokens (the Linear weight gradient) runs as split-K: K-slices
     as a batch + an ordered sum (runtime/cuda/matmul.py).  Checked against float64 and, at a smaller K, the oracle."""
