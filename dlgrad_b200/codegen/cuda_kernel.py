@@ -1006,6 +1006,29 @@ extern "C" __global__ void __launch_bounds__(256) {KNAME}{SIG} {{
 
 
 @cache
+def rowdot(rows: int, D: int) -> Kernel:
+    """out[r] = sum_d a[r][d] * b[r][d] for D in {32, 64}: D/4 threads per row, float4 loads, shuffle tree.  Used for
+    rowsum(dO * O), the per-row term of the softmax backward inside the fused attention backward.  p0 = a, p1 = b."""
+    g = D // 4                                        # threads per row
+    rpb = 256 // g
+    src = f"""
+extern "C" __global__ void __launch_bounds__(256) {KNAME}{SIG} {{
+    const unsigned r = blockIdx.x * {rpb}u + threadIdx.x / {g}u, t = threadIdx.x % {g}u;
+    float s = 0.f;
+    if (r < {rows}u) {{
+        const float4 a = __ldg(reinterpret_cast<const float4*>(p0) + (size_t)r * {g}u + t);
+        const float4 b = __ldg(reinterpret_cast<const float4*>(p1) + (size_t)r * {g}u + t);
+        s = a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w;
+    }}
+    #pragma unroll
+    for (unsigned o = {g // 2}u; o > 0u; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (t == 0u && r < {rows}u) out[r] = s;
+}}
+"""
+    return Kernel("rowdot", src, (_cdiv(rows, rpb), 1, 1), (256, 1, 1), 0, rows)
+
+
+@cache
 def mask_bits(rows: int, cols: int) -> Kernel:
     """out[r][w] (uint32, stored through the float* plan output) = bit e set iff mask[r][32 w + e] > 0.  The fused
     attention-scores kernel reads a row's mask as 2 words per key tile instead of 64 floats (it is the same

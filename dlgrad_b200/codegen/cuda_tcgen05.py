@@ -1442,6 +1442,353 @@ extern "C" __global__ void __launch_bounds__({nthreads}, 1)
     return TcKernel("attn_scores", src, (grid, 1, 1), nthreads, smem, batch * Tq * Tk, BN, stages)
 
 
+@cache
+def attn_dscores_tc(Tq: int, Tk: int, D: int, batch: int, scale: float) -> TcKernel:
+    """Backward twin of attn_scores_tc:  dS = masked_fill(P * (dP - rowsum(dP * P)), mask, 0) * scale  with
+    dP = dO @ V^T computed tile by tile in TMEM and never written (the unfused chain writes dP, 403 MB per layer at
+    C5, and reads it back in the softmax backward).  rowsum(dP * P) = rowsum(dO * O) — the flash-attention identity —
+    arrives precomputed, so ONE pass over the key tiles suffices: read P once, write dS once.
+    dO (batch, Tq, D) and V (batch, Tk, D) K-major.  Kernel parameters: (tmDO, tmV, tmDS, dS, P, aux) with
+    aux = [rowsum(dO * O): batch * Tq floats | mask bits: Tq * Tk / 32 words]."""
+    fill = 0.0
+    import os
+    trace = os.environ.get("DLGRAD_TC_TRACE", "0") == "1"      # diagnostic: CTA 0 timestamps its first 32 key tiles
+
+    def TR(kind, idx, cond="lane == 0u"):
+        return f"if (blockIdx.x == 0u && {idx} < 32u && {cond}) trace[{kind}][{idx}] = clock64();" if trace else ""
+    assert Tq % 128 == 0 and Tk % 128 == 0 and Tk <= 2048 and D in (32, 64)      # D <= 64: 2 Q buffers + 2 S buffers fill TMEM
+    kbq = D // 32                                   # k-blocks per tile
+    BN = 128
+    q_bytes = kbq * 16384                           # one Q tile (128 x D fp32), K-major, 16 KiB per k-block
+    k_tile = BN * BK * 4                            # 16 KiB: one k-block of a key tile
+    per_stage = 2 * k_tile                          # raw (= hi) | lo
+    NB, AHEAD = 4, 2                     # 32x32 boxes per row warp: P arrives in them by cp.async AHEAD chunks early, dS leaves from them
+    epi_bytes = 8 * NB * 4096
+    budget = 227 * 1024 - 1024 - 512 - epi_bytes - q_bytes       # Q: ONE shared-memory tile (it only lives until it is split into TMEM)
+    stages = max(2, min(6, budget // per_stage))
+    smem = q_bytes + stages * per_stage + epi_bytes + 1024 + 512
+    q_tmem0 = 2 * BN                                # S accumulators first (double buffered), then Q hi/lo x 2 buffers
+    tmem_need = q_tmem0 + 2 * kbq * 64
+    assert tmem_need <= 512, tmem_need
+    tmem_cols = 512
+    idesc = _idesc(BM, BN, False, False)
+    nq, nk = Tq // 128, Tk // 128
+    items = batch * nq
+    grid = min(items, NUM_SMS)
+    nthreads = 64 + 256 + 128           # producer, MMA | 8 row warps (two per TMEM lane quarter, 64 columns each) | 4 K-splitter warps
+    # the row warps work in the base-2 domain: softmax(x) = 2^((x - m) log2 e) / sum, one MUFU.EX2 per element
+    # instead of expf's ~10 instructions (they, not the tensor pipe, were the bottleneck: 4 us per tile)
+    import math
+    import numpy as _np
+    log2e = float(_np.float32(math.log2(math.e)))
+    sc = _f32lit(float(_np.float32(scale)))
+    fl = _f32lit(fill)
+    regs = ", ".join(f"%{i}" for i in range(32))
+    outs = ", ".join(f'"=r"(v[{i}])' for i in range(32))
+    regs_in = ", ".join(f"%{i + 1}" for i in range(32))
+    hi_ops = ", ".join(f'"r"(hi[{i}])' for i in range(32))
+    lo_ops = ", ".join(f'"r"(lo[{i}])' for i in range(32))
+    stage_writes = "\n                        ".join(
+        f"*reinterpret_cast<float4*>(sbuf_gen + lane * 128u + (({j}u ^ (lane & 7u)) << 4)) = "
+        f"make_float4(x[{4 * j}], x[{4 * j + 1}], x[{4 * j + 2}], x[{4 * j + 3}]);"
+        for j in range(8))
+    src = _HELPERS + _HELPERS_TS + """
+__device__ __forceinline__ float ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+""" + f"""
+extern "C" __global__ void __launch_bounds__({nthreads}, 1)
+{KNAME}(const __grid_constant__ TMap tmQ, const __grid_constant__ TMap tmK, const __grid_constant__ TMap tmP, float* __restrict__ P, const float* __restrict__ Pin, const float* __restrict__ aux)
+{{
+    extern __shared__ unsigned char smem_raw[];
+    const unsigned smem = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    unsigned char* smem_gen = smem_raw + (smem - smem_u32(smem_raw));
+    const unsigned qs = smem;                                   // the Q tile being split
+    const unsigned ring = smem + {q_bytes}u;                // K stages: raw | lo
+    const unsigned epi = ring + {stages * per_stage}u;
+    const unsigned bars = epi + {epi_bytes}u;
+    const unsigned kfull = bars, kempty = bars + {stages * 8}u, ksplit = bars + {stages * 16}u;
+    const unsigned sfull = bars + {stages * 24}u, sempty = sfull + 16u, qfull = sempty + 16u, qsplit = qfull + 16u, qfree = qsplit + 16u;
+    __shared__ unsigned tmem_slot;
+    {"__shared__ long long trace[5][32];" if trace else ""}
+    const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+
+    if (threadIdx.x == 0) {{
+        for (unsigned s = 0; s < {stages}u; ++s) {{
+            mbar_init(kfull + s * 8u, 1u);
+            mbar_init(kempty + s * 8u, 1u);
+            mbar_init(ksplit + s * 8u, 4u);
+        }}
+        for (unsigned b = 0; b < 2u; ++b) {{
+            mbar_init(sfull + b * 8u, 1u);
+            mbar_init(sempty + b * 8u, 8u);
+            mbar_init(qfull + b * 8u, 1u);
+            mbar_init(qsplit + b * 8u, 4u);
+            mbar_init(qfree + b * 8u, 1u);
+        }}
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }}
+    if (warp == 1) {{
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&tmem_slot)), "n"({tmem_cols}));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }}
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const unsigned tmem_base = tmem_slot;
+
+    if (warp == 0) {{
+        // ===== TMA producer: K tiles twice per item; the NEXT item's Q tile is requested between the two passes so
+        //       that the row warps can split it while the MMAs run pass 1 =====
+        unsigned it = 0, n = 0;
+        auto load_q = [&](unsigned nn, unsigned ww) {{
+            const unsigned zz = ww / {nq}u, qq0 = (ww % {nq}u) * 128u, qb = nn & 1u;
+            mbar_wait(qfree + qb * 8u, ((nn >> 1) & 1u) ^ 1u);          // the MMAs of the item that used this TMEM Q buffer are done
+            if (nn != 0u) mbar_wait(qsplit + ((nn - 1u) & 1u) * 8u, ((nn - 1u) >> 1) & 1u);   // the previous Q tile has left shared memory
+            if (elect_one()) {{
+                mbar_expect_tx(qfull + qb * 8u, {q_bytes}u);
+                #pragma unroll
+                for (unsigned kk = 0; kk < {kbq}u; ++kk)
+                    tma_load_3d(qs + kk * 16384u, &tmQ, qfull + qb * 8u, (int)(kk * 32u), (int)qq0, (int)zz);
+            }}
+            __syncwarp();
+        }};
+        if (blockIdx.x < {items}u) load_q(0u, blockIdx.x);
+        for (unsigned w = blockIdx.x; w < {items}u; w += {grid}u, ++n) {{
+            const unsigned z = w / {nq}u;
+            {{
+                // The row warps read P with plain loads, one 32-column chunk ahead in registers: far too little in
+                // flight to cover HBM latency (measured 6000-9000 clk per tile).  This otherwise idle warp pulls
+                // the P tiles into L2 a few tiles ahead, so those loads become L2 hits.
+                auto prefetch_p = [&](unsigned jj) {{
+                    const float* pt = Pin + ((size_t)z * {Tq}u + (w % {nq}u) * 128u) * {Tk}u + jj * 128u;
+                    #pragma unroll
+                    for (unsigned r = 0; r < 4u; ++r) {{
+                        const float* pr = pt + (size_t)(lane + r * 32u) * {Tk}u;
+                        #pragma unroll
+                        for (unsigned c = 0; c < 4u; ++c) asm volatile("prefetch.global.L2 [%0];" :: "l"(pr + c * 32u));
+                    }}
+                }};
+                #pragma unroll 1
+                for (unsigned jj = 0; jj < {min(3, nk)}u; ++jj) prefetch_p(jj);
+                for (unsigned j = 0; j < {nk}u; ++j) {{
+                    if (j + {min(3, nk)}u < {nk}u) prefetch_p(j + {min(3, nk)}u);
+                    if (j == {nk // 2}u && w + {grid}u < {items}u) load_q(n + 1u, w + {grid}u);
+                    for (unsigned kk = 0; kk < {kbq}u; ++kk, ++it) {{
+                        const unsigned s = it % {stages}u, ph = (it / {stages}u) & 1u;
+                        mbar_wait(kempty + s * 8u, ph ^ 1u);
+                        {TR(4, f"(it / {kbq}u)", "lane == 0u && kk == 0u")}
+                        if (elect_one()) {{
+                            mbar_expect_tx(kfull + s * 8u, {k_tile}u);
+                            tma_load_3d(ring + s * {per_stage}u, &tmK, kfull + s * 8u, (int)(kk * 32u), (int)(j * 128u), (int)z);
+                        }}
+                        __syncwarp();
+                    }}
+                }}
+            }}
+        }}
+    }} else if (warp == 1) {{
+        // ===== MMA issuer: S[b] = Q_hi/lo (TMEM) x K_hi/lo (smem), 3 MMAs per 8-wide k step =====
+        unsigned it = 0, u = 0, n = 0;
+        const unsigned long long bdesc0 = make_desc(ring, 1u, 64u, 2u);
+        for (unsigned w = blockIdx.x; w < {items}u; w += {grid}u, ++n) {{
+            const unsigned qb = n & 1u;
+            mbar_wait(qsplit + qb * 8u, (n >> 1) & 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const unsigned q_t = tmem_base + {q_tmem0}u + qb * {kbq * 64}u;
+            for (unsigned pj = 0; pj < {nk}u; ++pj, ++u) {{
+                const unsigned b = u & 1u;
+                mbar_wait(sempty + b * 8u, ((u >> 1) & 1u) ^ 1u);
+                {TR(0, "u")}
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const unsigned tacc = tmem_base + b * {BN}u;
+                for (unsigned kk = 0; kk < {kbq}u; ++kk, ++it) {{
+                    const unsigned s = it % {stages}u, ph = (it / {stages}u) & 1u;
+                    mbar_wait(ksplit + s * 8u, ph);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const unsigned long long bdesc = bdesc0 + (unsigned long long)(s * {per_stage // 16}u);
+                    const unsigned a_hi = q_t + kk * 64u, a_lo = a_hi + 32u;
+                    if (elect_one()) {{
+                        #pragma unroll
+                        for (unsigned k = 0; k < 4u; ++k) {{
+                            const unsigned long long b_hi = bdesc + (unsigned long long)(k * 2u);
+                            umma_tf32_ts(tacc, a_lo + k * 8u, b_hi, {idesc}u, (kk | k) != 0u);
+                            umma_tf32_ts(tacc, a_hi + k * 8u, b_hi + {k_tile // 16}ull, {idesc}u, 1u);
+                            umma_tf32_ts(tacc, a_hi + k * 8u, b_hi, {idesc}u, 1u);
+                        }}
+                        umma_commit(kempty + s * 8u);
+                        if (kk + 1u == {kbq}u) umma_commit(sfull + b * 8u);
+                    }}
+                    __syncwarp();
+                }}
+                {TR(1, "u")}
+            }}
+            if (elect_one()) umma_commit(qfree + qb * 8u);
+            __syncwarp();
+        }}
+    }} else if (warp < 10u) {{
+        // ===== row warps: thread = query row = TMEM lane; warps 2-5 take columns 0-63 of every key tile, warps 6-9
+        //       columns 64-127 (the row work — TMEM reads, exponentials, stores — is what paces this kernel).  Split Q into TMEM; pass 0: running max / sum over the
+        //       key tiles; pass 1: normalise and store P =====
+        const unsigned sq = warp & 3u;
+        const unsigned half = (warp >= 6u) ? 1u : 0u;               // which 64 columns of a key tile
+        const unsigned my_epi = epi + (warp - 2u) * {NB * 4096}u;
+        unsigned char* my_epi_gen = smem_gen + {q_bytes + stages * per_stage}u + (warp - 2u) * {NB * 4096}u;
+        unsigned nstore = 0, nfetch = 0;
+        unsigned u = 0, n = 0;
+
+        auto split_q = [&](unsigned nn) {{
+            const unsigned qb = nn & 1u;
+            mbar_wait(qfull + qb * 8u, (nn >> 1) & 1u);
+            #pragma unroll 1
+            for (unsigned kk = 0; kk < {kbq}u; ++kk) {{
+                const unsigned char* arow = smem_gen + kk * 16384u + (sq * 32u + lane) * 128u;
+                unsigned hi[32], lo[32];
+                #pragma unroll
+                for (unsigned j = 0; j < 8u; ++j) {{
+                    const float4 v4 = *reinterpret_cast<const float4*>(arow + ((j ^ (lane & 7u)) << 4));
+                    const float xv[4] = {{v4.x, v4.y, v4.z, v4.w}};
+                    #pragma unroll
+                    for (unsigned e = 0; e < 4u; ++e) {{
+                        hi[4 * j + e] = __float_as_uint(xv[e]) & 0xffffe000u;
+                        lo[4 * j + e] = __float_as_uint(xv[e] - __uint_as_float(hi[4 * j + e]));
+                    }}
+                }}
+                const unsigned ta = tmem_base + ((sq * 32u) << 16) + {q_tmem0}u + qb * {kbq * 64}u + kk * 64u;
+                asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {{{regs_in}}};" :: "r"(ta), {hi_ops} : "memory");
+                asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {{{regs_in}}};" :: "r"(ta + 32u), {lo_ops} : "memory");
+            }}
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(qsplit + qb * 8u);
+        }};
+
+        if (half == 0u && blockIdx.x < {items}u) split_q(0u);
+        for (unsigned w = blockIdx.x; w < {items}u; w += {grid}u, ++n) {{
+            const unsigned z = w / {nq}u, q0 = (w % {nq}u) * 128u;
+            const unsigned row = q0 + sq * 32u + lane;
+            // this row's mask bits for the 64 columns of every key tile this warp owns (2 words per tile)
+            unsigned mbits[{Tk // 64}];
+            {{
+                const uint2* br = reinterpret_cast<const uint2*>(reinterpret_cast<const unsigned*>(aux + {batch * Tq}u) + (size_t)row * {Tk // 32}u + half * 2u);
+                #pragma unroll
+                for (unsigned j = 0; j < {nk}u; ++j) {{
+                    const uint2 w2 = __ldg(br + j * 2u);
+                    mbits[2 * j] = w2.x;
+                    mbits[2 * j + 1] = w2.y;
+                }}
+            }}
+            const float drow = __ldg(aux + (size_t)z * {Tq}u + row);            // rowsum(dO * O) of this row
+            // P travels global -> shared by cp.async (16 B per lane, eight lanes per 128-byte row, landing directly in the
+            // swizzled position of a staging box), TWO 32-column chunks ahead (a box is refilled once the store before
+            // last has left it): 8 KiB per warp, 64 KiB per SM in
+            // flight.  One chunk ahead in registers left the loads latency-bound (6000-9000 clk per key tile), and a
+            // thread reading its own row directly touches 32 cache lines per load.
+            auto fetch_p = [&](unsigned ww, unsigned g) {{          // chunk g = (key tile g / 2, column quarter half * 2 + g % 2) of item ww
+                const unsigned zz = ww / {nq}u, qq0 = (ww % {nq}u) * 128u;
+                const float* src = Pin + ((size_t)zz * {Tq}u + qq0 + sq * 32u + (lane >> 3)) * {Tk}u + (g >> 1) * 128u + half * 64u + (g & 1u) * 32u + (lane & 7u) * 4u;
+                const unsigned box = my_epi + (nfetch % {NB}u) * 4096u;
+                #pragma unroll
+                for (unsigned i = 0; i < 8u; ++i) {{
+                    const unsigned r = 4u * i + (lane >> 3);
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(box + r * 128u + (((lane & 7u) ^ (r & 7u)) << 4)), "l"(src + (size_t)(4u * i) * {Tk}u) : "memory");
+                }}
+                asm volatile("cp.async.commit_group;" ::: "memory");
+                ++nfetch;
+            }};
+            if (n == 0u) {{
+                #pragma unroll 1
+                for (unsigned g = 0; g < {AHEAD}u; ++g) fetch_p(w, g);
+            }}
+            for (unsigned j = 0; j < {nk}u; ++j, ++u) {{
+                if (half == 0u && j == {nk // 2}u && w + {grid}u < {items}u) split_q(n + 1u);   // next item's dO while the MMAs go on
+                const unsigned b = u & 1u;
+                mbar_wait(sfull + b * 8u, (u >> 1) & 1u);
+                {TR(2, "u", "threadIdx.x == 64u")}
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                #pragma unroll 1
+                for (unsigned cc = 0; cc < 2u; ++cc) {{
+                    const unsigned c = half * 2u + cc;
+                    unsigned v[32];
+                    const unsigned taddr = tmem_base + ((sq * 32u) << 16) + b * {BN}u + c * 32u;
+                    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {{{regs}}}, [%32];" : {outs} : "r"(taddr));
+                    {{   // fetch the chunk {AHEAD} ahead (possibly the next item's) into the box the store before last has left
+                        const unsigned g = j * 2u + cc + {AHEAD}u;
+                        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                        __syncwarp();
+                        if (g < {2 * nk}u) fetch_p(w, g);
+                        else if (w + {grid}u < {items}u) fetch_p(w + {grid}u, g - {2 * nk}u);
+                        else {{ asm volatile("cp.async.commit_group;" ::: "memory"); ++nfetch; }}      // keep the group count in step
+                    }}
+                    asm volatile("cp.async.wait_group {AHEAD};" ::: "memory");          // this chunk's P has landed (my copies)
+                    __syncwarp();                                                          // ... and everybody else's
+                    const unsigned sb = nstore % {NB}u;
+                    unsigned char* sbuf_gen = my_epi_gen + sb * 4096u;
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    float x[32];
+                    const unsigned bits = mbits[j * 2u + cc];
+                    #pragma unroll
+                    for (unsigned jj = 0; jj < 8u; ++jj) {{
+                        const float4 p4 = *reinterpret_cast<const float4*>(sbuf_gen + lane * 128u + ((jj ^ (lane & 7u)) << 4));
+                        const float pe[4] = {{p4.x, p4.y, p4.z, p4.w}};
+                        #pragma unroll
+                        for (unsigned e = 0; e < 4u; ++e) {{
+                            const float t = pe[e] * (__uint_as_float(v[4 * jj + e]) - drow);
+                            x[4 * jj + e] = ((bits >> (4u * jj + e)) & 1u) ? 0.f : t * {sc};
+                        }}
+                    }}
+                    {stage_writes}
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) {{
+                        tma_store_3d(&tmP, my_epi + sb * 4096u, (int)(j * 128u + c * 32u), (int)(q0 + sq * 32u), (int)z);
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }}
+                    ++nstore;
+                }}
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(sempty + b * 8u);
+                {TR(3, "u", "threadIdx.x == 64u")}
+            }}
+        }}
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }} else {{
+        // ===== K splitter warps: K_lo = x - trunc_tf32(x) into the twin buffer =====
+        const unsigned ctid = threadIdx.x - 320u;
+        unsigned it = 0;
+        for (unsigned w = blockIdx.x; w < {items}u; w += {grid}u) {{
+            for (unsigned i2 = 0; i2 < {nk * kbq}u; ++i2, ++it) {{
+                const unsigned s = it % {stages}u, ph = (it / {stages}u) & 1u;
+                mbar_wait(kfull + s * 8u, ph);
+                const float4* bsrc = reinterpret_cast<const float4*>(smem_gen + {q_bytes}u + s * {per_stage}u);
+                float4* bdst = reinterpret_cast<float4*>(smem_gen + {q_bytes}u + s * {per_stage}u + {k_tile}u);
+                #pragma unroll 8
+                for (unsigned i = ctid; i < {k_tile // 16}u; i += 128u) {{
+                    const float4 v4 = bsrc[i];
+                    float4 l4;
+                    l4.x = v4.x - __uint_as_float(__float_as_uint(v4.x) & 0xffffe000u);
+                    l4.y = v4.y - __uint_as_float(__float_as_uint(v4.y) & 0xffffe000u);
+                    l4.z = v4.z - __uint_as_float(__float_as_uint(v4.z) & 0xffffe000u);
+                    l4.w = v4.w - __uint_as_float(__float_as_uint(v4.w) & 0xffffe000u);
+                    bdst[i] = l4;
+                }}
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(ksplit + s * 8u);
+            }}
+        }}
+    }}
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    {"if (blockIdx.x == 0u && threadIdx.x < 160u) reinterpret_cast<long long*>(P)[threadIdx.x] = (&trace[0][0])[threadIdx.x];" if trace else ""}
+    if (warp == 1) {{
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "n"({tmem_cols}));
+    }}
+}}
+"""
+    return TcKernel("attn_dscores", src, (grid, 1, 1), nthreads, smem, batch * Tq * Tk, BN, stages)
+
+
 # =====================================================================================================
 # v3: CTA-pair kernel (cta_group::2).  Two CTAs of a cluster (one TPC) compute a 256 x BN tile: each
 # stages ITS 128 rows of A and ITS half of the B columns, the leader issues M=256 MMAs that read both

@@ -372,7 +372,8 @@ class MatMul(OP):
     def forward(self, x: Buffer, y: Buffer) -> Buffer:
         self.p1, self.p2, self.out_shape = broadcast_shapes(x.shape, y.shape)
         self.x, self.y = x, y
-        return x @ y
+        self.out = x @ y                 # kept for the fused attention backward: rowsum(dP * P) = rowsum(dO * O)
+        return self.out
 
     def backward(self, upstream_grad: Buffer) -> tuple[Buffer | None, Buffer | None]:
         g = upstream_grad if upstream_grad.shape == self.out_shape else upstream_grad.reshape(self.out_shape)
@@ -398,7 +399,16 @@ class MatMul(OP):
                 if xr._pending is not None and xr._pending[0] == "tr":
                     gx = lazy_t(mm(yr, g, batch + (self.p1[-1], self.p1[-2]), trans_y=True))
                 else:
-                    gx = mm(g, yr, batch + (self.p1[-2], self.p1[-1]), trans_y=True)
+                    gx = None
+                    if yr._pending is None and g._pending is None:
+                        # dP = dO @ v^T of an attention block: deferred, so that the softmax / masked_fill / scale
+                        # backward that follow can absorb it into one kernel (runtime/cuda/attention.dscores)
+                        from dlgrad_b200.runtime.cuda import attention
+                        yt = lazy_t(yr)
+                        if attention.BWD_ENABLED and attention.eligible(g, yt):
+                            gx = Buffer._deferred(("mm", g, yt, self.out), batch + (self.p1[-2], self.p1[-1]), g.dtype)
+                    if gx is None:
+                        gx = mm(g, yr, batch + (self.p1[-2], self.p1[-1]), trans_y=True)
                 gx = unbroadcast(gx, self.x.shape)
             if self.req_grad[1]:
                 if yr._pending is not None and yr._pending[0] == "tr":

@@ -18,6 +18,10 @@ from dlgrad_b200.runtime.cuda import compiler, shim
 from dlgrad_b200.runtime.cuda import profile as _profile
 
 ENABLED = os.environ.get("DLGRAD_FUSED_SCORES", "1") != "0"
+# The backward twin (attn_dscores_tc: dS from dO, v, P in one kernel, dP never written) is correct but not faster
+# yet — one persistent CTA per SM cannot keep enough of P in flight to cover loaded HBM latency: 221 us + 25 us of
+# helpers against 247 us for GEMM + fused softmax backward at C5 — so it is opt-in.
+BWD_ENABLED = os.environ.get("DLGRAD_FUSED_ATTN_BWD", "0") == "1"
 MIN_SCORES = 1 << 22          # elements of (batch, Tq, Tk) below which the eager chain is just as good
 _plans: dict = {}
 
@@ -84,3 +88,48 @@ def scores(q: Buffer, k: Buffer, scale: float, mask: Buffer, fill: float):
     if out == shim.NULL:
         raise RuntimeError("fused attention-scores launch failed: " + shim.last_error())
     return shim.own(out, nbytes)
+
+
+def dscores(dO: Buffer, v: Buffer, O: Buffer, P: Buffer, mask: Buffer, scale: float):
+    """dS = masked_fill(P * (dO @ v^T - rowsum(dO * O)), mask, 0) * scale in one kernel; returns the owned pointer."""
+    from dlgrad_b200.codegen import cuda_kernel as ck
+    from dlgrad_b200.runtime.cuda import matmul_tc, ops as _ops
+    xs, vs = dO.metadata.shape, v.metadata.shape
+    nb, Tq, Tk, D = prod_(xs[:-2]), xs[-2], vs[-2], xs[-1]
+    key = ("bwd", nb, Tq, Tk, D, scale)
+    plan = _plans.get(key)
+    if plan is None:
+        kern = tc.attn_dscores_tc(Tq, Tk, D, nb, scale)
+        fn = compiler.get_function(kern.name, kern.source)
+        da, db, dc = tc.tmap_descs(Tq, Tk, D, nb, False, False, False, False, kern.bn)
+        p = shim.lib.dlg_mm_plan_create(fn, kern.grid[0], 1, 1, kern.threads, kern.smem, 1, kern.out_elems * 4,
+                                        matmul_tc._tmap(da), matmul_tc._tmap(db), matmul_tc._tmap(dc))
+        if p == shim.NULL:
+            raise RuntimeError("dlg_mm_plan_create failed: " + shim.last_error())
+        aux = shim.alloc((nb * Tq + Tq * Tk // 32) * 4)          # [rowsum(dO * O) | mask bits], reused by every launch
+        plan = _plans[key] = (p, kern.out_elems * 4, aux, _ops.Plan(ck.rowdot(nb * Tq, D)), _ops.Plan(ck.mask_bits(Tq, Tk)))
+    p, nbytes, aux, dot_plan, bits_plan = plan
+    dot_plan.run_into(aux, _ops._dev_ptr(dO), _ops._dev_ptr(O))
+    bits_plan.run_into(aux + nb * Tq, _ops._dev_ptr(mask))
+    pd, pv, pp = _ops._dev_ptr(dO), _ops._dev_ptr(v), _ops._dev_ptr(P)
+    timer = _profile.matmul_timer
+    t0 = timer.start() if timer is not None else None
+    out = shim.lib.dlg_mm_plan_run_aux(p, pd, pv, pp, aux)
+    if timer is not None:
+        timer.stop(t0, 2.0 * nb * Tq * Tk * D, ("attn_dscores", Tq, Tk, D, nb))
+    if out == shim.NULL:
+        raise RuntimeError("fused attention-backward launch failed: " + shim.last_error())
+    return shim.own(out, nbytes)
+
+
+def bwd_chain_matches(chain: list, out_shape: tuple) -> tuple | None:
+    """[("mfill", _, mask, 0.0), ("scale", _, s)] — the backward of scale -> masked_fill in reverse order."""
+    if len(chain) != 2 or chain[0][0] != "mfill" or chain[1][0] != "scale" or float(chain[0][3]) != 0.0:
+        return None
+    mask = chain[0][2]
+    ms = tuple(mask.metadata.shape)
+    while len(ms) > 2 and ms[0] == 1:
+        ms = ms[1:]
+    if ms != tuple(out_shape[-2:]) or not mask.aligned or mask.scalar is not None:
+        return None
+    return mask, float(chain[1][2])

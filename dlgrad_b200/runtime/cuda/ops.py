@@ -150,6 +150,15 @@ def materialize(buf: Buffer) -> None:
     bp = base._pending
     if bp is not None and bp[0] == "softmax_bwd":
         _, y, g, dim, kind = bp
+        gp = g._pending
+        if gp is not None and gp[0] == "mm" and len(gp) == 4 and kind == "softmax" and y._pending is None:
+            # upstream is the deferred dP = dO @ v^T of an attention block (ops.MatMul.backward): dS in one kernel
+            from dlgrad_b200.runtime.cuda import attention
+            m = attention.bwd_chain_matches(chain, shape)
+            vt = gp[2]
+            if m is not None and vt._pending is not None and vt._pending[0] == "tr" and gp[3] is not None:
+                buf.ptr = attention.dscores(gp[1], vt._pending[1], gp[3], y, m[0], m[1])
+                return
         rows = _rows_of(shape, dim)
         args = _row_chain_args(chain, shape, y.aligned and g.aligned) if rows is not None else None
         if args is not None:

@@ -671,6 +671,47 @@ def test_fused_attention_scores(oracle, B, H, T, D, mask_kind, fill):
                      "deferred q @ k^T materialised")
 
 
+@pytest.mark.parametrize("B,H,T,D,mask_kind", [(2, 16, 512, 64, "causal"), (1, 16, 1024, 32, "random"), (8, 12, 1024, 64, "causal")])
+def test_fused_attention_block_forward_and_backward(oracle, B, H, T, D, mask_kind):
+    """A whole attention block, y = softmax(masked_fill((q @ k^T) * scale, mask, -inf)) @ v, as examples/gpt.py:49-55 writes
+    it.  On CUDA the scores run as one kernel forward (attn_scores_tc) and, in the backward, dP = dO @ v^T is deferred
+    and absorbed together with the softmax / masked_fill / scale backward into one kernel (attn_dscores_tc, using
+    rowsum(dP * P) = rowsum(dO * O)).  Output and dq, dk, dv must match the same graph with the fusions switched off,
+    and — at the smaller sizes — the oracle."""
+    from dlgrad_b200 import Tensor
+    from dlgrad_b200.runtime.cuda import attention
+    rng = np.random.default_rng(T + D + B)
+    q, k, v = ((rng.random((B, H, T, D), dtype=np.float32) - 0.5).astype(np.float32) for _ in range(3))
+    mask = (np.triu(np.ones((T, T), dtype=np.float32), 1) if mask_kind == "causal"
+            else np.minimum((rng.random((T, T)) > 0.6).astype(np.float32), 1.0 - np.eye(T, dtype=np.float32)))   # no dead rows
+    w = np.linspace(0.5, 1.5, B * H * T * D, dtype=np.float32).reshape(B, H, T, D)
+    scale = float(1.0 / np.sqrt(D))
+    compile_only = __import__("tests.conftest", fromlist=["x"]).COMPILE_ONLY
+
+    def run(dev):
+        Q, K, V = (Tensor(a.copy(), device=dev, requires_grad=True) for a in (q, k, v))
+        M = Tensor(mask.copy(), device=dev)
+        att = ((Q @ K.transpose(2, 3)) * scale).masked_fill(M, float("-inf")).softmax(dim=3)
+        y = att @ V
+        (y * Tensor(w.copy(), device=dev)).sum().backward()
+        return [y.numpy(), Q.grad.numpy(), K.grad.numpy(), V.grad.numpy()]
+
+    attention.ENABLED, attention.BWD_ENABLED, bwd_default = True, True, attention.BWD_ENABLED     # the backward twin is opt-in
+    fused = run("cuda")
+    attention.ENABLED, attention.BWD_ENABLED = False, False
+    plain = run("cuda")
+    attention.ENABLED, attention.BWD_ENABLED = True, bwd_default
+    names = ("y", "dq", "dk", "dv")
+    for a, b, what in zip(fused, plain, names):
+        runner.rel_check(check, a, b, SOFTMAX_GRAD_TOL if what != "y" else runner.TOL_MATMUL, f"{what}: fused vs unfused")
+    if B * H * T * T <= (1 << 23):
+        ref = run("cpu")
+        for a, b, what in zip(fused, ref, names):
+            runner.rel_check(check, a, b, 1e-4, f"{what}: fused vs oracle")
+    if not compile_only:
+        assert any(k[0] == "bwd" for k in attention._plans if isinstance(k, tuple)), "expected the fused backward kernel to have run"
+
+
 def test_split_k_weight_gradient_gemm(oracle):
     """x^T @ g with a small output and K = batch*tokens (the Linear weight gradient) runs as split-K: K-slices
     as a batch + an ordered sum (runtime/cuda/matmul.py).  Checked against float64 and, at a smaller K, the oracle."""
