@@ -1555,22 +1555,7 @@ extern "C" __global__ void __launch_bounds__({nthreads}, 1)
         for (unsigned w = blockIdx.x; w < {items}u; w += {grid}u, ++n) {{
             const unsigned z = w / {nq}u;
             {{
-                // The row warps read P with plain loads, one 32-column chunk ahead in registers: far too little in
-                // flight to cover HBM latency (measured 6000-9000 clk per tile).  This otherwise idle warp pulls
-                // the P tiles into L2 a few tiles ahead, so those loads become L2 hits.
-                auto prefetch_p = [&](unsigned jj) {{
-                    const float* pt = Pin + ((size_t)z * {Tq}u + (w % {nq}u) * 128u) * {Tk}u + jj * 128u;
-                    #pragma unroll
-                    for (unsigned r = 0; r < 4u; ++r) {{
-                        const float* pr = pt + (size_t)(lane + r * 32u) * {Tk}u;
-                        #pragma unroll
-                        for (unsigned c = 0; c < 4u; ++c) asm volatile("prefetch.global.L2 [%0];" :: "l"(pr + c * 32u));
-                    }}
-                }};
-                #pragma unroll 1
-                for (unsigned jj = 0; jj < {min(3, nk)}u; ++jj) prefetch_p(jj);
                 for (unsigned j = 0; j < {nk}u; ++j) {{
-                    if (j + {min(3, nk)}u < {nk}u) prefetch_p(j + {min(3, nk)}u);
                     if (j == {nk // 2}u && w + {grid}u < {items}u) load_q(n + 1u, w + {grid}u);
                     for (unsigned kk = 0; kk < {kbq}u; ++kk, ++it) {{
                         const unsigned s = it % {stages}u, ph = (it / {stages}u) & 1u;
@@ -1713,7 +1698,7 @@ extern "C" __global__ void __launch_bounds__({nthreads}, 1)
                     asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {{{regs}}}, [%32];" : {outs} : "r"(taddr));
                     {{   // fetch the chunk {AHEAD} ahead (possibly the next item's) into the box the store before last has left
                         const unsigned g = j * 2u + cc + {AHEAD}u;
-                        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read {NB - AHEAD - 1};" ::: "memory");
                         __syncwarp();
                         if (g < {2 * nk}u) fetch_p(w, g);
                         else if (w + {grid}u < {items}u) fetch_p(w + {grid}u, g - {2 * nk}u);

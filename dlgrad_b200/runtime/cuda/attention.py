@@ -5,7 +5,8 @@ five softmax kernels).  Here `q @ k.transpose(-2, -1)` of attention-shaped opera
 "mm"); if the next consumers are `* scalar`, `masked_fill(mask2d, v)` and `softmax(dim=-1)`, the softmax dispatch
 lands here and ONE tensor-core kernel (codegen/cuda_tcgen05.attn_scores_tc) produces P without S = q @ k^T ever
 existing in HBM.  Any other consumer materialises the deferred product with the ordinary GEMM, so values and
-semantics are those of the eager chain.  DLGRAD_FUSED_SCORES=0 disables the deferral.
+semantics are those of the eager chain.  DLGRAD_FUSED_SCORES=0 / DLGRAD_FUSED_ATTN_BWD=0 disable the forward /
+backward deferral.
 """
 from __future__ import annotations
 
@@ -18,10 +19,9 @@ from dlgrad_b200.runtime.cuda import compiler, shim
 from dlgrad_b200.runtime.cuda import profile as _profile
 
 ENABLED = os.environ.get("DLGRAD_FUSED_SCORES", "1") != "0"
-# The backward twin (attn_dscores_tc: dS from dO, v, P in one kernel, dP never written) is correct but not faster
-# yet — one persistent CTA per SM cannot keep enough of P in flight to cover loaded HBM latency: 221 us + 25 us of
-# helpers against 247 us for GEMM + fused softmax backward at C5 — so it is opt-in.
-BWD_ENABLED = os.environ.get("DLGRAD_FUSED_ATTN_BWD", "0") == "1"
+# The backward twin (attn_dscores_tc: dS from dO, v, P in one kernel, dP never written): 173 us + 25 us of helper
+# kernels against 247 us for GEMM + fused softmax backward at C5; GPT step 34.7 -> 33.9 ms on the same box.
+BWD_ENABLED = os.environ.get("DLGRAD_FUSED_ATTN_BWD", "1") != "0"
 MIN_SCORES = 1 << 22          # elements of (batch, Tq, Tk) below which the eager chain is just as good
 _plans: dict = {}
 
