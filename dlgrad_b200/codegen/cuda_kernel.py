@@ -1030,10 +1030,13 @@ extern "C" __global__ void __launch_bounds__(256) {KNAME}{SIG} {{
 
 @cache
 def mask_bits(rows: int, cols: int) -> Kernel:
-    """out[r][w] (uint32, stored through the float* plan output) = bit e set iff mask[r][32 w + e] > 0.  The fused
-    attention-scores kernel reads a row's mask as 2 words per key tile instead of 64 floats (it is the same
-    (T, T) plane for every head).  p0 = mask (rows, cols), cols % 32 == 0."""
-    words = rows * cols // 32
+    """out[r][w] (uint32, stored through the float* plan output) = bit e set iff mask[r][32 w + e] > 0, followed by one
+    uint32 per (128-row, 128-column) tile that is non-zero iff the tile has an UNMASKED entry.  The fused attention
+    kernels read a row's mask as 2 words per key tile instead of 64 floats (the same (T, T) plane serves every
+    head) and skip tiles that are masked out entirely.  p0 = mask (rows, cols); rows, cols % 128 == 0."""
+    wpr = cols // 32
+    words = rows * wpr
+    nk = cols // 128
     src = f"""
 extern "C" __global__ void __launch_bounds__(256) {KNAME}{SIG} {{
     const unsigned w = blockIdx.x * 256u + threadIdx.x;
@@ -1045,10 +1048,12 @@ extern "C" __global__ void __launch_bounds__(256) {KNAME}{SIG} {{
         const float4 v = __ldg(m + j);
         bits |= ((v.x > 0.f ? 1u : 0u) | (v.y > 0.f ? 2u : 0u) | (v.z > 0.f ? 4u : 0u) | (v.w > 0.f ? 8u : 0u)) << (4u * j);
     }}
-    reinterpret_cast<unsigned*>(out)[w] = bits;
+    unsigned* o = reinterpret_cast<unsigned*>(out);
+    o[w] = bits;
+    if (bits != 0xffffffffu) atomicOr(o + {words}u + ((w / {wpr}u) >> 7) * {nk}u + ((w % {wpr}u) >> 2), 1u);
 }}
 """
-    return Kernel("mask_bits", src, (_cdiv(words, 256), 1, 1), (256, 1, 1), 0, words)
+    return Kernel("mask_bits", src, (_cdiv(words, 256), 1, 1), (256, 1, 1), 0, words + (rows // 128) * nk, zero_out=True)
 
 
 @cache

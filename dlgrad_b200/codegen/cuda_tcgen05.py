@@ -1096,11 +1096,14 @@ def _f32lit(x: float) -> str:
 def attn_scores_tc(Tq: int, Tk: int, D: int, batch: int, scale: float, fill: float) -> TcKernel:
     """q (batch, Tq, D) K-major, k (batch, Tk, D) K-major, out (batch, Tq, Tk).  The mask arrives as bits
     (uint32 [Tq][Tk/32], bit set = masked; cuda_kernel.mask_bits).  Kernel parameters: (tmQ, tmK, tmP, P, bits, unused)."""
+    import math
     import os
     trace = os.environ.get("DLGRAD_TC_TRACE", "0") == "1"      # diagnostic: CTA 0 timestamps its first 32 key tiles
+    nk_ok = Tk // 128 <= 16 and os.environ.get("DLGRAD_ATTN_SKIP", "1") != "0"
 
     def TR(kind, idx, cond="lane == 0u"):
         return f"if (blockIdx.x == 0u && {idx} < 32u && {cond}) trace[{kind}][{idx}] = clock64();" if trace else ""
+    skip = math.isinf(fill) and fill < 0 and nk_ok
     assert Tq % 128 == 0 and Tk % 128 == 0 and Tk <= 2048 and D in (32, 64) and scale > 0      # D <= 64: 2 Q buffers + 2 S buffers fill TMEM
     kbq = D // 32                                   # k-blocks per tile
     BN = 128
@@ -1155,6 +1158,13 @@ extern "C" __global__ void __launch_bounds__({nthreads}, 1)
     {"__shared__ long long trace[5][32];" if trace else ""}
     const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
 
+    // key tiles with at least one unmasked entry, as a bit mask per query tile (from cuda_kernel.mask_bits); a tile that
+    // is masked out entirely is never loaded, multiplied or read — under a causal mask that is 28 of 64 tile pairs.
+    // Only when the fill value is -inf (a masked entry then contributes exactly nothing to the row sum).
+    auto live_tiles = [&](unsigned ww) -> unsigned {{
+        {"const unsigned* tf = mask + " + str(Tq * Tk // 32) + "u + (ww % " + str(nq) + "u) * " + str(nk) + "u; unsigned lm = 0u; for (unsigned j = 0; j < " + str(nk) + "u; ++j) lm |= (__ldg(tf + j) != 0u ? 1u : 0u) << j; return lm;" if skip else "return " + str((1 << nk) - 1) + "u;"}
+    }};
+
     if (threadIdx.x == 0) {{
         for (unsigned s = 0; s < {stages}u; ++s) {{
             mbar_init(kfull + s * 8u, 1u);
@@ -1198,9 +1208,11 @@ extern "C" __global__ void __launch_bounds__({nthreads}, 1)
         if (blockIdx.x < {items}u) load_q(0u, blockIdx.x);
         for (unsigned w = blockIdx.x; w < {items}u; w += {grid}u, ++n) {{
             const unsigned z = w / {nq}u;
+            const unsigned lm = live_tiles(w);
             for (unsigned pass = 0; pass < 2u; ++pass) {{
                 if (pass == 1u && w + {grid}u < {items}u) load_q(n + 1u, w + {grid}u);
                 for (unsigned j = 0; j < {nk}u; ++j) {{
+                    if (!((lm >> j) & 1u)) continue;
                     for (unsigned kk = 0; kk < {kbq}u; ++kk, ++it) {{
                         const unsigned s = it % {stages}u, ph = (it / {stages}u) & 1u;
                         mbar_wait(kempty + s * 8u, ph ^ 1u);
@@ -1223,7 +1235,9 @@ extern "C" __global__ void __launch_bounds__({nthreads}, 1)
             mbar_wait(qsplit + qb * 8u, (n >> 1) & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const unsigned q_t = tmem_base + {q_tmem0}u + qb * {kbq * 64}u;
-            for (unsigned pj = 0; pj < {2 * nk}u; ++pj, ++u) {{
+            const unsigned lm = live_tiles(w);
+            for (unsigned pj = 0; pj < {2 * nk}u; ++pj) {{
+                if (!((lm >> (pj % {nk}u)) & 1u)) continue;
                 const unsigned b = u & 1u;
                 mbar_wait(sempty + b * 8u, ((u >> 1) & 1u) ^ 1u);
                 {TR(0, "u")}
@@ -1249,6 +1263,7 @@ extern "C" __global__ void __launch_bounds__({nthreads}, 1)
                     __syncwarp();
                 }}
                 {TR(1, "u")}
+                ++u;
             }}
             if (elect_one()) umma_commit(qfree + qb * 8u);
             __syncwarp();
@@ -1307,6 +1322,7 @@ extern "C" __global__ void __launch_bounds__({nthreads}, 1)
                 }}
             }}
             float m = __int_as_float(0xff800000), l = 0.f, inv_l = 0.f;
+            const unsigned lm = live_tiles(w);
             for (unsigned pass = 0; pass < 2u; ++pass) {{
                 if (pass == 1u) {{
                     // combine the two column halves of every row: (m, l) of the partner warp through shared memory
@@ -1325,7 +1341,24 @@ extern "C" __global__ void __launch_bounds__({nthreads}, 1)
                     inv_l = 1.f / l;
                     if (half == 0u && w + {grid}u < {items}u) split_q(n + 1u);   // next item's Q while the MMAs run pass 1
                 }}
-                for (unsigned j = 0; j < {nk}u; ++j, ++u) {{
+                for (unsigned j = 0; j < {nk}u; ++j) {{
+                    if (!((lm >> j) & 1u)) {{
+                        // a key tile that is masked out entirely: nothing for the row sums (fill = -inf); in pass 1 its
+                        // probabilities are the per-row constant 2^(-inf - m) / l = 0 (NaN for a row with no live
+                        // entry at all, like the unfused kernel), stored straight from registers, eight lanes per row
+                        if (pass == 1u) {{
+                            const float pv = ex2({fl} - m) * inv_l;
+                            float* dst = P + ((size_t)z * {Tq}u + q0 + sq * 32u + (lane >> 3)) * {Tk}u + j * 128u + half * 64u + (lane & 7u) * 4u;
+                            #pragma unroll
+                            for (unsigned i = 0; i < 8u; ++i) {{
+                                const float pr = __shfl_sync(0xffffffffu, pv, 4u * i + (lane >> 3));
+                                const float4 o4 = make_float4(pr, pr, pr, pr);
+                                *reinterpret_cast<float4*>(dst + (size_t)(4u * i) * {Tk}u) = o4;
+                                *reinterpret_cast<float4*>(dst + (size_t)(4u * i) * {Tk}u + 32u) = o4;
+                            }}
+                        }}
+                        continue;
+                    }}
                     const unsigned b = u & 1u;
                     mbar_wait(sfull + b * 8u, (u >> 1) & 1u);
                     {TR(2, "u", "threadIdx.x == 64u")}
@@ -1401,6 +1434,7 @@ extern "C" __global__ void __launch_bounds__({nthreads}, 1)
                     __syncwarp();
                     if (lane == 0) mbar_arrive(sempty + b * 8u);
                     {TR(3, "u", "threadIdx.x == 64u")}
+                    ++u;
                 }}
             }}
         }}
@@ -1410,7 +1444,8 @@ extern "C" __global__ void __launch_bounds__({nthreads}, 1)
         const unsigned ctid = threadIdx.x - 320u;
         unsigned it = 0;
         for (unsigned w = blockIdx.x; w < {items}u; w += {grid}u) {{
-            for (unsigned i2 = 0; i2 < {2 * nk * kbq}u; ++i2, ++it) {{
+            const unsigned nlive = __popc(live_tiles(w));
+            for (unsigned i2 = 0; i2 < 2u * nlive * {kbq}u; ++i2, ++it) {{
                 const unsigned s = it % {stages}u, ph = (it / {stages}u) & 1u;
                 mbar_wait(kfull + s * 8u, ph);
                 const float4* bsrc = reinterpret_cast<const float4*>(smem_gen + {q_bytes}u + s * {per_stage}u);
@@ -1453,6 +1488,7 @@ def attn_dscores_tc(Tq: int, Tk: int, D: int, batch: int, scale: float) -> TcKer
     fill = 0.0
     import os
     trace = os.environ.get("DLGRAD_TC_TRACE", "0") == "1"      # diagnostic: CTA 0 timestamps its first 32 key tiles
+    skip = Tk // 128 <= 16 and os.environ.get("DLGRAD_ATTN_SKIP", "1") != "0"
 
     def TR(kind, idx, cond="lane == 0u"):
         return f"if (blockIdx.x == 0u && {idx} < 32u && {cond}) trace[{kind}][{idx}] = clock64();" if trace else ""
@@ -1511,6 +1547,12 @@ extern "C" __global__ void __launch_bounds__({nthreads}, 1)
     {"__shared__ long long trace[5][32];" if trace else ""}
     const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
 
+    // key tiles with at least one unmasked entry, one bit per tile (cuda_kernel.mask_bits): dS of a tile that is masked out
+    // entirely is zero whatever P and dP hold, so such a tile is neither loaded nor multiplied nor read — just zeroed
+    auto live_tiles = [&](unsigned ww) -> unsigned {{
+        {"const unsigned* tf = reinterpret_cast<const unsigned*>(aux + " + str(batch * Tq) + "u) + " + str(Tq * Tk // 32) + "u + (ww % " + str(nq) + "u) * " + str(nk) + "u; unsigned lm = 0u; for (unsigned j = 0; j < " + str(nk) + "u; ++j) lm |= (__ldg(tf + j) != 0u ? 1u : 0u) << j; return lm;" if skip else "return " + str((1 << nk) - 1) + "u;"}
+    }};
+
     if (threadIdx.x == 0) {{
         for (unsigned s = 0; s < {stages}u; ++s) {{
             mbar_init(kfull + s * 8u, 1u);
@@ -1555,8 +1597,10 @@ extern "C" __global__ void __launch_bounds__({nthreads}, 1)
         for (unsigned w = blockIdx.x; w < {items}u; w += {grid}u, ++n) {{
             const unsigned z = w / {nq}u;
             {{
+                const unsigned lm = live_tiles(w);
+                if (w + {grid}u < {items}u) load_q(n + 1u, w + {grid}u);       // (waits for the MMAs of item n - 1 only)
                 for (unsigned j = 0; j < {nk}u; ++j) {{
-                    if (j == {nk // 2}u && w + {grid}u < {items}u) load_q(n + 1u, w + {grid}u);
+                    if (!((lm >> j) & 1u)) continue;
                     for (unsigned kk = 0; kk < {kbq}u; ++kk, ++it) {{
                         const unsigned s = it % {stages}u, ph = (it / {stages}u) & 1u;
                         mbar_wait(kempty + s * 8u, ph ^ 1u);
@@ -1579,7 +1623,9 @@ extern "C" __global__ void __launch_bounds__({nthreads}, 1)
             mbar_wait(qsplit + qb * 8u, (n >> 1) & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const unsigned q_t = tmem_base + {q_tmem0}u + qb * {kbq * 64}u;
-            for (unsigned pj = 0; pj < {nk}u; ++pj, ++u) {{
+            const unsigned lm = live_tiles(w);
+            for (unsigned pj = 0; pj < {nk}u; ++pj) {{
+                if (!((lm >> pj) & 1u)) continue;
                 const unsigned b = u & 1u;
                 mbar_wait(sempty + b * 8u, ((u >> 1) & 1u) ^ 1u);
                 {TR(0, "u")}
@@ -1605,6 +1651,7 @@ extern "C" __global__ void __launch_bounds__({nthreads}, 1)
                     __syncwarp();
                 }}
                 {TR(1, "u")}
+                ++u;
             }}
             if (elect_one()) umma_commit(qfree + qb * 8u);
             __syncwarp();
@@ -1617,7 +1664,7 @@ extern "C" __global__ void __launch_bounds__({nthreads}, 1)
         const unsigned half = (warp >= 6u) ? 1u : 0u;               // which 64 columns of a key tile
         const unsigned my_epi = epi + (warp - 2u) * {NB * 4096}u;
         unsigned char* my_epi_gen = smem_gen + {q_bytes + stages * per_stage}u + (warp - 2u) * {NB * 4096}u;
-        unsigned nstore = 0, nfetch = 0;
+        unsigned nstore = 0, nfetch = 0, fw = 0, fg = 0, flm = 0;      // fetch cursor: item, live-chunk index, its live mask
         unsigned u = 0, n = 0;
 
         auto split_q = [&](unsigned nn) {{
@@ -1668,24 +1715,51 @@ extern "C" __global__ void __launch_bounds__({nthreads}, 1)
             // last has left it): 8 KiB per warp, 64 KiB per SM in
             // flight.  One chunk ahead in registers left the loads latency-bound (6000-9000 clk per key tile), and a
             // thread reading its own row directly touches 32 cache lines per load.
-            auto fetch_p = [&](unsigned ww, unsigned g) {{          // chunk g = (key tile g / 2, column quarter half * 2 + g % 2) of item ww
+            auto fetch_p = [&](unsigned ww, unsigned jt, unsigned cq) {{      // 32 columns cq (0/1) of this warp's half of key tile jt, item ww
                 const unsigned zz = ww / {nq}u, qq0 = (ww % {nq}u) * 128u;
-                const float* src = Pin + ((size_t)zz * {Tq}u + qq0 + sq * 32u + (lane >> 3)) * {Tk}u + (g >> 1) * 128u + half * 64u + (g & 1u) * 32u + (lane & 7u) * 4u;
+                const float* src = Pin + ((size_t)zz * {Tq}u + qq0 + sq * 32u + (lane >> 3)) * {Tk}u + jt * 128u + half * 64u + cq * 32u + (lane & 7u) * 4u;
                 const unsigned box = my_epi + (nfetch % {NB}u) * 4096u;
                 #pragma unroll
                 for (unsigned i = 0; i < 8u; ++i) {{
                     const unsigned r = 4u * i + (lane >> 3);
                     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(box + r * 128u + (((lane & 7u) ^ (r & 7u)) << 4)), "l"(src + (size_t)(4u * i) * {Tk}u) : "memory");
                 }}
-                asm volatile("cp.async.commit_group;" ::: "memory");
+            }};
+            // the fetch cursor runs {AHEAD} live chunks ahead of the chunk being processed, across work items
+            auto fetch_next = [&]() {{
+                while (fw < {items}u && fg >= 2u * __popc(flm)) {{ fw += {grid}u; fg = 0u; flm = (fw < {items}u) ? live_tiles(fw) : 0u; }}
+                if (fw < {items}u) {{
+                    unsigned t = flm, k = fg >> 1;
+                    while (k--) t &= t - 1u;                         // drop the k lowest live tiles
+                    fetch_p(fw, __ffs(t) - 1u, fg & 1u);
+                    ++fg;
+                }}
+                asm volatile("cp.async.commit_group;" ::: "memory");   // (an empty group keeps the count in step)
                 ++nfetch;
             }};
+            const unsigned lm = live_tiles(w);
             if (n == 0u) {{
+                fw = w; fg = 0u; flm = lm;
                 #pragma unroll 1
-                for (unsigned g = 0; g < {AHEAD}u; ++g) fetch_p(w, g);
+                for (unsigned g = 0; g < {AHEAD}u; ++g) fetch_next();
             }}
-            for (unsigned j = 0; j < {nk}u; ++j, ++u) {{
-                if (half == 0u && j == {nk // 2}u && w + {grid}u < {items}u) split_q(n + 1u);   // next item's dO while the MMAs go on
+            // dead key tiles: zeros straight from registers, eight lanes per 128-byte row
+            for (unsigned j = 0; j < {nk}u; ++j) {{
+                if ((lm >> j) & 1u) continue;
+                float* dst = P + ((size_t)z * {Tq}u + q0 + sq * 32u + (lane >> 3)) * {Tk}u + j * 128u + half * 64u + (lane & 7u) * 4u;
+                const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                #pragma unroll
+                for (unsigned i = 0; i < 8u; ++i) {{
+                    *reinterpret_cast<float4*>(dst + (size_t)(4u * i) * {Tk}u) = z4;
+                    *reinterpret_cast<float4*>(dst + (size_t)(4u * i) * {Tk}u + 32u) = z4;
+                }}
+            }}
+            const unsigned nlive = __popc(lm);
+            unsigned kdone = 0;
+            if (nlive == 0u && half == 0u && w + {grid}u < {items}u) split_q(n + 1u);
+            for (unsigned j = 0; j < {nk}u; ++j) {{
+                if (!((lm >> j) & 1u)) continue;
+                if (kdone++ == nlive / 2u && half == 0u && w + {grid}u < {items}u) split_q(n + 1u);   // next item's dO, mid-item
                 const unsigned b = u & 1u;
                 mbar_wait(sfull + b * 8u, (u >> 1) & 1u);
                 {TR(2, "u", "threadIdx.x == 64u")}
@@ -1696,13 +1770,10 @@ extern "C" __global__ void __launch_bounds__({nthreads}, 1)
                     unsigned v[32];
                     const unsigned taddr = tmem_base + ((sq * 32u) << 16) + b * {BN}u + c * 32u;
                     asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {{{regs}}}, [%32];" : {outs} : "r"(taddr));
-                    {{   // fetch the chunk {AHEAD} ahead (possibly the next item's) into the box the store before last has left
-                        const unsigned g = j * 2u + cc + {AHEAD}u;
+                    {{   // fetch the live chunk {AHEAD} ahead (possibly the next item's) into the box the store before last has left
                         if (lane == 0) asm volatile("cp.async.bulk.wait_group.read {NB - AHEAD - 1};" ::: "memory");
                         __syncwarp();
-                        if (g < {2 * nk}u) fetch_p(w, g);
-                        else if (w + {grid}u < {items}u) fetch_p(w + {grid}u, g - {2 * nk}u);
-                        else {{ asm volatile("cp.async.commit_group;" ::: "memory"); ++nfetch; }}      // keep the group count in step
+                        fetch_next();
                     }}
                     asm volatile("cp.async.wait_group {AHEAD};" ::: "memory");          // this chunk's P has landed (my copies)
                     __syncwarp();                                                          // ... and everybody else's
@@ -1734,6 +1805,7 @@ extern "C" __global__ void __launch_bounds__({nthreads}, 1)
                 __syncwarp();
                 if (lane == 0) mbar_arrive(sempty + b * 8u);
                 {TR(3, "u", "threadIdx.x == 64u")}
+                ++u;
             }}
         }}
         if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
@@ -1742,7 +1814,8 @@ extern "C" __global__ void __launch_bounds__({nthreads}, 1)
         const unsigned ctid = threadIdx.x - 320u;
         unsigned it = 0;
         for (unsigned w = blockIdx.x; w < {items}u; w += {grid}u) {{
-            for (unsigned i2 = 0; i2 < {nk * kbq}u; ++i2, ++it) {{
+            const unsigned nlive = __popc(live_tiles(w));
+            for (unsigned i2 = 0; i2 < nlive * {kbq}u; ++i2, ++it) {{
                 const unsigned s = it % {stages}u, ph = (it / {stages}u) & 1u;
                 mbar_wait(kfull + s * 8u, ph);
                 const float4* bsrc = reinterpret_cast<const float4*>(smem_gen + {q_bytes}u + s * {per_stage}u);

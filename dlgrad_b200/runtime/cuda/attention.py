@@ -106,7 +106,7 @@ def dscores(dO: Buffer, v: Buffer, O: Buffer, P: Buffer, mask: Buffer, scale: fl
                                         matmul_tc._tmap(da), matmul_tc._tmap(db), matmul_tc._tmap(dc))
         if p == shim.NULL:
             raise RuntimeError("dlg_mm_plan_create failed: " + shim.last_error())
-        aux = shim.alloc((nb * Tq + Tq * Tk // 32) * 4)          # [rowsum(dO * O) | mask bits], reused by every launch
+        aux = shim.alloc((nb * Tq + Tq * Tk // 32 + (Tq // 128) * (Tk // 128)) * 4)   # [rowsum(dO * O) | mask bits | live tiles]
         plan = _plans[key] = (p, kern.out_elems * 4, aux, _ops.Plan(ck.rowdot(nb * Tq, D)), _ops.Plan(ck.mask_bits(Tq, Tk)))
     p, nbytes, aux, dot_plan, bits_plan = plan
     dot_plan.run_into(aux, _ops._dev_ptr(dO), _ops._dev_ptr(O))
