@@ -377,7 +377,11 @@ class Buffer:
     # fused row ops (CUDA backend); a host runtime may register the 5-op composition
     def softmax(self, dim: int) -> "Buffer":
         dev = Buffer._route(self)
-        return self._like(_dispatch(op=UnaryOps.SOFTMAX, device=dev, x=self, dim=dim), self.shape, dev)
+        out = self._like(_dispatch(op=UnaryOps.SOFTMAX, device=dev, x=self, dim=dim), self.shape, dev)
+        if dev is _CUDA:
+            from dlgrad_b200.runtime.cuda import attention
+            attention.claim(out)                 # P from the fused scores kernel carries its live-tile table
+        return out
 
     def log_softmax(self, dim: int) -> "Buffer":
         dev = Buffer._route(self)

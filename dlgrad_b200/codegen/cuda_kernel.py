@@ -1030,13 +1030,19 @@ extern "C" __global__ void __launch_bounds__(256) {KNAME}{SIG} {{
 
 @cache
 def mask_bits(rows: int, cols: int) -> Kernel:
-    """out[r][w] (uint32, stored through the float* plan output) = bit e set iff mask[r][32 w + e] > 0, followed by one
-    uint32 per (128-row, 128-column) tile that is non-zero iff the tile has an UNMASKED entry.  The fused attention
-    kernels read a row's mask as 2 words per key tile instead of 64 floats (the same (T, T) plane serves every
-    head) and skip tiles that are masked out entirely.  p0 = mask (rows, cols); rows, cols % 128 == 0."""
+    """The attention mask, digested once per call for the fused attention kernels (the same (T, T) plane serves
+    every head).  Output, as uint32 words behind the float* plan output:
+        [rows * cols / 32]     bit e of word (r, w) set iff mask[r][32 w + e] > 0
+        [rows/128 * cols/128]  non-zero iff that 128 x 128 tile has an UNMASKED entry ("live")
+        [rows]                 non-zero iff that row has an unmasked entry
+        [1]                    number of rows that have one
+    A row's mask is then 2 words per key tile instead of 64 floats, dead tiles are skipped, and the k-sparse GEMMs
+    that consume P / dS know whether some row is fully masked (its probabilities are NaN, nothing may be skipped).
+    p0 = mask (rows, cols); rows, cols % 128 == 0."""
     wpr = cols // 32
     words = rows * wpr
     nk = cols // 128
+    tiles = (rows // 128) * nk
     src = f"""
 extern "C" __global__ void __launch_bounds__(256) {KNAME}{SIG} {{
     const unsigned w = blockIdx.x * 256u + threadIdx.x;
@@ -1050,10 +1056,14 @@ extern "C" __global__ void __launch_bounds__(256) {KNAME}{SIG} {{
     }}
     unsigned* o = reinterpret_cast<unsigned*>(out);
     o[w] = bits;
-    if (bits != 0xffffffffu) atomicOr(o + {words}u + ((w / {wpr}u) >> 7) * {nk}u + ((w % {wpr}u) >> 2), 1u);
+    if (bits != 0xffffffffu) {{
+        const unsigned r = w / {wpr}u;
+        atomicOr(o + {words}u + (r >> 7) * {nk}u + ((w % {wpr}u) >> 2), 1u);
+        if (atomicOr(o + {words + tiles}u + r, 1u) == 0u) atomicAdd(o + {words + tiles + rows}u, 1u);
+    }}
 }}
 """
-    return Kernel("mask_bits", src, (_cdiv(words, 256), 1, 1), (256, 1, 1), 0, words + (rows // 128) * nk, zero_out=True)
+    return Kernel("mask_bits", src, (_cdiv(words, 256), 1, 1), (256, 1, 1), 0, words + tiles + rows + 1, zero_out=True)
 
 
 @cache

@@ -716,7 +716,7 @@ def pick_bn_ts(M: int, N: int, batch: int, kblocks: int) -> int:
 @cache
 def matmul_tc_ts(M: int, N: int, K: int, batch: int, a_mn: bool, b_mn: bool, a_bcast: bool, b_bcast: bool,
                  bn: int | None = None, stages: int | None = None, kc_blocks: int | None = None,
-                 bias: bool = False, issuers: int | None = None, streamk: bool = False) -> TcKernel:
+                 bias: bool = False, issuers: int | None = None, streamk: bool = False, ksparse: str | None = None) -> TcKernel:
     """Kernel parameters after C: `bias` (a length-N row the epilogue adds to every output row when `bias` is
     set — the Linear bias; it rides on the plain store) and `flags` (uint32[ntiles * 4], zero, used when
     `streamk` is set).
@@ -726,7 +726,14 @@ def matmul_tc_ts(M: int, N: int, K: int, batch: int, a_mn: bool, b_mn: bool, a_b
     is finished by two CTAs: the one holding its k-tail meets it FIRST in its range, stores the partial sum
     and raises flags[tile][quarter]; the one holding its k-head meets it LAST, waits for the flag (long
     since raised) and TMA-reduce-adds its partial.  Two addends in fixed roles -> the sum is deterministic.
-    Requires ntiles >= grid (every range at least one tile long, so no tile has three owners)."""
+    Requires ntiles >= grid (every range at least one tile long, so no tile has three owners).
+
+    ksparse ("nn" | "tn"): the A operand is an attention matrix (P or dS, query rows x key columns; "tn" = it is read
+    transposed) whose 128 x 128 tiles that the mask kills entirely are exactly zero.  `flags` then points at the
+    live-tile table of cuda_kernel.mask_bits ([query tiles][key tiles], then one word per query row, then the number
+    of query rows that have a live entry): k-blocks inside dead tiles are neither loaded, split nor multiplied —
+    under a causal mask 28 of 64 tile pairs.  If some query row has no live entry at all its probabilities are NaN,
+    not zero, and nothing is skipped (the NaN must reach the output like in the dense product)."""
     import os
     tmode = os.environ.get("DLGRAD_TC_TRACE", "0")            # diagnostic: CTA 0 timestamps its first 32 k-blocks
     trace = tmode in ("1", "2", "3")                          # 1 = one stamp per pipeline role, 2 = inside the MMA warp,
@@ -769,13 +776,30 @@ def matmul_tc_ts(M: int, N: int, K: int, batch: int, a_mn: bool, b_mn: bool, a_b
     b_boxes = BN // 32 if b_mn else 1
     grid = min(ntiles, NUM_SMS)
     units = ntiles * kblocks
+    if ksparse:
+        assert not streamk and nchunks == 1 and M % 128 == 0 and K % 128 == 0 and K <= 4096, (M, K, nchunks)
+        kt_n = K // 128                                      # tiles along K
+        q_tiles, k_tiles = (M // 128, kt_n) if ksparse == "nn" else (kt_n, M // 128)
+        q_rows = q_tiles * 128
+        idx = f"mt_ * {k_tiles}u + kt" if ksparse == "nn" else f"kt * {k_tiles}u + mt_"
+        sp_decl = f"""
+            const unsigned mt_ = (t % {ntm * ntn}u) / {ntn}u;
+            unsigned lk = {(1 << kt_n) - 1 if kt_n < 32 else 0xffffffff}u;
+            if (sp_on) {{ lk = 0u; for (unsigned kt = 0; kt < {kt_n}u; ++kt) lk |= (__ldg(flags + {idx}) != 0u ? 1u : 0u) << kt; }}
+            const unsigned last_kb = lk ? (31u - __clz(lk)) * 4u + 3u : 0xffffffffu;"""
+        sp_on = f"const bool sp_on = __ldg(flags + {q_tiles * k_tiles + q_rows}u) == {q_rows}u;      // every query row has a live entry"
+        dead = "if (!((lk >> (kb >> 2)) & 1u)) {{ --it; continue; }}"
+        dead_mma = "if (!((lk >> (kb >> 2)) & 1u)) {{ --it; --kbl; continue; }}"
+        last_kb = "kb == last_kb"
+    else:
+        sp_decl, sp_on, dead, dead_mma, last_kb = "", "", "", "", "kb + 1u == kend"
     if streamk:
         assert ntiles >= grid and units < (1 << 30), (ntiles, grid)
         seg_open = f"""for (unsigned u = u_begin, t, kb0, kb1; u < u_end; u += kb1 - kb0) {{
             t = u / {kblocks}u; kb0 = u - t * {kblocks}u; kb1 = min({kblocks}u, kb0 + (u_end - u));"""
     else:
         seg_open = f"""for (unsigned t = blockIdx.x; t < {ntiles}u; t += {grid}u) {{
-            const unsigned kb0 = 0u, kb1 = {kblocks}u;"""
+            const unsigned kb0 = 0u, kb1 = {kblocks}u;""" + sp_decl
     nthreads = 64 + 128 + 128 + 128 + (32 if NI == 2 else 0)   # producer, MMA | 4 A-split | 4 B-split | 4 epilogue | 2nd MMA issuer
     epi_w0 = 10
 
@@ -849,6 +873,29 @@ def matmul_tc_ts(M: int, N: int, K: int, batch: int, a_mn: bool, b_mn: bool, a_b
             }"""
     else:
         sk_seg_begin, sk_seg_end = "const bool seg_head = false;", ""
+    zero_tile = "" if not ksparse else f"""if (lk == 0u) {{
+                    // every k-block of this output tile lies in a dead attention tile: the product is exactly zero
+                    #pragma unroll 1
+                    for (unsigned c = 0; c < {BN // 32}u; ++c) {{
+                        if (n0 + c * 32u < {N}u && m0 + q * 32u < {M}u) {{
+                            const unsigned sb = nstore & {EPI_BUFS - 1}u;
+                            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read {EPI_BUFS - 1};" ::: "memory");
+                            __syncwarp();
+                            float4* zb = reinterpret_cast<float4*>(my_epi_gen + sb * 4096u);
+                            #pragma unroll
+                            for (unsigned j = 0; j < 8u; ++j) zb[lane * 8u + j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                            __syncwarp();
+                            if (lane == 0) {{
+                                tma_store_3d(&tmC, my_epi + sb * 4096u, (int)(n0 + c * 32u), (int)(m0 + q * 32u), (int)z);
+                                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                            }}
+                            ++nstore;
+                        }}
+                    }}
+                    --ua;
+                    continue;
+                }}"""
     regs = ", ".join(f"%{i}" for i in range(32))
     outs = ", ".join(f'"=r"(v[{i}])' for i in range(32))
     stage_writes = "\n                    ".join(
@@ -894,6 +941,7 @@ extern "C" __global__ void __launch_bounds__({nthreads}, 1)
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const unsigned tmem_base = tmem_slot;
+    {sp_on}
 
     if (warp == 0) {{
         // ===== TMA producer: the warp walks the ring together, one elected lane issues =====
@@ -902,6 +950,7 @@ extern "C" __global__ void __launch_bounds__({nthreads}, 1)
             {seg_open}
                 {decode}
                 for (unsigned kb = kb0; kb < kb1; ++kb, ++it) {{
+                    {dead}
                     const unsigned s = it % {stages}u, ph = (it / {stages}u) & 1u;
                     mbar_wait(empty + s * 8u, ph ^ 1u);
                     {TR(0, "lane == 0u")}
@@ -930,10 +979,12 @@ extern "C" __global__ void __launch_bounds__({nthreads}, 1)
             const unsigned a_tmem = tmem_base + {a_tmem0}u;
             {seg_open}
                 for (unsigned cs = kb0; cs < kb1; cs += {kc}u, ++ua) {{
+                    {"if (lk == 0u) { --ua; continue; }      // no live k-block: the epilogue zero-fills, no accumulator is used" if ksparse else ""}
                     const unsigned b = ua % {acc_bufs}u;
                     const unsigned tacc = tmem_base + b * {BN}u;
                     const unsigned kend = min(cs + {kc}u, kb1);
                     for (unsigned kb = cs, kbl = 0; kb < kend; ++kb, ++kbl, ++it) {{
+                        {dead_mma}
                         if ({NI}u == 2u && (it & 1u) != me) continue;
                         if (kbl == 0u) {{
                             mbar_wait(tempty + b * 8u, ((ua / {acc_bufs}u) & 1u) ^ 1u);      // epilogue has drained this accumulator
@@ -956,7 +1007,7 @@ extern "C" __global__ void __launch_bounds__({nthreads}, 1)
                             }}
                             {"mbar_arrive(turn + (me ^ 1u) * 8u);" if NI == 2 else ""}
                             umma_commit(empty + s * 8u);
-                            if (kb + 1u == kend) umma_commit(tfull + b * 8u);      // in-order pipe: the other issuer's earlier MMAs are done too
+                            if ({last_kb}) umma_commit(tfull + b * 8u);      // in-order pipe: the other issuer's earlier MMAs are done too
                         }}
                         __syncwarp();
                         {TR(4, "lane == 0u")}
@@ -971,6 +1022,7 @@ extern "C" __global__ void __launch_bounds__({nthreads}, 1)
         unsigned it = 0;
         {seg_open}
             for (unsigned kb = kb0; kb < kb1; ++kb, ++it) {{
+                {dead}
                 const unsigned s = it % {stages}u, ph = (it / {stages}u) & 1u;
                 mbar_wait(full + s * 8u, ph);
                 {TR(1, "threadIdx.x == 64u")}
@@ -998,6 +1050,7 @@ extern "C" __global__ void __launch_bounds__({nthreads}, 1)
         unsigned it = 0;
         {seg_open}
             for (unsigned kb = kb0; kb < kb1; ++kb, ++it) {{
+                {dead}
                 const unsigned s = it % {stages}u, ph = (it / {stages}u) & 1u;
                 mbar_wait(full + s * 8u, ph);
                 const float4* bsrc = reinterpret_cast<const float4*>(smem_gen + s * {per_stage}u + {a_tile}u);
@@ -1027,6 +1080,7 @@ extern "C" __global__ void __launch_bounds__({nthreads}, 1)
             {decode}
             {sk_seg_begin}
             for (unsigned cs = kb0; cs < kb1; cs += {kc}u, ++ua) {{
+                {zero_tile}
                 const unsigned b = ua % {acc_bufs}u;
                 const bool plain = (cs == kb0) && !seg_head;       // this chunk STORES; every other one reduce-adds
                 mbar_wait(tfull + b * 8u, (ua / {acc_bufs}u) & 1u);
@@ -1072,7 +1126,7 @@ extern "C" __global__ void __launch_bounds__({nthreads}, 1)
     }}
 }}
 """
-    return TcKernel("mm_tcts" + ("_b" if bias else "") + ("_sk" if streamk else ""), src, (grid, 1, 1), nthreads, smem, batch * M * N, BN, stages)
+    return TcKernel("mm_tcts" + ("_b" if bias else "") + ("_sk" if streamk else "") + (f"_sp{ksparse}" if ksparse else ""), src, (grid, 1, 1), nthreads, smem, batch * M * N, BN, stages)
 
 
 # =====================================================================================================

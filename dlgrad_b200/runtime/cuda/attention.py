@@ -18,7 +18,33 @@ from dlgrad_b200.helpers import prod_
 from dlgrad_b200.runtime.cuda import compiler, shim
 from dlgrad_b200.runtime.cuda import profile as _profile
 
+import weakref
+
 ENABLED = os.environ.get("DLGRAD_FUSED_SCORES", "1") != "0"
+SPARSE = os.environ.get("DLGRAD_ATTN_SPARSE_GEMM", "1") != "0"
+# P and dS produced by the fused kernels carry their live-tile table: the GEMMs that read them (P @ v, P^T @ dO,
+# dS @ k, dS^T @ q) skip the k-blocks of tiles the mask kills entirely (codegen/cuda_tcgen05.matmul_tc_ts, ksparse)
+_tags: dict = {}             # id(Buffer) -> table (Buffer.__eq__ is the elementwise op, so no dict keyed by the object itself)
+_fresh: dict = {}            # device address of a just produced P / dS -> (owner of the table, table pointer, Tq, Tk)
+
+
+def mask_words(Tq: int, Tk: int) -> int:
+    return Tq * Tk // 32 + (Tq // 128) * (Tk // 128) + Tq + 1
+
+
+def claim(buf: Buffer) -> None:
+    """Attach the live-tile table of a freshly produced P / dS to the Buffer that now owns the pointer."""
+    if _fresh:
+        info = _fresh.pop(shim.address(buf._ptr), None)
+        _fresh.clear()
+        if info is not None:
+            _tags[id(buf)] = info
+            weakref.finalize(buf, _tags.pop, id(buf), None)
+
+
+def tag_of(buf: Buffer):
+    return _tags.get(id(buf)) if SPARSE else None
+
 # The backward twin (attn_dscores_tc: dS from dO, v, P in one kernel, dP never written): 173 us + 25 us of helper
 # kernels against 247 us for GEMM + fused softmax backward at C5; GPT step 34.7 -> 33.9 ms on the same box.
 BWD_ENABLED = os.environ.get("DLGRAD_FUSED_ATTN_BWD", "1") != "0"
@@ -87,7 +113,9 @@ def scores(q: Buffer, k: Buffer, scale: float, mask: Buffer, fill: float):
         timer.stop(t0, 2.0 * nb * Tq * Tk * D, ("attn_scores", Tq, Tk, D, nb))
     if out == shim.NULL:
         raise RuntimeError("fused attention-scores launch failed: " + shim.last_error())
-    return shim.own(out, nbytes)
+    res = shim.own(out, nbytes)
+    _fresh[shim.address(res)] = (bits, bits + Tq * Tk // 32, Tq, Tk)
+    return res
 
 
 def dscores(dO: Buffer, v: Buffer, O: Buffer, P: Buffer, mask: Buffer, scale: float):
@@ -106,9 +134,9 @@ def dscores(dO: Buffer, v: Buffer, O: Buffer, P: Buffer, mask: Buffer, scale: fl
                                         matmul_tc._tmap(da), matmul_tc._tmap(db), matmul_tc._tmap(dc))
         if p == shim.NULL:
             raise RuntimeError("dlg_mm_plan_create failed: " + shim.last_error())
-        aux = shim.alloc((nb * Tq + Tq * Tk // 32 + (Tq // 128) * (Tk // 128)) * 4)   # [rowsum(dO * O) | mask bits | live tiles]
-        plan = _plans[key] = (p, kern.out_elems * 4, aux, _ops.Plan(ck.rowdot(nb * Tq, D)), _ops.Plan(ck.mask_bits(Tq, Tk)))
-    p, nbytes, aux, dot_plan, bits_plan = plan
+        plan = _plans[key] = (p, kern.out_elems * 4, _ops.Plan(ck.rowdot(nb * Tq, D)), _ops.Plan(ck.mask_bits(Tq, Tk)))
+    p, nbytes, dot_plan, bits_plan = plan
+    aux = shim.alloc((nb * Tq + mask_words(Tq, Tk)) * 4)     # [rowsum(dO * O) | mask bits, live tiles, live rows]; it travels with dS
     dot_plan.run_into(aux, _ops._dev_ptr(dO), _ops._dev_ptr(O))
     bits_plan.run_into(aux + nb * Tq, _ops._dev_ptr(mask))
     pd, pv, pp = _ops._dev_ptr(dO), _ops._dev_ptr(v), _ops._dev_ptr(P)
@@ -119,7 +147,9 @@ def dscores(dO: Buffer, v: Buffer, O: Buffer, P: Buffer, mask: Buffer, scale: fl
         timer.stop(t0, 2.0 * nb * Tq * Tk * D, ("attn_dscores", Tq, Tk, D, nb))
     if out == shim.NULL:
         raise RuntimeError("fused attention-backward launch failed: " + shim.last_error())
-    return shim.own(out, nbytes)
+    res = shim.own(out, nbytes)
+    _fresh[shim.address(res)] = (aux, aux + nb * Tq + Tq * Tk // 32, Tq, Tk)
+    return res
 
 
 def bwd_chain_matches(chain: list, out_shape: tuple) -> tuple | None:

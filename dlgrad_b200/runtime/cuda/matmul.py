@@ -59,6 +59,19 @@ def run_matmul(x: Buffer, y: Buffer, trans_x: bool = False, trans_y: bool = Fals
     x, trans_x = _fold_transpose(x, trans_x)
     y, trans_y = _fold_transpose(y, trans_y)
     aligned = x.aligned and y.aligned
+    if x._pending is not None:
+        _ops.materialize(x)            # a deferred dS gets its live-tile table while it is materialised
+    sp = _sparse_plan(x, y, trans_x, trans_y, aligned) if bias is None else None
+    if sp is not None:
+        plan, flags = sp
+        args = (_ops._dev_ptr(x), _ops._dev_ptr(y), _ops.NULL, flags)
+        timer = _profile.matmul_timer
+        if timer is None:
+            return plan(*args)
+        t0 = timer.start()
+        out = plan(*args)
+        timer.stop(t0, plan.flops, plan.tag)
+        return out
     fused = None
     if bias is not None and bias.aligned and bias.scalar is None:
         bkey = (x.metadata.shape, y.metadata.shape, trans_x, trans_y, aligned, "bias")
@@ -81,6 +94,29 @@ def run_matmul(x: Buffer, y: Buffer, trans_x: bool = False, trans_y: bool = Fals
         out = plan(*args)
         timer.stop(t0, plan.flops, plan.tag)
     return out if bias is None else (out, fused is not None)
+
+
+def _sparse_plan(x: Buffer, y: Buffer, tx: bool, ty: bool, aligned: bool):
+    """(plan, live-tile table) when `x` is a P / dS matrix from the fused attention kernels: the GEMM skips the k-blocks
+    of tiles the mask kills entirely."""
+    from dlgrad_b200.runtime.cuda import attention
+    info = attention.tag_of(x)
+    if info is None:
+        return None
+    _, flags, Tq, Tk = info
+    xs = x.metadata.shape
+    if xs[-2:] != (Tq, Tk):
+        return None
+    key = (xs, y.metadata.shape, tx, ty, aligned, "ksparse")
+    plan = _plans.get(key)
+    if plan is None and key not in _plans:
+        M, N, K, batch, a_bs, b_bs, _ = _geometry(xs, y.metadata.shape, tx, ty)
+        from dlgrad_b200.runtime.cuda import matmul_tc
+        plan = None
+        if not FORCE_SIMT and M % 128 == 0 and K % 128 == 0 and K <= 2048:
+            plan = matmul_tc.try_build(M, N, K, batch, a_bs, b_bs, tx, ty, aligned, ksparse="tn" if tx else "nn")
+        _plans[key] = plan
+    return None if plan is None else (plan, flags)
 
 
 def _build_bias(xs, ys, tx, ty, aligned):

@@ -158,6 +158,7 @@ def materialize(buf: Buffer) -> None:
             vt = gp[2]
             if m is not None and vt._pending is not None and vt._pending[0] == "tr" and gp[3] is not None:
                 buf.ptr = attention.dscores(gp[1], vt._pending[1], gp[3], y, m[0], m[1])
+                attention.claim(buf)                # dS carries the live-tile table for the two GEMMs that read it
                 return
         rows = _rows_of(shape, dim)
         args = _row_chain_args(chain, shape, y.aligned and g.aligned) if rows is not None else None

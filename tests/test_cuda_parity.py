@@ -709,7 +709,25 @@ def test_fused_attention_block_forward_and_backward(oracle, B, H, T, D, mask_kin
         for a, b, what in zip(fused, ref, names):
             runner.rel_check(check, a, b, 1e-4, f"{what}: fused vs oracle")
     if not compile_only:
+        from dlgrad_b200.runtime.cuda import matmul as mm
         assert any(k[0] == "bwd" for k in attention._plans if isinstance(k, tuple)), "expected the fused backward kernel to have run"
+        assert any(k[-1] == "ksparse" and v is not None for k, v in mm._plans.items()), "expected the tile-skipping GEMMs"
+    # a fully masked query row makes its probabilities NaN: the tile-skipping GEMM must then skip nothing, so that the
+    # NaN reaches y exactly where the dense product puts it
+    if T <= 512:
+        dead = mask.copy()
+        dead[5, :] = 1.0
+        outs = []
+        for on in (True, False):
+            attention.ENABLED = on
+            Q, K, V = (Tensor(a.copy(), device="cuda") for a in (q, k, v))
+            att = ((Q @ K.transpose(2, 3)) * scale).masked_fill(Tensor(dead.copy(), device="cuda"), float("-inf")).softmax(dim=3)
+            outs.append((att @ V).numpy())
+        attention.ENABLED = True
+        if not compile_only:
+            assert np.isnan(outs[0]).any() and (np.isnan(outs[0]) == np.isnan(outs[1])).all()
+            ok = ~np.isnan(outs[1])
+            runner.rel_check(check, outs[0][ok], outs[1][ok], runner.TOL_MATMUL, "y with a dead row: fused vs unfused")
 
 
 def test_split_k_weight_gradient_gemm(oracle):
