@@ -1,14 +1,21 @@
-"""Attention-shaped batched GEMMs for an ncu --set full capture."""
-import os, sys
-import numpy as np
+"""A few launches of the fused attention kernels and the tile-skipping GEMMs at C5 size, for `ncu --set full`
+(run once plain, then under ncu: scripts/gpu_ncu7.sh)."""
+import os
+import sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from dlgrad_b200 import Tensor
-from dlgrad_b200.runtime.cuda import shim
+import numpy as np  # noqa: E402
+from dlgrad_b200 import Tensor  # noqa: E402
+from dlgrad_b200.runtime.cuda import shim  # noqa: E402
+
 rng = np.random.default_rng(0)
-T = lambda *s: Tensor(rng.random(s, dtype=np.float32), device="cuda")   # noqa: E731
-q, kT, v, att = T(8, 12, 1024, 64), T(8, 12, 64, 1024), T(8, 12, 1024, 64), T(8, 12, 1024, 1024)
+B, H, T, D = 8, 12, 1024, 64
+q, k, v = (Tensor((rng.random((B, H, T, D), dtype=np.float32) - 0.5), device="cuda", requires_grad=True) for _ in range(3))
+mask = Tensor(np.triu(np.ones((T, T), dtype=np.float32), 1), device="cuda")
+w = Tensor(rng.random((B, H, T, D), dtype=np.float32), device="cuda")
 for _ in range(2):
-    s = q @ kT          # QK^T-like: (1024 x 1024 x 64) x 96, output-bound
-    y = att @ v         # AV-like:   (1024 x 64 x 1024) x 96, input-bound
+    att = ((q @ k.transpose(2, 3)) * 0.125).masked_fill(mask, float("-inf")).softmax(dim=3)
+    y = att @ v
+    (y * w).sum().backward()
+    q.grad = k.grad = v.grad = None
 shim.synchronize()
 print("ok")
