@@ -135,3 +135,54 @@ def test_every_kernel_gets_the_dependent_launch_prologue():
         first = body[body.index("{") + 1:]
         assert first.lstrip().startswith("//") and "griddepcontrol.launch_dependents" in first[:400]
         assert first.index("griddepcontrol.wait") < first.index("blockIdx") if "blockIdx" in first else True
+
+
+def _cuda_buf(shape):
+    from dlgrad_b200.buffer import Buffer
+    return Buffer(None, shape, Device.CUDA)
+
+
+def test_fused_attention_eligibility_and_chain_matching():
+    """runtime/cuda/attention.py decides on the host which q @ k^T products are deferred and which pending chains the
+    fused kernels may absorb; everything else must fall back to the eager kernels."""
+    from dlgrad_b200.buffer import Buffer
+    from dlgrad_b200.runtime.cuda import attention
+    q, k = _cuda_buf((8, 12, 1024, 64)), _cuda_buf((8, 12, 1024, 64))
+    kt = Buffer._deferred(("tr", k), (8, 12, 64, 1024))
+    assert attention.eligible(q, kt)
+    assert not attention.eligible(q, _cuda_buf((8, 12, 64, 1024)))                    # k^T materialised: plain GEMM
+    assert not attention.eligible(_cuda_buf((8, 12, 1000, 64)), Buffer._deferred(("tr", _cuda_buf((8, 12, 1000, 64))), (8, 12, 64, 1000)))
+    assert not attention.eligible(_cuda_buf((8, 12, 1024, 128)), Buffer._deferred(("tr", _cuda_buf((8, 12, 1024, 128))), (8, 12, 128, 1024)))
+    assert not attention.eligible(_cuda_buf((2, 2, 128, 64)), Buffer._deferred(("tr", _cuda_buf((2, 2, 128, 64))), (2, 2, 64, 128)))  # too small
+    assert not attention.eligible(_cuda_buf((4, 12, 1024, 64)), kt)                   # batch dims differ
+    mask = _cuda_buf((1024, 1024))
+    s = _cuda_buf((8, 12, 1024, 1024))
+    fwd = [("scale", s, 0.125), ("mfill", s, mask, float("-inf"))]
+    assert attention.chain_matches(fwd, (8, 12, 1024, 1024)) == (0.125, mask, float("-inf"))
+    assert attention.chain_matches(fwd[::-1], (8, 12, 1024, 1024)) is None            # masked_fill before the scale
+    assert attention.chain_matches([("scale", s, -1.0), fwd[1]], (8, 12, 1024, 1024)) is None      # row max taken on raw scores
+    assert attention.chain_matches([fwd[0], ("mfill", s, _cuda_buf((12, 1024, 1024)), 0.0)], (8, 12, 1024, 1024)) is None  # per-head mask
+    assert attention.chain_matches([fwd[0], ("mfill", s, _cuda_buf((1, 1, 1024, 1024)), -1e9)], (8, 12, 1024, 1024)) is not None
+    bwd = [("mfill", s, mask, 0.0), ("scale", s, 0.125)]
+    assert attention.bwd_chain_matches(bwd, (8, 12, 1024, 1024)) == (mask, 0.125)
+    assert attention.bwd_chain_matches([("mfill", s, mask, 1.0), bwd[1]], (8, 12, 1024, 1024)) is None
+    assert attention.mask_words(1024, 1024) == 1024 * 32 + 64 + 1024 + 1
+    # a Buffer's live-tile table is found by identity (Buffer.__eq__ is the elementwise op) and dies with the Buffer
+    p = _cuda_buf((8, 12, 1024, 1024))
+    attention._tags[id(p)] = ("owner", "flags", 1024, 1024)
+    assert attention.tag_of(p) == ("owner", "flags", 1024, 1024) and attention.tag_of(_cuda_buf((8, 12, 1024, 1024))) is None
+    attention._tags.pop(id(p))
+
+
+def test_fused_attention_kernels_generate_for_every_supported_head_dim():
+    for D in (32, 64):
+        kf = tc.attn_scores_tc(512, 1024, D, 6, 0.25, float("-inf"))
+        kb = tc.attn_dscores_tc(512, 1024, D, 6, 0.25)
+        for k in (kf, kb):
+            assert k.threads == 448 and k.smem <= 227 * 1024 and k.grid[0] <= 148 and k.out_elems == 6 * 512 * 1024
+        assert "live_tiles" in kf.source and "cp.async.cg.shared.global" in kb.source
+    assert "return 255u;" in tc.attn_scores_tc(1024, 1024, 64, 4, 0.125, -1e9).source     # finite fill: no tile is skipped
+    with pytest.raises(AssertionError):
+        tc.attn_scores_tc(1024, 1024, 128, 4, 0.125, float("-inf"))                         # TMEM cannot hold two Q buffers
+    ks = tc.matmul_tc_ts(1024, 64, 1024, 96, True, True, False, False, bn=64, ksparse="tn")
+    assert ks.name.endswith("_sptn") and "last_kb" in ks.source
