@@ -118,7 +118,8 @@ class Buffer:
     # A CUDA Buffer may be created WITHOUT running its kernel: `_pending` records a cheap pointwise
     # producer — ("scale", src, s) for `src * python_scalar`, ("mfill", src, mask, val) for masked_fill,
     # ("softmax_bwd", y, g, dim, kind) for the row backward, ("tr", src) for a transpose of the two
-    # innermost dims, ("mm", x, y) for an attention-shaped q @ k^T.  Reading `.ptr` materialises it (one fused
+    # innermost dims, ("mm", x, y) for an attention-shaped q @ k^T, ("relu", src) for Tensor.relu (folded into the
+    # splitter of the GEMM that consumes it).  Reading `.ptr` materialises it (one fused
     # kernel for the whole pending chain); consumers that can fold the chain into their own kernel
     # (softmax forward, and the chain materialiser itself) never trigger the intermediate writes.  The
     # values are identical either way; only the number of passes over HBM changes.
@@ -237,6 +238,9 @@ class Buffer:
         if prod_(new_shape) != self.metadata.numel:
             raise ValueError(f"Cannot reshape {self.shape} ({self.metadata.numel} elements) to "
                              f"{new_shape} ({prod_(new_shape)} elements)")
+        if self._pending is not None and self._pending[0] == "relu":
+            # a pointwise producer commutes with reshape: stay deferred (Linear flattens its input before the GEMM)
+            return Buffer._deferred(("relu", self._pending[1].reshape(new_shape)), new_shape, self.metadata.dtype)
         return Buffer(self.ptr, new_shape, self.metadata.device, self.metadata.dtype,
                       scalar=self.scalar, aligned=self.aligned, keep=self._keep)
 

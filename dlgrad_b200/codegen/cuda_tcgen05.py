@@ -716,7 +716,8 @@ def pick_bn_ts(M: int, N: int, batch: int, kblocks: int) -> int:
 @cache
 def matmul_tc_ts(M: int, N: int, K: int, batch: int, a_mn: bool, b_mn: bool, a_bcast: bool, b_bcast: bool,
                  bn: int | None = None, stages: int | None = None, kc_blocks: int | None = None,
-                 bias: bool = False, issuers: int | None = None, streamk: bool = False, ksparse: str | None = None) -> TcKernel:
+                 bias: bool = False, issuers: int | None = None, streamk: bool = False, ksparse: str | None = None,
+                 a_relu: bool = False, b_relu: bool = False) -> TcKernel:
     """Kernel parameters after C: `bias` (a length-N row the epilogue adds to every output row when `bias` is
     set — the Linear bias; it rides on the plain store) and `flags` (uint32[ntiles * 4], zero, used when
     `streamk` is set).
@@ -727,6 +728,11 @@ def matmul_tc_ts(M: int, N: int, K: int, batch: int, a_mn: bool, b_mn: bool, a_b
     and raises flags[tile][quarter]; the one holding its k-head meets it LAST, waits for the flag (long
     since raised) and TMA-reduce-adds its partial.  Two addends in fixed roles -> the sum is deterministic.
     Requires ntiles >= grid (every range at least one tile long, so no tile has three owners).
+
+    a_relu / b_relu: the operand is relu(stored matrix) — a deferred `Tensor.relu()` (Buffer pending kind "relu") —
+    applied where the operand passes through registers anyway: in the A splitter before the hi/lo split, in the B
+    splitter (which then also writes the clamped value back as the `hi` tile).  The relu kernel and its 2 x 100 MB
+    of traffic per MLP block disappear.
 
     ksparse ("nn" | "tn"): the A operand is an attention matrix (P or dS, query rows x key columns; "tn" = it is read
     transposed) whose 128 x 128 tiles that the mask kills entirely are exactly zero.  `flags` then points at the
@@ -1031,6 +1037,7 @@ extern "C" __global__ void __launch_bounds__({nthreads}, 1)
                 unsigned hi[32], lo[32];
                 #pragma unroll
                 for (unsigned k = 0; k < 32u; ++k) {{
+                    {"x[k] = fmaxf(x[k], 0.f);" if a_relu else ""}
                     hi[k] = __float_as_uint(x[k]) & 0xffffe000u;
                     lo[k] = __float_as_uint(x[k] - __uint_as_float(hi[k]));
                 }}
@@ -1053,11 +1060,11 @@ extern "C" __global__ void __launch_bounds__({nthreads}, 1)
                 {dead}
                 const unsigned s = it % {stages}u, ph = (it / {stages}u) & 1u;
                 mbar_wait(full + s * 8u, ph);
-                const float4* bsrc = reinterpret_cast<const float4*>(smem_gen + s * {per_stage}u + {a_tile}u);
+                {"float4*" if b_relu else "const float4*"} bsrc = reinterpret_cast<{"float4*" if b_relu else "const float4*"}>(smem_gen + s * {per_stage}u + {a_tile}u);
                 float4* bdst = reinterpret_cast<float4*>(smem_gen + s * {per_stage}u + {a_tile + b_tile}u);
                 #pragma unroll 8
                 for (unsigned i = ctid; i < {0 if exp in ("nobsplit", "nosplit") else b_tile // 16}u; i += 128u) {{
-                    const float4 v4 = bsrc[i];
+                    {"float4 v4 = bsrc[i]; v4.x = fmaxf(v4.x, 0.f); v4.y = fmaxf(v4.y, 0.f); v4.z = fmaxf(v4.z, 0.f); v4.w = fmaxf(v4.w, 0.f); bsrc[i] = v4;" if b_relu else "const float4 v4 = bsrc[i];"}
                     float4 l4;
                     l4.x = v4.x - __uint_as_float(__float_as_uint(v4.x) & 0xffffe000u);
                     l4.y = v4.y - __uint_as_float(__float_as_uint(v4.y) & 0xffffe000u);
@@ -1126,7 +1133,7 @@ extern "C" __global__ void __launch_bounds__({nthreads}, 1)
     }}
 }}
 """
-    return TcKernel("mm_tcts" + ("_b" if bias else "") + ("_sk" if streamk else "") + (f"_sp{ksparse}" if ksparse else ""), src, (grid, 1, 1), nthreads, smem, batch * M * N, BN, stages)
+    return TcKernel("mm_tcts" + ("_b" if bias else "") + ("_sk" if streamk else "") + (f"_sp{ksparse}" if ksparse else "") + ("_ra" if a_relu else "") + ("_rb" if b_relu else ""), src, (grid, 1, 1), nthreads, smem, batch * M * N, BN, stages)
 
 
 # =====================================================================================================

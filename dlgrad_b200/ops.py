@@ -209,14 +209,23 @@ class RSqrt(OP):
 
 
 class Relu(OP):
+    """On CUDA a large relu is DEFERRED (Buffer pending kind "relu"): the GEMM that consumes it applies max(., 0) in
+    its operand splitter and relu(x) is never written; any other consumer materialises it with the reference's
+    `where(x > 0, x, 0)` kernel (dlgrad/ops.py:151-158).  The backward selects on the pre-activation
+    (x > 0 <=> relu(x) > 0), so it does not need the output either."""
     def forward(self, x: Buffer) -> Buffer:
-        self.out = x.relu()
+        from dlgrad_b200.buffer import LAZY_MIN_NUMEL
+        self.x = x
+        if Buffer._route(x) is Device.CUDA and x.scalar is None and x.numel >= LAZY_MIN_NUMEL:
+            self.out = Buffer._deferred(("relu", x), x.shape, x.dtype)
+        else:
+            self.out = x.relu()
         return self.out
 
     def backward(self, upstream_grad: Buffer) -> tuple[Buffer]:
-        if Buffer._route(self.out, upstream_grad) is Device.CUDA and self.out.shape == upstream_grad.shape:
+        if Buffer._route(self.x, upstream_grad) is Device.CUDA and self.x.shape == upstream_grad.shape:
             # one select instead of the reference's where(1, 0) followed by a multiply (same values)
-            return (self.out.where(upstream_grad, 0.0),)
+            return (self.x.where(upstream_grad, 0.0),)
         return (self.out.where(inp=1.0, other=0.0) * upstream_grad,)
 
 

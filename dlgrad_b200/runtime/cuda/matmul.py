@@ -58,6 +58,10 @@ def run_matmul(x: Buffer, y: Buffer, trans_x: bool = False, trans_y: bool = Fals
     # a deferred transpose of an operand (Buffer.transpose) is folded into the kernel's operand-major flag
     x, trans_x = _fold_transpose(x, trans_x)
     y, trans_y = _fold_transpose(y, trans_y)
+    if bias is None and ((x._pending is not None and x._pending[0] == "relu") or (y._pending is not None and y._pending[0] == "relu")):
+        out = _relu_operand_matmul(x, y, trans_x, trans_y)
+        if out is not None:
+            return out
     aligned = x.aligned and y.aligned
     if x._pending is not None:
         _ops.materialize(x)            # a deferred dS gets its live-tile table while it is materialised
@@ -94,6 +98,38 @@ def run_matmul(x: Buffer, y: Buffer, trans_x: bool = False, trans_y: bool = Fals
         out = plan(*args)
         timer.stop(t0, plan.flops, plan.tag)
     return out if bias is None else (out, fused is not None)
+
+
+def _relu_operand_matmul(x: Buffer, y: Buffer, tx: bool, ty: bool):
+    """An operand is a deferred relu (Buffer pending kind "relu"): the tensor-core kernel applies max(., 0) while the
+    operand passes through its splitter, so relu(h) is never written.  None when the shape does not run there as one
+    launch (the caller then materialises the relu and takes the ordinary route)."""
+    a_relu = x._pending is not None and x._pending[0] == "relu"
+    b_relu = y._pending is not None and y._pending[0] == "relu"
+    xs = x._pending[1] if a_relu else x
+    ys = y._pending[1] if b_relu else y
+    if xs._pending is not None or ys._pending is not None or xs.metadata.shape != x.metadata.shape or ys.metadata.shape != y.metadata.shape:
+        return None
+    aligned = xs.aligned and ys.aligned
+    key = (xs.metadata.shape, ys.metadata.shape, tx, ty, aligned, "relu", a_relu, b_relu)
+    plan = _plans.get(key)
+    if plan is None and key not in _plans:
+        M, N, K, batch, a_bs, b_bs, _ = _geometry(xs.metadata.shape, ys.metadata.shape, tx, ty)
+        plan = None
+        if not FORCE_SIMT and _split_k(M, N, K, batch, tx, ty) == 1:
+            from dlgrad_b200.runtime.cuda import matmul_tc
+            plan = matmul_tc.try_build(M, N, K, batch, a_bs, b_bs, tx, ty, aligned, a_relu=a_relu, b_relu=b_relu)
+        _plans[key] = plan
+    if plan is None:
+        return None
+    args = (_ops._dev_ptr(xs), _ops._dev_ptr(ys))
+    timer = _profile.matmul_timer
+    if timer is None:
+        return plan(*args)
+    t0 = timer.start()
+    out = plan(*args)
+    timer.stop(t0, plan.flops, plan.tag)
+    return out
 
 
 def _sparse_plan(x: Buffer, y: Buffer, tx: bool, ty: bool, aligned: bool):

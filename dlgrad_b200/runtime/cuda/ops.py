@@ -145,6 +145,9 @@ def materialize(buf: Buffer) -> None:
     if pend[0] == "mm":
         buf.ptr = matmul(pend[1], pend[2])
         return
+    if pend[0] == "relu":
+        buf.ptr = pend[1].relu().ptr
+        return
     chain, base = _peel_chain(buf)
     shape = buf.metadata.shape
     bp = base._pending

@@ -730,6 +730,50 @@ def test_fused_attention_block_forward_and_backward(oracle, B, H, T, D, mask_kin
             runner.rel_check(check, outs[0][ok], outs[1][ok], runner.TOL_MATMUL, "y with a dead row: fused vs unfused")
 
 
+def test_deferred_relu_folds_into_the_consuming_gemm(oracle):
+    """Tensor.relu of a large CUDA tensor is deferred (ops.Relu, Buffer pending kind "relu"): the Linear that consumes
+    it applies max(., 0) in the GEMM's operand splitter — as the A operand in the forward, as the B operand of the
+    weight-gradient GEMM in the backward — and the relu output is never written.  MLP block x -> fc -> relu -> proj
+    forward and all gradients vs the oracle; the relu read on its own, reshaped, and fed to a non-GEMM op still has
+    the eager values."""
+    from dlgrad_b200 import Tensor
+    from dlgrad_b200.runtime.cuda import matmul as mm
+    compile_only = __import__("tests.conftest", fromlist=["x"]).COMPILE_ONLY
+    rng = np.random.default_rng(31)
+    x = (rng.random((4, 256, 192), dtype=np.float32) - 0.5).astype(np.float32)
+    w1 = (rng.random((768, 192), dtype=np.float32) - 0.5).astype(np.float32)
+    w2 = (rng.random((192, 768), dtype=np.float32) - 0.5).astype(np.float32)
+    res = {}
+    for dev in ("cuda", "cpu"):
+        X = Tensor(x.copy(), device=dev, requires_grad=True)
+        W1 = Tensor(w1.copy(), device=dev, requires_grad=True)
+        W2 = Tensor(w2.copy(), device=dev, requires_grad=True)
+        h = X.linear(W1, None)
+        r = h.relu()
+        if dev == "cuda" and not compile_only:
+            assert r.data._pending is not None and r.data._pending[0] == "relu"
+        y = r.linear(W2, None)
+        coef = Tensor(np.linspace(0.5, 1.5, y.numel, dtype=np.float32).reshape(y.shape), device=dev)
+        (y * coef).sum().backward()
+        res[dev] = (y.numpy(), X.grad.numpy(), W1.grad.numpy(), W2.grad.numpy())
+        if dev == "cuda" and not compile_only:
+            assert r.data._pending is not None, "the GEMMs must not have materialised the relu"
+            assert any(k[5] == "relu" and v is not None for k, v in mm._plans.items() if len(k) == 8), "expected relu-operand GEMM plans"
+    for got, exp, what in zip(res["cuda"], res["cpu"], ("y", "dx", "dw1", "dw2")):
+        runner.rel_check(check, got, exp, runner.TOL_MATMUL, f"fc -> relu -> proj: {what}")
+    # other consumers see the eager values
+    H = Tensor((x * 4).copy(), device="cuda")
+    ref = np.maximum(x * 4, 0)
+    check(H.relu().numpy(), ref, exact=True, what="deferred relu -> numpy")
+    check(H.relu().reshape((1024, 192)).numpy(), ref.reshape(1024, 192), exact=True, what="deferred relu -> reshape -> numpy")
+    check((H.relu() + 1.0).numpy(), ref + np.float32(1), exact=True, what="deferred relu -> add")
+    nanrow = (x * 4).copy()
+    nanrow[0, 0, :8] = np.nan
+    got = Tensor(nanrow, device="cuda").relu().linear(Tensor(w1.T.copy()[:, :192].copy(), device="cuda") if False else Tensor(w2[:, :192].copy(), device="cuda"), None).numpy()
+    exp = np.where(nanrow > 0, nanrow, 0).astype(np.float64) @ w2[:, :192].astype(np.float64).T
+    runner.rel_check(check, got, exp, runner.TOL_MATMUL, "relu(NaN) = 0 inside the GEMM, like where(x > 0, x, 0)")
+
+
 def test_split_k_weight_gradient_gemm(oracle):
     """x^T @ g with a small output and K = batch*tokens (the Linear weight gradient) runs as split-K: K-slices
     as a batch + an ordered sum (runtime/cuda/matmul.py).  Checked against float64 and, at a smaller K, the oracle."""
