@@ -347,6 +347,44 @@ def test_config4_char_gpt_two_train_steps_vs_oracle(oracle):
         check(res["cuda"][i], res["cpu"][i], rtol=1e-5, atol=2 * lr * steps, what=f"char-GPT {what}")
 
 
+def test_gpt_with_every_attention_fusion_vs_oracle(oracle):
+    """A GPT whose attention is large enough (T = 512, head dim 32) for every fusion of runtime/cuda/attention.py to
+    engage inside the model code — fused scores, fused backward, dead-tile skipping, tile-skipping GEMMs, deferred
+    relu and transposes — two Adam steps against the CPU oracle, which runs the reference's unfused graph."""
+    import dlgrad_b200 as dl
+    from dlgrad_b200 import Tensor, nn
+    from dlgrad_b200.runtime.cuda import attention
+    from tests import models
+    compile_only = __import__("tests.conftest", fromlist=["x"]).COMPILE_ONLY
+    old_min, attention.MIN_SCORES = attention.MIN_SCORES, 1 << 20
+    try:
+        res = {}
+        for dev in ("cuda", "cpu"):
+            cfg = models.GPTConfig(vocab_size=96, block_size=512, n_layer=2, n_head=4, n_embd=128, device=dev)
+            gpt = models.GPT(dl, cfg, np.random.default_rng(14))
+            xb, yb = models.gpt_batch(cfg, 2, np.random.default_rng(15))
+            opt = nn.optim.Adam(nn.utils.get_parameters(gpt), lr=1e-4)
+            losses = []
+            for step in range(2):
+                opt.zero_grad()
+                _, loss = gpt(Tensor(xb.copy(), device=dev), Tensor(yb.copy(), device=dev))
+                losses.append(float(loss.numpy()))
+                loss.backward()
+                if step == 0:
+                    grads = [gpt.blocks[0].attn.q_proj.weight.grad.numpy(), gpt.blocks[1].attn.v_proj.weight.grad.numpy(),
+                             gpt.blocks[0].c_fc.weight.grad.numpy()]
+                opt.step()
+            res[dev] = (np.array(losses), *grads)
+        if not compile_only:
+            kinds = {k[0] if isinstance(k[0], str) else "fwd" for k in attention._plans}
+            assert "bwd" in kinds and "fwd" in kinds, "expected the fused attention kernels inside the model"
+        tols = (1e-5, 1e-3, 1e-3, 1e-3)
+        for i, what in enumerate(("losses", "grad q_proj[0]", "grad v_proj[1]", "grad c_fc[0]")):
+            runner.rel_check(check, res["cuda"][i], res["cpu"][i], tols[i], f"fused-attention GPT {what}")
+    finally:
+        attention.MIN_SCORES = old_min
+
+
 def test_inference_kv_cache_path_vs_oracle(oracle):
     """examples/gpt.py's incremental decoding (forward_incremental, :131-153): the KV cache round-trips
     through numpy each token (`np.concatenate((past_k.numpy(), k.numpy()))`, `Tensor(k_np, device=...)`), so it
