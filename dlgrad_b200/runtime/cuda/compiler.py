@@ -74,7 +74,10 @@ def _compile_single(key: str, fname: str, src: str) -> str:
             f.write(src.replace(KNAME, fname))
         tmp_out = os.path.join(tmpdir, "k.cubin")
         _run_nvcc(cu, tmp_out)
-        shutil.move(tmp_out, out)
+        # several ranks may compile the same missing kernel at once: publish with an atomic rename inside the cache
+        staged = f"{out}.{os.getpid()}.tmp"
+        shutil.copyfile(tmp_out, staged)
+        os.replace(staged, out)
     finally:
         if not os.environ.get("DLGRAD_KEEP_SRC"):
             shutil.rmtree(tmpdir, ignore_errors=True)
