@@ -296,7 +296,7 @@ extern "C" __global__ void __launch_bounds__({BLOCK}) {KNAME}{SIG} {{
 
 @cache
 def reduce_cols(op: str, outer: int, R: int, inner: int, aligned: bool = True,
-                splits: int = 1, scale_R: int | None = None, cluster: bool = False) -> Kernel:
+                splits: int = 1, scale_R: int | None = None, cluster: bool = False, prod3: bool = False) -> Kernel:
     """Strided reduce: out[o][i] = red_r x[(o*R + r)*inner + i].  Threads run along `inner` (coalesced
     128-bit loads), the 8 warps of a CTA take interleaved rows and meet in shared memory.  When
     outer*inner alone cannot fill 148 SMs, R is cut into `splits` slices along blockIdx.z:
@@ -306,7 +306,10 @@ def reduce_cols(op: str, outer: int, R: int, inner: int, aligned: bool = True,
                     ld.shared::cluster) — one launch, no atomics, deterministic order;
       cluster=False the partials go to out[s][o][i] and a second reduce_cols pass over `splits` finishes.
     The reference walks this case with a strided inner loop (cpu_kernel.py:69-148), its slowest pattern
-    (152 ms for 4096^2 axis 0)."""
+    (152 ms for 4096^2 axis 0).
+    prod3: the reduced value is x[r][i] * (y[r][i] * t[r]) with y = p1 (same layout) and t = p2 (one value per
+    row) — the RMSNorm weight gradient sum_rows g * (x * rstd) without writing the product first.  Explicit
+    round-to-nearest multiplies, no FMA contraction with the running sum: bit-identical to multiply-then-sum."""
     init, comb, fin = _RED[op]
     final_here = splits == 1 or cluster
     fin = fin.format(R=scale_R if scale_R is not None else R) if final_here else "acc"
@@ -323,6 +326,11 @@ def reduce_cols(op: str, outer: int, R: int, inner: int, aligned: bool = True,
     ldv = (f"__ldg(reinterpret_cast<const float4*>(base + (size_t)r * {inner}u) + cv)" if V == 4
            else f"__ldg(base + (size_t)r * {inner}u + cv)")
     fin_store = each("res{c} = " + fin.replace("acc", "acc{c}") + ";")
+    if prod3:
+        assert outer == 1 and not cluster
+        ld2 = (f"__ldg(reinterpret_cast<const float4*>(p1 + (size_t)r * {inner}u) + cv)" if V == 4
+               else f"__ldg(p1 + (size_t)r * {inner}u + cv)")
+        ldv = f"mul3({ldv}, {ld2}, __ldg(p2 + r))"
     if cluster and splits > 1:
         ld_remote = ('asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(o.x), "=f"(o.y), "=f"(o.z), "=f"(o.w) : "r"(ra));'
                      if V == 4 else 'asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(o) : "r"(ra));')
@@ -358,6 +366,10 @@ def reduce_cols(op: str, outer: int, R: int, inner: int, aligned: bool = True,
         out_elems = splits * outer * inner
     src = f"""
 __device__ __forceinline__ float red(float a, float b) {{ return {comb}; }}
+__device__ __forceinline__ float mul3(float a, float b, float t) {{ return __fmul_rn(a, __fmul_rn(b, t)); }}
+__device__ __forceinline__ float4 mul3(float4 a, float4 b, float t) {{
+    return make_float4(mul3(a.x, b.x, t), mul3(a.y, b.y, t), mul3(a.z, b.z, t), mul3(a.w, b.w, t));
+}}
 extern "C" __global__ void {attr}__launch_bounds__({32 * Y}) {KNAME}{SIG} {{
     __shared__ {T} part[{Y}][33];
     const unsigned cv = blockIdx.x * 32u + threadIdx.x;
@@ -371,7 +383,7 @@ extern "C" __global__ void {attr}__launch_bounds__({32 * Y}) {KNAME}{SIG} {{
         #pragma unroll 4
         for (; r + {Y}u < r1; r += {2 * Y}u) {{
             const {T} v = {ldv};
-            const {T} w = {ldv.replace("(size_t)r", "(size_t)(r + %du)" % Y)};
+            const {T} w = {ldv.replace("(size_t)r", "(size_t)(r + %du)" % Y).replace("p2 + r)", "p2 + r + %du)" % Y)};
             {each("acc{c} = red(acc{c}, v{c});")} {each("acc2{c} = red(acc2{c}, w{c});")}
         }}
         if (r < r1) {{ const {T} v = {ldv}; {each("acc{c} = red(acc{c}, v{c});")} }}
@@ -386,7 +398,7 @@ extern "C" __global__ void {attr}__launch_bounds__({32 * Y}) {KNAME}{SIG} {{
 }}
 """
     grid = (_cdiv(ncolv, 32), outer, splits)
-    return Kernel(f"red_{op}_cols", src, grid, (32, Y, 1), 0, out_elems)
+    return Kernel(f"red_{op}_cols" + ("_prod3" if prod3 else ""), src, grid, (32, Y, 1), 0, out_elems)
 
 
 @cache

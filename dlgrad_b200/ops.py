@@ -322,8 +322,7 @@ class RMSNorm(OP):
             else:
                 gx = Buffer(_rt.ewise3("rms_dx", "v0 * v1", x.shape, [g, t]), x.shape, Device.CUDA, x.dtype)
         if w is not None and len(self.req_grad) > 1 and self.req_grad[1]:
-            z = Buffer(_rt.ewise3("rms_dw", "v0 * (v1 * v2)", x.shape, [g, x, t]), x.shape, Device.CUDA, x.dtype)
-            gw = z.reshape((x.numel // x.shape[-1], x.shape[-1])).sum(0, keepdim=True).reshape(w.shape)
+            gw = Buffer(_rt.rms_dw(g, x, t), w.shape, Device.CUDA, x.dtype)       # sum_rows g * (x * rstd), product never written
         return (gx, gw)
 
 

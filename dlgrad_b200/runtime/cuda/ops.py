@@ -474,6 +474,31 @@ def _build_reduce(op: str, shape: tuple, dim: int, aligned: bool) -> list[Plan]:
             Plan(ck.reduce_cols(op, 1, splits, outer * inner, aligned and (outer * inner) % 4 == 0, 1, scale_R=R))]
 
 
+def rms_dw(g: Buffer, x: Buffer, rstd: Buffer) -> CDataPtr:
+    """sum over rows of g * (x * rstd) (the RMSNorm weight gradient, dlgrad/nn/__init__.py:28-41 through autograd)
+    in the column-reduce kernel itself: the (rows, C) product is never written.  Same strips / splits / order as
+    `(g * (x * rstd)).sum(0)`, hence the same bits."""
+    C = x.metadata.shape[-1]
+    R = x.metadata.numel // C
+    ok = g.aligned and x.aligned
+    key = ("rms_dw", R, C, ok)
+    plans = _plans.get(key)
+    if plans is None:
+        V = 4 if (ok and C % 4 == 0) else 1
+        blocks = -(-(C // V) // 32)
+        splits = 1
+        if blocks < 4 * ck.NUM_SMS and R >= 64:
+            splits = builtins_max(1, builtins_min(R // 16, -(-8 * ck.NUM_SMS // blocks), 64))
+        plans = [Plan(ck.reduce_cols("sum", 1, R, C, ok, splits, prod3=True))]
+        if splits > 1:
+            plans.append(Plan(ck.reduce_cols("sum", 1, splits, C, C % 4 == 0, 1, scale_R=R)))
+        _plans[key] = plans
+    ptr = plans[0].run(_dev_ptr(g), _dev_ptr(x), _dev_ptr(rstd))
+    for p in plans[1:]:
+        ptr = p.run(ptr)
+    return ptr
+
+
 @dispatcher.register(UnaryOps.SUM, CUDA)
 def sum_(x: Buffer, dim: int) -> CDataPtr:
     return _reduce("sum", x, dim)
