@@ -717,7 +717,7 @@ def pick_bn_ts(M: int, N: int, batch: int, kblocks: int) -> int:
 def matmul_tc_ts(M: int, N: int, K: int, batch: int, a_mn: bool, b_mn: bool, a_bcast: bool, b_bcast: bool,
                  bn: int | None = None, stages: int | None = None, kc_blocks: int | None = None,
                  bias: bool = False, issuers: int | None = None, streamk: bool = False, ksparse: str | None = None,
-                 a_relu: bool = False, b_relu: bool = False) -> TcKernel:
+                 a_relu: bool = False, b_relu: bool = False, splitk: int = 0) -> TcKernel:
     """Kernel parameters after C: `bias` (a length-N row the epilogue adds to every output row when `bias` is
     set — the Linear bias; it rides on the plain store) and `flags` (uint32[ntiles * 4], zero, used when
     `streamk` is set).
@@ -728,6 +728,11 @@ def matmul_tc_ts(M: int, N: int, K: int, batch: int, a_mn: bool, b_mn: bool, a_b
     and raises flags[tile][quarter]; the one holding its k-head meets it LAST, waits for the flag (long
     since raised) and TMA-reduce-adds its partial.  Two addends in fixed roles -> the sum is deterministic.
     Requires ntiles >= grid (every range at least one tile long, so no tile has three owners).
+
+    splitk = S > 1: the batch dimension holds S K-slices of ONE product (x^T @ g with K = batch * tokens: both operands
+    are stored [K][cols], so slices are a batch).  C is then the scratch [S][M][N] of partial sums, `bias` carries the
+    pointer of the real output and `flags` one counter per (output tile, row quarter): the slice that finishes a
+    quarter LAST adds the S partials in slice order and writes the result — deterministic, no second kernel.
 
     a_relu / b_relu: the operand is relu(stored matrix) — a deferred `Tensor.relu()` (Buffer pending kind "relu") —
     applied where the operand passes through registers anyway: in the A splitter before the hi/lo split, in the B
@@ -877,6 +882,42 @@ def matmul_tc_ts(M: int, N: int, K: int, batch: int, a_mn: bool, b_mn: bool, a_b
                 asm volatile("fence.proxy.async;" ::: "memory");
                 asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(flag), "r"(1u) : "memory");
             }"""
+    elif splitk > 1:
+        assert nchunks == 1 and not bias and batch == splitk and N % 4 == 0
+        partial_sum = " ".join(
+            f"{{ const float4 o = __ldcg(reinterpret_cast<const float4*>(C + ((size_t){sl} * {M}u + row) * {N}u + col)); "
+            "acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w; }" for sl in range(1, splitk))
+        sk_seg_begin = "const bool seg_head = false;"
+        sk_seg_end = f"""{{
+                // split-K: whichever slice finishes this quarter of the output tile LAST adds the {splitk} partial sums, in
+                // slice order, and writes the result; the counter re-arms itself for the next launch
+                unsigned last = 0u;
+                unsigned* cnt = flags + rem * 4u + q;
+                if (lane == 0) {{
+                    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");      // this slice's partial has landed
+                    asm volatile("fence.proxy.async;" ::: "memory");
+                    __threadfence();
+                    last = (atomicAdd(cnt, 1u) == {splitk - 1}u) ? 1u : 0u;
+                }}
+                last = __shfl_sync(0xffffffffu, last, 0);
+                if (last) {{
+                    __threadfence();
+                    float* fin = const_cast<float*>(bias);
+                    for (unsigned r = 0; r < 32u; ++r) {{
+                        const unsigned row = m0 + q * 32u + r;
+                        if (row >= {M}u) break;
+                        for (unsigned cv = lane; cv < {BN // 4}u; cv += 32u) {{
+                            const unsigned col = n0 + cv * 4u;
+                            if (col < {N}u) {{
+                                float4 acc = __ldcg(reinterpret_cast<const float4*>(C + (size_t)row * {N}u + col));
+                                {partial_sum}
+                                *reinterpret_cast<float4*>(fin + (size_t)row * {N}u + col) = acc;
+                            }}
+                        }}
+                    }}
+                    if (lane == 0) *cnt = 0u;
+                }}
+            }}"""
     else:
         sk_seg_begin, sk_seg_end = "const bool seg_head = false;", ""
     zero_tile = "" if not ksparse else f"""if (lk == 0u) {{
@@ -1133,7 +1174,7 @@ extern "C" __global__ void __launch_bounds__({nthreads}, 1)
     }}
 }}
 """
-    return TcKernel("mm_tcts" + ("_b" if bias else "") + ("_sk" if streamk else "") + (f"_sp{ksparse}" if ksparse else "") + ("_ra" if a_relu else "") + ("_rb" if b_relu else ""), src, (grid, 1, 1), nthreads, smem, batch * M * N, BN, stages)
+    return TcKernel("mm_tcts" + ("_b" if bias else "") + ("_sk" if streamk else "") + (f"_sp{ksparse}" if ksparse else "") + ("_ra" if a_relu else "") + ("_rb" if b_relu else "") + (f"_k{splitk}" if splitk > 1 else ""), src, (grid, 1, 1), nthreads, smem, batch * M * N, BN, stages)
 
 
 # =====================================================================================================

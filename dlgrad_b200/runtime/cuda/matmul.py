@@ -18,6 +18,7 @@ from dlgrad_b200.runtime.cuda import profile as _profile
 
 _plans: dict = {}
 FORCE_SIMT = os.environ.get("DLGRAD_MATMUL", "").lower() == "simt"
+FUSED_SPLITK = os.environ.get("DLGRAD_FUSED_SPLITK", "1") != "0"
 
 
 def _geometry(xs: tuple, ys: tuple, tx: bool, ty: bool):
@@ -200,6 +201,11 @@ def _split_k(M: int, N: int, K: int, batch: tuple, tx: bool, ty: bool) -> int:
 def _build_split_k(M: int, N: int, K: int, S: int, aligned: bool):
     from dlgrad_b200.runtime.cuda import matmul_tc
     ks = K // S
+    if FUSED_SPLITK and ks <= 2048 and N % 4 == 0:
+        # one launch: the slice that finishes an output tile last adds the S partial sums itself
+        one = matmul_tc.try_build(M, N, ks, (1, S), (0, ks * M), (0, ks * N), True, False, aligned, splitk=S)
+        if one is not None:
+            return MatmulPlan(one.fn, 2.0 * M * N * K, ("tc3_splitk", M, N, K, S))
     part = matmul_tc.try_build(M, N, ks, (1, S), (0, ks * M), (0, ks * N), True, False, aligned)
     if part is None:
         return None

@@ -827,3 +827,31 @@ def test_split_k_weight_gradient_gemm(oracle):
     runner.rel_check(check, W.grad.numpy(), ref, runner.TOL_MATMUL, "dW = g^T @ x, K = 8192 (split-K)")
     runner.rel_check(check, lin_in.grad.numpy(), g.astype(np.float64) @ W.numpy().astype(np.float64), runner.TOL_MATMUL,
                      "dX = g @ W")
+
+
+def test_split_k_in_kernel_finish_matches_two_kernel_sum():
+    """The fused split-K GEMM (the last slice to finish an output tile adds the partial sums in slice order) must give
+    the SAME BITS as the two-kernel form (batched slices + column reduce), launch after launch (its tile counters
+    re-arm themselves), also for a ragged output whose edge tiles are partly outside the matrix."""
+    from dlgrad_b200.runtime.cuda import matmul
+    from dlgrad_b200.runtime.cuda.transfer import download, upload_numpy as upload
+    rng = np.random.default_rng(77)
+    for M, N, K, S in ((768, 768, 8192, 4), (200, 332, 4096, 8), (128, 64, 2048, 2)):
+        a = (rng.random((K, M), dtype=np.float32) - 0.5).astype(np.float32)
+        b = (rng.random((K, N), dtype=np.float32) - 0.5).astype(np.float32)
+        da, db = upload(a), upload(b)
+        matmul.FUSED_SPLITK = True
+        fused = matmul._build_split_k(M, N, K, S, True)
+        matmul.FUSED_SPLITK = False
+        try:
+            plain = matmul._build_split_k(M, N, K, S, True)
+        finally:
+            matmul.FUSED_SPLITK = True
+        assert fused is not None and plain is not None
+        want = download(plain(da, db), M * N).reshape(M, N)
+        for rep in range(3):
+            got = download(fused(da, db), M * N).reshape(M, N)
+            check(got, want, exact=True,
+                  what=f"fused split-K {M}x{N}x{K}/{S}, launch {rep}: bit-identical to slices + ordered sum")
+        runner.rel_check(check, got, a.astype(np.float64).T @ b.astype(np.float64), runner.TOL_MATMUL,
+                         f"fused split-K {M}x{N}x{K}/{S} vs float64")
