@@ -193,13 +193,14 @@ def workload_config(cfg_kw: dict, batch: int, gpus: int) -> dict:
 # ---------------------------------------------------------------------------------------------------
 # this package
 # ---------------------------------------------------------------------------------------------------
-def build_gpt(cfg_kw: dict, device: str):
+def build_gpt(cfg_kw: dict, device: str, fused_dp: bool = False):
     import dlgrad_b200 as dl
-    from dlgrad_b200 import nn
+    from dlgrad_b200 import distributed, nn
     cfg = models.GPTConfig(device=device, **cfg_kw)
     gpt = models.GPT(dl, cfg, np.random.default_rng(0))       # identical weights on every rank
     params = nn.utils.get_parameters(gpt)
-    opt = nn.optim.Adam(params, lr=1e-4)
+    # data parallel: reduce-scatter + Adam + all-gather in one kernel over NVLink peer memory
+    opt = distributed.Adam(params, lr=1e-4) if fused_dp else nn.optim.Adam(params, lr=1e-4)
     return cfg, gpt, params, opt
 
 
@@ -208,8 +209,8 @@ def train_step(gpt, opt, params, x, y, world):
     opt.zero_grad()
     _, loss = gpt(x, y)
     loss.backward()
-    if world > 1:
-        distributed.all_reduce_gradients(params)
+    if world > 1 and not isinstance(opt, distributed.Adam):
+        distributed.all_reduce_gradients(params)     # DLGRAD_DP_FUSED=0: ncclAllReduce, then the local Adam kernel
     opt.step()
     return loss
 
@@ -309,7 +310,8 @@ def run_b200(args) -> None:
             dist.barrier()
 
     cfg_kw = C5 if args.config == "c5" else C4
-    cfg, gpt, params, opt = build_gpt(cfg_kw, "cuda")
+    fused_dp = world > 1 and os.environ.get("DLGRAD_DP_FUSED", "1") != "0"
+    cfg, gpt, params, opt = build_gpt(cfg_kw, "cuda", fused_dp)
     opt.grad_scale = 1.0 / world
     data_rng = np.random.default_rng(1000 + rank)            # rank-specific tokens
     batches = [models.gpt_batch(cfg, args.batch, data_rng) for _ in range(4)]
@@ -317,6 +319,7 @@ def run_b200(args) -> None:
 
     if args.prebuild:       # compile-only census of every kernel the bench launches
         train_step(gpt, opt, params, *dev_batches[0], world)
+        distributed.prebuild([p.numel for p in params])           # the fused data-parallel step at 2, 4 and 8 ranks
         op_microbench(load_peaks())
         return
 
@@ -404,7 +407,9 @@ def run_b200(args) -> None:
         "metric": "gpt_train_steps_per_s", "value": value, "unit": "steps/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_a / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(cfg_kw, args.batch, world),
+        "config": dict(workload_config(cfg_kw, args.batch, world), **({"gradient_exchange": (
+            "one kernel per rank: reduce-scatter (NVLink peer loads) + Adam on the 1/world shard + all-gather (peer stores)"
+            if fused_dp else "ncclAllReduce of the flat gradient bucket, then the local Adam kernel")} if world > 1 else {})),
         "tokens_per_s": value * args.batch * cfg.block_size,
         "model_tflops": value * flops_step / 1e12,
         "last_loss": last_loss,

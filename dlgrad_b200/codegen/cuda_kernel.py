@@ -1274,3 +1274,109 @@ extern "C" __global__ void __launch_bounds__(256) {KNAME}{SIG_ALIAS} {{
 }}
 """
     return Kernel("adam_multi", src, (acc, 1, 1), (256, 1, 1), 0, 0)
+
+
+def dp_adam(world: int, shard_vecs: int, beta1: float, beta2: float, eps: float, timeout_s: float = 20.0) -> Kernel:
+    """Data-parallel optimizer step as ONE kernel per rank over NVLink peer memory: reduce-scatter of the gradients
+    (P2P loads), Adam on this rank's 1/world shard, all-gather of the updated parameters (P2P stores).  It replaces
+    ncclAllReduce(grads) + adam_multi ("fused with its collective").
+
+      p0  table of 64-bit words: [world] gradient buckets, [world] parameter buckets, [world] flag arrays — every
+          rank's, as mapped into THIS process (own entries are the local allocations) — then this rank's index
+      p1, p2  Adam moments of the shard only (shard_vecs float4 each): optimizer state is sharded, not replicated
+      p3  this rank's flag array (uint32): [0, world) "rank r's gradients are ready", [world, 2*world) "rank r has
+          stored its shard of the new parameters everywhere", [2*world] last finished epoch, [2*world + 1] CTA counter
+      f0..f3  bias corrections 1 - beta^t, learning rate, gradient scale (1/world)
+
+    Element i of the shard is sum_{r = 0..world-1} grad_r[i] in RANK ORDER on every rank, and only the owner computes
+    the update, so all replicas receive bit-identical parameters (NCCL's ring order differs per rank count).  The
+    per-element arithmetic after the sum is adam_multi's.  Flags are epochs: they only grow, nothing is reset.  A rank
+    that waits longer than `timeout_s` for a peer traps — a dead peer must fail loudly, not hang the node."""
+    W = world
+    b1, b2, e_ = _flit(beta1), _flit(beta2), _flit(eps)
+    omb1, omb2 = _flit(1.0 - beta1), _flit(1.0 - beta2)
+    body = []
+    for c in "xyzw":
+        body.append(f"""
+            {{ const float gg = __fmul_rn(g.{c}, f3);
+              const float mn = __fadd_rn(__fmul_rn(m.{c}, {b1}), __fmul_rn(gg, {omb1}));
+              const float vn = __fadd_rn(__fmul_rn(v.{c}, {b2}), __fmul_rn(__fmul_rn(gg, gg), {omb2}));
+              const float mh = __fdiv_rn(mn, f0), vh = __fdiv_rn(vn, f1);
+              p.{c} = __fsub_rn(p.{c}, __fmul_rn(__fdiv_rn(mh, __fadd_rn(__fsqrt_rn(vh), {e_})), f2));
+              m.{c} = mn; v.{c} = vn; }}""")
+    THREADS = 512
+    grid = max(1, min(2 * NUM_SMS, _cdiv(shard_vecs, THREADS)))
+    src = f"""
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {{
+    unsigned v; asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
+}}
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {{
+    asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}}
+__device__ __forceinline__ unsigned long long wall_ns() {{
+    unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t;
+}}
+__device__ __forceinline__ void wait_epoch(const unsigned* flag, unsigned e) {{
+    const unsigned long long t0 = wall_ns();
+    while ((int)(ld_acquire_sys(flag) - e) < 0) {{
+        if (wall_ns() - t0 > {int(timeout_s * 1e9)}ULL) __trap();
+        __nanosleep(200);
+    }}
+}}
+extern "C" __global__ void __launch_bounds__({THREADS}) {KNAME}{SIG_ALIAS} {{
+    const unsigned long long* tab = reinterpret_cast<const unsigned long long*>(p0);
+    unsigned* sync = reinterpret_cast<unsigned*>(p3);
+    const unsigned rank = (unsigned)tab[{3 * W}];
+    const unsigned e = *reinterpret_cast<volatile unsigned*>(sync + {2 * W}) + 1u;     // this step's epoch
+    __shared__ unsigned long long s_tab[{2 * W}];
+    if (threadIdx.x < {2 * W}u) s_tab[threadIdx.x] = tab[threadIdx.x];
+
+    // ---- every rank's gradients are complete (its kernel has started, i.e. its backward has finished) ----
+    if (blockIdx.x == 0u && threadIdx.x < {W}u) {{
+        __threadfence_system();
+        st_release_sys(reinterpret_cast<unsigned*>(tab[{2 * W}u + threadIdx.x]) + rank, e);
+    }}
+    if (threadIdx.x < {W}u) wait_epoch(sync + threadIdx.x, e);
+    __syncthreads();
+
+    // ---- reduce-scatter (peer loads) -> Adam on the shard -> all-gather (peer stores) ----
+    float4* M = reinterpret_cast<float4*>(p1);
+    float4* V = reinterpret_cast<float4*>(p2);
+    const size_t base = (size_t)rank * {shard_vecs}u;
+    for (unsigned i = blockIdx.x * {THREADS}u + threadIdx.x; i < {shard_vecs}u; i += gridDim.x * {THREADS}u) {{
+        float4 gr[{W}];
+        #pragma unroll
+        for (unsigned r = 0; r < {W}u; ++r)
+            gr[r] = __ldcg(reinterpret_cast<const float4*>(s_tab[r]) + base + i);
+        float4 p = __ldcg(reinterpret_cast<const float4*>(s_tab[{W}u + rank]) + base + i);
+        float4 m = M[i], v = V[i];
+        float4 g = gr[0];
+        #pragma unroll
+        for (unsigned r = 1; r < {W}u; ++r) {{
+            g.x = __fadd_rn(g.x, gr[r].x); g.y = __fadd_rn(g.y, gr[r].y);
+            g.z = __fadd_rn(g.z, gr[r].z); g.w = __fadd_rn(g.w, gr[r].w);
+        }}
+        {''.join(body)}
+        M[i] = m; V[i] = v;
+        #pragma unroll
+        for (unsigned r = 0; r < {W}u; ++r)
+            reinterpret_cast<float4*>(s_tab[{W}u + r])[base + i] = p;
+    }}
+
+    // ---- this rank's shard is stored everywhere; leave only when every other shard has arrived here ----
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0u) {{
+        __threadfence_system();
+        if (atomicAdd(sync + {2 * W + 1}, 1u) == gridDim.x - 1u) {{          // last CTA of this rank
+            sync[{2 * W + 1}] = 0u;
+            for (unsigned r = 0; r < {W}u; ++r)
+                st_release_sys(reinterpret_cast<unsigned*>(tab[{2 * W}u + r]) + {W}u + rank, e);
+            for (unsigned r = 0; r < {W}u; ++r) wait_epoch(sync + {W}u + r, e);
+            *reinterpret_cast<volatile unsigned*>(sync + {2 * W}) = e;
+            __threadfence();
+        }}
+    }}
+}}
+"""
+    return Kernel("dp_adam", src, (grid, 1, 1), (THREADS, 1, 1), 0, 0)

@@ -41,7 +41,8 @@
     X(cuModuleLoad) X(cuModuleLoadData) X(cuModuleGetFunction) X(cuFuncSetAttribute)      \
     X(cuLaunchKernel) X(cuLaunchKernelEx) X(cuTensorMapEncodeTiled)                       \
     X(cuStreamBeginCapture) X(cuStreamEndCapture) X(cuGraphInstantiate) X(cuGraphLaunch)  \
-    X(cuGraphExecDestroy) X(cuGraphDestroy) X(cuMemGetInfo)
+    X(cuGraphExecDestroy) X(cuGraphDestroy) X(cuMemGetInfo)                               \
+    X(cuIpcGetMemHandle) X(cuIpcOpenMemHandle) X(cuIpcCloseMemHandle)
 
 namespace {
 
@@ -676,6 +677,51 @@ int dlg_nccl_wait(void) {
     REQUIRE_READY(g_status)
     CU(cuEventRecord(g_ev_comm, g_comm_stream));
     CU(cuStreamWaitEvent(g_stream, g_ev_comm, 0));
+    return 0;
+}
+
+// ---- peer memory: allocations that other ranks of the node map into their own address space ----------------
+// (cuMemAlloc'd directly: the caching allocator never recycles them, and an IPC handle covers exactly this block)
+void *dlg_ipc_alloc(size_t nbytes) {
+    REQUIRE_READY(nullptr)
+    CUdeviceptr p = 0;
+    size_t sz = (nbytes + 0x1FFFFF) & ~size_t(0x1FFFFF);
+    CUresult r = drv.p_cuMemAlloc(&p, sz);
+    if (r != CUDA_SUCCESS) { fail((int)r, "cuMemAlloc (peer memory)"); return nullptr; }
+    r = drv.p_cuMemsetD8Async(p, 0, sz, g_stream);
+    if (r == CUDA_SUCCESS) r = drv.p_cuStreamSynchronize(g_stream);
+    if (r != CUDA_SUCCESS) { fail((int)r, "cuMemsetD8Async (peer memory)"); drv.p_cuMemFree(p); return nullptr; }
+    return (void *)p;
+}
+
+int dlg_ipc_free(void *dptr) {
+    if (!dptr || !g_ready || g_shutdown) return 0;
+    CU(cuMemFree((CUdeviceptr)dptr));
+    return 0;
+}
+
+int dlg_ipc_export(void *dptr, unsigned char handle[64]) {
+    REQUIRE_READY(g_status)
+    static_assert(sizeof(CUipcMemHandle) == 64, "CUipcMemHandle is 64 bytes");
+    CUipcMemHandle h;
+    CU(cuIpcGetMemHandle(&h, (CUdeviceptr)dptr));
+    memcpy(handle, &h, 64);
+    return 0;
+}
+
+void *dlg_ipc_open(const unsigned char handle[64]) {
+    REQUIRE_READY(nullptr)
+    CUipcMemHandle h;
+    memcpy(&h, handle, 64);
+    CUdeviceptr p = 0;
+    CUresult r = drv.p_cuIpcOpenMemHandle(&p, h, CU_IPC_MEM_LAZY_ENABLE_PEER_ACCESS);
+    if (r != CUDA_SUCCESS) { fail((int)r, "cuIpcOpenMemHandle"); return nullptr; }
+    return (void *)p;
+}
+
+int dlg_ipc_close(void *mapped) {
+    if (!mapped || !g_ready || g_shutdown) return 0;
+    CU(cuIpcCloseMemHandle((CUdeviceptr)mapped));
     return 0;
 }
 

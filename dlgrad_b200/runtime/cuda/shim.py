@@ -116,6 +116,11 @@ class _CompileOnlyLib:
     def dlg_nccl_wait(self): return 0
     def dlg_nccl_destroy(self): return 0
     def dlg_nccl_version(self): return 0
+    def dlg_ipc_alloc(self, n): return self._addr(n)
+    def dlg_ipc_free(self, p): return 0
+    def dlg_ipc_export(self, p, h): return 0
+    def dlg_ipc_open(self, h): return self._addr(1 << 21)
+    def dlg_ipc_close(self, p): return 0
 
 
 def _load():

@@ -129,6 +129,16 @@ int   dlg_nccl_wait(void);                   /* compute stream waits for the com
 int   dlg_nccl_destroy(void);
 int   dlg_nccl_version(void);
 
+/* ---- peer memory over NVLink (no reference counterpart; SURVEY §8e "fused with its collective") ----------
+ * A rank allocates its gradient bucket, parameter bucket and flag words with dlg_ipc_alloc, exports a 64-byte
+ * handle for each, and maps every peer's with dlg_ipc_open; the fused reduce-scatter + Adam + all-gather kernel
+ * (dlgrad_b200/distributed.py) then loads and stores peer memory directly.  One process per GPU, one node. */
+void *dlg_ipc_alloc(size_t nbytes);          /* zero-filled, never recycled by the caching allocator */
+int   dlg_ipc_free(void *dptr);
+int   dlg_ipc_export(void *dptr, unsigned char handle[64]);
+void *dlg_ipc_open(const unsigned char handle[64]);      /* NULL on failure                  */
+int   dlg_ipc_close(void *mapped);
+
 #ifdef __cplusplus
 }
 #endif

@@ -855,3 +855,33 @@ def test_split_k_in_kernel_finish_matches_two_kernel_sum():
                   what=f"fused split-K {M}x{N}x{K}/{S}, launch {rep}: bit-identical to slices + ordered sum")
         runner.rel_check(check, got, a.astype(np.float64).T @ b.astype(np.float64), runner.TOL_MATMUL,
                          f"fused split-K {M}x{N}x{K}/{S} vs float64")
+
+
+def test_fused_dp_adam_single_rank_is_bit_identical_to_adam():
+    """distributed.Adam (reduce-scatter + Adam + all-gather in one kernel over peer memory) at world == 1: the
+    parameters move into one flat bucket, the moments are flat, and three steps must give the SAME BITS as
+    nn.optim.Adam's multi-tensor kernel.  The multi-rank exchange itself is exercised by scripts/dp_fused_check.py
+    under torchrun (2+ GPUs; profiles/r01_dp_fused_check.txt)."""
+    from dlgrad_b200 import Tensor, distributed, nn
+    rng = np.random.default_rng(5)
+    shapes = [(96, 64), (64,), (256, 64), (7, 3), (1, 1)]
+    init = [rng.standard_normal(s).astype(np.float32) for s in shapes]
+    grads = [[rng.standard_normal(s).astype(np.float32) for s in shapes] for _ in range(3)]
+    a = [Tensor(w.copy(), device="cuda", requires_grad=True) for w in init]
+    b = [Tensor(w.copy(), device="cuda", requires_grad=True) for w in init]
+    ref = nn.optim.Adam(a, lr=1e-2, betas=(0.8, 0.95))
+    fused = distributed.Adam(b, lr=1e-2, betas=(0.8, 0.95))
+    check(b[2].numpy(), init[2], exact=True, what="parameters keep their values when they move into the bucket")
+    for step in range(3):
+        for p, q, g in zip(a, b, grads[step]):
+            p.grad = Tensor(g.copy(), device="cuda")
+            q.grad = Tensor(g.copy(), device="cuda")
+        ref.step()
+        fused.step()
+        for i, (p, q) in enumerate(zip(a, b)):
+            check(q.numpy(), p.numpy(), exact=True, what=f"fused DP Adam step {step}, tensor {i}")
+    # the re-homed parameters are ordinary tensors: ops read them where they now live
+    x = rng.standard_normal((5, 64)).astype(np.float32)
+    got = (Tensor(x.copy(), device="cuda") @ b[0].transpose(0, 1)).numpy()
+    want = (Tensor(x.copy(), device="cuda") @ a[0].transpose(0, 1)).numpy()
+    check(got, want, exact=True, what="matmul against a bucket-resident weight")

@@ -71,6 +71,39 @@ def test_shard_offsets_layout():
     assert offs[-1] % 64 == 0
 
 
+@pytest.mark.parametrize("world", [1, 2, 3, 8])
+def test_bucket_layout_and_sharded_update_cover_every_parameter(world):
+    """distributed.Adam's layout: the flat bucket splits into `world` shards of whole float4s whose boundaries may
+    cut through tensors.  A numpy walk of the kernel's schedule (sum the ranks' buckets in rank order on the owner's
+    shard, update, store the shard to every replica) must touch every element exactly once and equal the
+    all-reduce + per-tensor update it replaces."""
+    from dlgrad_b200.distributed import bucket_layout
+    sizes = [96 * 32, 1, 7, 130, 4 * 32 * 32, 33]
+    offs, total, shard = bucket_layout(sizes, world)
+    assert total == shard * world and shard % 4 == 0 and total >= offs[-1] + sizes[-1]
+    assert all(o % 64 == 0 for o in offs)
+    rng = np.random.default_rng(world)
+    grads = rng.standard_normal((world, total)).astype(np.float32)
+    weights = np.tile(rng.standard_normal(total).astype(np.float32), (world, 1))       # identical replicas
+    want = weights[0] - np.float32(0.1) * (np.add.reduce(grads, axis=0, dtype=np.float32) * np.float32(1.0 / world))
+    touched = np.zeros(total, dtype=np.int32)
+    for owner in range(world):
+        lo, hi = owner * shard, (owner + 1) * shard
+        g = grads[0, lo:hi].copy()
+        for r in range(1, world):
+            g += grads[r, lo:hi]
+        new = weights[owner, lo:hi] - np.float32(0.1) * (g * np.float32(1.0 / world))
+        for r in range(world):
+            weights[r, lo:hi] = new
+        touched[lo:hi] += 1
+    assert (touched == 1).all()
+    for r in range(world):
+        assert np.array_equal(weights[r], weights[0])
+    np.testing.assert_allclose(weights[0], want, rtol=1e-6, atol=1e-7)
+    for o, n in zip(offs, sizes):                          # every tensor lies inside the bucket, in order
+        assert o + n <= total
+
+
 @pytest.mark.timeout(300)
 def test_two_rank_dp_step_equals_full_batch_step(tmp_path):
     import torch.multiprocessing as mp
