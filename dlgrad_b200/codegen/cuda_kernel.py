@@ -1276,6 +1276,47 @@ extern "C" __global__ void __launch_bounds__(256) {KNAME}{SIG_ALIAS} {{
     return Kernel("adam_multi", src, (acc, 1, 1), (256, 1, 1), 0, 0)
 
 
+def pack_multi(sizes: tuple, offsets: tuple) -> Kernel:
+    """Copy every gradient tensor into its slice of the flat bucket in ONE launch (instead of one device-to-device
+    copy per tensor): p0 is a device table of source addresses, `out` the bucket, `offsets` the element offset of each
+    slice (multiples of 4).  Sources must be 16-byte aligned; a size that is not a multiple of 4 ends in scalar copies."""
+    CH = 2048                                       # float4 per block
+    starts, acc = [0], 0
+    for n in sizes:
+        acc += max(1, _cdiv(n // 4, CH))
+        starts.append(acc)
+    src = f"""
+__device__ const unsigned blk_start[{len(starts)}] = {{{", ".join(str(s) + "u" for s in starts)}}};
+__device__ const unsigned elem_count[{len(sizes)}] = {{{", ".join(str(n) + "u" for n in sizes)}}};
+__device__ const unsigned dst_vec[{len(sizes)}] = {{{", ".join(str(o // 4) + "u" for o in offsets)}}};
+extern "C" __global__ void __launch_bounds__(256) {KNAME}{SIG_ALIAS} {{
+    const unsigned long long* tab = reinterpret_cast<const unsigned long long*>(p0);
+    unsigned lo = 0, hi = {len(sizes)}u;            // tensor t with blk_start[t] <= blockIdx.x < blk_start[t+1]
+    while (hi - lo > 1u) {{ const unsigned mid = (lo + hi) >> 1; if (blk_start[mid] <= blockIdx.x) lo = mid; else hi = mid; }}
+    const unsigned t = lo, n = elem_count[t], nv = n >> 2;
+    const float4* S = reinterpret_cast<const float4*>(tab[t]);
+    float4* D = reinterpret_cast<float4*>(out) + dst_vec[t];
+    const unsigned base = (blockIdx.x - blk_start[t]) * {CH}u;
+    float4 v[{CH // 256}];
+    #pragma unroll
+    for (unsigned k = 0; k < {CH // 256}u; ++k) {{
+        const unsigned i = base + k * 256u + threadIdx.x;
+        if (i < nv) v[k] = __ldcs(S + i);
+    }}
+    #pragma unroll
+    for (unsigned k = 0; k < {CH // 256}u; ++k) {{
+        const unsigned i = base + k * 256u + threadIdx.x;
+        if (i < nv) D[i] = v[k];
+    }}
+    if (base == 0u && threadIdx.x < (n & 3u)) {{
+        const unsigned i = (nv << 2) + threadIdx.x;
+        reinterpret_cast<float*>(D)[i] = reinterpret_cast<const float*>(S)[i];
+    }}
+}}
+"""
+    return Kernel("pack_multi", src, (acc, 1, 1), (256, 1, 1), 0, 0)
+
+
 def dp_adam(world: int, shard_vecs: int, beta1: float, beta2: float, eps: float, timeout_s: float = 20.0) -> Kernel:
     """Data-parallel optimizer step as ONE kernel per rank over NVLink peer memory: reduce-scatter of the gradients
     (P2P loads), Adam on this rank's 1/world shard, all-gather of the updated parameters (P2P stores).  It replaces

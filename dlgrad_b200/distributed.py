@@ -118,9 +118,9 @@ def prebuild(sizes: list[int], worlds: tuple = (2, 4, 8), betas: tuple = (0.9, 0
     from dlgrad_b200.codegen import cuda_kernel as ck
     from dlgrad_b200.runtime.cuda import compiler
     for w in worlds:
-        _, _, shard = bucket_layout(sizes, w)
-        k = ck.dp_adam(w, shard // 4, betas[0], betas[1], eps)
-        compiler.get_function(k.name, k.source)
+        offs, _, shard = bucket_layout(sizes, w)
+        for k in (ck.dp_adam(w, shard // 4, betas[0], betas[1], eps), ck.pack_multi(tuple(sizes), tuple(offs))):
+            compiler.get_function(k.name, k.source)
 
 
 class _PeerBlock:
@@ -198,6 +198,16 @@ class Adam:
         self.m = shim.calloc(self.shard * 4)
         self.v = shim.calloc(self.shard * 4)
         self.plan = cuda_ops.Plan(ck.dp_adam(world, self.shard // 4, self.beta1, self.beta2, self.eps))
+        # gradient packing: one launch over a table of source addresses (two pinned staging tables alternate, so
+        # one is never rewritten while its copy may still be in flight)
+        n = len(params)
+        self.pack = cuda_ops.Plan(ck.pack_multi(tuple(self.sizes), tuple(self.offs)))
+        self.pack_host = [lib.dlg_host_alloc(8 * n), lib.dlg_host_alloc(8 * n)]
+        if shim.NULL in self.pack_host:
+            raise MemoryError("pinned staging allocation failed: " + shim.last_error())
+        self.pack_view = [shim.ffi.cast("unsigned long long *", h) for h in self.pack_host]
+        self.pack_dev = shim.alloc(8 * n)
+        self.flip = 0
         shim.synchronize()
         if world > 1:
             all_gather_bytes(b"\0")                # nobody launches before every rank has mapped its peers
@@ -212,15 +222,24 @@ class Adam:
         bc1 = float(f32(1.0 - self.beta1 ** self.t))
         bc2 = float(f32(1.0 - self.beta2 ** self.t))
         lib = shim.lib
-        for p, off, n in zip(self.params, self.offs, self.sizes):
-            dst = self.grads.fptr + off
-            if p.grad is None:
-                shim.check(lib.dlg_memset32(dst, 0, n), "dlg_memset32")
-                continue
-            g = p.grad.data
-            if g.metadata.device is not Device.CUDA:
+        grads = [None if p.grad is None else p.grad.data for p in self.params]
+        for g in grads:
+            if g is not None and g.metadata.device is not Device.CUDA:
                 g._to_cuda()
-            shim.check(lib.dlg_d2d(dst, g.ptr, n * 4), "dlg_d2d")
+        if all(g is not None and g.aligned for g in grads):
+            self.flip ^= 1
+            view = self.pack_view[self.flip]
+            for i, g in enumerate(grads):
+                view[i] = shim.address(g.ptr)
+            shim.check(lib.dlg_h2d_async(self.pack_dev, self.pack_host[self.flip], 8 * len(grads)), "dlg_h2d_async")
+            self.pack.run_into(self.grads.fptr, self.pack_dev)
+        else:
+            for g, off, n in zip(grads, self.offs, self.sizes):
+                dst = self.grads.fptr + off
+                if g is None:
+                    shim.check(lib.dlg_memset32(dst, 0, n), "dlg_memset32")
+                else:
+                    shim.check(lib.dlg_d2d(dst, g.ptr, n * 4), "dlg_d2d")
         flush_pending(tuple(p.data for p in self.params))
         self.plan.run_into(shim.NULL, self.table, self.m, self.v, self.flags.fptr, bc1, bc2, float(f32(self.lr)),
                            1.0 / _state["world"])

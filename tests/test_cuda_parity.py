@@ -885,3 +885,15 @@ def test_fused_dp_adam_single_rank_is_bit_identical_to_adam():
     got = (Tensor(x.copy(), device="cuda") @ b[0].transpose(0, 1)).numpy()
     want = (Tensor(x.copy(), device="cuda") @ a[0].transpose(0, 1)).numpy()
     check(got, want, exact=True, what="matmul against a bucket-resident weight")
+    # a parameter that receives no gradient stays put (its slice of the gradient bucket is cleared, moments are zero)
+    c = [Tensor(w.copy(), device="cuda", requires_grad=True) for w in init[:2]]
+    solo = distributed.Adam(c, lr=1e-2)
+    lone = nn.optim.Adam([Tensor(init[0].copy(), device="cuda", requires_grad=True)], lr=1e-2)
+    for step in range(2):
+        c[0].grad = Tensor(grads[step][0].copy(), device="cuda")
+        lone.params[0].grad = Tensor(grads[step][0].copy(), device="cuda")
+        c[1].grad = None
+        solo.step()
+        lone.step()
+    check(c[0].numpy(), lone.params[0].numpy(), exact=True, what="fused DP Adam, tensor with a gradient (copy path)")
+    check(c[1].numpy(), init[1], exact=True, what="fused DP Adam, tensor without a gradient is unchanged")
