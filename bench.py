@@ -311,6 +311,11 @@ def run_b200(args) -> None:
 
     cfg_kw = C5 if args.config == "c5" else C4
     fused_dp = world > 1 and os.environ.get("DLGRAD_DP_FUSED", "1") != "0"
+    if fused_dp and not distributed.peer_memory_available():
+        fused_dp = False
+        if rank == 0:
+            print("[bench] peer memory cannot be mapped on this box: gradient exchange falls back to ncclAllReduce "
+                  f"({shim.last_error()})", file=sys.stderr)
     cfg, gpt, params, opt = build_gpt(cfg_kw, "cuda", fused_dp)
     opt.grad_scale = 1.0 / world
     data_rng = np.random.default_rng(1000 + rank)            # rank-specific tokens

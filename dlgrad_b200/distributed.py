@@ -123,6 +123,36 @@ def prebuild(sizes: list[int], worlds: tuple = (2, 4, 8), betas: tuple = (0.9, 0
             compiler.get_function(k.name, k.source)
 
 
+def peer_memory_available() -> bool:
+    """Collective probe: can every rank map every other rank's memory (cuIpc handles, peer access over NVLink)?
+    All ranks get the same answer, so they can agree to use ncclAllReduce + nn.optim.Adam instead when some
+    container or topology forbids it."""
+    world, rank_ = _state["world"], _state["rank"]
+    if world == 1:
+        return True
+    ffi, lib = shim.ffi, shim.lib
+    shim.init()
+    h = ffi.new("unsigned char[64]")
+    ptr = lib.dlg_ipc_alloc(1 << 21)
+    ok = ptr != shim.NULL and lib.dlg_ipc_export(ptr, h) == 0
+    rows = all_gather_bytes(bytes(ffi.buffer(h, 64)) + bytes([int(ok)]))
+    if all(r[64] == 1 for r in rows):
+        for r in range(world):
+            if r == rank_:
+                continue
+            m = lib.dlg_ipc_open(ffi.new("unsigned char[64]", rows[r][:64]))
+            if m == shim.NULL:
+                ok = False
+                break
+            lib.dlg_ipc_close(m)
+    else:
+        ok = False
+    verdict = all(r[0] == 1 for r in all_gather_bytes(bytes([int(ok)])))     # also: nobody frees before all closed
+    if ptr != shim.NULL:
+        lib.dlg_ipc_free(ptr)
+    return verdict
+
+
 class _PeerBlock:
     """One dlg_ipc_alloc'd block and its peers' mappings; `addr[r]` is rank r's block as seen from this process."""
 

@@ -8,6 +8,8 @@ generated sm_100a kernels, and is compared with
 bit-exact for integer / index / selection / data-movement work, within the north star's tolerances
 otherwise (tests/runner.py: 1e-5 relative for elementwise / reduce / softmax, 1e-4 for matmul).
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -897,3 +899,24 @@ def test_fused_dp_adam_single_rank_is_bit_identical_to_adam():
         lone.step()
     check(c[0].numpy(), lone.params[0].numpy(), exact=True, what="fused DP Adam, tensor with a gradient (copy path)")
     check(c[1].numpy(), init[1], exact=True, what="fused DP Adam, tensor without a gradient is unchanged")
+
+
+@pytest.mark.timeout(600)
+def test_fused_dp_step_across_two_gpus():
+    """The multi-rank exchange itself (peer-memory mapping, the two cross-GPU barriers, rank-ordered sums): two ranks
+    under torchrun run scripts/dp_fused_check.py, which demands bit-identity with a float32 restatement of the
+    schedule and with ncclAllReduce + Adam.  Skipped on a single-GPU box."""
+    import socket
+    import subprocess
+    import sys
+    from dlgrad_b200.runtime.cuda import shim
+    if shim.COMPILE_ONLY or shim.lib.dlg_device_count() < 2:
+        pytest.skip("needs two GPUs")
+    with socket.socket() as sock:
+        sock.bind(("127.0.0.1", 0))
+        port = sock.getsockname()[1]
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", str(port), "scripts/dp_fused_check.py"],
+                         cwd=root, capture_output=True, text=True, timeout=500)
+    assert res.returncode == 0 and "PASS" in res.stdout, res.stdout[-2000:] + res.stderr[-2000:]
