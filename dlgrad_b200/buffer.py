@@ -15,6 +15,7 @@ Differences from the reference that are deliberate:
 """
 from __future__ import annotations
 
+import os
 import weakref
 
 from dlgrad_b200.device import Device, as_device
@@ -71,11 +72,62 @@ LAZY_MIN_NUMEL = 1 << 16      # pointwise producers below this size are not wort
 _pending_buffers: "weakref.WeakSet[Buffer]" = None  # type: ignore[assignment]  (created below)
 
 
+# ---- buffers whose content is a pure function of shapes and python scalars ------------------------------------
+# `Tensor.tril(Tensor.ones((T, T)))`, `mask == 0` and friends are rebuilt by every attention layer of every step
+# (examples/gpt.py:50-52): six small launch-bound kernels per layer.  Creation ops (FULL, ARANGE) therefore run
+# lazily and carry a content tag; elementwise ops whose operands are all tagged (or host scalars) are tagged in turn
+# and evaluated ONCE: the device storage of the result is kept under its tag and handed to every later Buffer with
+# the same tag.  Such storage is shared, so it is copy-on-write (`_cow`): flush_pending(written) — which every
+# in-place writer calls first — gives a written Buffer a private copy and drops its tag.  Results of FULL / ARANGE
+# themselves are never shared (a `Tensor.ones` is a perfectly good parameter).
+CONST_CACHE_LIMIT = 256 << 20
+_const_cache: dict = {}                  # content tag -> device storage
+_const_cache_bytes = [0]
+CONST_FOLD = os.environ.get("DLGRAD_CONST_FOLD", "1") != "0"
+
+
+def _operand_tag(b: "Buffer"):
+    return ("s", float(b.scalar).hex()) if b.scalar is not None else b._const      # hex: -0.0 != 0.0, nan == nan
+
+
+def _const_node(tag: tuple, shape: tuple, dtype: DType, compute) -> "Buffer":
+    """The Buffer for content `tag`: shared storage if it has been computed before, else `compute()` (kept if it fits)."""
+    hit = _const_cache.get(tag)
+    if hit is not None:
+        b = Buffer(hit, shape, _CUDA, dtype)
+        b._const, b._cow = tag, True
+        return b
+    b = compute()
+    if b.metadata.device is _CUDA and _const_cache_bytes[0] + b.metadata.nbytes <= CONST_CACHE_LIMIT:
+        _const_cache[tag] = b.ptr
+        _const_cache_bytes[0] += b.metadata.nbytes
+        b._cow = True
+    b._const = tag
+    return b
+
+
+def _unshare(b: "Buffer") -> None:
+    """`b` is about to be written in place: its content stops being a function of its tag, and storage it shares
+    with the constant cache is replaced by a private copy."""
+    b._const = None
+    if b._cow:
+        from dlgrad_b200.runtime.cuda import shim
+        fresh = shim.alloc(b.metadata.nbytes)
+        shim.check(shim.lib.dlg_d2d(fresh, b._ptr, b.metadata.nbytes), "dlg_d2d")
+        b.ptr = fresh
+        b._keep = None
+
+
 def flush_pending(written: tuple = ()) -> None:
     """Materialise deferred buffers before an IN-PLACE write (optimizer steps, the cross-entropy in-place
     subtract, copy_from): a deferred producer reads its sources when it runs, so it must run before one of
     them is overwritten.  With `written` (the Buffers about to be mutated) only chains that read one of
     them are forced; without it every pending buffer is."""
+    for w in written:
+        if w._const is not None or w._cow:
+            if w._pending is not None:
+                _ = w.ptr
+            _unshare(w)
     if not _pending_buffers:
         return
     ids = {id(w) for w in written}
@@ -102,7 +154,7 @@ def _reads_any(b: "Buffer", ids: set) -> bool:
 
 
 class Buffer:
-    __slots__ = ("_ptr", "_pending", "metadata", "scalar", "aligned", "_keep", "__weakref__")
+    __slots__ = ("_ptr", "_pending", "metadata", "scalar", "aligned", "_keep", "_const", "_cow", "__weakref__")
 
     def __init__(self, data: CDataPtr, shape: tuple, device: str | Device | None = _CPU,
                  dtype: str | DType | None = _F32, **kwargs) -> None:
@@ -113,6 +165,8 @@ class Buffer:
         self.scalar = kwargs.get("scalar")       # python float for host 0-d scalars
         self.aligned = kwargs.get("aligned", True)   # 16-byte aligned base (false for odd-offset slices)
         self._keep = kwargs.get("keep")          # object that owns the memory `ptr` points into
+        self._const = None                       # content tag (see _const_node above)
+        self._cow = False                        # storage shared with the constant cache: copy before writing
 
     # ------------------------------------------------------------------ deferred pointwise producers
     # A CUDA Buffer may be created WITHOUT running its kernel: `_pending` records a cheap pointwise
@@ -134,6 +188,7 @@ class Buffer:
     def ptr(self, value: CDataPtr) -> None:
         self._ptr = value
         self._pending = None
+        self._cow = False
 
     @staticmethod
     def _deferred(pending: tuple, shape: tuple, dtype: DType = _F32) -> "Buffer":
@@ -176,12 +231,22 @@ class Buffer:
     @staticmethod
     def full(shape: tuple, fill_value: Scalar, device: Device, dtype: DType = _F32) -> "Buffer":
         label, run = Buffer._creation_device(device)
+        if run is _CUDA and CONST_FOLD:
+            b = Buffer(None, shape, _CUDA, dtype)          # runs on first use; never if only its tag is needed
+            b._pending = ("full", tuple(shape), fill_value)
+            b._const = ("full", tuple(shape), float(fill_value).hex())
+            return b
         return Buffer(_dispatch(op=BufferOps.FULL, device=run, shape=shape, fill_value=fill_value),
                       shape, label, dtype)
 
     @staticmethod
     def arange(shape: tuple, device: Device, dtype: DType = _F32) -> "Buffer":
         label, run = Buffer._creation_device(device)
+        if run is _CUDA and CONST_FOLD:
+            b = Buffer(None, shape, _CUDA, dtype)
+            b._pending = ("arange", tuple(shape))
+            b._const = ("arange", tuple(shape))
+            return b
         return Buffer(_dispatch(op=BufferOps.ARANGE, device=run, shape=shape), shape, label, dtype)
 
     # ------------------------------------------------------------------ device routing
@@ -241,8 +306,12 @@ class Buffer:
         if self._pending is not None and self._pending[0] == "relu":
             # a pointwise producer commutes with reshape: stay deferred (Linear flattens its input before the GEMM)
             return Buffer._deferred(("relu", self._pending[1].reshape(new_shape)), new_shape, self.metadata.dtype)
-        return Buffer(self.ptr, new_shape, self.metadata.device, self.metadata.dtype,
+        view = Buffer(self.ptr, new_shape, self.metadata.device, self.metadata.dtype,
                       scalar=self.scalar, aligned=self.aligned, keep=self._keep)
+        if self._const is not None:
+            view._const = ("reshape", self._const, new_shape)
+        view._cow = self._cow
+        return view
 
     def unsqueeze(self, dim: list[int] | int) -> None:
         if dim == -1:
@@ -399,7 +468,8 @@ class Buffer:
     def where(self, inp: "Buffer | Scalar", other: "Buffer | Scalar") -> "Buffer":
         inp, other = Buffer._as_buffer(inp), Buffer._as_buffer(other)
         dev = Buffer._route(self, inp, other)
-        return self._like(_dispatch(op=UnaryOps.WHERE, device=dev, cond=self, x=inp, y=other), self.shape, dev)
+        run = lambda: self._like(_dispatch(op=UnaryOps.WHERE, device=dev, cond=self, x=inp, y=other), self.shape, dev)  # noqa: E731
+        return Buffer._folded(dev, ("where",), (self, inp, other), self.shape, run)
 
     @staticmethod
     def masked_fill(x: "Buffer", mask: "Buffer", val: Scalar) -> "Buffer":
@@ -413,13 +483,24 @@ class Buffer:
     def __le__(self, other: "Buffer") -> "Buffer":
         out_shape = get_broadcast_shape(self.shape, other.shape)
         dev = Buffer._route(self, other)
-        return self._like(_dispatch(op=BinaryOps.CMP, device=dev, x=self, y=other, out_shape=out_shape,
-                                    mode="<="), out_shape, dev)
+        run = lambda: self._like(_dispatch(op=BinaryOps.CMP, device=dev, x=self, y=other, out_shape=out_shape,  # noqa: E731
+                                           mode="<="), out_shape, dev)
+        return Buffer._folded(dev, ("cmp<=",), (self, other), out_shape, run)
 
     def _compare(self, other: "Buffer | Scalar", op: BinaryOps) -> "Buffer":
         other = Buffer._as_buffer(other)
         dev = Buffer._route(self, other)
-        return self._like(_dispatch(op=op, device=dev, x=self, y=other), self.shape, dev)
+        run = lambda: self._like(_dispatch(op=op, device=dev, x=self, y=other), self.shape, dev)  # noqa: E731
+        return Buffer._folded(dev, (op.name,), (self, other), self.shape, run)
+
+    @staticmethod
+    def _folded(dev: Device, head: tuple, operands: tuple, shape: tuple, run) -> "Buffer":
+        """`run()`, or the stored result if every operand's content is a pure function of shapes and scalars."""
+        if dev is _CUDA and CONST_FOLD:
+            tags = tuple(_operand_tag(o) for o in operands)
+            if None not in tags and any(o.scalar is None for o in operands):
+                return _const_node(head + tags + (tuple(shape),), shape, operands[0].metadata.dtype, run)
+        return run()
 
     def __gt__(self, other: "Buffer | Scalar") -> "Buffer":
         return self._compare(other, BinaryOps.GT)
@@ -440,6 +521,9 @@ class Buffer:
         # for the one-sided broadcasts it supports that equals the broadcast shape used here.
         out_shape = get_broadcast_shape(self.shape, other.shape)
         dev = Buffer._route(self, other)
+        if dev is _CUDA and CONST_FOLD and _operand_tag(self) is not None and _operand_tag(other) is not None:
+            run = lambda: self._like(_dispatch(op=op, device=dev, x=self, y=other), out_shape, dev)  # noqa: E731
+            return Buffer._folded(dev, (op.name,), (self, other), out_shape, run)
         if op is BinaryOps.MUL and dev is _CUDA:
             if other.scalar is not None and self.scalar is None and self.numel >= LAZY_MIN_NUMEL:
                 return Buffer._deferred(("scale", self, float(other.scalar)), out_shape, self.dtype)

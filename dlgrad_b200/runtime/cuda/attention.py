@@ -50,6 +50,26 @@ def tag_of(buf: Buffer):
 BWD_ENABLED = os.environ.get("DLGRAD_FUSED_ATTN_BWD", "1") != "0"
 MIN_SCORES = 1 << 22          # elements of (batch, Tq, Tk) below which the eager chain is just as good
 _plans: dict = {}
+_digests: dict = {}           # (content tag of the mask, Tq, Tk) -> mask_bits output; a tagged mask (Buffer._const) is a
+                              # pure function of shapes and scalars, so its digest is computed once, not per layer and step
+
+
+def _mask_digest(mask: Buffer, Tq: int, Tk: int):
+    from dlgrad_b200.codegen import cuda_kernel as ck
+    from dlgrad_b200.runtime.cuda import ops as _ops
+    bkey = ("mask_bits", Tq, Tk)
+    bplan = _plans.get(bkey)
+    if bplan is None:
+        bplan = _plans[bkey] = _ops.Plan(ck.mask_bits(Tq, Tk))
+    tag = mask._const
+    if tag is None:
+        return bplan.run(_ops._dev_ptr(mask))
+    bits = _digests.get((tag, Tq, Tk))
+    if bits is None:
+        if len(_digests) >= 64:
+            _digests.clear()
+        bits = _digests[(tag, Tq, Tk)] = bplan.run(_ops._dev_ptr(mask))
+    return bits
 
 
 def eligible(x: Buffer, y: Buffer) -> bool:
@@ -99,12 +119,7 @@ def scores(q: Buffer, k: Buffer, scale: float, mask: Buffer, fill: float):
             raise RuntimeError("dlg_mm_plan_create failed: " + shim.last_error())
         plan = _plans[key] = (p, kern.out_elems * 4)
     p, nbytes = plan
-    bkey = ("mask_bits", Tq, Tk)
-    bplan = _plans.get(bkey)
-    if bplan is None:
-        from dlgrad_b200.codegen import cuda_kernel as ck
-        bplan = _plans[bkey] = _ops.Plan(ck.mask_bits(Tq, Tk))
-    bits = bplan.run(_ops._dev_ptr(mask))             # the same (Tq, Tk) plane for every head: 1 bit per entry
+    bits = _mask_digest(mask, Tq, Tk)                 # the same (Tq, Tk) plane for every head: 1 bit per entry
     pq, pk, pm = _ops._dev_ptr(q), _ops._dev_ptr(k), bits
     timer = _profile.matmul_timer
     t0 = timer.start() if timer is not None else None
@@ -138,7 +153,10 @@ def dscores(dO: Buffer, v: Buffer, O: Buffer, P: Buffer, mask: Buffer, scale: fl
     p, nbytes, dot_plan, bits_plan = plan
     aux = shim.alloc((nb * Tq + mask_words(Tq, Tk)) * 4)     # [rowsum(dO * O) | mask bits, live tiles, live rows]; it travels with dS
     dot_plan.run_into(aux, _ops._dev_ptr(dO), _ops._dev_ptr(O))
-    bits_plan.run_into(aux + nb * Tq, _ops._dev_ptr(mask))
+    if mask._const is not None:                      # digest of a constant mask: computed once, copied (a few hundred KB)
+        shim.check(shim.lib.dlg_d2d(aux + nb * Tq, _mask_digest(mask, Tq, Tk), mask_words(Tq, Tk) * 4), "dlg_d2d")
+    else:
+        bits_plan.run_into(aux + nb * Tq, _ops._dev_ptr(mask))
     pd, pv, pp = _ops._dev_ptr(dO), _ops._dev_ptr(v), _ops._dev_ptr(P)
     timer = _profile.matmul_timer
     t0 = timer.start() if timer is not None else None

@@ -137,6 +137,12 @@ def materialize(buf: Buffer) -> None:
     pend = buf._pending
     if pend is None:
         return
+    if pend[0] == "full":
+        buf.ptr = full(pend[1], pend[2])
+        return
+    if pend[0] == "arange":
+        buf.ptr = arange(pend[1])
+        return
     if pend[0] == "tr":
         src = pend[1]
         nd = len(src.metadata.shape)

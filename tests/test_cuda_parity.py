@@ -920,3 +920,44 @@ def test_fused_dp_step_across_two_gpus():
                           "--master-addr", "127.0.0.1", "--master-port", str(port), "scripts/dp_fused_check.py"],
                          cwd=root, capture_output=True, text=True, timeout=500)
     assert res.returncode == 0 and "PASS" in res.stdout, res.stdout[-2000:] + res.stderr[-2000:]
+
+
+def test_constant_masks_are_computed_once_shared_and_copy_on_write():
+    """Buffers whose content is a pure function of shapes and scalars (tril(ones), mask == 0, ...) are evaluated once
+    and share storage (dlgrad_b200/buffer.py, _const_node); FULL / ARANGE run lazily.  Values are unchanged, results of
+    `ones` are never shared, and an in-place writer gets a private copy first."""
+    from dlgrad_b200 import Tensor, nn
+    from dlgrad_b200.runtime.cuda import shim
+    T = 256
+    want = np.tril(np.ones((T, T), dtype=np.float32))
+    m1 = Tensor.tril(Tensor.ones((T, T), device="cuda"), k=0.0)
+    m2 = Tensor.tril(Tensor.ones((T, T), device="cuda"), k=0.0)
+    check(m1.numpy(), want, exact=True, what="tril(ones)")
+    check(m2.numpy(), want, exact=True, what="tril(ones), second construction")
+    if not shim.COMPILE_ONLY:
+        assert shim.address(m1.data.ptr) == shim.address(m2.data.ptr), "same content tag -> same storage"
+    z1, z2 = (m1 == Tensor(0.0)), (m2 == Tensor(0.0))
+    check(z1.numpy(), (want == 0).astype(np.float32), exact=True, what="tril(ones) == 0")
+    check(z2.numpy(), (want == 0).astype(np.float32), exact=True, what="tril(ones) == 0, again")
+    check(Tensor.tril(Tensor.ones((T, T), device="cuda"), k=1.0).numpy(), np.tril(np.ones((T, T), dtype=np.float32), 1),
+          exact=True, what="another diagonal is another tag")
+    # in-place writer on shared storage: copy first, the other holders and the cache keep the constant
+    m2.requires_grad = True
+    m2.grad = Tensor(np.ones((T, T), dtype=np.float32), device="cuda")
+    nn.optim.SGD([m2], lr=0.5).step()
+    check(m2.numpy(), want - np.float32(0.5), exact=True, what="SGD step on a tensor that shared constant storage")
+    check(m1.numpy(), want, exact=True, what="the other holder of that storage is untouched")
+    check(Tensor.tril(Tensor.ones((T, T), device="cuda"), k=0.0).numpy(), want, exact=True, what="and so is the cache")
+    check((m2 == Tensor(0.0)).numpy(), ((want - np.float32(0.5)) == 0).astype(np.float32), exact=True,
+          what="a written tensor is no longer a constant")
+    # FULL results are lazily created but never shared: a `ones` parameter is private
+    a, b = Tensor.ones((64, 64), device="cuda"), Tensor.ones((64, 64), device="cuda")
+    a.requires_grad = True
+    a.grad = Tensor(np.full((64, 64), 2.0, dtype=np.float32), device="cuda")
+    nn.optim.SGD([a], lr=0.25).step()
+    check(a.numpy(), np.full((64, 64), 0.5, dtype=np.float32), exact=True, what="updated ones")
+    check(b.numpy(), np.ones((64, 64), dtype=np.float32), exact=True, what="independent ones")
+    check(Tensor.full((4, 4), 0.5, device="cuda").numpy(), np.zeros((4, 4), dtype=np.float32), exact=True,
+          what="full() keeps the reference's int cast of the fill value")
+    check((Tensor.ones((8, 8), device="cuda") * 3.0 + Tensor.full((8, 8), 2.0, device="cuda")).numpy(),
+          np.full((8, 8), 5.0, dtype=np.float32), exact=True, what="arithmetic on constants")
