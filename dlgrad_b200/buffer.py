@@ -157,14 +157,16 @@ class Buffer:
     __slots__ = ("_ptr", "_pending", "metadata", "scalar", "aligned", "_keep", "_const", "_cow", "__weakref__")
 
     def __init__(self, data: CDataPtr, shape: tuple, device: str | Device | None = _CPU,
-                 dtype: str | DType | None = _F32, **kwargs) -> None:
+                 dtype: str | DType | None = _F32, scalar: float | None = None, aligned: bool = True,
+                 keep: object = None) -> None:
         self._ptr = data
         self._pending = None                     # deferred producer (CUDA only), see _deferred()
-        self.metadata = BufferMetadata(tuple(shape), dtype if isinstance(dtype, DType) else _F32,
+        self.metadata = BufferMetadata(shape if type(shape) is tuple else tuple(shape),
+                                       dtype if isinstance(dtype, DType) else _F32,
                                        device if isinstance(device, Device) else as_device(device))
-        self.scalar = kwargs.get("scalar")       # python float for host 0-d scalars
-        self.aligned = kwargs.get("aligned", True)   # 16-byte aligned base (false for odd-offset slices)
-        self._keep = kwargs.get("keep")          # object that owns the memory `ptr` points into
+        self.scalar = scalar                     # python float for host 0-d scalars
+        self.aligned = aligned                   # 16-byte aligned base (false for odd-offset slices)
+        self._keep = keep                        # object that owns the memory `ptr` points into
         self._const = None                       # content tag (see _const_node above)
         self._cow = False                        # storage shared with the constant cache: copy before writing
 

@@ -766,13 +766,13 @@ def adam_multi(params: list, grads: list, ms: list, vs: list, beta1: float, beta
         ent = _adam_tables[key] = {"plan": plan, "host": host, "views": views, "dev": shim.alloc(32 * n), "flip": 0}
     ent["flip"] ^= 1
     tab = ent["views"][ent["flip"]]
-    cast = ffi.cast
+    addr = shim.address
     i = 0
     for p, g, m, v in zip(params, grads, ms, vs):
-        tab[i] = int(cast("uintptr_t", _dev_ptr(p)))
-        tab[i + 1] = int(cast("uintptr_t", _dev_ptr(g)))
-        tab[i + 2] = int(cast("uintptr_t", _dev_ptr(m)))
-        tab[i + 3] = int(cast("uintptr_t", _dev_ptr(v)))
+        tab[i] = addr(_dev_ptr(p))
+        tab[i + 1] = addr(_dev_ptr(g))
+        tab[i + 2] = addr(_dev_ptr(m))
+        tab[i + 3] = addr(_dev_ptr(v))
         i += 4
     shim.check(lib.dlg_h2d_async(ent["dev"], ent["host"][ent["flip"]], 32 * len(sizes)), "dlg_h2d_async")
     ent["plan"].run_into(NULL, ent["dev"], NULL, NULL, NULL, bc1, bc2, lr, grad_scale)

@@ -199,10 +199,15 @@ def calloc(nbytes: int):
     return own(p, nbytes)
 
 
+_FLOAT_P = ffi.typeof("float *")
+_UINTPTR = ffi.typeof("uintptr_t")
+_cast, _gc, _free = ffi.cast, ffi.gc, lib.dlg_free
+
+
 def own(p, nbytes: int = 0):
     """Attach allocator ownership to a pointer returned by dlg_plan_run / dlg_alloc."""
-    return ffi.gc(ffi.cast("float *", p), lib.dlg_free, nbytes)
+    return _gc(_cast(_FLOAT_P, p), _free, nbytes)
 
 
 def address(ptr) -> int:
-    return int(ffi.cast("uintptr_t", ptr))
+    return int(_cast(_UINTPTR, ptr))
