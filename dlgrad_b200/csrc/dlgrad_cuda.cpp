@@ -107,9 +107,21 @@ int load_driver() {
 // ------------------------------------------------------------------------------------
 // caching allocator
 // ------------------------------------------------------------------------------------
+// A captured CUDA graph replays with the addresses it was captured with, so every block handed out while a
+// graph is being captured belongs to that graph's private POOL: when Python frees it — during the capture or
+// any time later — it goes back to the pool, never to the global cache, and only allocations of the same
+// capture can get it again.  Eager allocations between replays therefore never alias memory the graph writes.
+struct Pool {
+    std::unordered_map<size_t, std::vector<void *>> cache;
+    bool dead = false;                                         // its graph is gone: frees release to the driver
+};
+
 struct Allocator {
-    std::unordered_map<void *, size_t> live;                  // handed out: ptr -> rounded size
+    struct Block { size_t size; int pool; };
+    std::unordered_map<void *, Block> live;                   // handed out: ptr -> rounded size, owning pool (0 = none)
     std::unordered_map<size_t, std::vector<void *>> cache;    // rounded size -> free blocks
+    std::unordered_map<int, Pool> pools;
+    int cur_pool = 0, next_pool = 1;
     size_t live_bytes = 0, reserved_bytes = 0, peak_bytes = 0;
 
     static size_t round(size_t n) {
@@ -132,8 +144,17 @@ struct Allocator {
     void *get(size_t nbytes) {
         size_t sz = round(nbytes);
         void *p = nullptr;
+        if (cur_pool) {
+            auto &pc = pools[cur_pool].cache;
+            auto pit = pc.find(sz);
+            if (pit != pc.end() && !pit->second.empty()) {
+                p = pit->second.back();
+                pit->second.pop_back();
+            }
+        }
         auto it = cache.find(sz);
-        if (it != cache.end() && !it->second.empty()) {
+        if (p) {
+        } else if (it != cache.end() && !it->second.empty()) {
             p = it->second.back();
             it->second.pop_back();
         } else {
@@ -151,7 +172,7 @@ struct Allocator {
             reserved_bytes += sz;
             p = (void *)d;
         }
-        live.emplace(p, sz);
+        live.emplace(p, Block{sz, cur_pool});
         live_bytes += sz;
         if (live_bytes > peak_bytes) peak_bytes = live_bytes;
         return p;
@@ -160,10 +181,34 @@ struct Allocator {
     void put(void *p) {
         auto it = live.find(p);
         if (it == live.end()) return;   // not ours (a view into a block, or already freed)
-        size_t sz = it->second;
+        size_t sz = it->second.size;
+        int pool = it->second.pool;
         live.erase(it);
         live_bytes -= sz;
-        cache[sz].push_back(p);
+        if (!pool) {
+            cache[sz].push_back(p);
+            return;
+        }
+        Pool &pl = pools[pool];
+        if (pl.dead) {
+            drv.p_cuMemFree((CUdeviceptr)p);
+            reserved_bytes -= sz;
+        } else {
+            pl.cache[sz].push_back(p);
+        }
+    }
+
+    void destroy_pool(int id) {
+        auto it = pools.find(id);
+        if (it == pools.end()) return;
+        it->second.dead = true;                               // blocks still held by Python are released when freed
+        for (auto &kv : it->second.cache) {
+            for (void *p : kv.second) {
+                drv.p_cuMemFree((CUdeviceptr)p);
+                reserved_bytes -= kv.first;
+            }
+            kv.second.clear();
+        }
     }
 };
 
@@ -620,6 +665,30 @@ void *dlg_graph_end(void) {
         return nullptr;
     }
     return (void *)ge;
+}
+int dlg_pool_begin(void) {
+    REQUIRE_READY(-1)
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g_alloc.cur_pool) {
+        snprintf(g_err, sizeof g_err, "a capture pool is already open");
+        g_status = -120;
+        return -1;
+    }
+    g_alloc.cur_pool = g_alloc.next_pool++;
+    g_alloc.pools[g_alloc.cur_pool];
+    return g_alloc.cur_pool;
+}
+int dlg_pool_end(void) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    g_alloc.cur_pool = 0;
+    return 0;
+}
+int dlg_pool_destroy(int pool) {
+    if (!g_ready || g_shutdown) return 0;
+    drv.p_cuStreamSynchronize(g_stream);                      // no replay may still be writing the pool's blocks
+    std::lock_guard<std::mutex> lk(g_mu);
+    g_alloc.destroy_pool(pool);
+    return 0;
 }
 int dlg_graph_launch(void *ge) {
     REQUIRE_READY(g_status)

@@ -82,6 +82,10 @@ class Adam(Optimizer):
         self.v = {id(p): Tensor.zeros_like(p) for p in params}
 
     def step(self) -> None:
+        from dlgrad_b200.runtime.cuda import shim
+        if shim.capture["on"]:
+            raise RuntimeError("Adam.step() inside a captured step: its bias corrections 1 - beta^t change every step and "
+                               "would be frozen into the graph.  Capture forward + backward, call step() after each replay.")
         self.t += 1
         # python-double scalars rounded to float32 once, exactly where the reference wraps them in a
         # 0-d Tensor (dlgrad/nn/optim.py:64-69)

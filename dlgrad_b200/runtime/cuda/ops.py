@@ -428,6 +428,7 @@ def arange(shape: tuple) -> CDataPtr:
 def uniform(shape: tuple, low: float = 0.0, high: float = 1.0) -> CDataPtr:
     # initialisation only: generated on the host, one H2D (SURVEY §2a "init only")
     shim.init()
+    shim.no_capture("Tensor.uniform / dropout (host random numbers would be frozen into the graph)")
     vals = (low + (high - low) * _rng.random(prod_(shape), dtype=np.float32)).astype(np.float32)
     return transfer.upload_numpy(vals)
 

@@ -110,6 +110,9 @@ class _CompileOnlyLib:
     def dlg_graph_end(self): return ffi.cast("void *", 1)
     def dlg_graph_launch(self, g): return 0
     def dlg_graph_destroy(self, g): return None
+    def dlg_pool_begin(self): return 1
+    def dlg_pool_end(self): return 0
+    def dlg_pool_destroy(self, p): return 0
     def dlg_nccl_unique_id(self, out): return 0
     def dlg_nccl_init(self, r, w, i): return 0
     def dlg_nccl_allreduce_sum(self, p, n): return 0
@@ -135,6 +138,16 @@ def _load():
 
 lib = _load()
 _state = {"device": None}
+
+# set by dlgrad_b200/graph.py while a step is being captured into a CUDA graph: host round trips are illegal then
+# (the stream cannot be synchronised), and host data uploaded inside the step is staged in pinned memory the graph owns
+capture = {"on": False, "keep": None}
+
+
+def no_capture(what: str) -> None:
+    if capture["on"]:
+        raise RuntimeError(f"{what} inside a step that is being captured into a CUDA graph: the host cannot wait for "
+                           "the device there.  Pass per-step data as graph inputs and read results after the replay.")
 
 
 def last_error() -> str:
@@ -175,6 +188,7 @@ def device_available() -> bool:
 
 def synchronize() -> None:
     if is_initialized():
+        no_capture("synchronize()")
         check(lib.dlg_sync(), "dlg_sync")
 
 

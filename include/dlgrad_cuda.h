@@ -119,6 +119,13 @@ int   dlg_graph_begin(void);                 /* stream capture on the compute st
 void *dlg_graph_end(void);                   /* instantiated executable graph                */
 int   dlg_graph_launch(void *graph_exec);
 void  dlg_graph_destroy(void *graph_exec);
+/* memory pool of a captured step (dlgrad_b200/graph.py): every dlg_alloc between dlg_pool_begin and
+ * dlg_pool_end belongs to the pool; dlg_free of such a block — then or later — returns it to the pool, never to
+ * the global cache, so eager allocations cannot alias memory that replays of the graph write.
+ * dlg_pool_destroy (after the graph is destroyed) releases the pool's blocks. */
+int   dlg_pool_begin(void);                  /* pool id > 0, or -1                            */
+int   dlg_pool_end(void);
+int   dlg_pool_destroy(int pool);
 
 /* ---- data-parallel gradient exchange (no reference counterpart) ----------*/
 int   dlg_nccl_unique_id(char out[128]);

@@ -9,7 +9,8 @@
 
 These steps are launch- and host-bound on a B200: a step is a few hundred kernels of microseconds each,
 issued by a single Python thread.  Reported per config: steps/s with the batch resident in HBM (`value`), steps/s with
-host batches and the loss read back every step (`e2e`), kernel launches per step, and the same step on the CPU arm —
+host batches and the loss read back every step (`e2e`), kernel launches per step, the same with forward + backward
+replayed as a captured CUDA graph (`captured`, dlgrad_b200/graph.py), and the same step on the CPU arm —
 this package's autograd layer over the reference's own generated C kernels (oracle/_ref; the oracle restatement if
 that library is absent), single thread like the reference.  Synthetic MNIST-shaped data (no network for the real files).
 The GPU runs come first: installing the CPU arm registers a host runtime, which changes where default-device tensors live.
@@ -36,13 +37,12 @@ def make_mlp(dl, device):
     x = rng.random((128, 784), dtype=np.float32)
     y = rng.integers(0, 10, size=(128, 1)).astype(np.float32)
 
-    def step(xt, yt):
+    def fwd_bwd(xt, yt):
         opt.zero_grad()
         loss = mlp(xt).cross_entropy_loss(yt)
         loss.backward()
-        opt.step()
         return loss
-    return step, (x, y), lambda a: Tensor(a, device=device)
+    return [(fwd_bwd, opt)], (x, y), lambda a: Tensor(a, device=device)
 
 
 def make_gan(dl, device):
@@ -54,19 +54,20 @@ def make_gan(dl, device):
     real = (2.0 * rng.random((100, 784), dtype=np.float32) - 1.0).astype(np.float32)
     noise = (2.0 * rng.random((100, 128), dtype=np.float32) - 1.0).astype(np.float32)
 
-    def step(real_t, noise_t):
+    def d_phase(real_t, noise_t):
         fake = gan.generator(noise_t).detach()
         opt_d.zero_grad()
         d_loss = (gan.discriminator(real_t).bcewithlogitsloss(Tensor.full((100, 1), 1.0, device=device))
                   + gan.discriminator(fake).bcewithlogitsloss(Tensor.full((100, 1), 0.0, device=device))) / 2.0
         d_loss.backward()
-        opt_d.step()
+        return d_loss
+
+    def g_phase(real_t, noise_t):
         opt_g.zero_grad()
         g_loss = gan.discriminator(gan.generator(noise_t)).bcewithlogitsloss(Tensor.full((100, 1), 1.0, device=device))
         g_loss.backward()
-        opt_g.step()
         return g_loss
-    return step, (real, noise), lambda a: Tensor(a, device=device)
+    return [(d_phase, opt_d), (g_phase, opt_g)], (real, noise), lambda a: Tensor(a, device=device)
 
 
 def make_gpt(dl, device):
@@ -77,13 +78,12 @@ def make_gpt(dl, device):
     opt = nn.optim.Adam(params, lr=1e-4)
     x, y = models.gpt_batch(cfg, 16, np.random.default_rng(7))
 
-    def step(xt, yt):
+    def fwd_bwd(xt, yt):
         opt.zero_grad()
         _, loss = gpt(xt, yt)
         loss.backward()
-        opt.step()
         return loss
-    return step, (x, y), lambda a: Tensor(a, device=device)
+    return [(fwd_bwd, opt)], (x, y), lambda a: Tensor(a, device=device)
 
 
 CONFIGS = (("c1_mlp", "configs[0] examples/mnist_mlp.py MLP 784-64-10, batch 128, SGD", make_mlp, 200, 20),
@@ -91,10 +91,57 @@ CONFIGS = (("c1_mlp", "configs[0] examples/mnist_mlp.py MLP 784-64-10, batch 128
            ("c4_gpt", "configs[3] examples/gpt.py char-GPT L6 h4 C128 T128, batch 16, Adam", make_gpt, 50, 2))
 
 
+def eager_step(phases):
+    def step(*inputs):
+        for fwd_bwd, opt in phases:
+            loss = fwd_bwd(*inputs)
+            opt.step()
+        return loss
+    return step
+
+
+def graph_arm(make, steps: int) -> dict:
+    """Every phase (forward + backward) captured once and replayed as one CUDA graph launch; optimizer steps eager."""
+    import dlgrad_b200 as dl
+    from dlgrad_b200 import graph
+    from dlgrad_b200.runtime.cuda import profile, shim
+    phases, host, to_dev = make(dl, "cuda")
+    dev = tuple(to_dev(a) for a in host)
+    caps = [(graph.CapturedStep(fwd_bwd, *dev, params=opt.params), opt) for fwd_bwd, opt in phases]
+
+    def step(*arrays):
+        for i, (cap, opt) in enumerate(caps):
+            loss = cap(*arrays) if i == 0 else cap()          # later phases reuse the input buffers just filled
+            opt.step()
+        return loss
+    for _ in range(3):
+        loss = step()
+    _ = loss.numpy()
+    n0 = int(shim.lib.dlg_launch_count())
+    e0 = profile.Event().record()
+    for _ in range(steps):
+        loss = step()
+    e1 = profile.Event().record()
+    e1.sync()
+    ms = e1.ms_since(e0) / steps
+    eager_launches = (int(shim.lib.dlg_launch_count()) - n0) / steps
+    e0 = profile.Event().record()
+    for _ in range(steps):
+        last = float(step(*host).numpy())
+    e1 = profile.Event().record()
+    e1.sync()
+    ms_e2e = e1.ms_since(e0) / steps
+    for cap, _ in caps:
+        cap.close()
+    return {"value": 1000.0 / ms, "ms_per_step": ms, "e2e": 1000.0 / ms_e2e, "graph_launches_per_step": len(caps),
+            "eager_launches_per_step": eager_launches, "last_loss": last}
+
+
 def gpu_arm(make, steps: int) -> dict:
     import dlgrad_b200 as dl
     from dlgrad_b200.runtime.cuda import profile, shim
-    step, host, to_dev = make(dl, "cuda")
+    phases, host, to_dev = make(dl, "cuda")
+    step = eager_step(phases)
     dev = tuple(to_dev(a) for a in host)
     for _ in range(5):
         loss = step(*dev)
@@ -119,7 +166,8 @@ def gpu_arm(make, steps: int) -> dict:
 
 def cpu_arm(make, steps: int) -> dict:
     import dlgrad_b200 as dl
-    step, host, to_dev = make(dl, "cpu")
+    phases, host, to_dev = make(dl, "cpu")
+    step = eager_step(phases)
     step(*(to_dev(a.copy()) for a in host))
     t0 = time.perf_counter()
     for _ in range(steps):
@@ -132,6 +180,7 @@ def main() -> None:
     from dlgrad_b200.runtime.cuda import shim
     shim.init()
     gpu = {name: gpu_arm(make, n_gpu) for name, _, make, n_gpu, _ in CONFIGS}
+    captured = {name: graph_arm(make, n_gpu) for name, _, make, n_gpu, _ in CONFIGS}
     from oracle import backend
     backend.install()
     for name, what, make, n_gpu, n_cpu in CONFIGS:
@@ -148,7 +197,13 @@ def main() -> None:
             "cpu_baseline": {"value": cpu["value"], "unit": "steps/s", "cores": 1, "kind": bench.cpu_kind(),
                              "sample": f"{cpu['steps']} full steps, {cpu['ms_per_step']:.1f} ms each, on {bench.cpu_kind_text()}; "
                                        f"host has {os.cpu_count()} cores, the reference is single-threaded"},
-            "speedup_vs_cpu": g["e2e"] / cpu["value"],
+            "captured": {"value": captured[name]["value"], "ms_per_step": captured[name]["ms_per_step"],
+                         "e2e": captured[name]["e2e"], "unit": "steps/s",
+                         "graph_launches_per_step": captured[name]["graph_launches_per_step"],
+                         "eager_launches_per_step": captured[name]["eager_launches_per_step"],
+                         "what": "forward + backward of every phase replayed as one CUDA graph (dlgrad_b200/graph.py), "
+                                 "optimizer steps eager"},
+            "speedup_vs_cpu": max(g["e2e"], captured[name]["e2e"]) / cpu["value"],
         }), flush=True)
 
 

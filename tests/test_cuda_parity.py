@@ -13,7 +13,7 @@ import os
 import numpy as np
 import pytest
 
-from tests import cases, runner
+from tests import cases, models, runner
 from tests.conftest import check
 from tests.test_oracle_golden import compare_models, models_run
 
@@ -961,3 +961,85 @@ def test_constant_masks_are_computed_once_shared_and_copy_on_write():
           what="full() keeps the reference's int cast of the fill value")
     check((Tensor.ones((8, 8), device="cuda") * 3.0 + Tensor.full((8, 8), 2.0, device="cuda")).numpy(),
           np.full((8, 8), 5.0, dtype=np.float32), exact=True, what="arithmetic on constants")
+
+
+def test_captured_step_replays_bit_identically_to_eager():
+    """graph.CapturedStep records forward + backward of a step once and replays it as one CUDA graph launch.  Two
+    copies of each model — one stepped eagerly, one through the graph — must stay bit-identical over several steps
+    with different batches, with eager allocations in between (the capture's memory pool must not be handed out),
+    and host round trips inside a capture must raise."""
+    import dlgrad_b200 as dl
+    from dlgrad_b200 import Tensor, graph, nn
+    rng = np.random.default_rng(21)
+
+    # ---- MLP + SGD (configs[0]) ----
+    nets = [models.MLP(dl, "cuda", np.random.default_rng(3)) for _ in range(2)]
+    opts = [nn.optim.SGD(nn.utils.get_parameters(n), lr=1e-2) for n in nets]
+    batches = [(rng.random((128, 784), dtype=np.float32), rng.integers(0, 10, size=(128, 1)).astype(np.float32))
+               for _ in range(5)]
+
+    def mlp_fwd_bwd(net, opt):
+        def run(x, y):
+            opt.zero_grad()
+            loss = net(x).cross_entropy_loss(y)
+            loss.backward()
+            return loss
+        return run
+    x0, y0 = Tensor(batches[0][0].copy(), device="cuda"), Tensor(batches[0][1].copy(), device="cuda")
+    cap = graph.CapturedStep(mlp_fwd_bwd(nets[1], opts[1]), x0, y0)
+    for step, (x, y) in enumerate(batches):
+        loss_e = mlp_fwd_bwd(nets[0], opts[0])(Tensor(x.copy(), device="cuda"), Tensor(y.copy(), device="cuda"))
+        opts[0].step()
+        junk = [Tensor(rng.random((256, 784), dtype=np.float32), device="cuda") * 3.0 for _ in range(4)]   # eager traffic
+        loss_g = cap(x, y)
+        opts[1].step()
+        check(loss_g.numpy(), loss_e.numpy(), exact=True, what=f"MLP loss, replay {step}")
+        check(nets[1].l1.weight.numpy(), nets[0].l1.weight.numpy(), exact=True, what=f"MLP W1 after step {step}")
+        check(nets[1].l2.bias.numpy(), nets[0].l2.bias.numpy(), exact=True, what=f"MLP b2 after step {step}")
+        del junk
+    cap.close()
+
+    # ---- small GPT + Adam (the step builds its position indices from numpy inside the captured call) ----
+    cfg = models.GPTConfig(vocab_size=33, block_size=32, n_layer=2, n_head=2, n_embd=64, device="cuda")
+    gpts = [models.GPT(dl, cfg, np.random.default_rng(4)) for _ in range(2)]
+    params = [nn.utils.get_parameters(g) for g in gpts]
+    adams = [nn.optim.Adam(p, lr=1e-3) for p in params]
+    data = [models.gpt_batch(cfg, 4, rng) for _ in range(4)]
+
+    def gpt_fwd_bwd(net, opt):
+        def run(x, y):
+            opt.zero_grad()
+            _, loss = net(x, y)
+            loss.backward()
+            return loss
+        return run
+    cap = graph.CapturedStep(gpt_fwd_bwd(gpts[1], adams[1]), Tensor(data[0][0].copy(), device="cuda"),
+                             Tensor(data[0][1].copy(), device="cuda"))
+    for step, (x, y) in enumerate(data):
+        loss_e = gpt_fwd_bwd(gpts[0], adams[0])(Tensor(x.copy(), device="cuda"), Tensor(y.copy(), device="cuda"))
+        adams[0].step()
+        loss_g = cap(x, y)
+        adams[1].step()
+        check(loss_g.numpy(), loss_e.numpy(), exact=True, what=f"GPT loss, replay {step}")
+        for i in (0, len(params[0]) // 2, len(params[0]) - 1):
+            check(params[1][i].numpy(), params[0][i].numpy(), exact=True, what=f"GPT parameter {i} after step {step}")
+    cap.close()
+
+    # ---- what cannot be captured says so ----
+    w = Tensor(rng.random((8, 8), dtype=np.float32), device="cuda", requires_grad=True)
+    for bad in (lambda t: Tensor(np.float32(t.sum().numpy())),            # host read-back inside the step
+                lambda t: (nn.optim.Adam([w]).step(), t)[1]):             # Adam.step inside the step
+        with pytest.raises(RuntimeError):
+            graph.CapturedStep(_CaptureOnce(bad), Tensor(np.ones((8, 8), dtype=np.float32), device="cuda"), warmup=1)
+    check((w * 2.0).numpy(), w.numpy() * 2.0, exact=True, what="eager mode works again after a failed capture")
+
+
+class _CaptureOnce:
+    """Runs harmlessly during warm-up and the offending call only while capturing."""
+
+    def __init__(self, bad) -> None:
+        self.bad = bad
+
+    def __call__(self, t):
+        from dlgrad_b200.runtime.cuda import shim
+        return self.bad(t) if shim.capture["on"] else t
