@@ -1115,14 +1115,16 @@ def _flit(x: float) -> str:
 
 
 @cache
-def adam_step(numel: int, beta1: float, beta2: float, eps: float, aligned: bool = True) -> Kernel:
+def adam_step(numel: int, beta1: float, beta2: float, eps: float, aligned: bool = True,
+              scalars_in_memory: bool = False) -> Kernel:
     """One fused, in-place Adam update per parameter tensor: reads g, m, v, p and writes m, v, p
     (28 B/param) instead of the reference's ~14 elementwise dispatches with a fresh allocation
     each (dlgrad/nn/optim.py:59-70).  The float32 operation sequence per element is the
     reference's, op for op (no FMA contraction): m*b1 + g*(1-b1); v*b2 + (g*g)*(1-b2);
     m/(1-b1^t); v/(1-b2^t); p - (mh/(sqrt(vh)+eps))*lr.  f0 = 1-b1^t, f1 = 1-b2^t, f2 = lr,
     f3 = gradient scale (1.0 on one GPU — an exact no-op — or 1/world after a data-parallel sum).
-    p0 = param, p1 = grad, p2 = m, p3 = v."""
+    p0 = param, p1 = grad, p2 = m, p3 = v.  With `scalars_in_memory` f0..f2 come from out[0..2] (set_scalars): the
+    form recorded into a captured graph."""
     V = 4 if (aligned and numel % 4 == 0) else 1
     nv = numel // V
     VT = "float4" if V == 4 else "float"
@@ -1143,6 +1145,7 @@ def adam_step(numel: int, beta1: float, beta2: float, eps: float, aligned: bool 
 extern "C" __global__ void __launch_bounds__(256) {KNAME}{SIG_ALIAS} {{
     const unsigned i = blockIdx.x * 256u + threadIdx.x;
     if (i >= {nv}u) return;
+    {"f0 = out[0]; f1 = out[1]; f2 = out[2];" if scalars_in_memory else ""}
     {VT} p = reinterpret_cast<{VT}*>(p0)[i];
     const {VT} g = reinterpret_cast<const {VT}*>(p1)[i];
     {VT} m = reinterpret_cast<{VT}*>(p2)[i];
@@ -1227,7 +1230,18 @@ extern "C" __global__ void __launch_bounds__({BLOCK}) {KNAME}{SIG} {{
 
 
 @cache
-def adam_multi(sizes: tuple, beta1: float, beta2: float, eps: float) -> Kernel:
+def set_scalars() -> Kernel:
+    """out[0..3] = f0..f3: launch arguments parked in device memory, for kernels inside a captured graph whose
+    per-step scalars (Adam's bias corrections) must change between replays."""
+    src = f"""
+extern "C" __global__ void __launch_bounds__(32) {KNAME}{SIG_ALIAS} {{
+    if (threadIdx.x == 0) {{ out[0] = f0; out[1] = f1; out[2] = f2; out[3] = f3; }}
+}}
+"""
+    return Kernel("set_scalars", src, (1, 1, 1), (32, 1, 1), 0, 0)
+
+
+def adam_multi(sizes: tuple, beta1: float, beta2: float, eps: float, scalars_in_memory: bool = False) -> Kernel:
     """The Adam update of EVERY parameter tensor in one launch (multi-tensor apply).  p0 is a device table of
     4 addresses per tensor (param, grad, m, v); the block -> tensor map is a literal prefix array, found by
     binary search.  Same per-element arithmetic as adam_step.  All tensors must be 16-byte aligned with
@@ -1254,6 +1268,7 @@ __device__ const unsigned blk_start[{len(starts)}] = {{{", ".join(str(s) + "u" f
 __device__ const unsigned vec_count[{len(sizes)}] = {{{", ".join(str(n // 4) + "u" for n in sizes)}}};
 extern "C" __global__ void __launch_bounds__(256) {KNAME}{SIG_ALIAS} {{
     const unsigned long long* tab = reinterpret_cast<const unsigned long long*>(p0);
+    {"f0 = p1[0]; f1 = p1[1]; f2 = p1[2];      // bias corrections and learning rate of THIS step (set_scalars), not of the captured one" if scalars_in_memory else ""}
     unsigned lo = 0, hi = {len(sizes)}u;            // tensor t with blk_start[t] <= blockIdx.x < blk_start[t+1]
     while (hi - lo > 1u) {{ const unsigned mid = (lo + hi) >> 1; if (blk_start[mid] <= blockIdx.x) lo = mid; else hi = mid; }}
     const unsigned t = lo, nv = vec_count[t];

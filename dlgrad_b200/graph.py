@@ -5,10 +5,9 @@ No reference counterpart: dlgrad issues every kernel from Python, and so does th
 workloads (MLP, GAN, char-GPT: SURVEY §8d "launch/host-bound").  A steady-state step launches the same kernels on
 the same shapes every time, so it can be recorded once and replayed:
 
-    fwd_bwd = graph.CapturedStep(lambda x, y: loss_and_backward(model, opt, x, y), x0, y0)
+    step = graph.CapturedStep(lambda x, y: train_step(model, opt, x, y), x0, y0, params=opt.params)
     for x, y in batches:
-        loss = fwd_bwd(x, y)          # copies x, y into the captured input buffers, launches the graph
-        opt.step()                    # eager: Adam's bias corrections change every step
+        loss = step(x, y)             # copies x, y into the captured input buffers, launches the graph
 
 How it stays correct
   * memory: every allocation made while capturing comes from a private pool of the caching allocator (dlg_pool_*):
@@ -19,13 +18,16 @@ How it stays correct
   * host data created inside the step (examples/gpt.py builds its position indices from numpy every call) is frozen:
     staged once in pinned memory owned by the graph and re-copied by every replay.  Anything that must differ between
     steps has to be a graph input.
-  * host round trips (numpy(), synchronize, host random numbers, Adam.step) raise inside a capture instead of
-    silently recording something else.
+  * host round trips (numpy(), synchronize, host random numbers) raise inside a capture instead of silently
+    recording something else.
+  * optimizer steps may be part of the captured call.  SGD's launch arguments never change.  Adam's bias corrections
+    1 - beta^t do: inside a capture Adam records its multi-tensor kernel in the form that reads them from device
+    memory, and a hook advances `t` and rewrites those scalars (one tiny eager launch) before every replay.
+  * a capture records, it does not execute: the warm-up calls before it are real steps, the captured call is not.
   * deferred buffers (Buffer._pending) still alive when the captured call returns are materialised inside the graph.
   * Python-side effects are not replayed.  The one that matters is which Tensor each parameter's `.grad` names: pass
     `params=` and every replay re-binds `.grad` to the gradient Tensors of the captured call (two captured phases that
     both touch the same parameters — a GAN's discriminator and generator steps — would otherwise read each other's).
-  * the warm-up calls before the capture run the step for real.
 """
 from __future__ import annotations
 
@@ -53,7 +55,8 @@ class CapturedStep:
         if self.pool <= 0:
             raise RuntimeError("dlg_pool_begin failed: " + shim.last_error())
         self.keep: list = []
-        shim.capture["on"], shim.capture["keep"] = True, self.keep
+        self.hooks: list = []                      # run before every replay (Adam: advance t, refresh its device scalars)
+        shim.capture["on"], shim.capture["keep"], shim.capture["hooks"] = True, self.keep, self.hooks
         self.exec = shim.NULL
         try:
             shim.check(lib.dlg_graph_begin(), "dlg_graph_begin")
@@ -65,7 +68,7 @@ class CapturedStep:
             finally:
                 self.exec = lib.dlg_graph_end()
         finally:
-            shim.capture["on"], shim.capture["keep"] = False, None
+            shim.capture["on"], shim.capture["keep"], shim.capture["hooks"] = False, None, None
             lib.dlg_pool_end()
         if self.exec == shim.NULL:
             raise RuntimeError("capturing the step failed: " + shim.last_error())
@@ -92,6 +95,8 @@ class CapturedStep:
             if a.size != t.numel:
                 raise ValueError(f"input of {a.size} elements for a captured buffer of shape {t.shape}")
             shim.check(shim.lib.dlg_h2d(t.data.ptr, shim.ffi.from_buffer("float *", a), a.nbytes), "dlg_h2d")
+        for hook in self.hooks:
+            hook()
         shim.check(shim.lib.dlg_graph_launch(self.exec), "dlg_graph_launch")
         for p, g in self.grads:
             p.grad = g

@@ -80,12 +80,12 @@ class Adam(Optimizer):
         self.grad_scale = 1.0
         self.m = {id(p): Tensor.zeros_like(p) for p in params}
         self.v = {id(p): Tensor.zeros_like(p) for p in params}
+        self._scal = None         # device float[4] holding 1 - beta1^t, 1 - beta2^t, lr for steps inside a captured graph
 
     def step(self) -> None:
         from dlgrad_b200.runtime.cuda import shim
         if shim.capture["on"]:
-            raise RuntimeError("Adam.step() inside a captured step: its bias corrections 1 - beta^t change every step and "
-                               "would be frozen into the graph.  Capture forward + backward, call step() after each replay.")
+            return self._captured_step()
         self.t += 1
         # python-double scalars rounded to float32 once, exactly where the reference wraps them in a
         # 0-d Tensor (dlgrad/nn/optim.py:64-69)
@@ -97,6 +97,11 @@ class Adam(Optimizer):
         live = [p for p in self.params if p.grad is not None]
         if live:
             dev = self._device_for(*[p.data for p in live], *[p.grad.data for p in live])
+            if self._scal is None and dev is Device.CUDA:
+                # allocated by an EAGER step on purpose: a block taken during a capture comes from the capture's pool,
+                # where the graph's own kernels may write (graph.CapturedStep always runs a warm-up step first)
+                from dlgrad_b200.runtime.cuda import shim as _shim
+                self._scal = _shim.alloc(16)
             if dispatcher.has(CustomOps.ADAM_MULTI, dev):
                 done = dispatcher.dispatch(
                     op=CustomOps.ADAM_MULTI, device=dev, params=[p.data for p in live],
@@ -113,3 +118,35 @@ class Adam(Optimizer):
             dispatcher.dispatch(op=CustomOps.ADAM_STEP, device=dev, param=p.data, grad=p.grad.data,
                                 m=m.data, v=v.data, beta1=b1, beta2=b2, eps=eps, bc1=bc1, bc2=bc2, lr=lr,
                                 grad_scale=self.grad_scale)
+
+    # ------------------------------------------------------------------ inside a captured graph (dlgrad_b200/graph.py)
+    def _scalars(self) -> tuple[float, float, float]:
+        return (float(_f32(1.0 - self.beta1 ** self.t)), float(_f32(1.0 - self.beta2 ** self.t)), float(_f32(self.lr)))
+
+    def _tick(self) -> None:
+        """Before every replay: the step count advances on the host, the new scalars go to device memory."""
+        from dlgrad_b200.runtime.cuda import ops as cuda_ops
+        self.t += 1
+        cuda_ops.adam_scalars(self._scal, *self._scalars())
+
+    def _captured_step(self) -> None:
+        """Record the multi-tensor kernel in the form that reads 1 - beta^t and lr from device memory; the capture
+        itself executes nothing, so `t` does not advance here — `_tick` runs before each replay."""
+        from dlgrad_b200.runtime.cuda import shim
+        self._before_inplace([t.data for t in self.m.values()] + [t.data for t in self.v.values()])
+        live = [p for p in self.params if p.grad is not None]
+        if not live:
+            return
+        if self._scal is None:
+            raise RuntimeError("Adam.step() inside a captured step needs one eager step first (graph.CapturedStep's "
+                               "warm-up provides it)")
+        kw = dict(beta1=self.beta1, beta2=self.beta2, eps=self.eps, bc1=0.0, bc2=0.0, lr=0.0, grad_scale=self.grad_scale,
+                  scalars=self._scal)
+        done = dispatcher.dispatch(
+            op=CustomOps.ADAM_MULTI, device=Device.CUDA, params=[p.data for p in live], grads=[p.grad.data for p in live],
+            ms=[self.m[id(p)].data for p in live], vs=[self.v[id(p)].data for p in live], **kw)
+        if not done:                               # some tensor is not float4-shaped: one launch per tensor, like eager
+            for p in live:
+                dispatcher.dispatch(op=CustomOps.ADAM_STEP, device=Device.CUDA, param=p.data, grad=p.grad.data,
+                                    m=self.m[id(p)].data, v=self.v[id(p)].data, **kw)
+        shim.capture["hooks"].append(self._tick)

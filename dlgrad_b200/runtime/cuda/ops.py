@@ -732,13 +732,14 @@ def embedding(x: Buffer, idx: Buffer, out_numel: int, backward: bool = False,
 # ------------------------------------------------------------------------------------------------
 @dispatcher.register(CustomOps.ADAM_STEP, CUDA)
 def adam_step(param: Buffer, grad: Buffer, m: Buffer, v: Buffer, beta1: float, beta2: float,
-              eps: float, bc1: float, bc2: float, lr: float, grad_scale: float = 1.0) -> None:
+              eps: float, bc1: float, bc2: float, lr: float, grad_scale: float = 1.0, scalars=None) -> None:
     ok = param.aligned and grad.aligned and m.aligned and v.aligned
-    key = ("adam", param.metadata.numel, beta1, beta2, eps, ok)
+    key = ("adam", param.metadata.numel, beta1, beta2, eps, ok, scalars is not None)
     plan = _plans.get(key)
     if plan is None:
-        plan = _plans[key] = Plan(ck.adam_step(param.metadata.numel, beta1, beta2, eps, ok))
-    plan.run_into(NULL, _dev_ptr(param), _dev_ptr(grad), _dev_ptr(m), _dev_ptr(v), bc1, bc2, lr, grad_scale)
+        plan = _plans[key] = Plan(ck.adam_step(param.metadata.numel, beta1, beta2, eps, ok, scalars is not None))
+    plan.run_into(NULL if scalars is None else scalars, _dev_ptr(param), _dev_ptr(grad), _dev_ptr(m), _dev_ptr(v),
+                  bc1, bc2, lr, grad_scale)
 
 
 _adam_tables: dict = {}
@@ -746,20 +747,24 @@ _adam_tables: dict = {}
 
 @dispatcher.register(CustomOps.ADAM_MULTI, CUDA)
 def adam_multi(params: list, grads: list, ms: list, vs: list, beta1: float, beta2: float, eps: float,
-               bc1: float, bc2: float, lr: float, grad_scale: float = 1.0) -> bool:
+               bc1: float, bc2: float, lr: float, grad_scale: float = 1.0, scalars=None) -> bool:
     """One launch for all parameter tensors (codegen adam_multi).  The address table (4 pointers per tensor)
     is staged in pinned host memory and copied asynchronously ahead of the kernel on the compute stream; two
     staging buffers alternate so a table is never rewritten while its copy may still be in flight.  Returns
-    False (nothing done) when a tensor does not qualify for the 128-bit path."""
+    False (nothing done) when a tensor does not qualify for the 128-bit path.
+
+    `scalars` (a device float[4], see adam_scalars): the kernel reads bc1, bc2 and lr from it instead of its launch
+    arguments — the form recorded into a captured graph, whose staging table is private to that capture."""
     bufs = list(params) + list(grads) + list(ms) + list(vs)
     if not all(b.aligned and b.metadata.numel % 4 == 0 for b in bufs):
         return False
     sizes = tuple(p.metadata.numel for p in params)
-    key = ("adam_multi", sizes, beta1, beta2, eps)
+    token = id(shim.capture["keep"]) if shim.capture["on"] else 0
+    key = ("adam_multi", sizes, beta1, beta2, eps, scalars is not None, token)
     ent = _adam_tables.get(key)
     if ent is None:
         n = len(sizes)
-        plan = Plan(ck.adam_multi(sizes, beta1, beta2, eps))
+        plan = Plan(ck.adam_multi(sizes, beta1, beta2, eps, scalars is not None))
         host = [lib.dlg_host_alloc(32 * n), lib.dlg_host_alloc(32 * n)]
         if host[0] == NULL or host[1] == NULL:
             raise MemoryError("pinned staging allocation failed: " + shim.last_error())
@@ -776,8 +781,19 @@ def adam_multi(params: list, grads: list, ms: list, vs: list, beta1: float, beta
         tab[i + 3] = addr(_dev_ptr(v))
         i += 4
     shim.check(lib.dlg_h2d_async(ent["dev"], ent["host"][ent["flip"]], 32 * len(sizes)), "dlg_h2d_async")
-    ent["plan"].run_into(NULL, ent["dev"], NULL, NULL, NULL, bc1, bc2, lr, grad_scale)
+    ent["plan"].run_into(NULL, ent["dev"], NULL if scalars is None else scalars, NULL, NULL, bc1, bc2, lr, grad_scale)
     return True
+
+
+def adam_scalars(dst, bc1: float, bc2: float, lr: float):
+    """Park this step's bias corrections and learning rate in device memory (`dst`, or a fresh float[4])."""
+    plan = _plans.get("set_scalars")
+    if plan is None:
+        plan = _plans["set_scalars"] = Plan(ck.set_scalars())
+    if dst is None:
+        dst = shim.alloc(16)
+    plan.run_into(dst, NULL, NULL, NULL, NULL, bc1, bc2, lr, 0.0)
+    return dst
 
 
 @dispatcher.register(CustomOps.SGD_STEP, CUDA)

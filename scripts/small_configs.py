@@ -107,12 +107,17 @@ def graph_arm(make, steps: int) -> dict:
     from dlgrad_b200.runtime.cuda import profile, shim
     phases, host, to_dev = make(dl, "cuda")
     dev = tuple(to_dev(a) for a in host)
-    caps = [(graph.CapturedStep(fwd_bwd, *dev, params=opt.params), opt) for fwd_bwd, opt in phases]
+    def whole(fwd_bwd, opt):             # the optimizer step is part of the graph (Adam reads 1 - beta^t from device memory)
+        def run(*inputs):
+            loss = fwd_bwd(*inputs)
+            opt.step()
+            return loss
+        return run
+    caps = [graph.CapturedStep(whole(fwd_bwd, opt), *dev, params=opt.params) for fwd_bwd, opt in phases]
 
     def step(*arrays):
-        for i, (cap, opt) in enumerate(caps):
+        for i, cap in enumerate(caps):
             loss = cap(*arrays) if i == 0 else cap()          # later phases reuse the input buffers just filled
-            opt.step()
         return loss
     for _ in range(3):
         loss = step()
@@ -131,7 +136,7 @@ def graph_arm(make, steps: int) -> dict:
     e1 = profile.Event().record()
     e1.sync()
     ms_e2e = e1.ms_since(e0) / steps
-    for cap, _ in caps:
+    for cap in caps:
         cap.close()
     return {"value": 1000.0 / ms, "ms_per_step": ms, "e2e": 1000.0 / ms_e2e, "graph_launches_per_step": len(caps),
             "eager_launches_per_step": eager_launches, "last_loss": last}
@@ -202,7 +207,8 @@ def main() -> None:
                          "graph_launches_per_step": captured[name]["graph_launches_per_step"],
                          "eager_launches_per_step": captured[name]["eager_launches_per_step"],
                          "what": "forward + backward of every phase replayed as one CUDA graph (dlgrad_b200/graph.py), "
-                                 "optimizer steps eager"},
+                                 "optimizer step included (Adam reads its bias corrections from device memory, "
+                                 "refreshed by one tiny eager launch per replay)"},
             "speedup_vs_cpu": max(g["e2e"], captured[name]["e2e"]) / cpu["value"],
         }), flush=True)
 

@@ -999,6 +999,29 @@ def test_captured_step_replays_bit_identically_to_eager():
         del junk
     cap.close()
 
+    # ---- the whole step in the graph: SGD's launch arguments do not change from step to step ----
+    nets = [models.MLP(dl, "cuda", np.random.default_rng(8)) for _ in range(2)]
+    opts = [nn.optim.SGD(nn.utils.get_parameters(n), lr=1e-2) for n in nets]
+
+    def mlp_step(net, opt):
+        inner = mlp_fwd_bwd(net, opt)
+
+        def run(x, y):
+            loss = inner(x, y)
+            opt.step()
+            return loss
+        return run
+    cap = graph.CapturedStep(mlp_step(nets[1], opts[1]), Tensor(batches[0][0].copy(), device="cuda"),
+                             Tensor(batches[0][1].copy(), device="cuda"), warmup=1)
+    for _ in range(1):                                   # the warm-up call was a real step on batch 0 (a capture only records)
+        mlp_step(nets[0], opts[0])(Tensor(batches[0][0].copy(), device="cuda"), Tensor(batches[0][1].copy(), device="cuda"))
+    for step, (x, y) in enumerate(batches[1:]):
+        loss_e = mlp_step(nets[0], opts[0])(Tensor(x.copy(), device="cuda"), Tensor(y.copy(), device="cuda"))
+        loss_g = cap(x, y)
+        check(loss_g.numpy(), loss_e.numpy(), exact=True, what=f"MLP loss, whole-step replay {step}")
+        check(nets[1].l1.weight.numpy(), nets[0].l1.weight.numpy(), exact=True, what=f"MLP W1, whole-step replay {step}")
+    cap.close()
+
     # ---- small GPT + Adam (the step builds its position indices from numpy inside the captured call) ----
     cfg = models.GPTConfig(vocab_size=33, block_size=32, n_layer=2, n_head=2, n_embd=64, device="cuda")
     gpts = [models.GPT(dl, cfg, np.random.default_rng(4)) for _ in range(2)]
@@ -1025,10 +1048,59 @@ def test_captured_step_replays_bit_identically_to_eager():
             check(params[1][i].numpy(), params[0][i].numpy(), exact=True, what=f"GPT parameter {i} after step {step}")
     cap.close()
 
+    # ---- Adam inside the graph: 1 - beta^t and lr live in device memory, a hook refreshes them before each replay ----
+    gpts = [models.GPT(dl, cfg, np.random.default_rng(6)) for _ in range(2)]
+    params = [nn.utils.get_parameters(g) for g in gpts]
+    adams = [nn.optim.Adam(p, lr=1e-3) for p in params]
+
+    def gpt_step(net, opt):
+        inner = gpt_fwd_bwd(net, opt)
+
+        def run(x, y):
+            loss = inner(x, y)
+            opt.step()
+            return loss
+        return run
+    cap = graph.CapturedStep(gpt_step(gpts[1], adams[1]), Tensor(data[0][0].copy(), device="cuda"),
+                             Tensor(data[0][1].copy(), device="cuda"), warmup=1, params=params[1])
+    gpt_step(gpts[0], adams[0])(Tensor(data[0][0].copy(), device="cuda"), Tensor(data[0][1].copy(), device="cuda"))
+    for step, (x, y) in enumerate(data[1:] + data[:2]):
+        loss_e = gpt_step(gpts[0], adams[0])(Tensor(x.copy(), device="cuda"), Tensor(y.copy(), device="cuda"))
+        loss_g = cap(x, y)
+        check(loss_g.numpy(), loss_e.numpy(), exact=True, what=f"GPT loss, whole-step replay {step}")
+        for i in (0, len(params[0]) // 2, len(params[0]) - 1):
+            check(params[1][i].numpy(), params[0][i].numpy(), exact=True, what=f"GPT parameter {i}, whole-step replay {step}")
+    assert adams[1].t == adams[0].t
+    cap.close()
+
+    # ---- Adam over tensors that are not float4-shaped (a (1, 1) bias): per-tensor kernels inside the graph ----
+    pairs = [models.GANPair(dl, "cuda", np.random.default_rng(9), widths_g=(4, 8), widths_d=(16, 8, 1)) for _ in range(2)]
+    dparams = [nn.utils.get_parameters(p.d_layers) for p in pairs]
+    dopts = [nn.optim.Adam(p, lr=5e-4, betas=(0.5, 0.999)) for p in dparams]
+    reals = [(2.0 * rng.random((10, 16), dtype=np.float32) - 1.0).astype(np.float32) for _ in range(4)]
+
+    def d_step(pair, opt):
+        def run(real):
+            opt.zero_grad()
+            loss = pair.discriminator(real).bcewithlogitsloss(Tensor.full((10, 1), 1.0, device="cuda"))
+            loss.backward()
+            opt.step()
+            return loss
+        return run
+    cap = graph.CapturedStep(d_step(pairs[1], dopts[1]), Tensor(reals[0].copy(), device="cuda"), warmup=1, params=dparams[1])
+    d_step(pairs[0], dopts[0])(Tensor(reals[0].copy(), device="cuda"))
+    for step, r in enumerate(reals[1:]):
+        loss_e = d_step(pairs[0], dopts[0])(Tensor(r.copy(), device="cuda"))
+        loss_g = cap(r)
+        check(loss_g.numpy(), loss_e.numpy(), exact=True, what=f"discriminator loss, whole-step replay {step}")
+        for i, (a, b) in enumerate(zip(dparams[0], dparams[1])):
+            check(b.numpy(), a.numpy(), exact=True, what=f"discriminator parameter {i}, whole-step replay {step}")
+    cap.close()
+
     # ---- what cannot be captured says so ----
     w = Tensor(rng.random((8, 8), dtype=np.float32), device="cuda", requires_grad=True)
     for bad in (lambda t: Tensor(np.float32(t.sum().numpy())),            # host read-back inside the step
-                lambda t: (nn.optim.Adam([w]).step(), t)[1]):             # Adam.step inside the step
+                lambda t: t.dropout(0.5)):                                # host random numbers inside the step
         with pytest.raises(RuntimeError):
             graph.CapturedStep(_CaptureOnce(bad), Tensor(np.ones((8, 8), dtype=np.float32), device="cuda"), warmup=1)
     check((w * 2.0).numpy(), w.numpy() * 2.0, exact=True, what="eager mode works again after a failed capture")
