@@ -1230,6 +1230,59 @@ extern "C" __global__ void __launch_bounds__({BLOCK}) {KNAME}{SIG} {{
 
 
 @cache
+def uniform_philox(numel: int, base_in_memory: bool = False) -> Kernel:
+    """out[i] = f0 + (f1 - f0) * u_i, u_i in [0, 1) from Philox4x32-10 (Salmon et al., SC'11; the counter-based generator
+    of cuRAND / Random123), replacing the reference's host PCG32 reseeded from /dev/random on every call
+    (dlgrad/codegen/cpu_kernel.py:774-874).  Thread t encrypts the counter
+    (t, 0, call_lo, call_hi) under the 64-bit key in p0[0..1] and emits elements 4t .. 4t+3 as (x >> 8) * 2^-24.
+    The call number — distinct for every uniform() — is f2 + 2^24 * f3 (two exact 24-bit integers in floats); with
+    `base_in_memory` (the form recorded into a captured graph) p0[2] is added to it, so that replays, which cannot
+    change launch arguments, still draw fresh numbers: a hook rewrites p0[2] before every replay (set_call_base)."""
+    nthreads = _cdiv(numel, 4)
+    src = f"""
+__device__ __forceinline__ void philox_round(unsigned& c0, unsigned& c1, unsigned& c2, unsigned& c3, unsigned k0, unsigned k1) {{
+    const unsigned hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const unsigned hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    c0 = hi1 ^ c1 ^ k0; c1 = lo1; c2 = hi0 ^ c3 ^ k1; c3 = lo0;
+}}
+extern "C" __global__ void __launch_bounds__(256) {KNAME}{SIG_ALIAS} {{
+    const unsigned t = blockIdx.x * 256u + threadIdx.x;
+    if (t >= {nthreads}u) return;
+    const unsigned* state = reinterpret_cast<const unsigned*>(p0);
+    unsigned k0 = state[0], k1 = state[1];
+    unsigned long long call = (unsigned long long)f2 + ((unsigned long long)f3 << 24);
+    {"call += state[2];" if base_in_memory else ""}
+    unsigned c0 = t, c1 = 0u, c2 = (unsigned)call, c3 = (unsigned)(call >> 32);
+    #pragma unroll
+    for (int r = 0; r < 10; ++r) {{
+        philox_round(c0, c1, c2, c3, k0, k1);
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }}
+    const float span = __fsub_rn(f1, f0);
+    const float u[4] = {{ (float)(c0 >> 8) * 5.9604644775390625e-08f, (float)(c1 >> 8) * 5.9604644775390625e-08f,
+                         (float)(c2 >> 8) * 5.9604644775390625e-08f, (float)(c3 >> 8) * 5.9604644775390625e-08f }};
+    #pragma unroll
+    for (unsigned j = 0; j < 4u; ++j) {{
+        const unsigned i = 4u * t + j;
+        if (i < {numel}u) out[i] = __fadd_rn(f0, __fmul_rn(span, u[j]));
+    }}
+}}
+"""
+    return Kernel("uniform_philox", src, (_cdiv(nthreads, 256), 1, 1), (256, 1, 1), 0, numel)
+
+
+@cache
+def set_call_base() -> Kernel:
+    """word 2 of the RNG state at `out` = f0 + 2^24 * f1: the call number the next replay of a captured graph starts from."""
+    src = f"""
+extern "C" __global__ void __launch_bounds__(32) {KNAME}{SIG_ALIAS} {{
+    if (threadIdx.x == 0) reinterpret_cast<unsigned*>(out)[2] = (unsigned)f0 + ((unsigned)f1 << 24);
+}}
+"""
+    return Kernel("set_call_base", src, (1, 1, 1), (32, 1, 1), 0, 0)
+
+
+@cache
 def set_scalars() -> Kernel:
     """out[0..3] = f0..f3: launch arguments parked in device memory, for kernels inside a captured graph whose
     per-step scalars (Adam's bias corrections) must change between replays."""

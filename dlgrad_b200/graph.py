@@ -18,8 +18,9 @@ How it stays correct
   * host data created inside the step (examples/gpt.py builds its position indices from numpy every call) is frozen:
     staged once in pinned memory owned by the graph and re-copied by every replay.  Anything that must differ between
     steps has to be a graph input.
-  * host round trips (numpy(), synchronize, host random numbers) raise inside a capture instead of silently
-    recording something else.
+  * host round trips (numpy(), synchronize) raise inside a capture instead of silently recording something else.
+  * random numbers (dropout) come from a counter-based device generator; inside a capture the counter base lives in
+    device memory and a hook advances it before every replay, so every replay draws fresh masks.
   * optimizer steps may be part of the captured call.  SGD's launch arguments never change.  Adam's bias corrections
     1 - beta^t do: inside a capture Adam records its multi-tensor kernel in the form that reads them from device
     memory, and a hook advances `t` and rewrites those scalars (one tiny eager launch) before every replay.
@@ -57,6 +58,7 @@ class CapturedStep:
         self.keep: list = []
         self.hooks: list = []                      # run before every replay (Adam: advance t, refresh its device scalars)
         shim.capture["on"], shim.capture["keep"], shim.capture["hooks"] = True, self.keep, self.hooks
+        shim.capture["rng"] = {"n": 0, "hooked": False}   # random draws recorded in this step (runtime/cuda/ops.uniform)
         self.exec = shim.NULL
         try:
             shim.check(lib.dlg_graph_begin(), "dlg_graph_begin")
@@ -68,7 +70,7 @@ class CapturedStep:
             finally:
                 self.exec = lib.dlg_graph_end()
         finally:
-            shim.capture["on"], shim.capture["keep"], shim.capture["hooks"] = False, None, None
+            shim.capture["on"], shim.capture["keep"], shim.capture["hooks"], shim.capture["rng"] = False, None, None, None
             lib.dlg_pool_end()
         if self.exec == shim.NULL:
             raise RuntimeError("capturing the step failed: " + shim.last_error())

@@ -13,6 +13,7 @@ Python per dispatch there.
 from __future__ import annotations
 
 import builtins
+import os
 
 import numpy as np
 
@@ -38,15 +39,49 @@ ffi, lib, NULL = shim.ffi, shim.lib, shim.NULL
 _own = shim.own
 CUDA = Device.CUDA
 _plans: dict = {}
-_rng = np.random.default_rng()
+_rng_state = {"dev": None, "seed": None, "calls": 0}     # Philox key (device float[4] block) and the next call number
 builtins_max, builtins_min = builtins.max, builtins.min
 
 
 def manual_seed(seed: int) -> None:
     """Seed Tensor.uniform/rand on this backend (the reference reseeds from /dev/random on every
     call, dlgrad/codegen/cpu_kernel.py:774-874, and cannot be made reproducible)."""
-    global _rng
-    _rng = np.random.default_rng(seed)
+    st = _rng_state
+    st["seed"], st["calls"] = int(seed) & 0xFFFFFFFFFFFFFFFF, 0
+    if st["dev"] is not None:
+        _write_rng_key()
+
+
+def _write_rng_key() -> None:
+    st = _rng_state
+    words = np.array([st["seed"] & 0xFFFFFFFF, st["seed"] >> 32, 0, 0], dtype=np.uint32)
+    transfer.write_bytes(st["dev"], words.tobytes())
+
+
+def _rng_buffer():
+    """Device block [key lo, key hi, call base of the next replay, -].  Set up by an eager call: a block taken inside a
+    capture would come from the capture's pool, where the graph's own kernels write."""
+    st = _rng_state
+    if st["dev"] is None:
+        shim.no_capture("the first random draw of the process (graph.CapturedStep's warm-up step does it eagerly)")
+        if st["seed"] is None:
+            st["seed"] = int.from_bytes(os.urandom(8), "little")
+        st["dev"] = shim.alloc(16)
+        _write_rng_key()
+    return st["dev"]
+
+
+def _rng_replay_hook(info: dict):
+    """Before a replay: reserve the call numbers the graph's draws will use and tell the device where they start."""
+    def tick() -> None:
+        st = _rng_state
+        base = st["calls"] & 0xFFFFFFFF
+        st["calls"] += info["n"]
+        plan = _plans.get("set_call_base")
+        if plan is None:
+            plan = _plans["set_call_base"] = Plan(ck.set_call_base())
+        plan.run_into(st["dev"], NULL, NULL, NULL, NULL, float(base & 0xFFFFFF), float(base >> 24))
+    return tick
 
 
 class Plan:
@@ -426,11 +461,27 @@ def arange(shape: tuple) -> CDataPtr:
 
 @dispatcher.register(BufferOps.UNIFORM, CUDA)
 def uniform(shape: tuple, low: float = 0.0, high: float = 1.0) -> CDataPtr:
-    # initialisation only: generated on the host, one H2D (SURVEY §2a "init only")
+    """U[low, high) on the device: Philox4x32-10 keyed by manual_seed (codegen uniform_philox).  Every call draws from
+    its own counter range, so weight initialisation and dropout masks never repeat; inside a captured graph the call
+    number comes from device memory and a pre-replay hook advances it."""
     shim.init()
-    shim.no_capture("Tensor.uniform / dropout (host random numbers would be frozen into the graph)")
-    vals = (low + (high - low) * _rng.random(prod_(shape), dtype=np.float32)).astype(np.float32)
-    return transfer.upload_numpy(vals)
+    n = prod_(shape)
+    state = _rng_buffer()
+    cap = shim.capture["rng"] if shim.capture["on"] else None
+    key = ("uniform_philox", n, cap is not None)
+    plan = _plans.get(key)
+    if plan is None:
+        plan = _plans[key] = Plan(ck.uniform_philox(n, cap is not None))
+    if cap is not None:
+        call = cap["n"]                                  # ordinal of this draw inside the captured step
+        cap["n"] += 1
+        if not cap["hooked"]:
+            cap["hooked"] = True
+            shim.capture["hooks"].append(_rng_replay_hook(cap))
+    else:
+        call = _rng_state["calls"]
+        _rng_state["calls"] += 1
+    return plan.run(state, NULL, NULL, NULL, float(low), float(high), float(call & 0xFFFFFF), float((call >> 24) & 0xFFFFFF))
 
 
 # ------------------------------------------------------------------------------------------------

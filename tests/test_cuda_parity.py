@@ -1099,8 +1099,7 @@ def test_captured_step_replays_bit_identically_to_eager():
 
     # ---- what cannot be captured says so ----
     w = Tensor(rng.random((8, 8), dtype=np.float32), device="cuda", requires_grad=True)
-    for bad in (lambda t: Tensor(np.float32(t.sum().numpy())),            # host read-back inside the step
-                lambda t: t.dropout(0.5)):                                # host random numbers inside the step
+    for bad in (lambda t: Tensor(np.float32(t.sum().numpy())),):          # host read-back inside the step
         with pytest.raises(RuntimeError):
             graph.CapturedStep(_CaptureOnce(bad), Tensor(np.ones((8, 8), dtype=np.float32), device="cuda"), warmup=1)
     check((w * 2.0).numpy(), w.numpy() * 2.0, exact=True, what="eager mode works again after a failed capture")
@@ -1115,3 +1114,44 @@ class _CaptureOnce:
     def __call__(self, t):
         from dlgrad_b200.runtime.cuda import shim
         return self.bad(t) if shim.capture["on"] else t
+
+
+def test_device_uniform_is_philox_and_dropout_draws_fresh_masks():
+    """Tensor.uniform / dropout on Device.CUDA: Philox4x32-10 on the device (codegen uniform_philox; the reference draws
+    on the host from a PCG32 reseeded per call, dlgrad/codegen/cpu_kernel.py:774-874, so only statistics are
+    comparable with it).  Bit-exact against the numpy restatement pinned by Random123's known answers; successive
+    draws differ; manual_seed reproduces; inside a captured graph every replay draws a fresh dropout mask."""
+    import dlgrad_b200 as dl
+    from dlgrad_b200 import Tensor, graph
+    from tests import philox_ref
+    from tests.conftest import COMPILE_ONLY
+    dl.manual_seed(1234)
+    a = Tensor.uniform((1000, 37), device="cuda", low=-2.0, high=3.0).numpy()
+    b = Tensor.uniform((1000, 37), device="cuda", low=-2.0, high=3.0).numpy()
+    c = Tensor.uniform((5,), device="cuda").numpy()
+    check(a.reshape(-1), philox_ref.uniform(37000, 1234, 0, -2.0, 3.0), exact=True, what="uniform, draw 0 of seed 1234")
+    check(b.reshape(-1), philox_ref.uniform(37000, 1234, 1, -2.0, 3.0), exact=True, what="uniform, draw 1")
+    check(c, philox_ref.uniform(5, 1234, 2), exact=True, what="uniform, draw 2 (ragged tail of a float4)")
+    dl.manual_seed(1234)
+    check(Tensor.uniform((1000, 37), device="cuda", low=-2.0, high=3.0).numpy(), a, exact=True, what="manual_seed reproduces")
+    if not COMPILE_ONLY:
+        assert a.min() >= -2.0 and a.max() < 3.0 and abs(a.mean() - 0.5) < 0.03 and abs(a.var() - 25.0 / 12.0) < 0.05
+        assert abs(np.corrcoef(a.reshape(-1), b.reshape(-1))[0, 1]) < 0.02
+    # dropout inside a captured step: the call number comes from device memory, advanced before every replay
+    x = np.random.default_rng(0).random((64, 256), dtype=np.float32) + 0.5
+    xt = Tensor(x.copy(), device="cuda")
+    cap = graph.CapturedStep(lambda t: t.dropout(0.25), xt, warmup=1)
+    masks = []
+    for _ in range(4):
+        out = cap().numpy()
+        masks.append(out != 0)
+        if not COMPILE_ONLY:
+            np.testing.assert_allclose(out[masks[-1]], x[masks[-1]] / 0.75, rtol=1e-6)
+            assert abs(masks[-1].mean() - 0.75) < 0.02
+    eager = xt.dropout(0.25).numpy() != 0
+    if not COMPILE_ONLY:
+        for i in range(4):
+            for j in range(i + 1, 4):
+                assert (masks[i] != masks[j]).mean() > 0.2, "replays must not repeat the mask"
+            assert (masks[i] != eager).mean() > 0.2
+    cap.close()

@@ -186,3 +186,18 @@ def test_fused_attention_kernels_generate_for_every_supported_head_dim():
         tc.attn_scores_tc(1024, 1024, 128, 4, 0.125, float("-inf"))                         # TMEM cannot hold two Q buffers
     ks = tc.matmul_tc_ts(1024, 64, 1024, 96, True, True, False, False, bn=64, ksparse="tn")
     assert ks.name.endswith("_sptn") and "last_kb" in ks.source
+
+
+def test_philox_reference_matches_random123_known_answers():
+    """tests/philox_ref.py — the numpy checker of the device generator — against Random123's kat_vectors for
+    philox4x32 with 10 rounds (counter, key -> output)."""
+    from tests import philox_ref
+    kats = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+            ((0xffffffff,) * 4, (0xffffffff, 0xffffffff), (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+            ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
+             (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for counter, key, want in kats:
+        assert tuple(int(x) for x in philox_ref.philox4x32_10(counter, key)) == want
+    u = philox_ref.uniform(1001, seed=7, call=3, low=-1.0, high=1.0)
+    assert u.shape == (1001,) and u.dtype == np.float32 and (u >= -1.0).all() and (u < 1.0).all()
+    assert not np.array_equal(u, philox_ref.uniform(1001, seed=7, call=4, low=-1.0, high=1.0))
