@@ -884,9 +884,15 @@ def matmul_tc_ts(M: int, N: int, K: int, batch: int, a_mn: bool, b_mn: bool, a_b
             }"""
     elif splitk > 1:
         assert nchunks == 1 and not bias and batch == splitk and N % 4 == 0
-        partial_sum = " ".join(
-            f"{{ const float4 o = __ldcg(reinterpret_cast<const float4*>(C + ((size_t){sl} * {M}u + row) * {N}u + col)); "
-            "acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w; }" for sl in range(1, splitk))
+        # rows of the quarter handled per pass: all R x S partial vectors are requested before the first add, so a
+        # lane has ~16 independent 16-byte loads in flight (one row at a time is a chain of 32 L2 round trips, ~20 us)
+        R = max(1, min(8, 16 // splitk))
+        loads = "\n                            ".join(
+            f"v[rr][{sl}] = ok ? __ldcg(reinterpret_cast<const float4*>(C + ((size_t){sl} * {M}u + row) * {N}u + col)) : z4;"
+            for sl in range(splitk))
+        adds = " ".join(
+            f"acc.x += v[rr][{sl}].x; acc.y += v[rr][{sl}].y; acc.z += v[rr][{sl}].z; acc.w += v[rr][{sl}].w;"
+            for sl in range(1, splitk))
         sk_seg_begin = "const bool seg_head = false;"
         sk_seg_end = f"""{{
                 // split-K: whichever slice finishes this quarter of the output tile LAST adds the {splitk} partial sums, in
@@ -903,15 +909,24 @@ def matmul_tc_ts(M: int, N: int, K: int, batch: int, a_mn: bool, b_mn: bool, a_b
                 if (last) {{
                     __threadfence();
                     float* fin = const_cast<float*>(bias);
-                    for (unsigned r = 0; r < 32u; ++r) {{
-                        const unsigned row = m0 + q * 32u + r;
-                        if (row >= {M}u) break;
-                        for (unsigned cv = lane; cv < {BN // 4}u; cv += 32u) {{
-                            const unsigned col = n0 + cv * 4u;
-                            if (col < {N}u) {{
-                                float4 acc = __ldcg(reinterpret_cast<const float4*>(C + (size_t)row * {N}u + col));
-                                {partial_sum}
-                                *reinterpret_cast<float4*>(fin + (size_t)row * {N}u + col) = acc;
+                    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                    for (unsigned cv = lane; cv < {BN // 4}u; cv += 32u) {{
+                        const unsigned col = n0 + cv * 4u;
+                        #pragma unroll 1
+                        for (unsigned r0 = 0; r0 < 32u; r0 += {R}u) {{
+                            float4 v[{R}][{splitk}];
+                            #pragma unroll
+                            for (unsigned rr = 0; rr < {R}u; ++rr) {{
+                                const unsigned row = m0 + q * 32u + r0 + rr;
+                                const bool ok = row < {M}u && col < {N}u;
+                                {loads}
+                            }}
+                            #pragma unroll
+                            for (unsigned rr = 0; rr < {R}u; ++rr) {{
+                                const unsigned row = m0 + q * 32u + r0 + rr;
+                                float4 acc = v[rr][0];
+                                {adds}
+                                if (row < {M}u && col < {N}u) *reinterpret_cast<float4*>(fin + (size_t)row * {N}u + col) = acc;
                             }}
                         }}
                     }}

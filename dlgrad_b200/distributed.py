@@ -18,6 +18,8 @@ uses torch.distributed's gloo store for that and for the timing barrier — plum
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 
 from dlgrad_b200.buffer import Buffer, flush_pending
@@ -26,6 +28,8 @@ from dlgrad_b200.runtime.cuda import shim
 from dlgrad_b200.tensor import Tensor
 
 _state = {"rank": 0, "world": 1, "bucket": None, "bucket_elems": 0}
+# seconds a rank waits inside the fused step for a peer before it traps (a dead peer must not hang the node)
+PEER_TIMEOUT_S = float(os.environ.get("DLGRAD_DP_TIMEOUT_S", "20"))
 
 
 def unique_id() -> bytes:
@@ -119,7 +123,7 @@ def prebuild(sizes: list[int], worlds: tuple = (2, 4, 8), betas: tuple = (0.9, 0
     from dlgrad_b200.runtime.cuda import compiler
     for w in worlds:
         offs, _, shard = bucket_layout(sizes, w)
-        for k in (ck.dp_adam(w, shard // 4, betas[0], betas[1], eps), ck.pack_multi(tuple(sizes), tuple(offs))):
+        for k in (ck.dp_adam(w, shard // 4, betas[0], betas[1], eps, PEER_TIMEOUT_S), ck.pack_multi(tuple(sizes), tuple(offs))):
             compiler.get_function(k.name, k.source)
 
 
@@ -227,7 +231,7 @@ class Adam:
         self.table = transfer.upload(shim.ffi.from_buffer("char *", table), table.nbytes)
         self.m = shim.calloc(self.shard * 4)
         self.v = shim.calloc(self.shard * 4)
-        self.plan = cuda_ops.Plan(ck.dp_adam(world, self.shard // 4, self.beta1, self.beta2, self.eps))
+        self.plan = cuda_ops.Plan(ck.dp_adam(world, self.shard // 4, self.beta1, self.beta2, self.eps, PEER_TIMEOUT_S))
         # gradient packing: one launch over a table of source addresses (two pinned staging tables alternate, so
         # one is never rewritten while its copy may still be in flight)
         n = len(params)
