@@ -201,3 +201,19 @@ def test_philox_reference_matches_random123_known_answers():
     u = philox_ref.uniform(1001, seed=7, call=3, low=-1.0, high=1.0)
     assert u.shape == (1001,) and u.dtype == np.float32 and (u >= -1.0).all() and (u < 1.0).all()
     assert not np.array_equal(u, philox_ref.uniform(1001, seed=7, call=4, low=-1.0, high=1.0))
+
+
+@pytest.mark.parametrize("batch,ntile,grid", [(96, 8, 148), (8, 8, 64), (3, 5, 15), (200, 2, 148), (1, 8, 8)])
+def test_balanced_work_order_covers_every_item_once_and_evens_out_a_causal_mask(batch, ntile, grid):
+    """The persistent attention kernels and the tile-skipping GEMMs walk (head, tile) items in an order that spreads the
+    cost of a causal mask (tile i has i + 1 live key tiles) over the CTAs; round-robin leaves 36 vs 13 units at C5."""
+    items = batch * ntile
+    per_cta = [tc.balanced_items(c, grid, items, batch, ntile) for c in range(grid)]
+    assert sorted(w for lst in per_cta for w in lst) == list(range(items))
+    for cost in (lambda w: w % ntile + 1, lambda w: ntile - w % ntile):
+        loads = [sum(cost(w) for w in lst) for lst in per_cta]
+        mean = sum(loads) / grid
+        assert max(loads) <= mean + ntile, (max(loads), mean)
+    if (batch, ntile, grid) == (96, 8, 148):
+        rr = [sum((w % 8) + 1 for w in range(c, items, grid)) for c in range(grid)]
+        assert max(rr) == 36 and max(sum(w % 8 + 1 for w in lst) for lst in per_cta) <= 24
