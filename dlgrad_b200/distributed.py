@@ -251,6 +251,7 @@ class Adam:
             p.grad = None
 
     def step(self) -> None:
+        shim.no_capture("distributed.Adam.step() (ranks wait for each other inside the kernel; capture forward + backward only)")
         self.t += 1
         f32 = np.float32
         bc1 = float(f32(1.0 - self.beta1 ** self.t))

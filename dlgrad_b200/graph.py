@@ -105,8 +105,21 @@ class CapturedStep:
         self.replays += 1
         return self.out
 
+    def __enter__(self) -> "CapturedStep":
+        return self
+
+    def __exit__(self, *exc) -> None:
+        self.close()
+
+    def __del__(self) -> None:
+        try:
+            self.close()
+        except Exception:          # interpreter shutdown: the library may already be gone
+            pass
+
     def close(self) -> None:
-        if self.exec != shim.NULL:
+        """Destroy the graph and release its memory pool; the Tensors of the captured call stay valid until dropped."""
+        if getattr(self, "exec", shim.NULL) != shim.NULL:
             shim.synchronize()
             shim.lib.dlg_graph_destroy(self.exec)
             self.exec = shim.NULL
