@@ -731,7 +731,8 @@ def balanced_items(cta: int, grid: int, items: int, batch: int, ntile: int) -> l
 def matmul_tc_ts(M: int, N: int, K: int, batch: int, a_mn: bool, b_mn: bool, a_bcast: bool, b_bcast: bool,
                  bn: int | None = None, stages: int | None = None, kc_blocks: int | None = None,
                  bias: bool = False, issuers: int | None = None, streamk: bool = False, ksparse: str | None = None,
-                 a_relu: bool = False, b_relu: bool = False, splitk: int = 0) -> TcKernel:
+                 a_relu: bool = False, b_relu: bool = False, splitk: int = 0,
+                 relu_mask: bool = False) -> TcKernel:
     """Kernel parameters after C: `bias` (a length-N row the epilogue adds to every output row when `bias` is
     set — the Linear bias; it rides on the plain store) and `flags` (uint32[ntiles * 4], zero, used when
     `streamk` is set).
@@ -747,6 +748,10 @@ def matmul_tc_ts(M: int, N: int, K: int, batch: int, a_mn: bool, b_mn: bool, a_b
     are stored [K][cols], so slices are a batch).  C is then the scratch [S][M][N] of partial sums, `bias` carries the
     pointer of the real output and `flags` one counter per (output tile, row quarter): the slice that finishes a
     quarter LAST adds the S partials in slice order and writes the result — deterministic, no second kernel.
+
+    relu_mask: `bias` points at a matrix X laid out like C; the epilogue writes X > 0 ? C : 0 — the backward of a relu
+    whose output fed the Linear this GEMM differentiates (dX = g @ W masked by the pre-activation), so the separate
+    `where(x > 0, g, 0)` pass over three (tokens, 4C) matrices disappears (ops.Linear.backward / ops.Relu.backward).
 
     a_relu / b_relu: the operand is relu(stored matrix) — a deferred `Tensor.relu()` (Buffer pending kind "relu") —
     applied where the operand passes through registers anyway: in the A splitter before the hi/lo split, in the B
@@ -885,6 +890,32 @@ def matmul_tc_ts(M: int, N: int, K: int, batch: int, a_mn: bool, b_mn: bool, a_b
                                     v[4 * j + 2] = __float_as_uint(__uint_as_float(v[4 * j + 2]) + bv.z);
                                     v[4 * j + 3] = __float_as_uint(__uint_as_float(v[4 * j + 3]) + bv.w);
                                 }}
+                            }}
+                        }}"""
+    mask_code = ""
+    if relu_mask:
+        assert not bias and not streamk and not splitk and N % 4 == 0
+        sel = " ".join(
+            f"v[4 * j + {i}] = xv.{c} > 0.f ? v[4 * j + {i}] : 0u;" for i, c in enumerate("xyzw"))
+        mask_code = f"""
+                        {{
+                            // relu backward: keep the gradient where the pre-activation X is positive (NaN -> 0, like where()).
+                            // The X tile comes in coalesced (4 rows x 128 B per instruction, 8 loads in flight per lane)
+                            // through the staging box; each thread then reads the row it owns.
+                            #pragma unroll
+                            for (unsigned i = 0; i < 8u; ++i) {{
+                                const unsigned r = 4u * i + (lane >> 3), cc = lane & 7u;
+                                const unsigned row = m0 + q * 32u + r, col = n0 + c * 32u + cc * 4u;
+                                float4 xv = make_float4(0.f, 0.f, 0.f, 0.f);
+                                if (row < {M}u && col < {N}u)
+                                    xv = __ldg(reinterpret_cast<const float4*>(bias + ((size_t)z * {M}u + row) * {N}u + col));
+                                *reinterpret_cast<float4*>(sbuf_gen + r * 128u + ((cc ^ (r & 7u)) << 4)) = xv;
+                            }}
+                            __syncwarp();
+                            #pragma unroll
+                            for (unsigned j = 0; j < 8u; ++j) {{
+                                const float4 xv = *reinterpret_cast<const float4*>(sbuf_gen + lane * 128u + ((j ^ (lane & 7u)) << 4));
+                                {sel}
                             }}
                         }}"""
     if streamk:
@@ -1188,7 +1219,7 @@ extern "C" __global__ void __launch_bounds__({nthreads}, 1)
                         const unsigned sb = nstore & {EPI_BUFS - 1}u;
                         if (lane == 0) asm volatile("cp.async.bulk.wait_group.read {EPI_BUFS - 1};" ::: "memory");
                         __syncwarp();
-                        unsigned char* sbuf_gen = my_epi_gen + sb * 4096u;
+                        unsigned char* sbuf_gen = my_epi_gen + sb * 4096u;{mask_code}
                         {stage_writes}
                         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                         __syncwarp();
@@ -1217,7 +1248,7 @@ extern "C" __global__ void __launch_bounds__({nthreads}, 1)
     }}
 }}
 """
-    return TcKernel("mm_tcts" + ("_b" if bias else "") + ("_sk" if streamk else "") + (f"_sp{ksparse}" if ksparse else "") + ("_ra" if a_relu else "") + ("_rb" if b_relu else "") + (f"_k{splitk}" if splitk > 1 else ""), src, (grid, 1, 1), nthreads, smem, batch * M * N, BN, stages)
+    return TcKernel("mm_tcts" + ("_b" if bias else "") + ("_sk" if streamk else "") + (f"_sp{ksparse}" if ksparse else "") + ("_ra" if a_relu else "") + ("_rb" if b_relu else "") + (f"_k{splitk}" if splitk > 1 else "") + ("_rm" if relu_mask else ""), src, (grid, 1, 1), nthreads, smem, batch * M * N, BN, stages)
 
 
 # =====================================================================================================

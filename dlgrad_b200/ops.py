@@ -10,6 +10,9 @@ kept and marked QUIRK:
 """
 from __future__ import annotations
 
+import os
+import weakref
+
 from dlgrad_b200.buffer import Buffer
 from dlgrad_b200.device import Device
 from dlgrad_b200.dispatch import dispatcher
@@ -208,6 +211,12 @@ class RSqrt(OP):
         return (grad_output * ((self.out ** 3) * -0.5),)
 
 
+# gradient Buffers that a Linear backward produced with the relu-backward select already applied in the GEMM epilogue:
+# id(gradient Buffer) -> id(pre-activation Buffer)   (Buffer.__eq__ is the elementwise op, so no dict keyed by the object)
+_premasked: dict = {}
+RELU_BWD_EPILOGUE = os.environ.get("DLGRAD_RELU_BWD_EPILOGUE", "1") != "0"
+
+
 class Relu(OP):
     """On CUDA a large relu is DEFERRED (Buffer pending kind "relu"): the GEMM that consumes it applies max(., 0) in
     its operand splitter and relu(x) is never written; any other consumer materialises it with the reference's
@@ -223,6 +232,8 @@ class Relu(OP):
         return self.out
 
     def backward(self, upstream_grad: Buffer) -> tuple[Buffer]:
+        if _premasked.get(id(upstream_grad)) == id(self.x):
+            return (upstream_grad,)      # the GEMM that produced this gradient already selected on x > 0 (Linear.backward)
         if Buffer._route(self.x, upstream_grad) is Device.CUDA and self.x.shape == upstream_grad.shape:
             # one select instead of the reference's where(1, 0) followed by a multiply (same values)
             return (self.x.where(upstream_grad, 0.0),)
@@ -440,6 +451,9 @@ class Linear(OP):
     def forward(self, x: Buffer, weight: Buffer, bias: Buffer | None = None) -> Buffer:
         from dlgrad_b200.helpers import BinaryOps
         self.x, self.w, self.b = x, weight, bias
+        # the input is a deferred relu (ops.Relu): its backward is a select on the pre-activation, which the dX GEMM of
+        # this Linear can apply in its epilogue
+        self.relu_src = x._pending[1] if (x._pending is not None and x._pending[0] == "relu") else None
         out_f, in_f = weight.shape
         rows = x.numel // in_f
         x2 = x.reshape((rows, in_f))
@@ -458,7 +472,14 @@ class Linear(OP):
         rows = self.x.numel // in_f
         g2 = upstream_grad.reshape((rows, out_f))
         gx = gw = gb = None
-        if self.req_grad[0]:
+        if self.req_grad[0] and self.relu_src is not None and RELU_BWD_EPILOGUE and self.relu_src._pending is None:
+            ptr, applied = dispatcher.dispatch(op=BinaryOps.MATMUL, device=Device.CUDA, x=g2, y=self.w,
+                                               relu_mask=self.relu_src.reshape((rows, in_f)))
+            gx = Buffer(ptr, self.x.shape, Device.CUDA, self.x.dtype)
+            if applied:
+                _premasked[id(gx)] = id(self.relu_src)
+                weakref.finalize(gx, _premasked.pop, id(gx), None)
+        elif self.req_grad[0]:
             gx = Buffer(dispatcher.dispatch(op=BinaryOps.MATMUL, device=Device.CUDA, x=g2, y=self.w),
                         self.x.shape, Device.CUDA, self.x.dtype)
         if self.req_grad[1]:

@@ -53,12 +53,17 @@ def _fold_transpose(b: Buffer, flag: bool):
     return b, flag
 
 
-def run_matmul(x: Buffer, y: Buffer, trans_x: bool = False, trans_y: bool = False, bias: Buffer | None = None):
+def run_matmul(x: Buffer, y: Buffer, trans_x: bool = False, trans_y: bool = False, bias: Buffer | None = None,
+               relu_mask: Buffer | None = None):
     """`bias` (a length-N row) is added by the GEMM epilogue when the shape runs on the TS tensor-core kernel;
-    returns (ptr, bias_applied) in that case so the caller adds it separately otherwise."""
+    returns (ptr, bias_applied) in that case so the caller adds it separately otherwise.  `relu_mask` (a matrix shaped
+    like the product): the epilogue keeps the product only where it is positive; returns (ptr, applied)."""
     # a deferred transpose of an operand (Buffer.transpose) is folded into the kernel's operand-major flag
     x, trans_x = _fold_transpose(x, trans_x)
     y, trans_y = _fold_transpose(y, trans_y)
+    if relu_mask is not None:
+        out = _relu_masked_matmul(x, y, trans_x, trans_y, relu_mask)
+        return (out, True) if out is not None else (run_matmul(x, y, trans_x, trans_y), False)
     if bias is None and ((x._pending is not None and x._pending[0] == "relu") or (y._pending is not None and y._pending[0] == "relu")):
         out = _relu_operand_matmul(x, y, trans_x, trans_y)
         if out is not None:
@@ -99,6 +104,38 @@ def run_matmul(x: Buffer, y: Buffer, trans_x: bool = False, trans_y: bool = Fals
         out = plan(*args)
         timer.stop(t0, plan.flops, plan.tag)
     return out if bias is None else (out, fused is not None)
+
+
+def _relu_masked_matmul(x: Buffer, y: Buffer, tx: bool, ty: bool, mask: Buffer):
+    """x @ y with the relu-backward select on `mask` (the pre-activation) in the epilogue; None when the shape does not
+    run on the tensor-core kernel as one launch."""
+    if x._pending is not None or y._pending is not None or mask._pending is not None or mask.scalar is not None:
+        return None
+    aligned = x.aligned and y.aligned and mask.aligned
+    key = (x.metadata.shape, y.metadata.shape, tx, ty, aligned, "rmask")
+    plan = _plans.get(key)
+    if plan is None and key not in _plans:
+        M, N, K, batch, a_bs, b_bs, out_shape = _geometry(x.metadata.shape, y.metadata.shape, tx, ty)
+        plan = None
+        if not FORCE_SIMT and aligned and N % 4 == 0 and prod_(mask.metadata.shape) == prod_(batch) * M * N \
+                and _split_k(M, N, K, batch, tx, ty) == 1:
+            from dlgrad_b200.runtime.cuda import matmul_tc
+            # BN <= 128 keeps two accumulators in TMEM, so the longer epilogue (it also reads the X tile) overlaps the
+            # next tile's MMAs; at BN = 192 there is one accumulator and the select costs more than the kernel it replaces
+            bn = int(os.environ.get("DLGRAD_RMASK_BN", "128"))
+            plan = matmul_tc.try_build(M, N, K, batch, a_bs, b_bs, tx, ty, aligned, relu_mask=True,
+                                       bn=bn if N >= bn else None)
+        _plans[key] = plan
+    if plan is None:
+        return None
+    args = (_ops._dev_ptr(x), _ops._dev_ptr(y), _ops._dev_ptr(mask))
+    timer = _profile.matmul_timer
+    if timer is None:
+        return plan(*args)
+    t0 = timer.start()
+    out = plan(*args)
+    timer.stop(t0, plan.flops, plan.tag)
+    return out
 
 
 def _relu_operand_matmul(x: Buffer, y: Buffer, tx: bool, ty: bool):

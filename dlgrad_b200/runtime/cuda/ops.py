@@ -716,10 +716,11 @@ def cat(x: Buffer, y: Buffer, dim: int) -> CDataPtr:
 # matmul                                                      reference: cpu.py:505-602
 # ------------------------------------------------------------------------------------------------
 @dispatcher.register(BinaryOps.MATMUL, CUDA)
-def matmul(x: Buffer, y: Buffer, trans_x: bool = False, trans_y: bool = False, bias: Buffer | None = None):
-    """With `bias` (CUDA extension used by ops.Linear) returns (ptr, bias_applied)."""
+def matmul(x: Buffer, y: Buffer, trans_x: bool = False, trans_y: bool = False, bias: Buffer | None = None,
+           relu_mask: Buffer | None = None):
+    """With `bias` or `relu_mask` (CUDA extensions used by ops.Linear) returns (ptr, applied)."""
     from dlgrad_b200.runtime.cuda import matmul as _mm
-    return _mm.run_matmul(x, y, trans_x, trans_y, bias)
+    return _mm.run_matmul(x, y, trans_x, trans_y, bias, relu_mask)
 
 
 # ------------------------------------------------------------------------------------------------

@@ -799,6 +799,8 @@ def test_deferred_relu_folds_into_the_consuming_gemm(oracle):
         if dev == "cuda" and not compile_only:
             assert r.data._pending is not None, "the GEMMs must not have materialised the relu"
             assert any(k[5] == "relu" and v is not None for k, v in mm._plans.items() if len(k) == 8), "expected relu-operand GEMM plans"
+            assert any(k[5] == "rmask" and v is not None for k, v in mm._plans.items() if len(k) == 6), \
+                "expected the relu backward to ride on the dX GEMM's epilogue"
     for got, exp, what in zip(res["cuda"], res["cpu"], ("y", "dx", "dw1", "dw2")):
         runner.rel_check(check, got, exp, runner.TOL_MATMUL, f"fc -> relu -> proj: {what}")
     # other consumers see the eager values
