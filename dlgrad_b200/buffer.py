@@ -69,7 +69,9 @@ def _host_compute_enabled() -> bool:
 
 
 LAZY_MIN_NUMEL = 1 << 16      # pointwise producers below this size are not worth deferring
-_pending_buffers: "weakref.WeakSet[Buffer]" = None  # type: ignore[assignment]  (created below)
+# deferred buffers that are still alive, id -> weak reference.  Not a WeakSet: its discard() compares referents with
+# ==, and Buffer.__eq__ is the elementwise op — every discard would launch an EQ kernel over the whole buffer.
+_pending_buffers: "dict[int, weakref.ref]" = {}
 
 
 # ---- buffers whose content is a pure function of shapes and python scalars ------------------------------------
@@ -131,14 +133,15 @@ def flush_pending(written: tuple = ()) -> None:
     if not _pending_buffers:
         return
     ids = {id(w) for w in written}
-    for b in list(_pending_buffers):
-        if b._pending is None:
-            _pending_buffers.discard(b)
+    for key, ref in list(_pending_buffers.items()):
+        b = ref()
+        if b is None or b._pending is None:
+            _pending_buffers.pop(key, None)
             continue
         if ids and not _reads_any(b, ids):
             continue
         _ = b.ptr
-        _pending_buffers.discard(b)
+        _pending_buffers.pop(key, None)
 
 
 def _reads_any(b: "Buffer", ids: set) -> bool:
@@ -196,7 +199,8 @@ class Buffer:
     def _deferred(pending: tuple, shape: tuple, dtype: DType = _F32) -> "Buffer":
         b = Buffer(None, shape, _CUDA, dtype)
         b._pending = pending
-        _pending_buffers.add(b)
+        key = id(b)
+        _pending_buffers[key] = weakref.ref(b, lambda _r, k=key: _pending_buffers.pop(k, None))
         return b
 
     # ------------------------------------------------------------------ construction
@@ -616,6 +620,3 @@ class Buffer:
     @property
     def nbytes(self) -> int:
         return self.metadata.nbytes
-
-
-_pending_buffers = weakref.WeakSet()
