@@ -217,3 +217,16 @@ def test_balanced_work_order_covers_every_item_once_and_evens_out_a_causal_mask(
     if (batch, ntile, grid) == (96, 8, 148):
         rr = [sum((w % 8) + 1 for w in range(c, items, grid)) for c in range(grid)]
         assert max(rr) == 36 and max(sum(w % 8 + 1 for w in lst) for lst in per_cta) <= 24
+
+
+def test_constant_folding_capture_and_rng_host_invariants():
+    """tests/_host_capture_script.py with the stand-in library (no GPU): lazy FULL / ARANGE and shared copy-on-write
+    storage of constant masks, the guards and pre-replay hooks of graph.CapturedStep (Adam's step count, .grad
+    re-binding), and the call-number bookkeeping of the device RNG."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, os.path.join(root, "tests", "_host_capture_script.py")], cwd=root,
+                         capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0 and "all host checks passed" in res.stdout, res.stdout[-3000:] + res.stderr[-3000:]
