@@ -3,6 +3,7 @@ from enum import Enum, auto
 
 
 class Device(Enum):
+    __hash__ = object.__hash__        # identity hash in C: these are dict keys on every dispatch (Enum's is a Python call)
     CPU = auto()     # host staging memory (numpy views, checkpoints); no kernels of its own here
     METAL = auto()   # kept so that dlgrad code naming it still imports; never dispatched to
     CUDA = auto()    # B200 / sm_100a

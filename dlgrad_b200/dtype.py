@@ -10,6 +10,7 @@ Scalar = float
 
 
 class DType(Enum):
+    __hash__ = object.__hash__        # identity hash in C: these are dict keys on every dispatch (Enum's is a Python call)
     FLOAT32 = auto()
 
     @staticmethod

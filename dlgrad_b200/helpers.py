@@ -18,6 +18,7 @@ ffi = FFI()
 
 
 class UnaryOps(Enum):
+    __hash__ = object.__hash__        # identity hash in C: these are dict keys on every dispatch (Enum's is a Python call)
     SUM = auto()
     MAX = auto()
     NEG = auto()
@@ -43,6 +44,7 @@ class UnaryOps(Enum):
 
 
 class BufferOps(Enum):
+    __hash__ = object.__hash__        # identity hash in C: these are dict keys on every dispatch (Enum's is a Python call)
     CREATE = auto()
     UNIFORM = auto()
     ARANGE = auto()
@@ -50,6 +52,7 @@ class BufferOps(Enum):
 
 
 class BinaryOps(Enum):
+    __hash__ = object.__hash__        # identity hash in C: these are dict keys on every dispatch (Enum's is a Python call)
     ADD = auto()
     SUB = auto()
     MUL = auto()
@@ -62,6 +65,7 @@ class BinaryOps(Enum):
 
 
 class CustomOps(Enum):
+    __hash__ = object.__hash__        # identity hash in C: these are dict keys on every dispatch (Enum's is a Python call)
     INDEX = auto()
     CE_FORWARD = auto()
     CE_BACKWARD = auto()
