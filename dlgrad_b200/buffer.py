@@ -330,14 +330,21 @@ class Buffer:
             assert d <= len(shp), f"Cannot unsqueeze {dims} from {self.shape}"
         for d in sorted(dims, reverse=True):
             shp.insert(d, 1)
-        self.metadata.set_shape(tuple(shp))
+        self._set_shape(tuple(shp))
+
+    def _set_shape(self, shape: tuple) -> None:
+        """In-place relabelling (the reference's Sum / Max backward and squeeze / unsqueeze do it): the content tag
+        follows the new shape, like reshape()."""
+        self.metadata.set_shape(shape)
+        if self._const is not None:
+            self._const = ("reshape", self._const, tuple(shape))
 
     def squeeze(self, dim: list[int] | int) -> None:
         for d in ([dim] if isinstance(dim, int) else list(dim)):
             if self.shape[d] == 1:
                 shp = list(self.shape)
                 shp.pop(d)
-                self.metadata.set_shape(tuple(shp))
+                self._set_shape(tuple(shp))
 
     # ------------------------------------------------------------------ reductions
     def _reduce(self, op: UnaryOps, dim: int, keepdim: bool) -> "Buffer":

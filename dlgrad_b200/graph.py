@@ -46,6 +46,7 @@ class CapturedStep:
             if not isinstance(t, Tensor) or t.device is not Device.CUDA:
                 raise ValueError("CapturedStep inputs must be Tensors on Device.CUDA (their storage becomes the graph's input)")
         self.fn, self.inputs = fn, inputs
+        flush_pending(tuple(t.data for t in inputs))     # replays overwrite the inputs in place: private, untagged storage
         lib = shim.lib
         for _ in range(max(1, warmup)):            # compiles every kernel, fills the plan / constant caches
             out = fn(*inputs)

@@ -99,6 +99,7 @@ class Tensor:
             raise ValueError(f"Buffer size mismatch! Expected {self.nbytes} bytes, got {len(source_bytes)}")
         from dlgrad_b200.buffer import flush_pending
         flush_pending()
+        flush_pending((self.data,))       # in-place write: private storage, and the content tag (if any) no longer holds
         if self.data.metadata.device is _CUDA:
             from dlgrad_b200.runtime.cuda import transfer
             transfer.write_bytes(self.data.ptr, bytes(source_bytes))

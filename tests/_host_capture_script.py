@@ -43,6 +43,17 @@ a, b = Tensor.ones((8, 8), device="cuda"), Tensor.ones((8, 8), device="cuda")
 ok(shim.address(a.data.ptr) != shim.address(b.data.ptr), "FULL results themselves are never shared")
 ok(Tensor.tril(Tensor.ones((256, 256), device="cuda"), k=1.0).data._const != m1.data._const, "another diagonal is another tag")
 
+c = Tensor.tril(Tensor.ones((256, 256), device="cuda"), k=0.0)
+shared = shim.address(c.data.ptr)
+c.copy_from(np.zeros((256, 256), dtype=np.float32).tobytes())
+ok(c.data._const is None and shim.address(c.data.ptr) != shared, "copy_from writes a private, untagged copy (the cached constant is untouched)")
+o = Tensor.ones((4, 4), device="cuda")
+o.copy_from(np.full((4, 4), 7.0, dtype=np.float32).tobytes())
+ok(o.data._const is None and (o * 2.0).data._const is None, "a loaded tensor is no longer a constant: nothing derived from it is folded")
+u = Tensor.ones((3, 1), device="cuda")
+u.data.unsqueeze(0)
+ok(u.data._const[0] == "reshape" and u.data._const[2] == (1, 3, 1), "an in-place relabel carries the tag to the new shape")
+
 # ---- captured steps: guards, hooks, state restore ------------------------------------------------------------------
 w = Tensor(np.ones((16, 16), dtype=np.float32), device="cuda", requires_grad=True)
 opt = nn.optim.Adam([w], lr=1e-2)
@@ -57,6 +68,10 @@ def step(x):
     return loss
 
 
+xin = Tensor.ones((16, 16), device="cuda")
+capin = graph.CapturedStep(lambda t: t * 2.0, xin, warmup=1)
+ok(xin.data._const is None and not xin.data._cow, "a constant passed as a graph input becomes an ordinary buffer")
+capin.close()
 cap = graph.CapturedStep(step, x0, warmup=2, params=[w])
 ok(opt.t == 2 and len(cap.hooks) == 1, "warm-up steps are real steps, the captured call is not; Adam registered its hook")
 g_captured = w.grad

@@ -963,6 +963,16 @@ def test_constant_masks_are_computed_once_shared_and_copy_on_write():
           what="full() keeps the reference's int cast of the fill value")
     check((Tensor.ones((8, 8), device="cuda") * 3.0 + Tensor.full((8, 8), 2.0, device="cuda")).numpy(),
           np.full((8, 8), 5.0, dtype=np.float32), exact=True, what="arithmetic on constants")
+    # copy_from (checkpoint loading) is an in-place writer too: the tensor stops being a constant, the cache is untouched
+    loaded = Tensor.ones((4, 4), device="cuda")
+    loaded.copy_from(np.full((4, 4), 7.0, dtype=np.float32).tobytes())
+    check((loaded * 2.0).numpy(), np.full((4, 4), 14.0, dtype=np.float32), exact=True, what="ones -> copy_from(7) -> * 2")
+    check((Tensor.ones((4, 4), device="cuda") * 2.0).numpy(), np.full((4, 4), 2.0, dtype=np.float32), exact=True,
+          what="a fresh ones * 2 is still 2")
+    over = Tensor.tril(Tensor.ones((T, T), device="cuda"), k=0.0)
+    over.copy_from(np.zeros((T, T), dtype=np.float32).tobytes())
+    check(over.numpy(), np.zeros((T, T), dtype=np.float32), exact=True, what="copy_from over a tensor that shared constant storage")
+    check(Tensor.tril(Tensor.ones((T, T), device="cuda"), k=0.0).numpy(), want, exact=True, what="the cached constant survives it")
 
 
 def test_captured_step_replays_bit_identically_to_eager():
