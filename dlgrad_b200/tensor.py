@@ -377,6 +377,7 @@ class Tensor:
         base = self.data
         view = Buffer(base.ptr + offset, shape, base.device, base.dtype,
                       aligned=base.aligned and offset % 4 == 0, keep=(base.ptr, base._keep))
+        view._cow = base._cow            # a slice of storage shared with the constant cache is copy-on-write as well
         return Tensor(view, requires_grad=self.requires_grad)
 
     # ------------------------------------------------------------------ operators
