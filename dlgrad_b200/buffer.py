@@ -83,6 +83,7 @@ _pending_buffers: "dict[int, weakref.ref]" = {}
 # in-place writer calls first — gives a written Buffer a private copy and drops its tag.  Results of FULL / ARANGE
 # themselves are never shared (a `Tensor.ones` is a perfectly good parameter).
 CONST_CACHE_LIMIT = 256 << 20
+CONST_CACHE_ENTRIES = 4096
 _const_cache: dict = {}                  # content tag -> device storage
 _const_cache_bytes = [0]
 CONST_FOLD = os.environ.get("DLGRAD_CONST_FOLD", "1") != "0"
@@ -100,6 +101,9 @@ def _const_node(tag: tuple, shape: tuple, dtype: DType, compute) -> "Buffer":
         b._const, b._cow = tag, True
         return b
     b = compute()
+    if len(_const_cache) >= CONST_CACHE_ENTRIES:       # a loop that keeps inventing new constants: start over (Buffers
+        _const_cache.clear()                           # that share the dropped storage keep it alive themselves)
+        _const_cache_bytes[0] = 0
     if b.metadata.device is _CUDA and _const_cache_bytes[0] + b.metadata.nbytes <= CONST_CACHE_LIMIT:
         _const_cache[tag] = b.ptr
         _const_cache_bytes[0] += b.metadata.nbytes
