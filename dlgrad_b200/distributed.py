@@ -70,6 +70,7 @@ def all_reduce_gradients(params: list[Tensor]) -> None:
     live = [p for p in params if p.grad is not None]
     if world == 1 or not live:
         return
+    shim.no_capture("all_reduce_gradients() (the collective runs on its own stream; capture forward + backward only)")
     sizes = [p.grad.numel for p in live]
     offs = shard_offsets(sizes)
     total = offs[-1]
