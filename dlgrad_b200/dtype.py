@@ -2,24 +2,31 @@
 argmax results are float32 holding integers.  The CUDA backend keeps that representation."""
 from __future__ import annotations
 
-from enum import Enum, auto
+import enum
 from typing import Any, NewType
 
-CDataPtr = NewType("CDataPtr", Any)   # a cffi `float *` cdata: host address on CPU, CUdeviceptr on CUDA
+# a cffi `float *` cdata: host address on CPU, CUdeviceptr on CUDA
+CDataPtr = NewType("CDataPtr", Any)
 Scalar = float
 
 
-class DType(Enum):
-    __hash__ = object.__hash__        # identity hash in C: these are dict keys on every dispatch (Enum's is a Python call)
-    FLOAT32 = auto()
+class DType(enum.Enum):
+    """Element types; the value of a member is its size in bytes."""
+    __hash__ = object.__hash__        # identity hash in C: a member keys dict lookups on every dispatch
+
+    FLOAT32 = 4
+
+    @property
+    def itemsize(self) -> int:
+        return self.value
 
     @staticmethod
     def from_str(d: str) -> "DType":
-        try:
-            return DType[d.upper()]
-        except KeyError:
-            raise ValueError(f"Invalid dtype: {d}") from None
+        member = DType.__members__.get(str(d).strip().upper())
+        if member is None:
+            raise ValueError(f"Invalid dtype: {d}")
+        return member
 
     @staticmethod
     def get_n_bytes(d: "DType") -> int:
-        return 4
+        return d.itemsize
