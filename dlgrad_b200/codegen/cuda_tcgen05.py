@@ -793,7 +793,12 @@ def matmul_tc_ts(M: int, N: int, K: int, batch: int, a_mn: bool, b_mn: bool, a_b
     # MMA-issuing warps.  Two help the narrow tiles, whose k-block is issue-bound (BN=64: 390 -> 335 ns per
     # k-block); at BN >= 128 the k-block is bound by shared-memory traffic and a second issuer changes nothing
     # (BN=128: 569 vs 546 ns, BN=192: 794 vs 818 ns).
-    NI = issuers or int(os.environ.get("DLGRAD_TC_ISSUERS", "0")) or (2 if BN <= 96 else 1)
+    # One MMA-issuing warp.  A second one taking alternate k-blocks (DLGRAD_TC_ISSUERS=2) is 14 % faster on narrow tiles
+    # (BN <= 96 is issue-bound), but MMAs issued by two different warps into one accumulator are not guaranteed to
+    # execute in issue order: the fp32 accumulation order — and with it the last bits of a training run — then varies
+    # from run to run (measured: two 21-step runs of the GPT differ in the 7th digit of the loss with two issuers, are
+    # identical with one).  Reproducibility wins; the reference's CPU path is deterministic.
+    NI = issuers or int(os.environ.get("DLGRAD_TC_ISSUERS", "0")) or 1
     tmem_cols = 32
     while tmem_cols < a_tmem0 + 64 * stages:
         tmem_cols *= 2
