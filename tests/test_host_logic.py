@@ -230,3 +230,13 @@ def test_constant_folding_capture_and_rng_host_invariants():
     res = subprocess.run([sys.executable, os.path.join(root, "tests", "_host_capture_script.py")], cwd=root,
                          capture_output=True, text=True, timeout=300)
     assert res.returncode == 0 and "all host checks passed" in res.stdout, res.stdout[-3000:] + res.stderr[-3000:]
+
+
+def test_one_mma_issuing_warp_by_default(monkeypatch):
+    """Two MMA-issuing warps per CTA are faster on narrow tiles but make the accumulation order, hence the bits of a
+    run, vary (profiles/r01_tc_pipeline_findings.md): the default must stay at one issuer, two only on request."""
+    monkeypatch.delenv("DLGRAD_TC_ISSUERS", raising=False)
+    narrow = tc.matmul_tc_ts(1024, 64, 1024, 96, False, False, False, False)
+    assert narrow.bn <= 96 and narrow.threads == 448 and "warp == 14" not in narrow.source
+    two = tc.matmul_tc_ts(1024, 64, 1024, 96, False, False, False, False, issuers=2)
+    assert two.threads == 480 and "warp == 14" in two.source
