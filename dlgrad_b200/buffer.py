@@ -97,6 +97,7 @@ def _const_node(tag: tuple, shape: tuple, dtype: DType, compute) -> "Buffer":
     """The Buffer for content `tag`: shared storage if it has been computed before, else `compute()` (kept if it fits)."""
     hit = _const_cache.get(tag)
     if hit is not None:
+        _pin_for_capture(hit)
         b = Buffer(hit, shape, _CUDA, dtype)
         b._const, b._cow = tag, True
         return b
@@ -108,8 +109,18 @@ def _const_node(tag: tuple, shape: tuple, dtype: DType, compute) -> "Buffer":
         _const_cache[tag] = b.ptr
         _const_cache_bytes[0] += b.metadata.nbytes
         b._cow = True
+        _pin_for_capture(b._ptr)
     b._const = tag
     return b
+
+
+def _pin_for_capture(storage) -> None:
+    """Constant storage read by a step that is being captured into a CUDA graph is baked into the graph by address:
+    the graph keeps a reference, so clearing the constant cache later (CONST_CACHE_ENTRIES overflow) cannot hand the
+    block to somebody else while replays still read it (dlgrad_b200/graph.py, CapturedStep.refs)."""
+    from dlgrad_b200.runtime.cuda import shim
+    if shim.capture["on"] and shim.capture["refs"] is not None:
+        shim.capture["refs"].append(storage)
 
 
 def _unshare(b: "Buffer") -> None:
@@ -136,7 +147,13 @@ def flush_pending(written: tuple = ()) -> None:
             _unshare(w)
     if not _pending_buffers:
         return
+    # a deferred chain may read a reshape / slice / detach VIEW of a written buffer: match by the storage the
+    # Buffers point into (their own pointer object and whatever they keep alive), not only by Buffer identity
     ids = {id(w) for w in written}
+    for w in written:
+        if w._ptr is not None:
+            ids.add(id(w._ptr))
+        ids.update(_storage_ids(w._keep))
     for key, ref in list(_pending_buffers.items()):
         b = ref()
         if b is None or b._pending is None:
@@ -148,11 +165,25 @@ def flush_pending(written: tuple = ()) -> None:
         _pending_buffers.pop(key, None)
 
 
+def _storage_ids(keep) -> set:
+    """ids of the storage objects a Buffer's `_keep` chain holds (a slice keeps `(base pointer, base keep)`)."""
+    out, stack = set(), [keep]
+    while stack:
+        k = stack.pop()
+        if k is None:
+            continue
+        if isinstance(k, tuple):
+            stack.extend(k)
+        else:
+            out.add(id(k))
+    return out
+
+
 def _reads_any(b: "Buffer", ids: set) -> bool:
     stack = [b]
     while stack:
         cur = stack.pop()
-        if id(cur) in ids:
+        if id(cur) in ids or (cur._ptr is not None and id(cur._ptr) in ids) or (_storage_ids(cur._keep) & ids):
             return True
         pend = cur._pending
         if pend is not None:
@@ -354,6 +385,11 @@ class Buffer:
     def _reduce(self, op: UnaryOps, dim: int, keepdim: bool) -> "Buffer":
         out_shape = cal_sum_max_out_shape(ndim=self.ndim, dim=dim, inp_shape=self.shape, keepdim=keepdim)
         dev = Buffer._route(self)
+        if dev is _CUDA and dim == -1 and keepdim:
+            # SURVEY quirk 12 is NOT mirrored on the device: the reference labels the one-element result of a full
+            # reduction with the INPUT shape (dlgrad/helpers.py:205-206) — a latent out-of-bounds read on the host,
+            # a read of other tensors' memory (or a sticky fault) in HBM.  (1,)*ndim broadcasts like keepdim should.
+            out_shape = (1,) * self.ndim
         return self._like(_dispatch(op=op, device=dev, x=self, dim=dim), out_shape, dev)
 
     def sum(self, dim: int = -1, keepdim: bool = False) -> "Buffer":

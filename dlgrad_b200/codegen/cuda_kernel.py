@@ -1182,6 +1182,33 @@ extern "C" __global__ void __launch_bounds__(256) {KNAME}{SIG_ALIAS} {{
     return Kernel("sgd", src, (_cdiv(nv, 256), 1, 1), (256, 1, 1), 0, 0)
 
 
+@cache
+def sgd_momentum_step(numel: int, aligned: bool = True) -> Kernel:
+    """In-place v = v*mu + g; p = p - lr*v — what the reference's momentum branch spells (dlgrad/nn/optim.py:38-44:
+    `velocity = momentum * velocity + grad`, then `param - lr * velocity`), same op order as the eager chain
+    MUL, ADD, MUL, SUB, with the velocity updated IN PLACE so that the launch arguments never change from step to
+    step (a captured step replays it).  p0 = param, p1 = grad, p2 = velocity, f0 = lr, f1 = momentum, f3 = scale."""
+    V = 4 if (aligned and numel % 4 == 0) else 1
+    nv = numel // V
+    VT = "float4" if V == 4 else "float"
+    comps = [".x", ".y", ".z", ".w"] if V == 4 else [""]
+    body = " ".join(f"v{c} = __fadd_rn(__fmul_rn(v{c}, f1), g{c}); p{c} = __fsub_rn(p{c}, __fmul_rn(f0, __fmul_rn(v{c}, f3)));"
+                    for c in comps)
+    src = f"""
+extern "C" __global__ void __launch_bounds__(256) {KNAME}{SIG_ALIAS} {{
+    const unsigned i = blockIdx.x * 256u + threadIdx.x;
+    if (i >= {nv}u) return;
+    {VT} p = reinterpret_cast<{VT}*>(p0)[i];
+    const {VT} g = reinterpret_cast<const {VT}*>(p1)[i];
+    {VT} v = reinterpret_cast<{VT}*>(p2)[i];
+    {body}
+    reinterpret_cast<{VT}*>(p2)[i] = v;
+    reinterpret_cast<{VT}*>(p0)[i] = p;
+}}
+"""
+    return Kernel("sgd_mom", src, (_cdiv(nv, 256), 1, 1), (256, 1, 1), 0, 0)
+
+
 # ------------------------------------------------------------------------------------------------
 # RMSNorm (fused forward)
 # ------------------------------------------------------------------------------------------------

@@ -28,8 +28,10 @@ from dlgrad_b200.runtime.cuda import shim
 from dlgrad_b200.tensor import Tensor
 
 _state = {"rank": 0, "world": 1, "bucket": None, "bucket_elems": 0}
-# seconds a rank waits inside the fused step for a peer before it traps (a dead peer must not hang the node)
-PEER_TIMEOUT_S = float(os.environ.get("DLGRAD_DP_TIMEOUT_S", "20"))
+# seconds a rank waits inside the fused step for a peer before it traps (a dead peer must not hang the node).  The trap
+# is a sticky context failure on every waiting rank, so the limit is sized for a DEAD peer, not for ordinary skew: a
+# rank that evaluates, writes a checkpoint or JIT-compiles a cold kernel may legitimately be minutes late.
+PEER_TIMEOUT_S = float(os.environ.get("DLGRAD_DP_TIMEOUT_S", "600"))
 
 
 def unique_id() -> bytes:
@@ -243,6 +245,8 @@ class Adam:
         self.pack_view = [shim.ffi.cast("unsigned long long *", h) for h in self.pack_host]
         self.pack_dev = shim.alloc(8 * n)
         self.flip = 0
+        self.pack_events = [None, None]
+        self.pack_last = None
         shim.synchronize()
         if world > 1:
             all_gather_bytes(b"\0")                # nobody launches before every rank has mapped its peers
@@ -263,11 +267,23 @@ class Adam:
             if g is not None and g.metadata.device is not Device.CUDA:
                 g._to_cuda()
         if all(g is not None and g.aligned for g in grads):
-            self.flip ^= 1
-            view = self.pack_view[self.flip]
-            for i, g in enumerate(grads):
-                view[i] = shim.address(g.ptr)
-            shim.check(lib.dlg_h2d_async(self.pack_dev, self.pack_host[self.flip], 8 * len(grads)), "dlg_h2d_async")
+            table = [shim.address(g.ptr) for g in grads]
+            if table != self.pack_last:
+                # new gradient addresses: upload the table.  The staging buffer about to be rewritten may still belong
+                # to an H2D copy the device has not executed (the host runs ahead), so every upload is followed by an
+                # event that is waited for before its buffer is reused; an unchanged table is not uploaded at all.
+                self.flip ^= 1
+                f = self.flip
+                if self.pack_events[f] is not None:
+                    shim.check(lib.dlg_event_sync(self.pack_events[f]), "dlg_event_sync")
+                view = self.pack_view[f]
+                for i, a in enumerate(table):
+                    view[i] = a
+                shim.check(lib.dlg_h2d_async(self.pack_dev, self.pack_host[f], 8 * len(grads)), "dlg_h2d_async")
+                if self.pack_events[f] is None:
+                    self.pack_events[f] = lib.dlg_event_create()
+                shim.check(lib.dlg_event_record(self.pack_events[f]), "dlg_event_record")
+                self.pack_last = table
             self.pack.run_into(self.grads.fptr, self.pack_dev)
         else:
             for g, off, n in zip(grads, self.offs, self.sizes):

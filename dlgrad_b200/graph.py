@@ -21,7 +21,8 @@ How it stays correct
   * host round trips (numpy(), synchronize) raise inside a capture instead of silently recording something else.
   * random numbers (dropout) come from a counter-based device generator; inside a capture the counter base lives in
     device memory and a hook advances it before every replay, so every replay draws fresh masks.
-  * optimizer steps may be part of the captured call.  SGD's launch arguments never change.  Adam's bias corrections
+  * optimizer steps may be part of the captured call.  SGD's launch arguments never change (with momentum the velocity
+    is updated in place by the same kernel).  Adam's bias corrections
     1 - beta^t do: inside a capture Adam records its multi-tensor kernel in the form that reads them from device
     memory, and a hook advances `t` and rewrites those scalars (one tiny eager launch) before every replay.
   * a capture records, it does not execute: the warm-up calls before it are real steps, the captured call is not.
@@ -58,7 +59,9 @@ class CapturedStep:
             raise RuntimeError("dlg_pool_begin failed: " + shim.last_error())
         self.keep: list = []
         self.hooks: list = []                      # run before every replay (Adam: advance t, refresh its device scalars)
+        self.refs: list = []                       # device storage the graph reads by address but does not own (constants)
         shim.capture["on"], shim.capture["keep"], shim.capture["hooks"] = True, self.keep, self.hooks
+        shim.capture["refs"] = self.refs
         shim.capture["rng"] = {"n": 0, "hooked": False}   # random draws recorded in this step (runtime/cuda/ops.uniform)
         self.exec = shim.NULL
         try:
@@ -72,6 +75,7 @@ class CapturedStep:
                 self.exec = lib.dlg_graph_end()
         finally:
             shim.capture["on"], shim.capture["keep"], shim.capture["hooks"], shim.capture["rng"] = False, None, None, None
+            shim.capture["refs"] = None
             lib.dlg_pool_end()
         if self.exec == shim.NULL:
             raise RuntimeError("capturing the step failed: " + shim.last_error())
@@ -129,3 +133,4 @@ class CapturedStep:
             for pin in self.keep:
                 shim.lib.dlg_host_free(pin)
             self.keep = []
+            self.refs = []

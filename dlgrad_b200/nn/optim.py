@@ -58,13 +58,22 @@ class SGD(Optimizer):
     def step(self) -> None:
         if self.momentum == 0:
             return super().step()
-        self._before_inplace()
+        self._before_inplace([v.data for v in self.velocities.values()])
         for p in self.params:
             if p.grad is None:
                 continue
-            v = (self.velocities[id(p)] * self.momentum + p.grad).detach()
+            vel = self.velocities[id(p)]
+            dev = self._device_for(p.data, p.grad.data, vel.data)
+            if dev is Device.CUDA:
+                # velocity and parameter are updated IN PLACE by one kernel: the launch arguments are the same every
+                # step, so a captured step (dlgrad_b200/graph.py) replays it correctly; rebinding self.velocities to
+                # a fresh Tensor every step (the host form below) is a Python side effect a replay would not see
+                from dlgrad_b200.runtime.cuda import ops as cuda_ops
+                cuda_ops.sgd_momentum_step(p.data, p.grad.data, vel.data, float(_f32(self.lr)),
+                                           float(_f32(self.momentum)), self.grad_scale)
+                continue
+            v = (vel * self.momentum + p.grad).detach()
             self.velocities[id(p)] = v
-            dev = self._device_for(p.data, v.data)
             dispatcher.dispatch(op=CustomOps.SGD_STEP, device=dev, param=p.data, grad=v.data,
                                 lr=float(_f32(self.lr)), grad_scale=self.grad_scale)
 

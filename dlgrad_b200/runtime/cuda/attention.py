@@ -10,6 +10,7 @@ backward deferral.
 """
 from __future__ import annotations
 
+import math
 import os
 
 from dlgrad_b200.buffer import Buffer
@@ -129,7 +130,10 @@ def scores(q: Buffer, k: Buffer, scale: float, mask: Buffer, fill: float):
     if out == shim.NULL:
         raise RuntimeError("fused attention-scores launch failed: " + shim.last_error())
     res = shim.own(out, nbytes)
-    _fresh[shim.address(res)] = (bits, bits + Tq * Tk // 32, Tq, Tk)
+    if math.isinf(fill) and fill < 0:
+        # only a -inf fill makes the masked probabilities EXACTLY zero, which is what lets the GEMMs that read P skip
+        # the tiles the mask kills; with a finite fill (masked_fill(mask, -5.0)) P is dense and stays untagged
+        _fresh[shim.address(res)] = (bits, bits + Tq * Tk // 32, Tq, Tk)
     return res
 
 

@@ -821,18 +821,30 @@ def adam_multi(params: list, grads: list, ms: list, vs: list, beta1: float, beta
         if host[0] == NULL or host[1] == NULL:
             raise MemoryError("pinned staging allocation failed: " + shim.last_error())
         views = [ffi.cast("unsigned long long *", h) for h in host]
-        ent = _adam_tables[key] = {"plan": plan, "host": host, "views": views, "dev": shim.alloc(32 * n), "flip": 0}
-    ent["flip"] ^= 1
-    tab = ent["views"][ent["flip"]]
+        ent = _adam_tables[key] = {"plan": plan, "host": host, "views": views, "dev": shim.alloc(32 * n), "flip": 0,
+                                   "events": [None, None], "last": None}
     addr = shim.address
-    i = 0
+    table = []
     for p, g, m, v in zip(params, grads, ms, vs):
-        tab[i] = addr(_dev_ptr(p))
-        tab[i + 1] = addr(_dev_ptr(g))
-        tab[i + 2] = addr(_dev_ptr(m))
-        tab[i + 3] = addr(_dev_ptr(v))
-        i += 4
-    shim.check(lib.dlg_h2d_async(ent["dev"], ent["host"][ent["flip"]], 32 * len(sizes)), "dlg_h2d_async")
+        table += [addr(_dev_ptr(p)), addr(_dev_ptr(g)), addr(_dev_ptr(m)), addr(_dev_ptr(v))]
+    if table != ent["last"]:
+        # the addresses moved (first step, or the allocator handed out other gradient blocks): upload a new table.  The
+        # host does not wait for the device between steps, so the staging buffer about to be rewritten may belong to a
+        # copy that has not executed yet: each upload is followed by an event, and the event is waited for before its
+        # buffer is reused.  In the steady state the table is unchanged and nothing is uploaded at all.
+        ent["flip"] ^= 1
+        f = ent["flip"]
+        if ent["events"][f] is not None:
+            shim.check(lib.dlg_event_sync(ent["events"][f]), "dlg_event_sync")
+        tab = ent["views"][f]
+        for i, a in enumerate(table):
+            tab[i] = a
+        shim.check(lib.dlg_h2d_async(ent["dev"], ent["host"][f], 32 * len(sizes)), "dlg_h2d_async")
+        if not shim.capture["on"]:                 # a captured table is private to its graph and recorded exactly once
+            if ent["events"][f] is None:
+                ent["events"][f] = lib.dlg_event_create()
+            shim.check(lib.dlg_event_record(ent["events"][f]), "dlg_event_record")
+        ent["last"] = table
     ent["plan"].run_into(NULL, ent["dev"], NULL if scalars is None else scalars, NULL, NULL, bc1, bc2, lr, grad_scale)
     return True
 
@@ -856,6 +868,16 @@ def sgd_step(param: Buffer, grad: Buffer, lr: float, grad_scale: float = 1.0) ->
     if plan is None:
         plan = _plans[key] = Plan(ck.sgd_step(param.metadata.numel, ok))
     plan.run_into(NULL, _dev_ptr(param), _dev_ptr(grad), NULL, NULL, lr, 0.0, 0.0, grad_scale)
+
+
+def sgd_momentum_step(param: Buffer, grad: Buffer, vel: Buffer, lr: float, momentum: float, grad_scale: float = 1.0) -> None:
+    """SGD with momentum as ONE in-place kernel (velocity and parameter both updated where they live)."""
+    ok = param.aligned and grad.aligned and vel.aligned
+    key = ("sgd_mom", param.metadata.numel, ok)
+    plan = _plans.get(key)
+    if plan is None:
+        plan = _plans[key] = Plan(ck.sgd_momentum_step(param.metadata.numel, ok))
+    plan.run_into(NULL, _dev_ptr(param), _dev_ptr(grad), _dev_ptr(vel), NULL, lr, momentum, 0.0, grad_scale)
 
 
 @dispatcher.register(CustomOps.RMSNORM, CUDA)

@@ -141,7 +141,7 @@ _state = {"device": None}
 
 # set by dlgrad_b200/graph.py while a step is being captured into a CUDA graph: host round trips are illegal then
 # (the stream cannot be synchronised), and host data uploaded inside the step is staged in pinned memory the graph owns
-capture = {"on": False, "keep": None, "hooks": None, "rng": None}
+capture = {"on": False, "keep": None, "hooks": None, "rng": None, "refs": None}
 
 
 def no_capture(what: str) -> None:
