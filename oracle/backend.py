@@ -113,7 +113,7 @@ def _binary(name: str, x: Buffer, y: Buffer, out_shape=None):
     sy = get_broadcast_strides_2(oshape, ys, calculate_stride(ys))
     xa, ya = _np(x), _np(y)
     nd = len(oshape)
-    r = _ref(f"{name}_{nd}d") if (name != "lte" and 1 <= nd <= 4) else (_ref("cmp") if (name == "lte" and nd == 2) else None)
+    r = _ref(f"{name}_{nd}d") if (name != "lte" and 0 <= nd <= 4) else (_ref("cmp") if (name == "lte" and nd == 2) else None)
     if r is not None:
         _count("reference")
         if name == "lte":      # cmp_2d, cpu.py:835-862

@@ -59,7 +59,7 @@ def build_oracle(force: bool = False) -> str:
 # (file stem, generator name, args) — the kernels of SURVEY §2a that are on the hot path
 _REF_KERNELS = (
     [(f"{op}_{nd}d", "arithmetic", (op, nd)) for op in ("add", "sub", "mul", "div", "eq", "gt", "gte")
-     for nd in (1, 2, 3, 4)]
+     for nd in (0, 1, 2, 3, 4)]      # 0-d: scalar (op) scalar, e.g. (loss_real + loss_fake) / 2.0 of the GAN script
     + [(f"c_{f}", "utils", (f,)) for f in ("neg", "exp", "log", "pow", "sqrt", "rsqrt")]
     + [(f"reduce_{op}_{nd}d_axis{d}", "reduce_source", (op, nd, d))
        for op in ("sum", "max", "mean") for nd in (1, 2, 3, 4) for d in range(nd)]

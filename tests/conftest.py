@@ -41,6 +41,13 @@ def pytest_collection_modifyitems(config, items):
 
 
 def pytest_sessionfinish(session, exitstatus):
+    path = os.environ.get("DLGRAD_PARITY_REPORT")
+    if path and not COMPILE_ONLY:
+        import json
+        from tests import runner
+        with open(path, "w") as f:
+            for row in runner.REPORT:
+                f.write(json.dumps(row) + "\n")
     if COMPILE_ONLY:
         from dlgrad_b200.runtime.cuda import compiler
         n = compiler.flush_pending()

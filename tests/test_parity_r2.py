@@ -1,0 +1,208 @@
+"""Round-2 parity gates (`-m gpu`): the headline config's own shapes against the oracle and float64.
+
+VERDICT r1 "weak 1" listed the holes these close:
+  (a) one C5 transformer block (T=1024, C=768, h=12), B=1, forward + backward vs the oracle (oracle/_ref when built):
+      y, dx and all six weight gradients — the block bench.py's CPU arm times (`cpu_block_sample`);
+  (b) every GEMM shape of the bench line's `by_shape` list, through the variants that run inside the step
+      (plain NT / NN / TN, split-K, bias, relu operand A and B, relu-mask epilogue) vs float64;
+  (c) the full-width GAN of examples/mnist_gan.py:30-58 (G 128-256-512-1024-784, D 784-1024-512-256-1, batch 100),
+      one discriminator + one generator Adam step vs the oracle — including its N=1 / K=1 GEMMs;
+  (d) the C4 char-GPT loss curve over 30 Adam steps, CUDA vs oracle, tolerance stated in the test;
+  (e) an attention block with a FINITE mask fill (P is dense then; no tile may be skipped).
+"""
+import numpy as np
+import pytest
+
+from tests import models, runner
+from tests.conftest import COMPILE_ONLY, check
+
+pytestmark = pytest.mark.gpu
+
+
+def _weights_of_block(blk):
+    a = blk.attn
+    return {"q_proj": a.q_proj.weight, "k_proj": a.k_proj.weight, "v_proj": a.v_proj.weight, "c_proj(attn)": a.c_proj.weight,
+            "c_fc": blk.c_fc.weight, "c_proj(mlp)": blk.c_proj.weight}
+
+
+def test_c5_transformer_block_forward_backward_vs_oracle(oracle):
+    """(a) BASELINE configs[4] dimensions, one sequence: T = 1024, C = 768, 12 heads.  Every fusion of the headline
+    step engages at this size (tensor-core GEMMs at the bench shapes' N / K, fused attention, deferred relu, fused
+    RMSNorm).  Tolerances: activations and input gradient 1e-4 of the largest magnitude (matmul bound of the north
+    star), weight gradients 1e-4 as well (K = 1024 tokens summed)."""
+    import dlgrad_b200 as dl
+    from dlgrad_b200 import Tensor
+    cfg_kw = dict(vocab_size=96, block_size=1024, n_layer=12, n_head=12, n_embd=768)
+    x = (np.random.default_rng(0).random((1, 1024, 768), dtype=np.float32) - 0.5).astype(np.float32)
+    coef = np.linspace(0.5, 1.5, x.size, dtype=np.float32).reshape(x.shape)
+    res = {}
+    for dev in ("cuda", "cpu"):
+        cfg = models.GPTConfig(device=dev, **cfg_kw)
+        blk = models._Block(dl, cfg, np.random.default_rng(7))
+        xt = Tensor(x.copy(), requires_grad=True, device=dev)
+        y = blk(xt)
+        (y * Tensor(coef.copy(), device=dev)).sum().backward()
+        out = {"y": y.numpy(), "dx": xt.grad.numpy()}
+        for name, w in _weights_of_block(blk).items():
+            out["d" + name] = w.grad.numpy()
+        out["dln1"], out["dln2"] = blk.ln1.weight.grad.numpy(), blk.ln2.weight.grad.numpy()
+        res[dev] = out
+    for k in res["cpu"]:
+        runner.rel_check(check, res["cuda"][k], res["cpu"][k], runner.TOL_MATMUL, f"C5 block {k}")
+
+
+def _f64(a):
+    return np.asarray(a, dtype=np.float64)
+
+
+@pytest.mark.parametrize("rows,in_f,out_f,bias", [(8192, 768, 768, False), (8192, 768, 768, True), (8192, 768, 96, False)])
+def test_bench_linear_shapes_vs_float64(rows, in_f, out_f, bias):
+    """(b) the projection GEMMs of the C5 step through ops.Linear: forward x @ W^T (8192 x out x in, NT), dX = g @ W
+    (NN), dW = g^T @ x (TN; 768 x 768 x 8192 and 96 x 768 x 8192 run as in-kernel split-K), bias in the epilogue.
+    All against float64 (1e-4 of the largest magnitude; per-element figures are logged)."""
+    from dlgrad_b200 import Tensor
+    rng = np.random.default_rng(rows + in_f + out_f + int(bias))
+    x = (rng.random((rows, in_f), dtype=np.float32) - 0.5).astype(np.float32)
+    w = ((rng.random((out_f, in_f), dtype=np.float32) - 0.5) * 0.1).astype(np.float32)
+    b = (rng.random((1, out_f), dtype=np.float32) - 0.5).astype(np.float32)
+    g = (rng.random((rows, out_f), dtype=np.float32) - 0.5).astype(np.float32)
+    X = Tensor(x.copy(), device="cuda", requires_grad=True)
+    W = Tensor(w.copy(), device="cuda", requires_grad=True)
+    Bt = Tensor(b.copy(), device="cuda", requires_grad=True) if bias else None
+    y = X.linear(W, Bt)
+    (y * Tensor(g.copy(), device="cuda")).sum().backward()
+    ref = _f64(x) @ _f64(w).T + (_f64(b) if bias else 0.0)
+    runner.rel_check(check, y.numpy(), ref, runner.TOL_MATMUL, f"linear {rows}x{out_f}x{in_f} forward")
+    runner.rel_check(check, X.grad.numpy(), _f64(g) @ _f64(w), runner.TOL_MATMUL, f"linear {rows}x{in_f}x{out_f} dX")
+    runner.rel_check(check, W.grad.numpy(), _f64(g).T @ _f64(x), runner.TOL_MATMUL, f"linear {out_f}x{in_f}x{rows} dW")
+    if bias:
+        runner.rel_check(check, Bt.grad.numpy(), _f64(g).sum(0, keepdims=True), 1e-5, "linear db")
+
+
+def test_bench_mlp_block_shapes_vs_float64():
+    """(b) c_fc -> relu -> c_proj at the C5 sizes (8192 tokens, 768 -> 3072 -> 768): forward GEMMs 8192 x 3072 x 768 and
+    8192 x 768 x 3072 (A operand = deferred relu), backward dH = g @ W2 with the relu-mask epilogue, dW2 = g^T @ relu(h)
+    (B operand = deferred relu, 768 x 3072 x 8192 TN), dW1 = dH^T @ x (3072 x 768 x 8192 TN), dX = dH @ W1."""
+    from dlgrad_b200 import Tensor
+    rng = np.random.default_rng(3072)
+    x = (rng.random((8, 1024, 768), dtype=np.float32) - 0.5).astype(np.float32)
+    w1 = ((rng.random((3072, 768), dtype=np.float32) - 0.5) * 0.1).astype(np.float32)
+    w2 = ((rng.random((768, 3072), dtype=np.float32) - 0.5) * 0.1).astype(np.float32)
+    g = (rng.random((8, 1024, 768), dtype=np.float32) - 0.5).astype(np.float32)
+    X = Tensor(x.copy(), device="cuda", requires_grad=True)
+    W1 = Tensor(w1.copy(), device="cuda", requires_grad=True)
+    W2 = Tensor(w2.copy(), device="cuda", requires_grad=True)
+    y = X.linear(W1, None).relu().linear(W2, None)
+    (y * Tensor(g.copy(), device="cuda")).sum().backward()
+    x2, g2 = _f64(x).reshape(8192, 768), _f64(g).reshape(8192, 768)
+    h = x2 @ _f64(w1).T
+    r = np.maximum(h, 0.0)
+    dh = (g2 @ _f64(w2)) * (h > 0)
+    runner.rel_check(check, y.numpy().reshape(8192, 768), r @ _f64(w2).T, runner.TOL_MATMUL, "mlp forward")
+    runner.rel_check(check, W2.grad.numpy(), g2.T @ r, runner.TOL_MATMUL, "mlp dW2 (relu operand B)")
+    runner.rel_check(check, W1.grad.numpy(), dh.T @ x2, runner.TOL_MATMUL, "mlp dW1 (through the relu-mask epilogue)")
+    runner.rel_check(check, X.grad.numpy().reshape(8192, 768), dh @ _f64(w1), runner.TOL_MATMUL, "mlp dX")
+
+
+def test_full_width_gan_step_vs_oracle(oracle):
+    """(c) examples/mnist_gan.py:30-58 at full width, batch 100: one discriminator step and one generator step with
+    Adam(5e-4, betas (0.5, 0.999)) on Device.CUDA vs the oracle.  Includes the N = 1 output GEMM of the discriminator
+    and its K = 1 backward.  Tolerances: losses 1e-5; first-step gradients 1e-4 of their largest magnitude; updated
+    weights: Adam moves every element by ~lr whatever its gradient, so elements whose gradient is rounding noise may
+    differ by 2 * lr (stated absolute bound)."""
+    import dlgrad_b200 as dl
+    from dlgrad_b200 import Tensor, nn
+    data = np.random.default_rng(11)
+    real = (data.random((100, 784), dtype=np.float32) * 2 - 1).astype(np.float32)
+    noise1 = (data.random((100, 128), dtype=np.float32) * 2 - 1).astype(np.float32)
+    noise2 = (data.random((100, 128), dtype=np.float32) * 2 - 1).astype(np.float32)
+    res = {}
+    for dev in ("cuda", "cpu"):
+        gan = models.GANPair(dl, dev, np.random.default_rng(1))
+        opt_g = nn.optim.Adam(nn.utils.get_parameters(gan.g_layers), lr=0.0005, betas=(0.5, 0.999))
+        opt_d = nn.optim.Adam(nn.utils.get_parameters(gan.d_layers), lr=0.0005, betas=(0.5, 0.999))
+        T = lambda a: Tensor(np.array(a), device=dev)     # noqa: E731
+        fake = gan.generator(T(noise1)).detach()
+        opt_d.zero_grad()
+        d_loss = (gan.discriminator(T(real)).bcewithlogitsloss(Tensor.full((100, 1), 1.0, device=dev))
+                  + gan.discriminator(fake).bcewithlogitsloss(Tensor.full((100, 1), 0.0, device=dev))) / 2.0
+        d_loss.backward()
+        gd = [gan.d_layers[0].weight.grad.numpy(), gan.d_layers[3].weight.grad.numpy(), gan.d_layers[3].bias.grad.numpy()]
+        opt_d.step()
+        opt_g.zero_grad()
+        g_loss = gan.discriminator(gan.generator(T(noise2))).bcewithlogitsloss(Tensor.full((100, 1), 1.0, device=dev))
+        g_loss.backward()
+        gg = [gan.g_layers[0].weight.grad.numpy(), gan.g_layers[3].weight.grad.numpy()]
+        opt_g.step()
+        res[dev] = dict(d_loss=np.array(float(d_loss.numpy())), g_loss=np.array(float(g_loss.numpy())), fake=fake.numpy(),
+                        gd0=gd[0], gd3=gd[1], gdb3=gd[2], gg0=gg[0], gg3=gg[1],
+                        d_w3=gan.d_layers[3].weight.numpy(), g_w0=gan.g_layers[0].weight.numpy())
+    a, b = res["cuda"], res["cpu"]
+    for k in ("d_loss", "g_loss"):
+        runner.rel_check(check, a[k], b[k], 1e-5, f"GAN {k}")
+    runner.rel_check(check, a["fake"], b["fake"], runner.TOL_MATMUL, "GAN generator output (tanh)")
+    for k in ("gd0", "gd3", "gdb3", "gg0", "gg3"):
+        runner.rel_check(check, a[k], b[k], runner.TOL_MATMUL, f"GAN first-step gradient {k}")
+    for k in ("d_w3", "g_w0"):
+        check(a[k], b[k], rtol=1e-5, atol=2 * 0.0005, what=f"GAN updated weight {k}")
+
+
+@pytest.mark.timeout(900)
+def test_c4_char_gpt_loss_curve_30_steps_vs_oracle(oracle):
+    """(d) BASELINE configs[3] (n_layer 6, n_head 4, n_embd 128, block 128, batch 16, V 96), 30 Adam steps (lr 1e-4) on
+    the same 4 rotating batches, Device.CUDA vs the oracle.  Stated tolerance on the loss curve: 2e-4 relative at every
+    step — Adam's update is ~ +-lr per element whatever the size of its gradient, so elements whose gradient is
+    rounding noise drift apart by up to lr per step; the LOSS, which depends on all of them, is the quantity the
+    north star bounds ("within a stated tolerance on loss curves").  The first step, which depends on no update, is
+    held to 1e-5."""
+    import dlgrad_b200 as dl
+    from dlgrad_b200 import Tensor, nn
+    steps = 2 if COMPILE_ONLY else 30          # walking the test to pre-build its kernels needs no curve
+    curves = {}
+    for dev in ("cuda", "cpu"):
+        cfg = models.GPTConfig(vocab_size=96, block_size=128, n_layer=6, n_head=4, n_embd=128, device=dev)
+        gpt = models.GPT(dl, cfg, np.random.default_rng(4))
+        brng = np.random.default_rng(5)
+        batches = [models.gpt_batch(cfg, 16, brng) for _ in range(4)]
+        opt = nn.optim.Adam(nn.utils.get_parameters(gpt), lr=1e-4)
+        losses = []
+        for step in range(steps):
+            xb, yb = batches[step % 4]
+            opt.zero_grad()
+            _, loss = gpt(Tensor(xb.copy(), device=dev), Tensor(yb.copy(), device=dev))
+            losses.append(float(loss.numpy()))
+            loss.backward()
+            opt.step()
+        curves[dev] = np.array(losses)
+    if COMPILE_ONLY:
+        return
+    a, b = curves["cuda"], curves["cpu"]
+    rel = np.abs(a - b) / np.abs(b)
+    print(f"\nC4 loss curve: first {b[0]:.3f} last {b[-1]:.3f}; max relative deviation {rel.max():.3g} at step {int(rel.argmax())}")
+    assert b[-1] < b[0], "the oracle's loss must go down over 30 steps"
+    assert rel[0] <= 1e-5, f"step 0 loss differs by {rel[0]:.3g}"
+    assert rel.max() <= 2e-4, f"loss curve deviates by {rel.max():.3g} (step {int(rel.argmax())}); stated tolerance 2e-4"
+
+
+@pytest.mark.parametrize("fill", [-5.0, 0.0])
+def test_attention_with_finite_mask_fill_is_dense(oracle, fill):
+    """(e) masked_fill(mask, finite) leaves NON-zero probabilities in the masked tiles: the GEMMs that read P must not
+    skip them (ADVICE r1 — only a -inf fill makes the dead tiles exactly zero).  y, dq, dk, dv vs the oracle at a size
+    where every attention fusion engages (B*H*T*T = 4 Mi scores)."""
+    from dlgrad_b200 import Tensor
+    B, H, T, D = 1, 16, 512, 64
+    rng = np.random.default_rng(99)
+    q, k, v = ((rng.random((B, H, T, D), dtype=np.float32) - 0.5).astype(np.float32) for _ in range(3))
+    mask = np.triu(np.ones((T, T), dtype=np.float32), 1)
+    w = np.linspace(0.5, 1.5, B * H * T * D, dtype=np.float32).reshape(B, H, T, D)
+    scale = float(1.0 / np.sqrt(D))
+
+    def run(dev):
+        Q, K, V = (Tensor(a.copy(), device=dev, requires_grad=True) for a in (q, k, v))
+        att = ((Q @ K.transpose(2, 3)) * scale).masked_fill(Tensor(mask.copy(), device=dev), fill).softmax(dim=3)
+        y = att @ V
+        (y * Tensor(w.copy(), device=dev)).sum().backward()
+        return [y.numpy(), Q.grad.numpy(), K.grad.numpy(), V.grad.numpy()]
+    got, ref = run("cuda"), run("cpu")
+    for a, b, what in zip(got, ref, ("y", "dq", "dk", "dv")):
+        runner.rel_check(check, a, b, 1e-4, f"attention with fill {fill}: {what} vs oracle")
