@@ -153,28 +153,67 @@ def cpu_equiv_steps_per_s(block_seconds: float, cfg_kw: dict, batch: int) -> flo
     return 1.0 / step_seconds
 
 
+_cpu_model: dict = {}
+
+
+def cpu_full_step_sample(cfg_kw: dict) -> tuple[float, str]:
+    """Seconds for ONE complete train step (forward + backward + Adam, all layers, embedding, head, loss) of the
+    benchmark config at batch 1 on the CPU oracle — 1/B of the workload's step, measured, not extrapolated."""
+    import dlgrad_b200 as dl
+    from dlgrad_b200 import Tensor, nn
+    from oracle import backend
+    backend.install()
+    key = tuple(sorted(cfg_kw.items()))
+    if key not in _cpu_model:
+        cfg = models.GPTConfig(device="cpu", **cfg_kw)
+        gpt = models.GPT(dl, cfg, np.random.default_rng(0))
+        params = nn.utils.get_parameters(gpt)
+        _cpu_model[key] = (cfg, gpt, nn.optim.Adam(params, lr=1e-4), np.random.default_rng(1000))
+    cfg, gpt, opt, rng = _cpu_model[key]
+    xb, yb = models.gpt_batch(cfg, 1, rng)
+    t0 = time.perf_counter()
+    opt.zero_grad()
+    _, loss = gpt(Tensor(xb), Tensor(yb))
+    loss.backward()
+    opt.step()
+    _ = float(loss.numpy())
+    dt = time.perf_counter() - t0
+    return dt, (f"one full train step (all {cfg.n_layer} layers, embeddings, head, loss, Adam) at batch 1 "
+                f"(T={cfg.block_size}, C={cfg.n_embd}) on {cpu_kind_text()}, single thread")
+
+
 def run_reference(args) -> None:
+    """The reference's CPU path on the benchmark config.  One timed "step" of this arm is a BOUNDED SAMPLE of the
+    workload's step: the complete train step at batch 1 (the workload's batch is `--batch` independent sequences, the
+    CPU path is single-threaded and linear in the batch), so `ms_per_step` is the measured time of one sample and
+    `value` = 1 / (batch x sample seconds).  At most `--steps` samples, and no more than fit in REF_BUDGET_S seconds;
+    the warm-up is one transformer-block sample (it loads every kernel), which also cross-checks the full step."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cfg_kw = C5 if args.config == "c5" else C4
-    times = []
-    sample = ""
-    for i in range(args.warmup + args.steps):
-        t, sample = cpu_block_sample(cfg_kw)
-        if i >= args.warmup:
-            times.append(t)
-        if sum(times) > 240:      # keep the whole run within a few minutes
+    budget = float(os.environ.get("DLGRAD_REF_BUDGET_S", "150"))
+    t_block, _ = cpu_block_sample(cfg_kw)                       # warm-up: every kernel of the step loaded and run once
+    times, sample, t_start = [], "", time.perf_counter()
+    while len(times) < max(1, args.steps):
+        t, sample = cpu_full_step_sample(cfg_kw)
+        times.append(t)
+        if time.perf_counter() - t_start + t > budget:           # the next sample would overrun the budget
             break
-    per_gpu = cpu_equiv_steps_per_s(float(np.mean(times)), cfg_kw, args.batch)
-    value = per_gpu           # the CPU path does not scale with --gpus: one host, one thread
+    mean = float(np.mean(times))
+    value = 1.0 / (mean * args.batch)     # the CPU path does not scale with --gpus: one host, one thread
+    extrap = cpu_equiv_steps_per_s(t_block, cfg_kw, args.batch)
     line = {
         "impl": "reference", "metric": "gpt_train_steps_per_s", "value": value, "unit": "steps/s",
-        "n_gpus": args.gpus, "steps": len(times), "warmup": args.warmup, "ms_per_step": 1000.0 / value,
+        "n_gpus": args.gpus, "steps": len(times), "warmup": 1, "ms_per_step": 1000.0 * mean,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(cfg_kw, args.batch, args.gpus),
-        "cpu_baseline": {"value": value, "unit": "steps/s", "cores": 1, "kind": cpu_kind(), "sample": sample
-                         + f"; {len(times)} samples, mean {np.mean(times):.2f} s, scaled by L x B x FLOP share"},
+        "cpu_baseline": {"value": value, "unit": "steps/s", "cores": 1, "kind": cpu_kind(),
+                         "sample": sample + f"; {len(times)} samples, mean {mean:.2f} s each; value = 1 / ({args.batch} x "
+                                            f"sample): the workload's step is {args.batch} such sequences and the reference "
+                                            "is single-threaded",
+                         "cross_check": {"block_sample_s": t_block, "extrapolated_steps_per_s": extrap,
+                                         "ratio_measured_over_extrapolated": value / extrap}},
         "e2e": {"value": value, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "host": {"cpu_count": os.cpu_count()},
     }
@@ -237,9 +276,20 @@ def op_microbench(peaks: dict, only: tuple | None = None) -> dict:
              ("sum_all", lambda i: a[i].sum(), one, "GB/s"),
              ("exp", lambda i: a[i].exp(), half, "GB/s"), ("transpose", lambda i: a[i].permute((1, 0)), half, "GB/s"),
              ("softmax_rows", lambda i: a[i].softmax(dim=1), half, "GB/s"),
-             ("matmul_4096", lambda i: a[i] @ b[i], 2.0 * n ** 3, "TFLOP/s")]
+             ("matmul_4096", lambda i: a[i] @ b[i], 2.0 * n ** 3, "TFLOP/s"),
+             # the two backward GEMMs of configs[1]'s "matmul 4096^3 fwd+bwd", as MatMul.backward issues them: the
+             # stored operands are read transposed inside the kernel (no materialised transposes)
+             ("matmul_4096_bwd_dA", lambda i: mm_t(a[i], b[i], trans_y=True), 2.0 * n ** 3, "TFLOP/s"),
+             ("matmul_4096_bwd_dB", lambda i: mm_t(a[i], b[i], trans_x=True), 2.0 * n ** 3, "TFLOP/s")]
     out = {}
     scratch = [shim.alloc(one) for _ in range(SETS)]
+
+    def mm_t(x, y, **kw):
+        from dlgrad_b200.buffer import Buffer
+        from dlgrad_b200.device import Device
+        from dlgrad_b200.dispatch import dispatcher
+        from dlgrad_b200.helpers import BinaryOps
+        return Buffer(dispatcher.dispatch(op=BinaryOps.MATMUL, device=Device.CUDA, x=x.data, y=y.data, **kw), (n, n), Device.CUDA)
 
     def timed(fn, rounds):
         """Seconds per launch.  The ROUNDS x SETS launches are captured into ONE CUDA graph and the graph is
@@ -283,6 +333,11 @@ def op_microbench(peaks: dict, only: tuple | None = None) -> dict:
             ach = work / t / 1e12
             out[name] = {"achieved": ach, "unit": unit, "ms": t * 1e3,
                          "frac_of_3xtf32_peak": ach / (peaks["bf16_burst"] / 6.0)}
+    if all(k in out for k in ("matmul_4096", "matmul_4096_bwd_dA", "matmul_4096_bwd_dB")):
+        ms = sum(out[k]["ms"] for k in ("matmul_4096", "matmul_4096_bwd_dA", "matmul_4096_bwd_dB"))
+        ach = 3 * 2.0 * n ** 3 / (ms * 1e-3) / 1e12
+        out["matmul_4096_fwd_bwd"] = {"achieved": ach, "unit": "TFLOP/s", "ms": ms, "gflop": 3 * 2.0 * n ** 3 / 1e9,
+                                      "frac_of_3xtf32_peak": ach / (peaks["bf16_burst"] / 6.0)}
     shim.synchronize()
     return out
 
@@ -390,8 +445,18 @@ def run_b200(args) -> None:
             _ = float((fill @ fill).sum().numpy())
     clocks.__exit__(None, None, None)
 
+    replicas_identical = None
     if dist is not None:      # max over ranks; launches summed over ranks
         import torch
+        import zlib
+        # correctness of the data-parallel step travels with the speed: every rank hashes its parameters (all bytes,
+        # after the timed steps) and the hashes must agree — replicas that drifted apart would make `value` meaningless
+        crc = 0
+        for p in params:
+            crc = zlib.crc32(p.numpy().tobytes(), crc)
+        hashes = [None] * world
+        dist.all_gather_object(hashes, crc)
+        replicas_identical = len(set(hashes)) == 1
         t = torch.tensor([ms_a, ms_b], dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_a, ms_b = float(t[0]), float(t[1])
@@ -405,6 +470,20 @@ def run_b200(args) -> None:
 
     value = world * args.steps / (ms_a * 1e-3)
     e2e = world * args.steps / (ms_b * 1e-3)
+    # dense GEMMs vs attention-class kernels (fused attention + the GEMMs that skip masked tiles): the latter are
+    # credited their NOMINAL (dense) flops by the per-launch timer; under the causal mask only (nq + 1) / (2 nq) of the
+    # 128 x 128 tile pairs are executed, so both figures are reported
+    nq = cfg.block_size // 128
+    live = (nq + 1) / (2.0 * nq) if nq else 1.0
+    split = {"dense": [0.0, 0.0, 0], "attention": [0.0, 0.0, 0]}
+    for t, v in mm["by_tag"].items():
+        cls = "attention" if (str(t[0]).startswith("attn") or "_sp" in str(t[0])) else "dense"
+        split[cls][0] += v[2]
+        split[cls][1] += v[1]
+        split[cls][2] += v[0]
+
+    def _tf(work, ms):
+        return work / (ms * 1e-3) / 1e12 if ms > 0 else None
     flops_step = models.gpt_train_flops(cfg, args.batch)
     mm_tflops = (mm["work"] / (mm["ms"] * 1e-3) / 1e12) if mm["ms"] > 0 else 0.0
     peak_3xtf32 = peaks["bf16_sustained"] / 6.0      # TF32 dense = bf16/2, three MMAs per product
@@ -430,18 +509,47 @@ def run_b200(args) -> None:
                      "peak_note": f"3xTF32 = sustained bf16 {peaks['bf16_sustained']} TF/s / 6 ({peaks['source']}: "
                                   "MEASURED_PEAKS.json has no TF32 entry; TF32 dense = bf16/2, 3 MMAs per product)",
                      "matmul_share_of_step": mm["ms"] / ms_a if ms_a else None, "matmul_launches": mm["launches"],
+                     "tf32_in_box_note": "cuBLAS TF32 measured on a B200 of this pool: 723 burst / 599 sustained TFLOP/s "
+                                         "(profiles/r01_tf32_peak_cublas.txt), i.e. 241 / 200 for 3xTF32; the stricter "
+                                         "bf16/6 figure is the denominator used",
+                     "split": {
+                         "dense_gemms": {"launches": split["dense"][2], "ms_per_step": split["dense"][1] / args.steps,
+                                         "tflops": _tf(split["dense"][0], split["dense"][1]),
+                                         "frac": (_tf(split["dense"][0], split["dense"][1]) or 0.0) / peak_3xtf32},
+                         "attention_class": {"launches": split["attention"][2], "ms_per_step": split["attention"][1] / args.steps,
+                                             "nominal_tflops": _tf(split["attention"][0], split["attention"][1]),
+                                             "executed_tflops": _tf(split["attention"][0] * live, split["attention"][1]),
+                                             "executed_fraction_of_nominal": live,
+                                             "frac_executed": (_tf(split["attention"][0] * live, split["attention"][1]) or 0.0) / peak_3xtf32,
+                                             "note": "fused attention kernels and tile-skipping GEMMs; the causal mask kills "
+                                                     f"{nq * (nq - 1) // 2} of {nq * nq} 128x128 tile pairs per head"}},
                      "by_shape": [{"kernel": t[0], "M": t[1], "N": t[2], "K": t[3], "batch": t[4], "launches": v[0],
                                    "ms_per_step": v[1] / args.steps, "tflops": v[2] / (v[1] * 1e-3) / 1e12 if v[1] else None}
                                   for t, v in sorted(mm["by_tag"].items(), key=lambda kv: -kv[1][1])[:12]]},
     }
-    if world == 1 and not args.no_cpu:
-        t, sample = cpu_block_sample(cfg_kw)
-        v = cpu_equiv_steps_per_s(t, cfg_kw, args.batch)
-        line["cpu_baseline"] = {"value": v, "unit": "steps/s", "cores": 1, "kind": cpu_kind(),
-                                "sample": sample + f" ({t:.2f} s), scaled by L x B x FLOP share; host has {os.cpu_count()} cores, "
-                                "the reference is single-threaded"}
+    if world > 1:
+        line["replicas_identical"] = replicas_identical
     if world == 1 and not args.no_ops:
         line["ops"] = op_microbench(peaks)
+    if world == 1 and not args.no_small:
+        # BASELINE configs[0], [2], [3] — the reference's own CPU-sized workloads — eager and as captured CUDA graphs
+        # (host-dispatch bound; scripts/small_configs.py has the full per-config report incl. the CPU arm)
+        from scripts import small_configs as sc
+        small = {}
+        for name, what, make, n_gpu, _ in sc.CONFIGS:
+            g, c = sc.gpu_arm(make, max(10, n_gpu // 2)), sc.graph_arm(make, max(10, n_gpu // 2))
+            small[name] = {"config": what, "unit": "steps/s", "eager": g["value"], "eager_e2e": g["e2e"],
+                           "launches_per_step": g["launches_per_step"], "us_per_launch": g["us_per_launch"],
+                           "captured": c["value"], "captured_e2e": c["e2e"]}
+        line["small_configs"] = small
+    if world == 1 and not args.no_cpu:
+        # last: installing the CPU arm registers a host runtime, which changes where default-device tensors live
+        t, sample = cpu_block_sample(cfg_kw, repeats=3)
+        v = cpu_equiv_steps_per_s(t, cfg_kw, args.batch)
+        line["cpu_baseline"] = {"value": v, "unit": "steps/s", "cores": 1, "kind": cpu_kind(),
+                                "sample": sample + f" (best of 3: {t:.2f} s), scaled by L x B x FLOP share — `--impl reference` "
+                                f"measures whole batch-1 steps and reports how well this extrapolation holds; host has "
+                                f"{os.cpu_count()} cores, the reference is single-threaded"}
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
@@ -457,6 +565,7 @@ def main() -> None:
     ap.add_argument("--batch", type=int, default=8)
     ap.add_argument("--no-ops", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-small", action="store_true", help="skip the configs[0]/[2]/[3] extras (MLP, GAN, char-GPT)")
     ap.add_argument("--prebuild", action="store_true", help="compile-only census (used by __graft_entry__.build)")
     ap.add_argument("--ops-only", action="store_true", help="run only the configs[1] op microbenches")
     ap.add_argument("--profile", action="store_true", help="per-kernel-family CUDA-event breakdown of 3 steps (not a bench value)")
