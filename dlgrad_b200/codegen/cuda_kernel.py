@@ -1299,6 +1299,59 @@ extern "C" __global__ void __launch_bounds__(256) {KNAME}{SIG_ALIAS} {{
 
 
 @cache
+def sample_rows(rows: int, stride_rows: int, V: int) -> Kernel:
+    """out[r] = index drawn from softmax(x[r, :] / f0): the sampling step of examples/gpt.py:262-266 (`logits / temperature`,
+    subtract the max, exp, normalise, np.random.choice) as ONE block per row, so the V probabilities never travel to the
+    host — only the chosen index does (or nothing at all, when it is fed straight back into the embedding).
+    p0 = logits, row r starts at p0 + r * stride_rows (the last token of every sequence of a (B, T, V) tensor);
+    p1 = one uniform number in [0, 1) per row (uniform_philox).  Inverse CDF like numpy's choice(): the first index whose
+    running sum of e_i exceeds u * sum(e); thread t owns the contiguous chunk [t * per, (t + 1) * per), chunk sums are
+    scanned in thread order, so the result is deterministic for a given u."""
+    T = 256
+    per = _cdiv(V, T)
+    src = f"""
+extern "C" __global__ void __launch_bounds__({T}) {KNAME}{SIG} {{
+    __shared__ float red[{T}];
+    __shared__ float pre[{T} + 1];
+    const unsigned r = blockIdx.x, t = threadIdx.x;
+    const float* x = p0 + (size_t)r * {stride_rows}u;
+    const unsigned lo = t * {per}u, hi = min(lo + {per}u, {V}u);
+    const float temp = f0;
+    float m = __int_as_float(0xff800000);
+    for (unsigned i = lo; i < hi; ++i) m = fmaxf(m, __fdiv_rn(x[i], temp));
+    red[t] = m;
+    __syncthreads();
+    for (unsigned s = {T // 2}u; s > 0u; s >>= 1) {{ if (t < s) red[t] = fmaxf(red[t], red[t + s]); __syncthreads(); }}
+    m = red[0];
+    __syncthreads();
+    float mine = 0.f;
+    for (unsigned i = lo; i < hi; ++i) mine += expf(__fdiv_rn(x[i], temp) - m);
+    red[t] = mine;
+    __syncthreads();
+    if (t == 0) {{
+        float acc = 0.f;
+        for (unsigned j = 0; j < {T}u; ++j) {{ pre[j] = acc; acc += red[j]; }}
+        pre[{T}] = acc;
+    }}
+    __syncthreads();
+    const float target = p1[r] * pre[{T}];
+    // the chunk whose running sum first exceeds the target; the LAST non-empty chunk catches target == total (u -> 1)
+    const bool mine_is_it = lo < hi && pre[t] <= target && (target < pre[t + 1] || hi == {V}u);
+    if (mine_is_it) {{
+        float acc = pre[t];
+        unsigned pick = hi - 1u;
+        for (unsigned i = lo; i < hi; ++i) {{
+            acc += expf(__fdiv_rn(x[i], temp) - m);
+            if (target < acc) {{ pick = i; break; }}
+        }}
+        out[r] = (float)pick;
+    }}
+}}
+"""
+    return Kernel("sample_rows", src, (rows, 1, 1), (T, 1, 1), 0, rows)
+
+
+@cache
 def set_call_base() -> Kernel:
     """word 2 of the RNG state at `out` = f0 + 2^24 * f1: the call number the next replay of a captured graph starts from."""
     src = f"""

@@ -484,6 +484,32 @@ def uniform(shape: tuple, low: float = 0.0, high: float = 1.0) -> CDataPtr:
     return plan.run(state, NULL, NULL, NULL, float(low), float(high), float(call & 0xFFFFFF), float((call >> 24) & 0xFFFFFF))
 
 
+def sample_last(x: Buffer, temperature: float = 1.0, u: Buffer | None = None) -> CDataPtr:
+    """One index per sequence, drawn on the device from softmax(x[..., -1, :] / temperature) — the sampling step of
+    examples/gpt.py:216-221,262-266, which the reference does on the host after a D2H of the logits.  x is (V,), (B, V)
+    or (B, T, V); returns B floats holding the indices.  `u` (B uniform numbers) may be supplied for testing; by
+    default they come from the backend's Philox stream (manual_seed)."""
+    shape = x.metadata.shape
+    V = shape[-1]
+    if len(shape) == 3:
+        rows, stride, first = shape[0], shape[1] * V, (shape[1] - 1) * V
+    elif len(shape) == 2:
+        rows, stride, first = shape[0], V, 0
+    elif len(shape) == 1:
+        rows, stride, first = 1, V, 0
+    else:
+        raise ValueError(f"sample_last expects (V,), (B, V) or (B, T, V) logits, got {shape}")
+    if not temperature > 0.0:
+        raise ValueError("temperature must be positive")
+    if u is None:
+        u = Buffer(uniform((rows,)), (rows,), CUDA)
+    key = ("sample_rows", rows, stride, V)
+    plan = _plans.get(key)
+    if plan is None:
+        plan = _plans[key] = Plan(ck.sample_rows(rows, stride, V))
+    return plan.run(_dev_ptr(x) + first, _dev_ptr(u), NULL, NULL, float(temperature))
+
+
 # ------------------------------------------------------------------------------------------------
 # reductions                                                  reference: cpu.py:605-761,911-959
 # ------------------------------------------------------------------------------------------------

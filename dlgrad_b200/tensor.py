@@ -327,6 +327,28 @@ class Tensor:
             other = Tensor(other)
         return ops.Where.execute(cond, inp, other)
 
+    def sample_last(self, temperature: float = 1.0, u: "Tensor | None" = None) -> "Tensor":
+        """Draw the next token of every sequence from softmax(self[..., -1, :] / temperature) ON THE DEVICE and return
+        the indices as a (B, 1) float tensor (like argmax).  Extension for the inference path: the reference's
+        generate loops (examples/gpt.py:216-221, 262-266) copy the logits to the host and call np.random.choice for
+        every token; with this op only the chosen index crosses PCIe — or nothing, when the result is fed straight back
+        into the embedding.  On a host runtime (the test oracle) the same inverse-CDF rule runs in numpy."""
+        import numpy as np
+        rows = 1 if self.ndim == 1 else self.shape[0]
+        if self._on_host_runtime():
+            x = self.numpy().reshape(rows, -1, self.shape[-1])[:, -1, :].astype(np.float32)
+            un = (np.random.default_rng().random(rows) if u is None else u.numpy().reshape(rows)).astype(np.float32)
+            z = (x / np.float32(temperature)).astype(np.float32)
+            e = np.exp(z - z.max(axis=1, keepdims=True)).astype(np.float64)
+            cdf = np.cumsum(e, axis=1)
+            pick = [min(int(np.searchsorted(cdf[r], float(un[r]) * cdf[r, -1], side="right")), x.shape[1] - 1) for r in range(rows)]
+            return Tensor(np.array(pick, dtype=np.float32).reshape(rows, 1))
+        self.data._to_cuda()
+        if u is not None:
+            u.data._to_cuda()
+        ptr = _cuda_runtime.sample_last(self.data, float(temperature), None if u is None else u.data)
+        return Tensor(Buffer(ptr, (rows, 1), _CUDA, self.dtype))
+
     def detach(self) -> "Tensor":
         return Tensor(self.data, requires_grad=False)
 

@@ -164,3 +164,38 @@ def gpt_train_flops(cfg: GPTConfig, batch: int, T: int | None = None) -> float:
     T = T or cfg.block_size
     C, L, V = cfg.n_embd, cfg.n_layer, cfg.vocab_size
     return 3.0 * (L * (24.0 * batch * T * C * C + 4.0 * batch * T * T * C) + 2.0 * batch * T * C * V)
+
+
+def generate_on_device(gpt: GPT, idx, max_new_tokens: int, temperature: float = 0.7):
+    """The KV-cache decode loop of examples/gpt.py:131-153,173-229 with nothing but token indices leaving the device:
+    keys / values are appended with Tensor.cat, the next token is drawn with Tensor.sample_last and fed straight back
+    into the embedding.  `idx` is a (1, T0) prompt; returns the (1, T0 + max_new_tokens) token tensor."""
+    Tensor = type(idx)
+    cfg = gpt.cfg
+    dev = idx.device
+    prompt = idx.numpy().reshape(-1) if idx.shape[1] > 1 else None
+    caches = [None] * len(gpt.blocks)
+    toks = idx
+    n_prompt = idx.shape[1]
+    cur = idx if n_prompt == 1 else Tensor(np.array([[prompt[0]]], dtype=np.float32), device=dev)
+    for pos in range(n_prompt + max_new_tokens - 1):
+        x = gpt.wte(cur) + gpt.wpe(Tensor(np.array([float(pos)], dtype=np.float32), device=dev))
+        for i, blk in enumerate(gpt.blocks):
+            a = blk.attn
+            h = blk.ln1(x)
+            q = a.q_proj(h).reshape((1, 1, a.n_head, a.head_dim)).transpose(1, 2)
+            k = a.k_proj(h).reshape((1, 1, a.n_head, a.head_dim)).transpose(1, 2)
+            v = a.v_proj(h).reshape((1, 1, a.n_head, a.head_dim)).transpose(1, 2)
+            if caches[i] is not None:
+                k, v = Tensor.cat([caches[i][0], k], dim=2), Tensor.cat([caches[i][1], v], dim=2)
+            caches[i] = (k, v)
+            att = ((q @ k.transpose(2, 3)) * a.scale).softmax(dim=3)
+            y = (att @ v).transpose(1, 2).reshape((1, 1, cfg.n_embd))
+            x = x + a.c_proj(y)
+            x = x + blk.c_proj(blk.c_fc(blk.ln2(x)).relu())
+        if pos + 1 < n_prompt:
+            cur = Tensor(np.array([[prompt[pos + 1]]], dtype=np.float32), device=dev)
+            continue
+        cur = gpt.lm_head(gpt.ln_f(x)).sample_last(temperature)      # (1, 1) index tensor, stays on the device
+        toks = Tensor.cat([toks, cur], dim=1)
+    return toks

@@ -240,3 +240,16 @@ def test_one_mma_issuing_warp_by_default(monkeypatch):
     assert narrow.bn <= 96 and narrow.threads == 448 and "warp == 14" not in narrow.source
     two = tc.matmul_tc_ts(1024, 64, 1024, 96, False, False, False, False, issuers=2)
     assert two.threads == 480 and "warp == 14" in two.source
+
+
+def test_sample_last_on_the_host_runtime_is_the_inverse_cdf(oracle):
+    """Tensor.sample_last on a host runtime (the oracle): inverse CDF of softmax(x[..., -1, :] / temperature) with the
+    supplied uniform numbers — the rule the CUDA kernel implements (tests/test_parity_r2.py checks it on the device)."""
+    import numpy as np
+    from dlgrad_b200 import Tensor
+    x = np.zeros((2, 3, 4), dtype=np.float32)
+    x[0, -1] = [0.0, np.log(2.0), np.log(3.0), np.log(4.0)]          # probabilities 0.1 0.2 0.3 0.4
+    x[1, -1] = [5.0, -50.0, -50.0, -50.0]
+    for u, want in ((0.05, 0), (0.15, 1), (0.45, 2), (0.75, 3), (0.999999, 3)):
+        got = Tensor(x.copy()).sample_last(1.0, u=Tensor(np.array([u, 0.5], dtype=np.float32))).numpy().reshape(-1)
+        assert got.tolist() == [float(want), 0.0], (u, got)

@@ -206,3 +206,64 @@ def test_attention_with_finite_mask_fill_is_dense(oracle, fill):
     got, ref = run("cuda"), run("cpu")
     for a, b, what in zip(got, ref, ("y", "dq", "dk", "dv")):
         runner.rel_check(check, a, b, 1e-4, f"attention with fill {fill}: {what} vs oracle")
+
+
+@pytest.mark.parametrize("shape,temperature", [((4, 7, 96), 0.7), ((3, 50257), 1.0), ((96,), 1.3), ((64, 1, 96), 0.7)])
+def test_device_side_sampling_matches_inverse_cdf(shape, temperature):
+    """§8f2: Tensor.sample_last draws the next token on the device (examples/gpt.py:216-221, 262-266 do it on the host
+    after a D2H of the logits).  With the uniform numbers supplied, the chosen index must be the inverse-CDF index of
+    softmax(logits[..., -1, :] / temperature) computed in float64 — except where u falls within 1e-5 of a CDF step,
+    where float32 summation may legitimately pick the neighbour."""
+    from dlgrad_b200 import Tensor
+    rng = np.random.default_rng(sum(shape))
+    x = (rng.standard_normal(shape) * 3).astype(np.float32)
+    rows = 1 if len(shape) == 1 else shape[0]
+    u = rng.random(rows, dtype=np.float32)
+    u[0] = np.float32(1.0) - np.float32(2.0 ** -24)          # the largest value the generator can produce
+    got = Tensor(x.copy(), device="cuda").sample_last(temperature, u=Tensor(u.copy(), device="cuda")).numpy().reshape(rows)
+    if COMPILE_ONLY:
+        return
+    last = x.reshape(rows, -1, shape[-1])[:, -1, :].astype(np.float32)
+    z = (last / np.float32(temperature)).astype(np.float64)
+    e = np.exp(z - z.max(axis=1, keepdims=True))
+    cdf = np.cumsum(e, axis=1) / e.sum(axis=1, keepdims=True)
+    for r in range(rows):
+        want = min(int(np.searchsorted(cdf[r], float(u[r]), side="right")), shape[-1] - 1)
+        g = int(got[r])
+        assert 0 <= g < shape[-1] and float(got[r]) == g
+        if g != want:
+            edge = cdf[r][min(g, want)]
+            assert abs(edge - float(u[r])) < 1e-5 and abs(g - want) == 1, f"row {r}: got {g}, inverse CDF gives {want} (u={u[r]}, step at {edge})"
+
+
+def test_device_side_sampling_distribution_and_generate_loop():
+    """Sampling from the backend's own Philox stream reproduces the distribution (chi-square against the float64
+    probabilities over 32768 draws), and a KV-cache generate loop that never copies the distribution to the host — sampled
+    index fed straight back into the embedding, keys / values appended with Tensor.cat — runs end to end."""
+    import dlgrad_b200 as dl
+    from dlgrad_b200 import Tensor
+    from dlgrad_b200.runtime.cuda import ops as cuda_ops
+    from dlgrad_b200.runtime.cuda import transfer
+    cuda_ops.manual_seed(1234)
+    V, N = 96, 32768
+    row = (np.random.default_rng(0).standard_normal(V) * 2).astype(np.float32)
+    logits = Tensor(np.tile(row, (N, 1)), device="cuda")
+    idx = logits.sample_last(0.7).numpy().reshape(N).astype(np.int64)
+    if not COMPILE_ONLY:
+        z = row.astype(np.float64) / 0.7
+        p = np.exp(z - z.max())
+        p /= p.sum()
+        counts = np.bincount(idx, minlength=V).astype(np.float64)
+        keep = p * N >= 5
+        chi2 = float((((counts - p * N) ** 2) / (p * N))[keep].sum())
+        assert chi2 < 2.0 * keep.sum() + 40, f"chi-square {chi2:.1f} over {int(keep.sum())} bins"
+    # generate loop on a tiny GPT: device-side KV cache + device-side sampling; only the printed tokens cross PCIe
+    cfg = models.GPTConfig(vocab_size=V, block_size=32, n_layer=2, n_head=2, n_embd=32, device="cuda")
+    gpt = models.GPT(dl, cfg, np.random.default_rng(3))
+    transfer.reset_counters()
+    toks = models.generate_on_device(gpt, Tensor(np.array([[5.0]], dtype=np.float32), device="cuda"), 12, temperature=0.7)
+    io = transfer.counters()
+    out = toks.numpy().reshape(-1)
+    if not COMPILE_ONLY:
+        assert out.shape == (13,) and out[0] == 5 and ((out >= 0) & (out < V)).all() and (out == np.round(out)).all()
+        assert io["d2h_bytes"] == 0, f"the generate loop copied {io['d2h_bytes']} bytes to the host"
