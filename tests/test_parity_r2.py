@@ -35,7 +35,7 @@ def test_c5_transformer_block_forward_backward_vs_oracle(oracle):
     cfg_kw = dict(vocab_size=96, block_size=1024, n_layer=12, n_head=12, n_embd=768)
     x = (np.random.default_rng(0).random((1, 1024, 768), dtype=np.float32) - 0.5).astype(np.float32)
     coef = np.linspace(0.5, 1.5, x.size, dtype=np.float32).reshape(x.shape)
-    res = {}
+    res, pre = {}, {}
     for dev in ("cuda", "cpu"):
         cfg = models.GPTConfig(device=dev, **cfg_kw)
         blk = models._Block(dl, cfg, np.random.default_rng(7))
@@ -47,8 +47,38 @@ def test_c5_transformer_block_forward_backward_vs_oracle(oracle):
             out["d" + name] = w.grad.numpy()
         out["dln1"], out["dln2"] = blk.ln1.weight.grad.numpy(), blk.ln2.weight.grad.numpy()
         res[dev] = out
+        # the relu's pre-activation, recomputed with the block's own layers (no gradient): see below
+        x0 = Tensor(x.copy(), device=dev)
+        x1 = x0 + blk.attn(blk.ln1(x0))
+        pre[dev] = blk.c_fc(blk.ln2(x1)).numpy().reshape(1024, 3072)
+    if COMPILE_ONLY:
+        return
+    # relu is discontinuous: a pre-activation within rounding of zero lands on different sides in the oracle's
+    # sequential-fp32 GEMM and in 3xTF32 (expected here: 3.1 M units x P(|h| < 1e-6) ~ a handful).  One flipped unit
+    # (token r, hidden unit c) moves row r of dx and row c of dc_fc by O(1e-3) of their scale — a property of the
+    # function, not an error of either side.  Flips must be few and must sit within 1e-5 of zero; the rows they touch
+    # are compared at 1e-2, everything else at the stated 1e-4.
+    flips = np.argwhere((pre["cuda"] > 0) != (pre["cpu"] > 0))
+    assert len(flips) <= 64, f"{len(flips)} relu units have different signs on the two sides"
+    if len(flips):
+        assert np.abs(pre["cpu"][flips[:, 0], flips[:, 1]]).max() < 1e-5 * np.abs(pre["cpu"]).max()
+    tok, unit = np.unique(flips[:, 0]) if len(flips) else [], np.unique(flips[:, 1]) if len(flips) else []
     for k in res["cpu"]:
-        runner.rel_check(check, res["cuda"][k], res["cpu"][k], runner.TOL_MATMUL, f"C5 block {k}")
+        a, b = res["cuda"][k], res["cpu"][k]
+        if k == "dx" and len(tok):
+            keep = np.ones(1024, dtype=bool)
+            keep[tok] = False
+            scale = float(np.abs(b).max())
+            check(a[0][~keep], b[0][~keep], rtol=1e-2, atol=1e-2 * scale, what="C5 block dx, tokens with a flipped relu unit")
+            runner.rel_check(check, a[0][keep], b[0][keep], runner.TOL_MATMUL, "C5 block dx")
+        elif k == "dc_fc" and len(unit):
+            keep = np.ones(3072, dtype=bool)
+            keep[unit] = False
+            scale = float(np.abs(b).max())
+            check(a[~keep], b[~keep], rtol=1e-2, atol=1e-2 * scale, what="C5 block dc_fc, hidden units with a flipped relu")
+            runner.rel_check(check, a[keep], b[keep], runner.TOL_MATMUL, "C5 block dc_fc")
+        else:
+            runner.rel_check(check, a, b, runner.TOL_MATMUL, f"C5 block {k}")
 
 
 def _f64(a):
@@ -59,7 +89,7 @@ def _f64(a):
 def test_bench_linear_shapes_vs_float64(rows, in_f, out_f, bias):
     """(b) the projection GEMMs of the C5 step through ops.Linear: forward x @ W^T (8192 x out x in, NT), dX = g @ W
     (NN), dW = g^T @ x (TN; 768 x 768 x 8192 and 96 x 768 x 8192 run as in-kernel split-K), bias in the epilogue.
-    All against float64 (1e-4 of the largest magnitude; per-element figures are logged)."""
+    All against float64: 1e-4 of the largest magnitude AND, per entry, 1e-4 x (|A| |B|)_ij (runner.gemm_check)."""
     from dlgrad_b200 import Tensor
     rng = np.random.default_rng(rows + in_f + out_f + int(bias))
     x = (rng.random((rows, in_f), dtype=np.float32) - 0.5).astype(np.float32)
@@ -71,10 +101,9 @@ def test_bench_linear_shapes_vs_float64(rows, in_f, out_f, bias):
     Bt = Tensor(b.copy(), device="cuda", requires_grad=True) if bias else None
     y = X.linear(W, Bt)
     (y * Tensor(g.copy(), device="cuda")).sum().backward()
-    ref = _f64(x) @ _f64(w).T + (_f64(b) if bias else 0.0)
-    runner.rel_check(check, y.numpy(), ref, runner.TOL_MATMUL, f"linear {rows}x{out_f}x{in_f} forward")
-    runner.rel_check(check, X.grad.numpy(), _f64(g) @ _f64(w), runner.TOL_MATMUL, f"linear {rows}x{in_f}x{out_f} dX")
-    runner.rel_check(check, W.grad.numpy(), _f64(g).T @ _f64(x), runner.TOL_MATMUL, f"linear {out_f}x{in_f}x{rows} dW")
+    runner.gemm_check(check, y.numpy(), x, w.T, runner.TOL_MATMUL, f"linear {rows}x{out_f}x{in_f} forward", bias=b if bias else None)
+    runner.gemm_check(check, X.grad.numpy(), g, w, runner.TOL_MATMUL, f"linear {rows}x{in_f}x{out_f} dX")
+    runner.gemm_check(check, W.grad.numpy(), g.T, x, runner.TOL_MATMUL, f"linear {out_f}x{in_f}x{rows} dW")
     if bias:
         runner.rel_check(check, Bt.grad.numpy(), _f64(g).sum(0, keepdims=True), 1e-5, "linear db")
 
@@ -92,16 +121,22 @@ def test_bench_mlp_block_shapes_vs_float64():
     X = Tensor(x.copy(), device="cuda", requires_grad=True)
     W1 = Tensor(w1.copy(), device="cuda", requires_grad=True)
     W2 = Tensor(w2.copy(), device="cuda", requires_grad=True)
-    y = X.linear(W1, None).relu().linear(W2, None)
+    H = X.linear(W1, None)
+    y = H.relu().linear(W2, None)
     (y * Tensor(g.copy(), device="cuda")).sum().backward()
     x2, g2 = _f64(x).reshape(8192, 768), _f64(g).reshape(8192, 768)
-    h = x2 @ _f64(w1).T
-    r = np.maximum(h, 0.0)
-    dh = (g2 @ _f64(w2)) * (h > 0)
-    runner.rel_check(check, y.numpy().reshape(8192, 768), r @ _f64(w2).T, runner.TOL_MATMUL, "mlp forward")
-    runner.rel_check(check, W2.grad.numpy(), g2.T @ r, runner.TOL_MATMUL, "mlp dW2 (relu operand B)")
-    runner.rel_check(check, W1.grad.numpy(), dh.T @ x2, runner.TOL_MATMUL, "mlp dW1 (through the relu-mask epilogue)")
-    runner.rel_check(check, X.grad.numpy().reshape(8192, 768), dh @ _f64(w1), runner.TOL_MATMUL, "mlp dX")
+    # relu is discontinuous: a pre-activation within rounding of zero may fall on either side in float64 and in 3xTF32,
+    # and one flipped unit moves a whole row of dW1 / dX by O(1).  The float64 references below therefore take the
+    # relu pattern of the DEVICE's own pre-activation (which is itself checked against float64 first).
+    h_dev = H.numpy().reshape(8192, 3072)
+    runner.gemm_check(check, h_dev, x2, _f64(w1).T, runner.TOL_MATMUL, "mlp pre-activation")
+    on = h_dev > 0
+    r = np.where(on, _f64(h_dev), 0.0)
+    dh = (g2 @ _f64(w2)) * on
+    runner.gemm_check(check, y.numpy().reshape(8192, 768), r, _f64(w2).T, runner.TOL_MATMUL, "mlp forward (relu operand A)")
+    runner.gemm_check(check, W2.grad.numpy(), g2.T, r, runner.TOL_MATMUL, "mlp dW2 (relu operand B)")
+    runner.gemm_check(check, W1.grad.numpy(), dh.T, x2, runner.TOL_MATMUL, "mlp dW1 (through the relu-mask epilogue)")
+    runner.gemm_check(check, X.grad.numpy().reshape(8192, 768), dh, _f64(w1), runner.TOL_MATMUL, "mlp dX")
 
 
 def test_full_width_gan_step_vs_oracle(oracle):
