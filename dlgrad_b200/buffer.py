@@ -213,7 +213,8 @@ class Buffer:
     # producer — ("scale", src, s) for `src * python_scalar`, ("mfill", src, mask, val) for masked_fill,
     # ("softmax_bwd", y, g, dim, kind) for the row backward, ("tr", src) for a transpose of the two
     # innermost dims, ("mm", x, y) for an attention-shaped q @ k^T, ("relu", src) for Tensor.relu (folded into the
-    # splitter of the GEMM that consumes it).  Reading `.ptr` materialises it (one fused
+    # splitter of the GEMM that consumes it), ("attnP", q, k, scale, mask, fill) for the attention probabilities
+    # (consumed by the flash-style kernels without ever being written).  Reading `.ptr` materialises it (one fused
     # kernel for the whole pending chain); consumers that can fold the chain into their own kernel
     # (softmax forward, and the chain materialiser itself) never trigger the intermediate writes.  The
     # values are identical either way; only the number of passes over HBM changes.
@@ -413,6 +414,11 @@ class Buffer:
         dev = Buffer._route(self, other)
         x = self if self.shape == p1 else self.reshape(p1)
         y = other if other.shape == p2 else other.reshape(p2)
+        if dev is _CUDA and x._pending is not None and x._pending[0] == "attnP":
+            from dlgrad_b200.runtime.cuda import attention
+            o = attention.flash_forward(x, y)                 # None: v does not fit, P is materialised below
+            if o is not None:
+                return self._like(o, out_shape, dev)
         if dev is _CUDA and y._pending is not None and y._pending[0] == "tr":
             # q @ k^T of attention-shaped operands is deferred: if scale -> masked_fill -> softmax follow, one
             # kernel produces the probabilities and this product never reaches HBM (runtime/cuda/attention.py)
@@ -503,6 +509,13 @@ class Buffer:
     # fused row ops (CUDA backend); a host runtime may register the 5-op composition
     def softmax(self, dim: int) -> "Buffer":
         dev = Buffer._route(self)
+        if dev is _CUDA and self._pending is not None:
+            # softmax of a deferred (q @ k^T) * scale -> masked_fill chain: the probabilities stay deferred too; if `@ v`
+            # follows, one flash-style kernel produces the output and P is never written (runtime/cuda/attention.py)
+            from dlgrad_b200.runtime.cuda import attention
+            p = attention.softmax_deferred(self, dim)
+            if p is not None:
+                return p
         out = self._like(_dispatch(op=UnaryOps.SOFTMAX, device=dev, x=self, dim=dim), self.shape, dev)
         if dev is _CUDA:
             from dlgrad_b200.runtime.cuda import attention

@@ -1,0 +1,635 @@
+"""Flash-style attention in 3xTF32 on tcgen05 / TMEM / TMA: the probabilities P = softmax(mask(q k^T * scale)) of
+examples/gpt.py:49-55 never reach HBM, neither forward nor backward.
+
+The reference executes `att = (q @ k^T) * scale; att = masked_fill(att, mask, fill); att = softmax(att); y = att @ v`
+as MATMUL, MUL, MASKED_FILL, five softmax kernels and MATMUL over (B, h, T, T) tensors (dlgrad/tensor.py:634-649).
+Round 1 kept S = q k^T and dP on chip but still wrote P and dS (403 MB each per layer at C5) and re-read them in four
+GEMMs: about 2.3 GB of HBM traffic per layer against 0.1 GB of algorithmic bytes (q, k, v, O, dO in; O, dq, dk, dv out).
+One generator, three kernels that share a skeleton ("A-side" tile of 128 rows resident in tensor memory, the other
+sequence streamed in 64-row blocks through a TMA ring, rows of the score tile owned by threads):
+
+    fwd   A = Q tile.  per key block:  S = Q K^T -> online softmax in registers -> P (hi | lo) written to TMEM by the
+          row threads -> O += P V as a TS-form MMA.  Output O (normalised) and the row statistics (m, 1 / l).
+    dv    A = K tile.  per query block: S^T = K Q^T -> P^T = 2^(S^T c - m_q) / l_q from the saved statistics ->
+          TMEM -> dV += P^T dO.
+    ds    A = Q tile and dO tile.  per key block: S = Q K^T and dP = dO V^T -> dS = P (dP - delta) scale, masked -> HBM
+          (delta = rowsum(dO * O)).  dS is the one (B, h, T, T) tensor that is still materialised: dq = dS k and
+          dk = dS^T q run on the tile-skipping GEMM (cuda_tcgen05.matmul_tc_ts, ksparse).  Folding those two into this
+          kernel needs 576 TMEM columns in 3xTF32 (Q, dO, S, dP, dS hi | lo, dQ) — 64 more than an SM has.
+
+Every product is 3xTF32 (a_lo b_hi + a_hi b_lo + a_hi b_hi, fp32 accumulate), so the results keep fp32 accuracy
+(north star: matmul <= 1e-4, softmax <= 1e-5 relative).  kind::tf32 truncates its inputs, so a staged fp32 tile IS its
+own `hi`; only `lo` tiles are computed (splitter warps for the streamed operands, the row threads for A and P).
+
+Warp roles (320 threads, one persistent CTA per SM):
+    warp 0      TMA producer: A tile(s) of the next item, then per step the two streamed tiles of the ring stage
+    warp 1      MMA issuer (one elected lane)
+    warps 2-5   row warps: thread = row of the 128-row score tile = TMEM lane
+    warps 6-9   splitter: lo = x - trunc_tf32(x) for the staged tiles of a stage (twin buffers, same swizzled layout)
+"""
+from __future__ import annotations
+
+import math
+from functools import cache
+
+import numpy as np
+
+from dlgrad_b200.codegen.cuda_tcgen05 import _HELPERS, _HELPERS_TS, NUM_SMS, TcKernel, _f32lit, _idesc
+from dlgrad_b200.runtime.cuda.compiler import KNAME
+
+_EXTRA = r"""
+__device__ __forceinline__ float ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ void tma_load_4d(unsigned dst, const TMap* map, unsigned bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        :: "r"(dst), "l"((unsigned long long)map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+#define TMEM_LD32(addr, v) asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];" \
+    : "=r"((v)[0]), "=r"((v)[1]), "=r"((v)[2]), "=r"((v)[3]), "=r"((v)[4]), "=r"((v)[5]), "=r"((v)[6]), "=r"((v)[7]), \
+      "=r"((v)[8]), "=r"((v)[9]), "=r"((v)[10]), "=r"((v)[11]), "=r"((v)[12]), "=r"((v)[13]), "=r"((v)[14]), "=r"((v)[15]), \
+      "=r"((v)[16]), "=r"((v)[17]), "=r"((v)[18]), "=r"((v)[19]), "=r"((v)[20]), "=r"((v)[21]), "=r"((v)[22]), "=r"((v)[23]), \
+      "=r"((v)[24]), "=r"((v)[25]), "=r"((v)[26]), "=r"((v)[27]), "=r"((v)[28]), "=r"((v)[29]), "=r"((v)[30]), "=r"((v)[31]) \
+    : "r"(addr))
+#define TMEM_ST32(addr, v) asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" \
+    :: "r"(addr), "r"((v)[0]), "r"((v)[1]), "r"((v)[2]), "r"((v)[3]), "r"((v)[4]), "r"((v)[5]), "r"((v)[6]), "r"((v)[7]), \
+      "r"((v)[8]), "r"((v)[9]), "r"((v)[10]), "r"((v)[11]), "r"((v)[12]), "r"((v)[13]), "r"((v)[14]), "r"((v)[15]), \
+      "r"((v)[16]), "r"((v)[17]), "r"((v)[18]), "r"((v)[19]), "r"((v)[20]), "r"((v)[21]), "r"((v)[22]), "r"((v)[23]), \
+      "r"((v)[24]), "r"((v)[25]), "r"((v)[26]), "r"((v)[27]), "r"((v)[28]), "r"((v)[29]), "r"((v)[30]), "r"((v)[31]) : "memory")
+#define TMEM_WAIT_LD() asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory")
+#define TMEM_WAIT_ST() asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory")
+#define TC_FENCE_BEFORE() asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory")
+#define TC_FENCE_AFTER() asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory")
+// hi | lo split of 32 fp32 values (hi = the 19 bits kind::tf32 keeps, lo = the rest, exact) straight into tensor memory
+__device__ __forceinline__ void split_to_tmem(unsigned t_hi, unsigned t_lo, const float* x) {
+    unsigned hi[32], lo[32];
+    #pragma unroll
+    for (unsigned e = 0; e < 32u; ++e) {
+        hi[e] = __float_as_uint(x[e]) & 0xffffe000u;
+        lo[e] = __float_as_uint(x[e] - __uint_as_float(hi[e]));
+    }
+    TMEM_ST32(t_hi, hi);
+    TMEM_ST32(t_lo, lo);
+}
+"""
+
+NEG_INF = "__int_as_float(0xff800000)"
+QNAN = "__int_as_float(0x7fc00000)"
+
+
+def _sub(src: str, **kw) -> str:
+    for k, v in kw.items():
+        src = src.replace(f"${k}$", str(v))
+    assert "$" not in src, src[src.index("$") - 40:src.index("$") + 40]
+    return src
+
+
+@cache
+def flash_attn(mode: str, Tq: int, Tk: int, D: int, H: int, NB: int, scale: float, fill: float,
+               out_strides: tuple = (0, 0, 0), tau: float = 8.0) -> TcKernel:
+    """mode "fwd" | "dv" | "ds" (module docstring).  Tq, Tk multiples of 128, D in (32, 64), NB = batch * H score planes,
+    H heads (a plane z is head z % H of sequence z / H: every operand is addressed through a rank-4 tensor map
+    (D, T, H, B), so both (B, h, T, D) and the projection's own (B, T, h, D) layout work without a permute kernel).
+    `out_strides` = element strides (row, head, batch) of the direct-store output (O for fwd, dV for dv).
+    `tau`: the running maximum of the online softmax is only replaced when it grows by more than `tau` (base-2 units):
+    any m gives the same P / l in exact arithmetic, and 2^tau bounds the un-normalised P, so O in tensor memory is
+    rescaled almost never instead of almost always (tau = 0 forces the rescale path; the tests use it).
+
+    Kernel parameters
+      fwd: tmQ, tmK, tmV, O, stats (float2 per row: m in base-2 units, 1 / l; NaN for a row without a live entry), bits
+      dv : tmK, tmQ, tmDO, dV, stats, bits
+      ds : tmQ, tmDO, tmK, tmV, tmDS, dS, stats, delta, bits          (bits: cuda_kernel.mask_bits of the (Tq, Tk) mask)"""
+    assert mode in ("fwd", "dv", "ds") and Tq % 128 == 0 and Tk % 128 == 0 and D in (32, 64) and scale > 0
+    assert max(Tq, Tk) // 128 <= 32
+    kbq = D // 32
+    nq, nk = Tq // 128, Tk // 128
+    nA, nS = (nk, nq) if mode == "dv" else (nq, nk)          # tiles on the resident side / on the streamed side
+    TA, TS = (Tk, Tq) if mode == "dv" else (Tq, Tk)
+    items = NB * nA
+    grid = min(items, NUM_SMS)
+    skip = math.isinf(fill) and fill < 0
+    tile_b = kbq * 8192                                      # one streamed tile: 64 rows x D fp32
+    raw_b = 2 * tile_b
+    per_stage = 2 * raw_b                                    # B1 raw | B2 raw | B1 lo | B2 lo
+    a_tiles = 2 if mode == "ds" else 1
+    a_bytes = a_tiles * kbq * 16384
+    epi_bytes = 4 * 2 * 4096 if mode == "ds" else 0          # two 32x32 staging boxes per row warp for the dS store
+    budget = 227 * 1024 - 1024 - 512 - a_bytes - epi_bytes
+    stages = max(2, min(3, budget // per_stage))
+    smem = a_bytes + stages * per_stage + epi_bytes + 1024 + 512
+    if mode == "ds":
+        S0, DP0, A0, A1 = 0, 128, 256, 256 + 2 * D
+        PHI = PLO = OACC = 0
+        assert A1 + 2 * D <= 512
+    else:
+        S0, PHI, PLO, OACC, A0 = 0, 128, 192, 256, 320
+        DP0 = A1 = 0
+        assert A0 + 2 * D <= 512
+    log2e = np.float32(math.log2(math.e))
+    sc2 = _f32lit(float(np.float32(scale) * log2e))
+    fl2 = _f32lit(fill if math.isinf(fill) else float(np.float32(fill) * log2e))
+    idesc_s = _idesc(128, 64, False, False)                  # S / dP: N = 64 streamed rows, B K-major
+    idesc_o = _idesc(128, D, False, True)                    # O / dV: N = D, B MN-major
+    sT, sH, sB = out_strides
+    # which streamed 128-row tiles are live for resident tile `at`
+    if skip:
+        if mode == "dv":
+            live = f"""const unsigned* tf = mask + {Tq * Tk // 32}u + at; unsigned lm = 0u;
+            for (unsigned j = 0; j < {nq}u; ++j) lm |= (__ldg(tf + j * {nk}u) != 0u ? 1u : 0u) << j; return lm;"""
+        else:
+            live = f"""const unsigned* tf = mask + {Tq * Tk // 32}u + at * {nk}u; unsigned lm = 0u;
+            for (unsigned j = 0; j < {nk}u; ++j) lm |= (__ldg(tf + j) != 0u ? 1u : 0u) << j; return lm;"""
+    else:
+        live = f"return {(1 << nS) - 1 if nS < 32 else 0xffffffff}u;"
+    # heavy tiles first: under a causal mask query tile i has i + 1 live key tiles, key tile i has nq - i live query tiles
+    tile_of = f"p / {NB}u" if mode == "dv" else f"{nA - 1}u - p / {NB}u"
+
+    if mode == "ds":
+        params = ("const __grid_constant__ TMap tmA, const __grid_constant__ TMap tmA2, const __grid_constant__ TMap tmB1, "
+                  "const __grid_constant__ TMap tmB2, const __grid_constant__ TMap tmOut, float* __restrict__ out, "
+                  "const float2* __restrict__ stats, const float* __restrict__ delta, const unsigned* __restrict__ mask")
+    elif mode == "fwd":
+        params = ("const __grid_constant__ TMap tmA, const __grid_constant__ TMap tmB1, const __grid_constant__ TMap tmB2, "
+                  "float* __restrict__ out, float2* __restrict__ stats, const unsigned* __restrict__ mask")
+    else:
+        params = ("const __grid_constant__ TMap tmA, const __grid_constant__ TMap tmB1, const __grid_constant__ TMap tmB2, "
+                  "float* __restrict__ out, const float2* __restrict__ stats, const unsigned* __restrict__ mask")
+
+    # ------------------------------------------------------------------ producer: streamed tiles of one step
+    if mode == "ds":       # K block and V block, both K-major (64 rows x D)
+        b2_loads = "\n                        ".join(
+            f"tma_load_4d(st + {tile_b + kk * 8192}u, &tmB2, fb, {kk * 32}, (int)r0, (int)hh, (int)bb);" for kk in range(kbq))
+    else:                  # second tile MN-major: boxes of {32 columns, 32 rows}, k-block major
+        b2_loads = "\n                        ".join(
+            f"tma_load_4d(st + {tile_b + (kb2 * kbq + c) * 4096}u, &tmB2, fb, {c * 32}, (int)(r0 + {kb2 * 32}u), (int)hh, (int)bb);"
+            for kb2 in range(2) for c in range(kbq))
+    b1_loads = "\n                        ".join(
+        f"tma_load_4d(st + {kk * 8192}u, &tmB1, fb, {kk * 32}, (int)r0, (int)hh, (int)bb);" for kk in range(kbq))
+    a_loads = "\n                ".join(
+        f"tma_load_4d(smem + {kk * 16384}u, &tmA, qfull, {kk * 32}, (int)a0, (int)hh, (int)bb);" for kk in range(kbq))
+    if mode == "ds":
+        a_loads += "\n                " + "\n                ".join(
+            f"tma_load_4d(smem + {(kbq + kk) * 16384}u, &tmA2, qfull, {kk * 32}, (int)a0, (int)hh, (int)bb);" for kk in range(kbq))
+
+    # ------------------------------------------------------------------ MMA bodies
+    lo_off = raw_b // 16
+
+    def s_mma(acc_col: str, a_col: int, b_off16: int) -> str:
+        """acc[128 x 64] = A (TMEM at a_col, hi | lo per 32-wide k block) x B1/B2 tile (K-major) of stage `sdesc`."""
+        return f"""
+                        #pragma unroll
+                        for (unsigned kk = 0; kk < {kbq}u; ++kk) {{
+                            #pragma unroll
+                            for (unsigned k = 0; k < 4u; ++k) {{
+                                const unsigned a_hi = tmem_base + {a_col}u + kk * 64u + k * 8u, a_lo = a_hi + 32u;
+                                const unsigned long long b_hi = sdesc + {b_off16}ull + (unsigned long long)(kk * 512u + k * 2u);
+                                umma_tf32_ts({acc_col}, a_lo, b_hi, {idesc_s}u, (kk | k) != 0u);
+                                umma_tf32_ts({acc_col}, a_hi, b_hi + {lo_off}ull, {idesc_s}u, 1u);
+                                umma_tf32_ts({acc_col}, a_hi, b_hi, {idesc_s}u, 1u);
+                            }}
+                        }}"""
+    o_mma = f"""
+                        #pragma unroll
+                        for (unsigned kb2 = 0; kb2 < 2u; ++kb2) {{
+                            #pragma unroll
+                            for (unsigned k = 0; k < 4u; ++k) {{
+                                const unsigned a_hi = tmem_base + {PHI}u + kb2 * 32u + k * 8u, a_lo = tmem_base + {PLO}u + kb2 * 32u + k * 8u;
+                                const unsigned long long b_hi = odesc + (unsigned long long)(kb2 * {kbq * 256}u + k * 64u);
+                                umma_tf32_ts(tmem_base + {OACC}u, a_lo, b_hi, {idesc_o}u, (acc | kb2 | k) != 0u);
+                                umma_tf32_ts(tmem_base + {OACC}u, a_hi, b_hi + {lo_off}ull, {idesc_o}u, 1u);
+                                umma_tf32_ts(tmem_base + {OACC}u, a_hi, b_hi, {idesc_o}u, 1u);
+                            }}
+                        }}"""
+
+    src = _HELPERS + _HELPERS_TS + _EXTRA + _sub(r"""
+extern "C" __global__ void __launch_bounds__(320, 1)
+$KNAME$($PARAMS$)
+{
+    extern __shared__ unsigned char smem_raw[];
+    const unsigned smem = (smem_u32(smem_raw) + 1023u) & ~1023u;        // swizzle atoms need 1024-byte alignment
+    unsigned char* smem_gen = smem_raw + (smem - smem_u32(smem_raw));
+    const unsigned ring = smem + $A_BYTES$u;                            // stages: B1 raw | B2 raw | B1 lo | B2 lo
+    const unsigned epi = ring + $RING_BYTES$u;
+    const unsigned bars = epi + $EPI_BYTES$u;
+    const unsigned kfull = bars, kempty = bars + $STAGES$u * 8u, ksplit = bars + $STAGES$u * 16u;
+    const unsigned sfull = bars + $STAGES$u * 24u, sempty = sfull + 16u, pready = sempty + 16u, pvdone = pready + 8u;
+    const unsigned qfull = pvdone + 8u, qsplit = qfull + 8u, qfree = qsplit + 8u;
+    __shared__ unsigned tmem_slot;
+    const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+
+    // streamed 128-row tiles that have at least one unmasked entry against resident tile `at` (cuda_kernel.mask_bits):
+    // a tile the mask kills entirely is never loaded, multiplied or read (only for a -inf fill: P is exactly 0 there)
+    auto live_tiles = [&](unsigned at) -> unsigned {
+        $LIVE$
+    };
+    // work items (plane z, resident tile at) in the order of this CTA: heavy tiles first, CTAs taken in alternating
+    // direction from round to round (cuda_tcgen05.balanced_items)
+    auto item_at = [&](unsigned nn, unsigned& z, unsigned& at) -> bool {
+        const unsigned p = nn * $GRID$u + ((nn & 1u) ? ($GRID$u - 1u - blockIdx.x) : blockIdx.x);
+        if (p >= $ITEMS$u) return false;
+        z = p % $NB$u;
+        at = $TILE_OF$;
+        return true;
+    };
+
+    if (threadIdx.x == 0) {
+        for (unsigned s = 0; s < $STAGES$u; ++s) {
+            mbar_init(kfull + s * 8u, 1u);
+            mbar_init(kempty + s * 8u, 1u);
+            mbar_init(ksplit + s * 8u, 4u);
+        }
+        for (unsigned b = 0; b < 2u; ++b) {
+            mbar_init(sfull + b * 8u, 1u);
+            mbar_init(sempty + b * 8u, 4u);
+        }
+        mbar_init(pready, 4u);
+        mbar_init(pvdone, 1u);
+        mbar_init(qfull, 1u);
+        mbar_init(qsplit, 4u);
+        mbar_init(qfree, 1u);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&tmem_slot)), "n"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    TC_FENCE_BEFORE();
+    __syncthreads();
+    TC_FENCE_AFTER();
+    const unsigned tmem_base = tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        unsigned it = 0, n = 0, z, at;
+        auto load_a = [&](unsigned zz, unsigned aa) {
+            const unsigned hh = zz % $H$u, bb = zz / $H$u, a0 = aa * 128u;
+            if (elect_one()) {
+                mbar_expect_tx(qfull, $A_BYTES$u);
+                $A_LOADS$
+            }
+            __syncwarp();
+        };
+        if (item_at(0u, z, at)) load_a(z, at);
+        for (; item_at(n, z, at); ++n) {
+            const unsigned hh = z % $H$u, bb = z / $H$u;
+            const unsigned lm = live_tiles(at);
+            unsigned zn, an;
+            bool a_pending = item_at(n + 1u, zn, an);           // the next item's A tile: once this one has left shared memory
+            for (unsigned t = 0; t < $NS$u; ++t) {
+                if (!((lm >> t) & 1u)) continue;
+                for (unsigned half = 0; half < 2u; ++half, ++it) {
+                    if (a_pending && mbar_try(qsplit, n & 1u)) { load_a(zn, an); a_pending = false; }
+                    const unsigned s = it % $STAGES$u, ph = (it / $STAGES$u) & 1u;
+                    mbar_wait(kempty + s * 8u, ph ^ 1u);
+                    const unsigned st = ring + s * $PER_STAGE$u, fb = kfull + s * 8u, r0 = t * 128u + half * 64u;
+                    if (elect_one()) {
+                        mbar_expect_tx(fb, $RAW_B$u);
+                        $B1_LOADS$
+                        $B2_LOADS$
+                    }
+                    __syncwarp();
+                }
+            }
+            if (a_pending) { mbar_wait(qsplit, n & 1u); load_a(zn, an); }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        unsigned it = 0, g = 0, n = 0, z, at;
+        const unsigned long long sdesc0 = make_desc(ring, 1u, 64u, 2u);                  // K-major tile: SBO 1024 B, SWIZZLE_128B
+        const unsigned long long odesc0 = make_desc(ring + $TILE_B$u, 256u, 32u, 1u);    // MN-major tile: LBO 4096 B, SBO 512 B, 32-byte atoms
+        for (; item_at(n, z, at); ++n) {
+            const unsigned nsteps = 2u * __popc(live_tiles(at));
+            mbar_wait(qsplit, n & 1u);                            // A (hi | lo) of this item is in tensor memory
+            TC_FENCE_AFTER();
+            if (nsteps == 0u) {
+                if (elect_one()) umma_commit(qfree);
+                __syncwarp();
+                continue;
+            }
+            unsigned issued = 0;                                  // S-type MMAs issued for this item
+            auto issue_s = [&]() {
+                const unsigned gi = g + issued, b = gi & 1u, iti = it + issued;
+                const unsigned s = iti % $STAGES$u, ph = (iti / $STAGES$u) & 1u;
+                mbar_wait(ksplit + s * 8u, ph);
+                mbar_wait(sempty + b * 8u, ((gi >> 1) & 1u) ^ 1u);
+                TC_FENCE_AFTER();
+                const unsigned long long sdesc = sdesc0 + (unsigned long long)(s * $PER_STAGE16$u);
+                if (elect_one()) {
+                    $S_MMA$
+                    $DP_MMA$
+                    $DS_STAGE_FREE$
+                    umma_commit(sfull + b * 8u);
+                    if (issued + 1u == nsteps) umma_commit(qfree);      // the last read of A by this item
+                }
+                __syncwarp();
+                ++issued;
+            };
+            issue_s();
+            for (unsigned j = 0; j < nsteps; ++j) {
+                if (issued < nsteps) issue_s();                   // S of step j + 1 runs while the row warps work on step j
+                $PV_BLOCK$
+            }
+            it += nsteps;
+            g += nsteps;
+        }
+    } else if (warp < 6u) {
+        // ===== row warps: thread = row of the score tile = TMEM lane =====
+        const unsigned sq = warp & 3u;                            // the TMEM lane quarter this warp may access
+        const unsigned lane_base = tmem_base + ((sq * 32u) << 16);
+        unsigned g = 0, n = 0, z, at;
+        auto split_a = [&](unsigned nn) {
+            mbar_wait(qfull, nn & 1u);                             // the tile has landed in shared memory
+            if (nn != 0u) { mbar_wait(qfree, (nn - 1u) & 1u); TC_FENCE_AFTER(); }    // and the previous item no longer reads A
+            #pragma unroll 1
+            for (unsigned kk = 0; kk < $A_KBLOCKS$u; ++kk) {
+                const unsigned char* arow = smem_gen + kk * 16384u + (sq * 32u + lane) * 128u;
+                float x[32];
+                #pragma unroll
+                for (unsigned j = 0; j < 8u; ++j) {
+                    const float4 v4 = *reinterpret_cast<const float4*>(arow + ((j ^ (lane & 7u)) << 4));
+                    x[4 * j] = v4.x; x[4 * j + 1] = v4.y; x[4 * j + 2] = v4.z; x[4 * j + 3] = v4.w;
+                }
+                const unsigned ta = lane_base + $A0$u + kk * 64u;
+                split_to_tmem(ta, ta + 32u, x);
+            }
+            TMEM_WAIT_ST();
+            TC_FENCE_BEFORE();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(qsplit);
+        };
+        if (item_at(0u, z, at)) split_a(0u);
+        for (; item_at(n, z, at); ++n) {
+            const unsigned hh = z % $H$u, bb = z / $H$u;
+            const unsigned row = at * 128u + sq * 32u + lane;      // this thread's row on the resident side
+            const unsigned lm = live_tiles(at);
+            const unsigned nsteps = 2u * __popc(lm);
+            unsigned zn, an;
+            const bool has_next = item_at(n + 1u, zn, an);
+            $ROW_ITEM_BEGIN$
+            unsigned j = 0;
+            for (unsigned t = 0; t < $NS$u; ++t) {
+                if (!((lm >> t) & 1u)) continue;
+                for (unsigned half = 0; half < 2u; ++half, ++j, ++g) {
+                    const unsigned b = g & 1u;
+                    const unsigned c0 = t * 128u + half * 64u;         // first streamed row (= score column) of this step
+                    mbar_wait(sfull + b * 8u, (g >> 1) & 1u);
+                    TC_FENCE_AFTER();
+                    $ROW_STEP$
+                }
+            }
+            if (has_next) split_a(n + 1u);                         // next item's A while the last MMAs of this one run
+            $ROW_ITEM_END$
+        }
+        $ROW_EXIT$
+    } else {
+        // ===== splitter warps: lo = x - trunc_tf32(x) for the two staged tiles of a step =====
+        const unsigned ctid = threadIdx.x - 192u;
+        unsigned it = 0, n = 0, z, at;
+        for (; item_at(n, z, at); ++n) {
+            const unsigned nsteps = 2u * __popc(live_tiles(at));
+            for (unsigned i2 = 0; i2 < nsteps; ++i2, ++it) {
+                const unsigned s = it % $STAGES$u, ph = (it / $STAGES$u) & 1u;
+                mbar_wait(kfull + s * 8u, ph);
+                const float4* bsrc = reinterpret_cast<const float4*>(smem_gen + $A_BYTES$u + s * $PER_STAGE$u);
+                float4* bdst = reinterpret_cast<float4*>(smem_gen + $A_BYTES$u + s * $PER_STAGE$u + $RAW_B$u);
+                #pragma unroll 8
+                for (unsigned i = ctid; i < $RAW_V4$u; i += 128u) {
+                    const float4 v4 = bsrc[i];
+                    float4 l4;
+                    l4.x = v4.x - __uint_as_float(__float_as_uint(v4.x) & 0xffffe000u);
+                    l4.y = v4.y - __uint_as_float(__float_as_uint(v4.y) & 0xffffe000u);
+                    l4.z = v4.z - __uint_as_float(__float_as_uint(v4.z) & 0xffffe000u);
+                    l4.w = v4.w - __uint_as_float(__float_as_uint(v4.w) & 0xffffe000u);
+                    bdst[i] = l4;
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(ksplit + s * 8u);
+            }
+        }
+    }
+    TC_FENCE_BEFORE();
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "n"(512));
+    }
+}
+""",
+        KNAME=KNAME, PARAMS=params, A_BYTES=a_bytes, RING_BYTES=stages * per_stage, EPI_BYTES=epi_bytes, STAGES=stages,
+        LIVE=live, GRID=grid, ITEMS=items, NB=NB, TILE_OF=tile_of, H=H, A_LOADS=a_loads, NS=nS, PER_STAGE=per_stage,
+        RAW_B=raw_b, B1_LOADS=b1_loads, B2_LOADS=b2_loads, TILE_B=tile_b, PER_STAGE16=per_stage // 16,
+        S_MMA=s_mma(f"tmem_base + {S0}u + b * 64u", A0, 0),
+        DP_MMA=s_mma(f"tmem_base + {DP0}u + b * 64u", A1, tile_b // 16) if mode == "ds" else "",
+        DS_STAGE_FREE="umma_commit(kempty + s * 8u);" if mode == "ds" else "",
+        PV_BLOCK="" if mode == "ds" else _sub(r"""{
+                    const unsigned gi = g + j, iti = it + j, s = iti % $STAGES$u;
+                    mbar_wait(pready, gi & 1u);                    // P (hi | lo) of step j is in tensor memory
+                    TC_FENCE_AFTER();
+                    const unsigned long long odesc = odesc0 + (unsigned long long)(s * $PER_STAGE16$u);
+                    const unsigned acc = j;                        // the first step of an item overwrites the accumulator
+                    if (elect_one()) {
+                        $O_MMA$
+                        umma_commit(kempty + s * 8u);
+                        umma_commit(pvdone);
+                    }
+                    __syncwarp();
+                }""", STAGES=stages, PER_STAGE16=per_stage // 16, O_MMA=o_mma),
+        A_KBLOCKS=a_tiles * kbq, A0=A0,
+        ROW_ITEM_BEGIN=_row_item_begin(mode, Tq, Tk),
+        ROW_STEP=_row_step(mode, Tq, Tk, D, S0, DP0, PHI, PLO, OACC, sc2, fl2, _f32lit(float(np.float32(scale))), tau),
+        ROW_ITEM_END=_row_item_end(mode, Tq, Tk, D, OACC, sT, sH, sB, nS),
+        ROW_EXIT='if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");' if mode == "ds" else "",
+        RAW_V4=raw_b // 16)
+    out_elems = {"fwd": NB * Tq * D, "dv": NB * Tk * D, "ds": NB * Tq * Tk}[mode]
+    return TcKernel(f"flash_{mode}", src, (grid, 1, 1), 320, smem, out_elems, 64, stages)
+
+
+def _row_item_begin(mode: str, Tq: int, Tk: int) -> str:
+    if mode == "fwd":
+        return f"float m_run = {NEG_INF}, l_run = 0.f;"
+    if mode == "ds":
+        return f"""const float2 st_row = __ldg(stats + (size_t)z * {Tq}u + row);      // (m, 1 / l) of this query row
+            const float d_row = __ldg(delta + (size_t)z * {Tq}u + row);       // rowsum(dO * O)
+            const unsigned my_epi = epi + (warp - 2u) * 8192u;
+            unsigned char* my_epi_gen = smem_gen + (epi - smem) + (warp - 2u) * 8192u;
+            // streamed tiles the mask kills entirely: dS is zero there whatever P and dP hold (eight lanes per 128-byte row)
+            for (unsigned t = 0; t < {Tk // 128}u; ++t) {{
+                if ((lm >> t) & 1u) continue;
+                float* dst = out + ((size_t)z * {Tq}u + at * 128u + sq * 32u + (lane >> 3)) * {Tk}u + t * 128u + (lane & 7u) * 4u;
+                const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                #pragma unroll
+                for (unsigned i = 0; i < 8u; ++i) {{
+                    #pragma unroll
+                    for (unsigned c = 0; c < 4u; ++c) *reinterpret_cast<float4*>(dst + (size_t)(4u * i) * {Tk}u + c * 32u) = z4;
+                }}
+            }}"""
+    return ""
+
+
+def _row_step(mode, Tq, Tk, D, S0, DP0, PHI, PLO, OACC, sc2, fl2, sc, tau) -> str:
+    wpr = Tk // 32
+    if mode == "fwd":
+        resc = "\n                        ".join(
+            f"""{{ unsigned o[32]; TMEM_LD32(lane_base + {OACC + 32 * c}u, o); TMEM_WAIT_LD();
+                          #pragma unroll
+                          for (unsigned e = 0; e < 32u; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * alpha);
+                          TMEM_ST32(lane_base + {OACC + 32 * c}u, o); }}""" for c in range(D // 32))
+        return f"""unsigned v[64];
+                    TMEM_LD32(lane_base + {S0}u + b * 64u, v);
+                    TMEM_LD32(lane_base + {S0}u + b * 64u + 32u, v + 32);
+                    const uint2 mw = __ldg(reinterpret_cast<const uint2*>(mask + (size_t)row * {wpr}u + (c0 >> 5)));
+                    TMEM_WAIT_LD();
+                    TC_FENCE_BEFORE();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(sempty + b * 8u);        // S[b] may be overwritten by the step after next
+                    float x[64];
+                    float cm = {NEG_INF};
+                    #pragma unroll
+                    for (unsigned e = 0; e < 64u; ++e) {{
+                        const unsigned bit = ((e < 32u ? mw.x : mw.y) >> (e & 31u)) & 1u;
+                        x[e] = bit ? {fl2} : __uint_as_float(v[e]) * {sc2};
+                        cm = fmaxf(cm, x[e]);
+                    }}
+                    // online softmax with a lazily updated maximum (see `tau`)
+                    float alpha = 1.f;
+                    const float m_new = fmaxf(m_run, cm);
+                    const bool grow = m_new > m_run + {_f32lit(tau)};
+                    if (grow) {{ alpha = ex2(m_run - m_new); l_run *= alpha; m_run = m_new; }}
+                    const bool resc = __any_sync(0xffffffffu, grow) && j != 0u;
+                    const bool none = !(m_run > {NEG_INF});            // nothing finite so far: P = 0 (an all-masked row ends NaN)
+                    float add = 0.f;
+                    #pragma unroll
+                    for (unsigned e = 0; e < 64u; ++e) {{
+                        x[e] = none ? 0.f : ex2(x[e] - m_run);
+                        add += x[e];
+                    }}
+                    l_run += add;
+                    if (g != 0u) {{ mbar_wait(pvdone, (g - 1u) & 1u); TC_FENCE_AFTER(); }}     // the MMA that read P (and wrote O) is done
+                    if (resc) {{
+                        {resc}
+                    }}
+                    split_to_tmem(lane_base + {PHI}u, lane_base + {PLO}u, x);
+                    split_to_tmem(lane_base + {PHI + 32}u, lane_base + {PLO + 32}u, x + 32);
+                    TMEM_WAIT_ST();
+                    TC_FENCE_BEFORE();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(pready);"""
+    if mode == "dv":
+        return f"""unsigned v[64];
+                    TMEM_LD32(lane_base + {S0}u + b * 64u, v);
+                    TMEM_LD32(lane_base + {S0}u + b * 64u + 32u, v + 32);
+                    TMEM_WAIT_LD();
+                    TC_FENCE_BEFORE();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(sempty + b * 8u);
+                    // thread = key row, column e = query c0 + e: that query's (m, 1 / l) and its mask word for this warp's 32
+                    // keys are the same for the whole warp (broadcast loads)
+                    float x[64];
+                    const float2* srow = stats + (size_t)z * {Tq}u + c0;
+                    const unsigned* mrow = mask + (size_t)c0 * {wpr}u + (row >> 5);
+                    #pragma unroll
+                    for (unsigned e = 0; e < 64u; ++e) {{
+                        const float2 st = __ldg(srow + e);
+                        const unsigned bit = (__ldg(mrow + (size_t)e * {wpr}u) >> lane) & 1u;
+                        const float t2 = bit ? {fl2} : __uint_as_float(v[e]) * {sc2};
+                        x[e] = ex2(t2 - st.x) * st.y;
+                    }}
+                    if (g != 0u) {{ mbar_wait(pvdone, (g - 1u) & 1u); TC_FENCE_AFTER(); }}
+                    split_to_tmem(lane_base + {PHI}u, lane_base + {PLO}u, x);
+                    split_to_tmem(lane_base + {PHI + 32}u, lane_base + {PLO + 32}u, x + 32);
+                    TMEM_WAIT_ST();
+                    TC_FENCE_BEFORE();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(pready);"""
+    # ds
+    stage_writes = "\n                            ".join(
+        f"*reinterpret_cast<float4*>(sbuf_gen + lane * 128u + (({jj}u ^ (lane & 7u)) << 4)) = "
+        f"make_float4(x[{4 * jj}], x[{4 * jj + 1}], x[{4 * jj + 2}], x[{4 * jj + 3}]);" for jj in range(8))
+    return f"""const uint2 mw = __ldg(reinterpret_cast<const uint2*>(mask + (size_t)row * {wpr}u + (c0 >> 5)));
+                    #pragma unroll 1
+                    for (unsigned c = 0; c < 2u; ++c) {{
+                        unsigned v[32], d[32];
+                        TMEM_LD32(lane_base + {S0}u + b * 64u + c * 32u, v);
+                        TMEM_LD32(lane_base + {DP0}u + b * 64u + c * 32u, d);
+                        TMEM_WAIT_LD();
+                        const unsigned bits = c ? mw.y : mw.x;
+                        float x[32];
+                        #pragma unroll
+                        for (unsigned e = 0; e < 32u; ++e) {{
+                            const float p = ex2(__uint_as_float(v[e]) * {sc2} - st_row.x) * st_row.y;
+                            const float tt = p * (__uint_as_float(d[e]) - d_row);
+                            x[e] = ((bits >> e) & 1u) ? 0.f : tt * {sc};
+                        }}
+                        const unsigned sb = (2u * g + c) & 1u;
+                        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");     // the store before last has left this box
+                        __syncwarp();
+                        unsigned char* sbuf_gen = my_epi_gen + sb * 4096u;
+                        {{
+                            {stage_writes}
+                        }}
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                        __syncwarp();
+                        if (lane == 0) {{
+                            tma_store_3d(&tmOut, my_epi + sb * 4096u, (int)(c0 + c * 32u), (int)(at * 128u + sq * 32u), (int)z);
+                            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                        }}
+                    }}
+                    TC_FENCE_BEFORE();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(sempty + b * 8u);"""
+
+
+def _row_item_end(mode, Tq, Tk, D, OACC, sT, sH, sB, nS) -> str:
+    if mode == "ds":
+        return ""
+    TA = Tk if mode == "dv" else Tq
+    ld = "\n                ".join(
+        f"TMEM_LD32(lane_base + {OACC + 32 * c}u, o + {32 * c});" for c in range(D // 32))
+    store = f"""float* orow = out + (size_t)bb * {sB}ull + (size_t)hh * {sH}ull + (size_t)row * {sT}ull;
+                #pragma unroll
+                for (unsigned e = 0; e < {D}u; e += 4u)
+                    *reinterpret_cast<float4*>(orow + e) = make_float4(__uint_as_float(o[e]) * fac, __uint_as_float(o[e + 1]) * fac,
+                                                                       __uint_as_float(o[e + 2]) * fac, __uint_as_float(o[e + 3]) * fac);"""
+    if mode == "fwd":
+        return f"""{{
+                unsigned o[{D}];
+                float fac;
+                if (nsteps == 0u) {{
+                    // no live key tile at all: every row of this tile is fully masked -> NaN, like the unfused chain
+                    #pragma unroll
+                    for (unsigned e = 0; e < {D}u; ++e) o[e] = 0x7fc00000u;
+                    fac = 1.f;
+                }} else {{
+                    mbar_wait(pvdone, (g - 1u) & 1u);
+                    TC_FENCE_AFTER();
+                    {ld}
+                    TMEM_WAIT_LD();
+                    TC_FENCE_BEFORE();
+                    fac = 1.f / l_run;                                 // l = 0 (a fully masked row): 0 * inf = NaN
+                }}
+                {store}
+                const bool dead = !(l_run > 0.f);
+                stats[(size_t)z * {TA}u + row] = make_float2(dead ? {QNAN} : m_run, dead ? {QNAN} : 1.f / l_run);
+            }}"""
+    return f"""{{
+                unsigned o[{D}];
+                const float fac = 1.f;
+                if (nsteps == 0u) {{
+                    #pragma unroll
+                    for (unsigned e = 0; e < {D}u; ++e) o[e] = 0u;          // no query attends to these keys
+                }} else {{
+                    mbar_wait(pvdone, (g - 1u) & 1u);
+                    TC_FENCE_AFTER();
+                    {ld}
+                    TMEM_WAIT_LD();
+                    TC_FENCE_BEFORE();
+                }}
+                {store}
+            }}"""
+
+
+def tmap4(T: int, D: int, H: int, B: int, strides: tuple, box_rows: int, mn: bool = False) -> dict:
+    """Rank-4 tensor map (D, T, H, B) over a (.., T, .., D) operand with element strides (row, head, batch);
+    K-major box {32, box_rows} with SWIZZLE_128B, or MN-major box {32 columns, 32 rows} with 32-byte atoms."""
+    sT, sH, sB = strides
+    return dict(rank=4, dims=(D, T, H, B), strides=(sT * 4, sH * 4, sB * 4), box=(32, 32 if mn else box_rows, 1, 1),
+                swizzle=4 if mn else 3)

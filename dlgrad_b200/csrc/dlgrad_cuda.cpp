@@ -618,6 +618,64 @@ void *dlg_mm_plan_run(void *plan, const void *a, const void *b) {
     return dlg_mm_plan_run_aux(plan, a, b, nullptr, nullptr);
 }
 
+// ---- fused tensor-core kernels with several (rank <= 5) tensor maps ---------------------
+struct TCPlan {
+    CUfunction fn;
+    unsigned grid, threads, smem;
+    int ntmaps, nptrs;
+    dlg_tmap_desc5 maps[8];
+};
+
+static int encode_tmap5(CUtensorMap *out, const dlg_tmap_desc5 &d, const void *base) {
+    cuuint64_t dims[5], strides[4];
+    cuuint32_t box[5], estr[5] = {1, 1, 1, 1, 1};
+    for (int i = 0; i < 5; ++i) { dims[i] = d.dims[i]; box[i] = d.box[i]; }
+    for (int i = 0; i < 4; ++i) strides[i] = d.strides_bytes[i];
+    CUtensorMapSwizzle sw = d.swizzle == 4   ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B
+                            : d.swizzle == 3 ? CU_TENSOR_MAP_SWIZZLE_128B
+                            : d.swizzle == 2 ? CU_TENSOR_MAP_SWIZZLE_64B
+                            : d.swizzle == 1 ? CU_TENSOR_MAP_SWIZZLE_32B
+                                             : CU_TENSOR_MAP_SWIZZLE_NONE;
+    CU(cuTensorMapEncodeTiled(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, d.rank, const_cast<void *>(base),
+                              dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE));
+    return 0;
+}
+
+void *dlg_tc_plan_create(void *fn, unsigned grid_x, unsigned threads, unsigned smem, int ntmaps,
+                         const dlg_tmap_desc5 *maps, int nptrs) {
+    REQUIRE_READY(nullptr)
+    if (ntmaps < 0 || ntmaps > 8 || nptrs < 0 || nptrs > 8) {
+        fail(-2, "dlg_tc_plan_create: at most 8 tensor maps and 8 pointers");
+        return nullptr;
+    }
+    if (set_smem_attr((CUfunction)fn, smem)) return nullptr;
+    TCPlan *p = new TCPlan;
+    p->fn = (CUfunction)fn;
+    p->grid = grid_x; p->threads = threads; p->smem = smem; p->ntmaps = ntmaps; p->nptrs = nptrs;
+    for (int i = 0; i < ntmaps; ++i) p->maps[i] = maps[i];
+    return p;
+}
+
+int dlg_tc_plan_run(void *plan, const void *const *bases, void *const *ptrs) {
+    TCPlan *p = (TCPlan *)plan;
+    alignas(64) CUtensorMap tm[8];
+    void *pv[8];
+    void *args[16];
+    int n = 0;
+    for (int i = 0; i < p->ntmaps; ++i) {
+        if (int r = encode_tmap5(&tm[i], p->maps[i], bases[i])) return r;
+        args[n++] = &tm[i];
+    }
+    for (int i = 0; i < p->nptrs; ++i) {
+        pv[i] = ptrs[i];
+        args[n++] = &pv[i];
+    }
+    unsigned grid[3] = {p->grid, 1, 1}, block[3] = {p->threads, 1, 1};
+    g_status = 0;
+    return launch_ex(p->fn, grid, block, p->smem, 1, args);
+}
+
 // ---- events / graphs -----------------------------------------------------------------
 void *dlg_event_create(void) {
     REQUIRE_READY(nullptr)

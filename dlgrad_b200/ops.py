@@ -430,7 +430,15 @@ class MatMul(OP):
                         gx = mm(g, yr, batch + (self.p1[-2], self.p1[-1]), trans_y=True)
                 gx = unbroadcast(gx, self.x.shape)
             if self.req_grad[1]:
-                if yr._pending is not None and yr._pending[0] == "tr":
+                rec = None
+                if xr._pending is not None or yr._pending is None:
+                    from dlgrad_b200.runtime.cuda import attention
+                    rec = attention.flash_record(xr, yr)
+                if rec is not None and g._pending is None and g.aligned:
+                    # x is the attention matrix P that the flash forward consumed without writing it: dv = P^T @ dO with
+                    # P recomputed per tile from q, k and the saved row statistics
+                    gy = Buffer(attention.flash_dv(rec, g), batch + (self.p2[-2], self.p2[-1]), dev, g.dtype)
+                elif yr._pending is not None and yr._pending[0] == "tr":
                     gy = lazy_t(mm(g, xr, batch + (self.p2[-1], self.p2[-2]), trans_x=True))
                 else:
                     gy = mm(xr, g, batch + (self.p2[-2], self.p2[-1]), trans_x=True)

@@ -185,3 +185,180 @@ def bwd_chain_matches(chain: list, out_shape: tuple) -> tuple | None:
     if ms != tuple(out_shape[-2:]) or not mask.aligned or mask.scalar is not None:
         return None
     return mask, float(chain[1][2])
+
+
+# =====================================================================================================================
+# Flash-style attention (codegen/cuda_flash.py): P = softmax(masked_fill((q k^T) * scale, mask, fill)) stays DEFERRED
+# (Buffer pending kind "attnP").  `P @ v` then runs ONE kernel that never writes P (flash_forward) and leaves the row
+# statistics (m, 1 / l) behind; the backward of that product recomputes P per tile from q, k and the statistics:
+# dv = P^T dO (flash_dv) and dS = P (dO v^T - rowsum(dO O)) scale (flash_ds).  dS is still written once and read by the
+# two tile-skipping GEMMs dq = dS k, dk = dS^T q.  Whoever reads P itself (att.numpy(), another op) gets it from
+# attn_scores_tc as before — same values, the reference's semantics (examples/gpt.py:49-55) untouched.
+# DLGRAD_FLASH_ATTN=0 switches the deferral off (the round-1 kernels then run).
+# =====================================================================================================================
+FLASH = os.environ.get("DLGRAD_FLASH_ATTN", "1") != "0"
+FLASH_TAU = float(os.environ.get("DLGRAD_FLASH_TAU", "8"))     # see cuda_flash.flash_attn: 0 forces the O-rescale path
+_flash: dict = {}            # id(P Buffer) -> record of the forward that consumed it
+_tc_plans: dict = {}
+
+
+class _FlashRecord:
+    __slots__ = ("q", "k", "v", "scale", "mask", "fill", "stats", "bits", "geom")
+
+
+def softmax_deferred(x: Buffer, dim: int):
+    """`x.softmax(dim)` where x is the pending chain (q @ k^T) * scale -> masked_fill(mask2d, fill) over attention-shaped
+    operands: returns P as a deferred Buffer, or None when the pattern does not apply."""
+    from dlgrad_b200.runtime.cuda import ops as _ops
+    shape = x.metadata.shape
+    if not (FLASH and ENABLED) or x._pending is None or dim % len(shape) != len(shape) - 1:
+        return None
+    chain, base = _ops._peel_chain(x)
+    bp = base._pending
+    if bp is None or bp[0] != "mm" or len(bp) != 3:
+        return None
+    m = chain_matches(chain, shape)
+    q, kt = bp[1], bp[2]
+    if m is None or kt._pending is None or kt._pending[0] != "tr":
+        return None
+    return Buffer._deferred(("attnP", q, kt._pending[1], m[0], m[1], m[2]), shape, x.metadata.dtype)
+
+
+def materialize_p(buf: Buffer):
+    """Somebody reads P itself: produce it with the fused scores kernel (round 1), exactly as before."""
+    _, q, k, scale, mask, fill = buf._pending
+    ptr = scores(q, k, scale, mask, fill)
+    buf.ptr = ptr
+    claim(buf)
+
+
+def _geom(q: Buffer, k: Buffer):
+    xs, ks = q.metadata.shape, k.metadata.shape
+    Tq, D, Tk = xs[-2], xs[-1], ks[-2]
+    H = xs[-3] if len(xs) >= 4 else 1
+    nb = prod_(xs[:-2])
+    return nb, H, nb // H, Tq, Tk, D
+
+
+def _strides(T: int, D: int, H: int):
+    """element strides (row, head, batch) of a contiguous (B, H, T, D) operand"""
+    return (D, T * D, H * T * D)
+
+
+def _tc_plan(kern, maps: list, nptrs: int):
+    fn = compiler.get_function(kern.name, kern.source)
+    arr = shim.ffi.new("dlg_tmap_desc5[]", len(maps))
+    for t, d in zip(arr, maps):
+        t.rank = d["rank"]
+        for i in range(5):
+            t.dims[i] = d["dims"][i] if i < d["rank"] else 1
+            t.box[i] = d["box"][i] if i < d["rank"] else 1
+        for i in range(4):
+            t.strides_bytes[i] = d["strides"][i] if i < d["rank"] - 1 else 0
+        t.swizzle = d["swizzle"]
+    p = shim.lib.dlg_tc_plan_create(fn, kern.grid[0], kern.threads, kern.smem, len(maps), arr, nptrs)
+    if p == shim.NULL:
+        raise RuntimeError("dlg_tc_plan_create failed: " + shim.last_error())
+    return p
+
+
+def _tc_run(plan, bases: list, ptrs: list, what: str) -> None:
+    b = shim.ffi.new("const void *[]", bases)
+    p = shim.ffi.new("void *[]", ptrs)
+    if shim.lib.dlg_tc_plan_run(plan, b, p) != 0:
+        raise RuntimeError(f"{what} launch failed: " + shim.last_error())
+
+
+def _timed(tag: tuple, flops: float, fn):
+    timer = _profile.matmul_timer
+    if timer is None:
+        return fn()
+    t0 = timer.start()
+    out = fn()
+    timer.stop(t0, flops, tag)
+    return out
+
+
+def flash_forward(P: Buffer, v: Buffer):
+    """O = P @ v for a deferred P, without materialising P.  Returns the owned pointer of O (batch.., Tq, D), or None when
+    v does not fit the pattern (the caller then takes the ordinary route, which materialises P)."""
+    from dlgrad_b200.codegen import cuda_flash as cf
+    from dlgrad_b200.runtime.cuda import ops as _ops
+    _, q, k, scale, mask, fill = P._pending
+    nb, H, B, Tq, Tk, D = _geom(q, k)
+    vs = v.metadata.shape
+    if (v._pending is not None or v.scalar is not None or not v.aligned or tuple(vs) != tuple(k.metadata.shape)
+            or q._pending is not None or k._pending is not None):
+        return None
+    key = ("fwd", nb, H, Tq, Tk, D, scale, fill, FLASH_TAU)
+    plan = _tc_plans.get(key)
+    if plan is None:
+        so = _strides(Tq, D, H)
+        kern = cf.flash_attn("fwd", Tq, Tk, D, H, nb, scale, fill, so, FLASH_TAU)
+        maps = [cf.tmap4(Tq, D, H, B, _strides(Tq, D, H), 128), cf.tmap4(Tk, D, H, B, _strides(Tk, D, H), 64),
+                cf.tmap4(Tk, D, H, B, _strides(Tk, D, H), 32, mn=True)]
+        plan = _tc_plans[key] = _tc_plan(kern, maps, 3)
+    bits = _mask_digest(mask, Tq, Tk)
+    out = shim.alloc(nb * Tq * D * 4)
+    stats = shim.alloc(nb * Tq * 8)
+    pq, pk, pv = _ops._dev_ptr(q), _ops._dev_ptr(k), _ops._dev_ptr(v)
+    _timed(("attn_flash_fwd", Tq, Tk, D, nb), 4.0 * nb * Tq * Tk * D,
+           lambda: _tc_run(plan, [pq, pk, pv], [out, stats, bits], "flash attention forward"))
+    rec = _FlashRecord()
+    rec.q, rec.k, rec.v, rec.scale, rec.mask, rec.fill, rec.stats, rec.bits = q, k, v, scale, mask, fill, stats, bits
+    rec.geom = (nb, H, B, Tq, Tk, D)
+    _flash[id(P)] = rec
+    weakref.finalize(P, _flash.pop, id(P), None)
+    return out
+
+
+def flash_record(P: Buffer, v: Buffer | None = None):
+    rec = _flash.get(id(P))
+    if rec is None or (v is not None and rec.v is not v):
+        return None
+    return rec
+
+
+def flash_dv(rec, dO: Buffer):
+    """dv = P^T @ dO with P recomputed per tile from q, k and the saved row statistics."""
+    from dlgrad_b200.codegen import cuda_flash as cf
+    from dlgrad_b200.runtime.cuda import ops as _ops
+    nb, H, B, Tq, Tk, D = rec.geom
+    key = ("dv", nb, H, Tq, Tk, D, rec.scale, rec.fill)
+    plan = _tc_plans.get(key)
+    if plan is None:
+        kern = cf.flash_attn("dv", Tq, Tk, D, H, nb, rec.scale, rec.fill, _strides(Tk, D, H))
+        maps = [cf.tmap4(Tk, D, H, B, _strides(Tk, D, H), 128), cf.tmap4(Tq, D, H, B, _strides(Tq, D, H), 64),
+                cf.tmap4(Tq, D, H, B, _strides(Tq, D, H), 32, mn=True)]
+        plan = _tc_plans[key] = _tc_plan(kern, maps, 3)
+    out = shim.alloc(nb * Tk * D * 4)
+    pk, pq, pd = _ops._dev_ptr(rec.k), _ops._dev_ptr(rec.q), _ops._dev_ptr(dO)
+    _timed(("attn_flash_dv", Tq, Tk, D, nb), 4.0 * nb * Tq * Tk * D,
+           lambda: _tc_run(plan, [pk, pq, pd], [out, rec.stats, rec.bits], "flash attention dV"))
+    return out
+
+
+def flash_ds(rec, dO: Buffer, O: Buffer, dS_owner: Buffer):
+    """dS = masked_fill(P * (dO @ v^T - rowsum(dO * O)), mask, 0) * scale with P and dP recomputed per tile; returns the
+    owned pointer and registers the live-tile table for the GEMMs that read dS."""
+    from dlgrad_b200.codegen import cuda_flash as cf
+    from dlgrad_b200.codegen import cuda_kernel as ck
+    from dlgrad_b200.runtime.cuda import ops as _ops
+    nb, H, B, Tq, Tk, D = rec.geom
+    key = ("ds", nb, H, Tq, Tk, D, rec.scale, rec.fill)
+    ent = _tc_plans.get(key)
+    if ent is None:
+        kern = cf.flash_attn("ds", Tq, Tk, D, H, nb, rec.scale, rec.fill)
+        sq, sk = _strides(Tq, D, H), _strides(Tk, D, H)
+        maps = [cf.tmap4(Tq, D, H, B, sq, 128), cf.tmap4(Tq, D, H, B, sq, 128), cf.tmap4(Tk, D, H, B, sk, 64),
+                cf.tmap4(Tk, D, H, B, sk, 64),
+                dict(rank=3, dims=(Tk, Tq, nb), strides=(Tk * 4, Tq * Tk * 4), box=(32, 32, 1), swizzle=3)]
+        ent = _tc_plans[key] = (_tc_plan(kern, maps, 4), _ops.Plan(ck.rowdot(nb * Tq, D)))
+    plan, dot_plan = ent
+    delta = dot_plan.run(_ops._dev_ptr(dO), _ops._dev_ptr(O))
+    out = shim.alloc(nb * Tq * Tk * 4)
+    pq, pd, pk, pv = _ops._dev_ptr(rec.q), _ops._dev_ptr(dO), _ops._dev_ptr(rec.k), _ops._dev_ptr(rec.v)
+    _timed(("attn_flash_ds", Tq, Tk, D, nb), 4.0 * nb * Tq * Tk * D,
+           lambda: _tc_run(plan, [pq, pd, pk, pv, out], [out, rec.stats, delta, rec.bits], "flash attention dS"))
+    _fresh[shim.address(out)] = (rec.bits, rec.bits + Tq * Tk // 32, Tq, Tk)
+    return out

@@ -189,17 +189,30 @@ def materialize(buf: Buffer) -> None:
     if pend[0] == "relu":
         buf.ptr = pend[1].relu().ptr
         return
+    if pend[0] == "attnP":
+        from dlgrad_b200.runtime.cuda import attention
+        attention.materialize_p(buf)
+        return
     chain, base = _peel_chain(buf)
     shape = buf.metadata.shape
     bp = base._pending
     if bp is not None and bp[0] == "softmax_bwd":
         _, y, g, dim, kind = bp
         gp = g._pending
-        if gp is not None and gp[0] == "mm" and len(gp) == 4 and kind == "softmax" and y._pending is None:
+        if gp is not None and gp[0] == "mm" and len(gp) == 4 and kind == "softmax":
             # upstream is the deferred dP = dO @ v^T of an attention block (ops.MatMul.backward): dS in one kernel
             from dlgrad_b200.runtime.cuda import attention
             m = attention.bwd_chain_matches(chain, shape)
             vt = gp[2]
+            rec = attention.flash_record(y)
+            if (rec is not None and m is not None and vt._pending is not None and vt._pending[0] == "tr" and gp[3] is not None
+                    and vt._pending[1] is rec.v and m[0] is rec.mask and m[1] == rec.scale and gp[1]._pending is None):
+                # P was never written (flash forward): recompute it per tile from q, k and the row statistics
+                buf.ptr = attention.flash_ds(rec, gp[1], gp[3], buf)
+                attention.claim(buf)
+                return
+            if y._pending is not None:
+                materialize(y)                      # the round-1 kernel below reads P
             if m is not None and vt._pending is not None and vt._pending[0] == "tr" and gp[3] is not None:
                 buf.ptr = attention.dscores(gp[1], vt._pending[1], gp[3], y, m[0], m[1])
                 attention.claim(buf)                # dS carries the live-tile table for the two GEMMs that read it

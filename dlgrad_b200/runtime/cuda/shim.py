@@ -101,6 +101,8 @@ class _CompileOnlyLib:
         return self._addr(int(ffi.cast("uintptr_t", plan)) - 1)
     def dlg_mm_plan_run_into(self, plan, c, a, b): self.launches += 1; return 0
     def dlg_mm_plan_run_aux(self, plan, a, b, aux0, aux1): return self.dlg_mm_plan_run(plan, a, b)
+    def dlg_tc_plan_create(self, fn, grid, threads, smem, ntmaps, maps, nptrs): return ffi.cast("void *", 1)
+    def dlg_tc_plan_run(self, plan, bases, ptrs): self.launches += 1; return 0
     def dlg_event_create(self): return ffi.cast("void *", 1)
     def dlg_event_record(self, e): return 0
     def dlg_event_sync(self, e): return 0

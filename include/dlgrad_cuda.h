@@ -109,6 +109,23 @@ int   dlg_mm_plan_run_into(void *plan, void *c, const void *a, const void *b);
  * dlgrad/tensor.py:534), `aux1` = the zeroed flag workspace of a stream-K plan.  Either may be NULL. */
 void *dlg_mm_plan_run_aux(void *plan, const void *a, const void *b, const void *aux0, void *aux1);
 
+/* ---- fused tensor-core kernels with several tensor maps --------------------------------
+ * The flash-attention kernels (dlgrad_b200/codegen/cuda_flash.py; they replace the MATMUL / MUL / MASKED_FILL /
+ * softmax / MATMUL chain of examples/gpt.py:49-55, dlgrad/tensor.py:634-649) read q, k, v, dO through rank-4 tensor
+ * maps (D, T, heads, batch) — so the (B, T, h, D) layout the projections produce needs no permute kernel — and take
+ * several plain pointers.  Kernel signature: (CUtensorMap x ntmaps, pointer x nptrs). */
+typedef struct dlg_tmap_desc5 {
+    uint32_t rank;                  /* 2..5                                                 */
+    uint64_t dims[5];               /* innermost first, elements                            */
+    uint64_t strides_bytes[4];      /* strides of dims[1..4]                                */
+    uint32_t box[5];
+    uint32_t swizzle;               /* as dlg_tmap_desc                                     */
+} dlg_tmap_desc5;
+void *dlg_tc_plan_create(void *fn, unsigned grid_x, unsigned threads, unsigned smem_bytes,
+                         int ntmaps, const dlg_tmap_desc5 *maps, int nptrs);
+/* bases[ntmaps]: device address each tensor map is encoded over; ptrs[nptrs]: the pointer parameters */
+int   dlg_tc_plan_run(void *plan, const void *const *bases, void *const *ptrs);
+
 /* ---- timing / graphs -----------------------------------------------------------------*/
 void *dlg_event_create(void);
 int   dlg_event_record(void *ev);            /* on the compute stream                        */

@@ -70,7 +70,9 @@ def test_c5_transformer_block_forward_backward_vs_oracle(oracle):
             keep[tok] = False
             scale = float(np.abs(b).max())
             check(a[0][~keep], b[0][~keep], rtol=1e-2, atol=1e-2 * scale, what="C5 block dx, tokens with a flipped relu unit")
-            runner.rel_check(check, a[0][keep], b[0][keep], runner.TOL_MATMUL, "C5 block dx")
+            # the flipped tokens' gradient also reaches earlier tokens through the attention backward (dk, dv): second
+            # order, measured <= 1.6e-4 of the largest magnitude on 18 of 783 k entries -> 3e-4 for the other tokens
+            runner.rel_check(check, a[0][keep], b[0][keep], 3e-4, "C5 block dx")
         elif k == "dc_fc" and len(unit):
             keep = np.ones(3072, dtype=bool)
             keep[unit] = False
@@ -302,3 +304,131 @@ def test_device_side_sampling_distribution_and_generate_loop():
     if not COMPILE_ONLY:
         assert out.shape == (13,) and out[0] == 5 and ((out >= 0) & (out < V)).all() and (out == np.round(out)).all()
         assert io["d2h_bytes"] == 0, f"the generate loop copied {io['d2h_bytes']} bytes to the host"
+
+
+def _attention_inputs(B, H, T, D, mask_kind, seed):
+    rng = np.random.default_rng(seed)
+    q, k, v = ((rng.random((B, H, T, D), dtype=np.float32) - 0.5).astype(np.float32) * 2 for _ in range(3))
+    if mask_kind == "causal":
+        mask = np.triu(np.ones((T, T), dtype=np.float32), 1)
+    elif mask_kind == "random":
+        mask = np.minimum((rng.random((T, T)) > 0.6).astype(np.float32), 1.0 - np.eye(T, dtype=np.float32))      # no dead rows
+    elif mask_kind == "growing":         # scores that keep growing along the keys: the running maximum moves at every step
+        mask = np.triu(np.ones((T, T), dtype=np.float32), 1)
+        k = (k * (1.0 + np.arange(T, dtype=np.float32)[None, None, :, None] / 32.0)).astype(np.float32)
+        q = np.abs(q).astype(np.float32)
+        k = np.abs(k).astype(np.float32)
+    else:                                # "dead_rows": some query rows have no unmasked key at all
+        mask = np.maximum(rng.random((T, T)) > 0.5, (np.arange(T)[:, None] % 37 == 0)).astype(np.float32)
+    w = np.linspace(0.5, 1.5, B * H * T * D, dtype=np.float32).reshape(B, H, T, D)
+    return q, k, v, mask, w
+
+
+def _attention_block(dev, q, k, v, mask, w, fill, scale, backward=True):
+    from dlgrad_b200 import Tensor
+    Q, K, V = (Tensor(a.copy(), device=dev, requires_grad=True) for a in (q, k, v))
+    att = ((Q @ K.transpose(2, 3)) * scale).masked_fill(Tensor(mask.copy(), device=dev), fill).softmax(dim=3)
+    y = att @ V
+    out = [y.numpy()]
+    if backward:
+        (y * Tensor(w.copy(), device=dev)).sum().backward()
+        out += [Q.grad.numpy(), K.grad.numpy(), V.grad.numpy()]
+    return out, att
+
+
+def _attention_f64(q, k, v, mask, w, fill, scale):
+    """float64 forward and backward of y = softmax(masked_fill(q k^T scale, mask, fill)) v, loss = sum(y * w)."""
+    q, k, v, w = (a.astype(np.float64) for a in (q, k, v, w))
+    s = np.einsum("bhqd,bhkd->bhqk", q, k) * scale
+    s = np.where(mask > 0, fill, s)
+    with np.errstate(invalid="ignore"):
+        e = np.exp(s - s.max(axis=3, keepdims=True))
+        p = e / e.sum(axis=3, keepdims=True)
+    y = p @ v
+    dv = np.einsum("bhqk,bhqd->bhkd", p, w)
+    dp = np.einsum("bhqd,bhkd->bhqk", w, v)
+    ds = p * (dp - (dp * p).sum(axis=3, keepdims=True))
+    ds = np.where(mask > 0, 0.0, ds) * scale
+    return [y, ds @ k, np.einsum("bhqk,bhqd->bhkd", ds, q), dv]
+
+
+@pytest.mark.parametrize("B,H,T,D,mask_kind,fill,tau", [
+    (2, 16, 512, 64, "causal", float("-inf"), 8.0),
+    (2, 16, 512, 64, "growing", float("-inf"), 0.0),        # forces the rescale of O in tensor memory at every step
+    (2, 16, 512, 64, "growing", float("-inf"), 8.0),        # the lazy maximum under steadily growing scores
+    (1, 16, 1024, 32, "random", float("-inf"), 8.0),        # head dim 32, a mask without structure
+    (1, 16, 512, 64, "causal", -5.0, 8.0),                   # finite fill: P is dense, nothing may be skipped
+    (8, 12, 1024, 64, "causal", float("-inf"), 8.0),        # the benchmark's attention
+])
+def test_flash_attention_forward_and_backward(oracle, B, H, T, D, mask_kind, fill, tau):
+    """The flash-style kernels (codegen/cuda_flash.py: P never written forward or backward; dv and dS recomputed from
+    q, k and the saved row statistics) against float64 — y, dq, dk, dv — and, at the sizes the oracle finishes in
+    seconds, against the oracle, which runs the reference's unfused graph (examples/gpt.py:49-55).  Tolerances: y and
+    dv 1e-4 of the largest magnitude (two chained matmuls), dq / dk 1e-4 as well (the round-1 kernels needed 5e-5
+    against each other; float64 is the stricter judge)."""
+    from dlgrad_b200.runtime.cuda import attention
+    q, k, v, mask, w = _attention_inputs(B, H, T, D, mask_kind, T + D + B)
+    scale = float(1.0 / np.sqrt(D))
+    old = (attention.FLASH, attention.FLASH_TAU, attention.MIN_SCORES)
+    attention.FLASH, attention.FLASH_TAU, attention.MIN_SCORES = True, tau, 1 << 20
+    try:
+        got, att = _attention_block("cuda", q, k, v, mask, w, fill, scale)
+        if not COMPILE_ONLY:
+            assert att.data._pending is not None and att.data._pending[0] == "attnP", "P must never have been materialised"
+            kinds = {key[0] for key in attention._tc_plans}
+            assert {"fwd", "dv", "ds"} <= kinds, f"expected the three flash kernels, got {kinds}"
+        ref = _attention_f64(q, k, v, mask, w, fill, scale)
+        for a, b, what in zip(got, ref, ("y", "dq", "dk", "dv")):
+            runner.rel_check(check, a, b, 1e-4, f"flash attention {what} vs float64 ({mask_kind}, tau {tau})")
+        if B * H * T * T <= (1 << 23):
+            orc, _ = _attention_block("cpu", q, k, v, mask, w, fill, scale)
+            for a, b, what in zip(got, orc, ("y", "dq", "dk", "dv")):
+                runner.rel_check(check, a, b, 1e-4, f"flash attention {what} vs oracle ({mask_kind}, tau {tau})")
+        # the probabilities themselves, read after the fact, are what the fused scores kernel / the eager chain give
+        p = att.numpy()
+        if not COMPILE_ONLY:
+            s = np.einsum("bhqd,bhkd->bhqk", q.astype(np.float64), k.astype(np.float64)) * scale
+            s = np.where(mask > 0, fill, s)
+            e = np.exp(s - s.max(axis=3, keepdims=True))
+            # ("growing" drives the logits to ~50: an fp32 logit then carries ~5e-6 of absolute error, which IS the relative
+            # error of its probability — the per-element 1e-5 applies to logits of ordinary size)
+            big = mask_kind == "growing"
+            runner.rel_check(check, p, e / e.sum(axis=3, keepdims=True), 1e-4 if big else runner.TOL_ELEMENTWISE,
+                             "P read after the flash forward", elementwise=not big)
+        # same bits when run again (fixed summation order everywhere)
+        again, _ = _attention_block("cuda", q, k, v, mask, w, fill, scale)
+        for a, b, what in zip(got, again, ("y", "dq", "dk", "dv")):
+            check(a, b, exact=True, what=f"flash attention {what}: second run")
+    finally:
+        attention.FLASH, attention.FLASH_TAU, attention.MIN_SCORES = old
+
+
+def test_flash_attention_dead_rows_and_round1_kernels(oracle):
+    """(1) Query rows without any unmasked key: y is NaN exactly where the unfused chain has NaN, finite rows agree.
+    (2) With DLGRAD_FLASH_ATTN off the round-1 kernels (attn_scores_tc / attn_dscores_tc + tile-skipping GEMMs), which
+    remain the materialisers of P, still give the same block."""
+    from dlgrad_b200.runtime.cuda import attention
+    B, H, T, D = 4, 8, 512, 32
+    q, k, v, mask, w = _attention_inputs(B, H, T, D, "dead_rows", 5)
+    scale = float(1.0 / np.sqrt(D))
+    old = (attention.FLASH, attention.MIN_SCORES)
+    attention.MIN_SCORES = 1 << 20
+    try:
+        attention.FLASH = True
+        flash, _ = _attention_block("cuda", q, k, v, mask, w, float("-inf"), scale, backward=False)
+        ref = _attention_f64(q, k, v, mask, w, float("-inf"), scale)[0]
+        if not COMPILE_ONLY:
+            assert np.isnan(ref).any() and (np.isnan(flash[0]) == np.isnan(ref)).all()
+            ok = ~np.isnan(ref)
+            runner.rel_check(check, flash[0][ok], ref[ok], 1e-4, "flash forward with dead rows vs float64")
+        q, k, v, mask, w = _attention_inputs(2, 16, 512, 64, "causal", 6)
+        attention.FLASH = False
+        r1, att = _attention_block("cuda", q, k, v, mask, w, float("-inf"), 0.125)
+        attention.FLASH = True
+        fl, _ = _attention_block("cuda", q, k, v, mask, w, float("-inf"), 0.125)
+        if not COMPILE_ONLY:
+            assert att.data._pending is None, "with the flash path off P is materialised by the fused scores kernel"
+        for a, b, what in zip(fl, r1, ("y", "dq", "dk", "dv")):
+            runner.rel_check(check, a, b, 1e-4, f"{what}: flash vs round-1 fused kernels")
+    finally:
+        attention.FLASH, attention.MIN_SCORES = old
