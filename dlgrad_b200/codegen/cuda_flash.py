@@ -21,11 +21,13 @@ Every product is 3xTF32 (a_lo b_hi + a_hi b_lo + a_hi b_hi, fp32 accumulate), so
 (north star: matmul <= 1e-4, softmax <= 1e-5 relative).  kind::tf32 truncates its inputs, so a staged fp32 tile IS its
 own `hi`; only `lo` tiles are computed (splitter warps for the streamed operands, the row threads for A and P).
 
-Warp roles (320 threads, one persistent CTA per SM):
-    warp 0      TMA producer: A tile(s) of the next item, then per step the two streamed tiles of the ring stage
-    warp 1      MMA issuer (one elected lane)
-    warps 2-5   row warps: thread = row of the 128-row score tile = TMEM lane
-    warps 6-9   splitter: lo = x - trunc_tf32(x) for the staged tiles of a stage (twin buffers, same swizzled layout)
+Warp roles (448 threads, one persistent CTA per SM):
+    warp 0       TMA producer: A tile(s) of the next item, then per step the two streamed tiles of the ring stage
+    warp 1       MMA issuer (one elected lane)
+    warps 2-9    row warps: thread = row of the 128-row score tile = TMEM lane; two warps per lane quarter, each owns 32
+                 of the 64 score columns of a step (the row work — TMEM reads, exponentials, hi | lo splits, TMEM writes —
+                 paces these kernels, not the tensor pipe: with four row warps the forward ran at 50 % pipe utilisation)
+    warps 10-13  splitter: lo = x - trunc_tf32(x) for the staged tiles of a stage (twin buffers, same swizzled layout)
 """
 from __future__ import annotations
 
@@ -95,9 +97,10 @@ def flash_attn(mode: str, Tq: int, Tk: int, D: int, H: int, NB: int, scale: floa
     rescaled almost never instead of almost always (tau = 0 forces the rescale path; the tests use it).
 
     Kernel parameters
-      fwd: tmQ, tmK, tmV, O, stats (float2 per row: m in base-2 units, 1 / l; NaN for a row without a live entry), bits
-      dv : tmK, tmQ, tmDO, dV, stats, bits
-      ds : tmQ, tmDO, tmK, tmV, tmDS, dS, stats, delta, bits          (bits: cuda_kernel.mask_bits of the (Tq, Tk) mask)"""
+      fwd: tmQ, tmK, tmV, O, lse (one float per row: log2 of the row's sum of 2^(s c), i.e. P = 2^(s c - lse); NaN for a
+           row without a live entry), bits
+      dv : tmK, tmQ, tmDO, dV, lse, bits
+      ds : tmQ, tmDO, tmK, tmV, tmDS, dS, lse, delta, bits            (bits: cuda_kernel.mask_bits of the (Tq, Tk) mask)"""
     assert mode in ("fwd", "dv", "ds") and Tq % 128 == 0 and Tk % 128 == 0 and D in (32, 64) and scale > 0
     assert max(Tq, Tk) // 128 <= 32
     kbq = D // 32
@@ -112,10 +115,11 @@ def flash_attn(mode: str, Tq: int, Tk: int, D: int, H: int, NB: int, scale: floa
     per_stage = 2 * raw_b                                    # B1 raw | B2 raw | B1 lo | B2 lo
     a_tiles = 2 if mode == "ds" else 1
     a_bytes = a_tiles * kbq * 16384
-    epi_bytes = 4 * 2 * 4096 if mode == "ds" else 0          # two 32x32 staging boxes per row warp for the dS store
-    budget = 227 * 1024 - 1024 - 512 - a_bytes - epi_bytes
+    epi_bytes = 8 * 4096 if mode == "ds" else 0              # one 32x32 staging box per row warp for the dS store
+    tail_bytes = 256 + 1024                                  # barriers | end-of-item exchange of the row sums (fwd)
+    budget = 227 * 1024 - 1024 - tail_bytes - a_bytes - epi_bytes
     stages = max(2, min(3, budget // per_stage))
-    smem = a_bytes + stages * per_stage + epi_bytes + 1024 + 512
+    smem = a_bytes + stages * per_stage + epi_bytes + 1024 + tail_bytes
     if mode == "ds":
         S0, DP0, A0, A1 = 0, 128, 256, 256 + 2 * D
         PHI = PLO = OACC = 0
@@ -146,13 +150,13 @@ def flash_attn(mode: str, Tq: int, Tk: int, D: int, H: int, NB: int, scale: floa
     if mode == "ds":
         params = ("const __grid_constant__ TMap tmA, const __grid_constant__ TMap tmA2, const __grid_constant__ TMap tmB1, "
                   "const __grid_constant__ TMap tmB2, const __grid_constant__ TMap tmOut, float* __restrict__ out, "
-                  "const float2* __restrict__ stats, const float* __restrict__ delta, const unsigned* __restrict__ mask")
+                  "const float* __restrict__ lse, const float* __restrict__ delta, const unsigned* __restrict__ mask")
     elif mode == "fwd":
         params = ("const __grid_constant__ TMap tmA, const __grid_constant__ TMap tmB1, const __grid_constant__ TMap tmB2, "
-                  "float* __restrict__ out, float2* __restrict__ stats, const unsigned* __restrict__ mask")
+                  "float* __restrict__ out, float* __restrict__ lse, const unsigned* __restrict__ mask")
     else:
         params = ("const __grid_constant__ TMap tmA, const __grid_constant__ TMap tmB1, const __grid_constant__ TMap tmB2, "
-                  "float* __restrict__ out, const float2* __restrict__ stats, const unsigned* __restrict__ mask")
+                  "float* __restrict__ out, const float* __restrict__ lse, const unsigned* __restrict__ mask")
 
     # ------------------------------------------------------------------ producer: streamed tiles of one step
     if mode == "ds":       # K block and V block, both K-major (64 rows x D)
@@ -201,7 +205,7 @@ def flash_attn(mode: str, Tq: int, Tk: int, D: int, H: int, NB: int, scale: floa
                         }}"""
 
     src = _HELPERS + _HELPERS_TS + _EXTRA + _sub(r"""
-extern "C" __global__ void __launch_bounds__(320, 1)
+extern "C" __global__ void __launch_bounds__(448, 1)
 $KNAME$($PARAMS$)
 {
     extern __shared__ unsigned char smem_raw[];
@@ -213,6 +217,7 @@ $KNAME$($PARAMS$)
     const unsigned kfull = bars, kempty = bars + $STAGES$u * 8u, ksplit = bars + $STAGES$u * 16u;
     const unsigned sfull = bars + $STAGES$u * 24u, sempty = sfull + 16u, pready = sempty + 16u, pvdone = pready + 8u;
     const unsigned qfull = pvdone + 8u, qsplit = qfull + 8u, qfree = qsplit + 8u;
+    float* xch = reinterpret_cast<float*>(smem_gen + (bars - smem) + 256u);      // [8 row warps][32]
     __shared__ unsigned tmem_slot;
     const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
 
@@ -239,12 +244,12 @@ $KNAME$($PARAMS$)
         }
         for (unsigned b = 0; b < 2u; ++b) {
             mbar_init(sfull + b * 8u, 1u);
-            mbar_init(sempty + b * 8u, 4u);
+            mbar_init(sempty + b * 8u, 8u);
         }
-        mbar_init(pready, 4u);
+        mbar_init(pready, 8u);
         mbar_init(pvdone, 1u);
         mbar_init(qfull, 1u);
-        mbar_init(qsplit, 4u);
+        mbar_init(qsplit, $NSPLIT$u);
         mbar_init(qfree, 1u);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -331,16 +336,18 @@ $KNAME$($PARAMS$)
             it += nsteps;
             g += nsteps;
         }
-    } else if (warp < 6u) {
-        // ===== row warps: thread = row of the score tile = TMEM lane =====
+    } else if (warp < 10u) {
+        // ===== row warps: thread = row of the score tile = TMEM lane; warps 2-5 own score columns 0-31 of a step, 6-9 columns 32-63 =====
         const unsigned sq = warp & 3u;                            // the TMEM lane quarter this warp may access
+        const unsigned wh = (warp >= 6u) ? 1u : 0u;               // which 32 of a step's 64 score columns this warp owns
         const unsigned lane_base = tmem_base + ((sq * 32u) << 16);
         unsigned g = 0, n = 0, z, at;
         auto split_a = [&](unsigned nn) {
             mbar_wait(qfull, nn & 1u);                             // the tile has landed in shared memory
             if (nn != 0u) { mbar_wait(qfree, (nn - 1u) & 1u); TC_FENCE_AFTER(); }    // and the previous item no longer reads A
+            if ($A_KBLOCKS$u < 2u && wh != 0u) return;             // a single k-block: the first warp of the pair splits it
             #pragma unroll 1
-            for (unsigned kk = 0; kk < $A_KBLOCKS$u; ++kk) {
+            for (unsigned kk = ($A_KBLOCKS$u < 2u ? 0u : wh); kk < $A_KBLOCKS$u; kk += 2u) {
                 const unsigned char* arow = smem_gen + kk * 16384u + (sq * 32u + lane) * 128u;
                 float x[32];
                 #pragma unroll
@@ -382,7 +389,7 @@ $KNAME$($PARAMS$)
         $ROW_EXIT$
     } else {
         // ===== splitter warps: lo = x - trunc_tf32(x) for the two staged tiles of a step =====
-        const unsigned ctid = threadIdx.x - 192u;
+        const unsigned ctid = threadIdx.x - 320u;
         unsigned it = 0, n = 0, z, at;
         for (; item_at(n, z, at); ++n) {
             const unsigned nsteps = 2u * __popc(live_tiles(at));
@@ -415,7 +422,7 @@ $KNAME$($PARAMS$)
 }
 """,
         KNAME=KNAME, PARAMS=params, A_BYTES=a_bytes, RING_BYTES=stages * per_stage, EPI_BYTES=epi_bytes, STAGES=stages,
-        LIVE=live, GRID=grid, ITEMS=items, NB=NB, TILE_OF=tile_of, H=H, A_LOADS=a_loads, NS=nS, PER_STAGE=per_stage,
+        NSPLIT=8 if a_tiles * kbq >= 2 else 4, LIVE=live, GRID=grid, ITEMS=items, NB=NB, TILE_OF=tile_of, H=H, A_LOADS=a_loads, NS=nS, PER_STAGE=per_stage,
         RAW_B=raw_b, B1_LOADS=b1_loads, B2_LOADS=b2_loads, TILE_B=tile_b, PER_STAGE16=per_stage // 16,
         S_MMA=s_mma(f"tmem_base + {S0}u + b * 64u", A0, 0),
         DP_MMA=s_mma(f"tmem_base + {DP0}u + b * 64u", A1, tile_b // 16) if mode == "ds" else "",
@@ -440,26 +447,27 @@ $KNAME$($PARAMS$)
         ROW_EXIT='if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");' if mode == "ds" else "",
         RAW_V4=raw_b // 16)
     out_elems = {"fwd": NB * Tq * D, "dv": NB * Tk * D, "ds": NB * Tq * Tk}[mode]
-    return TcKernel(f"flash_{mode}", src, (grid, 1, 1), 320, smem, out_elems, 64, stages)
+    return TcKernel(f"flash_{mode}", src, (grid, 1, 1), 448, smem, out_elems, 64, stages)
 
 
 def _row_item_begin(mode: str, Tq: int, Tk: int) -> str:
     if mode == "fwd":
-        return f"float m_run = {NEG_INF}, l_run = 0.f;"
+        return f"float m_run = {NEG_INF}, l_run = 0.f;      // l_run: this warp's 32 columns of every step only"
     if mode == "ds":
-        return f"""const float2 st_row = __ldg(stats + (size_t)z * {Tq}u + row);      // (m, 1 / l) of this query row
+        return f"""const float lse_row = __ldg(lse + (size_t)z * {Tq}u + row);       // P = 2^(s c - lse) for this query row
             const float d_row = __ldg(delta + (size_t)z * {Tq}u + row);       // rowsum(dO * O)
-            const unsigned my_epi = epi + (warp - 2u) * 8192u;
-            unsigned char* my_epi_gen = smem_gen + (epi - smem) + (warp - 2u) * 8192u;
-            // streamed tiles the mask kills entirely: dS is zero there whatever P and dP hold (eight lanes per 128-byte row)
+            const unsigned my_epi = epi + (warp - 2u) * 4096u;
+            unsigned char* sbuf_gen = smem_gen + (epi - smem) + (warp - 2u) * 4096u;
+            // streamed tiles the mask kills entirely: dS is zero there whatever P and dP hold (eight lanes per 128-byte row;
+            // each warp of a pair clears its 64 of the 128 columns)
             for (unsigned t = 0; t < {Tk // 128}u; ++t) {{
                 if ((lm >> t) & 1u) continue;
-                float* dst = out + ((size_t)z * {Tq}u + at * 128u + sq * 32u + (lane >> 3)) * {Tk}u + t * 128u + (lane & 7u) * 4u;
+                float* dst = out + ((size_t)z * {Tq}u + at * 128u + sq * 32u + (lane >> 3)) * {Tk}u + t * 128u + wh * 64u + (lane & 7u) * 4u;
                 const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
                 #pragma unroll
                 for (unsigned i = 0; i < 8u; ++i) {{
-                    #pragma unroll
-                    for (unsigned c = 0; c < 4u; ++c) *reinterpret_cast<float4*>(dst + (size_t)(4u * i) * {Tk}u + c * 32u) = z4;
+                    *reinterpret_cast<float4*>(dst + (size_t)(4u * i) * {Tk}u) = z4;
+                    *reinterpret_cast<float4*>(dst + (size_t)(4u * i) * {Tk}u + 32u) = z4;
                 }}
             }}"""
     return ""
@@ -468,162 +476,185 @@ def _row_item_begin(mode: str, Tq: int, Tk: int) -> str:
 def _row_step(mode, Tq, Tk, D, S0, DP0, PHI, PLO, OACC, sc2, fl2, sc, tau) -> str:
     wpr = Tk // 32
     if mode == "fwd":
-        resc = "\n                        ".join(
-            f"""{{ unsigned o[32]; TMEM_LD32(lane_base + {OACC + 32 * c}u, o); TMEM_WAIT_LD();
+        if D == 64:
+            resc = f"""{{ unsigned o[32]; TMEM_LD32(lane_base + {OACC}u + wh * 32u, o); TMEM_WAIT_LD();
                           #pragma unroll
                           for (unsigned e = 0; e < 32u; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * alpha);
-                          TMEM_ST32(lane_base + {OACC + 32 * c}u, o); }}""" for c in range(D // 32))
-        return f"""unsigned v[64];
-                    TMEM_LD32(lane_base + {S0}u + b * 64u, v);
-                    TMEM_LD32(lane_base + {S0}u + b * 64u + 32u, v + 32);
+                          TMEM_ST32(lane_base + {OACC}u + wh * 32u, o); }}"""
+        else:
+            resc = f"""if (wh == 0u) {{ unsigned o[32]; TMEM_LD32(lane_base + {OACC}u, o); TMEM_WAIT_LD();
+                          #pragma unroll
+                          for (unsigned e = 0; e < 32u; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * alpha);
+                          TMEM_ST32(lane_base + {OACC}u, o); }}"""
+        return f"""// both warps of a pair read all 64 scores of the row for the maximum (no exchange between them), then each
+                    // exponentiates, sums and splits its own 32 columns
+                    unsigned v[32], u[32];
+                    TMEM_LD32(lane_base + {S0}u + b * 64u + wh * 32u, v);             // mine
+                    TMEM_LD32(lane_base + {S0}u + b * 64u + (wh ^ 1u) * 32u, u);      // the partner's
                     const uint2 mw = __ldg(reinterpret_cast<const uint2*>(mask + (size_t)row * {wpr}u + (c0 >> 5)));
+                    const unsigned mine_bits = wh ? mw.y : mw.x, other_bits = wh ? mw.x : mw.y;
                     TMEM_WAIT_LD();
                     TC_FENCE_BEFORE();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(sempty + b * 8u);        // S[b] may be overwritten by the step after next
-                    float x[64];
-                    float cm = {NEG_INF};
-                    #pragma unroll
-                    for (unsigned e = 0; e < 64u; ++e) {{
-                        const unsigned bit = ((e < 32u ? mw.x : mw.y) >> (e & 31u)) & 1u;
-                        x[e] = bit ? {fl2} : __uint_as_float(v[e]) * {sc2};
-                        cm = fmaxf(cm, x[e]);
+                    float cm;
+                    if ((mine_bits | other_bits) == 0u) {{                // nothing masked in this row's 64 columns (scale > 0)
+                        cm = fmaxf(__uint_as_float(v[0]), __uint_as_float(u[0]));
+                        #pragma unroll
+                        for (unsigned e = 1; e < 32u; ++e) cm = fmaxf(cm, fmaxf(__uint_as_float(v[e]), __uint_as_float(u[e])));
+                        cm *= {sc2};
+                    }} else {{
+                        cm = {NEG_INF};
+                        #pragma unroll
+                        for (unsigned e = 0; e < 32u; ++e) {{
+                            cm = fmaxf(cm, ((mine_bits >> e) & 1u) ? {fl2} : __uint_as_float(v[e]) * {sc2});
+                            cm = fmaxf(cm, ((other_bits >> e) & 1u) ? {fl2} : __uint_as_float(u[e]) * {sc2});
+                        }}
                     }}
-                    // online softmax with a lazily updated maximum (see `tau`)
+                    // online softmax with a lazily updated maximum (see `tau`); identical in both warps of the pair
                     float alpha = 1.f;
                     const float m_new = fmaxf(m_run, cm);
                     const bool grow = m_new > m_run + {_f32lit(tau)};
                     if (grow) {{ alpha = ex2(m_run - m_new); l_run *= alpha; m_run = m_new; }}
                     const bool resc = __any_sync(0xffffffffu, grow) && j != 0u;
-                    const bool none = !(m_run > {NEG_INF});            // nothing finite so far: P = 0 (an all-masked row ends NaN)
+                    float x[32];
                     float add = 0.f;
-                    #pragma unroll
-                    for (unsigned e = 0; e < 64u; ++e) {{
-                        x[e] = none ? 0.f : ex2(x[e] - m_run);
-                        add += x[e];
+                    if (!(m_run > {NEG_INF})) {{                          // nothing finite so far: P = 0 (an all-masked row ends NaN)
+                        #pragma unroll
+                        for (unsigned e = 0; e < 32u; ++e) x[e] = 0.f;
+                    }} else if (mine_bits == 0u) {{
+                        #pragma unroll
+                        for (unsigned e = 0; e < 32u; ++e) {{ x[e] = ex2(fmaf(__uint_as_float(v[e]), {sc2}, -m_run)); add += x[e]; }}
+                    }} else {{
+                        #pragma unroll
+                        for (unsigned e = 0; e < 32u; ++e) {{
+                            x[e] = ex2((((mine_bits >> e) & 1u) ? {fl2} : __uint_as_float(v[e]) * {sc2}) - m_run);
+                            add += x[e];
+                        }}
                     }}
                     l_run += add;
                     if (g != 0u) {{ mbar_wait(pvdone, (g - 1u) & 1u); TC_FENCE_AFTER(); }}     // the MMA that read P (and wrote O) is done
                     if (resc) {{
                         {resc}
                     }}
-                    split_to_tmem(lane_base + {PHI}u, lane_base + {PLO}u, x);
-                    split_to_tmem(lane_base + {PHI + 32}u, lane_base + {PLO + 32}u, x + 32);
+                    split_to_tmem(lane_base + {PHI}u + wh * 32u, lane_base + {PLO}u + wh * 32u, x);
                     TMEM_WAIT_ST();
                     TC_FENCE_BEFORE();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(pready);"""
     if mode == "dv":
-        return f"""unsigned v[64];
-                    TMEM_LD32(lane_base + {S0}u + b * 64u, v);
-                    TMEM_LD32(lane_base + {S0}u + b * 64u + 32u, v + 32);
+        return f"""unsigned v[32];
+                    TMEM_LD32(lane_base + {S0}u + b * 64u + wh * 32u, v);
+                    // thread = key row; column e of this warp = query c0 + 32 wh + e.  Lane e fetches that query's lse and its
+                    // mask word for this warp's 32 keys (coalesced); they reach the other lanes by shuffle.
+                    const unsigned qe = c0 + wh * 32u + lane;
+                    const float lse_e = __ldg(lse + (size_t)z * {Tq}u + qe);
+                    const unsigned mw_e = __ldg(mask + (size_t)qe * {wpr}u + (row >> 5));
+                    const bool any_masked = __any_sync(0xffffffffu, mw_e != 0u);
                     TMEM_WAIT_LD();
                     TC_FENCE_BEFORE();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(sempty + b * 8u);
-                    // thread = key row, column e = query c0 + e: that query's (m, 1 / l) and its mask word for this warp's 32
-                    // keys are the same for the whole warp (broadcast loads)
-                    float x[64];
-                    const float2* srow = stats + (size_t)z * {Tq}u + c0;
-                    const unsigned* mrow = mask + (size_t)c0 * {wpr}u + (row >> 5);
-                    #pragma unroll
-                    for (unsigned e = 0; e < 64u; ++e) {{
-                        const float2 st = __ldg(srow + e);
-                        const unsigned bit = (__ldg(mrow + (size_t)e * {wpr}u) >> lane) & 1u;
-                        const float t2 = bit ? {fl2} : __uint_as_float(v[e]) * {sc2};
-                        x[e] = ex2(t2 - st.x) * st.y;
+                    float x[32];
+                    if (!any_masked) {{
+                        #pragma unroll
+                        for (unsigned e = 0; e < 32u; ++e)
+                            x[e] = ex2(fmaf(__uint_as_float(v[e]), {sc2}, -__shfl_sync(0xffffffffu, lse_e, e)));
+                    }} else {{
+                        #pragma unroll
+                        for (unsigned e = 0; e < 32u; ++e) {{
+                            const unsigned bit = (__shfl_sync(0xffffffffu, mw_e, e) >> lane) & 1u;
+                            x[e] = ex2((bit ? {fl2} : __uint_as_float(v[e]) * {sc2}) - __shfl_sync(0xffffffffu, lse_e, e));
+                        }}
                     }}
                     if (g != 0u) {{ mbar_wait(pvdone, (g - 1u) & 1u); TC_FENCE_AFTER(); }}
-                    split_to_tmem(lane_base + {PHI}u, lane_base + {PLO}u, x);
-                    split_to_tmem(lane_base + {PHI + 32}u, lane_base + {PLO + 32}u, x + 32);
+                    split_to_tmem(lane_base + {PHI}u + wh * 32u, lane_base + {PLO}u + wh * 32u, x);
                     TMEM_WAIT_ST();
                     TC_FENCE_BEFORE();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(pready);"""
     # ds
-    stage_writes = "\n                            ".join(
+    stage_writes = "\n                        ".join(
         f"*reinterpret_cast<float4*>(sbuf_gen + lane * 128u + (({jj}u ^ (lane & 7u)) << 4)) = "
         f"make_float4(x[{4 * jj}], x[{4 * jj + 1}], x[{4 * jj + 2}], x[{4 * jj + 3}]);" for jj in range(8))
-    return f"""const uint2 mw = __ldg(reinterpret_cast<const uint2*>(mask + (size_t)row * {wpr}u + (c0 >> 5)));
-                    #pragma unroll 1
-                    for (unsigned c = 0; c < 2u; ++c) {{
-                        unsigned v[32], d[32];
-                        TMEM_LD32(lane_base + {S0}u + b * 64u + c * 32u, v);
-                        TMEM_LD32(lane_base + {DP0}u + b * 64u + c * 32u, d);
-                        TMEM_WAIT_LD();
-                        const unsigned bits = c ? mw.y : mw.x;
-                        float x[32];
-                        #pragma unroll
-                        for (unsigned e = 0; e < 32u; ++e) {{
-                            const float p = ex2(__uint_as_float(v[e]) * {sc2} - st_row.x) * st_row.y;
-                            const float tt = p * (__uint_as_float(d[e]) - d_row);
-                            x[e] = ((bits >> e) & 1u) ? 0.f : tt * {sc};
-                        }}
-                        const unsigned sb = (2u * g + c) & 1u;
-                        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");     // the store before last has left this box
-                        __syncwarp();
-                        unsigned char* sbuf_gen = my_epi_gen + sb * 4096u;
-                        {{
-                            {stage_writes}
-                        }}
-                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                        __syncwarp();
-                        if (lane == 0) {{
-                            tma_store_3d(&tmOut, my_epi + sb * 4096u, (int)(c0 + c * 32u), (int)(at * 128u + sq * 32u), (int)z);
-                            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                        }}
-                    }}
+    return f"""unsigned v[32], d[32];
+                    TMEM_LD32(lane_base + {S0}u + b * 64u + wh * 32u, v);
+                    TMEM_LD32(lane_base + {DP0}u + b * 64u + wh * 32u, d);
+                    const unsigned bits = __ldg(mask + (size_t)row * {wpr}u + (c0 >> 5) + wh);
+                    TMEM_WAIT_LD();
                     TC_FENCE_BEFORE();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(sempty + b * 8u);"""
+                    if (lane == 0) mbar_arrive(sempty + b * 8u);
+                    float x[32];
+                    #pragma unroll
+                    for (unsigned e = 0; e < 32u; ++e) {{
+                        const float p = ex2(fmaf(__uint_as_float(v[e]), {sc2}, -lse_row));
+                        const float tt = p * (__uint_as_float(d[e]) - d_row);
+                        x[e] = ((bits >> e) & 1u) ? 0.f : tt * {sc};
+                    }}
+                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");     // the previous store has left the box
+                    __syncwarp();
+                    {stage_writes}
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) {{
+                        tma_store_3d(&tmOut, my_epi, (int)(c0 + wh * 32u), (int)(at * 128u + sq * 32u), (int)z);
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }}"""
 
 
 def _row_item_end(mode, Tq, Tk, D, OACC, sT, sH, sB, nS) -> str:
     if mode == "ds":
         return ""
     TA = Tk if mode == "dv" else Tq
-    ld = "\n                ".join(
-        f"TMEM_LD32(lane_base + {OACC + 32 * c}u, o + {32 * c});" for c in range(D // 32))
-    store = f"""float* orow = out + (size_t)bb * {sB}ull + (size_t)hh * {sH}ull + (size_t)row * {sT}ull;
-                #pragma unroll
-                for (unsigned e = 0; e < {D}u; e += 4u)
-                    *reinterpret_cast<float4*>(orow + e) = make_float4(__uint_as_float(o[e]) * fac, __uint_as_float(o[e + 1]) * fac,
-                                                                       __uint_as_float(o[e + 2]) * fac, __uint_as_float(o[e + 3]) * fac);"""
+    # the accumulator's D columns: 32 per warp of the pair at D = 64; at D = 32 the first warp of the pair takes them all
+    mine = "true" if D == 64 else "wh == 0u"
+    col0 = "wh * 32u" if D == 64 else "0u"
+    store = f"""float* orow = out + (size_t)bb * {sB}ull + (size_t)hh * {sH}ull + (size_t)row * {sT}ull + {col0};
+                    #pragma unroll
+                    for (unsigned e = 0; e < 32u; e += 4u)
+                        *reinterpret_cast<float4*>(orow + e) = make_float4(__uint_as_float(o[e]) * fac, __uint_as_float(o[e + 1]) * fac,
+                                                                           __uint_as_float(o[e + 2]) * fac, __uint_as_float(o[e + 3]) * fac);"""
     if mode == "fwd":
         return f"""{{
-                unsigned o[{D}];
-                float fac;
+                // the row sum: each warp of a pair holds the sum over its 32 columns of every step (same maximum in both)
+                xch[(warp - 2u) * 32u + lane] = l_run;
+                asm volatile("bar.sync %0, 64;" :: "r"(1u + sq) : "memory");
+                const float l_tot = l_run + xch[((warp - 2u) ^ 4u) * 32u + lane];
+                asm volatile("bar.sync %0, 64;" :: "r"(1u + sq) : "memory");
+                unsigned o[32];
+                float fac = 1.f;
                 if (nsteps == 0u) {{
                     // no live key tile at all: every row of this tile is fully masked -> NaN, like the unfused chain
                     #pragma unroll
-                    for (unsigned e = 0; e < {D}u; ++e) o[e] = 0x7fc00000u;
-                    fac = 1.f;
+                    for (unsigned e = 0; e < 32u; ++e) o[e] = 0x7fc00000u;
                 }} else {{
                     mbar_wait(pvdone, (g - 1u) & 1u);
                     TC_FENCE_AFTER();
-                    {ld}
-                    TMEM_WAIT_LD();
+                    if ({mine}) {{ TMEM_LD32(lane_base + {OACC}u + {col0}, o); TMEM_WAIT_LD(); }}
                     TC_FENCE_BEFORE();
-                    fac = 1.f / l_run;                                 // l = 0 (a fully masked row): 0 * inf = NaN
+                    fac = 1.f / l_tot;                                 // l = 0 (a fully masked row): 0 * inf = NaN
                 }}
-                {store}
-                const bool dead = !(l_run > 0.f);
-                stats[(size_t)z * {TA}u + row] = make_float2(dead ? {QNAN} : m_run, dead ? {QNAN} : 1.f / l_run);
+                if ({mine}) {{
+                    {store}
+                }}
+                if (wh == 0u) lse[(size_t)z * {TA}u + row] = (l_tot > 0.f) ? m_run + log2f(l_tot) : {QNAN};
             }}"""
     return f"""{{
-                unsigned o[{D}];
+                unsigned o[32];
                 const float fac = 1.f;
                 if (nsteps == 0u) {{
                     #pragma unroll
-                    for (unsigned e = 0; e < {D}u; ++e) o[e] = 0u;          // no query attends to these keys
+                    for (unsigned e = 0; e < 32u; ++e) o[e] = 0u;           // no query attends to these keys
                 }} else {{
                     mbar_wait(pvdone, (g - 1u) & 1u);
                     TC_FENCE_AFTER();
-                    {ld}
-                    TMEM_WAIT_LD();
+                    if ({mine}) {{ TMEM_LD32(lane_base + {OACC}u + {col0}, o); TMEM_WAIT_LD(); }}
                     TC_FENCE_BEFORE();
                 }}
-                {store}
+                if ({mine}) {{
+                    {store}
+                }}
             }}"""
 
 
