@@ -21,9 +21,10 @@ Every product is 3xTF32 (a_lo b_hi + a_hi b_lo + a_hi b_hi, fp32 accumulate), so
 (north star: matmul <= 1e-4, softmax <= 1e-5 relative).  kind::tf32 truncates its inputs, so a staged fp32 tile IS its
 own `hi`; only `lo` tiles are computed (splitter warps for the streamed operands, the row threads for A and P).
 
-Warp roles (448 threads, one persistent CTA per SM):
+Warp roles (480 threads, one persistent CTA per SM):
     warp 0       TMA producer: A tile(s) of the next item, then per step the two streamed tiles of the ring stage
-    warp 1       MMA issuer (one elected lane)
+    warp 1, 14   MMA issuers (one elected lane each): warp 1 the score tiles, warp 14 the second product of the step; each
+                 owns its accumulators, so every accumulation order is one thread's program order (deterministic)
     warps 2-9    row warps: thread = row of the 128-row score tile = TMEM lane; two warps per lane quarter, each owns 32
                  of the 64 score columns of a step (the row work — TMEM reads, exponentials, hi | lo splits, TMEM writes —
                  paces these kernels, not the tensor pipe: with four row warps the forward ran at 50 % pipe utilisation)
@@ -45,6 +46,10 @@ __device__ __forceinline__ void tma_load_4d(unsigned dst, const TMap* map, unsig
     asm volatile(
         "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
         :: "r"(dst), "l"((unsigned long long)map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_4d(const TMap* map, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];"
+                 :: "l"((unsigned long long)map), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
 #define TMEM_LD32(addr, v) asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];" \
     : "=r"((v)[0]), "=r"((v)[1]), "=r"((v)[2]), "=r"((v)[3]), "=r"((v)[4]), "=r"((v)[5]), "=r"((v)[6]), "=r"((v)[7]), \
@@ -102,6 +107,15 @@ def flash_attn(mode: str, Tq: int, Tk: int, D: int, H: int, NB: int, scale: floa
       dv : tmK, tmQ, tmDO, dV, lse, bits
       ds : tmQ, tmDO, tmK, tmV, tmDS, dS, lse, delta, bits            (bits: cuda_kernel.mask_bits of the (Tq, Tk) mask)"""
     assert mode in ("fwd", "dv", "ds") and Tq % 128 == 0 and Tk % 128 == 0 and D in (32, 64) and scale > 0
+    import os
+    # diagnostic (scripts/flash_trace.py): CTA 0 timestamps the first 48 steps of every role into the unused second half of
+    # the lse allocation (NB * TA * 8 bytes are allocated, NB * TA * 4 used)
+    trace = os.environ.get("DLGRAD_FLASH_TRACE", "") == mode
+    lse_rows = NB * Tq
+
+    def TR(kind: int, idx: str, cond: str = "lane == 0u") -> str:
+        return (f"if (blockIdx.x == 0u && ({idx}) < 48u && ({cond})) reinterpret_cast<long long*>(const_cast<float*>(lse) + {lse_rows}u)"
+                f"[{kind * 48}u + ({idx})] = clock64();") if trace else ""
     assert max(Tq, Tk) // 128 <= 32
     kbq = D // 32
     nq, nk = Tq // 128, Tk // 128
@@ -134,16 +148,17 @@ def flash_attn(mode: str, Tq: int, Tk: int, D: int, H: int, NB: int, scale: floa
     idesc_s = _idesc(128, 64, False, False)                  # S / dP: N = 64 streamed rows, B K-major
     idesc_o = _idesc(128, D, False, True)                    # O / dV: N = D, B MN-major
     sT, sH, sB = out_strides
-    # which streamed 128-row tiles are live for resident tile `at`
+    # which streamed 128-row tiles are live for resident tile `at`: one word per resident tile, computed ONCE per CTA into
+    # shared memory (each role looked it up with global loads at every item boundary before: ~3000 clk of L2 latency under
+    # load, at the one point of the pipeline where nothing else can hide it)
     if skip:
         if mode == "dv":
-            live = f"""const unsigned* tf = mask + {Tq * Tk // 32}u + at; unsigned lm = 0u;
-            for (unsigned j = 0; j < {nq}u; ++j) lm |= (__ldg(tf + j * {nk}u) != 0u ? 1u : 0u) << j; return lm;"""
+            live_fill = f"""for (unsigned j = 0; j < {nq}u; ++j) lm |= (__ldg(mask + {Tq * Tk // 32}u + j * {nk}u + threadIdx.x) != 0u ? 1u : 0u) << j;"""
         else:
-            live = f"""const unsigned* tf = mask + {Tq * Tk // 32}u + at * {nk}u; unsigned lm = 0u;
-            for (unsigned j = 0; j < {nk}u; ++j) lm |= (__ldg(tf + j) != 0u ? 1u : 0u) << j; return lm;"""
+            live_fill = f"""for (unsigned j = 0; j < {nk}u; ++j) lm |= (__ldg(mask + {Tq * Tk // 32}u + threadIdx.x * {nk}u + j) != 0u ? 1u : 0u) << j;"""
     else:
-        live = f"return {(1 << nS) - 1 if nS < 32 else 0xffffffff}u;"
+        live_fill = f"lm = {(1 << nS) - 1 if nS < 32 else 0xffffffff}u;"
+    live = "return live_tab[at];"
     # heavy tiles first: under a causal mask query tile i has i + 1 live key tiles, key tile i has nq - i live query tiles
     tile_of = f"p / {NB}u" if mode == "dv" else f"{nA - 1}u - p / {NB}u"
 
@@ -173,6 +188,14 @@ def flash_attn(mode: str, Tq: int, Tk: int, D: int, H: int, NB: int, scale: floa
     if mode == "ds":
         a_loads += "\n                " + "\n                ".join(
             f"tma_load_4d(smem + {(kbq + kk) * 16384}u, &tmA2, qfull, {kk * 32}, (int)a0, (int)hh, (int)bb);" for kk in range(kbq))
+
+    # L2 prefetch of one streamed 128-row tile, box by box (the boxes of the tensor maps the loads use)
+    pf = [f"tma_prefetch_4d(&tmB1, {kk * 32}, (int)(pr0 + {r * 64}u), (int)phh, (int)pbb);" for r in range(2) for kk in range(kbq)]
+    if mode == "ds":
+        pf += [f"tma_prefetch_4d(&tmB2, {kk * 32}, (int)(pr0 + {r * 64}u), (int)phh, (int)pbb);" for r in range(2) for kk in range(kbq)]
+    else:
+        pf += [f"tma_prefetch_4d(&tmB2, {c * 32}, (int)(pr0 + {r * 32}u), (int)phh, (int)pbb);" for r in range(4) for c in range(kbq)]
+    pf_loads = "\n                ".join(pf)
 
     # ------------------------------------------------------------------ MMA bodies
     lo_off = raw_b // 16
@@ -205,7 +228,7 @@ def flash_attn(mode: str, Tq: int, Tk: int, D: int, H: int, NB: int, scale: floa
                         }}"""
 
     src = _HELPERS + _HELPERS_TS + _EXTRA + _sub(r"""
-extern "C" __global__ void __launch_bounds__(448, 1)
+extern "C" __global__ void __launch_bounds__(480, 1)
 $KNAME$($PARAMS$)
 {
     extern __shared__ unsigned char smem_raw[];
@@ -219,6 +242,8 @@ $KNAME$($PARAMS$)
     const unsigned qfull = pvdone + 8u, qsplit = qfull + 8u, qfree = qsplit + 8u;
     float* xch = reinterpret_cast<float*>(smem_gen + (bars - smem) + 256u);      // [8 row warps][32]
     __shared__ unsigned tmem_slot;
+    __shared__ unsigned live_tab[32];
+    $TRACE_DECL$
     const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
 
     // streamed 128-row tiles that have at least one unmasked entry against resident tile `at` (cuda_kernel.mask_bits):
@@ -236,21 +261,26 @@ $KNAME$($PARAMS$)
         return true;
     };
 
+    if (threadIdx.x >= 64u && threadIdx.x < 64u + $NA$u) {
+        unsigned lm = 0u;
+        $LIVE_FILL$
+        live_tab[threadIdx.x - 64u] = lm;
+    }
     if (threadIdx.x == 0) {
         for (unsigned s = 0; s < $STAGES$u; ++s) {
             mbar_init(kfull + s * 8u, 1u);
-            mbar_init(kempty + s * 8u, 1u);
+            mbar_init(kempty + s * 8u, $NISS$u);
             mbar_init(ksplit + s * 8u, 4u);
         }
         for (unsigned b = 0; b < 2u; ++b) {
-            mbar_init(sfull + b * 8u, 1u);
+            mbar_init(sfull + b * 8u, $NISS$u);
             mbar_init(sempty + b * 8u, 8u);
         }
         mbar_init(pready, 8u);
         mbar_init(pvdone, 1u);
         mbar_init(qfull, 1u);
         mbar_init(qsplit, $NSPLIT$u);
-        mbar_init(qfree, 1u);
+        mbar_init(qfree, $NISS$u);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -273,6 +303,26 @@ $KNAME$($PARAMS$)
             }
             __syncwarp();
         };
+        // L2 prefetch cursor: the streamed tiles are requested from HBM $PFD$ live tiles before the TMA load that brings them
+        // into shared memory (a load that misses L2 takes ~3000 clk; three 64 KiB stages cannot cover that, and the ring —
+        // not the tensor pipe — paced the kernel: pipe active 52 %)
+        unsigned pn = 0, pz = 0, pat = 0, plm = 0, pt = 0;
+        bool pvalid = item_at(0u, pz, pat);
+        if (pvalid) plm = live_tiles(pat);
+        auto pf_next = [&]() {                 // prefetch the cursor's tile (if any) and move it to the next live tile
+            while (pvalid && (pt >= $NS$u || !((plm >> pt) & 1u))) {
+                if (pt >= $NS$u || (plm >> pt) == 0u) { pvalid = item_at(++pn, pz, pat); plm = pvalid ? live_tiles(pat) : 0u; pt = 0u; }
+                else ++pt;
+            }
+            if (!pvalid) return;
+            const unsigned phh = pz % $H$u, pbb = pz / $H$u, pr0 = pt * 128u;
+            if (elect_one()) {
+                $PF_LOADS$
+            }
+            __syncwarp();
+            ++pt;
+        };
+        for (unsigned i = 0; i < $PFD$u; ++i) pf_next();
         if (item_at(0u, z, at)) load_a(z, at);
         for (; item_at(n, z, at); ++n) {
             const unsigned hh = z % $H$u, bb = z / $H$u;
@@ -281,10 +331,12 @@ $KNAME$($PARAMS$)
             bool a_pending = item_at(n + 1u, zn, an);           // the next item's A tile: once this one has left shared memory
             for (unsigned t = 0; t < $NS$u; ++t) {
                 if (!((lm >> t) & 1u)) continue;
+                pf_next();
                 for (unsigned half = 0; half < 2u; ++half, ++it) {
                     if (a_pending && mbar_try(qsplit, n & 1u)) { load_a(zn, an); a_pending = false; }
                     const unsigned s = it % $STAGES$u, ph = (it / $STAGES$u) & 1u;
                     mbar_wait(kempty + s * 8u, ph ^ 1u);
+                    $TR16$
                     const unsigned st = ring + s * $PER_STAGE$u, fb = kfull + s * 8u, r0 = t * 128u + half * 64u;
                     if (elect_one()) {
                         mbar_expect_tx(fb, $RAW_B$u);
@@ -292,50 +344,52 @@ $KNAME$($PARAMS$)
                         $B2_LOADS$
                     }
                     __syncwarp();
+                    $TR17$
                 }
             }
             if (a_pending) { mbar_wait(qsplit, n & 1u); load_a(zn, an); }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer =====
+        // ===== first MMA issuer: the score tiles S = A x B1^T (Q K^T; K Q^T for dv) into S[b] =====
+        // Two warps issue MMAs, each into accumulators of its own (this one S, the other O / dV resp. dP), so the
+        // accumulation order inside every accumulator is the program order of ONE thread: results stay bit-identical from
+        // run to run.  (MMAs of two warps into the SAME accumulator are not ordered — cuda_tcgen05.matmul_tc_ts.)  One
+        // thread issues an N = 64 MMA every ~50 clk, the tensor pipe needs 32: a single issuer left the pipe half idle.
         unsigned it = 0, g = 0, n = 0, z, at;
         const unsigned long long sdesc0 = make_desc(ring, 1u, 64u, 2u);                  // K-major tile: SBO 1024 B, SWIZZLE_128B
-        const unsigned long long odesc0 = make_desc(ring + $TILE_B$u, 256u, 32u, 1u);    // MN-major tile: LBO 4096 B, SBO 512 B, 32-byte atoms
         for (; item_at(n, z, at); ++n) {
             const unsigned nsteps = 2u * __popc(live_tiles(at));
+            $TR13$
             mbar_wait(qsplit, n & 1u);                            // A (hi | lo) of this item is in tensor memory
+            $TR14$
             TC_FENCE_AFTER();
             if (nsteps == 0u) {
                 if (elect_one()) umma_commit(qfree);
                 __syncwarp();
                 continue;
             }
-            unsigned issued = 0;                                  // S-type MMAs issued for this item
-            auto issue_s = [&]() {
-                const unsigned gi = g + issued, b = gi & 1u, iti = it + issued;
-                const unsigned s = iti % $STAGES$u, ph = (iti / $STAGES$u) & 1u;
+            for (unsigned i = 0; i < nsteps; ++i, ++it, ++g) {
+                const unsigned b = g & 1u, s = it % $STAGES$u, ph = (it / $STAGES$u) & 1u;
                 mbar_wait(ksplit + s * 8u, ph);
-                mbar_wait(sempty + b * 8u, ((gi >> 1) & 1u) ^ 1u);
+                $TR0$
+                mbar_wait(sempty + b * 8u, ((g >> 1) & 1u) ^ 1u);
+                $TR1$
                 TC_FENCE_AFTER();
                 const unsigned long long sdesc = sdesc0 + (unsigned long long)(s * $PER_STAGE16$u);
                 if (elect_one()) {
                     $S_MMA$
-                    $DP_MMA$
                     $DS_STAGE_FREE$
                     umma_commit(sfull + b * 8u);
-                    if (issued + 1u == nsteps) umma_commit(qfree);      // the last read of A by this item
+                    if (i + 1u == nsteps) umma_commit(qfree);          // the last read of A by this item
                 }
                 __syncwarp();
-                ++issued;
-            };
-            issue_s();
-            for (unsigned j = 0; j < nsteps; ++j) {
-                if (issued < nsteps) issue_s();                   // S of step j + 1 runs while the row warps work on step j
-                $PV_BLOCK$
+                $TR2$
             }
-            it += nsteps;
-            g += nsteps;
         }
+    } else if (warp == 14u) {
+        // ===== second MMA issuer: O += P V (fwd), dV += P^T dO (dv), dP = dO V^T (ds) =====
+        unsigned it = 0, g = 0, n = 0, z, at;
+        $ISSUER2$
     } else if (warp < 10u) {
         // ===== row warps: thread = row of the score tile = TMEM lane; warps 2-5 own score columns 0-31 of a step, 6-9 columns 32-63 =====
         const unsigned sq = warp & 3u;                            // the TMEM lane quarter this warp may access
@@ -343,8 +397,11 @@ $KNAME$($PARAMS$)
         const unsigned lane_base = tmem_base + ((sq * 32u) << 16);
         unsigned g = 0, n = 0, z, at;
         auto split_a = [&](unsigned nn) {
+            $TR9$
             mbar_wait(qfull, nn & 1u);                             // the tile has landed in shared memory
+            $TR10$
             if (nn != 0u) { mbar_wait(qfree, (nn - 1u) & 1u); TC_FENCE_AFTER(); }    // and the previous item no longer reads A
+            $TR11$
             if ($A_KBLOCKS$u < 2u && wh != 0u) return;             // a single k-block: the first warp of the pair splits it
             #pragma unroll 1
             for (unsigned kk = ($A_KBLOCKS$u < 2u ? 0u : wh); kk < $A_KBLOCKS$u; kk += 2u) {
@@ -362,6 +419,7 @@ $KNAME$($PARAMS$)
             TC_FENCE_BEFORE();
             __syncwarp();
             if (lane == 0) mbar_arrive(qsplit);
+            $TR12$
         };
         if (item_at(0u, z, at)) split_a(0u);
         for (; item_at(n, z, at); ++n) {
@@ -372,22 +430,38 @@ $KNAME$($PARAMS$)
             unsigned zn, an;
             const bool has_next = item_at(n + 1u, zn, an);
             $ROW_ITEM_BEGIN$
+            $PF_DECL$
+            if (lm != 0u) {
+                const unsigned nc0 = (__ffs(lm) - 1u) * 128u;
+                $PF_NEXT$
+            }
             unsigned j = 0;
             for (unsigned t = 0; t < $NS$u; ++t) {
                 if (!((lm >> t) & 1u)) continue;
                 for (unsigned half = 0; half < 2u; ++half, ++j, ++g) {
                     const unsigned b = g & 1u;
                     const unsigned c0 = t * 128u + half * 64u;         // first streamed row (= score column) of this step
+                    // the mask words (and, for dv, the row statistics) of a step are fetched one step ahead: a global load
+                    // takes longer than the whole TMEM read it used to be issued next to
+                    $PF_TAKE$
+                    {
+                        const unsigned rest = (t + 1u < $NS$u) ? (lm >> (t + 1u)) : 0u;
+                        const unsigned nc0 = (half == 0u) ? c0 + 64u : (rest ? (t + __ffs(rest)) * 128u : c0);
+                        $PF_NEXT$
+                    }
                     mbar_wait(sfull + b * 8u, (g >> 1) & 1u);
+                    $TR5$
                     TC_FENCE_AFTER();
                     $ROW_STEP$
+                    $TR8$
                 }
             }
             if (has_next) split_a(n + 1u);                         // next item's A while the last MMAs of this one run
             $ROW_ITEM_END$
+            $TR15$
         }
         $ROW_EXIT$
-    } else {
+    } else if (warp < 14u) {
         // ===== splitter warps: lo = x - trunc_tf32(x) for the two staged tiles of a step =====
         const unsigned ctid = threadIdx.x - 320u;
         unsigned it = 0, n = 0, z, at;
@@ -396,6 +470,7 @@ $KNAME$($PARAMS$)
             for (unsigned i2 = 0; i2 < nsteps; ++i2, ++it) {
                 const unsigned s = it % $STAGES$u, ph = (it / $STAGES$u) & 1u;
                 mbar_wait(kfull + s * 8u, ph);
+                $TR18$
                 const float4* bsrc = reinterpret_cast<const float4*>(smem_gen + $A_BYTES$u + s * $PER_STAGE$u);
                 float4* bdst = reinterpret_cast<float4*>(smem_gen + $A_BYTES$u + s * $PER_STAGE$u + $RAW_B$u);
                 #pragma unroll 8
@@ -411,43 +486,97 @@ $KNAME$($PARAMS$)
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
                 if (lane == 0) mbar_arrive(ksplit + s * 8u);
+                $TR19$
             }
         }
     }
     TC_FENCE_BEFORE();
     __syncthreads();
+    $TRACE_DUMP$
     if (warp == 1) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "n"(512));
     }
 }
 """,
         KNAME=KNAME, PARAMS=params, A_BYTES=a_bytes, RING_BYTES=stages * per_stage, EPI_BYTES=epi_bytes, STAGES=stages,
-        NSPLIT=8 if a_tiles * kbq >= 2 else 4, LIVE=live, GRID=grid, ITEMS=items, NB=NB, TILE_OF=tile_of, H=H, A_LOADS=a_loads, NS=nS, PER_STAGE=per_stage,
+        TR0=TR(0, "g"), TR1=TR(1, "g"), TR2=TR(2, "g"), TR5=TR(5, "g", "threadIdx.x == 64u"), TR8=TR(8, "g", "threadIdx.x == 64u"),
+        TRACE_DECL="", TRACE_DUMP="", TR16=TR(16, "it"), TR17=TR(17, "it"), TR18=TR(18, "it", "threadIdx.x == 320u"), TR19=TR(19, "it", "threadIdx.x == 320u"), TR9=TR(9, "nn", "threadIdx.x == 64u"), TR10=TR(10, "nn", "threadIdx.x == 64u"), TR11=TR(11, "nn", "threadIdx.x == 64u"),
+        TR12=TR(12, "nn", "threadIdx.x == 64u"), TR13=TR(13, "n"), TR14=TR(14, "n"), TR15=TR(15, "n", "threadIdx.x == 64u"),
+        NSPLIT=8 if a_tiles * kbq >= 2 else 4, NISS=2 if mode == "ds" else 1, PF_LOADS=pf_loads, PFD=int(os.environ.get("DLGRAD_FLASH_PF", "2")), LIVE=live, LIVE_FILL=live_fill.replace("threadIdx.x", "(threadIdx.x - 64u)"), NA=nA, GRID=grid, ITEMS=items, NB=NB, TILE_OF=tile_of, H=H, A_LOADS=a_loads, NS=nS, PER_STAGE=per_stage,
         RAW_B=raw_b, B1_LOADS=b1_loads, B2_LOADS=b2_loads, TILE_B=tile_b, PER_STAGE16=per_stage // 16,
         S_MMA=s_mma(f"tmem_base + {S0}u + b * 64u", A0, 0),
-        DP_MMA=s_mma(f"tmem_base + {DP0}u + b * 64u", A1, tile_b // 16) if mode == "ds" else "",
         DS_STAGE_FREE="umma_commit(kempty + s * 8u);" if mode == "ds" else "",
-        PV_BLOCK="" if mode == "ds" else _sub(r"""{
-                    const unsigned gi = g + j, iti = it + j, s = iti % $STAGES$u;
-                    mbar_wait(pready, gi & 1u);                    // P (hi | lo) of step j is in tensor memory
-                    TC_FENCE_AFTER();
-                    const unsigned long long odesc = odesc0 + (unsigned long long)(s * $PER_STAGE16$u);
-                    const unsigned acc = j;                        // the first step of an item overwrites the accumulator
-                    if (elect_one()) {
-                        $O_MMA$
-                        umma_commit(kempty + s * 8u);
-                        umma_commit(pvdone);
-                    }
-                    __syncwarp();
-                }""", STAGES=stages, PER_STAGE16=per_stage // 16, O_MMA=o_mma),
+        ISSUER2=_sub(r"""const unsigned long long sdesc0 = make_desc(ring, 1u, 64u, 2u);
+        for (; item_at(n, z, at); ++n) {
+            const unsigned nsteps = 2u * __popc(live_tiles(at));
+            mbar_wait(qsplit, n & 1u);                            // dO (hi | lo) of this item is in tensor memory
+            TC_FENCE_AFTER();
+            if (nsteps == 0u) {
+                if (elect_one()) umma_commit(qfree);
+                __syncwarp();
+                continue;
+            }
+            for (unsigned i = 0; i < nsteps; ++i, ++it, ++g) {
+                const unsigned b = g & 1u, s = it % $STAGES$u, ph = (it / $STAGES$u) & 1u;
+                mbar_wait(ksplit + s * 8u, ph);
+                mbar_wait(sempty + b * 8u, ((g >> 1) & 1u) ^ 1u);
+                TC_FENCE_AFTER();
+                const unsigned long long sdesc = sdesc0 + (unsigned long long)(s * $PER_STAGE16$u);
+                if (elect_one()) {
+                    $DP_MMA$
+                    umma_commit(kempty + s * 8u);
+                    umma_commit(sfull + b * 8u);
+                    if (i + 1u == nsteps) umma_commit(qfree);
+                }
+                __syncwarp();
+            }
+        }""", STAGES=stages, PER_STAGE16=per_stage // 16, DP_MMA=s_mma(f"tmem_base + {DP0}u + b * 64u", A1, tile_b // 16))
+        if mode == "ds" else _sub(r"""const unsigned long long odesc0 = make_desc(ring + $TILE_B$u, 256u, 32u, 1u);    // MN-major tile: LBO 4096 B, SBO 512 B, 32-byte atoms
+        for (; item_at(n, z, at); ++n) {
+            const unsigned nsteps = 2u * __popc(live_tiles(at));
+            for (unsigned j = 0; j < nsteps; ++j, ++it, ++g) {
+                const unsigned s = it % $STAGES$u, ph = (it / $STAGES$u) & 1u;
+                mbar_wait(ksplit + s * 8u, ph);                    // the streamed tiles of this step are split
+                mbar_wait(pready, g & 1u);                         // P (hi | lo) of this step is in tensor memory
+                $TR3$
+                TC_FENCE_AFTER();
+                const unsigned long long odesc = odesc0 + (unsigned long long)(s * $PER_STAGE16$u);
+                const unsigned acc = j;                            // the first step of an item overwrites the accumulator
+                if (elect_one()) {
+                    $O_MMA$
+                    umma_commit(kempty + s * 8u);
+                    umma_commit(pvdone);
+                }
+                __syncwarp();
+                $TR4$
+            }
+        }""", STAGES=stages, PER_STAGE16=per_stage // 16, TILE_B=tile_b, O_MMA=o_mma, TR3=TR(3, "g"), TR4=TR(4, "g")),
         A_KBLOCKS=a_tiles * kbq, A0=A0,
-        ROW_ITEM_BEGIN=_row_item_begin(mode, Tq, Tk),
-        ROW_STEP=_row_step(mode, Tq, Tk, D, S0, DP0, PHI, PLO, OACC, sc2, fl2, _f32lit(float(np.float32(scale))), tau),
+        ROW_ITEM_BEGIN=_row_item_begin(mode, Tq, Tk), PF_DECL=_pf(mode, Tq, Tk)[0], PF_NEXT=_pf(mode, Tq, Tk)[1], PF_TAKE=_pf(mode, Tq, Tk)[2],
+        ROW_STEP=_row_step(mode, Tq, Tk, D, S0, DP0, PHI, PLO, OACC, sc2, fl2, _f32lit(float(np.float32(scale))), tau)
+        .replace("TRACE6", TR(6, "g", "threadIdx.x == 64u")).replace("TRACE7", TR(7, "g", "threadIdx.x == 64u")),
         ROW_ITEM_END=_row_item_end(mode, Tq, Tk, D, OACC, sT, sH, sB, nS),
         ROW_EXIT='if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");' if mode == "ds" else "",
         RAW_V4=raw_b // 16)
     out_elems = {"fwd": NB * Tq * D, "dv": NB * Tk * D, "ds": NB * Tq * Tk}[mode]
-    return TcKernel(f"flash_{mode}", src, (grid, 1, 1), 448, smem, out_elems, 64, stages)
+    return TcKernel(f"flash_{mode}", src, (grid, 1, 1), 480, smem, out_elems, 64, stages)
+
+
+def _pf(mode: str, Tq: int, Tk: int) -> tuple:
+    """(declarations, prefetch for the step whose first streamed row is `nc0`, take-over at the top of a step)."""
+    wpr = Tk // 32
+    if mode == "fwd":
+        return ("uint2 mw_n = make_uint2(0u, 0u);",
+                f"mw_n = __ldg(reinterpret_cast<const uint2*>(mask + (size_t)row * {wpr}u + (nc0 >> 5)));",
+                "const uint2 mw = mw_n;")
+    if mode == "dv":
+        return ("float lse_n = 0.f; unsigned mwe_n = 0u;",
+                f"{{ const unsigned qe_ = nc0 + wh * 32u + lane; lse_n = __ldg(lse + (size_t)z * {Tq}u + qe_); "
+                f"mwe_n = __ldg(mask + (size_t)qe_ * {wpr}u + (row >> 5)); }}",
+                "const float lse_e = lse_n; const unsigned mw_e = mwe_n;")
+    return ("unsigned bits_n = 0u;",
+            f"bits_n = __ldg(mask + (size_t)row * {wpr}u + (nc0 >> 5) + wh);",
+            "const unsigned bits = bits_n;")
 
 
 def _row_item_begin(mode: str, Tq: int, Tk: int) -> str:
@@ -491,7 +620,6 @@ def _row_step(mode, Tq, Tk, D, S0, DP0, PHI, PLO, OACC, sc2, fl2, sc, tau) -> st
                     unsigned v[32], u[32];
                     TMEM_LD32(lane_base + {S0}u + b * 64u + wh * 32u, v);             // mine
                     TMEM_LD32(lane_base + {S0}u + b * 64u + (wh ^ 1u) * 32u, u);      // the partner's
-                    const uint2 mw = __ldg(reinterpret_cast<const uint2*>(mask + (size_t)row * {wpr}u + (c0 >> 5)));
                     const unsigned mine_bits = wh ? mw.y : mw.x, other_bits = wh ? mw.x : mw.y;
                     TMEM_WAIT_LD();
                     TC_FENCE_BEFORE();
@@ -533,7 +661,9 @@ def _row_step(mode, Tq, Tk, D, S0, DP0, PHI, PLO, OACC, sc2, fl2, sc, tau) -> st
                         }}
                     }}
                     l_run += add;
+                    TRACE6
                     if (g != 0u) {{ mbar_wait(pvdone, (g - 1u) & 1u); TC_FENCE_AFTER(); }}     // the MMA that read P (and wrote O) is done
+                    TRACE7
                     if (resc) {{
                         {resc}
                     }}
@@ -547,9 +677,6 @@ def _row_step(mode, Tq, Tk, D, S0, DP0, PHI, PLO, OACC, sc2, fl2, sc, tau) -> st
                     TMEM_LD32(lane_base + {S0}u + b * 64u + wh * 32u, v);
                     // thread = key row; column e of this warp = query c0 + 32 wh + e.  Lane e fetches that query's lse and its
                     // mask word for this warp's 32 keys (coalesced); they reach the other lanes by shuffle.
-                    const unsigned qe = c0 + wh * 32u + lane;
-                    const float lse_e = __ldg(lse + (size_t)z * {Tq}u + qe);
-                    const unsigned mw_e = __ldg(mask + (size_t)qe * {wpr}u + (row >> 5));
                     const bool any_masked = __any_sync(0xffffffffu, mw_e != 0u);
                     TMEM_WAIT_LD();
                     TC_FENCE_BEFORE();
@@ -580,7 +707,6 @@ def _row_step(mode, Tq, Tk, D, S0, DP0, PHI, PLO, OACC, sc2, fl2, sc, tau) -> st
     return f"""unsigned v[32], d[32];
                     TMEM_LD32(lane_base + {S0}u + b * 64u + wh * 32u, v);
                     TMEM_LD32(lane_base + {DP0}u + b * 64u + wh * 32u, d);
-                    const unsigned bits = __ldg(mask + (size_t)row * {wpr}u + (c0 >> 5) + wh);
                     TMEM_WAIT_LD();
                     TC_FENCE_BEFORE();
                     __syncwarp();
