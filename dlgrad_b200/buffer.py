@@ -87,6 +87,7 @@ CONST_CACHE_ENTRIES = 4096
 _const_cache: dict = {}                  # content tag -> device storage
 _const_cache_bytes = [0]
 CONST_FOLD = os.environ.get("DLGRAD_CONST_FOLD", "1") != "0"
+HSPLIT_DEFER = os.environ.get("DLGRAD_HSPLIT_DEFER", "1") != "0"
 
 
 def _operand_tag(b: "Buffer"):
@@ -418,7 +419,7 @@ class Buffer:
             from dlgrad_b200.runtime.cuda import attention
             o = attention.flash_forward(x, y)                 # None: v does not fit, P is materialised below
             if o is not None:
-                return self._like(o, out_shape, dev)
+                return o
         if dev is _CUDA and y._pending is not None and y._pending[0] == "tr":
             # q @ k^T of attention-shaped operands is deferred: if scale -> masked_fill -> softmax follow, one
             # kernel produces the probabilities and this product never reaches HBM (runtime/cuda/attention.py)
@@ -430,6 +431,16 @@ class Buffer:
     def permute(self, order: tuple) -> "Buffer":
         out_shape = tuple(self.shape[i] for i in order)
         pend = self._pending
+        if tuple(order) == (0, 2, 1, 3) and self.metadata.device is _CUDA and self.scalar is None:
+            # the head split / merge of attention — (B, T, h, d) <-> (B, h, T, d), examples/gpt.py:46-48,63 — is deferred
+            # (pending kind "hsplit"): the flash-attention kernels and the GEMMs around them address the stored layout through
+            # rank-4 tensor maps, so q, k, v, the output and all four gradients never pass through a permute kernel; the
+            # merge of a deferred split (and the split of a deferred merge) is the stored buffer itself.  Any other
+            # consumer materialises it through `.ptr` with the permute kernel.
+            if pend is not None and pend[0] == "hsplit" and pend[1].shape == out_shape:
+                return pend[1]
+            if pend is None and self.numel >= LAZY_MIN_NUMEL and HSPLIT_DEFER and self.aligned:
+                return Buffer._deferred(("hsplit", self), out_shape, self.metadata.dtype)
         if pend is not None and pend[0] == "tr":
             # permuting a deferred transpose: one kernel over the stored operand with the composed order
             nd, src = self.ndim, pend[1]
@@ -452,6 +463,8 @@ class Buffer:
             pend = self._pending
             if pend is not None and pend[0] == "tr":
                 src = pend[1]
+                if src._pending is not None:
+                    return src                   # still deferred itself (a head split): hand it on, do not materialise it
                 return Buffer(src.ptr, src.shape, _CUDA, src.metadata.dtype, aligned=src.aligned, keep=src._keep)
             return Buffer._deferred(("tr", self), tuple(self.shape[i] for i in order), self.metadata.dtype)
         return self.permute(tuple(order))

@@ -42,11 +42,6 @@ from dlgrad_b200.runtime.cuda.compiler import KNAME
 
 _EXTRA = r"""
 __device__ __forceinline__ float ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-__device__ __forceinline__ void tma_load_4d(unsigned dst, const TMap* map, unsigned bar, int c0, int c1, int c2, int c3) {
-    asm volatile(
-        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-        :: "r"(dst), "l"((unsigned long long)map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
-}
 __device__ __forceinline__ void tma_prefetch_4d(const TMap* map, int c0, int c1, int c2, int c3) {
     asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];"
                  :: "l"((unsigned long long)map), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
@@ -92,11 +87,12 @@ def _sub(src: str, **kw) -> str:
 
 @cache
 def flash_attn(mode: str, Tq: int, Tk: int, D: int, H: int, NB: int, scale: float, fill: float,
-               out_strides: tuple = (0, 0, 0), tau: float = 8.0) -> TcKernel:
+               out_strides: tuple = (0, 0, 0), tau: float = 8.0, delta_split: bool = False) -> TcKernel:
     """mode "fwd" | "dv" | "ds" (module docstring).  Tq, Tk multiples of 128, D in (32, 64), NB = batch * H score planes,
     H heads (a plane z is head z % H of sequence z / H: every operand is addressed through a rank-4 tensor map
     (D, T, H, B), so both (B, h, T, D) and the projection's own (B, T, h, D) layout work without a permute kernel).
     `out_strides` = element strides (row, head, batch) of the direct-store output (O for fwd, dV for dv).
+    `delta_split` (ds): delta = rowsum(dO * O) is indexed (batch, row, head) — dO and O stored as (B, T, h, D).
     `tau`: the running maximum of the online softmax is only replaced when it grows by more than `tau` (base-2 units):
     any m gives the same P / l in exact arithmetic, and 2^tau bounds the un-normalised P, so O in tensor memory is
     rescaled almost never instead of almost always (tau = 0 forces the rescale path; the tests use it).
@@ -552,7 +548,7 @@ $KNAME$($PARAMS$)
             }
         }""", STAGES=stages, PER_STAGE16=per_stage // 16, TILE_B=tile_b, O_MMA=o_mma, TR3=TR(3, "g"), TR4=TR(4, "g")),
         A_KBLOCKS=a_tiles * kbq, A0=A0,
-        ROW_ITEM_BEGIN=_row_item_begin(mode, Tq, Tk), PF_DECL=_pf(mode, Tq, Tk)[0], PF_NEXT=_pf(mode, Tq, Tk)[1], PF_TAKE=_pf(mode, Tq, Tk)[2],
+        ROW_ITEM_BEGIN=_row_item_begin(mode, Tq, Tk, H, delta_split), PF_DECL=_pf(mode, Tq, Tk)[0], PF_NEXT=_pf(mode, Tq, Tk)[1], PF_TAKE=_pf(mode, Tq, Tk)[2],
         ROW_STEP=_row_step(mode, Tq, Tk, D, S0, DP0, PHI, PLO, OACC, sc2, fl2, _f32lit(float(np.float32(scale))), tau)
         .replace("TRACE6", TR(6, "g", "threadIdx.x == 64u")).replace("TRACE7", TR(7, "g", "threadIdx.x == 64u")),
         ROW_ITEM_END=_row_item_end(mode, Tq, Tk, D, OACC, sT, sH, sB, nS),
@@ -579,12 +575,12 @@ def _pf(mode: str, Tq: int, Tk: int) -> tuple:
             "const unsigned bits = bits_n;")
 
 
-def _row_item_begin(mode: str, Tq: int, Tk: int) -> str:
+def _row_item_begin(mode: str, Tq: int, Tk: int, H: int = 1, delta_split: bool = False) -> str:
     if mode == "fwd":
         return f"float m_run = {NEG_INF}, l_run = 0.f;      // l_run: this warp's 32 columns of every step only"
     if mode == "ds":
         return f"""const float lse_row = __ldg(lse + (size_t)z * {Tq}u + row);       // P = 2^(s c - lse) for this query row
-            const float d_row = __ldg(delta + (size_t)z * {Tq}u + row);       // rowsum(dO * O)
+            const float d_row = __ldg(delta + {"((size_t)bb * " + str(Tq) + "u + row) * " + str(H) + "u + hh" if delta_split else "(size_t)z * " + str(Tq) + "u + row"});       // rowsum(dO * O), in dO's storage order
             const unsigned my_epi = epi + (warp - 2u) * 4096u;
             unsigned char* sbuf_gen = smem_gen + (epi - smem) + (warp - 2u) * 4096u;
             // streamed tiles the mask kills entirely: dS is zero there whatever P and dP hold (eight lanes per 128-byte row;

@@ -653,6 +653,15 @@ extern "C" __global__ void __launch_bounds__({nthreads}, 1)
 # (4 stages instead of 3 at BN=128).
 # =====================================================================================================
 _HELPERS_TS = r"""
+__device__ __forceinline__ void tma_load_4d(unsigned dst, const TMap* map, unsigned bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        :: "r"(dst), "l"((unsigned long long)map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const TMap* map, unsigned src, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                 :: "l"((unsigned long long)map), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
 // true in exactly one lane of a converged warp; ptxas recognises the elect.sync predicate and issues the
 // guarded tcgen05 instructions once, without the per-thread serialisation loop an `if (lane == 0)` gets
 __device__ __forceinline__ bool elect_one() {
@@ -732,7 +741,7 @@ def matmul_tc_ts(M: int, N: int, K: int, batch: int, a_mn: bool, b_mn: bool, a_b
                  bn: int | None = None, stages: int | None = None, kc_blocks: int | None = None,
                  bias: bool = False, issuers: int | None = None, streamk: bool = False, ksparse: str | None = None,
                  a_relu: bool = False, b_relu: bool = False, splitk: int = 0,
-                 relu_mask: bool = False) -> TcKernel:
+                 relu_mask: bool = False, hsplit: int = 0) -> TcKernel:
     """Kernel parameters after C: `bias` (a length-N row the epilogue adds to every output row when `bias` is
     set — the Linear bias; it rides on the plain store) and `flags` (uint32[ntiles * 4], zero, used when
     `streamk` is set).
@@ -757,6 +766,11 @@ def matmul_tc_ts(M: int, N: int, K: int, batch: int, a_mn: bool, b_mn: bool, a_b
     applied where the operand passes through registers anyway: in the A splitter before the hi/lo split, in the B
     splitter (which then also writes the clamped value back as the `hi` tile).  The relu kernel and its 2 x 100 MB
     of traffic per MLP block disappear.
+
+    hsplit = H > 0 (with ksparse): the B operand and C are the per-head matrices of a (B, T, H, D) tensor — the layout the
+    q / k / v projections produce and consume — addressed through rank-4 tensor maps (D, T, H, B) with the batch index z
+    split into (z % H, z / H): dq = dS @ k and dk = dS^T @ q then read k, q and write their results in place of the
+    head split / merge permutes of examples/gpt.py:46-48.
 
     ksparse ("nn" | "tn"): the A operand is an attention matrix (P or dS, query rows x key columns; "tn" = it is read
     transposed) whose 128 x 128 tiles that the mask kills entirely are exactly zero.  `flags` then points at the
@@ -852,9 +866,19 @@ def matmul_tc_ts(M: int, N: int, K: int, batch: int, a_mn: bool, b_mn: bool, a_b
     nthreads = 64 + 128 + 128 + 128 + (32 if NI == 2 else 0)   # producer, MMA | 4 A-split | 4 B-split | 4 epilogue | 2nd MMA issuer
     epi_w0 = 10
 
+    if hsplit:
+        assert ksparse and not a_bcast and not b_bcast and N % 32 == 0
+
     def tma_issue(which, boxes, mn, tile_var, row0):
         tm = f"tm{which}"
         z = "0" if (a_bcast if which == "A" else b_bcast) else "z"
+        if hsplit and which == "B":
+            zz = f"(int)(z % {hsplit}u), (int)(z / {hsplit}u)"
+            if mn:
+                return "\n                    ".join(
+                    f"tma_load_4d({tile_var} + {j * 4096}u, &{tm}, full_bar, (int)({row0} + {j * 32}u), (int)k0, {zz});"
+                    for j in range(boxes))
+            return f"tma_load_4d({tile_var}, &{tm}, full_bar, (int)k0, (int){row0}, {zz});"
         if mn:
             return "\n                    ".join(
                 f"tma_load_3d({tile_var} + {j * 4096}u, &{tm}, full_bar, (int)({row0} + {j * 32}u), (int)k0, (int){z});"
@@ -999,6 +1023,8 @@ def matmul_tc_ts(M: int, N: int, K: int, batch: int, a_mn: bool, b_mn: bool, a_b
             }}"""
     else:
         sk_seg_begin, sk_seg_end = "const bool seg_head = false;", ""
+    CSTORE = (f"tma_store_4d(&tmC, my_epi + sb * 4096u, (int)(n0 + c * 32u), (int)(m0 + q * 32u), (int)(z % {hsplit}u), (int)(z / {hsplit}u));"
+              if hsplit else "tma_store_3d(&tmC, my_epi + sb * 4096u, (int)(n0 + c * 32u), (int)(m0 + q * 32u), (int)z);")
     zero_tile = "" if not ksparse else f"""if (lk == 0u) {{
                     // every k-block of this output tile lies in a dead attention tile: the product is exactly zero
                     #pragma unroll 1
@@ -1013,7 +1039,7 @@ def matmul_tc_ts(M: int, N: int, K: int, batch: int, a_mn: bool, b_mn: bool, a_b
                             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                             __syncwarp();
                             if (lane == 0) {{
-                                tma_store_3d(&tmC, my_epi + sb * 4096u, (int)(n0 + c * 32u), (int)(m0 + q * 32u), (int)z);
+                                {CSTORE}
                                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                             }}
                             ++nstore;
@@ -1229,7 +1255,7 @@ extern "C" __global__ void __launch_bounds__({nthreads}, 1)
                         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                         __syncwarp();
                         if (lane == 0) {{
-                            if (plain) tma_store_3d(&tmC, my_epi + sb * 4096u, (int)(n0 + c * 32u), (int)(m0 + q * 32u), (int)z);
+                            if (plain) {{ {CSTORE} }}
                             else tma_reduce_add_3d(&tmC, my_epi + sb * 4096u, (int)(n0 + c * 32u), (int)(m0 + q * 32u), (int)z);
                             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                         }}
@@ -1253,7 +1279,7 @@ extern "C" __global__ void __launch_bounds__({nthreads}, 1)
     }}
 }}
 """
-    return TcKernel("mm_tcts" + ("_b" if bias else "") + ("_sk" if streamk else "") + (f"_sp{ksparse}" if ksparse else "") + ("_ra" if a_relu else "") + ("_rb" if b_relu else "") + (f"_k{splitk}" if splitk > 1 else "") + ("_rm" if relu_mask else ""), src, (grid, 1, 1), nthreads, smem, batch * M * N, BN, stages)
+    return TcKernel("mm_tcts" + ("_b" if bias else "") + ("_sk" if streamk else "") + (f"_sp{ksparse}" if ksparse else "") + ("_ra" if a_relu else "") + ("_rb" if b_relu else "") + (f"_k{splitk}" if splitk > 1 else "") + ("_rm" if relu_mask else "") + ("_hs" if hsplit else ""), src, (grid, 1, 1), nthreads, smem, batch * M * N, BN, stages)
 
 
 # =====================================================================================================

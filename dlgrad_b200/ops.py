@@ -419,7 +419,11 @@ class MatMul(OP):
                     gx = lazy_t(mm(yr, g, batch + (self.p1[-1], self.p1[-2]), trans_y=True))
                 else:
                     gx = None
-                    if yr._pending is None and g._pending is None:
+                    from dlgrad_b200.runtime.cuda import attention as _att
+                    if yr._pending is not None and yr._pending[0] == "tr":
+                        # dq = dS @ k with k (and dq) in the projections' (B, T, h, D) layout: no permute on either side
+                        gx = _att.ds_gemm(g, yr._pending[1], False)
+                    if gx is None and _att._stored(yr) and _att._stored(g):
                         # dP = dO @ v^T of an attention block: deferred, so that the softmax / masked_fill / scale
                         # backward that follow can absorb it into one kernel (runtime/cuda/attention.dscores)
                         from dlgrad_b200.runtime.cuda import attention
@@ -434,12 +438,14 @@ class MatMul(OP):
                 if xr._pending is not None or yr._pending is None:
                     from dlgrad_b200.runtime.cuda import attention
                     rec = attention.flash_record(xr, yr)
-                if rec is not None and g._pending is None and g.aligned:
+                if rec is not None and attention._stored(g) and g.aligned:
                     # x is the attention matrix P that the flash forward consumed without writing it: dv = P^T @ dO with
                     # P recomputed per tile from q, k and the saved row statistics
-                    gy = Buffer(attention.flash_dv(rec, g), batch + (self.p2[-2], self.p2[-1]), dev, g.dtype)
+                    gy = attention.flash_dv(rec, g)
                 elif yr._pending is not None and yr._pending[0] == "tr":
-                    gy = lazy_t(mm(g, xr, batch + (self.p2[-1], self.p2[-2]), trans_x=True))
+                    from dlgrad_b200.runtime.cuda import attention as _att2
+                    dk = _att2.ds_gemm(g, xr, True)              # dk = dS^T @ q, layouts as for dq above
+                    gy = lazy_t(dk if dk is not None else mm(g, xr, batch + (self.p2[-1], self.p2[-2]), trans_x=True))
                 else:
                     gy = mm(xr, g, batch + (self.p2[-2], self.p2[-1]), trans_x=True)
                 gy = unbroadcast(gy, self.y.shape)

@@ -73,13 +73,18 @@ def _mask_digest(mask: Buffer, Tq: int, Tk: int):
     return bits
 
 
+def _stored(b: Buffer) -> bool:
+    """materialised, or a deferred head split / merge of a materialised buffer (read in place through strided tensor maps)"""
+    return b._pending is None or (b._pending[0] == "hsplit" and b._pending[1]._pending is None)
+
+
 def eligible(x: Buffer, y: Buffer) -> bool:
     """`x @ y` with y a deferred transpose of k: (.., Tq, D) @ (.., Tk, D)^T, same batch dims, tile-sized."""
-    if not ENABLED or y._pending is None or y._pending[0] != "tr" or x._pending is not None:
+    if not ENABLED or y._pending is None or y._pending[0] != "tr" or not _stored(x):
         return False
     k = y._pending[1]
     xs, ks = x.metadata.shape, k.metadata.shape
-    if len(xs) < 3 or len(xs) != len(ks) or xs[:-2] != ks[:-2] or xs[-1] != ks[-1] or k._pending is not None:
+    if len(xs) < 3 or len(xs) != len(ks) or xs[:-2] != ks[:-2] or xs[-1] != ks[-1] or not _stored(k):
         return False
     if y.metadata.shape != ks[:-2] + (ks[-1], ks[-2]):
         return False
@@ -240,9 +245,27 @@ def _geom(q: Buffer, k: Buffer):
     return nb, H, nb // H, Tq, Tk, D
 
 
-def _strides(T: int, D: int, H: int):
-    """element strides (row, head, batch) of a contiguous (B, H, T, D) operand"""
-    return (D, T * D, H * T * D)
+def _strides(T: int, D: int, H: int, split: bool = False):
+    """element strides (row, head, batch) of a (B, H, T, D) operand: contiguous, or stored as (B, T, H, D) (`split`: a
+    deferred head split — the projection's own layout)"""
+    return (H * D, D, T * H * D) if split else (D, T * D, H * T * D)
+
+
+def _resolve(b: Buffer):
+    """(buffer that holds the data, stored-as-(B,T,H,D) flag) of an operand that is materialised or a deferred head split"""
+    if b._pending is not None and b._pending[0] == "hsplit" and b._pending[1]._pending is None:
+        return b._pending[1], True
+    return b, False
+
+
+def _wrap(ptr, shape: tuple, split: bool) -> Buffer:
+    """Buffer of logical shape (B, H, T, D) over `ptr`; when the kernel wrote the (B, T, H, D) layout it is handed on as a
+    deferred head split of that storage, which the merge (`transpose(1, 2)`) that follows cancels."""
+    from dlgrad_b200.device import Device
+    if not split:
+        return Buffer(ptr, shape, Device.CUDA)
+    B, H, T, D = shape
+    return Buffer._deferred(("hsplit", Buffer(ptr, (B, T, H, D), Device.CUDA)), shape)
 
 
 def _tc_plan(kern, maps: list, nptrs: int):
@@ -280,28 +303,31 @@ def _timed(tag: tuple, flops: float, fn):
 
 
 def flash_forward(P: Buffer, v: Buffer):
-    """O = P @ v for a deferred P, without materialising P.  Returns the owned pointer of O (batch.., Tq, D), or None when
-    v does not fit the pattern (the caller then takes the ordinary route, which materialises P)."""
+    """O = P @ v for a deferred P, without materialising P.  Returns O as a Buffer (batch.., Tq, D) — in the layout q came
+    in: a deferred head split when q is one — or None when v does not fit the pattern (the caller then takes the ordinary
+    route, which materialises P)."""
     from dlgrad_b200.codegen import cuda_flash as cf
     from dlgrad_b200.runtime.cuda import ops as _ops
     _, q, k, scale, mask, fill = P._pending
     nb, H, B, Tq, Tk, D = _geom(q, k)
     vs = v.metadata.shape
-    if (v._pending is not None or v.scalar is not None or not v.aligned or tuple(vs) != tuple(k.metadata.shape)
-            or q._pending is not None or k._pending is not None):
+    if (not _stored(v) or v.scalar is not None or not v.aligned or tuple(vs) != tuple(k.metadata.shape)
+            or not _stored(q) or not _stored(k)):
         return None
-    key = ("fwd", nb, H, Tq, Tk, D, scale, fill, FLASH_TAU)
+    (qb, qs), (kb, ks), (vb, vsplit) = _resolve(q), _resolve(k), _resolve(v)
+    if len(q.metadata.shape) != 4:
+        qs = ks = vsplit = False
+    key = ("fwd", nb, H, Tq, Tk, D, scale, fill, FLASH_TAU, qs, ks, vsplit)
     plan = _tc_plans.get(key)
     if plan is None:
-        so = _strides(Tq, D, H)
-        kern = cf.flash_attn("fwd", Tq, Tk, D, H, nb, scale, fill, so, FLASH_TAU)
-        maps = [cf.tmap4(Tq, D, H, B, _strides(Tq, D, H), 128), cf.tmap4(Tk, D, H, B, _strides(Tk, D, H), 64),
-                cf.tmap4(Tk, D, H, B, _strides(Tk, D, H), 32, mn=True)]
+        kern = cf.flash_attn("fwd", Tq, Tk, D, H, nb, scale, fill, _strides(Tq, D, H, qs), FLASH_TAU)
+        maps = [cf.tmap4(Tq, D, H, B, _strides(Tq, D, H, qs), 128), cf.tmap4(Tk, D, H, B, _strides(Tk, D, H, ks), 64),
+                cf.tmap4(Tk, D, H, B, _strides(Tk, D, H, vsplit), 32, mn=True)]
         plan = _tc_plans[key] = _tc_plan(kern, maps, 3)
     bits = _mask_digest(mask, Tq, Tk)
     out = shim.alloc(nb * Tq * D * 4)
     stats = shim.alloc(nb * Tq * 8)
-    pq, pk, pv = _ops._dev_ptr(q), _ops._dev_ptr(k), _ops._dev_ptr(v)
+    pq, pk, pv = _ops._dev_ptr(qb), _ops._dev_ptr(kb), _ops._dev_ptr(vb)
     _timed(("attn_flash_fwd", Tq, Tk, D, nb), 4.0 * nb * Tq * Tk * D,
            lambda: _tc_run(plan, [pq, pk, pv], [out, stats, bits], "flash attention forward"))
     rec = _FlashRecord()
@@ -309,7 +335,7 @@ def flash_forward(P: Buffer, v: Buffer):
     rec.geom = (nb, H, B, Tq, Tk, D)
     _flash[id(P)] = rec
     weakref.finalize(P, _flash.pop, id(P), None)
-    return out
+    return _wrap(out, tuple(q.metadata.shape), qs)
 
 
 def flash_record(P: Buffer, v: Buffer | None = None):
@@ -319,23 +345,26 @@ def flash_record(P: Buffer, v: Buffer | None = None):
     return rec
 
 
-def flash_dv(rec, dO: Buffer):
-    """dv = P^T @ dO with P recomputed per tile from q, k and the saved row statistics."""
+def flash_dv(rec, dO: Buffer) -> Buffer:
+    """dv = P^T @ dO with P recomputed per tile from q, k and the saved row statistics; dv comes out in v's layout."""
     from dlgrad_b200.codegen import cuda_flash as cf
     from dlgrad_b200.runtime.cuda import ops as _ops
     nb, H, B, Tq, Tk, D = rec.geom
-    key = ("dv", nb, H, Tq, Tk, D, rec.scale, rec.fill)
+    (qb, qs), (kb, ks), (_, vsplit), (db, dsplit) = _resolve(rec.q), _resolve(rec.k), _resolve(rec.v), _resolve(dO)
+    if len(rec.q.metadata.shape) != 4:
+        qs = ks = vsplit = dsplit = False
+    key = ("dv", nb, H, Tq, Tk, D, rec.scale, rec.fill, qs, ks, vsplit, dsplit)
     plan = _tc_plans.get(key)
     if plan is None:
-        kern = cf.flash_attn("dv", Tq, Tk, D, H, nb, rec.scale, rec.fill, _strides(Tk, D, H))
-        maps = [cf.tmap4(Tk, D, H, B, _strides(Tk, D, H), 128), cf.tmap4(Tq, D, H, B, _strides(Tq, D, H), 64),
-                cf.tmap4(Tq, D, H, B, _strides(Tq, D, H), 32, mn=True)]
+        kern = cf.flash_attn("dv", Tq, Tk, D, H, nb, rec.scale, rec.fill, _strides(Tk, D, H, vsplit))
+        maps = [cf.tmap4(Tk, D, H, B, _strides(Tk, D, H, ks), 128), cf.tmap4(Tq, D, H, B, _strides(Tq, D, H, qs), 64),
+                cf.tmap4(Tq, D, H, B, _strides(Tq, D, H, dsplit), 32, mn=True)]
         plan = _tc_plans[key] = _tc_plan(kern, maps, 3)
     out = shim.alloc(nb * Tk * D * 4)
-    pk, pq, pd = _ops._dev_ptr(rec.k), _ops._dev_ptr(rec.q), _ops._dev_ptr(dO)
+    pk, pq, pd = _ops._dev_ptr(kb), _ops._dev_ptr(qb), _ops._dev_ptr(db)
     _timed(("attn_flash_dv", Tq, Tk, D, nb), 4.0 * nb * Tq * Tk * D,
            lambda: _tc_run(plan, [pk, pq, pd], [out, rec.stats, rec.bits], "flash attention dV"))
-    return out
+    return _wrap(out, tuple(rec.v.metadata.shape), vsplit)
 
 
 def flash_ds(rec, dO: Buffer, O: Buffer, dS_owner: Buffer):
@@ -345,20 +374,68 @@ def flash_ds(rec, dO: Buffer, O: Buffer, dS_owner: Buffer):
     from dlgrad_b200.codegen import cuda_kernel as ck
     from dlgrad_b200.runtime.cuda import ops as _ops
     nb, H, B, Tq, Tk, D = rec.geom
-    key = ("ds", nb, H, Tq, Tk, D, rec.scale, rec.fill)
+    (qb, qs), (kb, ks), (vb, vsplit), (db, dsplit), (ob, osplit) = (_resolve(rec.q), _resolve(rec.k), _resolve(rec.v),
+                                                                   _resolve(dO), _resolve(O))
+    if len(rec.q.metadata.shape) != 4:
+        qs = ks = vsplit = dsplit = osplit = False
+    if dsplit != osplit:                       # rowsum(dO * O) walks both operands in storage order: they must agree
+        db, dsplit, ob, osplit = dO, False, O, False          # (reading .ptr below materialises the deferred one)
+    key = ("ds", nb, H, Tq, Tk, D, rec.scale, rec.fill, qs, ks, vsplit, dsplit)
     ent = _tc_plans.get(key)
     if ent is None:
-        kern = cf.flash_attn("ds", Tq, Tk, D, H, nb, rec.scale, rec.fill)
-        sq, sk = _strides(Tq, D, H), _strides(Tk, D, H)
-        maps = [cf.tmap4(Tq, D, H, B, sq, 128), cf.tmap4(Tq, D, H, B, sq, 128), cf.tmap4(Tk, D, H, B, sk, 64),
-                cf.tmap4(Tk, D, H, B, sk, 64),
+        kern = cf.flash_attn("ds", Tq, Tk, D, H, nb, rec.scale, rec.fill, delta_split=dsplit)
+        maps = [cf.tmap4(Tq, D, H, B, _strides(Tq, D, H, qs), 128), cf.tmap4(Tq, D, H, B, _strides(Tq, D, H, dsplit), 128),
+                cf.tmap4(Tk, D, H, B, _strides(Tk, D, H, ks), 64), cf.tmap4(Tk, D, H, B, _strides(Tk, D, H, vsplit), 64),
                 dict(rank=3, dims=(Tk, Tq, nb), strides=(Tk * 4, Tq * Tk * 4), box=(32, 32, 1), swizzle=3)]
         ent = _tc_plans[key] = (_tc_plan(kern, maps, 4), _ops.Plan(ck.rowdot(nb * Tq, D)))
     plan, dot_plan = ent
-    delta = dot_plan.run(_ops._dev_ptr(dO), _ops._dev_ptr(O))
+    delta = dot_plan.run(_ops._dev_ptr(db), _ops._dev_ptr(ob))       # rows in storage order: (b, h, t), or (b, t, h) when split
     out = shim.alloc(nb * Tq * Tk * 4)
-    pq, pd, pk, pv = _ops._dev_ptr(rec.q), _ops._dev_ptr(dO), _ops._dev_ptr(rec.k), _ops._dev_ptr(rec.v)
+    pq, pd, pk, pv = _ops._dev_ptr(qb), _ops._dev_ptr(db), _ops._dev_ptr(kb), _ops._dev_ptr(vb)
     _timed(("attn_flash_ds", Tq, Tk, D, nb), 4.0 * nb * Tq * Tk * D,
            lambda: _tc_run(plan, [pq, pd, pk, pv, out], [out, rec.stats, delta, rec.bits], "flash attention dS"))
     _fresh[shim.address(out)] = (rec.bits, rec.bits + Tq * Tk // 32, Tq, Tk)
     return out
+
+
+def ds_gemm(dS: Buffer, other: Buffer, trans_x: bool):
+    """dq = dS @ k (trans_x False) or dk = dS^T @ q (trans_x True) on the tile-skipping GEMM, reading k / q in the layout they
+    are stored in and writing the result the same way: when `other` is a deferred head split — (B, T, h, D) storage, the
+    projection's own layout — the GEMM addresses it through rank-4 tensor maps and the result is handed on as a deferred
+    head split too, which the merge that follows cancels (no permute kernels on either side).  None when dS carries no
+    live-tile table or the shapes do not fit; the caller then takes the ordinary matmul route."""
+    from dlgrad_b200.codegen import cuda_flash as cf
+    from dlgrad_b200.codegen import cuda_tcgen05 as tcg
+    from dlgrad_b200.runtime.cuda import ops as _ops
+    if not SPARSE or len(dS.metadata.shape) != 4 or tuple(other.metadata.shape[:2]) != tuple(dS.metadata.shape[:2]):
+        return None
+    ob, split = _resolve(other)
+    if not split or not _stored(other) or not other.aligned:
+        return None
+    if dS._pending is not None:
+        _ops.materialize(dS)                    # the flash dS kernel runs here and registers the live-tile table
+    info = tag_of(dS)
+    if info is None:
+        return None
+    _, flags, Tq, Tk = info
+    Bn, H = dS.metadata.shape[0], dS.metadata.shape[1]
+    nb = Bn * H
+    T_other, D = other.metadata.shape[-2], other.metadata.shape[-1]
+    if dS.metadata.shape[-2:] != (Tq, Tk) or T_other != (Tq if trans_x else Tk) or D % 32 or Tq % 128 or Tk % 128:
+        return None
+    M, K = (Tk, Tq) if trans_x else (Tq, Tk)
+    key = ("dsgemm", nb, H, Tq, Tk, D, trans_x)
+    plan = _tc_plans.get(key)
+    if plan is None:
+        kern = tcg.matmul_tc_ts(M, D, K, nb, trans_x, True, False, False, ksparse="tn" if trans_x else "nn", hsplit=H)
+        da, _, _ = tcg.tmap_descs(M, D, K, nb, trans_x, True, False, False, kern.bn)
+        so = _strides(T_other, D, H, True)
+        sc = _strides(M, D, H, True)
+        maps = [da, cf.tmap4(T_other, D, H, Bn, so, 32, mn=True),
+                dict(rank=4, dims=(D, M, H, Bn), strides=(sc[0] * 4, sc[1] * 4, sc[2] * 4), box=(32, 32, 1, 1), swizzle=3)]
+        plan = _tc_plans[key] = _tc_plan(kern, maps, 3)
+    out = shim.alloc(nb * M * D * 4)
+    pa, pb = _ops._dev_ptr(dS), _ops._dev_ptr(ob)
+    _timed(("tc3_sp" + ("tn" if trans_x else "nn") + "_hs", M, D, K, nb), 2.0 * nb * M * D * K,
+           lambda: _tc_run(plan, [pa, pb, out], [out, shim.NULL, flags], "tile-skipping GEMM over the head-split layout"))
+    return _wrap(out, tuple(dS.metadata.shape[:2]) + (M, D), True)

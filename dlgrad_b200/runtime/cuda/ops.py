@@ -189,6 +189,9 @@ def materialize(buf: Buffer) -> None:
     if pend[0] == "relu":
         buf.ptr = pend[1].relu().ptr
         return
+    if pend[0] == "hsplit":
+        buf.ptr = permute(pend[1], (0, 2, 1, 3))
+        return
     if pend[0] == "attnP":
         from dlgrad_b200.runtime.cuda import attention
         attention.materialize_p(buf)
@@ -206,7 +209,7 @@ def materialize(buf: Buffer) -> None:
             vt = gp[2]
             rec = attention.flash_record(y)
             if (rec is not None and m is not None and vt._pending is not None and vt._pending[0] == "tr" and gp[3] is not None
-                    and vt._pending[1] is rec.v and m[0] is rec.mask and m[1] == rec.scale and gp[1]._pending is None):
+                    and vt._pending[1] is rec.v and m[0] is rec.mask and m[1] == rec.scale and attention._stored(gp[1])):
                 # P was never written (flash forward): recompute it per tile from q, k and the row statistics
                 buf.ptr = attention.flash_ds(rec, gp[1], gp[3], buf)
                 attention.claim(buf)

@@ -79,6 +79,13 @@ def test_c5_transformer_block_forward_backward_vs_oracle(oracle):
             scale = float(np.abs(b).max())
             check(a[~keep], b[~keep], rtol=1e-2, atol=1e-2 * scale, what="C5 block dc_fc, hidden units with a flipped relu")
             runner.rel_check(check, a[keep], b[keep], runner.TOL_MATMUL, "C5 block dc_fc")
+        elif k in ("dq_proj", "dk_proj"):
+            # gradients that pass through the softmax backward: the oracle differentiates the reference's UNFUSED fp32 chain
+            # (max / sub / exp / sum / div over 1024-long rows), which is ill-conditioned on small entries — its own result
+            # moves by ~1e-5 with the summation order (tests/test_oracle_golden.py) and sits ~5e-4 of the largest magnitude
+            # from float64 at this size, while the flash kernels stay within 1e-4 of float64
+            # (test_flash_attention_forward_and_backward[8-12-1024-64]).  Held to 1e-3, like the GPT-level gradients.
+            runner.rel_check(check, a, b, 1e-3, f"C5 block {k}")
         else:
             runner.rel_check(check, a, b, runner.TOL_MATMUL, f"C5 block {k}")
 
@@ -432,3 +439,46 @@ def test_flash_attention_dead_rows_and_round1_kernels(oracle):
             runner.rel_check(check, a, b, 1e-4, f"{what}: flash vs round-1 fused kernels")
     finally:
         attention.FLASH, attention.MIN_SCORES = old
+
+
+def test_attention_in_the_projections_layout_needs_no_permute_kernels(oracle):
+    """The attention block exactly as examples/gpt.py:44-64 writes it — q / k / v = Linear(x).reshape(B, T, h, d)
+    .transpose(1, 2), y.transpose(1, 2).reshape(B, T, C) — on CUDA: the head split / merge transposes are deferred (Buffer
+    pending kind "hsplit"), the flash kernels and the two tile-skipping GEMMs read q, k, v, dO and write O, dq, dk, dv in
+    the (B, T, h, d) layout through rank-4 tensor maps, so NO permute kernel runs forward or backward (the reference runs
+    8 per layer).  Output and every gradient vs the oracle, which executes the reference's graph."""
+    from dlgrad_b200 import Tensor
+    from dlgrad_b200.runtime.cuda import attention, profile
+    B, T, H, D = 1, 512, 16, 64
+    C = H * D
+    rng = np.random.default_rng(21)
+    x = (rng.random((B, T, C), dtype=np.float32) - 0.5).astype(np.float32)
+    ws = [((rng.random((C, C), dtype=np.float32) - 0.5) * (2.0 / np.sqrt(C))).astype(np.float32) for _ in range(3)]
+    coef = np.linspace(0.5, 1.5, B * T * C, dtype=np.float32).reshape(B, T, C)
+    old = attention.MIN_SCORES
+    attention.MIN_SCORES = 1 << 20
+    res = {}
+    try:
+        for dev in ("cuda", "cpu"):
+            X = Tensor(x.copy(), device=dev, requires_grad=True)
+            W = [Tensor(w.copy(), device=dev, requires_grad=True) for w in ws]
+            if dev == "cuda" and not COMPILE_ONLY:
+                profile.kernel_timer = profile.KernelTimer()
+            q, k, v = (X.linear(w, None).reshape((B, T, H, D)).transpose(1, 2) for w in W)
+            att = (q @ k.transpose(2, 3)) * (D ** -0.5)
+            mask = Tensor.tril(Tensor.ones((T, T)), k=0.0)
+            att = att.masked_fill(mask == Tensor(0.0), float("-inf")).softmax(dim=3)
+            y = (att @ v).transpose(1, 2).reshape((B, T, C))
+            (y * Tensor(coef.copy(), device=dev)).sum().backward()
+            res[dev] = [y.numpy(), X.grad.numpy()] + [w.grad.numpy() for w in W]
+            if dev == "cuda" and not COMPILE_ONLY:
+                tags = profile.kernel_timer.collect()["by_tag"]
+                profile.kernel_timer = None
+                names = sorted({t[0] for t in tags})
+                assert not any("permute" in n or "transpose" in n for n in names), f"permute kernels ran: {names}"
+                assert att.data._pending is not None, "P must not have been materialised"
+    finally:
+        attention.MIN_SCORES = old
+        profile.kernel_timer = None
+    for a, b, what in zip(res["cuda"], res["cpu"], ("y", "dx", "dWq", "dWk", "dWv")):
+        runner.rel_check(check, a, b, 1e-4 if what in ("y", "dWv") else 1e-3, f"attention in the (B, T, h, d) layout: {what}")
