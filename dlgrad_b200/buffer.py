@@ -603,6 +603,21 @@ class Buffer:
         if dev is _CUDA and CONST_FOLD and _operand_tag(self) is not None and _operand_tag(other) is not None:
             run = lambda: self._like(_dispatch(op=op, device=dev, x=self, y=other), out_shape, dev)  # noqa: E731
             return Buffer._folded(dev, (op.name,), (self, other), out_shape, run)
+        if op is BinaryOps.ADD and dev is _CUDA and (self._pending is not None or other._pending is not None):
+            # one operand is a deferred GEMM / RMSNorm gradient that can absorb this addition (runtime/cuda/ops.fused_add)
+            for r, d in ((self, other), (other, self)):
+                if d._pending is not None and d._pending[0] in ("lin", "lin_dx", "rms_dx"):
+                    from dlgrad_b200.runtime.cuda import ops as _cuda_ops
+                    ptr = _cuda_ops.fused_add(r, d)
+                    if ptr is not None:
+                        out = self._like(ptr, out_shape, dev)
+                        # `d` itself was never written.  Should somebody still read it, it is recovered as out - r (equal to
+                        # the product up to one rounding of the sum) — a recipe that no longer reads the weight, so an
+                        # optimizer step need not materialise every consumed Linear output that the graph keeps alive
+                        # (flush_pending would: a deferred producer must run before one of its sources is overwritten)
+                        d._pending = ("diff", out, r)
+                        return out
+                    break
         if op is BinaryOps.MUL and dev is _CUDA:
             if other.scalar is not None and self.scalar is None and self.numel >= LAZY_MIN_NUMEL:
                 return Buffer._deferred(("scale", self, float(other.scalar)), out_shape, self.dtype)

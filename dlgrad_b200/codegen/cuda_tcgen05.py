@@ -741,7 +741,7 @@ def matmul_tc_ts(M: int, N: int, K: int, batch: int, a_mn: bool, b_mn: bool, a_b
                  bn: int | None = None, stages: int | None = None, kc_blocks: int | None = None,
                  bias: bool = False, issuers: int | None = None, streamk: bool = False, ksparse: str | None = None,
                  a_relu: bool = False, b_relu: bool = False, splitk: int = 0,
-                 relu_mask: bool = False, hsplit: int = 0) -> TcKernel:
+                 relu_mask: bool = False, hsplit: int = 0, radd: bool = False) -> TcKernel:
     """Kernel parameters after C: `bias` (a length-N row the epilogue adds to every output row when `bias` is
     set — the Linear bias; it rides on the plain store) and `flags` (uint32[ntiles * 4], zero, used when
     `streamk` is set).
@@ -766,6 +766,11 @@ def matmul_tc_ts(M: int, N: int, K: int, batch: int, a_mn: bool, b_mn: bool, a_b
     applied where the operand passes through registers anyway: in the A splitter before the hi/lo split, in the B
     splitter (which then also writes the clamped value back as the `hi` tile).  The relu kernel and its 2 x 100 MB
     of traffic per MLP block disappear.
+
+    radd: `bias` points at a matrix R laid out like C; the epilogue writes C + R (added once, by the chunk that stores).  This
+    is the residual connection `x + proj(h)` of examples/gpt.py:88-89 and the gradient accumulation `grad + g @ W` of
+    dlgrad/tensor.py:805 riding on the GEMM that produces the second operand: the separate broadcast-free ADD kernel (three
+    passes over a (tokens, C) matrix) becomes one extra read inside the epilogue.
 
     hsplit = H > 0 (with ksparse): the B operand and C are the per-head matrices of a (B, T, H, D) tensor — the layout the
     q / k / v projections produce and consume — addressed through rank-4 tensor maps (D, T, H, B) with the batch index z
@@ -946,6 +951,32 @@ def matmul_tc_ts(M: int, N: int, K: int, batch: int, a_mn: bool, b_mn: bool, a_b
                                 const float4 xv = *reinterpret_cast<const float4*>(sbuf_gen + lane * 128u + ((j ^ (lane & 7u)) << 4));
                                 {sel}
                             }}
+                        }}"""
+    if radd:
+        assert not bias and not streamk and not splitk and not relu_mask and N % 4 == 0
+        addv = " ".join(
+            f"v[4 * j + {i}] = __float_as_uint(__fadd_rn(xv.{c}, __uint_as_float(v[4 * j + {i}])));" for i, c in enumerate("xyzw"))
+        mask_code = f"""
+                        if (plain) {{
+                            // C + R: the R tile comes in coalesced (4 rows x 128 B per instruction, 8 loads in flight per lane)
+                            // through the staging box; each thread then adds the row it owns (R + product: the operand order of
+                            // the ADD kernel this replaces)
+                            #pragma unroll
+                            for (unsigned i = 0; i < 8u; ++i) {{
+                                const unsigned r = 4u * i + (lane >> 3), cc = lane & 7u;
+                                const unsigned row = m0 + q * 32u + r, col = n0 + c * 32u + cc * 4u;
+                                float4 xv = make_float4(0.f, 0.f, 0.f, 0.f);
+                                if (row < {M}u && col < {N}u)
+                                    xv = __ldg(reinterpret_cast<const float4*>(bias + ((size_t)z * {M}u + row) * {N}u + col));
+                                *reinterpret_cast<float4*>(sbuf_gen + r * 128u + ((cc ^ (r & 7u)) << 4)) = xv;
+                            }}
+                            __syncwarp();
+                            #pragma unroll
+                            for (unsigned j = 0; j < 8u; ++j) {{
+                                const float4 xv = *reinterpret_cast<const float4*>(sbuf_gen + lane * 128u + ((j ^ (lane & 7u)) << 4));
+                                {addv}
+                            }}
+                            __syncwarp();
                         }}"""
     if streamk:
         sk_seg_begin = """const bool seg_head = kb0 == 0u && kb1 < %du;      // k-head of a tile shared with the next CTA
@@ -1279,7 +1310,7 @@ extern "C" __global__ void __launch_bounds__({nthreads}, 1)
     }}
 }}
 """
-    return TcKernel("mm_tcts" + ("_b" if bias else "") + ("_sk" if streamk else "") + (f"_sp{ksparse}" if ksparse else "") + ("_ra" if a_relu else "") + ("_rb" if b_relu else "") + (f"_k{splitk}" if splitk > 1 else "") + ("_rm" if relu_mask else "") + ("_hs" if hsplit else ""), src, (grid, 1, 1), nthreads, smem, batch * M * N, BN, stages)
+    return TcKernel("mm_tcts" + ("_b" if bias else "") + ("_sk" if streamk else "") + (f"_sp{ksparse}" if ksparse else "") + ("_ra" if a_relu else "") + ("_rb" if b_relu else "") + (f"_k{splitk}" if splitk > 1 else "") + ("_rm" if relu_mask else "") + ("_hs" if hsplit else "") + ("_ra2" if radd else ""), src, (grid, 1, 1), nthreads, smem, batch * M * N, BN, stages)
 
 
 # =====================================================================================================

@@ -215,6 +215,7 @@ class RSqrt(OP):
 # id(gradient Buffer) -> id(pre-activation Buffer)   (Buffer.__eq__ is the elementwise op, so no dict keyed by the object)
 _premasked: dict = {}
 RELU_BWD_EPILOGUE = os.environ.get("DLGRAD_RELU_BWD_EPILOGUE", "1") != "0"
+LAZY_LINEAR = os.environ.get("DLGRAD_LAZY_LINEAR", "1") != "0"      # deferred Linear outputs / input gradients / rms_dx (fused adds)
 
 
 class Relu(OP):
@@ -328,7 +329,10 @@ class RMSNorm(OP):
         g, x, w, t = upstream_grad, self.x, self.w, self.rstd
         gx = gw = None
         if self.req_grad[0]:
-            if w is not None:
+            if w is not None and LAZY_LINEAR and x.numel >= (1 << 20) and g.shape == x.shape:
+                # deferred ("rms_dx"): usually added to the residual stream's gradient next — one kernel for both
+                gx = Buffer._deferred(("rms_dx", g, w, t), x.shape, x.dtype)
+            elif w is not None:
                 gx = Buffer(_rt.ewise3("rms_dx", "(v0 * v1) * v2", x.shape, [g, w, t]), x.shape, Device.CUDA, x.dtype)
             else:
                 gx = Buffer(_rt.ewise3("rms_dx", "v0 * v1", x.shape, [g, t]), x.shape, Device.CUDA, x.dtype)
@@ -476,6 +480,11 @@ class Linear(OP):
             y, applied = dispatcher.dispatch(op=BinaryOps.MATMUL, device=Device.CUDA, x=x2, y=weight, trans_y=True, bias=bias)
             out = Buffer(y, x.shape[:-1] + (out_f,), Device.CUDA, x.dtype)
             return out if applied else out + bias
+        if bias is None and LAZY_LINEAR and rows * out_f >= (1 << 20) and weight._pending is None:
+            # deferred (Buffer pending kind "lin"): when the consumer is an addition — the residual connection
+            # `x + proj(h)`, examples/gpt.py:88-89 — the GEMM runs with the add in its epilogue (matmul_tc_ts `radd`) and
+            # the three-pass ADD kernel disappears; every other consumer materialises it through `.ptr`
+            return Buffer._deferred(("lin", x2, weight), x.shape[:-1] + (out_f,), x.dtype)
         y = dispatcher.dispatch(op=BinaryOps.MATMUL, device=Device.CUDA, x=x2, y=weight, trans_y=True)
         out = Buffer(y, x.shape[:-1] + (out_f,), Device.CUDA, x.dtype)
         return out if bias is None else out + bias
@@ -494,8 +503,13 @@ class Linear(OP):
                 _premasked[id(gx)] = id(self.relu_src)
                 weakref.finalize(gx, _premasked.pop, id(gx), None)
         elif self.req_grad[0]:
-            gx = Buffer(dispatcher.dispatch(op=BinaryOps.MATMUL, device=Device.CUDA, x=g2, y=self.w),
-                        self.x.shape, Device.CUDA, self.x.dtype)
+            if LAZY_LINEAR and rows * in_f >= (1 << 20) and self.w._pending is None:
+                # deferred ("lin_dx"): the gradient accumulation `grad + g @ W` of the autograd driver (dlgrad/tensor.py:805)
+                # then rides on this GEMM's epilogue
+                gx = Buffer._deferred(("lin_dx", g2, self.w), self.x.shape, self.x.dtype)
+            else:
+                gx = Buffer(dispatcher.dispatch(op=BinaryOps.MATMUL, device=Device.CUDA, x=g2, y=self.w),
+                            self.x.shape, Device.CUDA, self.x.dtype)
         if self.req_grad[1]:
             gw = Buffer(dispatcher.dispatch(op=BinaryOps.MATMUL, device=Device.CUDA, x=g2,
                                             y=self.x.reshape((rows, in_f)), trans_x=True),

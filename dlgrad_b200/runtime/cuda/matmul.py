@@ -138,6 +138,40 @@ def _relu_masked_matmul(x: Buffer, y: Buffer, tx: bool, ty: bool, mask: Buffer):
     return out
 
 
+def radd_matmul(x: Buffer, y: Buffer, tx: bool, ty: bool, r: Buffer, a_relu: bool = False):
+    """r + x @ y with the addition in the GEMM's epilogue (codegen matmul_tc_ts, `radd`): the residual connection and the
+    gradient accumulation that follow a Linear.  `a_relu`: x is relu(stored x) (a deferred relu feeding the Linear).  None
+    when the shape does not run on the tensor-core kernel as one launch (the caller then adds separately)."""
+    if x._pending is not None and x._pending[0] == "relu" and x._pending[1]._pending is None \
+            and x._pending[1].metadata.shape == x.metadata.shape and not a_relu:
+        return radd_matmul(x._pending[1], y, tx, ty, r, a_relu=True)      # relu(h) @ W + r: the clamp rides in the A splitter
+    if x._pending is not None or y._pending is not None or r._pending is not None or r.scalar is not None:
+        return None
+    aligned = x.aligned and y.aligned and r.aligned
+    key = (x.metadata.shape, y.metadata.shape, tx, ty, aligned, "radd", a_relu)
+    plan = _plans.get(key)
+    if plan is None and key not in _plans:
+        M, N, K, batch, a_bs, b_bs, _ = _geometry(x.metadata.shape, y.metadata.shape, tx, ty)
+        plan = None
+        if (not FORCE_SIMT and aligned and N % 4 == 0 and prod_(r.metadata.shape) == prod_(batch) * M * N
+                and _split_k(M, N, K, batch, tx, ty) == 1):
+            from dlgrad_b200.runtime.cuda import matmul_tc
+            bn = int(os.environ.get("DLGRAD_RMASK_BN", "128"))      # two accumulators: the longer epilogue overlaps the next tile
+            plan = matmul_tc.try_build(M, N, K, batch, a_bs, b_bs, tx, ty, aligned, radd=True, a_relu=a_relu,
+                                       bn=bn if N >= bn else None)
+        _plans[key] = plan
+    if plan is None:
+        return None
+    args = (_ops._dev_ptr(x), _ops._dev_ptr(y), _ops._dev_ptr(r))
+    timer = _profile.matmul_timer
+    if timer is None:
+        return plan(*args)
+    t0 = timer.start()
+    out = plan(*args)
+    timer.stop(t0, plan.flops, plan.tag)
+    return out
+
+
 def _relu_operand_matmul(x: Buffer, y: Buffer, tx: bool, ty: bool):
     """An operand is a deferred relu (Buffer pending kind "relu"): the tensor-core kernel applies max(., 0) while the
     operand passes through its splitter, so relu(h) is never written.  None when the shape does not run there as one

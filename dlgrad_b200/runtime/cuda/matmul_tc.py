@@ -61,7 +61,7 @@ def qualifies(M, N, K, batch, a_bs, b_bs, tx, ty, aligned, force: bool = False) 
 def try_build(M, N, K, batch, a_bs, b_bs, tx, ty, aligned, passes: int | None = None, bn: int | None = None,
               stages: int | None = None, hi_inplace: bool = False, force: bool = False, kernel: str | None = None,
               split_warps: int | None = None, bias: bool = False, streamk: bool | None = None, ksparse: str | None = None,
-              a_relu: bool = False, b_relu: bool = False, splitk: int = 0, relu_mask: bool = False):
+              a_relu: bool = False, b_relu: bool = False, splitk: int = 0, relu_mask: bool = False, radd: bool = False):
     """`bias=True` builds the variant whose epilogue adds a length-N row (only the TS kernel has one; None otherwise)."""
     q = qualifies(M, N, K, batch, a_bs, b_bs, tx, ty, aligned, force)
     if q is None:
@@ -76,14 +76,15 @@ def try_build(M, N, K, batch, a_bs, b_bs, tx, ty, aligned, passes: int | None = 
         # A-in-TMEM beats both shared-memory-operand kernels on every shape of scripts/tc_probe.py perf/perf4
         # (e.g. 8192x768x768: 210 vs 156 TFLOP/s, 4096^3: 244 vs 235, TN 768x3072x8192: 240 vs 200)
         which = "v4" if passes == 3 else "v2"
-    if (bias or ksparse or a_relu or b_relu or splitk or relu_mask) and not (which == "v4" and passes == 3):
+    if (bias or ksparse or a_relu or b_relu or splitk or relu_mask or radd) and not (which == "v4" and passes == 3):
         return None
     if which == "v3" and passes == 3 and M > 128 and (bn or 256) % 64 == 0:
         k = tc.matmul_tc_pair(M, N, K, nb, a_mn, b_mn, a_bc, b_bc, bn, stages)
         cluster, b_rows = 2, k.bn // 2
     elif which == "v4" and passes == 3:
-        k = tc.matmul_tc_ts(M, N, K, nb, a_mn, b_mn, a_bc, b_bc, bn, stages, None, bias, None, False, ksparse, a_relu, b_relu, splitk, relu_mask)
-        sk = (tc.wants_streamk(M, N, K, nb, k.bn) if streamk is None else streamk) and not (ksparse or a_relu or b_relu or splitk or relu_mask)
+        k = tc.matmul_tc_ts(M, N, K, nb, a_mn, b_mn, a_bc, b_bc, bn, stages, None, bias, None, False, ksparse, a_relu, b_relu, splitk, relu_mask,
+                            0, radd)
+        sk = (tc.wants_streamk(M, N, K, nb, k.bn) if streamk is None else streamk) and not (ksparse or a_relu or b_relu or splitk or relu_mask or radd)
         if sk:
             k = tc.matmul_tc_ts(M, N, K, nb, a_mn, b_mn, a_bc, b_bc, k.bn, stages, None, bias, None, True)
             ntiles = -(-M // 128) * -(-N // k.bn) * nb
@@ -115,7 +116,7 @@ def try_build(M, N, K, batch, a_bs, b_bs, tx, ty, aligned, passes: int | None = 
                 raise RuntimeError("tensor-core matmul launch failed: " + shim.last_error())
             lib.dlg_free(scratch)               # stream-ordered: whoever gets this block next runs after the kernel
             return final
-    elif bias or flags is not None or ksparse or relu_mask:
+    elif bias or flags is not None or ksparse or relu_mask or radd:
         fl = NULL if flags is None else flags
 
         def run(a, b, aux=NULL, aux1=None):
@@ -130,4 +131,4 @@ def try_build(M, N, K, batch, a_bs, b_bs, tx, ty, aligned, passes: int | None = 
                 raise RuntimeError("tensor-core matmul launch failed: " + shim.last_error())
             return shim.own(out, nbytes)
     from dlgrad_b200.runtime.cuda.matmul import MatmulPlan
-    return MatmulPlan(run, 2.0 * nb * M * N * K, (f"tc{passes}" + (f"_sp{ksparse}" if ksparse else ""), M, N, K, nb))
+    return MatmulPlan(run, 2.0 * nb * M * N * K, (f"tc{passes}" + (f"_sp{ksparse}" if ksparse else "") + ("_radd" if radd else ""), M, N, K, nb))

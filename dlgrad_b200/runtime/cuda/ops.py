@@ -189,6 +189,18 @@ def materialize(buf: Buffer) -> None:
     if pend[0] == "relu":
         buf.ptr = pend[1].relu().ptr
         return
+    if pend[0] == "lin":
+        buf.ptr = matmul(pend[1], pend[2], trans_y=True)
+        return
+    if pend[0] == "lin_dx":
+        buf.ptr = matmul(pend[1], pend[2])
+        return
+    if pend[0] == "rms_dx":
+        buf.ptr = ewise3("rms_dx", "(v0 * v1) * v2", buf.metadata.shape, [pend[1], pend[2], pend[3]])
+        return
+    if pend[0] == "diff":
+        buf.ptr = sub(pend[1], pend[2])
+        return
     if pend[0] == "hsplit":
         buf.ptr = permute(pend[1], (0, 2, 1, 3))
         return
@@ -957,3 +969,24 @@ def show(x: Buffer) -> None:
 
 def launch_count() -> int:
     return int(lib.dlg_launch_count())
+
+
+def fused_add(r: Buffer, d: Buffer):
+    """r + d where d is a deferred producer that can absorb the addition: a Linear output ("lin": x @ W^T), a Linear input
+    gradient ("lin_dx": g @ W) — the GEMM adds r in its epilogue — or an RMSNorm input gradient ("rms_dx": one elementwise
+    kernel).  Returns the owned pointer of the sum, or None when the pattern does not apply."""
+    pend = d._pending
+    if pend is None or r.scalar is not None or r.metadata.shape != d.metadata.shape or r.metadata.device is not CUDA:
+        return None
+    if r._pending is not None:
+        materialize(r)
+    if pend[0] in ("lin", "lin_dx"):
+        from dlgrad_b200.runtime.cuda import matmul as _mm
+        x2, w = pend[1], pend[2]
+        return _mm.radd_matmul(x2, w, False, pend[0] == "lin", r.reshape((x2.metadata.shape[0], -1)))
+    if pend[0] == "rms_dx":
+        g, w, t = pend[1], pend[2], pend[3]
+        if g._pending is not None:
+            materialize(g)
+        return ewise3("rms_dx_add", "v3 + (v0 * v1) * v2", d.metadata.shape, [g, w, t, r])
+    return None
