@@ -21,14 +21,15 @@ Every product is 3xTF32 (a_lo b_hi + a_hi b_lo + a_hi b_hi, fp32 accumulate), so
 (north star: matmul <= 1e-4, softmax <= 1e-5 relative).  kind::tf32 truncates its inputs, so a staged fp32 tile IS its
 own `hi`; only `lo` tiles are computed (splitter warps for the streamed operands, the row threads for A and P).
 
-Warp roles (480 threads, one persistent CTA per SM):
-    warp 0       TMA producer: A tile(s) of the next item, then per step the two streamed tiles of the ring stage
+Warp roles (512 threads, one persistent CTA per SM):
+    warp 0       TMA producer: A tile(s) of the next item, L2 prefetch of coming tiles, and per step the first streamed tile (ring 1)
     warp 1, 14   MMA issuers (one elected lane each): warp 1 the score tiles, warp 14 the second product of the step; each
                  owns its accumulators, so every accumulation order is one thread's program order (deterministic)
     warps 2-9    row warps: thread = row of the 128-row score tile = TMEM lane; two warps per lane quarter, each owns 32
                  of the 64 score columns of a step (the row work — TMEM reads, exponentials, hi | lo splits, TMEM writes —
                  paces these kernels, not the tensor pipe: with four row warps the forward ran at 50 % pipe utilisation)
-    warps 10-13  splitter: lo = x - trunc_tf32(x) for the staged tiles of a stage (twin buffers, same swizzled layout)
+    warps 10-13  splitter: lo = x - trunc_tf32(x) into the twin buffer of a stage (same swizzled layout); 10-11 ring 1, 12-13 ring 2
+    warp 15      second TMA producer (ring 2)
 """
 from __future__ import annotations
 
@@ -87,20 +88,23 @@ def _sub(src: str, **kw) -> str:
 
 @cache
 def flash_attn(mode: str, Tq: int, Tk: int, D: int, H: int, NB: int, scale: float, fill: float,
-               out_strides: tuple = (0, 0, 0), tau: float = 8.0, delta_split: bool = False) -> TcKernel:
+               out_strides: tuple = (0, 0, 0), tau: float = 8.0, delta_split: bool = False, lazy_zero: bool = False) -> TcKernel:
     """mode "fwd" | "dv" | "ds" (module docstring).  Tq, Tk multiples of 128, D in (32, 64), NB = batch * H score planes,
     H heads (a plane z is head z % H of sequence z / H: every operand is addressed through a rank-4 tensor map
     (D, T, H, B), so both (B, h, T, D) and the projection's own (B, T, h, D) layout work without a permute kernel).
     `out_strides` = element strides (row, head, batch) of the direct-store output (O for fwd, dV for dv).
     `delta_split` (ds): delta = rowsum(dO * O) is indexed (batch, row, head) — dO and O stored as (B, T, h, D).
+    `lazy_zero` (ds): tiles of dS that the mask kills entirely are left UNWRITTEN when every query row has a live entry —
+    the tile-skipping GEMMs that consume dS never read them in that case (same test, same table), and they are 44 % of
+    the 403 MB the kernel would otherwise write per layer at C5.  Only for a dS that nobody else can read.
     `tau`: the running maximum of the online softmax is only replaced when it grows by more than `tau` (base-2 units):
     any m gives the same P / l in exact arithmetic, and 2^tau bounds the un-normalised P, so O in tensor memory is
     rescaled almost never instead of almost always (tau = 0 forces the rescale path; the tests use it).
 
     Kernel parameters
-      fwd: tmQ, tmK, tmV, O, lse (one float per row: log2 of the row's sum of 2^(s c), i.e. P = 2^(s c - lse); NaN for a
+      fwd: tmQ, tmK, tmV, tmO, O, lse (one float per row: log2 of the row's sum of 2^(s c), i.e. P = 2^(s c - lse); NaN for a
            row without a live entry), bits
-      dv : tmK, tmQ, tmDO, dV, lse, bits
+      dv : tmK, tmQ, tmDO, tmDV, dV, lse, bits
       ds : tmQ, tmDO, tmK, tmV, tmDS, dS, lse, delta, bits            (bits: cuda_kernel.mask_bits of the (Tq, Tk) mask)"""
     assert mode in ("fwd", "dv", "ds") and Tq % 128 == 0 and Tk % 128 == 0 and D in (32, 64) and scale > 0
     import os
@@ -122,7 +126,8 @@ def flash_attn(mode: str, Tq: int, Tk: int, D: int, H: int, NB: int, scale: floa
     skip = math.isinf(fill) and fill < 0
     tile_b = kbq * 8192                                      # one streamed tile: 64 rows x D fp32
     raw_b = 2 * tile_b
-    per_stage = 2 * raw_b                                    # B1 raw | B2 raw | B1 lo | B2 lo
+    per_stage = 2 * raw_b                                    # per step: ring 1 stage (B1 raw | B1 lo) + ring 2 stage (B2 raw | B2 lo)
+    rstage = 2 * tile_b                                      # one stage of one ring
     a_tiles = 2 if mode == "ds" else 1
     a_bytes = a_tiles * kbq * 16384
     epi_bytes = 8 * 4096 if mode == "ds" else 0              # one 32x32 staging box per row warp for the dS store
@@ -130,6 +135,7 @@ def flash_attn(mode: str, Tq: int, Tk: int, D: int, H: int, NB: int, scale: floa
     budget = 227 * 1024 - 1024 - tail_bytes - a_bytes - epi_bytes
     stages = max(2, min(3, budget // per_stage))
     smem = a_bytes + stages * per_stage + epi_bytes + 1024 + tail_bytes
+    ring2_off = stages * rstage
     if mode == "ds":
         S0, DP0, A0, A1 = 0, 128, 256, 256 + 2 * D
         PHI = PLO = OACC = 0
@@ -164,18 +170,18 @@ def flash_attn(mode: str, Tq: int, Tk: int, D: int, H: int, NB: int, scale: floa
                   "const float* __restrict__ lse, const float* __restrict__ delta, const unsigned* __restrict__ mask")
     elif mode == "fwd":
         params = ("const __grid_constant__ TMap tmA, const __grid_constant__ TMap tmB1, const __grid_constant__ TMap tmB2, "
-                  "float* __restrict__ out, float* __restrict__ lse, const unsigned* __restrict__ mask")
+                  "const __grid_constant__ TMap tmO, float* __restrict__ out, float* __restrict__ lse, const unsigned* __restrict__ mask")
     else:
         params = ("const __grid_constant__ TMap tmA, const __grid_constant__ TMap tmB1, const __grid_constant__ TMap tmB2, "
-                  "float* __restrict__ out, const float* __restrict__ lse, const unsigned* __restrict__ mask")
+                  "const __grid_constant__ TMap tmO, float* __restrict__ out, const float* __restrict__ lse, const unsigned* __restrict__ mask")
 
     # ------------------------------------------------------------------ producer: streamed tiles of one step
     if mode == "ds":       # K block and V block, both K-major (64 rows x D)
         b2_loads = "\n                        ".join(
-            f"tma_load_4d(st + {tile_b + kk * 8192}u, &tmB2, fb, {kk * 32}, (int)r0, (int)hh, (int)bb);" for kk in range(kbq))
+            f"tma_load_4d(st + {kk * 8192}u, &tmB2, fb, {kk * 32}, (int)r0, (int)hh, (int)bb);" for kk in range(kbq))
     else:                  # second tile MN-major: boxes of {32 columns, 32 rows}, k-block major
         b2_loads = "\n                        ".join(
-            f"tma_load_4d(st + {tile_b + (kb2 * kbq + c) * 4096}u, &tmB2, fb, {c * 32}, (int)(r0 + {kb2 * 32}u), (int)hh, (int)bb);"
+            f"tma_load_4d(st + {(kb2 * kbq + c) * 4096}u, &tmB2, fb, {c * 32}, (int)(r0 + {kb2 * 32}u), (int)hh, (int)bb);"
             for kb2 in range(2) for c in range(kbq))
     b1_loads = "\n                        ".join(
         f"tma_load_4d(st + {kk * 8192}u, &tmB1, fb, {kk * 32}, (int)r0, (int)hh, (int)bb);" for kk in range(kbq))
@@ -194,7 +200,7 @@ def flash_attn(mode: str, Tq: int, Tk: int, D: int, H: int, NB: int, scale: floa
     pf_loads = "\n                ".join(pf)
 
     # ------------------------------------------------------------------ MMA bodies
-    lo_off = raw_b // 16
+    lo_off = tile_b // 16                                   # lo twin follows the raw tile inside a ring stage
 
     def s_mma(acc_col: str, a_col: int, b_off16: int) -> str:
         """acc[128 x 64] = A (TMEM at a_col, hi | lo per 32-wide k block) x B1/B2 tile (K-major) of stage `sdesc`."""
@@ -224,18 +230,22 @@ def flash_attn(mode: str, Tq: int, Tk: int, D: int, H: int, NB: int, scale: floa
                         }}"""
 
     src = _HELPERS + _HELPERS_TS + _EXTRA + _sub(r"""
-extern "C" __global__ void __launch_bounds__(480, 1)
+extern "C" __global__ void __launch_bounds__(512, 1)
 $KNAME$($PARAMS$)
 {
     extern __shared__ unsigned char smem_raw[];
     const unsigned smem = (smem_u32(smem_raw) + 1023u) & ~1023u;        // swizzle atoms need 1024-byte alignment
     unsigned char* smem_gen = smem_raw + (smem - smem_u32(smem_raw));
-    const unsigned ring = smem + $A_BYTES$u;                            // stages: B1 raw | B2 raw | B1 lo | B2 lo
+    const unsigned ring = smem + $A_BYTES$u;                            // ring 1: stages of (B1 raw | B1 lo); ring 2 behind it: (B2 raw | B2 lo)
     const unsigned epi = ring + $RING_BYTES$u;
     const unsigned bars = epi + $EPI_BYTES$u;
+    // two rings, each with its own full / empty / split barriers: the first streamed tile of a step (K for fwd) is released
+    // when the score MMAs have read it, the second (V) only when the second product has — with ONE ring both waited for the
+    // later of the two, and the three 64 KiB stages could not cover TMA + split + MMA + softmax + MMA (~6000 clk per stage)
     const unsigned kfull = bars, kempty = bars + $STAGES$u * 8u, ksplit = bars + $STAGES$u * 16u;
-    const unsigned sfull = bars + $STAGES$u * 24u, sempty = sfull + 16u, pready = sempty + 16u, pvdone = pready + 8u;
-    const unsigned qfull = pvdone + 8u, qsplit = qfull + 8u, qfree = qsplit + 8u;
+    const unsigned vfull = bars + $STAGES$u * 24u, vempty = bars + $STAGES$u * 32u, vsplit = bars + $STAGES$u * 40u;
+    const unsigned sfull = bars + $STAGES$u * 48u, sempty = sfull + 16u, pready = sempty + 16u, pvdone = pready + 8u;
+    const unsigned qfull = pvdone + 8u, qsplit = qfull + 8u, qfree = qsplit + 8u, ofree = qfree + 8u;
     float* xch = reinterpret_cast<float*>(smem_gen + (bars - smem) + 256u);      // [8 row warps][32]
     __shared__ unsigned tmem_slot;
     __shared__ unsigned live_tab[32];
@@ -265,8 +275,11 @@ $KNAME$($PARAMS$)
     if (threadIdx.x == 0) {
         for (unsigned s = 0; s < $STAGES$u; ++s) {
             mbar_init(kfull + s * 8u, 1u);
-            mbar_init(kempty + s * 8u, $NISS$u);
-            mbar_init(ksplit + s * 8u, 4u);
+            mbar_init(kempty + s * 8u, 1u);
+            mbar_init(ksplit + s * 8u, 2u);
+            mbar_init(vfull + s * 8u, 1u);
+            mbar_init(vempty + s * 8u, 1u);
+            mbar_init(vsplit + s * 8u, 2u);
         }
         for (unsigned b = 0; b < 2u; ++b) {
             mbar_init(sfull + b * 8u, $NISS$u);
@@ -277,6 +290,7 @@ $KNAME$($PARAMS$)
         mbar_init(qfull, 1u);
         mbar_init(qsplit, $NSPLIT$u);
         mbar_init(qfree, $NISS$u);
+        mbar_init(ofree, $NSTORE$u);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -329,21 +343,20 @@ $KNAME$($PARAMS$)
                 if (!((lm >> t) & 1u)) continue;
                 pf_next();
                 for (unsigned half = 0; half < 2u; ++half, ++it) {
-                    if (a_pending && mbar_try(qsplit, n & 1u)) { load_a(zn, an); a_pending = false; }
+                    if (a_pending && mbar_try(qsplit, n & 1u) && $OFREE_TRY$) { load_a(zn, an); a_pending = false; }
                     const unsigned s = it % $STAGES$u, ph = (it / $STAGES$u) & 1u;
                     mbar_wait(kempty + s * 8u, ph ^ 1u);
                     $TR16$
-                    const unsigned st = ring + s * $PER_STAGE$u, fb = kfull + s * 8u, r0 = t * 128u + half * 64u;
+                    const unsigned st = ring + s * $RSTAGE$u, fb = kfull + s * 8u, r0 = t * 128u + half * 64u;
                     if (elect_one()) {
-                        mbar_expect_tx(fb, $RAW_B$u);
+                        mbar_expect_tx(fb, $TILE_B$u);
                         $B1_LOADS$
-                        $B2_LOADS$
                     }
                     __syncwarp();
                     $TR17$
                 }
             }
-            if (a_pending) { mbar_wait(qsplit, n & 1u); load_a(zn, an); }
+            if (a_pending) { mbar_wait(qsplit, n & 1u); $OFREE_WAIT$ load_a(zn, an); }
         }
     } else if (warp == 1) {
         // ===== first MMA issuer: the score tiles S = A x B1^T (Q K^T; K Q^T for dv) into S[b] =====
@@ -374,7 +387,7 @@ $KNAME$($PARAMS$)
                 const unsigned long long sdesc = sdesc0 + (unsigned long long)(s * $PER_STAGE16$u);
                 if (elect_one()) {
                     $S_MMA$
-                    $DS_STAGE_FREE$
+                    umma_commit(kempty + s * 8u);                      // the first streamed tile of this step may be refilled
                     umma_commit(sfull + b * 8u);
                     if (i + 1u == nsteps) umma_commit(qfree);          // the last read of A by this item
                 }
@@ -458,19 +471,22 @@ $KNAME$($PARAMS$)
         }
         $ROW_EXIT$
     } else if (warp < 14u) {
-        // ===== splitter warps: lo = x - trunc_tf32(x) for the two staged tiles of a step =====
-        const unsigned ctid = threadIdx.x - 320u;
+        // ===== splitter warps: lo = x - trunc_tf32(x) into the twin buffer of the stage; warps 10-11 serve ring 1, 12-13 ring 2 =====
+        const unsigned r2 = (warp >= 12u) ? 1u : 0u;
+        const unsigned ctid = threadIdx.x - (r2 ? 384u : 320u);
+        const unsigned fullb = r2 ? vfull : kfull, splitb = r2 ? vsplit : ksplit;
+        unsigned char* rbase = smem_gen + $A_BYTES$u + (r2 ? $RING2$u : 0u);
         unsigned it = 0, n = 0, z, at;
         for (; item_at(n, z, at); ++n) {
             const unsigned nsteps = 2u * __popc(live_tiles(at));
             for (unsigned i2 = 0; i2 < nsteps; ++i2, ++it) {
                 const unsigned s = it % $STAGES$u, ph = (it / $STAGES$u) & 1u;
-                mbar_wait(kfull + s * 8u, ph);
+                mbar_wait(fullb + s * 8u, ph);
                 $TR18$
-                const float4* bsrc = reinterpret_cast<const float4*>(smem_gen + $A_BYTES$u + s * $PER_STAGE$u);
-                float4* bdst = reinterpret_cast<float4*>(smem_gen + $A_BYTES$u + s * $PER_STAGE$u + $RAW_B$u);
+                const float4* bsrc = reinterpret_cast<const float4*>(rbase + s * $RSTAGE$u);
+                float4* bdst = reinterpret_cast<float4*>(rbase + s * $RSTAGE$u + $TILE_B$u);
                 #pragma unroll 8
-                for (unsigned i = ctid; i < $RAW_V4$u; i += 128u) {
+                for (unsigned i = ctid; i < $TILE_V4$u; i += 64u) {
                     const float4 v4 = bsrc[i];
                     float4 l4;
                     l4.x = v4.x - __uint_as_float(__float_as_uint(v4.x) & 0xffffe000u);
@@ -481,8 +497,28 @@ $KNAME$($PARAMS$)
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
-                if (lane == 0) mbar_arrive(ksplit + s * 8u);
+                if (lane == 0) mbar_arrive(splitb + s * 8u);
                 $TR19$
+            }
+        }
+    } else if (warp == 15u) {
+        // ===== second TMA producer: ring 2 (V for fwd / ds, dO for dv) =====
+        unsigned it = 0, n = 0, z, at;
+        for (; item_at(n, z, at); ++n) {
+            const unsigned hh = z % $H$u, bb = z / $H$u;
+            const unsigned lm = live_tiles(at);
+            for (unsigned t = 0; t < $NS$u; ++t) {
+                if (!((lm >> t) & 1u)) continue;
+                for (unsigned half = 0; half < 2u; ++half, ++it) {
+                    const unsigned s = it % $STAGES$u, ph = (it / $STAGES$u) & 1u;
+                    mbar_wait(vempty + s * 8u, ph ^ 1u);
+                    const unsigned st = ring + $RING2$u + s * $RSTAGE$u, fb = vfull + s * 8u, r0 = t * 128u + half * 64u;
+                    if (elect_one()) {
+                        mbar_expect_tx(fb, $TILE_B$u);
+                        $B2_LOADS$
+                    }
+                    __syncwarp();
+                }
             }
         }
     }
@@ -498,11 +534,12 @@ $KNAME$($PARAMS$)
         TR0=TR(0, "g"), TR1=TR(1, "g"), TR2=TR(2, "g"), TR5=TR(5, "g", "threadIdx.x == 64u"), TR8=TR(8, "g", "threadIdx.x == 64u"),
         TRACE_DECL="", TRACE_DUMP="", TR16=TR(16, "it"), TR17=TR(17, "it"), TR18=TR(18, "it", "threadIdx.x == 320u"), TR19=TR(19, "it", "threadIdx.x == 320u"), TR9=TR(9, "nn", "threadIdx.x == 64u"), TR10=TR(10, "nn", "threadIdx.x == 64u"), TR11=TR(11, "nn", "threadIdx.x == 64u"),
         TR12=TR(12, "nn", "threadIdx.x == 64u"), TR13=TR(13, "n"), TR14=TR(14, "n"), TR15=TR(15, "n", "threadIdx.x == 64u"),
-        NSPLIT=8 if a_tiles * kbq >= 2 else 4, NISS=2 if mode == "ds" else 1, PF_LOADS=pf_loads, PFD=int(os.environ.get("DLGRAD_FLASH_PF", "2")), LIVE=live, LIVE_FILL=live_fill.replace("threadIdx.x", "(threadIdx.x - 64u)"), NA=nA, GRID=grid, ITEMS=items, NB=NB, TILE_OF=tile_of, H=H, A_LOADS=a_loads, NS=nS, PER_STAGE=per_stage,
-        RAW_B=raw_b, B1_LOADS=b1_loads, B2_LOADS=b2_loads, TILE_B=tile_b, PER_STAGE16=per_stage // 16,
+        OFREE_TRY="true" if mode == "ds" else "(n == 0u || mbar_try(ofree, (n - 1u) & 1u))",
+        OFREE_WAIT="" if mode == "ds" else "if (n != 0u) mbar_wait(ofree, (n - 1u) & 1u);",
+        NSPLIT=8 if a_tiles * kbq >= 2 else 4, NSTORE=8 if D == 64 else 4, NISS=2 if mode == "ds" else 1, PF_LOADS=pf_loads, PFD=int(os.environ.get("DLGRAD_FLASH_PF", "2")), LIVE=live, LIVE_FILL=live_fill.replace("threadIdx.x", "(threadIdx.x - 64u)"), NA=nA, GRID=grid, ITEMS=items, NB=NB, TILE_OF=tile_of, H=H, A_LOADS=a_loads, NS=nS, PER_STAGE=per_stage,
+        RAW_B=raw_b, B1_LOADS=b1_loads, B2_LOADS=b2_loads, TILE_B=tile_b, PER_STAGE16=rstage // 16,
         S_MMA=s_mma(f"tmem_base + {S0}u + b * 64u", A0, 0),
-        DS_STAGE_FREE="umma_commit(kempty + s * 8u);" if mode == "ds" else "",
-        ISSUER2=_sub(r"""const unsigned long long sdesc0 = make_desc(ring, 1u, 64u, 2u);
+        ISSUER2=_sub(r"""const unsigned long long sdesc0 = make_desc(ring + $RING2$u, 1u, 64u, 2u);      // ring 2: the V block, K-major
         for (; item_at(n, z, at); ++n) {
             const unsigned nsteps = 2u * __popc(live_tiles(at));
             mbar_wait(qsplit, n & 1u);                            // dO (hi | lo) of this item is in tensor memory
@@ -514,25 +551,25 @@ $KNAME$($PARAMS$)
             }
             for (unsigned i = 0; i < nsteps; ++i, ++it, ++g) {
                 const unsigned b = g & 1u, s = it % $STAGES$u, ph = (it / $STAGES$u) & 1u;
-                mbar_wait(ksplit + s * 8u, ph);
+                mbar_wait(vsplit + s * 8u, ph);
                 mbar_wait(sempty + b * 8u, ((g >> 1) & 1u) ^ 1u);
                 TC_FENCE_AFTER();
                 const unsigned long long sdesc = sdesc0 + (unsigned long long)(s * $PER_STAGE16$u);
                 if (elect_one()) {
                     $DP_MMA$
-                    umma_commit(kempty + s * 8u);
+                    umma_commit(vempty + s * 8u);
                     umma_commit(sfull + b * 8u);
                     if (i + 1u == nsteps) umma_commit(qfree);
                 }
                 __syncwarp();
             }
-        }""", STAGES=stages, PER_STAGE16=per_stage // 16, DP_MMA=s_mma(f"tmem_base + {DP0}u + b * 64u", A1, tile_b // 16))
-        if mode == "ds" else _sub(r"""const unsigned long long odesc0 = make_desc(ring + $TILE_B$u, 256u, 32u, 1u);    // MN-major tile: LBO 4096 B, SBO 512 B, 32-byte atoms
+        }""", STAGES=stages, PER_STAGE16=rstage // 16, RING2=ring2_off, DP_MMA=s_mma(f"tmem_base + {DP0}u + b * 64u", A1, 0))
+        if mode == "ds" else _sub(r"""const unsigned long long odesc0 = make_desc(ring + $RING2$u, 256u, 32u, 1u);    // ring 2, MN-major tile: LBO 4096 B, SBO 512 B, 32-byte atoms
         for (; item_at(n, z, at); ++n) {
             const unsigned nsteps = 2u * __popc(live_tiles(at));
             for (unsigned j = 0; j < nsteps; ++j, ++it, ++g) {
                 const unsigned s = it % $STAGES$u, ph = (it / $STAGES$u) & 1u;
-                mbar_wait(ksplit + s * 8u, ph);                    // the streamed tiles of this step are split
+                mbar_wait(vsplit + s * 8u, ph);                    // the second streamed tile of this step is split
                 mbar_wait(pready, g & 1u);                         // P (hi | lo) of this step is in tensor memory
                 $TR3$
                 TC_FENCE_AFTER();
@@ -540,22 +577,24 @@ $KNAME$($PARAMS$)
                 const unsigned acc = j;                            // the first step of an item overwrites the accumulator
                 if (elect_one()) {
                     $O_MMA$
-                    umma_commit(kempty + s * 8u);
+                    umma_commit(vempty + s * 8u);
                     umma_commit(pvdone);
                 }
                 __syncwarp();
                 $TR4$
             }
-        }""", STAGES=stages, PER_STAGE16=per_stage // 16, TILE_B=tile_b, O_MMA=o_mma, TR3=TR(3, "g"), TR4=TR(4, "g")),
+        }""", STAGES=stages, PER_STAGE16=rstage // 16, RING2=ring2_off, O_MMA=o_mma, TR3=TR(3, "g"), TR4=TR(4, "g")),
         A_KBLOCKS=a_tiles * kbq, A0=A0,
-        ROW_ITEM_BEGIN=_row_item_begin(mode, Tq, Tk, H, delta_split), PF_DECL=_pf(mode, Tq, Tk)[0], PF_NEXT=_pf(mode, Tq, Tk)[1], PF_TAKE=_pf(mode, Tq, Tk)[2],
+        ROW_ITEM_BEGIN=_row_item_begin(mode, Tq, Tk, H, delta_split, lazy_zero), PF_DECL=_pf(mode, Tq, Tk)[0], PF_NEXT=_pf(mode, Tq, Tk)[1], PF_TAKE=_pf(mode, Tq, Tk)[2],
         ROW_STEP=_row_step(mode, Tq, Tk, D, S0, DP0, PHI, PLO, OACC, sc2, fl2, _f32lit(float(np.float32(scale))), tau)
         .replace("TRACE6", TR(6, "g", "threadIdx.x == 64u")).replace("TRACE7", TR(7, "g", "threadIdx.x == 64u")),
-        ROW_ITEM_END=_row_item_end(mode, Tq, Tk, D, OACC, sT, sH, sB, nS),
-        ROW_EXIT='if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");' if mode == "ds" else "",
-        RAW_V4=raw_b // 16)
+        ROW_ITEM_END=_row_item_end(mode, Tq, Tk, D, OACC, sT, sH, sB, nS).replace("TRACE20", TR(20, "n", "threadIdx.x == 64u"))
+        .replace("TRACE21", TR(21, "n", "threadIdx.x == 64u")).replace("TRACE22", TR(22, "n", "threadIdx.x == 64u"))
+        .replace("TRACE23", TR(23, "n", "threadIdx.x == 64u")),
+        ROW_EXIT='if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");',
+        RSTAGE=rstage, RING2=ring2_off, TILE_V4=tile_b // 16)
     out_elems = {"fwd": NB * Tq * D, "dv": NB * Tk * D, "ds": NB * Tq * Tk}[mode]
-    return TcKernel(f"flash_{mode}", src, (grid, 1, 1), 480, smem, out_elems, 64, stages)
+    return TcKernel(f"flash_{mode}", src, (grid, 1, 1), 512, smem, out_elems, 64, stages)
 
 
 def _pf(mode: str, Tq: int, Tk: int) -> tuple:
@@ -575,7 +614,7 @@ def _pf(mode: str, Tq: int, Tk: int) -> tuple:
             "const unsigned bits = bits_n;")
 
 
-def _row_item_begin(mode: str, Tq: int, Tk: int, H: int = 1, delta_split: bool = False) -> str:
+def _row_item_begin(mode: str, Tq: int, Tk: int, H: int = 1, delta_split: bool = False, lazy_zero: bool = False) -> str:
     if mode == "fwd":
         return f"float m_run = {NEG_INF}, l_run = 0.f;      // l_run: this warp's 32 columns of every step only"
     if mode == "ds":
@@ -587,6 +626,7 @@ def _row_item_begin(mode: str, Tq: int, Tk: int, H: int = 1, delta_split: bool =
             // each warp of a pair clears its 64 of the 128 columns)
             for (unsigned t = 0; t < {Tk // 128}u; ++t) {{
                 if ((lm >> t) & 1u) continue;
+                {"if (__ldg(mask + " + str(Tq * Tk // 32 + (Tq // 128) * (Tk // 128) + Tq) + "u) == " + str(Tq) + "u) break;      // every query row is live: the consumers skip dead tiles too" if lazy_zero else ""}
                 float* dst = out + ((size_t)z * {Tq}u + at * 128u + sq * 32u + (lane >> 3)) * {Tk}u + t * 128u + wh * 64u + (lane & 7u) * 4u;
                 const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
                 #pragma unroll
@@ -732,11 +772,28 @@ def _row_item_end(mode, Tq, Tk, D, OACC, sT, sH, sB, nS) -> str:
     # the accumulator's D columns: 32 per warp of the pair at D = 64; at D = 32 the first warp of the pair takes them all
     mine = "true" if D == 64 else "wh == 0u"
     col0 = "wh * 32u" if D == 64 else "0u"
-    store = f"""float* orow = out + (size_t)bb * {sB}ull + (size_t)hh * {sH}ull + (size_t)row * {sT}ull + {col0};
-                    #pragma unroll
-                    for (unsigned e = 0; e < 32u; e += 4u)
-                        *reinterpret_cast<float4*>(orow + e) = make_float4(__uint_as_float(o[e]) * fac, __uint_as_float(o[e + 1]) * fac,
-                                                                           __uint_as_float(o[e + 2]) * fac, __uint_as_float(o[e + 3]) * fac);"""
+    # The tile leaves through shared memory and ONE TMA store per warp (a 32 x 32 box): a thread owns a row, so direct
+    # stores put 32 rows x 16 bytes in every instruction — measured 1600 clk of store back-pressure per item plus another
+    # 2000 before the next instruction got out, a quarter of the kernel.  The staging box is the warp's own 4 KiB of the A
+    # tile's shared-memory region (exactly the rows / k-block this warp split into tensor memory a moment ago); the
+    # producer does not refill that region before `ofree` says the stores have read it.
+    stage_writes = "\n                    ".join(
+        f"*reinterpret_cast<float4*>(obox_gen + lane * 128u + (({jj}u ^ (lane & 7u)) << 4)) = "
+        f"make_float4(__uint_as_float(o[{4 * jj}]) * fac, __uint_as_float(o[{4 * jj + 1}]) * fac, "
+        f"__uint_as_float(o[{4 * jj + 2}]) * fac, __uint_as_float(o[{4 * jj + 3}]) * fac);" for jj in range(8))
+    kk_of = "wh" if D == 64 else "0u"
+    store = f"""const unsigned obox = smem + {kk_of} * 16384u + sq * 4096u;
+                    unsigned char* obox_gen = smem_gen + {kk_of} * 16384u + sq * 4096u;
+                    {stage_writes}
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) {{
+                        tma_store_4d(&tmO, obox, (int)({col0}), (int)(at * 128u + sq * 32u), (int)hh, (int)bb);
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");      // the box has been read: it may be refilled
+                        mbar_arrive(ofree);
+                    }}
+                    __syncwarp();"""
     if mode == "fwd":
         return f"""{{
                 // the row sum: each warp of a pair holds the sum over its 32 columns of every step (same maximum in both)
@@ -744,6 +801,7 @@ def _row_item_end(mode, Tq, Tk, D, OACC, sT, sH, sB, nS) -> str:
                 asm volatile("bar.sync %0, 64;" :: "r"(1u + sq) : "memory");
                 const float l_tot = l_run + xch[((warp - 2u) ^ 4u) * 32u + lane];
                 asm volatile("bar.sync %0, 64;" :: "r"(1u + sq) : "memory");
+                TRACE20
                 unsigned o[32];
                 float fac = 1.f;
                 if (nsteps == 0u) {{
@@ -752,14 +810,17 @@ def _row_item_end(mode, Tq, Tk, D, OACC, sT, sH, sB, nS) -> str:
                     for (unsigned e = 0; e < 32u; ++e) o[e] = 0x7fc00000u;
                 }} else {{
                     mbar_wait(pvdone, (g - 1u) & 1u);
+                    TRACE21
                     TC_FENCE_AFTER();
                     if ({mine}) {{ TMEM_LD32(lane_base + {OACC}u + {col0}, o); TMEM_WAIT_LD(); }}
                     TC_FENCE_BEFORE();
                     fac = 1.f / l_tot;                                 // l = 0 (a fully masked row): 0 * inf = NaN
+                    TRACE22
                 }}
                 if ({mine}) {{
                     {store}
                 }}
+                TRACE23
                 if (wh == 0u) lse[(size_t)z * {TA}u + row] = (l_tot > 0.f) ? m_run + log2f(l_tot) : {QNAN};
             }}"""
     return f"""{{

@@ -204,6 +204,7 @@ def bwd_chain_matches(chain: list, out_shape: tuple) -> tuple | None:
 FLASH = os.environ.get("DLGRAD_FLASH_ATTN", "1") != "0"
 FLASH_TAU = float(os.environ.get("DLGRAD_FLASH_TAU", "8"))     # see cuda_flash.flash_attn: 0 forces the O-rescale path
 _flash: dict = {}            # id(P Buffer) -> record of the forward that consumed it
+_ds_private = [0]            # > 0 while ds_gemm materialises a dS that only the tile-skipping GEMMs will read (flash_ds: lazy_zero)
 _tc_plans: dict = {}
 
 
@@ -322,14 +323,14 @@ def flash_forward(P: Buffer, v: Buffer):
     if plan is None:
         kern = cf.flash_attn("fwd", Tq, Tk, D, H, nb, scale, fill, _strides(Tq, D, H, qs), FLASH_TAU)
         maps = [cf.tmap4(Tq, D, H, B, _strides(Tq, D, H, qs), 128), cf.tmap4(Tk, D, H, B, _strides(Tk, D, H, ks), 64),
-                cf.tmap4(Tk, D, H, B, _strides(Tk, D, H, vsplit), 32, mn=True)]
+                cf.tmap4(Tk, D, H, B, _strides(Tk, D, H, vsplit), 32, mn=True), cf.tmap4(Tq, D, H, B, _strides(Tq, D, H, qs), 32)]
         plan = _tc_plans[key] = _tc_plan(kern, maps, 3)
     bits = _mask_digest(mask, Tq, Tk)
     out = shim.alloc(nb * Tq * D * 4)
     stats = shim.alloc(nb * Tq * 8)
     pq, pk, pv = _ops._dev_ptr(qb), _ops._dev_ptr(kb), _ops._dev_ptr(vb)
     _timed(("attn_flash_fwd", Tq, Tk, D, nb), 4.0 * nb * Tq * Tk * D,
-           lambda: _tc_run(plan, [pq, pk, pv], [out, stats, bits], "flash attention forward"))
+           lambda: _tc_run(plan, [pq, pk, pv, out], [out, stats, bits], "flash attention forward"))
     rec = _FlashRecord()
     rec.q, rec.k, rec.v, rec.scale, rec.mask, rec.fill, rec.stats, rec.bits = q, k, v, scale, mask, fill, stats, bits
     rec.geom = (nb, H, B, Tq, Tk, D)
@@ -358,12 +359,12 @@ def flash_dv(rec, dO: Buffer) -> Buffer:
     if plan is None:
         kern = cf.flash_attn("dv", Tq, Tk, D, H, nb, rec.scale, rec.fill, _strides(Tk, D, H, vsplit))
         maps = [cf.tmap4(Tk, D, H, B, _strides(Tk, D, H, ks), 128), cf.tmap4(Tq, D, H, B, _strides(Tq, D, H, qs), 64),
-                cf.tmap4(Tq, D, H, B, _strides(Tq, D, H, dsplit), 32, mn=True)]
+                cf.tmap4(Tq, D, H, B, _strides(Tq, D, H, dsplit), 32, mn=True), cf.tmap4(Tk, D, H, B, _strides(Tk, D, H, vsplit), 32)]
         plan = _tc_plans[key] = _tc_plan(kern, maps, 3)
     out = shim.alloc(nb * Tk * D * 4)
     pk, pq, pd = _ops._dev_ptr(kb), _ops._dev_ptr(qb), _ops._dev_ptr(db)
     _timed(("attn_flash_dv", Tq, Tk, D, nb), 4.0 * nb * Tq * Tk * D,
-           lambda: _tc_run(plan, [pk, pq, pd], [out, rec.stats, rec.bits], "flash attention dV"))
+           lambda: _tc_run(plan, [pk, pq, pd, out], [out, rec.stats, rec.bits], "flash attention dV"))
     return _wrap(out, tuple(rec.v.metadata.shape), vsplit)
 
 
@@ -380,10 +381,11 @@ def flash_ds(rec, dO: Buffer, O: Buffer, dS_owner: Buffer):
         qs = ks = vsplit = dsplit = osplit = False
     if dsplit != osplit:                       # rowsum(dO * O) walks both operands in storage order: they must agree
         db, dsplit, ob, osplit = dO, False, O, False          # (reading .ptr below materialises the deferred one)
-    key = ("ds", nb, H, Tq, Tk, D, rec.scale, rec.fill, qs, ks, vsplit, dsplit)
+    lazy = bool(_ds_private[0]) and SPARSE and Tk <= 2048
+    key = ("ds", nb, H, Tq, Tk, D, rec.scale, rec.fill, qs, ks, vsplit, dsplit, lazy)
     ent = _tc_plans.get(key)
     if ent is None:
-        kern = cf.flash_attn("ds", Tq, Tk, D, H, nb, rec.scale, rec.fill, delta_split=dsplit)
+        kern = cf.flash_attn("ds", Tq, Tk, D, H, nb, rec.scale, rec.fill, delta_split=dsplit, lazy_zero=lazy)
         maps = [cf.tmap4(Tq, D, H, B, _strides(Tq, D, H, qs), 128), cf.tmap4(Tq, D, H, B, _strides(Tq, D, H, dsplit), 128),
                 cf.tmap4(Tk, D, H, B, _strides(Tk, D, H, ks), 64), cf.tmap4(Tk, D, H, B, _strides(Tk, D, H, vsplit), 64),
                 dict(rank=3, dims=(Tk, Tq, nb), strides=(Tk * 4, Tq * Tk * 4), box=(32, 32, 1), swizzle=3)]
@@ -413,7 +415,14 @@ def ds_gemm(dS: Buffer, other: Buffer, trans_x: bool):
     if not split or not _stored(other) or not other.aligned:
         return None
     if dS._pending is not None:
-        _ops.materialize(dS)                    # the flash dS kernel runs here and registers the live-tile table
+        # the flash dS kernel runs here and registers the live-tile table.  This dS is the interior gradient of the score
+        # matrix: it is consumed by dq = dS k and dk = dS^T q (both on the tile-skipping GEMM) and released, so the
+        # tiles the mask kills need not be written (cuda_flash.flash_attn, lazy_zero)
+        _ds_private[0] += 1
+        try:
+            _ops.materialize(dS)
+        finally:
+            _ds_private[0] -= 1
     info = tag_of(dS)
     if info is None:
         return None

@@ -22,7 +22,7 @@ if mode != "fwd":
 shim.synchronize()
 rec = attention._flash[id(att.data)]
 raw = transfer.download(rec.stats, 2 * B * H * T)[B * H * T:]
-tr = raw.view(np.int64)[:20 * 48].reshape(20, 48)
+tr = raw.view(np.int64)[:24 * 48].reshape(24, 48)
 t0 = tr[tr > 0].min()
 names = ["P:free", "P:issued", "X:full", "X:split", "S:split", "S:free", "S:issued", "O:Pready", "O:issued", "R:Sfull", "R:exp", "R:pvdone", "R:Pwritten"]
 kinds = [16, 17, 18, 19, 0, 1, 2, 3, 4, 5, 6, 7, 8]
@@ -32,5 +32,8 @@ for g in range(40):
 print("per item: row: split begin | A landed | A free | split done || S-issuer: at item | A split seen || row: item end done")
 for n in range(6):
     print(f"{n:4d} " + " ".join(f"{(tr[kind][n] - t0) if tr[kind][n] > 0 else -1:10d}" for kind in (9, 10, 11, 12, 13, 14, 15)))
+print("item end (row warp 2): l exchanged | last PV done | O read | O stored | done")
+for n in range(5):
+    print(f"{n:4d} " + " ".join(f"{(tr[kind][n] - t0) if tr[kind][n] > 0 else -1:10d}" for kind in (20, 21, 22, 23, 15)))
 d = np.diff(tr[8][2:18])
 print("row-warp step period (steps 2..17):", d.tolist())
