@@ -53,7 +53,7 @@ def load_peaks() -> dict:
 
 def load_traffic():
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant matmul shape, from the committed
-    `ncu --set full` capture (profiles/r01_ncu_mm_traffic.json); null when no capture is committed."""
+    `ncu --set full` capture (profiles/r02_ncu_mm_traffic.json); null when no capture is committed."""
     try:
         with open(os.path.join(ROOT, "profiles", "r01_ncu_mm_traffic.json")) as f:
             return json.load(f)
@@ -412,16 +412,22 @@ def run_b200(args) -> None:
     # ---- region A: device-resident inputs ----------------------------------------------------------
     barrier()
     launches0 = cuda_ops.launch_count()
-    profile.matmul_timer = profile.KernelTimer()
+    # roofline evidence is taken LIVE inside this region: every matmul-class launch of every 4th timed step is bracketed by
+    # CUDA events on the launching stream (runtime/cuda/profile.py).  Two event records per launch cost ~2 us of stream
+    # time each — 1.2 ms per step when every step carries them (round 1 did) — so three steps in four run bare.
+    timer = profile.KernelTimer()
+    timed_steps = 0
     clocks = ClockSampler(local).__enter__()          # keeps sampling through region B; closed after it
     e0 = profile.Event().record()
     for i in range(args.steps):
+        profile.matmul_timer = timer if i % 4 == 0 else None
+        timed_steps += int(i % 4 == 0)
         loss = train_step(gpt, opt, params, *dev_batches[i % 4], world)
+    profile.matmul_timer = None
     e1 = profile.Event().record()
     e1.sync()
     barrier()
-    mm = profile.matmul_timer.collect()
-    profile.matmul_timer = None
+    mm = timer.collect()
     ms_a = e1.ms_since(e0)
     launches = cuda_ops.launch_count() - launches0
     last_loss = float(loss.numpy())
@@ -477,7 +483,7 @@ def run_b200(args) -> None:
     live = (nq + 1) / (2.0 * nq) if nq else 1.0
     split = {"dense": [0.0, 0.0, 0], "attention": [0.0, 0.0, 0]}
     for t, v in mm["by_tag"].items():
-        cls = "attention" if (str(t[0]).startswith("attn") or "_sp" in str(t[0])) else "dense"
+        cls = "attention" if (str(t[0]).startswith("attn") or "_spnn" in str(t[0]) or "_sptn" in str(t[0])) else "dense"
         split[cls][0] += v[2]
         split[cls][1] += v[1]
         split[cls][2] += v[0]
@@ -508,15 +514,16 @@ def run_b200(args) -> None:
                      "frac": mm_tflops / peak_3xtf32 if peak_3xtf32 else None, "traffic": load_traffic(),
                      "peak_note": f"3xTF32 = sustained bf16 {peaks['bf16_sustained']} TF/s / 6 ({peaks['source']}: "
                                   "MEASURED_PEAKS.json has no TF32 entry; TF32 dense = bf16/2, 3 MMAs per product)",
-                     "matmul_share_of_step": mm["ms"] / ms_a if ms_a else None, "matmul_launches": mm["launches"],
+                     "matmul_share_of_step": (mm["ms"] / timed_steps) / (ms_a / args.steps) if ms_a else None,
+                     "matmul_launches": mm["launches"], "steps_with_per_launch_events": timed_steps,
                      "tf32_in_box_note": "cuBLAS TF32 measured on a B200 of this pool: 723 burst / 599 sustained TFLOP/s "
                                          "(profiles/r01_tf32_peak_cublas.txt), i.e. 241 / 200 for 3xTF32; the stricter "
                                          "bf16/6 figure is the denominator used",
                      "split": {
-                         "dense_gemms": {"launches": split["dense"][2], "ms_per_step": split["dense"][1] / args.steps,
+                         "dense_gemms": {"launches": split["dense"][2], "ms_per_step": split["dense"][1] / timed_steps,
                                          "tflops": _tf(split["dense"][0], split["dense"][1]),
                                          "frac": (_tf(split["dense"][0], split["dense"][1]) or 0.0) / peak_3xtf32},
-                         "attention_class": {"launches": split["attention"][2], "ms_per_step": split["attention"][1] / args.steps,
+                         "attention_class": {"launches": split["attention"][2], "ms_per_step": split["attention"][1] / timed_steps,
                                              "nominal_tflops": _tf(split["attention"][0], split["attention"][1]),
                                              "executed_tflops": _tf(split["attention"][0] * live, split["attention"][1]),
                                              "executed_fraction_of_nominal": live,
@@ -524,7 +531,7 @@ def run_b200(args) -> None:
                                              "note": "fused attention kernels and tile-skipping GEMMs; the causal mask kills "
                                                      f"{nq * (nq - 1) // 2} of {nq * nq} 128x128 tile pairs per head"}},
                      "by_shape": [{"kernel": t[0], "M": t[1], "N": t[2], "K": t[3], "batch": t[4], "launches": v[0],
-                                   "ms_per_step": v[1] / args.steps, "tflops": v[2] / (v[1] * 1e-3) / 1e12 if v[1] else None}
+                                   "ms_per_step": v[1] / timed_steps, "tflops": v[2] / (v[1] * 1e-3) / 1e12 if v[1] else None}
                                   for t, v in sorted(mm["by_tag"].items(), key=lambda kv: -kv[1][1])[:12]]},
     }
     if world > 1:
