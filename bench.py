@@ -498,7 +498,10 @@ def run_b200(args) -> None:
         "warmup": args.warmup, "ms_per_step": ms_a / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": dict(workload_config(cfg_kw, args.batch, world), **({"gradient_exchange": (
-            "one kernel per rank: reduce-scatter (NVLink peer loads) + Adam on the 1/world shard + all-gather (peer stores)"
+            (f"overlapped with backward: {len(opt.buckets)} parameter buckets, each exchanged on the comm stream as soon as its "
+             "gradients are final by ONE kernel per rank (reduce-scatter over NVLink peer loads + Adam on the 1/world shard + "
+             "all-gather over peer stores); cross-rank arrivals are stream memory operations" if getattr(opt, "overlap", False) else
+             "one kernel per rank after backward: reduce-scatter (NVLink peer loads) + Adam on the 1/world shard + all-gather (peer stores)")
             if fused_dp else "ncclAllReduce of the flat gradient bucket, then the local Adam kernel")} if world > 1 else {})),
         "tokens_per_s": value * args.batch * cfg.block_size,
         "model_tflops": value * flops_step / 1e12,

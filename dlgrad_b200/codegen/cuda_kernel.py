@@ -1465,7 +1465,8 @@ extern "C" __global__ void __launch_bounds__(256) {KNAME}{SIG_ALIAS} {{
     return Kernel("pack_multi", src, (acc, 1, 1), (256, 1, 1), 0, 0)
 
 
-def dp_adam(world: int, shard_vecs: int, beta1: float, beta2: float, eps: float, timeout_s: float = 20.0) -> Kernel:
+def dp_adam(world: int, shard_vecs: int, beta1: float, beta2: float, eps: float, timeout_s: float = 20.0,
+            barriers: bool = True, ctas: int = 0) -> Kernel:
     """Data-parallel optimizer step as ONE kernel per rank over NVLink peer memory: reduce-scatter of the gradients
     (P2P loads), Adam on this rank's 1/world shard, all-gather of the updated parameters (P2P stores).  It replaces
     ncclAllReduce(grads) + adam_multi ("fused with its collective").
@@ -1480,7 +1481,12 @@ def dp_adam(world: int, shard_vecs: int, beta1: float, beta2: float, eps: float,
     Element i of the shard is sum_{r = 0..world-1} grad_r[i] in RANK ORDER on every rank, and only the owner computes
     the update, so all replicas receive bit-identical parameters (NCCL's ring order differs per rank count).  The
     per-element arithmetic after the sum is adam_multi's.  Flags are epochs: they only grow, nothing is reset.  A rank
-    that waits longer than `timeout_s` for a peer traps — a dead peer must fail loudly, not hang the node."""
+    that waits longer than `timeout_s` for a peer traps — a dead peer must fail loudly, not hang the node.
+
+    `barriers=False` is the per-bucket form of the overlapped exchange (distributed.Adam): the two cross-rank barriers
+    are stream operations around the launch (dp_signal + a stream wait on this rank's counter), the table holds the
+    bucket's own base addresses, and `ctas` bounds the grid — the kernel runs on the comm stream next to the backward
+    of earlier layers, so it should saturate NVLink, not the SMs."""
     W = world
     b1, b2, e_ = _flit(beta1), _flit(beta2), _flit(eps)
     omb1, omb2 = _flit(1.0 - beta1), _flit(1.0 - beta2)
@@ -1494,7 +1500,33 @@ def dp_adam(world: int, shard_vecs: int, beta1: float, beta2: float, eps: float,
               p.{c} = __fsub_rn(p.{c}, __fmul_rn(__fdiv_rn(mh, __fadd_rn(__fsqrt_rn(vh), {e_})), f2));
               m.{c} = mn; v.{c} = vn; }}""")
     THREADS = 512
-    grid = max(1, min(2 * NUM_SMS, _cdiv(shard_vecs, THREADS)))
+    grid = max(1, min(ctas or 2 * NUM_SMS, _cdiv(shard_vecs, THREADS)))
+    bar_a = f"""
+    // ---- every rank's gradients are complete (its kernel has started, i.e. its backward has finished) ----
+    if (blockIdx.x == 0u && threadIdx.x < {W}u) {{
+        __threadfence_system();
+        st_release_sys(reinterpret_cast<unsigned*>(tab[{2 * W}u + threadIdx.x]) + rank, e);
+    }}
+    if (threadIdx.x < {W}u) wait_epoch(sync + threadIdx.x, e);
+    __syncthreads();
+""" if barriers else "    __syncthreads();\n"
+    bar_b = f"""
+    // ---- this rank's shard is stored everywhere; leave only when every other shard has arrived here ----
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0u) {{
+        __threadfence_system();
+        if (atomicAdd(sync + {2 * W + 1}, 1u) == gridDim.x - 1u) {{          // last CTA of this rank
+            sync[{2 * W + 1}] = 0u;
+            for (unsigned r = 0; r < {W}u; ++r)
+                st_release_sys(reinterpret_cast<unsigned*>(tab[{2 * W}u + r]) + {W}u + rank, e);
+            for (unsigned r = 0; r < {W}u; ++r) wait_epoch(sync + {W}u + r, e);
+            *reinterpret_cast<volatile unsigned*>(sync + {2 * W}) = e;
+            __threadfence();
+        }}
+    }}
+""" if barriers else ""
+    epoch = f"const unsigned e = *reinterpret_cast<volatile unsigned*>(sync + {2 * W}) + 1u;     // this step's epoch" if barriers else "(void)sync;"
     src = f"""
 __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {{
     unsigned v; asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
@@ -1516,18 +1548,10 @@ extern "C" __global__ void __launch_bounds__({THREADS}) {KNAME}{SIG_ALIAS} {{
     const unsigned long long* tab = reinterpret_cast<const unsigned long long*>(p0);
     unsigned* sync = reinterpret_cast<unsigned*>(p3);
     const unsigned rank = (unsigned)tab[{3 * W}];
-    const unsigned e = *reinterpret_cast<volatile unsigned*>(sync + {2 * W}) + 1u;     // this step's epoch
+    {epoch}
     __shared__ unsigned long long s_tab[{2 * W}];
     if (threadIdx.x < {2 * W}u) s_tab[threadIdx.x] = tab[threadIdx.x];
-
-    // ---- every rank's gradients are complete (its kernel has started, i.e. its backward has finished) ----
-    if (blockIdx.x == 0u && threadIdx.x < {W}u) {{
-        __threadfence_system();
-        st_release_sys(reinterpret_cast<unsigned*>(tab[{2 * W}u + threadIdx.x]) + rank, e);
-    }}
-    if (threadIdx.x < {W}u) wait_epoch(sync + threadIdx.x, e);
-    __syncthreads();
-
+{bar_a}
     // ---- reduce-scatter (peer loads) -> Adam on the shard -> all-gather (peer stores) ----
     float4* M = reinterpret_cast<float4*>(p1);
     float4* V = reinterpret_cast<float4*>(p2);
@@ -1551,21 +1575,50 @@ extern "C" __global__ void __launch_bounds__({THREADS}) {KNAME}{SIG_ALIAS} {{
         for (unsigned r = 0; r < {W}u; ++r)
             reinterpret_cast<float4*>(s_tab[{W}u + r])[base + i] = p;
     }}
+{bar_b}}}
+"""
+    return Kernel("dp_adam" if barriers else "dp_adam_bucket", src, (grid, 1, 1), (THREADS, 1, 1), 0, 0)
 
-    // ---- this rank's shard is stored everywhere; leave only when every other shard has arrived here ----
-    __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x == 0u) {{
+
+def dp_signal(world: int) -> Kernel:
+    """Cross-rank arrival for the overlapped exchange: add 1 to counter word `f0` of EVERY rank's flag block (p0: the
+    table of dp_adam, flag blocks at [2W, 3W)).  Launched on the comm stream after the work it announces, so a
+    system-scope fence + release makes that work (this rank's packed gradients, or its stores of new parameters into
+    the peers' buckets) visible to whoever observes the count.  The matching wait is a stream memory operation
+    (dlg_comm_wait_geq32: count >= epoch * world), which occupies no SM while a peer is late."""
+    W = world
+    src = f"""
+extern "C" __global__ void __launch_bounds__(32) {KNAME}{SIG_ALIAS} {{
+    const unsigned long long* tab = reinterpret_cast<const unsigned long long*>(p0);
+    const unsigned word = (unsigned)f0;
+    if (threadIdx.x < {W}u) {{
         __threadfence_system();
-        if (atomicAdd(sync + {2 * W + 1}, 1u) == gridDim.x - 1u) {{          // last CTA of this rank
-            sync[{2 * W + 1}] = 0u;
-            for (unsigned r = 0; r < {W}u; ++r)
-                st_release_sys(reinterpret_cast<unsigned*>(tab[{2 * W}u + r]) + {W}u + rank, e);
-            for (unsigned r = 0; r < {W}u; ++r) wait_epoch(sync + {W}u + r, e);
-            *reinterpret_cast<volatile unsigned*>(sync + {2 * W}) = e;
-            __threadfence();
-        }}
+        unsigned* dst = reinterpret_cast<unsigned*>(tab[{2 * W}u + threadIdx.x]) + word;
+        asm volatile("red.release.sys.global.add.u32 [%0], %1;" :: "l"(dst), "r"(1u) : "memory");
     }}
 }}
 """
-    return Kernel("dp_adam", src, (grid, 1, 1), (THREADS, 1, 1), 0, 0)
+    return Kernel("dp_signal", src, (1, 1, 1), (32, 1, 1), 0, 0)
+
+
+def dp_wait(timeout_s: float = 600.0) -> Kernel:
+    """Fallback of dlg_comm_wait_geq32 for drivers without stream memory operations: one thread spins on counter word
+    `f0` of this rank's flag block (p0) until it reaches `f1` (both exact small integers in floats... the target is
+    passed as two 16-bit halves f1 | f2 << 16).  It holds an SM slot while a peer is late, which is why the stream
+    operation is preferred."""
+    src = f"""
+extern "C" __global__ void __launch_bounds__(32) {KNAME}{SIG_ALIAS} {{
+    if (threadIdx.x != 0u) return;
+    const unsigned* flag = reinterpret_cast<const unsigned*>(p0) + (unsigned)f0;
+    const unsigned want = (unsigned)f1 | ((unsigned)f2 << 16);
+    unsigned long long t0; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (;;) {{
+        unsigned v; asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+        if ((int)(v - want) >= 0) break;
+        unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        if (t - t0 > {int(timeout_s * 1e9)}ULL) __trap();
+        __nanosleep(500);
+    }}
+}}
+"""
+    return Kernel("dp_wait", src, (1, 1, 1), (32, 1, 1), 0, 0)

@@ -36,7 +36,7 @@
     X(cuDevicePrimaryCtxRetain) X(cuCtxSetCurrent) X(cuCtxSynchronize) X(cuGetErrorString) \
     X(cuMemAlloc) X(cuMemFree) X(cuMemAllocHost) X(cuMemFreeHost) X(cuMemcpyHtoDAsync)     \
     X(cuMemcpyDtoHAsync) X(cuMemcpyDtoDAsync) X(cuMemsetD32Async) X(cuMemsetD8Async)      \
-    X(cuStreamCreate) X(cuStreamSynchronize) X(cuStreamWaitEvent) X(cuEventCreate)        \
+    X(cuStreamCreate) X(cuStreamCreateWithPriority) X(cuCtxGetStreamPriorityRange) X(cuStreamSynchronize) X(cuStreamWaitEvent) X(cuEventCreate)        \
     X(cuEventRecord) X(cuEventSynchronize) X(cuEventElapsedTime) X(cuEventDestroy)        \
     X(cuModuleLoad) X(cuModuleLoadData) X(cuModuleGetFunction) X(cuFuncSetAttribute)      \
     X(cuLaunchKernel) X(cuLaunchKernelEx) X(cuTensorMapEncodeTiled)                       \
@@ -385,7 +385,12 @@ int dlg_init(int device) {
     CU(cuDevicePrimaryCtxRetain(&g_ctx, g_cudev));
     CU(cuCtxSetCurrent(g_ctx));
     CU(cuStreamCreate(&g_stream, CU_STREAM_NON_BLOCKING));
-    CU(cuStreamCreate(&g_comm_stream, CU_STREAM_NON_BLOCKING));
+    {
+        // the comm stream outranks the compute stream: exchange kernels are few, short CTAs that should take the first free slots
+        int lo = 0, hi = 0;
+        if (drv.p_cuCtxGetStreamPriorityRange(&lo, &hi) != CUDA_SUCCESS) hi = 0;
+        CU(cuStreamCreateWithPriority(&g_comm_stream, CU_STREAM_NON_BLOCKING, hi));
+    }
     CU(cuEventCreate(&g_ev_compute, CU_EVENT_DISABLE_TIMING));
     CU(cuEventCreate(&g_ev_comm, CU_EVENT_DISABLE_TIMING));
     drv.p_cuDeviceGetName(g_name, sizeof g_name, g_cudev);
@@ -849,6 +854,59 @@ void *dlg_ipc_open(const unsigned char handle[64]) {
 int dlg_ipc_close(void *mapped) {
     if (!mapped || !g_ready || g_shutdown) return 0;
     CU(cuIpcCloseMemHandle((CUdeviceptr)mapped));
+    return 0;
+}
+
+// ---- comm-stream services for the overlapped data-parallel exchange ------------------------------------------
+int dlg_comm_after_compute(void) {
+    REQUIRE_READY(g_status)
+    CU(cuEventRecord(g_ev_compute, g_stream));
+    CU(cuStreamWaitEvent(g_comm_stream, g_ev_compute, 0));
+    return 0;
+}
+
+int dlg_compute_after_comm(void) { return dlg_nccl_wait(); }
+
+int dlg_comm_plan_run_into(void *plan, void *out, const void *p0, const void *p1, const void *p2,
+                           const void *p3, float f0, float f1, float f2, float f3) {
+    REQUIRE_READY(g_status)
+    Plan *p = (Plan *)plan;
+    if (p->zero_out && out && p->out_bytes)
+        CU(cuMemsetD8Async((CUdeviceptr)out, 0, p->out_bytes, g_comm_stream));
+    void *args[9] = {&p0, &p1, &p2, &p3, &out, &f0, &f1, &f2, &f3};
+    g_status = 0;
+    g_launches++;
+    // plain stream order (no programmatic serialisation): the kernel follows events and memory operations
+    CU(cuLaunchKernel(p->fn, p->grid[0], p->grid[1], p->grid[2], p->block[0], p->block[1], p->block[2],
+                      p->smem, g_comm_stream, args, nullptr));
+    return 0;
+}
+
+// cuStreamWaitValue32 is resolved on demand: older drivers without stream memory operations still load the library
+typedef CUresult (*WaitValue32Fn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+static WaitValue32Fn g_wait32 = nullptr;
+static int g_wait32_state = -1;
+
+int dlg_comm_memops_supported(void) {
+    if (!g_ready) return 0;
+    if (g_wait32_state < 0) {
+        g_wait32 = (WaitValue32Fn)dlsym(drv.handle, "cuStreamWaitValue32_v2");
+        if (!g_wait32) g_wait32 = (WaitValue32Fn)dlsym(drv.handle, "cuStreamWaitValue32");
+        g_wait32_state = g_wait32 ? 1 : 0;
+        const char *e = getenv("DLGRAD_DP_MEMOPS");
+        if (e && e[0] == '0') g_wait32_state = 0;
+    }
+    return g_wait32_state;
+}
+
+int dlg_comm_wait_geq32(void *dptr, uint32_t value) {
+    REQUIRE_READY(g_status)
+    if (!dlg_comm_memops_supported()) {
+        snprintf(g_err, sizeof g_err, "the driver has no stream memory operations (cuStreamWaitValue32)");
+        return g_status = -120;
+    }
+    CUresult r = g_wait32(g_comm_stream, (CUdeviceptr)dptr, value, CU_STREAM_WAIT_VALUE_GEQ);
+    if (r != CUDA_SUCCESS) return fail((int)r, "cuStreamWaitValue32");
     return 0;
 }
 

@@ -18,6 +18,7 @@ uses torch.distributed's gloo store for that and for the timing barrier — plum
 """
 from __future__ import annotations
 
+import math
 import os
 
 import numpy as np
@@ -32,6 +33,11 @@ _state = {"rank": 0, "world": 1, "bucket": None, "bucket_elems": 0}
 # is a sticky context failure on every waiting rank, so the limit is sized for a DEAD peer, not for ordinary skew: a
 # rank that evaluates, writes a checkpoint or JIT-compiles a cold kernel may legitimately be minutes late.
 PEER_TIMEOUT_S = float(os.environ.get("DLGRAD_DP_TIMEOUT_S", "600"))
+# the overlapped schedule of distributed.Adam: exchange buckets of ~BUCKET_MB as backward finishes them, on the comm
+# stream, with COMM_CTAS thread blocks per exchange kernel (enough loads in flight for NVLink, few enough SM slots)
+OVERLAP = os.environ.get("DLGRAD_DP_OVERLAP", "1") != "0"
+BUCKET_MB = float(os.environ.get("DLGRAD_DP_BUCKET_MB", "25"))
+COMM_CTAS = int(os.environ.get("DLGRAD_DP_CTAS", "64"))
 
 
 def unique_id() -> bytes:
@@ -120,13 +126,20 @@ def all_gather_bytes(payload: bytes) -> list[bytes]:
     return [out[r].astype(np.uint8).tobytes() for r in range(world)]
 
 
-def prebuild(sizes: list[int], worlds: tuple = (2, 4, 8), betas: tuple = (0.9, 0.999), eps: float = 1e-8) -> None:
+def prebuild(sizes: list[int], worlds: tuple = (2, 4, 8), betas: tuple = (0.9, 0.999), eps: float = 1e-8,
+             bucket_mb: float | None = None) -> None:
     """Compile the fused step for the given parameter sizes and world sizes into the kernel cache (build machine)."""
     from dlgrad_b200.codegen import cuda_kernel as ck
     from dlgrad_b200.runtime.cuda import compiler
+    mb = BUCKET_MB if bucket_mb is None else bucket_mb
     for w in worlds:
         offs, _, shard = bucket_layout(sizes, w)
-        for k in (ck.dp_adam(w, shard // 4, betas[0], betas[1], eps, PEER_TIMEOUT_S), ck.pack_multi(tuple(sizes), tuple(offs))):
+        kernels = [ck.dp_adam(w, shard // 4, betas[0], betas[1], eps, PEER_TIMEOUT_S), ck.pack_multi(tuple(sizes), tuple(offs)),
+                   ck.dp_signal(w), ck.dp_wait(PEER_TIMEOUT_S)]
+        for b in plan_buckets(sizes, w, max(1, int(mb * (1 << 20)) // 4)):
+            kernels.append(ck.dp_adam(w, b["shard"] // 4, betas[0], betas[1], eps, PEER_TIMEOUT_S, barriers=False, ctas=COMM_CTAS))
+            kernels.append(ck.pack_multi(tuple(sizes[i] for i in b["params"]), tuple(b["offs"])))
+        for k in kernels:
             compiler.get_function(k.name, k.source)
 
 
@@ -197,24 +210,118 @@ class _PeerBlock:
             self.ptr = None
 
 
+def plan_buckets(sizes: list[int], world: int, bucket_elems: int) -> list[dict]:
+    """Partition the parameters into exchange buckets for the overlapped step.  Parameters are walked in REVERSE
+    registration order — the order in which backward finishes them (the last layer first) — and a bucket closes once
+    it holds `bucket_elems` elements.  Each bucket is laid out like the flat bucket of `bucket_layout` (tensors at
+    64-element boundaries, padded to `world` shards of whole float4s) and starts on a 256-byte boundary of the flat
+    buffers, so every rank owns one shard of every bucket.  Returns, per bucket: `params` (indices into `sizes`),
+    `offs` (element offset of each inside the bucket), `start` (bucket offset in the flat buffers), `total`, `shard`,
+    `mstart` (offset of the bucket's shard in the per-rank moment arrays)."""
+    quantum = 64 * 4 * world // math.gcd(64, 4 * world)      # lcm(64, 4 * world): 256-byte starts, whole float4 shards
+    groups, cur, acc = [], [], 0
+    for i in reversed(range(len(sizes))):
+        cur.append(i)
+        acc += sizes[i]
+        if acc >= bucket_elems:
+            groups.append(cur)
+            cur, acc = [], 0
+    if cur:
+        groups.append(cur)
+    out, start, mstart = [], 0, 0
+    for idx in groups:
+        offs = shard_offsets([sizes[i] for i in idx])
+        total = -(-offs[-1] // quantum) * quantum
+        out.append({"params": idx, "offs": offs[:-1], "start": start, "total": total, "shard": total // world,
+                    "mstart": mstart})
+        start += total
+        mstart += total // world
+    return out
+
+
+_owners: dict = {}            # id(parameter Tensor) -> the distributed.Adam that exchanges it (overlapped mode)
+
+
+def _on_grad(t: Tensor) -> None:
+    """Autograd-driver hook (tensor.Tensor.backward): a gradient contribution has just been stored into `t.grad`."""
+    owner = _owners.get(id(t))
+    if owner is not None:
+        owner._grad_arrived(t)
+
+
+def _reads_range(b: Buffer, lo: int, hi: int) -> bool:
+    """Does the deferred producer chain of `b` read device storage inside [lo, hi)?"""
+    stack = [b]
+    while stack:
+        cur = stack.pop()
+        pend = cur._pending
+        if pend is not None:
+            stack.extend(x for x in pend[1:] if isinstance(x, Buffer))
+        elif cur._ptr is not None and cur.metadata.device is Device.CUDA and lo <= shim.address(cur._ptr) < hi:
+            return True
+    return False
+
+
+def _flush_readers(lo: int, hi: int) -> None:
+    """Materialise every deferred buffer that still reads parameter storage in [lo, hi): peers are about to overwrite
+    it (same contract as buffer.flush_pending, matched by address because all parameters share one peer block)."""
+    from dlgrad_b200 import buffer as _buf
+    for key, ref in list(_buf._pending_buffers.items()):
+        b = ref()
+        if b is None or b._pending is None:
+            _buf._pending_buffers.pop(key, None)
+            continue
+        if _reads_range(b, lo, hi):
+            _ = b.ptr
+            _buf._pending_buffers.pop(key, None)
+
+
 class Adam:
     """nn.optim.Adam (dlgrad/nn/optim.py:46-70) for data-parallel replicas: same constructor, `zero_grad()` and
-    `step()`; step() averages the gradients over the ranks and applies the update in one kernel per rank.
+    `step()`; the gradients are averaged over the ranks and the update is applied by the rank that owns the shard.
 
-    Construction re-homes every parameter into one flat peer-mappable bucket (values are kept, the Buffers keep
+    Construction re-homes every parameter into one flat peer-mappable buffer (values are kept, the Buffers keep
     their identity) and is collective: every rank must construct it with the same parameter list.  With
-    world == 1 it degenerates to a single-GPU fused Adam over the flat bucket (same arithmetic as adam_multi)."""
+    world == 1 it degenerates to a single-GPU fused Adam over the flat buffer (same arithmetic as adam_multi).
+
+    Two schedules, same arithmetic, same bits:
+
+    * overlapped (default): the parameters form buckets of ~`bucket_mb` MB in the order backward finishes them.  When
+      the last gradient of a bucket has been stored (the autograd driver reports every `.grad` assignment; the count
+      per parameter is learned in the first step), its exchange is enqueued on the comm stream — pack the gradients
+      into the peer-visible bucket, announce (dp_signal), wait until all ranks have announced (a stream memory
+      operation: no SM is held while a peer is late), then ONE kernel: reduce-scatter over NVLink loads, Adam on the
+      shard, all-gather over NVLink stores — while the compute stream continues with the backward of earlier layers.
+      step() enqueues what is left (the first layer's bucket and the embeddings), a final cross-rank arrival, and makes
+      the compute stream wait for it.  A bucket is enqueued one bucket late (when the first gradient of the next one
+      arrives) so that deferred consumers of its parameters — the fused RMSNorm-dx + residual add — have run; whatever
+      still reads the bucket's parameters is materialised first.
+    * monolithic (`overlap=False` / DLGRAD_DP_OVERLAP=0; round 1): pack everything after backward, then one kernel
+      with two in-kernel cross-rank barriers."""
 
     def __init__(self, params: list[Tensor], lr: float = 1e-3, betas: tuple[float, float] = (0.9, 0.999),
-                 eps: float = 1e-8) -> None:
+                 eps: float = 1e-8, overlap: bool | None = None, bucket_mb: float | None = None) -> None:
         from dlgrad_b200.codegen import cuda_kernel as ck
         from dlgrad_b200.runtime.cuda import ops as cuda_ops
+        from dlgrad_b200.runtime.cuda import transfer
         self.params = params
         self.lr, (self.beta1, self.beta2), self.eps = lr, betas, eps
         self.t = 0
         world = _state["world"]
+        self.overlap = OVERLAP if overlap is None else bool(overlap)
         self.sizes = [p.numel for p in params]
-        self.offs, self.total, self.shard = bucket_layout(self.sizes, world)
+        if self.overlap:
+            mb = BUCKET_MB if bucket_mb is None else bucket_mb
+            self.buckets = plan_buckets(self.sizes, world, max(1, int(mb * (1 << 20)) // 4))
+            self.offs = [0] * len(params)
+            for b in self.buckets:
+                for i, o in zip(b["params"], b["offs"]):
+                    self.offs[i] = b["start"] + o
+            self.total = self.buckets[-1]["start"] + self.buckets[-1]["total"]
+            self.shard = sum(b["shard"] for b in self.buckets)
+        else:
+            self.buckets = None
+            self.offs, self.total, self.shard = bucket_layout(self.sizes, world)
         flush_pending(tuple(p.data for p in params))
         self.grads = _PeerBlock(self.total * 4)
         self.weights = _PeerBlock(self.total * 4)
@@ -229,34 +336,190 @@ class Adam:
             buf._keep = self.weights
             buf.aligned = True
         shim.synchronize()                        # the old parameter storage is released only after the copies
-        table = np.array(self.grads.addr + self.weights.addr + self.flags.addr + [_state["rank"]], dtype=np.uint64)
-        from dlgrad_b200.runtime.cuda import transfer
-        self.table = transfer.upload(shim.ffi.from_buffer("char *", table), table.nbytes)
         self.m = shim.calloc(self.shard * 4)
         self.v = shim.calloc(self.shard * 4)
-        self.plan = cuda_ops.Plan(ck.dp_adam(world, self.shard // 4, self.beta1, self.beta2, self.eps, PEER_TIMEOUT_S))
-        # gradient packing: one launch over a table of source addresses (two pinned staging tables alternate, so
-        # one is never rewritten while its copy may still be in flight)
         n = len(params)
-        self.pack = cuda_ops.Plan(ck.pack_multi(tuple(self.sizes), tuple(self.offs)))
-        self.pack_host = [lib.dlg_host_alloc(8 * n), lib.dlg_host_alloc(8 * n)]
-        if shim.NULL in self.pack_host:
-            raise MemoryError("pinned staging allocation failed: " + shim.last_error())
-        self.pack_view = [shim.ffi.cast("unsigned long long *", h) for h in self.pack_host]
         self.pack_dev = shim.alloc(8 * n)
-        self.flip = 0
-        self.pack_events = [None, None]
-        self.pack_last = None
+        if self.overlap:
+            self._init_overlap(ck, cuda_ops, transfer, world)
+        else:
+            table = np.array(self.grads.addr + self.weights.addr + self.flags.addr + [_state["rank"]], dtype=np.uint64)
+            self.table = transfer.upload(shim.ffi.from_buffer("char *", table), table.nbytes)
+            self.plan = cuda_ops.Plan(ck.dp_adam(world, self.shard // 4, self.beta1, self.beta2, self.eps, PEER_TIMEOUT_S))
+            # gradient packing: one launch over a table of source addresses (two pinned staging tables alternate, so
+            # one is never rewritten while its copy may still be in flight)
+            self.pack = cuda_ops.Plan(ck.pack_multi(tuple(self.sizes), tuple(self.offs)))
+            self.pack_host = [lib.dlg_host_alloc(8 * n), lib.dlg_host_alloc(8 * n)]
+            if shim.NULL in self.pack_host:
+                raise MemoryError("pinned staging allocation failed: " + shim.last_error())
+            self.pack_view = [shim.ffi.cast("unsigned long long *", h) for h in self.pack_host]
+            self.flip = 0
+            self.pack_events = [None, None]
+            self.pack_last = None
         shim.synchronize()
         if world > 1:
             all_gather_bytes(b"\0")                # nobody launches before every rank has mapped its peers
 
+    # ------------------------------------------------------------------ overlapped schedule
+    def _init_overlap(self, ck, cuda_ops, transfer, world: int) -> None:
+        lib, ffi = shim.lib, shim.ffi
+        if len(self.buckets) + 1 > 1024:
+            raise ValueError("too many exchange buckets for the 4 KB flag block: raise bucket_mb")
+        self.memops = bool(lib.dlg_comm_memops_supported())
+        self.signal = cuda_ops.Plan(ck.dp_signal(world))
+        self.spin = None if self.memops else cuda_ops.Plan(ck.dp_wait(PEER_TIMEOUT_S))
+        self._index = {id(p): i for i, p in enumerate(self.params)}
+        self._bucket_of = [0] * len(self.params)
+        for k, b in enumerate(self.buckets):
+            tab = np.array([a + 4 * b["start"] for a in self.grads.addr] + [a + 4 * b["start"] for a in self.weights.addr]
+                           + self.flags.addr + [_state["rank"]], dtype=np.uint64)
+            b["table"] = transfer.upload(ffi.from_buffer("char *", tab), tab.nbytes)
+            b["adam"] = cuda_ops.Plan(ck.dp_adam(world, b["shard"] // 4, self.beta1, self.beta2, self.eps, PEER_TIMEOUT_S,
+                                                 barriers=False, ctas=COMM_CTAS))
+            b["pack"] = cuda_ops.Plan(ck.pack_multi(tuple(self.sizes[i] for i in b["params"]), tuple(b["offs"])))
+            nb = len(b["params"])
+            b["host"] = lib.dlg_host_alloc(8 * nb)
+            if b["host"] == shim.NULL:
+                raise MemoryError("pinned staging allocation failed: " + shim.last_error())
+            b["view"] = ffi.cast("unsigned long long *", b["host"])
+            b["event"] = None
+            b["last"] = None
+            b["slot"] = min(b["params"])               # the bucket's rows of the device table of source addresses
+            assert sorted(b["params"]) == list(range(b["slot"], b["slot"] + nb))
+            b["lo"] = self.weights.addr[_state["rank"]] + 4 * b["start"]
+            b["hi"] = b["lo"] + 4 * b["total"]
+            for i in b["params"]:
+                self._bucket_of[i] = k
+        for p in self.params:
+            _owners[id(p)] = self
+        from dlgrad_b200 import tensor as _tensor
+        _tensor._grad_hook = _on_grad
+        self._expect = None                       # gradient contributions per parameter in one backward (learned)
+        self._seen = [0] * len(self.params)
+        self._armed = False
+        self._left = [0] * len(self.buckets)
+        self._launched = [False] * len(self.buckets)
+        self._ready: list[int] = []
+
+    def _grad_arrived(self, t: Tensor) -> None:
+        i = self._index[id(t)]
+        self._seen[i] += 1
+        if not self._armed:
+            return
+        k = self._bucket_of[i]
+        if self._launched[k]:
+            raise RuntimeError(
+                "distributed.Adam (overlapped): a gradient arrived for a parameter whose bucket has already been exchanged "
+                "— the number of gradient contributions per parameter changed between steps, or backward ran twice before "
+                "step().  Construct the optimizer with overlap=False for such loops.")
+        if k in self._ready:
+            raise RuntimeError("distributed.Adam (overlapped): more gradient contributions than in the first step for a "
+                               "parameter of a completed bucket; construct the optimizer with overlap=False")
+        if self._ready:
+            # bucket k has started: the buckets completed before it are one bucket behind, their deferred readers have run
+            for r in self._ready:
+                self._exchange(r)
+            self._ready = []
+        self._left[k] -= 1
+        if self._left[k] == 0:
+            self._ready.append(k)
+
+    def _exchange(self, k: int) -> None:
+        """Enqueue bucket k's exchange on the comm stream, ordered after everything the compute stream holds now."""
+        b = self.buckets[k]
+        lib = shim.lib
+        world = _state["world"]
+        self._launched[k] = True
+        grads = [None if self.params[i].grad is None else self.params[i].grad.data for i in b["params"]]
+        for g in grads:
+            if g is not None and g.metadata.device is not Device.CUDA:
+                g._to_cuda()
+        _flush_readers(b["lo"], b["hi"])
+        gdst = self.grads.fptr + b["start"]
+        packed = all(g is not None and g.aligned for g in grads)
+        if packed:
+            table = [shim.address(g.ptr) for g in grads]
+            if table != b["last"]:
+                # new gradient addresses: upload this bucket's rows.  The host runs ahead of the device, so the staging
+                # buffer is rewritten only after the copy that last read it has executed.
+                if b["event"] is not None:
+                    shim.check(lib.dlg_event_sync(b["event"]), "dlg_event_sync")
+                view = b["view"]
+                for j, a in enumerate(table):
+                    view[j] = a
+                shim.check(lib.dlg_h2d_async(shim.ffi.cast("char *", self.pack_dev) + 8 * b["slot"], b["host"], 8 * len(table)),
+                           "dlg_h2d_async")
+                if b["event"] is None:
+                    b["event"] = lib.dlg_event_create()
+                shim.check(lib.dlg_event_record(b["event"]), "dlg_event_record")
+                b["last"] = table
+        else:
+            for g, off, i in zip(grads, b["offs"], b["params"]):
+                dst = gdst + off
+                if g is None:
+                    shim.check(lib.dlg_memset32(dst, 0, self.sizes[i]), "dlg_memset32")
+                else:
+                    shim.check(lib.dlg_d2d(dst, g.ptr, self.sizes[i] * 4), "dlg_d2d")
+        shim.check(lib.dlg_comm_after_compute(), "dlg_comm_after_compute")
+        if packed:
+            b["pack"].run_into_comm(gdst, shim.ffi.cast("char *", self.pack_dev) + 8 * b["slot"])
+        self._arrive(k, b["table"])
+        b["adam"].run_into_comm(shim.NULL, b["table"], self.m + b["mstart"], self.v + b["mstart"], self.flags.fptr,
+                                self._bc1, self._bc2, float(np.float32(self.lr)), 1.0 / world)
+
+    def _arrive(self, word: int, table) -> None:
+        """Cross-rank arrival on counter `word`: announce on every rank, then hold the comm stream until all have."""
+        lib = shim.lib
+        want = (self.t * _state["world"]) & 0xFFFFFFFF
+        self.signal.run_into_comm(shim.NULL, table, shim.NULL, shim.NULL, shim.NULL, float(word))
+        if self.memops:
+            shim.check(lib.dlg_comm_wait_geq32(shim.ffi.cast("char *", self.flags.ptr) + 4 * word, want), "dlg_comm_wait_geq32")
+        else:
+            self.spin.run_into_comm(shim.NULL, self.flags.fptr, shim.NULL, shim.NULL, shim.NULL, float(word),
+                                    float(want & 0xFFFF), float(want >> 16))
+
+    def _begin_step(self) -> None:
+        """Scalars of the step whose exchange starts now (the first bucket may be enqueued during backward)."""
+        self.t += 1
+        f32 = np.float32
+        self._bc1 = float(f32(1.0 - self.beta1 ** self.t))
+        self._bc2 = float(f32(1.0 - self.beta2 ** self.t))
+
+    def _step_overlapped(self) -> None:
+        if not self._armed:
+            self._begin_step()                     # nothing was enqueued during backward: the whole exchange starts here
+        for k in range(len(self.buckets)):
+            if not self._launched[k]:
+                self._exchange(k)
+        self._arrive(len(self.buckets), self.buckets[0]["table"])
+        shim.check(shim.lib.dlg_compute_after_comm(), "dlg_compute_after_comm")
+        if self._expect is None and any(self._seen):
+            self._expect = list(self._seen)
+        self._armed = False
+        self._launched = [False] * len(self.buckets)
+        self._ready = []
+
     def zero_grad(self) -> None:
+        if self.overlap and any(self._launched):
+            raise RuntimeError("distributed.Adam (overlapped): zero_grad() after a backward whose exchange has started and "
+                               "before step(); construct the optimizer with overlap=False for such loops")
         for p in self.params:
             p.grad = None
+        if self.overlap:
+            self._seen = [0] * len(self.params)
+            self._ready = []
+            if self._expect is not None:
+                # arm the overlap for the backward that follows: bucket k is complete after _left[k] contributions
+                self._left = [sum(self._expect[i] for i in b["params"]) for b in self.buckets]
+                if not self._armed:
+                    self._begin_step()
+                self._armed = True
 
     def step(self) -> None:
         shim.no_capture("distributed.Adam.step() (ranks wait for each other inside the kernel; capture forward + backward only)")
+        if self.overlap:
+            self._step_overlapped()
+            return
         self.t += 1
         f32 = np.float32
         bc1 = float(f32(1.0 - self.beta1 ** self.t))
@@ -298,5 +561,13 @@ class Adam:
 
     def close(self) -> None:
         shim.synchronize()
+        if self.overlap:
+            for p in self.params:
+                if _owners.get(id(p)) is self:
+                    del _owners[id(p)]
+            for b in self.buckets:
+                if b.get("host") is not None:
+                    shim.lib.dlg_host_free(b["host"])
+                    b["host"] = None
         for blk in (self.grads, self.weights, self.flags):
             blk.close()

@@ -118,6 +118,11 @@ class Plan:
         if timer is not None:
             timer.stop(t0, 0.0, (self.kernel.name, 0))
 
+    def run_into_comm(self, out, p0=NULL, p1=NULL, p2=NULL, p3=NULL, f0=0.0, f1=0.0, f2=0.0, f3=0.0) -> None:
+        """run_into on the comm stream (the overlapped data-parallel exchange, dlgrad_b200/distributed.py)."""
+        if lib.dlg_comm_plan_run_into(self.c, out, p0, p1, p2, p3, f0, f1, f2, f3) != 0:
+            raise RuntimeError("kernel launch on the comm stream failed: " + shim.last_error())
+
 
 # ------------------------------------------------------------------------------------------------
 # deferred pointwise chains (Buffer._pending)

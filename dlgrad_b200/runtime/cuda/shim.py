@@ -126,6 +126,11 @@ class _CompileOnlyLib:
     def dlg_ipc_export(self, p, h): return 0
     def dlg_ipc_open(self, h): return self._addr(1 << 21)
     def dlg_ipc_close(self, p): return 0
+    def dlg_comm_after_compute(self): return 0
+    def dlg_compute_after_comm(self): return 0
+    def dlg_comm_plan_run_into(self, plan, out, *a): self.launches += 1; return 0
+    def dlg_comm_memops_supported(self): return 1
+    def dlg_comm_wait_geq32(self, p, v): return 0
 
 
 def _load():

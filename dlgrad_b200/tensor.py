@@ -19,6 +19,9 @@ from dlgrad_b200.dtype import DType, Scalar
 from dlgrad_b200.runtime.cuda import ops as _cuda_runtime  # registers every (op, Device.CUDA)  # noqa: F401
 
 _CUDA = Device.CUDA
+# set by dlgrad_b200/distributed.py (overlapped data-parallel exchange): called with every tensor whose `.grad` the
+# backward sweep has just assigned or accumulated into, so a bucket of parameters can be exchanged as soon as it is final
+_grad_hook = None
 
 
 class OP:
@@ -382,6 +385,8 @@ class Tensor:
                     continue
                 g_t = Tensor(g)
                 parent.grad = g_t if parent.grad is None else parent.grad + g_t
+                if _grad_hook is not None:
+                    _grad_hook(parent)
             if node is not self:
                 # an interior node's gradient has been consumed: release it (a (B,h,T,T) attention gradient
                 # is 400 MB at the benchmark config; the reference keeps every one alive until the graph dies)

@@ -163,6 +163,20 @@ int   dlg_ipc_export(void *dptr, unsigned char handle[64]);
 void *dlg_ipc_open(const unsigned char handle[64]);      /* NULL on failure                  */
 int   dlg_ipc_close(void *mapped);
 
+/* ---- comm-stream services for the OVERLAPPED data-parallel exchange (dlgrad_b200/distributed.py) ----------
+ * The gradient exchange of a parameter bucket runs on the comm stream while the compute stream is still in the
+ * backward of earlier layers.  Cross-rank waits are stream memory operations (cuStreamWaitValue32 on a counter
+ * in this rank's peer-mapped flag block), so a rank that waits for a peer occupies no SM. */
+int   dlg_comm_after_compute(void);          /* later comm-stream work runs after everything enqueued so far on
+                                                the compute stream                                       */
+int   dlg_compute_after_comm(void);          /* and the reverse                                          */
+int   dlg_comm_plan_run_into(void *plan, void *out, const void *p0, const void *p1, const void *p2,
+                             const void *p3, float f0, float f1, float f2, float f3);
+                                             /* dlg_plan_run_into on the comm stream                     */
+int   dlg_comm_memops_supported(void);       /* 1 when the driver offers stream memory operations        */
+int   dlg_comm_wait_geq32(void *dptr, uint32_t value);
+                                             /* comm stream blocks until (int32)(*dptr - value) >= 0     */
+
 #ifdef __cplusplus
 }
 #endif

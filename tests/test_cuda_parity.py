@@ -864,12 +864,24 @@ def test_split_k_in_kernel_finish_matches_two_kernel_sum():
                          f"fused split-K {M}x{N}x{K}/{S} vs float64")
 
 
-def test_fused_dp_adam_single_rank_is_bit_identical_to_adam():
+@pytest.mark.parametrize("schedule", ["overlapped", "overlapped-spin", "monolithic"])
+def test_fused_dp_adam_single_rank_is_bit_identical_to_adam(schedule, monkeypatch):
     """distributed.Adam (reduce-scatter + Adam + all-gather in one kernel over peer memory) at world == 1: the
     parameters move into one flat bucket, the moments are flat, and three steps must give the SAME BITS as
-    nn.optim.Adam's multi-tensor kernel.  The multi-rank exchange itself is exercised by scripts/dp_fused_check.py
-    under torchrun (2+ GPUs; profiles/r01_dp_fused_check.txt)."""
+    nn.optim.Adam's multi-tensor kernel — with the bucketed schedule on the comm stream (several small buckets, cross-rank
+    arrivals as stream memory operations, or as a spinning kernel where the driver has none) and with the single kernel
+    of round 1.  The multi-rank exchange itself is exercised by scripts/dp_fused_check.py under torchrun (2+ GPUs)."""
     from dlgrad_b200 import Tensor, distributed, nn
+    _Adam = distributed.Adam
+
+    def make(params, **kw):
+        opt = _Adam(params, overlap=schedule != "monolithic", bucket_mb=0.01, **kw)
+        if schedule == "overlapped-spin" and opt.memops:
+            from dlgrad_b200.codegen import cuda_kernel as ck
+            from dlgrad_b200.runtime.cuda import ops as cuda_ops
+            opt.memops, opt.spin = False, cuda_ops.Plan(ck.dp_wait(30.0))
+        return opt
+    monkeypatch.setattr(distributed, "Adam", make)
     rng = np.random.default_rng(5)
     shapes = [(96, 64), (64,), (256, 64), (7, 3), (1, 1)]
     init = [rng.standard_normal(s).astype(np.float32) for s in shapes]
@@ -904,6 +916,48 @@ def test_fused_dp_adam_single_rank_is_bit_identical_to_adam():
         lone.step()
     check(c[0].numpy(), lone.params[0].numpy(), exact=True, what="fused DP Adam, tensor with a gradient (copy path)")
     check(c[1].numpy(), init[1], exact=True, what="fused DP Adam, tensor without a gradient is unchanged")
+    if schedule != "monolithic":
+        assert len(fused.buckets) >= 2
+
+
+def test_overlapped_dp_adam_trains_bit_identically_to_adam():
+    """The overlapped schedule driven by the autograd hook (world == 1, several buckets): from the second step on the
+    buckets are exchanged on the comm stream while backward is still running on the compute stream.  Five train steps of a
+    small GPT must leave the SAME BITS in every parameter as nn.optim.Adam, and the loss curve must be identical."""
+    import dlgrad_b200 as dl
+    from dlgrad_b200 import Tensor, distributed, nn
+    from tests import models
+    cfg = models.GPTConfig(vocab_size=96, block_size=64, n_layer=3, n_head=4, n_embd=128, device="cuda")
+    nets = [models.GPT(dl, cfg, np.random.default_rng(0)) for _ in range(2)]
+    plist = [nn.utils.get_parameters(n) for n in nets]
+    opts = [nn.optim.Adam(plist[0], lr=1e-3), distributed.Adam(plist[1], lr=1e-3, bucket_mb=0.3)]
+    assert len(opts[1].buckets) >= 4
+    rng = np.random.default_rng(3)
+    early = []
+    orig = opts[1]._exchange
+    state = {"bwd": False}
+
+    def traced(k):
+        if state["bwd"]:
+            early.append(k)
+        orig(k)
+    opts[1]._exchange = traced
+    for step in range(5):
+        x, y = models.gpt_batch(cfg, 8, rng)
+        losses = []
+        for net, opt in zip(nets, opts):
+            opt.zero_grad()
+            _, loss = net(Tensor(x.copy(), device="cuda"), Tensor(y.copy(), device="cuda"))
+            state["bwd"] = opt is opts[1]
+            loss.backward()
+            state["bwd"] = False
+            opt.step()
+            losses.append(float(loss.numpy()))
+        assert losses[0] == losses[1], (step, losses)
+        for i, (p, q) in enumerate(zip(*plist)):
+            check(q.numpy(), p.numpy(), exact=True, what=f"overlapped DP Adam, step {step}, parameter {i}")
+    assert len(early) >= 4 * (len(opts[1].buckets) - 2), early       # steps 2..5 really overlapped
+    opts[1].close()
 
 
 @pytest.mark.timeout(600)

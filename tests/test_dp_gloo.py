@@ -104,6 +104,86 @@ def test_bucket_layout_and_sharded_update_cover_every_parameter(world):
         assert o + n <= total
 
 
+@pytest.mark.parametrize("world", [1, 2, 3, 8])
+def test_exchange_buckets_partition_the_parameters_in_backward_order(world):
+    """distributed.plan_buckets (overlapped exchange): buckets take the parameters in reverse registration order, every
+    parameter lies in exactly one bucket, buckets and tensors start on 256-byte boundaries of the flat buffers, every
+    bucket splits into `world` shards of whole float4s, and the per-rank moment slices tile the moment arrays."""
+    from dlgrad_b200.distributed import plan_buckets
+    sizes = [96 * 32, 1024 * 32] + [32, 32 * 32, 32 * 32, 32 * 32, 32 * 32, 32, 128 * 32, 32 * 128] * 3 + [32, 96 * 32]
+    buckets = plan_buckets(sizes, world, 3000)
+    order = [i for b in buckets for i in b["params"]]
+    assert order == list(reversed(range(len(sizes))))
+    assert len(buckets) > 3
+    flat_end, m_end = 0, 0
+    for b in buckets:
+        assert b["start"] == flat_end and b["start"] % 64 == 0 and b["mstart"] == m_end
+        assert b["total"] == b["shard"] * world and b["shard"] % 4 == 0
+        for i, o, nxt in zip(b["params"], b["offs"], b["offs"][1:] + [b["total"]]):
+            assert o % 64 == 0 and o + sizes[i] <= nxt
+        flat_end += b["total"]
+        m_end += b["shard"]
+    # all but the last bucket reach the threshold; one huge tensor is a bucket of its own
+    assert all(sum(sizes[i] for i in b["params"]) >= 3000 for b in buckets[:-1])
+
+
+def test_overlapped_exchange_is_enqueued_during_backward():
+    """Host-side schedule of distributed.Adam (overlapped) walked with the device stubbed out: the first step learns the
+    number of gradient contributions per parameter and exchanges everything in step(); from the second step on every
+    bucket but the last ones is enqueued while backward is still running, one bucket late, each exactly once, and
+    a second backward before step() fails loudly."""
+    import subprocess
+    import sys
+    code = r"""
+import numpy as np
+import dlgrad_b200 as dl
+from dlgrad_b200 import Tensor, distributed, nn
+from dlgrad_b200.runtime.cuda import shim
+from tests import models
+cfg = models.GPTConfig(vocab_size=96, block_size=32, n_layer=3, n_head=2, n_embd=32, device="cuda")
+gpt = models.GPT(dl, cfg, np.random.default_rng(0))
+params = nn.utils.get_parameters(gpt)
+opt = distributed.Adam(params, lr=1e-3, bucket_mb=0.02)
+assert len(opt.buckets) >= 4, len(opt.buckets)
+x, y = models.gpt_batch(cfg, 2, np.random.default_rng(1))
+log = []
+orig = opt._exchange
+def traced(k):
+    log.append((k, in_backward[0]))
+    orig(k)
+opt._exchange = traced
+in_backward = [False]
+for step in range(3):
+    del log[:]
+    opt.zero_grad()
+    _, loss = gpt(Tensor(x, device="cuda"), Tensor(y, device="cuda"))
+    in_backward[0] = True
+    loss.backward()
+    in_backward[0] = False
+    opt.step()
+    assert sorted(k for k, _ in log) == list(range(len(opt.buckets))), log
+    early = [k for k, b in log if b]
+    if step == 0:
+        assert not early
+    else:
+        assert early == list(range(len(early))) and len(early) >= len(opt.buckets) - 2, log
+assert opt.t == 3 and all(e == 1 for e in opt._expect)
+opt.zero_grad()
+_, loss = gpt(Tensor(x, device="cuda"), Tensor(y, device="cuda"))
+loss.backward()
+try:
+    opt.zero_grad()
+    raise SystemExit("zero_grad() after a started exchange must raise")
+except RuntimeError:
+    pass
+print("SCHEDULE-OK")
+"""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, DLGRAD_CUDA_COMPILE_ONLY="1", PYTHONPATH=root)
+    res = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=280)
+    assert res.returncode == 0 and "SCHEDULE-OK" in res.stdout, res.stdout[-1500:] + res.stderr[-3000:]
+
+
 @pytest.mark.timeout(300)
 def test_two_rank_dp_step_equals_full_batch_step(tmp_path):
     import torch.multiprocessing as mp
