@@ -20,6 +20,8 @@ Inputs and activations are far larger than L2 (one step touches > 20 GB), so no 
 from __future__ import annotations
 
 import argparse
+import atexit
+import gc
 import json
 import os
 import subprocess
@@ -62,31 +64,48 @@ def load_traffic():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 100 ms while the timed regions (A and B, the same load) run."""
+    """nvidia-smi clocks / throttle reasons sampled every 100 ms while the timed regions (A and B, the same load) run.
+
+    ONE nvidia-smi process per job (rank 0 samples all the job's GPUs), started BEFORE the warm-up steps: its start-up
+    (NVML initialisation, attaching to every GPU of the box) stalls work submission on a GPU for ~30 ms — measured as one
+    58 ms step in a 20-step region when every rank started its own sampler at the top of the timed region, and with a
+    cross-rank barrier in every step one stalled rank stalls all of them.  Rows are kept only while `active`."""
 
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index: int) -> None:
-        self.rows, self.proc, self.index = [], None, index
+    def __init__(self, indices) -> None:
+        self.rows, self.proc, self.indices, self.active, self.seen = [], None, list(indices), False, 0
 
     def __enter__(self):
+        if not self.indices:
+            return self
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                ["nvidia-smi", "--id=" + ",".join(str(i) for i in self.indices), f"--query-gpu={self.Q}",
+                 "--format=csv,noheader,nounits", "-lms", "100"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
+            atexit.register(self.__exit__)
         except OSError:
             self.proc = None
         return self
 
+    def wait_started(self, timeout_s: float = 5.0) -> None:
+        """Block until nvidia-smi has printed its first row (its start-up is over) or `timeout_s` has passed."""
+        t_end = time.perf_counter() + timeout_s
+        while self.proc is not None and self.seen == 0 and self.proc.poll() is None and time.perf_counter() < t_end:
+            time.sleep(0.01)
+
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.seen += 1
+            if self.active:
+                self.rows.append([c.strip() for c in line.split(",")])
 
     def __exit__(self, *exc):
-        if self.proc:
+        if self.proc and self.proc.poll() is None:
             self.proc.terminate()
 
     def summary(self) -> dict:
@@ -365,12 +384,18 @@ def run_b200(args) -> None:
             dist.barrier()
 
     cfg_kw = C5 if args.config == "c5" else C4
-    fused_dp = world > 1 and os.environ.get("DLGRAD_DP_FUSED", "1") != "0"
-    if fused_dp and not distributed.peer_memory_available():
+    # DLGRAD_DP_FUSED=force: the data-parallel optimizer on ONE GPU too (its exchange degenerates to local loads and stores) —
+    # a cheap way to measure what the comm-stream kernels cost the backward they overlap with
+    fused_dp = (world > 1 and os.environ.get("DLGRAD_DP_FUSED", "1") != "0") or os.environ.get("DLGRAD_DP_FUSED") == "force"
+    if fused_dp and world > 1 and not distributed.peer_memory_available():
         fused_dp = False
         if rank == 0:
             print("[bench] peer memory cannot be mapped on this box: gradient exchange falls back to ncclAllReduce "
                   f"({shim.last_error()})", file=sys.stderr)
+    # rank 0 samples the clocks of all the job's GPUs (local rank = GPU index under the single-node launcher); started here so
+    # that nvidia-smi's start-up falls into the model build and the warm-up, not into a timed region
+    sampling = rank == 0 and not (args.prebuild or args.profile)
+    clocks = ClockSampler(range(world) if sampling else ()).__enter__()
     cfg, gpt, params, opt = build_gpt(cfg_kw, "cuda", fused_dp)
     opt.grad_scale = 1.0 / world
     data_rng = np.random.default_rng(1000 + rank)            # rank-specific tokens
@@ -409,25 +434,49 @@ def run_b200(args) -> None:
         return
 
     peaks = load_peaks()
+    # Python's cyclic collector: a full (generation-2) pass walks every live object of the process — 10 ms here, but ~80 ms
+    # once torch.distributed is imported for the N > 1 rendezvous (175 k objects) — and the host is never more than one
+    # launch queue (~2 steps) ahead of the device, so one such pause inside a timed region starves the GPU for 20-35 ms
+    # (seen as ONE 47-62 ms step per region at N = 2 and none at N = 1; with a cross-rank barrier in every step one paused
+    # rank pauses all).  Standard remedy for training loops: collect now, then freeze the survivors out of later passes.
+    if os.environ.get("DLGRAD_BENCH_GC_FREEZE", "1") != "0":
+        gc.collect()
+        gc.freeze()
     # ---- region A: device-resident inputs ----------------------------------------------------------
     barrier()
     launches0 = cuda_ops.launch_count()
-    # roofline evidence is taken LIVE inside this region: every matmul-class launch of every 4th timed step is bracketed by
+    # roofline evidence is taken LIVE inside this region: every matmul-class launch of every 10th timed step is bracketed by
     # CUDA events on the launching stream (runtime/cuda/profile.py).  Two event records per launch cost ~2 us of stream
-    # time each — 1.2 ms per step when every step carries them (round 1 did) — so three steps in four run bare.
+    # time each — 1.2 ms per step when every step carries them (round 1 did) — so nine steps in ten run bare.
     timer = profile.KernelTimer()
     timed_steps = 0
-    clocks = ClockSampler(local).__enter__()          # keeps sampling through region B; closed after it
-    e0 = profile.Event().record()
+    clocks.wait_started()
+    clocks.active = True                              # keeps sampling through region B; closed after it
+    e0 = e0_a = profile.Event().record()
+    step_times = os.environ.get("DLGRAD_BENCH_STEP_TIMES", "0") == "1"      # diagnosis: per-step device times of both regions
+    marks_a, marks_b = [], []
+    runahead = int(os.environ.get("DLGRAD_BENCH_RUNAHEAD", "0"))
+    step_events = []
+    # (round 2, measured: a step that carries the events takes +2.5 ms — 29.2 against 26.6 ms — so every 10th step does)
+    every = int(os.environ.get("DLGRAD_BENCH_TIMER_EVERY", "10"))      # 0: no per-launch events at all (A/B runs only)
     for i in range(args.steps):
-        profile.matmul_timer = timer if i % 4 == 0 else None
-        timed_steps += int(i % 4 == 0)
+        sampled = every > 0 and i % every == 0
+        profile.matmul_timer = timer if sampled else None
+        timed_steps += int(sampled)
         loss = train_step(gpt, opt, params, *dev_batches[i % 4], world)
+        if step_times:
+            marks_a.append(profile.Event().record())
+        if runahead > 0:
+            # bounded run-ahead: the host enqueues at most `runahead` steps beyond the one the device is executing
+            step_events.append(profile.Event().record())
+            if len(step_events) > runahead:
+                step_events.pop(0).sync()
     profile.matmul_timer = None
     e1 = profile.Event().record()
     e1.sync()
     barrier()
     mm = timer.collect()
+    timed_steps = max(timed_steps, 1)
     ms_a = e1.ms_since(e0)
     launches = cuda_ops.launch_count() - launches0
     last_loss = float(loss.numpy())
@@ -439,16 +488,26 @@ def run_b200(args) -> None:
         x, y = batches[i % 4]
         loss = train_step(gpt, opt, params, Tensor(x, device="cuda"), Tensor(y, device="cuda"), world)
         _ = loss.numpy()
+        if step_times:
+            marks_b.append(profile.Event().record())
     e1 = profile.Event().record()
     e1.sync()
     barrier()
     ms_b = e1.ms_since(e0)
+    if step_times:
+        for name, start, marks in (("A", e0_a, marks_a), ("B", e0, marks_b)):
+            prev, row = start, []
+            for m in marks:
+                row.append(round(m.ms_since(prev), 2))
+                prev = m
+            print(f"[bench] rank {rank} region {name} per-step ms: {row}", file=sys.stderr, flush=True)
     io = transfer.counters()
-    if not clocks.rows:                               # a very short run: keep the load up until one sample exists
+    if rank == 0 and not clocks.rows:                 # a very short run: keep the load up until one sample exists
         t_end = time.perf_counter() + 1.5
         fill = Tensor(np.ones((2048, 2048), dtype=np.float32), device="cuda")
         while not clocks.rows and time.perf_counter() < t_end:      # rank-local load only: no collective in here
             _ = float((fill @ fill).sum().numpy())
+    clocks.active = False
     clocks.__exit__(None, None, None)
 
     replicas_identical = None

@@ -1465,8 +1465,7 @@ extern "C" __global__ void __launch_bounds__(256) {KNAME}{SIG_ALIAS} {{
     return Kernel("pack_multi", src, (acc, 1, 1), (256, 1, 1), 0, 0)
 
 
-def dp_adam(world: int, shard_vecs: int, beta1: float, beta2: float, eps: float, timeout_s: float = 20.0,
-            barriers: bool = True, ctas: int = 0) -> Kernel:
+def dp_adam(world: int, shard_vecs: int, beta1: float, beta2: float, eps: float, timeout_s: float = 20.0) -> Kernel:
     """Data-parallel optimizer step as ONE kernel per rank over NVLink peer memory: reduce-scatter of the gradients
     (P2P loads), Adam on this rank's 1/world shard, all-gather of the updated parameters (P2P stores).  It replaces
     ncclAllReduce(grads) + adam_multi ("fused with its collective").
@@ -1481,12 +1480,7 @@ def dp_adam(world: int, shard_vecs: int, beta1: float, beta2: float, eps: float,
     Element i of the shard is sum_{r = 0..world-1} grad_r[i] in RANK ORDER on every rank, and only the owner computes
     the update, so all replicas receive bit-identical parameters (NCCL's ring order differs per rank count).  The
     per-element arithmetic after the sum is adam_multi's.  Flags are epochs: they only grow, nothing is reset.  A rank
-    that waits longer than `timeout_s` for a peer traps — a dead peer must fail loudly, not hang the node.
-
-    `barriers=False` is the per-bucket form of the overlapped exchange (distributed.Adam): the two cross-rank barriers
-    are stream operations around the launch (dp_signal + a stream wait on this rank's counter), the table holds the
-    bucket's own base addresses, and `ctas` bounds the grid — the kernel runs on the comm stream next to the backward
-    of earlier layers, so it should saturate NVLink, not the SMs."""
+    that waits longer than `timeout_s` for a peer traps — a dead peer must fail loudly, not hang the node."""
     W = world
     b1, b2, e_ = _flit(beta1), _flit(beta2), _flit(eps)
     omb1, omb2 = _flit(1.0 - beta1), _flit(1.0 - beta2)
@@ -1500,33 +1494,7 @@ def dp_adam(world: int, shard_vecs: int, beta1: float, beta2: float, eps: float,
               p.{c} = __fsub_rn(p.{c}, __fmul_rn(__fdiv_rn(mh, __fadd_rn(__fsqrt_rn(vh), {e_})), f2));
               m.{c} = mn; v.{c} = vn; }}""")
     THREADS = 512
-    grid = max(1, min(ctas or 2 * NUM_SMS, _cdiv(shard_vecs, THREADS)))
-    bar_a = f"""
-    // ---- every rank's gradients are complete (its kernel has started, i.e. its backward has finished) ----
-    if (blockIdx.x == 0u && threadIdx.x < {W}u) {{
-        __threadfence_system();
-        st_release_sys(reinterpret_cast<unsigned*>(tab[{2 * W}u + threadIdx.x]) + rank, e);
-    }}
-    if (threadIdx.x < {W}u) wait_epoch(sync + threadIdx.x, e);
-    __syncthreads();
-""" if barriers else "    __syncthreads();\n"
-    bar_b = f"""
-    // ---- this rank's shard is stored everywhere; leave only when every other shard has arrived here ----
-    __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x == 0u) {{
-        __threadfence_system();
-        if (atomicAdd(sync + {2 * W + 1}, 1u) == gridDim.x - 1u) {{          // last CTA of this rank
-            sync[{2 * W + 1}] = 0u;
-            for (unsigned r = 0; r < {W}u; ++r)
-                st_release_sys(reinterpret_cast<unsigned*>(tab[{2 * W}u + r]) + {W}u + rank, e);
-            for (unsigned r = 0; r < {W}u; ++r) wait_epoch(sync + {W}u + r, e);
-            *reinterpret_cast<volatile unsigned*>(sync + {2 * W}) = e;
-            __threadfence();
-        }}
-    }}
-""" if barriers else ""
-    epoch = f"const unsigned e = *reinterpret_cast<volatile unsigned*>(sync + {2 * W}) + 1u;     // this step's epoch" if barriers else "(void)sync;"
+    grid = max(1, min(2 * NUM_SMS, _cdiv(shard_vecs, THREADS)))
     src = f"""
 __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {{
     unsigned v; asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
@@ -1548,10 +1516,18 @@ extern "C" __global__ void __launch_bounds__({THREADS}) {KNAME}{SIG_ALIAS} {{
     const unsigned long long* tab = reinterpret_cast<const unsigned long long*>(p0);
     unsigned* sync = reinterpret_cast<unsigned*>(p3);
     const unsigned rank = (unsigned)tab[{3 * W}];
-    {epoch}
+    const unsigned e = *reinterpret_cast<volatile unsigned*>(sync + {2 * W}) + 1u;     // this step's epoch
     __shared__ unsigned long long s_tab[{2 * W}];
     if (threadIdx.x < {2 * W}u) s_tab[threadIdx.x] = tab[threadIdx.x];
-{bar_a}
+
+    // ---- every rank's gradients are complete (its kernel has started, i.e. its backward has finished) ----
+    if (blockIdx.x == 0u && threadIdx.x < {W}u) {{
+        __threadfence_system();
+        st_release_sys(reinterpret_cast<unsigned*>(tab[{2 * W}u + threadIdx.x]) + rank, e);
+    }}
+    if (threadIdx.x < {W}u) wait_epoch(sync + threadIdx.x, e);
+    __syncthreads();
+
     // ---- reduce-scatter (peer loads) -> Adam on the shard -> all-gather (peer stores) ----
     float4* M = reinterpret_cast<float4*>(p1);
     float4* V = reinterpret_cast<float4*>(p2);
@@ -1575,9 +1551,104 @@ extern "C" __global__ void __launch_bounds__({THREADS}) {KNAME}{SIG_ALIAS} {{
         for (unsigned r = 0; r < {W}u; ++r)
             reinterpret_cast<float4*>(s_tab[{W}u + r])[base + i] = p;
     }}
-{bar_b}}}
+
+    // ---- this rank's shard is stored everywhere; leave only when every other shard has arrived here ----
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0u) {{
+        __threadfence_system();
+        if (atomicAdd(sync + {2 * W + 1}, 1u) == gridDim.x - 1u) {{          // last CTA of this rank
+            sync[{2 * W + 1}] = 0u;
+            for (unsigned r = 0; r < {W}u; ++r)
+                st_release_sys(reinterpret_cast<unsigned*>(tab[{2 * W}u + r]) + {W}u + rank, e);
+            for (unsigned r = 0; r < {W}u; ++r) wait_epoch(sync + {W}u + r, e);
+            *reinterpret_cast<volatile unsigned*>(sync + {2 * W}) = e;
+            __threadfence();
+        }}
+    }}
+}}
 """
-    return Kernel("dp_adam" if barriers else "dp_adam_bucket", src, (grid, 1, 1), (THREADS, 1, 1), 0, 0)
+    return Kernel("dp_adam", src, (grid, 1, 1), (THREADS, 1, 1), 0, 0)
+
+
+def _adam_body(beta1: float, beta2: float, eps: float) -> str:
+    b1, b2, e_ = _flit(beta1), _flit(beta2), _flit(eps)
+    omb1, omb2 = _flit(1.0 - beta1), _flit(1.0 - beta2)
+    body = []
+    for c in "xyzw":
+        body.append(f"""
+            {{ const float gg = __fmul_rn(g.{c}, f3);
+              const float mn = __fadd_rn(__fmul_rn(m.{c}, {b1}), __fmul_rn(gg, {omb1}));
+              const float vn = __fadd_rn(__fmul_rn(v.{c}, {b2}), __fmul_rn(__fmul_rn(gg, gg), {omb2}));
+              const float mh = __fdiv_rn(mn, f0), vh = __fdiv_rn(vn, f1);
+              p.{c} = __fsub_rn(p.{c}, __fmul_rn(__fdiv_rn(mh, __fadd_rn(__fsqrt_rn(vh), {e_})), f2));
+              m.{c} = mn; v.{c} = vn; }}""")
+    return "".join(body)
+
+
+def dp_adam_bucket(world: int, shard_vecs: int, beta1: float, beta2: float, eps: float, threads: int = 128,
+                   unroll: int = 0) -> Kernel:
+    """dp_adam for ONE exchange bucket of the overlapped schedule (distributed.Adam): the same reduce-scatter (peer
+    loads, summed in rank order) + Adam on the shard + all-gather (peer stores), same per-element arithmetic, without
+    the in-kernel barriers — the cross-rank arrivals are stream operations around the launch (dp_signal + a stream
+    wait on this rank's counter).  p0 is the BUCKET's table ([W] gradient bases, [W] parameter bases, [W] flag
+    blocks, rank), p1 / p2 the bucket's slice of the sharded moments.
+
+    Shaped to run NEXT TO the backward of earlier layers, whose persistent tensor-core kernels own one CTA per SM:
+    many small short-lived CTAs (128 threads, `unroll` float4 per thread, no grid-stride loop) that fit into the
+    registers a GEMM CTA leaves free, each with `world x unroll` 16-byte loads in flight per thread so that the
+    ~150 resident CTAs keep NVLink busy; a kernel that needs the whole register file (flash attention) waits for at
+    most one such CTA, a few microseconds, not for the exchange."""
+    W = world
+    U = unroll or max(1, 8 // W)
+    chunk = threads * U
+    grid = max(1, _cdiv(shard_vecs, chunk))
+    src = f"""
+extern "C" __global__ void __launch_bounds__({threads}) {KNAME}{SIG_ALIAS} {{
+    const unsigned long long* tab = reinterpret_cast<const unsigned long long*>(p0);
+    const unsigned rank = (unsigned)__ldg(tab + {3 * W});
+    // no shared memory at all: a GEMM CTA of the backward leaves ~1.5 KB of the SM's 228 KB free, and a CTA of this kernel
+    // must fit next to it (the 1 KB the system reserves per CTA is all it may take); the 2W table words come through L1
+    unsigned long long s_tab[{2 * W}];
+    #pragma unroll
+    for (unsigned r = 0; r < {2 * W}u; ++r) s_tab[r] = __ldg(tab + r);
+    const float4* own = reinterpret_cast<const float4*>(__ldg(tab + {W}u + rank));
+    float4* M = reinterpret_cast<float4*>(p1);
+    float4* V = reinterpret_cast<float4*>(p2);
+    const size_t base = (size_t)rank * {shard_vecs}u;
+    const unsigned i0 = blockIdx.x * {chunk}u + threadIdx.x;
+    float4 gr[{U}][{W}];
+    #pragma unroll
+    for (unsigned u = 0; u < {U}u; ++u) {{
+        const unsigned i = i0 + u * {threads}u;
+        if (i < {shard_vecs}u) {{
+            #pragma unroll
+            for (unsigned r = 0; r < {W}u; ++r)
+                gr[u][r] = __ldcg(reinterpret_cast<const float4*>(s_tab[r]) + base + i);
+        }}
+    }}
+    #pragma unroll
+    for (unsigned u = 0; u < {U}u; ++u) {{
+        const unsigned i = i0 + u * {threads}u;
+        if (i < {shard_vecs}u) {{
+            float4 p = __ldcg(own + base + i);
+            float4 m = M[i], v = V[i];
+            float4 g = gr[u][0];
+            #pragma unroll
+            for (unsigned r = 1; r < {W}u; ++r) {{
+                g.x = __fadd_rn(g.x, gr[u][r].x); g.y = __fadd_rn(g.y, gr[u][r].y);
+                g.z = __fadd_rn(g.z, gr[u][r].z); g.w = __fadd_rn(g.w, gr[u][r].w);
+            }}
+            {_adam_body(beta1, beta2, eps)}
+            M[i] = m; V[i] = v;
+            #pragma unroll
+            for (unsigned r = 0; r < {W}u; ++r)
+                reinterpret_cast<float4*>(s_tab[{W}u + r])[base + i] = p;
+        }}
+    }}
+}}
+"""
+    return Kernel("dp_adam_bucket", src, (grid, 1, 1), (threads, 1, 1), 0, 0)
 
 
 def dp_signal(world: int) -> Kernel:

@@ -384,12 +384,18 @@ int dlg_init(int device) {
     CU(cuDeviceGet(&g_cudev, device));
     CU(cuDevicePrimaryCtxRetain(&g_ctx, g_cudev));
     CU(cuCtxSetCurrent(g_ctx));
-    CU(cuStreamCreate(&g_stream, CU_STREAM_NON_BLOCKING));
     {
-        // the comm stream outranks the compute stream: exchange kernels are few, short CTAs that should take the first free slots
-        int lo = 0, hi = 0;
-        if (drv.p_cuCtxGetStreamPriorityRange(&lo, &hi) != CUDA_SUCCESS) hi = 0;
-        CU(cuStreamCreateWithPriority(&g_comm_stream, CU_STREAM_NON_BLOCKING, hi));
+        // The compute stream outranks the comm stream.  The compute kernels are persistent — one CTA per SM for the whole
+        // kernel — so a compute CTA that cannot become resident doubles its kernel's time; the exchange kernels of the
+        // overlapped data-parallel step are many small CTAs that fill the registers a GEMM CTA leaves free.  With
+        // this order a pending compute CTA always goes first and waits for at most one short exchange CTA.
+        // (DLGRAD_COMM_PRIORITY=high reverses it, for measurements.)
+        int least = 0, greatest = 0;
+        if (drv.p_cuCtxGetStreamPriorityRange(&least, &greatest) != CUDA_SUCCESS) least = greatest = 0;
+        const char *e = getenv("DLGRAD_COMM_PRIORITY");
+        const bool comm_high = e && e[0] == 'h';
+        CU(cuStreamCreateWithPriority(&g_stream, CU_STREAM_NON_BLOCKING, comm_high ? least : greatest));
+        CU(cuStreamCreateWithPriority(&g_comm_stream, CU_STREAM_NON_BLOCKING, comm_high ? greatest : least));
     }
     CU(cuEventCreate(&g_ev_compute, CU_EVENT_DISABLE_TIMING));
     CU(cuEventCreate(&g_ev_comm, CU_EVENT_DISABLE_TIMING));

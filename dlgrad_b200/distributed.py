@@ -34,10 +34,11 @@ _state = {"rank": 0, "world": 1, "bucket": None, "bucket_elems": 0}
 # rank that evaluates, writes a checkpoint or JIT-compiles a cold kernel may legitimately be minutes late.
 PEER_TIMEOUT_S = float(os.environ.get("DLGRAD_DP_TIMEOUT_S", "600"))
 # the overlapped schedule of distributed.Adam: exchange buckets of ~BUCKET_MB as backward finishes them, on the comm
-# stream, with COMM_CTAS thread blocks per exchange kernel (enough loads in flight for NVLink, few enough SM slots)
+# stream, by small short-lived CTAs (COMM_THREADS threads, COMM_UNROLL float4 each) that fit next to a GEMM CTA
 OVERLAP = os.environ.get("DLGRAD_DP_OVERLAP", "1") != "0"
 BUCKET_MB = float(os.environ.get("DLGRAD_DP_BUCKET_MB", "25"))
-COMM_CTAS = int(os.environ.get("DLGRAD_DP_CTAS", "64"))
+COMM_THREADS = int(os.environ.get("DLGRAD_DP_THREADS", "128"))
+COMM_UNROLL = int(os.environ.get("DLGRAD_DP_UNROLL", "0"))          # 0: 8 // world float4 per thread
 
 
 def unique_id() -> bytes:
@@ -137,7 +138,7 @@ def prebuild(sizes: list[int], worlds: tuple = (2, 4, 8), betas: tuple = (0.9, 0
         kernels = [ck.dp_adam(w, shard // 4, betas[0], betas[1], eps, PEER_TIMEOUT_S), ck.pack_multi(tuple(sizes), tuple(offs)),
                    ck.dp_signal(w), ck.dp_wait(PEER_TIMEOUT_S)]
         for b in plan_buckets(sizes, w, max(1, int(mb * (1 << 20)) // 4)):
-            kernels.append(ck.dp_adam(w, b["shard"] // 4, betas[0], betas[1], eps, PEER_TIMEOUT_S, barriers=False, ctas=COMM_CTAS))
+            kernels.append(ck.dp_adam_bucket(w, b["shard"] // 4, betas[0], betas[1], eps, COMM_THREADS, COMM_UNROLL))
             kernels.append(ck.pack_multi(tuple(sizes[i] for i in b["params"]), tuple(b["offs"])))
         for k in kernels:
             compiler.get_function(k.name, k.source)
@@ -374,8 +375,8 @@ class Adam:
             tab = np.array([a + 4 * b["start"] for a in self.grads.addr] + [a + 4 * b["start"] for a in self.weights.addr]
                            + self.flags.addr + [_state["rank"]], dtype=np.uint64)
             b["table"] = transfer.upload(ffi.from_buffer("char *", tab), tab.nbytes)
-            b["adam"] = cuda_ops.Plan(ck.dp_adam(world, b["shard"] // 4, self.beta1, self.beta2, self.eps, PEER_TIMEOUT_S,
-                                                 barriers=False, ctas=COMM_CTAS))
+            b["adam"] = cuda_ops.Plan(ck.dp_adam_bucket(world, b["shard"] // 4, self.beta1, self.beta2, self.eps, COMM_THREADS,
+                                                        COMM_UNROLL))
             b["pack"] = cuda_ops.Plan(ck.pack_multi(tuple(self.sizes[i] for i in b["params"]), tuple(b["offs"])))
             nb = len(b["params"])
             b["host"] = lib.dlg_host_alloc(8 * nb)
