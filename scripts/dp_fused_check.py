@@ -25,6 +25,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 STEPS = 4
 LR, BETAS, EPS = 1e-3, (0.9, 0.999), 1e-8
+OVERLAP = os.environ.get("DLGRAD_DP_OVERLAP", "0") == "1"      # which schedule of distributed.Adam is checked
 BUCKET_MB = 0.25          # several exchange buckets for a 0.43 M parameter model: steps 2.. overlap with backward
 
 
@@ -63,7 +64,7 @@ def main() -> int:
     flat = lambda tensors: np.concatenate([t.numpy().reshape(-1) for t in tensors])     # noqa: E731
     ref_p = flat(plist[0]).copy()
     ref_m, ref_v = np.zeros_like(ref_p), np.zeros_like(ref_p)
-    fused = distributed.Adam(plist[0], lr=LR, betas=BETAS, eps=EPS, bucket_mb=BUCKET_MB)
+    fused = distributed.Adam(plist[0], lr=LR, betas=BETAS, eps=EPS, overlap=OVERLAP, bucket_mb=BUCKET_MB)
     plain = nn.optim.Adam(plist[1], lr=LR, betas=BETAS, eps=EPS)
     plain.grad_scale = 1.0 / world
     rng = np.random.default_rng(100 + rank)

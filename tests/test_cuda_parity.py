@@ -930,7 +930,7 @@ def test_overlapped_dp_adam_trains_bit_identically_to_adam():
     cfg = models.GPTConfig(vocab_size=96, block_size=64, n_layer=3, n_head=4, n_embd=128, device="cuda")
     nets = [models.GPT(dl, cfg, np.random.default_rng(0)) for _ in range(2)]
     plist = [nn.utils.get_parameters(n) for n in nets]
-    opts = [nn.optim.Adam(plist[0], lr=1e-3), distributed.Adam(plist[1], lr=1e-3, bucket_mb=0.3)]
+    opts = [nn.optim.Adam(plist[0], lr=1e-3), distributed.Adam(plist[1], lr=1e-3, overlap=True, bucket_mb=0.3)]
     assert len(opts[1].buckets) >= 4
     rng = np.random.default_rng(3)
     early = []
@@ -961,10 +961,12 @@ def test_overlapped_dp_adam_trains_bit_identically_to_adam():
 
 
 @pytest.mark.timeout(600)
-def test_fused_dp_step_across_two_gpus():
-    """The multi-rank exchange itself (peer-memory mapping, the two cross-GPU barriers, rank-ordered sums): two ranks
-    under torchrun run scripts/dp_fused_check.py, which demands bit-identity with a float32 restatement of the
-    schedule and with ncclAllReduce + Adam.  Skipped on a single-GPU box."""
+@pytest.mark.parametrize("overlap", ["0", "1"])
+def test_fused_dp_step_across_two_gpus(overlap):
+    """The multi-rank exchange itself (peer-memory mapping, the cross-GPU barriers / arrivals, rank-ordered sums): two
+    ranks under torchrun run scripts/dp_fused_check.py, which demands bit-identity with a float32 restatement of the
+    schedule and with ncclAllReduce + Adam — for the monolithic kernel and for the bucketed exchange that overlaps
+    with backward.  Skipped on a single-GPU box."""
     import socket
     import subprocess
     import sys
@@ -977,7 +979,7 @@ def test_fused_dp_step_across_two_gpus():
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
                           "--master-addr", "127.0.0.1", "--master-port", str(port), "scripts/dp_fused_check.py"],
-                         cwd=root, capture_output=True, text=True, timeout=500)
+                         cwd=root, capture_output=True, text=True, timeout=500, env=dict(os.environ, DLGRAD_DP_OVERLAP=overlap))
     assert res.returncode == 0 and "PASS" in res.stdout, res.stdout[-2000:] + res.stderr[-2000:]
 
 

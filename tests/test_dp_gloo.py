@@ -143,7 +143,7 @@ from tests import models
 cfg = models.GPTConfig(vocab_size=96, block_size=32, n_layer=3, n_head=2, n_embd=32, device="cuda")
 gpt = models.GPT(dl, cfg, np.random.default_rng(0))
 params = nn.utils.get_parameters(gpt)
-opt = distributed.Adam(params, lr=1e-3, bucket_mb=0.02)
+opt = distributed.Adam(params, lr=1e-3, overlap=True, bucket_mb=0.02)
 assert len(opt.buckets) >= 4, len(opt.buckets)
 x, y = models.gpt_batch(cfg, 2, np.random.default_rng(1))
 log = []
