@@ -349,6 +349,11 @@ class Buffer:
         if self._pending is not None and self._pending[0] == "relu":
             # a pointwise producer commutes with reshape: stay deferred (Linear flattens its input before the GEMM)
             return Buffer._deferred(("relu", self._pending[1].reshape(new_shape)), new_shape, self.metadata.dtype)
+        if self._pending is not None and self._pending[0] == "lin" and new_shape[-1] != self.metadata.shape[-1]:
+            # a head split (B, T, C) -> (B, T, h, d) of a deferred projection, examples/gpt.py:43-45.  The GEMM's result is the
+            # same storage under any shape: the view stays deferred and shares the producer's slot, so that the sibling
+            # projections created right after it can still join one grouped launch (whichever Buffer is read first runs it)
+            return Buffer._deferred(self._pending, new_shape, self.metadata.dtype)
         view = Buffer(self.ptr, new_shape, self.metadata.device, self.metadata.dtype,
                       scalar=self.scalar, aligned=self.aligned, keep=self._keep)
         if self._const is not None:
@@ -439,7 +444,7 @@ class Buffer:
             # consumer materialises it through `.ptr` with the permute kernel.
             if pend is not None and pend[0] == "hsplit" and pend[1].shape == out_shape:
                 return pend[1]
-            if pend is None and self.numel >= LAZY_MIN_NUMEL and HSPLIT_DEFER and self.aligned:
+            if (pend is None or pend[0] == "lin") and self.numel >= LAZY_MIN_NUMEL and HSPLIT_DEFER and self.aligned:
                 return Buffer._deferred(("hsplit", self), out_shape, self.metadata.dtype)
         if pend is not None and pend[0] == "tr":
             # permuting a deferred transpose: one kernel over the stored operand with the composed order
@@ -603,6 +608,18 @@ class Buffer:
         if dev is _CUDA and CONST_FOLD and _operand_tag(self) is not None and _operand_tag(other) is not None:
             run = lambda: self._like(_dispatch(op=op, device=dev, x=self, y=other), out_shape, dev)  # noqa: E731
             return Buffer._folded(dev, (op.name,), (self, other), out_shape, run)
+        if (op is BinaryOps.ADD and dev is _CUDA and self._pending is not None and other._pending is not None
+                and self._pending[0] in ("lin_dx", "lin_dx_sum") and other._pending[0] in ("lin_dx", "lin_dx_sum")
+                and self.shape == other.shape):
+            # the input gradients of sibling Linear layers meet in the autograd driver's `grad + g` (dlgrad/tensor.py:805):
+            # dq @ Wq + dk @ Wk + dv @ Wv stays deferred as ONE sum of products and runs as one K-concatenated launch
+            # (codegen matmul_tc_ts, group = ("k", G)) when somebody reads it
+            pa, pb = self._pending[1:], other._pending[1:]
+            from dlgrad_b200.runtime.cuda import matmul as _mm
+            if (_mm.GROUP_LINEAR and (len(pa) + len(pb)) // 2 <= 3
+                    and all(g.metadata.shape == pa[0].metadata.shape for g in (pa + pb)[0::2])
+                    and all(w.metadata.shape == pa[1].metadata.shape for w in (pa + pb)[1::2])):
+                return Buffer._deferred(("lin_dx_sum",) + pa + pb, out_shape, self.dtype)
         if op is BinaryOps.ADD and dev is _CUDA and (self._pending is not None or other._pending is not None):
             # one operand is a deferred GEMM / RMSNorm gradient that can absorb this addition (runtime/cuda/ops.fused_add)
             for r, d in ((self, other), (other, self)):

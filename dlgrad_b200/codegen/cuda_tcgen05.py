@@ -741,7 +741,7 @@ def matmul_tc_ts(M: int, N: int, K: int, batch: int, a_mn: bool, b_mn: bool, a_b
                  bn: int | None = None, stages: int | None = None, kc_blocks: int | None = None,
                  bias: bool = False, issuers: int | None = None, streamk: bool = False, ksparse: str | None = None,
                  a_relu: bool = False, b_relu: bool = False, splitk: int = 0,
-                 relu_mask: bool = False, hsplit: int = 0, radd: bool = False) -> TcKernel:
+                 relu_mask: bool = False, hsplit: int = 0, radd: bool = False, group: tuple | None = None) -> TcKernel:
     """Kernel parameters after C: `bias` (a length-N row the epilogue adds to every output row when `bias` is
     set — the Linear bias; it rides on the plain store) and `flags` (uint32[ntiles * 4], zero, used when
     `streamk` is set).
@@ -777,6 +777,15 @@ def matmul_tc_ts(M: int, N: int, K: int, batch: int, a_mn: bool, b_mn: bool, a_b
     split into (z % H, z / H): dq = dS @ k and dk = dS^T @ q then read k, q and write their results in place of the
     head split / merge permutes of examples/gpt.py:46-48.
 
+    group = ("n", G): G sibling products  C_g = A @ B_g  that share the A operand — the q / k / v projections of one attention
+    block (examples/gpt.py:43-45: three Linear layers applied to the same normed x) — as ONE persistent launch: called with
+    batch = G and a_bcast, the batch index z of a tile selects one of G B tensor maps and one of G C tensor maps (separate
+    allocations, nothing is copied or concatenated), so three launches of 2.59 tile waves each become one of 7.8.
+    group = ("k", G): the sum of G products  C = sum_g A_g @ B_g  — the input gradient of those three layers,
+    dq @ Wq + dk @ Wk + dv @ Wv — as ONE launch with the k loop running through the G operand pairs (K = G x K_g): the
+    k-block index selects the A and B tensor maps, the accumulator in tensor memory carries the sum, and the two ADD passes
+    (or add epilogues) disappear.
+
     ksparse ("nn" | "tn"): the A operand is an attention matrix (P or dS, query rows x key columns; "tn" = it is read
     transposed) whose 128 x 128 tiles that the mask kills entirely are exactly zero.  `flags` then points at the
     live-tile table of cuda_kernel.mask_bits ([query tiles][key tiles], then one word per query row, then the number
@@ -794,6 +803,18 @@ def matmul_tc_ts(M: int, N: int, K: int, batch: int, a_mn: bool, b_mn: bool, a_b
     TR = (lambda kind, cond="true": stamp(kind, cond)) if tmode == "1" else (lambda *a: "")
     TM = (lambda kind, cond="lane == 0u": stamp(kind, cond)) if tmode == "2" else (lambda *a: "")
     kblocks = _cdiv(K, BK)
+    gmode, G = group if group else (None, 1)
+    if gmode:
+        assert 2 <= G <= 3 and not (streamk or ksparse or splitk or relu_mask or hsplit or bias), group
+        if gmode == "n":
+            assert batch == G and a_bcast and not b_bcast and not radd
+        else:
+            assert gmode == "k" and batch == 1 and K % (G * BK) == 0
+    kbg = kblocks // G if gmode == "k" else kblocks           # k-blocks per operand pair
+
+    def sel(name, idx):
+        """Address of tensor map `name` number `idx` (a runtime 0..G-1): the maps are separate __grid_constant__ parameters."""
+        return f"({idx} == 0u ? &tm{name} : " + (f"&tm{name}1)" if G == 2 else f"({idx} == 1u ? &tm{name}1 : &tm{name}2))")
     kc = kc_blocks or (32 if kblocks > 64 else kblocks)       # K chunks of <= 1024, see matmul_tc_persistent
     nchunks = _cdiv(kblocks, kc)
     BN = bn or pick_bn_ts(M, N, batch, kblocks)
@@ -877,6 +898,14 @@ def matmul_tc_ts(M: int, N: int, K: int, batch: int, a_mn: bool, b_mn: bool, a_b
     def tma_issue(which, boxes, mn, tile_var, row0):
         tm = f"tm{which}"
         z = "0" if (a_bcast if which == "A" else b_bcast) else "z"
+        if (gmode == "n" and which == "B") or gmode == "k":
+            # grouped launch: the map was selected by the tile's batch index ("n") or the k-block's operand pair ("k")
+            tmp = f"tm{which}g"
+            if mn:
+                return "\n                    ".join(
+                    f"tma_load_3d({tile_var} + {j * 4096}u, {tmp}, full_bar, (int)({row0} + {j * 32}u), (int)k0, 0);"
+                    for j in range(boxes))
+            return f"tma_load_3d({tile_var}, {tmp}, full_bar, (int)k0, (int){row0}, 0);"
         if hsplit and which == "B":
             zz = f"(int)(z % {hsplit}u), (int)(z / {hsplit}u)"
             if mn:
@@ -1055,7 +1084,10 @@ def matmul_tc_ts(M: int, N: int, K: int, batch: int, a_mn: bool, b_mn: bool, a_b
     else:
         sk_seg_begin, sk_seg_end = "const bool seg_head = false;", ""
     CSTORE = (f"tma_store_4d(&tmC, my_epi + sb * 4096u, (int)(n0 + c * 32u), (int)(m0 + q * 32u), (int)(z % {hsplit}u), (int)(z / {hsplit}u));"
-              if hsplit else "tma_store_3d(&tmC, my_epi + sb * 4096u, (int)(n0 + c * 32u), (int)(m0 + q * 32u), (int)z);")
+              if hsplit else "tma_store_3d(tmCg, my_epi + sb * 4096u, (int)(n0 + c * 32u), (int)(m0 + q * 32u), 0);" if gmode == "n"
+              else "tma_store_3d(&tmC, my_epi + sb * 4096u, (int)(n0 + c * 32u), (int)(m0 + q * 32u), (int)z);")
+    CADD = ("tma_reduce_add_3d(tmCg, my_epi + sb * 4096u, (int)(n0 + c * 32u), (int)(m0 + q * 32u), 0);" if gmode == "n"
+            else "tma_reduce_add_3d(&tmC, my_epi + sb * 4096u, (int)(n0 + c * 32u), (int)(m0 + q * 32u), (int)z);")
     zero_tile = "" if not ksparse else f"""if (lk == 0u) {{
                     // every k-block of this output tile lies in a dead attention tile: the product is exactly zero
                     #pragma unroll 1
@@ -1086,9 +1118,11 @@ def matmul_tc_ts(M: int, N: int, K: int, batch: int, a_mn: bool, b_mn: bool, a_b
         f"make_float4(__uint_as_float(v[{4 * j}]), __uint_as_float(v[{4 * j + 1}]), __uint_as_float(v[{4 * j + 2}]), __uint_as_float(v[{4 * j + 3}]));"
         for j in range(8))
 
+    extra = [f"tmB{g}" for g in range(1, G)] + [f"tm{'C' if gmode == 'n' else 'A'}{g}" for g in range(1, G)] if gmode else []
+    gparams = "".join(f"const __grid_constant__ TMap {n}, " for n in extra)
     src = _HELPERS + _HELPERS_TS + f"""
 extern "C" __global__ void __launch_bounds__({nthreads}, 1)
-{KNAME}(const __grid_constant__ TMap tmA, const __grid_constant__ TMap tmB, const __grid_constant__ TMap tmC, float* __restrict__ C, const float* __restrict__ bias, unsigned* __restrict__ flags)
+{KNAME}(const __grid_constant__ TMap tmA, const __grid_constant__ TMap tmB, const __grid_constant__ TMap tmC, {gparams}float* __restrict__ C, const float* __restrict__ bias, unsigned* __restrict__ flags)
 {{
     extern __shared__ unsigned char smem_raw[];
     const unsigned smem = (smem_u32(smem_raw) + 1023u) & ~1023u;        // swizzle atoms need 1024-byte alignment
@@ -1139,7 +1173,8 @@ extern "C" __global__ void __launch_bounds__({nthreads}, 1)
                     {TR(0, "lane == 0u")}
                     const unsigned full_bar = full + s * 8u;
                     const unsigned a_s = smem + s * {per_stage}u, b_s = a_s + {a_tile}u;
-                    const unsigned k0 = kb * {BK}u;
+                    {f"const unsigned kg = kb / {kbg}u, k0 = (kb - kg * {kbg}u) * {BK}u; const TMap* tmAg = {sel('A', 'kg')}; const TMap* tmBg = {sel('B', 'kg')};" if gmode == "k" else f"const unsigned k0 = kb * {BK}u;"}
+                    {f"const TMap* tmBg = {sel('B', 'z')};" if gmode == "n" else ""}
                     if (elect_one()) {{
                         mbar_expect_tx(full_bar, {a_tile + b_tile}u);
                         {tma_issue("A", a_boxes, a_mn, "a_s", "m0")}
@@ -1262,6 +1297,7 @@ extern "C" __global__ void __launch_bounds__({nthreads}, 1)
         unsigned ua = 0, nstore = 0;
         {seg_open}
             {decode}
+            {f"const TMap* tmCg = {sel('C', 'z')};" if gmode == "n" else ""}
             {sk_seg_begin}
             for (unsigned cs = kb0; cs < kb1; cs += {kc}u, ++ua) {{
                 {zero_tile}
@@ -1287,7 +1323,7 @@ extern "C" __global__ void __launch_bounds__({nthreads}, 1)
                         __syncwarp();
                         if (lane == 0) {{
                             if (plain) {{ {CSTORE} }}
-                            else tma_reduce_add_3d(&tmC, my_epi + sb * 4096u, (int)(n0 + c * 32u), (int)(m0 + q * 32u), (int)z);
+                            else {CADD}
                             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                         }}
                         ++nstore;
@@ -1310,7 +1346,7 @@ extern "C" __global__ void __launch_bounds__({nthreads}, 1)
     }}
 }}
 """
-    return TcKernel("mm_tcts" + ("_b" if bias else "") + ("_sk" if streamk else "") + (f"_sp{ksparse}" if ksparse else "") + ("_ra" if a_relu else "") + ("_rb" if b_relu else "") + (f"_k{splitk}" if splitk > 1 else "") + ("_rm" if relu_mask else "") + ("_hs" if hsplit else "") + ("_ra2" if radd else ""), src, (grid, 1, 1), nthreads, smem, batch * M * N, BN, stages)
+    return TcKernel("mm_tcts" + ("_b" if bias else "") + ("_sk" if streamk else "") + (f"_sp{ksparse}" if ksparse else "") + ("_ra" if a_relu else "") + ("_rb" if b_relu else "") + (f"_k{splitk}" if splitk > 1 else "") + ("_rm" if relu_mask else "") + ("_hs" if hsplit else "") + ("_ra2" if radd else "") + (f"_g{gmode}{G}" if gmode else ""), src, (grid, 1, 1), nthreads, smem, batch * M * N, BN, stages)
 
 
 # =====================================================================================================

@@ -484,7 +484,10 @@ class Linear(OP):
             # deferred (Buffer pending kind "lin"): when the consumer is an addition — the residual connection
             # `x + proj(h)`, examples/gpt.py:88-89 — the GEMM runs with the add in its epilogue (matmul_tc_ts `radd`) and
             # the three-pass ADD kernel disappears; every other consumer materialises it through `.ptr`
-            return Buffer._deferred(("lin", x2, weight), x.shape[:-1] + (out_f,), x.dtype)
+            # ... and when sibling layers read the same input — the q / k / v projections, examples/gpt.py:43-45 — the
+            # first one that is needed runs all of them as ONE grouped launch (runtime/cuda/matmul.LinSlot)
+            from dlgrad_b200.runtime.cuda import matmul as _mm
+            return Buffer._deferred(("lin", x2, weight, _mm.lin_slot(x2, weight)), x.shape[:-1] + (out_f,), x.dtype)
         y = dispatcher.dispatch(op=BinaryOps.MATMUL, device=Device.CUDA, x=x2, y=weight, trans_y=True)
         out = Buffer(y, x.shape[:-1] + (out_f,), Device.CUDA, x.dtype)
         return out if bias is None else out + bias

@@ -75,7 +75,13 @@ def _mask_digest(mask: Buffer, Tq: int, Tk: int):
 
 def _stored(b: Buffer) -> bool:
     """materialised, or a deferred head split / merge of a materialised buffer (read in place through strided tensor maps)"""
-    return b._pending is None or (b._pending[0] == "hsplit" and b._pending[1]._pending is None)
+    pend = b._pending
+    if pend is not None and pend[0] == "hsplit":
+        src = pend[1]
+        if src._pending is not None and src._pending[0] == "lin":
+            _ = src.ptr        # a deferred projection under the head split: it runs now, as one launch with its siblings
+        return src._pending is None
+    return pend is None
 
 
 def eligible(x: Buffer, y: Buffer) -> bool:

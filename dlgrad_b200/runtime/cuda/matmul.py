@@ -9,6 +9,7 @@ MatMul.backward so that g @ B^T and A^T @ g need no materialised transpose.
 from __future__ import annotations
 
 import os
+import weakref
 
 from dlgrad_b200.buffer import Buffer
 from dlgrad_b200.codegen import cuda_kernel as ck
@@ -298,3 +299,132 @@ class MatmulPlan:
 
     def __call__(self, *operands):
         return self.fn(*operands)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# sibling Linear layers over one input: one grouped launch
+# ---------------------------------------------------------------------------------------------------------
+GROUP_LINEAR = os.environ.get("DLGRAD_GROUP_LINEAR", "1") != "0"
+
+
+class LinSlot:
+    """Result cell of one deferred Linear output `x2 @ w^T` (Buffer pending kind "lin").  Every Buffer that carries the
+    pending tuple — the output itself and deferred reshapes of it — resolves through the slot, so the product runs once.
+    Slots of consecutive Linear calls on the SAME stored input with equally shaped weights form a group (the q / k / v
+    projections of an attention block, examples/gpt.py:43-45); the first member that is needed computes every member
+    that is still open with one grouped tensor-core launch (codegen matmul_tc_ts, group = ("n", G)).
+    The group list holds WEAK references: a slot keeps its output storage alive, and a slot <-> list cycle would leave
+    25 MB activations to the cyclic garbage collector instead of the reference count."""
+    __slots__ = ("ptr", "x2", "w", "group", "__weakref__")
+
+    def __init__(self, x2: Buffer, w: Buffer) -> None:
+        self.ptr, self.x2, self.w = None, x2, w
+        self.group = [weakref.ref(self)]
+
+    def members(self) -> list:
+        return [m for m in (r() for r in self.group) if m is not None]
+
+    def leave(self) -> None:
+        self.group[:] = [r for r in self.group if r() is not self and r() is not None]
+        self.group = [weakref.ref(self)]
+
+
+_last_group: list = []
+
+
+def lin_slot(x2: Buffer, w: Buffer) -> LinSlot:
+    global _last_group
+    slot = LinSlot(x2, w)
+    g = [m for m in (r() for r in _last_group) if m is not None]
+    if (GROUP_LINEAR and g and len(g) < 3 and len(g) == len(_last_group) and x2._ptr is not None
+            and all(m.ptr is None for m in g) and g[0].x2._ptr is x2._ptr and g[0].x2.metadata.shape == x2.metadata.shape
+            and g[0].w.metadata.shape == w.metadata.shape and all(m.w is not w for m in g)):
+        _last_group.append(weakref.ref(slot))
+        slot.group = _last_group
+    _last_group = slot.group
+    return slot
+
+
+def run_lin_slot(slot: LinSlot):
+    """Storage of the slot's product; computes it — and its open siblings — if nobody has yet."""
+    if slot.ptr is None:
+        todo = [m for m in slot.members() if m.ptr is None]
+        outs = _grouped_linear(slot.x2, [m.w for m in todo]) if len(todo) >= 2 else None
+        if outs is not None:
+            for m, o in zip(todo, outs):
+                m.ptr = o
+        else:
+            slot.ptr = run_matmul(slot.x2, slot.w, trans_y=True)
+        for m in todo:
+            if m.ptr is not None:
+                m.x2 = m.w = None                    # the operands are not needed any more
+    return slot.ptr
+
+
+def _grouped_linear(x2: Buffer, ws: list):
+    """[x2 @ w^T for w in ws] as ONE launch, or None when the shape does not run on the tensor-core kernel."""
+    if FORCE_SIMT or x2._pending is not None or any(w._pending is not None or w.scalar is not None for w in ws):
+        return None
+    aligned = x2.aligned and all(w.aligned for w in ws)
+    G = len(ws)
+    key = (x2.metadata.shape, ws[0].metadata.shape, G, aligned, "group_n")
+    plan = _plans.get(key)
+    if plan is None and key not in _plans:
+        M, K = x2.metadata.shape
+        N = ws[0].metadata.shape[0]
+        plan = None
+        if aligned and _split_k(M, N, K, (1, 1), False, True) == 1:
+            from dlgrad_b200.runtime.cuda import matmul_tc
+            plan = matmul_tc.build_grouped("n", G, M, N, K, False, False)
+        _plans[key] = plan
+    if plan is None:
+        return None
+    args = (_ops._dev_ptr(x2), [_ops._dev_ptr(w) for w in ws])
+    timer = _profile.matmul_timer
+    if timer is None:
+        return plan(*args)
+    t0 = timer.start()
+    out = plan(*args)
+    timer.stop(t0, plan.flops, plan.tag)
+    return out
+
+
+def run_lin_dx_sum(gs: tuple, ws: tuple):
+    """sum_i gs[i] @ ws[i] — the input gradient shared by sibling Linear layers — as ONE K-concatenated tensor-core launch;
+    where the shape does not run there: the first product, then each further one with the add in its epilogue."""
+    G = len(gs)
+    if G == 1:
+        return run_matmul(gs[0], ws[0])
+    plan = None
+    ok = (not FORCE_SIMT and all(b._pending is None or b._pending[0] != "relu" for b in gs)
+          and all(w._pending is None and w.scalar is None for w in ws))
+    if ok:
+        for g in gs:
+            if g._pending is not None:
+                _ops.materialize(g)
+        aligned = all(b.aligned for b in gs + ws)
+        key = (gs[0].metadata.shape, ws[0].metadata.shape, G, aligned, "group_k")
+        plan = _plans.get(key)
+        if plan is None and key not in _plans:
+            M, K = gs[0].metadata.shape
+            N = ws[0].metadata.shape[1]
+            if aligned and len(gs[0].metadata.shape) == 2 and _split_k(M, N, K, (1, 1), False, False) == 1:
+                from dlgrad_b200.runtime.cuda import matmul_tc
+                plan = matmul_tc.build_grouped("k", G, M, N, K, False, True)
+            _plans[key] = plan
+    if plan is not None:
+        args = ([_ops._dev_ptr(g) for g in gs], [_ops._dev_ptr(w) for w in ws])
+        timer = _profile.matmul_timer
+        if timer is None:
+            return plan(*args)
+        t0 = timer.start()
+        out = plan(*args)
+        timer.stop(t0, plan.flops, plan.tag)
+        return out
+    acc = Buffer(run_matmul(gs[0], ws[0]), gs[0].metadata.shape[:-1] + (ws[0].metadata.shape[1],), gs[0].metadata.device)
+    for g, w in zip(gs[1:], ws[1:]):
+        nxt = radd_matmul(g, w, False, False, acc)
+        if nxt is None:
+            nxt = _ops.add(acc, Buffer(run_matmul(g, w), acc.metadata.shape, acc.metadata.device))
+        acc = Buffer(nxt, acc.metadata.shape, acc.metadata.device)
+    return acc.ptr

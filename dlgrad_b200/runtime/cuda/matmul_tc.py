@@ -132,3 +132,44 @@ def try_build(M, N, K, batch, a_bs, b_bs, tx, ty, aligned, passes: int | None = 
             return shim.own(out, nbytes)
     from dlgrad_b200.runtime.cuda.matmul import MatmulPlan
     return MatmulPlan(run, 2.0 * nb * M * N * K, (f"tc{passes}" + (f"_sp{ksparse}" if ksparse else "") + ("_radd" if radd else ""), M, N, K, nb))
+
+
+def build_grouped(mode: str, G: int, M: int, N: int, K: int, a_mn: bool, b_mn: bool, radd: bool = False):
+    """Plans for the grouped forms of matmul_tc_ts (separate tensor maps per member, nothing is concatenated):
+    mode "n": [A @ B_g for g < G] (K = the shared inner size) -> run(a, [b_g]) returns G output pointers;
+    mode "k": sum_g A_g @ B_g (K = inner size of ONE pair)      -> run([a_g], [b_g], r=None) returns one pointer
+    (`radd`: + r in the epilogue).  None when the tensor-core path is disabled or the shape does not qualify."""
+    if not ENABLED or PASSES != 3 or KERNEL not in ("auto", "v4"):
+        return None
+    if (M if a_mn else K) % 4 or (N if b_mn else K) % 4 or N % 4 or K < 8 or N < 8 or M < 128:
+        return None
+    from dlgrad_b200.runtime.cuda.attention import _tc_plan, _tc_run
+    if mode == "n":
+        k = tc.matmul_tc_ts(M, N, K, G, a_mn, b_mn, True, False, group=("n", G))
+        da, db, dc = tc.tmap_descs(M, N, K, 1, a_mn, b_mn, False, False, k.bn)
+        maps = [da, db, dc] + [db] * (G - 1) + [dc] * (G - 1)
+    else:
+        if K % tc.BK:
+            return None
+        k = tc.matmul_tc_ts(M, N, G * K, 1, a_mn, b_mn, False, False, radd=radd, group=("k", G),
+                            bn=(int(os.environ.get("DLGRAD_RMASK_BN", "128")) if radd and N >= 128 else None))
+        da, db, dc = tc.tmap_descs(M, N, K, 1, a_mn, b_mn, False, False, k.bn)
+        maps = [da, db, dc] + [db] * (G - 1) + [da] * (G - 1)
+    shim.init()
+    plan = _tc_plan(k, maps, 3)
+    nbytes = M * N * 4
+    NULLP = shim.NULL
+    what = f"grouped matmul ({mode}, {G})"
+
+    if mode == "n":
+        def run(a, bs):
+            outs = [shim.alloc(nbytes) for _ in range(G)]
+            _tc_run(plan, [a, bs[0], outs[0]] + list(bs[1:]) + outs[1:], [outs[0], NULLP, NULLP], what)
+            return outs
+    else:
+        def run(as_, bs, r=NULLP):
+            out = shim.alloc(nbytes)
+            _tc_run(plan, [as_[0], bs[0], out] + list(bs[1:]) + list(as_[1:]), [out, r, NULLP], what)
+            return out
+    from dlgrad_b200.runtime.cuda.matmul import MatmulPlan
+    return MatmulPlan(run, 2.0 * G * M * N * K, (f"tc{PASSES}_group_{mode}{G}" + ("_radd" if radd else ""), M, N, K, G))

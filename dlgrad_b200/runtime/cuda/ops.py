@@ -195,10 +195,15 @@ def materialize(buf: Buffer) -> None:
         buf.ptr = pend[1].relu().ptr
         return
     if pend[0] == "lin":
-        buf.ptr = matmul(pend[1], pend[2], trans_y=True)
+        from dlgrad_b200.runtime.cuda import matmul as _mm
+        buf.ptr = _mm.run_lin_slot(pend[3])
         return
     if pend[0] == "lin_dx":
         buf.ptr = matmul(pend[1], pend[2])
+        return
+    if pend[0] == "lin_dx_sum":
+        from dlgrad_b200.runtime.cuda import matmul as _mm
+        buf.ptr = _mm.run_lin_dx_sum(pend[1::2], pend[2::2])
         return
     if pend[0] == "rms_dx":
         buf.ptr = ewise3("rms_dx", "(v0 * v1) * v2", buf.metadata.shape, [pend[1], pend[2], pend[3]])
@@ -988,6 +993,10 @@ def fused_add(r: Buffer, d: Buffer):
     if pend[0] in ("lin", "lin_dx"):
         from dlgrad_b200.runtime.cuda import matmul as _mm
         x2, w = pend[1], pend[2]
+        if pend[0] == "lin":
+            if pend[3].ptr is not None:
+                return None                         # already computed (a sibling's grouped launch): plain add
+            pend[3].leave()                         # this product is absorbed here, not by a sibling's grouped launch
         return _mm.radd_matmul(x2, w, False, pend[0] == "lin", r.reshape((x2.metadata.shape[0], -1)))
     if pend[0] == "rms_dx":
         g, w, t = pend[1], pend[2], pend[3]

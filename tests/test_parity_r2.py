@@ -120,6 +120,74 @@ def test_bench_linear_shapes_vs_float64(rows, in_f, out_f, bias):
         runner.rel_check(check, Bt.grad.numpy(), _f64(g).sum(0, keepdims=True), 1e-5, "linear db")
 
 
+@pytest.mark.parametrize("B", [8, 2])
+def test_sibling_projections_run_as_grouped_launches(B):
+    """The q / k / v projections of an attention block (examples/gpt.py:43-45: three Linear layers on the same normed x,
+    each followed by the head split) at the C5 sizes.  Forward: ONE grouped launch [x @ Wq^T, x @ Wk^T, x @ Wv^T]
+    (matmul_tc_ts group ("n", 3): 7.8 tile waves instead of 3 x 2.6) — every output BIT-IDENTICAL to the single launch it
+    replaces and within the componentwise 1e-4 bound of float64.  Backward: the three input gradients meet in the
+    autograd driver's `grad + g` and run as ONE K-concatenated launch dq @ Wq + dk @ Wk + dv @ Wv (group ("k", 3)),
+    checked against float64 with the bound of the concatenated dot product; the weight gradients are unchanged GEMMs."""
+    from dlgrad_b200 import Tensor
+    from dlgrad_b200.runtime.cuda import profile
+    T, C, H = 1024, 768, 12
+    rows = B * T
+    rng = np.random.default_rng(40 + B)
+    x = (rng.random((B, T, C), dtype=np.float32) - 0.5).astype(np.float32)
+    w = [((rng.random((C, C), dtype=np.float32) - 0.5) * 0.1).astype(np.float32) for _ in range(3)]
+    g = [(rng.random((B, H, T, C // H), dtype=np.float32) - 0.5).astype(np.float32) for _ in range(3)]
+    X = Tensor(x.copy(), device="cuda", requires_grad=True)
+    W = [Tensor(a.copy(), device="cuda", requires_grad=True) for a in w]
+    if not COMPILE_ONLY:
+        profile.matmul_timer = profile.KernelTimer()
+    heads = [X.linear(Wi, None).reshape((B, T, H, C // H)).transpose(1, 2) for Wi in W]      # (B, h, T, d), like the script
+    loss = None
+    for hd, gi in zip(heads, g):
+        term = (hd * Tensor(gi.copy(), device="cuda")).sum()
+        loss = term if loss is None else loss + term
+    loss.backward()
+    outs = [hd.numpy() for hd in heads]
+    dx = X.grad.numpy()                                   # the deferred sum of the three input gradients runs here
+    if not COMPILE_ONLY:
+        tags = [t[0] for t in profile.matmul_timer.collect()["by_tag"]]
+        profile.matmul_timer = None
+        assert "tc3_group_n3" in tags and "tc3_group_k3" in tags, tags
+    profile.matmul_timer = None
+    x2 = x.reshape(rows, C)
+    g2 = [gi.transpose(0, 2, 1, 3).reshape(rows, C) for gi in g]          # gradient of each projection output, (rows, C)
+    for i in range(3):
+        got = outs[i].transpose(0, 2, 1, 3).reshape(rows, C)
+        runner.gemm_check(check, got, x2, w[i].T, runner.TOL_MATMUL, f"grouped projection {i} forward (B={B})")
+        single = (Tensor(x.copy(), device="cuda").linear(Tensor(w[i].copy(), device="cuda"), None)).numpy().reshape(rows, C)
+        check(got, single, exact=True, what=f"grouped projection {i} is bit-identical to the single launch (B={B})")
+        runner.gemm_check(check, W[i].grad.numpy(), g2[i].T, x2, runner.TOL_MATMUL, f"grouped projection {i} dW (B={B})")
+    runner.gemm_check(check, dx.reshape(rows, C), np.concatenate(g2, axis=1), np.concatenate(w, axis=0),
+                      runner.TOL_MATMUL, f"K-concatenated input gradient dq Wq + dk Wk + dv Wv (B={B})")
+
+
+def test_grouped_launches_are_optional_and_change_no_values(monkeypatch):
+    """DLGRAD_GROUP_LINEAR=0 (three launches + two add epilogues) and the grouped launches give the same forward bits and
+    input gradients within 1e-5 of the largest magnitude (one accumulator instead of three rounded products; measured 4.5e-6)."""
+    from dlgrad_b200 import Tensor
+    from dlgrad_b200.runtime.cuda import matmul as mm
+    B, T, C, H = 2, 1024, 768, 12
+    rng = np.random.default_rng(77)
+    x = (rng.random((B, T, C), dtype=np.float32) - 0.5).astype(np.float32)
+    w = [((rng.random((C, C), dtype=np.float32) - 0.5) * 0.1).astype(np.float32) for _ in range(3)]
+    res = {}
+    for grouped in (True, False):
+        monkeypatch.setattr(mm, "GROUP_LINEAR", grouped)
+        X = Tensor(x.copy(), device="cuda", requires_grad=True)
+        W = [Tensor(a.copy(), device="cuda", requires_grad=True) for a in w]
+        q, k, v = [X.linear(Wi, None).reshape((B, T, H, C // H)).transpose(1, 2) for Wi in W]
+        ((q * k).sum() + (v * v).sum()).backward()
+        res[grouped] = (q.numpy(), v.numpy(), X.grad.numpy(), W[1].grad.numpy())
+    check(res[True][0], res[False][0], exact=True, what="q: grouped vs single launches")
+    check(res[True][1], res[False][1], exact=True, what="v: grouped vs single launches")
+    check(res[True][3], res[False][3], exact=True, what="dWk: grouped vs single launches")
+    runner.rel_check(check, res[True][2], res[False][2], 1e-5, "dx: one K-concatenated launch vs three launches with add epilogues")
+
+
 def test_bench_mlp_block_shapes_vs_float64():
     """(b) c_fc -> relu -> c_proj at the C5 sizes (8192 tokens, 768 -> 3072 -> 768): forward GEMMs 8192 x 3072 x 768 and
     8192 x 768 x 3072 (A operand = deferred relu), backward dH = g @ W2 with the relu-mask epilogue, dW2 = g^T @ relu(h)
