@@ -57,7 +57,7 @@ def load_traffic():
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant matmul shape, from the committed
     `ncu --set full` capture (profiles/r02_ncu_mm_traffic.json); null when no capture is committed."""
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_ncu_mm_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r02_ncu_mm_traffic.json")) as f:
             return json.load(f)
     except (OSError, ValueError):
         return None
