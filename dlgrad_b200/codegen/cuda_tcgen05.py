@@ -781,6 +781,11 @@ def matmul_tc_ts(M: int, N: int, K: int, batch: int, a_mn: bool, b_mn: bool, a_b
     block (examples/gpt.py:43-45: three Linear layers applied to the same normed x) — as ONE persistent launch: called with
     batch = G and a_bcast, the batch index z of a tile selects one of G B tensor maps and one of G C tensor maps (separate
     allocations, nothing is copied or concatenated), so three launches of 2.59 tile waves each become one of 7.8.
+    group = ("m", G) (with splitk = S): G split-K weight gradients  dW_g = dY_g^T @ x  that share the B operand x — called
+    with batch = G x S work items: the batch index selects member g's A tensor map and the K slice, the partial sums go to
+    one scratch [G x S][M][N], and the slice that finishes a member's output tile LAST adds that member's S partials in
+    slice order and writes member g's own output (`bias`, `fin1`, `fin2`).  Three single-wave launches whose prologue and
+    finish are a third of their time become one persistent launch of 2.9 waves.
     group = ("k", G): the sum of G products  C = sum_g A_g @ B_g  — the input gradient of those three layers,
     dq @ Wq + dk @ Wk + dv @ Wv — as ONE launch with the k loop running through the G operand pairs (K = G x K_g): the
     k-block index selects the A and B tensor maps, the accumulator in tensor memory carries the sum, and the two ADD passes
@@ -805,11 +810,14 @@ def matmul_tc_ts(M: int, N: int, K: int, batch: int, a_mn: bool, b_mn: bool, a_b
     kblocks = _cdiv(K, BK)
     gmode, G = group if group else (None, 1)
     if gmode:
-        assert 2 <= G <= 3 and not (streamk or ksparse or splitk or relu_mask or hsplit or bias), group
+        assert 2 <= G <= 3 and not (streamk or ksparse or relu_mask or hsplit or bias), group
         if gmode == "n":
-            assert batch == G and a_bcast and not b_bcast and not radd
+            assert batch == G and a_bcast and not b_bcast and not radd and not splitk
+        elif gmode == "m":
+            # G split-K weight gradients  C_g = A_g^T-slices @ B-slices  that share the B operand (x): batch = G x S work items
+            assert splitk > 1 and batch == G * splitk and not radd and not a_bcast and not b_bcast
         else:
-            assert gmode == "k" and batch == 1 and K % (G * BK) == 0
+            assert gmode == "k" and batch == 1 and K % (G * BK) == 0 and not splitk
     kbg = kblocks // G if gmode == "k" else kblocks           # k-blocks per operand pair
 
     def sel(name, idx):
@@ -898,6 +906,15 @@ def matmul_tc_ts(M: int, N: int, K: int, batch: int, a_mn: bool, b_mn: bool, a_b
     def tma_issue(which, boxes, mn, tile_var, row0):
         tm = f"tm{which}"
         z = "0" if (a_bcast if which == "A" else b_bcast) else "z"
+        if gmode == "m":
+            # grouped split-K: the batch index z = g * S + slice; A comes from member g's map, B (shared) from the one map,
+            # both at batch coordinate `slice`
+            tmp = "tmAg" if which == "A" else "&tmB"
+            if mn:
+                return "\n                    ".join(
+                    f"tma_load_3d({tile_var} + {j * 4096}u, {tmp}, full_bar, (int)({row0} + {j * 32}u), (int)k0, (int)sl);"
+                    for j in range(boxes))
+            return f"tma_load_3d({tile_var}, {tmp}, full_bar, (int)k0, (int){row0}, (int)sl);"
         if (gmode == "n" and which == "B") or gmode == "k":
             # grouped launch: the map was selected by the tile's batch index ("n") or the k-block's operand pair ("k")
             tmp = f"tm{which}g"
@@ -1031,12 +1048,12 @@ def matmul_tc_ts(M: int, N: int, K: int, batch: int, a_mn: bool, b_mn: bool, a_b
                 asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(flag), "r"(1u) : "memory");
             }"""
     elif splitk > 1:
-        assert nchunks == 1 and not bias and batch == splitk and N % 4 == 0
+        assert nchunks == 1 and not bias and batch == (G if gmode == "m" else 1) * splitk and N % 4 == 0
         # rows of the quarter handled per pass: all R x S partial vectors are requested before the first add, so a
         # lane has ~16 independent 16-byte loads in flight (one row at a time is a chain of 32 L2 round trips, ~20 us)
         R = max(1, min(8, 16 // splitk))
         loads = "\n                            ".join(
-            f"v[rr][{sl}] = ok ? __ldcg(reinterpret_cast<const float4*>(C + ((size_t){sl} * {M}u + row) * {N}u + col)) : z4;"
+            f"v[rr][{sl}] = ok ? __ldcg(reinterpret_cast<const float4*>(C + ((size_t)(gz + {sl}u) * {M}u + row) * {N}u + col)) : z4;"
             for sl in range(splitk))
         adds = " ".join(
             f"acc.x += v[rr][{sl}].x; acc.y += v[rr][{sl}].y; acc.z += v[rr][{sl}].z; acc.w += v[rr][{sl}].w;"
@@ -1046,7 +1063,8 @@ def matmul_tc_ts(M: int, N: int, K: int, batch: int, a_mn: bool, b_mn: bool, a_b
                 // split-K: whichever slice finishes this quarter of the output tile LAST adds the {splitk} partial sums, in
                 // slice order, and writes the result; the counter re-arms itself for the next launch
                 unsigned last = 0u;
-                unsigned* cnt = flags + rem * 4u + q;
+                {f"const unsigned g = z / {splitk}u, gz = g * {splitk}u;" if gmode == "m" else "const unsigned gz = 0u;"}
+                unsigned* cnt = flags + ({f"g * {ntm * ntn}u + " if gmode == "m" else ""}rem) * 4u + q;
                 if (lane == 0) {{
                     asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");      // this slice's partial has landed
                     asm volatile("fence.proxy.async;" ::: "memory");
@@ -1056,7 +1074,7 @@ def matmul_tc_ts(M: int, N: int, K: int, batch: int, a_mn: bool, b_mn: bool, a_b
                 last = __shfl_sync(0xffffffffu, last, 0);
                 if (last) {{
                     __threadfence();
-                    float* fin = const_cast<float*>(bias);
+                    float* fin = {("(g == 0u ? const_cast<float*>(bias) : " + ("fin1)" if G == 2 else "(g == 1u ? fin1 : fin2))")) if gmode == "m" else "const_cast<float*>(bias)"};
                     const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
                     for (unsigned cv = lane; cv < {BN // 4}u; cv += 32u) {{
                         const unsigned col = n0 + cv * 4u;
@@ -1118,11 +1136,15 @@ def matmul_tc_ts(M: int, N: int, K: int, batch: int, a_mn: bool, b_mn: bool, a_b
         f"make_float4(__uint_as_float(v[{4 * j}]), __uint_as_float(v[{4 * j + 1}]), __uint_as_float(v[{4 * j + 2}]), __uint_as_float(v[{4 * j + 3}]));"
         for j in range(8))
 
-    extra = [f"tmB{g}" for g in range(1, G)] + [f"tm{'C' if gmode == 'n' else 'A'}{g}" for g in range(1, G)] if gmode else []
+    if gmode == "m":
+        extra = [f"tmA{g}" for g in range(1, G)]
+    else:
+        extra = [f"tmB{g}" for g in range(1, G)] + [f"tm{'C' if gmode == 'n' else 'A'}{g}" for g in range(1, G)] if gmode else []
     gparams = "".join(f"const __grid_constant__ TMap {n}, " for n in extra)
+    gtail = "".join(f", float* __restrict__ fin{g}" for g in range(1, G)) if gmode == "m" else ""
     src = _HELPERS + _HELPERS_TS + f"""
 extern "C" __global__ void __launch_bounds__({nthreads}, 1)
-{KNAME}(const __grid_constant__ TMap tmA, const __grid_constant__ TMap tmB, const __grid_constant__ TMap tmC, {gparams}float* __restrict__ C, const float* __restrict__ bias, unsigned* __restrict__ flags)
+{KNAME}(const __grid_constant__ TMap tmA, const __grid_constant__ TMap tmB, const __grid_constant__ TMap tmC, {gparams}float* __restrict__ C, const float* __restrict__ bias, unsigned* __restrict__ flags{gtail})
 {{
     extern __shared__ unsigned char smem_raw[];
     const unsigned smem = (smem_u32(smem_raw) + 1023u) & ~1023u;        // swizzle atoms need 1024-byte alignment
@@ -1175,6 +1197,7 @@ extern "C" __global__ void __launch_bounds__({nthreads}, 1)
                     const unsigned a_s = smem + s * {per_stage}u, b_s = a_s + {a_tile}u;
                     {f"const unsigned kg = kb / {kbg}u, k0 = (kb - kg * {kbg}u) * {BK}u; const TMap* tmAg = {sel('A', 'kg')}; const TMap* tmBg = {sel('B', 'kg')};" if gmode == "k" else f"const unsigned k0 = kb * {BK}u;"}
                     {f"const TMap* tmBg = {sel('B', 'z')};" if gmode == "n" else ""}
+                    {f"const unsigned g = z / {splitk}u, sl = z - g * {splitk}u; const TMap* tmAg = {sel('A', 'g')};" if gmode == "m" else ""}
                     if (elect_one()) {{
                         mbar_expect_tx(full_bar, {a_tile + b_tile}u);
                         {tma_issue("A", a_boxes, a_mn, "a_s", "m0")}

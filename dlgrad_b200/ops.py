@@ -514,9 +514,10 @@ class Linear(OP):
                 gx = Buffer(dispatcher.dispatch(op=BinaryOps.MATMUL, device=Device.CUDA, x=g2, y=self.w),
                             self.x.shape, Device.CUDA, self.x.dtype)
         if self.req_grad[1]:
-            gw = Buffer(dispatcher.dispatch(op=BinaryOps.MATMUL, device=Device.CUDA, x=g2,
-                                            y=self.x.reshape((rows, in_f)), trans_x=True),
-                        (out_f, in_f), Device.CUDA, self.w.dtype)
+            # dW = g^T @ x; the weight gradients of sibling layers (dWq, dWk, dWv: same x, split-K shapes) run as one grouped
+            # launch (runtime/cuda/matmul.lin_dw)
+            from dlgrad_b200.runtime.cuda import matmul as _mm
+            gw = _mm.lin_dw(g2, self.x.reshape((rows, in_f)), out_f, in_f, self.w.dtype)
         if self.b is not None and self.req_grad[2]:
             gb = g2.sum(0, keepdim=True).reshape(self.b.shape)
         return (gx, gw, gb) if self.b is not None else (gx, gw)

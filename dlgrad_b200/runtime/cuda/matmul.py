@@ -428,3 +428,89 @@ def run_lin_dx_sum(gs: tuple, ws: tuple):
             nxt = _ops.add(acc, Buffer(run_matmul(g, w), acc.metadata.shape, acc.metadata.device))
         acc = Buffer(nxt, acc.metadata.shape, acc.metadata.device)
     return acc.ptr
+
+
+# ---------------------------------------------------------------------------------------------------------
+# weight gradients of sibling Linear layers: one grouped split-K launch
+# ---------------------------------------------------------------------------------------------------------
+class DwSlot:
+    """Result cell of one deferred Linear weight gradient g2^T @ x2 (Buffer pending kind "lin_dw").  Slots of consecutive
+    Linear.backward calls over the SAME stored input with equally shaped gradients form a group (dWq, dWk, dWv); a group
+    runs as soon as it is complete (three members), when a Linear over another input follows, or when a member is read —
+    as ONE grouped split-K launch when two or three members are open.  The slot hands the result to its Buffer at once, so
+    the gradient operands (25 MB each at the benchmark's size) are released as early as without the deferral."""
+    __slots__ = ("ptr", "g2", "x2", "buf")
+
+    def __init__(self, g2: Buffer, x2: Buffer) -> None:
+        self.ptr, self.g2, self.x2, self.buf = None, g2, x2, None
+
+
+_open_dw: list = []
+
+
+def lin_dw(g2: Buffer, x2: Buffer, out_f: int, in_f: int, dtype) -> Buffer:
+    """dW = g2^T @ x2 of a Linear layer as a Buffer: deferred into the open group when the shape is a split-K weight gradient
+    that may get siblings, computed at once otherwise."""
+    global _open_dw
+    rows = g2.metadata.shape[0]
+    groupable = (GROUP_LINEAR and not FORCE_SIMT and g2._pending is None and x2._pending is None and g2._ptr is not None
+                 and x2._ptr is not None and g2.aligned and x2.aligned and _split_k(out_f, in_f, rows, (1, 1), True, False) > 1)
+    if _open_dw and not (groupable and len(_open_dw) < 3 and _open_dw[0].x2._ptr is x2._ptr
+                         and _open_dw[0].g2.metadata.shape == g2.metadata.shape and all(m.ptr is None for m in _open_dw)):
+        flush_dw()
+    if not groupable:
+        return Buffer(run_matmul(g2, x2, trans_x=True), (out_f, in_f), g2.metadata.device, dtype)
+    slot = DwSlot(g2, x2)
+    out = Buffer._deferred(("lin_dw", g2, x2, slot), (out_f, in_f), dtype)
+    slot.buf = weakref.ref(out)
+    _open_dw.append(slot)
+    if len(_open_dw) == 3:
+        flush_dw()
+    return out
+
+
+def flush_dw() -> None:
+    """Run the open group of deferred weight gradients."""
+    global _open_dw
+    todo, _open_dw = [m for m in _open_dw if m.ptr is None], []
+    if not todo:
+        return
+    outs = _grouped_dw([m.g2 for m in todo], todo[0].x2) if len(todo) >= 2 else None
+    for i, m in enumerate(todo):
+        m.ptr = outs[i] if outs is not None else run_matmul(m.g2, m.x2, trans_x=True)
+        m.g2 = m.x2 = None
+        b = m.buf() if m.buf is not None else None
+        if b is not None and b._pending is not None and b._pending[0] == "lin_dw":
+            b.ptr = m.ptr
+
+
+def run_dw_slot(slot: DwSlot):
+    if slot.ptr is None:
+        if any(m is slot for m in _open_dw):
+            flush_dw()
+        else:
+            slot.ptr = run_matmul(slot.g2, slot.x2, trans_x=True)
+            slot.g2 = slot.x2 = None
+    return slot.ptr
+
+
+def _grouped_dw(gs: list, x2: Buffer):
+    G = len(gs)
+    rows, M = gs[0].metadata.shape
+    N = x2.metadata.shape[1]
+    key = (gs[0].metadata.shape, x2.metadata.shape, G, "group_m")
+    plan = _plans.get(key)
+    if plan is None and key not in _plans:
+        from dlgrad_b200.runtime.cuda import matmul_tc
+        S = _split_k(M, N, rows, (1, 1), True, False)
+        plan = _plans[key] = matmul_tc.build_grouped("m", G, M, N, rows, True, True, radd=S) if S > 1 else None
+    if plan is None:
+        return None
+    args = ([_ops._dev_ptr(g) for g in gs], _ops._dev_ptr(x2))
+    timer = _profile.matmul_timer
+    if timer is None:
+        return plan(*args)
+    t0 = timer.start()
+    out = plan(*args)
+    timer.stop(t0, plan.flops, plan.tag)
+    return out

@@ -138,12 +138,16 @@ def build_grouped(mode: str, G: int, M: int, N: int, K: int, a_mn: bool, b_mn: b
     """Plans for the grouped forms of matmul_tc_ts (separate tensor maps per member, nothing is concatenated):
     mode "n": [A @ B_g for g < G] (K = the shared inner size) -> run(a, [b_g]) returns G output pointers;
     mode "k": sum_g A_g @ B_g (K = inner size of ONE pair)      -> run([a_g], [b_g], r=None) returns one pointer
-    (`radd`: + r in the epilogue).  None when the tensor-core path is disabled or the shape does not qualify."""
+    (`radd`: + r in the epilogue);
+    mode "m": [A_g^T @ B for g < G] as split-K (`radd` carries the number of K slices S; A_g stored [K][M], B stored
+    [K][N], K = the full inner size)                             -> run([a_g], b) returns G output pointers.  None when the tensor-core path is disabled or the shape does not qualify."""
     if not ENABLED or PASSES != 3 or KERNEL not in ("auto", "v4"):
         return None
     if (M if a_mn else K) % 4 or (N if b_mn else K) % 4 or N % 4 or K < 8 or N < 8 or M < 128:
         return None
     from dlgrad_b200.runtime.cuda.attention import _tc_plan, _tc_run
+    if mode == "m":
+        return _build_grouped_splitk(G, M, N, K, radd)
     if mode == "n":
         k = tc.matmul_tc_ts(M, N, K, G, a_mn, b_mn, True, False, group=("n", G))
         da, db, dc = tc.tmap_descs(M, N, K, 1, a_mn, b_mn, False, False, k.bn)
@@ -173,3 +177,27 @@ def build_grouped(mode: str, G: int, M: int, N: int, K: int, a_mn: bool, b_mn: b
             return out
     from dlgrad_b200.runtime.cuda.matmul import MatmulPlan
     return MatmulPlan(run, 2.0 * G * M * N * K, (f"tc{PASSES}_group_{mode}{G}" + ("_radd" if radd else ""), M, N, K, G))
+
+
+def _build_grouped_splitk(G: int, M: int, N: int, K: int, S: int):
+    """G weight gradients dW_g = A_g^T @ B over the same B (x) as ONE split-K launch of G x S work items per output tile
+    (matmul_tc_ts group ("m", G)); S slices of K / S each."""
+    from dlgrad_b200.runtime.cuda.attention import _tc_plan, _tc_run
+    ks = K // S
+    if S < 2 or K % S or ks > 2048 or ks % tc.BK or M % 4 or N % 4:
+        return None
+    k = tc.matmul_tc_ts(M, N, ks, G * S, True, True, False, False, bn=128 if N >= 128 else None, splitk=S, group=("m", G))
+    da, db, _ = tc.tmap_descs(M, N, ks, S, True, True, False, False, k.bn)
+    dc = dict(rank=3, dims=(N, M, G * S), strides=(N * 4, M * N * 4), box=(32, 32, 1), swizzle=3)
+    shim.init()
+    plan = _tc_plan(k, [da, db, dc] + [da] * (G - 1), 3 + (G - 1))
+    counters = shim.calloc(G * -(-M // 128) * -(-N // k.bn) * 16)
+    nbytes, scratch_bytes = M * N * 4, G * S * M * N * 4
+
+    def run(as_, b):
+        finals = [shim.alloc(nbytes) for _ in range(G)]
+        scratch = shim.alloc(scratch_bytes)            # freed on return: whoever gets the block next runs after this launch
+        _tc_run(plan, [as_[0], b, scratch] + list(as_[1:]), [scratch, finals[0], counters] + finals[1:], f"grouped split-K ({G} x {S})")
+        return finals
+    from dlgrad_b200.runtime.cuda.matmul import MatmulPlan
+    return MatmulPlan(run, 2.0 * G * M * N * K, (f"tc{PASSES}_splitk_group{G}", M, N, K, S))

@@ -201,6 +201,10 @@ def materialize(buf: Buffer) -> None:
     if pend[0] == "lin_dx":
         buf.ptr = matmul(pend[1], pend[2])
         return
+    if pend[0] == "lin_dw":
+        from dlgrad_b200.runtime.cuda import matmul as _mm
+        buf.ptr = _mm.run_dw_slot(pend[3])
+        return
     if pend[0] == "lin_dx_sum":
         from dlgrad_b200.runtime.cuda import matmul as _mm
         buf.ptr = _mm.run_lin_dx_sum(pend[1::2], pend[2::2])

@@ -127,7 +127,9 @@ def test_sibling_projections_run_as_grouped_launches(B):
     (matmul_tc_ts group ("n", 3): 7.8 tile waves instead of 3 x 2.6) — every output BIT-IDENTICAL to the single launch it
     replaces and within the componentwise 1e-4 bound of float64.  Backward: the three input gradients meet in the
     autograd driver's `grad + g` and run as ONE K-concatenated launch dq @ Wq + dk @ Wk + dv @ Wv (group ("k", 3)),
-    checked against float64 with the bound of the concatenated dot product; the weight gradients are unchanged GEMMs."""
+    checked against float64 with the bound of the concatenated dot product; the three weight gradients dW_g = dY_g^T @ x
+    run as ONE grouped split-K launch (group ("m", 3): 3 x 4 K-slices per output tile, each member's partial sums added in
+    slice order by the slice that finishes last) — bit-identical to the single split-K launches."""
     from dlgrad_b200 import Tensor
     from dlgrad_b200.runtime.cuda import profile
     T, C, H = 1024, 768, 12
@@ -151,7 +153,7 @@ def test_sibling_projections_run_as_grouped_launches(B):
     if not COMPILE_ONLY:
         tags = [t[0] for t in profile.matmul_timer.collect()["by_tag"]]
         profile.matmul_timer = None
-        assert "tc3_group_n3" in tags and "tc3_group_k3" in tags, tags
+        assert "tc3_group_n3" in tags and "tc3_group_k3" in tags and "tc3_splitk_group3" in tags, tags
     profile.matmul_timer = None
     x2 = x.reshape(rows, C)
     g2 = [gi.transpose(0, 2, 1, 3).reshape(rows, C) for gi in g]          # gradient of each projection output, (rows, C)
