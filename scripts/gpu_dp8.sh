@@ -14,4 +14,4 @@ run mono DLGRAD_DP_OVERLAP=0 DLGRAD_BENCH_STEP_TIMES=1
 grep "rank 0.*region A per-step" gpurun_out/r02_dp${N}_mono.err
 run over DLGRAD_DP_OVERLAP=1 DLGRAD_BENCH_STEP_TIMES=1
 grep "rank 0.*region A per-step" gpurun_out/r02_dp${N}_over.err
-run mono_b DLGRAD_DP_OVERLAP=0
+
