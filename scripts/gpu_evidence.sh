@@ -11,7 +11,7 @@ if [ "$1" = "tests" ]; then
 fi
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $O/r02_smoke.txt 2>&1; echo "smoke exit $?"; tail -1 $O/r02_smoke.txt
 timeout 900 python bench.py --steps 20 --warmup 5 > $O/r02_bench_1gpu.json 2> $O/r02_bench_1gpu.err; echo "bench exit $?"
-timeout 500 python bench.py --impl reference --steps 2 --warmup 1 > $O/r02_bench_reference_arm.json 2> $O/r02_bench_reference_arm.err; echo "ref exit $?"
+[ "$2" = "quick" ] || { timeout 500 python bench.py --impl reference --steps 2 --warmup 1 > $O/r02_bench_reference_arm.json 2> $O/r02_bench_reference_arm.err; echo "ref exit $?"; }
 B="python bench.py --steps 10 --warmup 3 --no-ops --no-small --no-cpu"
 {
   echo "same-box ablations (bench.py --steps 10 --warmup 3, ms/step):"
@@ -24,8 +24,8 @@ timeout 300 python bench.py --profile > $O/r02_step_profile_events.txt 2>&1; ech
 S="python bench.py --steps 2 --warmup 1 --no-ops --no-small --no-cpu"
 timeout 300 $S > /dev/null 2>&1 && timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file $O/r02_ncu_launches.csv $S > $O/r02_ncu_launches.log 2>&1; echo "ncu list exit $?"
 # (the report is exported to CSV here and deleted: gpurun copies back at most 64 MiB)
-timeout 900 ncu --set full --clock-control none -k regex:"flash_|mm_tcts" -s 200 -c 48 -f -o /tmp/r02_ncu_full_step $S > $O/r02_ncu_full_step.log 2>&1; echo "ncu full exit $?"; tail -2 $O/r02_ncu_full_step.log
+timeout 900 ncu --set full --clock-control none -k regex:"flash_|mm_tcts" -s 190 -c 48 -f -o /tmp/r02_ncu_full_step $S > $O/r02_ncu_full_step.log 2>&1; echo "ncu full exit $?"; tail -2 $O/r02_ncu_full_step.log
 ncu -i /tmp/r02_ncu_full_step.ncu-rep --page raw --csv > $O/r02_ncu_full_step_raw.csv 2>/dev/null; ls -la $O/r02_ncu_full_step_raw.csv
 timeout 600 python scripts/small_configs.py > $O/r02_small_configs.jsonl 2> $O/r02_small_configs.err; echo "small exit $?"
-for m in fwd dv ds; do DLGRAD_FLASH_TRACE=$m timeout 120 python scripts/flash_trace.py > $O/r02_flash_trace_$m.txt 2>&1; done; echo traces done
+[ "$2" = "quick" ] || { for m in fwd dv ds; do DLGRAD_FLASH_TRACE=$m timeout 120 python scripts/flash_trace.py > $O/r02_flash_trace_$m.txt 2>&1; done; echo traces done; }
 ls -la $O | head -40
