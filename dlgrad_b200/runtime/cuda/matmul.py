@@ -453,7 +453,7 @@ def lin_dw(g2: Buffer, x2: Buffer, out_f: int, in_f: int, dtype) -> Buffer:
     that may get siblings, computed at once otherwise."""
     global _open_dw
     rows = g2.metadata.shape[0]
-    groupable = (GROUP_LINEAR and not FORCE_SIMT and g2._pending is None and x2._pending is None and g2._ptr is not None
+    groupable = (GROUP_LINEAR and rows >= 2048 and not FORCE_SIMT and g2._pending is None and x2._pending is None and g2._ptr is not None
                  and x2._ptr is not None and g2.aligned and x2.aligned and _split_k(out_f, in_f, rows, (1, 1), True, False) > 1)
     if _open_dw and not (groupable and len(_open_dw) < 3 and _open_dw[0].x2._ptr is x2._ptr
                          and _open_dw[0].g2.metadata.shape == g2.metadata.shape and all(m.ptr is None for m in _open_dw)):
