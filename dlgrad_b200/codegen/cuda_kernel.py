@@ -1674,9 +1674,9 @@ extern "C" __global__ void __launch_bounds__(32) {KNAME}{SIG_ALIAS} {{
 
 def dp_wait(timeout_s: float = 600.0) -> Kernel:
     """Fallback of dlg_comm_wait_geq32 for drivers without stream memory operations: one thread spins on counter word
-    `f0` of this rank's flag block (p0) until it reaches `f1` (both exact small integers in floats... the target is
-    passed as two 16-bit halves f1 | f2 << 16).  It holds an SM slot while a peer is late, which is why the stream
-    operation is preferred."""
+    `f0` of this rank's flag block (p0) until (int)(count - target) >= 0.  The kernel's scalar arguments are floats, so the
+    32-bit target travels as two exact 16-bit halves, f1 | f2 << 16.  The thread holds an SM slot while a peer is late —
+    which is why the stream operation is preferred — and traps after `timeout_s` (a dead peer must not hang the node)."""
     src = f"""
 extern "C" __global__ void __launch_bounds__(32) {KNAME}{SIG_ALIAS} {{
     if (threadIdx.x != 0u) return;
