@@ -6,7 +6,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from dlgrad_b200 import Tensor
 from dlgrad_b200.runtime.cuda import attention, profile, shim
 
-B, H, T, D = 8, 12, int(os.environ.get("T", "1024")), int(os.environ.get("D", "64"))
+B, H, T, D = int(os.environ.get("B", "8")), 12, int(os.environ.get("T", "1024")), int(os.environ.get("D", "64"))
 rng = np.random.default_rng(0)
 split = os.environ.get("LAYOUT", "split") == "split"          # q, k, v stored (B, T, h, D) like the projections produce them
 shape = (B, T, H, D) if split else (B, H, T, D)
