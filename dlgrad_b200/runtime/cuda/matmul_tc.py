@@ -156,7 +156,8 @@ def build_grouped(mode: str, G: int, M: int, N: int, K: int, a_mn: bool, b_mn: b
         if K % tc.BK:
             return None
         k = tc.matmul_tc_ts(M, N, G * K, 1, a_mn, b_mn, False, False, radd=radd, group=("k", G),
-                            bn=(int(os.environ.get("DLGRAD_RMASK_BN", "128")) if radd and N >= 128 else None))
+                            bn=(int(os.environ.get("DLGRAD_RMASK_BN", "128")) if radd and N >= 128
+                                else (int(os.environ["DLGRAD_GROUPK_BN"]) if "DLGRAD_GROUPK_BN" in os.environ else None)))
         da, db, dc = tc.tmap_descs(M, N, K, 1, a_mn, b_mn, False, False, k.bn)
         maps = [da, db, dc] + [db] * (G - 1) + [da] * (G - 1)
     shim.init()
